@@ -1,0 +1,137 @@
+/*
+ * wd_b200 -- C ABI of the B200-native WordDiffusion denoising hot path.
+ *
+ * The reference (aniketntnu/WordDiffusion) has no FFI / plugin layer: the seam of its hot path is the
+ * Python nn.Module handed to the sampling / training loops (reference train.py:403,424;
+ * regenerateFromtrain2.py:1172,1291).  This header is the boundary a binding for that seam talks to:
+ * plain pointers and sizes, no torch types, every function returns 0 on success and a negative code on
+ * failure (wd_last_error() gives the message), nothing throws.  All pointers are DEVICE pointers unless
+ * a parameter says "host".  `stream` is a cudaStream_t passed as void*.  Calls on one engine must be
+ * serialised by the caller; different engines may run concurrently on different streams.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef WD_B200_H
+#define WD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WD_OK 0
+#define WD_IGNORED 1 /* load_param: a parameter the reference forward never reads (attnc.*, *.to_kv, res.*, ...) */
+#define WD_ERR_INVALID (-1)
+#define WD_ERR_UNSUPPORTED (-2)
+#define WD_ERR_CUDA (-3)
+#define WD_ERR_STATE (-4)
+
+#define WD_VARIANT_UNET 0  /* unet.py UNetModel: both attentions of a block are cross-attention (unet.py:337-345) */
+#define WD_VARIANT_PHOSC 1 /* unetPhosc.py / unetPhosc2.py UNetModelPhosc: self-attn + cross-attn (unetPhosc.py:241-246) */
+
+#define WD_STEP_EPS_ONLY 0
+#define WD_STEP_DDPM 1
+#define WD_STEP_DDIM 2
+
+typedef struct wd_engine wd_engine;
+
+/* Mirrors the constructor arguments of UNetModel / UNetModelPhosc (unet.py:1126-1156, unetPhosc.py:781-811). */
+typedef struct wd_config {
+  int variant;
+  int in_channels;
+  int model_channels;
+  int out_channels;
+  int num_res_blocks;
+  int n_channel_mult;
+  int channel_mult[8];
+  int n_attention_resolutions;
+  int attention_resolutions[8];
+  int num_heads;         /* -1 if num_head_channels is used */
+  int num_head_channels; /* -1 if num_heads is used */
+  int transformer_depth;
+  int context_dim;
+  int vocab_size;
+  int num_classes; /* 0: no label embedding */
+  int max_seq_len;
+  int latent_h; /* 8  */
+  int latent_w; /* 32 */
+  int add_label_emb; /* unet.py:1578-1581: label_emb is skipped when args.imgConditioned == 1 */
+  int phosc_len;     /* number of PHOSC tokens concatenated to the context (769), 0 = none (unetPhosc.py:1120-1130) */
+} wd_config;
+
+const char* wd_last_error(void);
+int wd_version(void);
+
+/* ---- engine life cycle -------------------------------------------------------------------------------- */
+int wd_engine_create(const wd_config* cfg, wd_engine** out);
+void wd_engine_destroy(wd_engine* e);
+
+/* state_dict entry -> packed device weights.  `name` is the reference state_dict key
+ * (e.g. "input_blocks.1.0.in_layers.2.weight"); `src` is the fp32 device tensor, contiguous. */
+int wd_engine_load_param(wd_engine* e, const char* name, const float* src, const int64_t* shape, int ndim, void* stream);
+/* CharacterEncoder.positional_encoding (unet.py:876-882) is not in the state_dict: [max_seq_len, context_dim] fp32 */
+int wd_engine_set_pos_encoding(wd_engine* e, const float* pe, void* stream);
+/* call once after all load_param calls (sums fused biases); returns the number of parameters still missing */
+int wd_engine_finalize_params(wd_engine* e, void* stream);
+
+/* allocate activations for up to `batch` latents and build the launch plan */
+int wd_engine_reserve(wd_engine* e, int batch);
+size_t wd_engine_workspace_bytes(const wd_engine* e);
+size_t wd_engine_weight_bytes(const wd_engine* e);
+/* kernels launched by the most recent wd_unet_eval / wd_sampler_step / wd_encode_context call */
+int wd_engine_last_launch_count(const wd_engine* e);
+
+/* ---- the hot path ------------------------------------------------------------------------------------ */
+/* Time-invariant conditioning: CharacterEncoder (+PHOSC tokens) and the K/V projections of every
+ * cross-attention (unet.py:1626-1636,839-882,180-183 ; unetPhosc.py:1117-1130).
+ * ctx_tokens: int64 [B, L]; phosc: int32 [B, phosc_len] or NULL. */
+int wd_encode_context(wd_engine* e, int batch, const int64_t* ctx_tokens, int L, const int32_t* phosc, void* stream);
+
+/* One UNet evaluation: eps = UNetModel(x, timesteps, context, y) (unet.py:1499-1836 / unetPhosc.py:1068-1159),
+ * using the context encoded by the last wd_encode_context.  x, eps_out: fp32 NCHW [B,4,H,W].
+ * timesteps: int64 [B] device pointer, or NULL to use t_scalar for every row. y: int64 [B] (may be NULL if
+ * num_classes == 0 or add_label_emb == 0). */
+int wd_unet_eval(wd_engine* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                 float* eps_out, void* stream);
+
+/* UNet evaluation fused with the sampler update of Diffusion.sampling (train.py:221-236): x is updated in place.
+ * mode WD_STEP_DDPM: coef = {1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-alpha_hat_t), sqrt(beta_t), 0}
+ * mode WD_STEP_DDIM: coef = {1/sqrt(ah_t), sqrt(1-ah_t), sqrt(ah_prev), sqrt(1-ah_prev)}   (eta = 0)
+ * noise: fp32 NCHW [B,4,H,W] or NULL; when NULL and use_philox != 0 the kernel draws N(0,1) from Philox4x32-10 keyed by
+ * (seed, step_index, sample_offset + sample, element).  eps_out may be NULL. */
+int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scalar, const int64_t* y, int mode, const float* coef4_host,
+                    const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index,
+                    float* eps_out, void* stream);
+
+/* ---- single operators (used by the parity tests; same kernels as the engine) -------------------------- */
+/* GroupNorm32(+SiLU) (unet.py:429-431,592-596): x,out bf16 NHWC [B,HW,C] */
+int wd_op_groupnorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta, int B, int HW, int C,
+                    int groups, float eps, int silu, void* stream);
+/* nn.LayerNorm(C) (unet.py:314-316): bf16 [M,C] */
+int wd_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta, int M, int C, float eps,
+                    void* stream);
+/* out[M,N] = act(A[M,K] W[N,K]^T + bias + residual) on tcgen05; A,W,residual,out bf16 (out fp32 if out_f32).
+ * geglu: W rows are nn.Linear(K, N) of GEGLU.proj in packed (tile-permuted) order, out is [M, N/2]. */
+int wd_op_gemm(const void* a_bf16, const void* w_bf16, const float* bias, const void* residual_bf16, void* out, int M,
+               int N, int K, int act_silu, int geglu, int out_f32, void* stream);
+/* 3x3 conv, pad 1, stride 1|2, NHWC bf16, weights pre-packed [Cout, 9*Cin] by wd_op_pack_conv3x3 */
+int wd_op_conv3x3(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* rowbias, int rb_ld,
+                  const void* residual_bf16, void* out_bf16, int B, int H, int W, int Cin, int Cout, int stride, void* stream);
+int wd_op_pack_conv3x3(const float* w_oihw, void* dst_bf16, int Cout, int Cin, void* stream);
+/* fp32 [N,K] -> bf16 [N,K] (geglu_perm != 0 applies the GEGLU tile permutation used by wd_op_gemm) */
+int wd_op_pack_linear(const float* w, void* dst_bf16, int N, int K, int geglu_perm, void* stream);
+int wd_op_pack_vec_geglu(const float* v, float* dst, int N, void* stream);
+/* softmax(q k^T scale) v with a short key sequence L <= 16; q [B,Sq,C], k,v [B,L,C], out [B,Sq,C] bf16; C = heads*80 */
+int wd_op_attention_small(const void* q, const void* k, const void* v, void* out, float* probs, int B, int Sq, int L,
+                          int heads, float scale, void* stream);
+/* flash-style attention, any Skv; q [B,Sq,ldq], k,v [B,Skv,ldkv] (row strides in elements) */
+int wd_op_attention(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int Sq,
+                    int Skv, int heads, float scale, void* stream);
+int wd_op_gemm_block_n(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WD_B200_H */

@@ -1,0 +1,1455 @@
+// Host-side engine of the WordDiffusion hot path: builds the layer inventory from the constructor
+// arguments (same loops as reference unet.py:1248-1458 / unetPhosc.py:864-1040), repacks state_dict tensors
+// into the layouts the kernels want, owns the activation arena and the per-batch launch plan (TMA
+// descriptors are encoded once per plan), and exposes the C ABI of include/wd_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/wd_b200.h"
+#include "gemm_tc.cuh"
+#include "ops.cuh"
+
+using namespace wd;
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail(WD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" const char* wd_last_error(void) { return g_err.c_str(); }
+extern "C" int wd_version(void) { return 1; }
+extern "C" int wd_op_gemm_block_n(void) { return gemm_tc_block_n(); }
+
+// ----------------------------------------------------------------------------------------------
+// arena
+// ----------------------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t used = 0;
+  template <class T>
+  T* alloc(size_t n) {
+    const size_t bytes = (n * sizeof(T) + 1023) & ~size_t(1023);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// layer inventory
+// ----------------------------------------------------------------------------------------------
+struct GemmW {
+  bf16* w = nullptr;  // [N, K] bf16, K-major
+  float* bias = nullptr;
+  int N = 0, K = 0;
+};
+struct NormW {
+  float* g = nullptr;
+  float* b = nullptr;
+  int C = 0;
+};
+struct ResL {
+  int Cin = 0, Cout = 0;
+  NormW gn1, gn2;
+  GemmW conv1, conv2;  // conv2.K = 9*Cout (+ Cin when the 1x1 skip conv is fused along K)
+  bool skip_conv = false;
+  float* b_main = nullptr;  // out_layers.3.bias
+  float* b_skip = nullptr;  // skip_connection.bias
+  int emb_off = 0;          // column offset inside the fused emb_layers GEMM
+};
+struct TBlockL {
+  NormW ln1, ln2, ln3;
+  GemmW a1_q;   // unet: attn1.to_q ; phosc: fused [to_q; to_k; to_v] of the self-attention
+  GemmW a1_kv;  // unet only: [to_k; to_v] applied to the context
+  GemmW a1_out;
+  GemmW a2_q, a2_kv, a2_out;
+  GemmW ff_proj, ff_out;
+  int kv1 = -1, kv2 = -1;  // index of the per-trajectory K/V buffer
+};
+struct STL {
+  int C = 0, heads = 0, dh = 0;
+  NormW gn;
+  GemmW proj_in, proj_out;
+  std::vector<TBlockL> blocks;
+};
+struct SampL {
+  int C = 0;
+  GemmW conv;
+};
+enum LayerKind { L_CONVIN, L_RES, L_ST, L_DOWN, L_UP };
+struct Layer {
+  LayerKind kind;
+  int idx;
+};
+typedef std::vector<Layer> Block;
+
+enum SlotKind { S_VEC, S_CONV3, S_LIN, S_CONV_IN, S_CONV_OUT, S_F32 };
+struct Slot {
+  SlotKind kind;
+  void* dst;
+  int64_t numel;
+  int N, K;  // S_LIN: [N,K]; S_CONV3: Cout, Cin
+  int ldk, k_off, n_off, geglu_bn;
+  bool loaded;
+};
+
+// ----------------------------------------------------------------------------------------------
+// launch plan
+// ----------------------------------------------------------------------------------------------
+enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_CONV_OUT, OP_UPSAMPLE,
+              OP_EMBED, OP_LINF32, OP_WORDATTN };
+enum Patch { P_NONE = 0, P_Y = 1 };
+struct Op {
+  OpKind kind;
+  int patch = P_NONE;
+  GemmLaunch gemm;
+  GroupNormArgs gn;
+  int gn_B = 0, gn_nslab = 0;
+  struct { const bf16* x; bf16* out; const float* g; const float* b; int M, C; float eps; } ln;
+  AttnSmallArgs as;
+  AttnFlashArgs af;
+  struct { bf16* out; int B, dim; } temb;
+  struct { const float* w; const float* bias; bf16* out; int B, H, W, Cout; } cin;
+  struct { const bf16* h; const float* w; const float* bias; int B, H, W, C; } cout_;
+  struct { const bf16* x; bf16* out; int B, H, W, C; } up;
+  struct { int which; const float* E; int vocab; const float* pe; int add_pe; float* out; int B, L, D; } emb;
+  struct { const float* x; const float* W; const float* b; float* out; int M, N, K; } lin;
+  struct { const float* q; const float* k; const float* v; bf16* ctx; int B, L, D, Ltot, row_off; } wa;
+};
+
+struct Plan {
+  int B = 0, L = 0, Ltot = 0;
+  std::vector<Op> ctx_ops;
+  std::vector<Op> step_ops;
+  size_t bytes = 0;
+  bool context_valid = false;
+};
+
+struct Act {
+  bf16* p;
+  int C, H, W;
+};
+
+struct wd_engine {
+  wd_config cfg;
+  int time_dim = 0;
+  // weights
+  Arena warena;
+  char* wbase = nullptr;
+  size_t wbytes = 0;
+  std::unordered_map<std::string, Slot> slots;
+  std::vector<ResL> res;
+  std::vector<STL> st;
+  std::vector<SampL> samp;
+  std::vector<Block> input_blocks, output_blocks;
+  Block middle;
+  GemmW te0, te2, emb_all;
+  float* label_emb = nullptr;
+  float* conv_in_w = nullptr;
+  float* conv_in_b = nullptr;
+  NormW out_gn;
+  float* conv_out_w = nullptr;
+  float* conv_out_b = nullptr;
+  // context encoder (fp32)
+  float *we_E = nullptr, *we_qw = nullptr, *we_qb = nullptr, *we_kw = nullptr, *we_kb = nullptr, *we_vw = nullptr,
+        *we_vb = nullptr, *we_pe = nullptr;
+  bool pe_set = false;
+  int n_kv = 0;
+  std::vector<GemmW*> kv_weights;  // per K/V buffer: the fused [to_k; to_v] weight
+  // activations
+  char* abase = nullptr;
+  size_t acap = 0;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  Plan* cur = nullptr;
+  int last_launches = 0;
+};
+
+// ----------------------------------------------------------------------------------------------
+// model builder
+// ----------------------------------------------------------------------------------------------
+namespace {
+
+struct Builder {
+  wd_engine* e;
+  Arena& A;
+  bool dry;
+  int bn;
+
+  void slot(const std::string& name, SlotKind kind, void* dst, int64_t numel, int N = 0, int K = 0, int ldk = 0,
+            int k_off = 0, int n_off = 0, int geglu_bn = 0) {
+    if (dry) return;
+    Slot s{kind, dst, numel, N, K, ldk, k_off, n_off, geglu_bn, false};
+    e->slots[name] = s;
+  }
+  NormW norm(const std::string& pfx, int C) {
+    NormW n;
+    n.C = C;
+    n.g = A.alloc<float>(C);
+    n.b = A.alloc<float>(C);
+    slot(pfx + ".weight", S_VEC, n.g, C);
+    slot(pfx + ".bias", S_VEC, n.b, C);
+    return n;
+  }
+  // nn.Linear / 1x1 conv [N, K] (+ optional bias)
+  GemmW linear(const std::string& pfx, int N, int K, bool bias, int geglu_bn = 0) {
+    GemmW g;
+    g.N = N;
+    g.K = K;
+    g.w = A.alloc<bf16>(static_cast<size_t>(N) * K);
+    slot(pfx + ".weight", S_LIN, g.w, static_cast<int64_t>(N) * K, N, K, K, 0, 0, geglu_bn);
+    if (bias) {
+      g.bias = A.alloc<float>(N);
+      slot(pfx + ".bias", S_VEC, g.bias, N, N, 0, 0, 0, 0, geglu_bn);
+    }
+    return g;
+  }
+  GemmW conv3(const std::string& pfx, int Cout, int Cin, int extraK = 0) {
+    GemmW g;
+    g.N = Cout;
+    g.K = 9 * Cin + extraK;
+    g.w = A.alloc<bf16>(static_cast<size_t>(g.N) * g.K);
+    g.bias = A.alloc<float>(Cout);
+    slot(pfx + ".weight", S_CONV3, g.w, static_cast<int64_t>(Cout) * Cin * 9, Cout, Cin, g.K, 0);
+    return g;
+  }
+
+  int add_res(const std::string& pfx, int Cin, int Cout, int& emb_cols) {
+    ResL r;
+    r.Cin = Cin;
+    r.Cout = Cout;
+    r.gn1 = norm(pfx + "in_layers.0", Cin);
+    r.conv1 = conv3(pfx + "in_layers.2", Cout, Cin);
+    slot(pfx + "in_layers.2.bias", S_VEC, r.conv1.bias, Cout);
+    r.emb_off = emb_cols;
+    emb_cols += Cout;
+    r.gn2 = norm(pfx + "out_layers.0", Cout);
+    r.skip_conv = (Cin != Cout);
+    r.conv2 = conv3(pfx + "out_layers.3", Cout, Cout, r.skip_conv ? Cin : 0);
+    r.b_main = A.alloc<float>(Cout);
+    slot(pfx + "out_layers.3.bias", S_VEC, r.b_main, Cout);
+    if (r.skip_conv) {
+      r.b_skip = A.alloc<float>(Cout);
+      slot(pfx + "skip_connection.weight", S_LIN, r.conv2.w, static_cast<int64_t>(Cout) * Cin, Cout, Cin, r.conv2.K,
+           9 * Cout, 0, 0);
+      slot(pfx + "skip_connection.bias", S_VEC, r.b_skip, Cout);
+    }
+    e->res.push_back(r);
+    return static_cast<int>(e->res.size()) - 1;
+  }
+
+  // [to_k ; to_v] fused along N
+  GemmW kv_fused(const std::string& pfx, int inner, int ctx_dim) {
+    GemmW g;
+    g.N = 2 * inner;
+    g.K = ctx_dim;
+    g.w = A.alloc<bf16>(static_cast<size_t>(g.N) * g.K);
+    slot(pfx + ".to_k.weight", S_LIN, g.w, static_cast<int64_t>(inner) * ctx_dim, inner, ctx_dim, ctx_dim, 0, 0, 0);
+    slot(pfx + ".to_v.weight", S_LIN, g.w, static_cast<int64_t>(inner) * ctx_dim, inner, ctx_dim, ctx_dim, 0, inner, 0);
+    return g;
+  }
+
+  int add_st(const std::string& pfx, int C, int heads, int dh) {
+    STL s;
+    s.C = C;
+    s.heads = heads;
+    s.dh = dh;
+    const int inner = heads * dh;
+    const int ctx_dim = e->cfg.context_dim;
+    s.gn = norm(pfx + "norm", C);
+    s.proj_in = linear(pfx + "proj_in", inner, C, true);
+    for (int d = 0; d < e->cfg.transformer_depth; ++d) {
+      const std::string tp = pfx + "transformer_blocks." + std::to_string(d) + ".";
+      TBlockL t;
+      if (e->cfg.variant == WD_VARIANT_PHOSC) {
+        t.ln1 = norm(tp + "norm1", inner);
+        // self-attention: q, k, v all from the normalised tokens -> one N = 3*inner GEMM
+        t.a1_q.N = 3 * inner;
+        t.a1_q.K = inner;
+        t.a1_q.w = A.alloc<bf16>(static_cast<size_t>(3) * inner * inner);
+        slot(tp + "attn1.to_q.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, 0, 0);
+        slot(tp + "attn1.to_k.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, inner, 0);
+        slot(tp + "attn1.to_v.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, 2 * inner, 0);
+      } else {
+        // unet.py:337-341 -- attn1 is a cross-attention over the context; norm1 is never applied
+        t.a1_q = linear(tp + "attn1.to_q", inner, inner, false);
+        t.a1_kv = kv_fused(tp + "attn1", inner, ctx_dim);
+      }
+      t.a1_out = linear(tp + "attn1.to_out.0", inner, inner, true);
+      t.ln2 = norm(tp + "norm2", inner);
+      t.a2_q = linear(tp + "attn2.to_q", inner, inner, false);
+      t.a2_kv = kv_fused(tp + "attn2", inner, ctx_dim);
+      t.a2_out = linear(tp + "attn2.to_out.0", inner, inner, true);
+      t.ln3 = norm(tp + "norm3", inner);
+      t.ff_proj = linear(tp + "ff.net.0.proj", inner * 8, inner, true, bn);
+      t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
+      s.blocks.push_back(t);
+    }
+    s.proj_out = linear(pfx + "proj_out", C, inner, true);
+    e->st.push_back(s);
+    return static_cast<int>(e->st.size()) - 1;
+  }
+
+  int add_samp(const std::string& pfx, int C) {
+    SampL s;
+    s.C = C;
+    s.conv = conv3(pfx, C, C);
+    slot(pfx + ".bias", S_VEC, s.conv.bias, C);
+    e->samp.push_back(s);
+    return static_cast<int>(e->samp.size()) - 1;
+  }
+
+  bool in_attn_res(int ds) const {
+    for (int i = 0; i < e->cfg.n_attention_resolutions; ++i)
+      if (e->cfg.attention_resolutions[i] == ds) return true;
+    return false;
+  }
+  void heads_for(int ch, int& heads, int& dh) const {
+    if (e->cfg.num_head_channels == -1) {
+      heads = e->cfg.num_heads;
+      dh = ch / heads;
+    } else {
+      heads = ch / e->cfg.num_head_channels;
+      dh = e->cfg.num_head_channels;
+    }
+  }
+
+  void build() {
+    const wd_config& c = e->cfg;
+    const int mc = c.model_channels;
+    const int ted = mc * 4;
+    e->time_dim = ted;
+    e->res.clear();
+    e->st.clear();
+    e->samp.clear();
+    e->input_blocks.clear();
+    e->output_blocks.clear();
+    e->middle.clear();
+
+    e->te0 = linear("time_embed.0", ted, mc, true);
+    e->te2 = linear("time_embed.2", ted, ted, true);
+    // CharacterEncoder (fp32)
+    const int D = c.context_dim;
+    e->we_E = A.alloc<float>(static_cast<size_t>(c.vocab_size) * D);
+    slot("word_emb.embedding.weight", S_F32, e->we_E, static_cast<int64_t>(c.vocab_size) * D);
+    e->we_qw = A.alloc<float>(static_cast<size_t>(D) * D);
+    e->we_kw = A.alloc<float>(static_cast<size_t>(D) * D);
+    e->we_vw = A.alloc<float>(static_cast<size_t>(D) * D);
+    e->we_qb = A.alloc<float>(D);
+    e->we_kb = A.alloc<float>(D);
+    e->we_vb = A.alloc<float>(D);
+    e->we_pe = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
+    slot("word_emb.attention.linear_query.weight", S_F32, e->we_qw, static_cast<int64_t>(D) * D);
+    slot("word_emb.attention.linear_query.bias", S_F32, e->we_qb, D);
+    slot("word_emb.attention.linear_key.weight", S_F32, e->we_kw, static_cast<int64_t>(D) * D);
+    slot("word_emb.attention.linear_key.bias", S_F32, e->we_kb, D);
+    slot("word_emb.attention.linear_value.weight", S_F32, e->we_vw, static_cast<int64_t>(D) * D);
+    slot("word_emb.attention.linear_value.bias", S_F32, e->we_vb, D);
+    if (c.num_classes > 0) {
+      e->label_emb = A.alloc<float>(static_cast<size_t>(c.num_classes) * ted);
+      slot("label_emb.weight", S_F32, e->label_emb, static_cast<int64_t>(c.num_classes) * ted);
+    }
+    // input_blocks.0.0 : conv_in
+    e->conv_in_w = A.alloc<float>(static_cast<size_t>(36) * mc);
+    e->conv_in_b = A.alloc<float>(mc);
+    slot("input_blocks.0.0.weight", S_CONV_IN, e->conv_in_w, static_cast<int64_t>(mc) * c.in_channels * 9, mc, c.in_channels);
+    slot("input_blocks.0.0.bias", S_VEC, e->conv_in_b, mc);
+    e->input_blocks.push_back(Block{Layer{L_CONVIN, 0}});
+
+    int emb_cols = 0;
+    std::vector<int> chans{mc};
+    int ch = mc, ds = 1;
+    // unet.py:1258-1318
+    for (int level = 0; level < c.n_channel_mult; ++level) {
+      const int mult = c.channel_mult[level];
+      for (int i = 0; i < c.num_res_blocks; ++i) {
+        const std::string pfx = "input_blocks." + std::to_string(e->input_blocks.size()) + ".";
+        Block b;
+        b.push_back(Layer{L_RES, add_res(pfx + "0.", ch, mult * mc, emb_cols)});
+        ch = mult * mc;
+        if (in_attn_res(ds)) {
+          int heads, dh;
+          heads_for(ch, heads, dh);
+          b.push_back(Layer{L_ST, add_st(pfx + "1.", ch, heads, dh)});
+        }
+        e->input_blocks.push_back(b);
+        chans.push_back(ch);
+      }
+      if (level != c.n_channel_mult - 1) {
+        const std::string pfx = "input_blocks." + std::to_string(e->input_blocks.size()) + ".0.op";
+        e->input_blocks.push_back(Block{Layer{L_DOWN, add_samp(pfx, ch)}});
+        chans.push_back(ch);
+        ds *= 2;
+      }
+    }
+    // middle block, unet.py:1366-1394
+    {
+      int heads, dh;
+      heads_for(ch, heads, dh);
+      e->middle.push_back(Layer{L_RES, add_res("middle_block.0.", ch, ch, emb_cols)});
+      e->middle.push_back(Layer{L_ST, add_st("middle_block.1.", ch, heads, dh)});
+      e->middle.push_back(Layer{L_RES, add_res("middle_block.2.", ch, ch, emb_cols)});
+    }
+    // output blocks, unet.py:1398-1451
+    for (int level = c.n_channel_mult - 1; level >= 0; --level) {
+      const int mult = c.channel_mult[level];
+      for (int i = 0; i < c.num_res_blocks + 1; ++i) {
+        const int ich = chans.back();
+        chans.pop_back();
+        const std::string pfx = "output_blocks." + std::to_string(e->output_blocks.size()) + ".";
+        Block b;
+        int li = 0;
+        b.push_back(Layer{L_RES, add_res(pfx + std::to_string(li++) + ".", ch + ich, mc * mult, emb_cols)});
+        ch = mc * mult;
+        if (in_attn_res(ds)) {
+          int heads, dh;
+          heads_for(ch, heads, dh);
+          b.push_back(Layer{L_ST, add_st(pfx + std::to_string(li++) + ".", ch, heads, dh)});
+        }
+        if (level && i == c.num_res_blocks) {
+          b.push_back(Layer{L_UP, add_samp(pfx + std::to_string(li++) + ".conv", ch)});
+          ds /= 2;
+        }
+        e->output_blocks.push_back(b);
+      }
+    }
+    // out, unet.py:1454-1458
+    e->out_gn = norm("out.0", ch);
+    e->conv_out_w = A.alloc<float>(static_cast<size_t>(9) * ch * c.out_channels);
+    e->conv_out_b = A.alloc<float>(c.out_channels);
+    slot("out.2.weight", S_CONV_OUT, e->conv_out_w, static_cast<int64_t>(c.out_channels) * ch * 9, c.out_channels, ch);
+    slot("out.2.bias", S_VEC, e->conv_out_b, c.out_channels);
+
+    // fused emb_layers GEMM: [sum Cout, time_dim]
+    e->emb_all.N = emb_cols;
+    e->emb_all.K = ted;
+    e->emb_all.w = A.alloc<bf16>(static_cast<size_t>(emb_cols) * ted);
+    e->emb_all.bias = A.alloc<float>(emb_cols);
+    if (!dry) {
+      int ri = 0;
+      auto reg = [&](const std::string& pfx, const ResL& r) {
+        slot(pfx + "emb_layers.1.weight", S_LIN, e->emb_all.w, static_cast<int64_t>(r.Cout) * ted, r.Cout, ted, ted, 0,
+             r.emb_off, 0);
+        slot(pfx + "emb_layers.1.bias", S_VEC, e->emb_all.bias, r.Cout, r.Cout, 0, 0, 0, r.emb_off, 0);
+        ++ri;
+      };
+      for (size_t bi = 0; bi < e->input_blocks.size(); ++bi)
+        for (size_t li = 0; li < e->input_blocks[bi].size(); ++li)
+          if (e->input_blocks[bi][li].kind == L_RES)
+            reg("input_blocks." + std::to_string(bi) + "." + std::to_string(li) + ".", e->res[e->input_blocks[bi][li].idx]);
+      for (size_t li = 0; li < e->middle.size(); ++li)
+        if (e->middle[li].kind == L_RES) reg("middle_block." + std::to_string(li) + ".", e->res[e->middle[li].idx]);
+      for (size_t bi = 0; bi < e->output_blocks.size(); ++bi)
+        for (size_t li = 0; li < e->output_blocks[bi].size(); ++li)
+          if (e->output_blocks[bi][li].kind == L_RES)
+            reg("output_blocks." + std::to_string(bi) + "." + std::to_string(li) + ".", e->res[e->output_blocks[bi][li].idx]);
+    }
+    // K/V buffers of the cross-attentions (time-invariant)
+    e->n_kv = 0;
+    e->kv_weights.clear();
+    for (auto& s : e->st)
+      for (auto& t : s.blocks) {
+        if (c.variant == WD_VARIANT_UNET) {
+          t.kv1 = e->n_kv++;
+          e->kv_weights.push_back(&t.a1_kv);
+        }
+        t.kv2 = e->n_kv++;
+        e->kv_weights.push_back(&t.a2_kv);
+      }
+  }
+};
+
+bool is_dead_param(const std::string& n, int variant) {
+  // parameters that exist in the reference state_dict but are never read by its forward (SURVEY 8a, a8')
+  if (n.find(".attnc.") != std::string::npos) return true;
+  if (n.find(".to_kv.") != std::string::npos) return true;
+  if (n.rfind("res.", 0) == 0) return true;
+  if (n.rfind("wrd_proj.", 0) == 0) return true;
+  if (variant == WD_VARIANT_UNET && n.find(".norm1.") != std::string::npos) return true;
+  if (variant == WD_VARIANT_PHOSC) {
+    // the self-attention's to_k/to_v are used; nothing else is dead
+  }
+  return false;
+}
+
+int validate(const wd_config& c) {
+  const int bn = gemm_tc_block_n();
+  if (c.variant != WD_VARIANT_UNET && c.variant != WD_VARIANT_PHOSC) return fail(WD_ERR_INVALID, "bad variant");
+  if (c.in_channels != 4 || c.out_channels != 4) return fail(WD_ERR_UNSUPPORTED, "in/out channels must be 4");
+  if (c.model_channels % 64 || c.model_channels % bn)
+    return fail(WD_ERR_UNSUPPORTED, "model_channels must be a multiple of 64 and of the GEMM N tile (%d)", bn);
+  if (c.n_channel_mult < 1 || c.n_channel_mult > 8) return fail(WD_ERR_INVALID, "channel_mult length");
+  if (c.context_dim % 64) return fail(WD_ERR_UNSUPPORTED, "context_dim must be a multiple of 64");
+  if (c.num_heads == -1 && c.num_head_channels == -1) return fail(WD_ERR_INVALID, "num_heads or num_head_channels");
+  if (c.transformer_depth < 1) return fail(WD_ERR_INVALID, "transformer_depth");
+  if (c.latent_h < 1 || c.latent_w < 1) return fail(WD_ERR_INVALID, "latent size");
+  return WD_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// C ABI: life cycle and weights
+// ----------------------------------------------------------------------------------------------
+extern "C" int wd_engine_create(const wd_config* cfg, wd_engine** out) {
+  if (!cfg || !out) return fail(WD_ERR_INVALID, "null argument");
+  int rc = validate(*cfg);
+  if (rc) return rc;
+  int dev = 0, major = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(WD_ERR_UNSUPPORTED, "wd_b200 needs an sm_100a GPU (found compute capability %d.x)", major);
+  std::unique_ptr<wd_engine> e(new wd_engine());
+  e->cfg = *cfg;
+  {
+    Arena dryA;
+    Builder b{e.get(), dryA, true, gemm_tc_block_n()};
+    b.build();
+    e->wbytes = dryA.used;
+  }
+  CUDA_TRY(cudaMalloc(&e->wbase, e->wbytes));
+  CUDA_TRY(cudaMemset(e->wbase, 0, e->wbytes));
+  e->warena.base = e->wbase;
+  e->warena.used = 0;
+  Builder b{e.get(), e->warena, false, gemm_tc_block_n()};
+  b.build();
+  for (auto& s : e->st)
+    for (auto& t : s.blocks)
+      if (s.dh != 80) return fail(WD_ERR_UNSUPPORTED, "attention kernels are built for d_head = 80 (got %d)", s.dh);
+  *out = e.release();
+  return WD_OK;
+}
+
+extern "C" void wd_engine_destroy(wd_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  if (e->wbase) cudaFree(e->wbase);
+  if (e->abase) cudaFree(e->abase);
+  delete e;
+}
+
+extern "C" size_t wd_engine_weight_bytes(const wd_engine* e) { return e ? e->wbytes : 0; }
+extern "C" size_t wd_engine_workspace_bytes(const wd_engine* e) { return e ? e->acap : 0; }
+extern "C" int wd_engine_last_launch_count(const wd_engine* e) { return e ? e->last_launches : 0; }
+
+extern "C" int wd_engine_load_param(wd_engine* e, const char* name, const float* src, const int64_t* shape, int ndim,
+                                    void* stream) {
+  if (!e || !name || !src) return fail(WD_ERR_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto it = e->slots.find(name);
+  if (it == e->slots.end()) {
+    if (is_dead_param(name, e->cfg.variant)) return WD_IGNORED;
+    return fail(WD_ERR_INVALID, "unknown parameter '%s'", name);
+  }
+  Slot& sl = it->second;
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  if (numel != sl.numel) return fail(WD_ERR_INVALID, "parameter '%s': %lld elements, expected %lld", name, (long long)numel,
+                                     (long long)sl.numel);
+  switch (sl.kind) {
+    case S_VEC:
+      CUDA_TRY(repack_vec_launch(src, static_cast<float*>(sl.dst), static_cast<int>(numel), sl.n_off, sl.geglu_bn, 0, s));
+      break;
+    case S_F32:
+      CUDA_TRY(cudaMemcpyAsync(sl.dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      break;
+    case S_CONV3:
+      CUDA_TRY(repack_conv3x3_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, s));
+      break;
+    case S_LIN:
+      CUDA_TRY(repack_linear_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, sl.n_off, sl.geglu_bn, s));
+      break;
+    case S_CONV_IN:
+      CUDA_TRY(repack_conv_in_launch(src, static_cast<float*>(sl.dst), sl.N, sl.K, s));
+      break;
+    case S_CONV_OUT:
+      CUDA_TRY(repack_conv_out_launch(src, static_cast<float*>(sl.dst), sl.N, sl.K, s));
+      break;
+  }
+  sl.loaded = true;
+  return WD_OK;
+}
+
+extern "C" int wd_engine_set_pos_encoding(wd_engine* e, const float* pe, void* stream) {
+  if (!e || !pe) return fail(WD_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaMemcpyAsync(e->we_pe, pe, static_cast<size_t>(e->cfg.max_seq_len) * e->cfg.context_dim * sizeof(float),
+                           cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  e->pe_set = true;
+  return WD_OK;
+}
+
+extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
+  if (!e) return fail(WD_ERR_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int missing = 0;
+  std::string first;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      if (!missing) first = kv.first;
+      ++missing;
+    }
+  if (!e->pe_set) {
+    ++missing;
+    if (first.empty()) first = "<positional encoding>";
+  }
+  if (missing) {
+    fail(WD_ERR_STATE, "%d parameters not loaded (first: %s)", missing, first.c_str());
+    return missing;
+  }
+  for (auto& r : e->res) {
+    CUDA_TRY(repack_vec_launch(r.b_main, r.conv2.bias, r.Cout, 0, 0, 0, s));
+    if (r.skip_conv) CUDA_TRY(repack_vec_launch(r.b_skip, r.conv2.bias, r.Cout, 0, 0, 1, s));
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// plan builder
+// ----------------------------------------------------------------------------------------------
+namespace {
+
+struct ASrc {
+  const bf16* p;
+  int C;   // channels taken from this source
+  int ld;  // pixel / row stride in elements
+  int taps;
+  int stride;
+  int H, W;  // input spatial size (conv mode)
+};
+struct Epi {
+  const float* rowbias = nullptr;
+  int rb_ld = 0;
+  int rows_per_sample = 1;
+  const bf16* residual = nullptr;
+  int res_ld = 0;
+  void* out = nullptr;
+  int out_ld = 0;
+  int out_f32 = 0;
+  int act = 0;
+  int geglu = 0;
+};
+
+struct PlanBuilder {
+  wd_engine* e;
+  Plan* plan;
+  Arena A;
+  bool dry;
+  int B;
+  std::string err;
+
+  Act new_act(int H, int W, int C) { return Act{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W}; }
+
+  bool gemm_op(std::vector<Op>& ops, int M, bool conv, int Hout, int Wout, const std::vector<ASrc>& srcs, const GemmW& w,
+               const Epi& ep, int patch = P_NONE) {
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_GEMM;
+    op.patch = patch;
+    GemmArgs& a = op.gemm.args;
+    a.M = M;
+    a.N = w.N;
+    a.num_src = static_cast<int>(srcs.size());
+    a.conv = conv ? 1 : 0;
+    a.Wout = conv ? Wout : 1;
+    a.HWout = conv ? Hout * Wout : 1;
+    a.bias = w.bias;
+    a.rowbias = ep.rowbias;
+    a.rowbias_idx = nullptr;
+    a.rb_ld = ep.rb_ld;
+    a.rows_per_sample = ep.rows_per_sample;
+    a.residual = ep.residual;
+    a.res_ld = ep.res_ld;
+    a.out = ep.out;
+    a.out_ld = ep.out_ld;
+    a.out_f32 = ep.out_f32;
+    a.act = ep.act;
+    a.geglu = ep.geglu;
+    int ktot = 0;
+    if (srcs.empty() || srcs.size() > GEMM_MAX_SRC) { err = "gemm: bad source count"; return false; }
+    for (size_t i = 0; i < srcs.size(); ++i) {
+      const ASrc& s = srcs[i];
+      if (s.C % GEMM_BLOCK_K) { err = "gemm: source channels must be a multiple of 64"; return false; }
+      a.taps[i] = s.taps;
+      a.chunks[i] = s.C / GEMM_BLOCK_K;
+      a.stride[i] = s.stride;
+      ktot += s.taps * s.C;
+      if (dry) continue;
+      bool ok;
+      if (!conv) {
+        ok = tmap_encode_2d_bf16(&op.gemm.mapA[i], s.p, s.C, M, s.ld, GEMM_BLOCK_K, GEMM_BLOCK_M);
+      } else {
+        const int HWout = Hout * Wout;
+        uint32_t bw, bh, bnn;
+        if (HWout >= GEMM_BLOCK_M) {
+          if (HWout % GEMM_BLOCK_M || GEMM_BLOCK_M % Wout) { err = "conv: unsupported spatial size"; return false; }
+          bw = Wout * s.stride;
+          bh = (GEMM_BLOCK_M / Wout) * s.stride;
+          bnn = 1;
+        } else {
+          if (GEMM_BLOCK_M % HWout) { err = "conv: unsupported spatial size"; return false; }
+          bw = s.W;
+          bh = s.H;
+          bnn = GEMM_BLOCK_M / HWout;
+        }
+        if (bw > 256 || bh > 256 || bnn > 256) { err = "conv: TMA box too large"; return false; }
+        ok = tmap_encode_4d_bf16(&op.gemm.mapA[i], s.p, s.C, s.W, s.H, B, s.ld, GEMM_BLOCK_K, bw, bh, bnn, s.stride);
+      }
+      if (!ok) { err = "cuTensorMapEncodeTiled failed (A)"; return false; }
+    }
+    if (ktot != w.K) { err = "gemm: K mismatch between sources and weight"; return false; }
+    if (w.N % gemm_tc_block_n()) { err = "gemm: N must be a multiple of the N tile"; return false; }
+    if (!dry) {
+      for (size_t i = srcs.size(); i < GEMM_MAX_SRC; ++i) op.gemm.mapA[i] = op.gemm.mapA[0];
+      if (!tmap_encode_2d_bf16(&op.gemm.mapB, w.w, w.K, w.N, w.K, GEMM_BLOCK_K, gemm_tc_block_n())) {
+        err = "cuTensorMapEncodeTiled failed (B)";
+        return false;
+      }
+    }
+    ops.push_back(op);
+    return true;
+  }
+
+  // GroupNorm over the channel-concatenation of `srcs` -> one [B,HW,sumC] tensor
+  bool gn_op(std::vector<Op>& ops, const std::vector<Act>& srcs, const NormW& nw, float eps, int silu, Act& out) {
+    int totalC = 0;
+    for (auto& s : srcs) totalC += s.C;
+    if (totalC != nw.C || totalC % 32) { err = "groupnorm: channel mismatch"; return false; }
+    const int cpg = totalC / 32;
+    const int H = srcs[0].H, W = srcs[0].W, HW = H * W;
+    // slab size: whole groups, multiple of 8 channels, fits in shared memory
+    int Cs = srcs[0].C;
+    for (auto& s : srcs)
+      if (s.C != Cs) { err = "groupnorm: concat sources must have equal channels"; return false; }
+    auto fits = [&](int cs) { return static_cast<size_t>(HW) * cs * 2 + 8 * cs * 4 + cs * 4 + 1024 <= 200 * 1024; };
+    while (!fits(Cs)) {
+      if (Cs % 2 || (Cs / 2) % cpg || (Cs / 2) % 8) { err = "groupnorm: cannot tile channels into shared memory"; return false; }
+      Cs /= 2;
+    }
+    if (Cs % cpg || Cs % 8) { err = "groupnorm: slab does not hold whole groups"; return false; }
+    const int per_src = srcs[0].C / Cs;
+    const int nslab = per_src * static_cast<int>(srcs.size());
+    if (nslab > 8) { err = "groupnorm: too many slabs"; return false; }
+    out = new_act(H, W, totalC);
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_GN;
+    for (int i = 0; i < nslab; ++i) {
+      const Act& s = srcs[i / per_src];
+      op.gn.x[i] = s.p + (i % per_src) * Cs;
+      op.gn.x_ld[i] = s.C;
+    }
+    op.gn.out = out.p;
+    op.gn.out_ld = totalC;
+    op.gn.gamma = nw.g;
+    op.gn.beta = nw.b;
+    op.gn.HW = HW;
+    op.gn.Cs = Cs;
+    op.gn.cpg = cpg;
+    op.gn.eps = eps;
+    op.gn.silu = silu;
+    op.gn_B = B;
+    op.gn_nslab = nslab;
+    ops.push_back(op);
+    return true;
+  }
+
+  void ln_op(std::vector<Op>& ops, const bf16* x, bf16* out, const NormW& nw, int M) {
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_LN;
+    op.ln = {x, out, nw.g, nw.b, M, nw.C, 1e-5f};
+    ops.push_back(op);
+  }
+
+  bool attn_op(std::vector<Op>& ops, const bf16* q, int q_ld, const bf16* k, const bf16* v, int kv_ld, bf16* out, int out_ld,
+               int Sq, int Skv, int heads, int dh) {
+    Op op;
+    memset(&op, 0, sizeof(op));
+    const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+    if (Skv <= 16) {
+      op.kind = OP_ATTN_SMALL;
+      op.as = AttnSmallArgs{q, q_ld, k, v, kv_ld, out, out_ld, nullptr, Sq, Skv, heads, scale};
+    } else {
+      op.kind = OP_ATTN_FLASH;
+      op.af = AttnFlashArgs{q, q_ld, k, v, kv_ld, out, out_ld, Sq, Skv, heads, scale};
+    }
+    ops.push_back(op);
+    return true;
+  }
+
+  // ---- ResBlock (unet.py:646-671) ----
+  bool res_block(std::vector<Op>& ops, const ResL& r, const std::vector<Act>& in, const float* emb_out, int emb_ld, Act& out) {
+    const int H = in[0].H, W = in[0].W, HW = H * W;
+    Act a1;
+    if (!gn_op(ops, in, r.gn1, 1e-5f, 1, a1)) return false;
+    Act h2 = new_act(H, W, r.Cout);
+    {
+      Epi ep;
+      ep.rowbias = emb_out + r.emb_off;
+      ep.rb_ld = emb_ld;
+      ep.rows_per_sample = HW;
+      ep.out = h2.p;
+      ep.out_ld = r.Cout;
+      if (!gemm_op(ops, B * HW, true, H, W, {ASrc{a1.p, a1.C, a1.C, 9, 1, H, W}}, r.conv1, ep)) return false;
+    }
+    Act a2;
+    if (!gn_op(ops, {h2}, r.gn2, 1e-5f, 1, a2)) return false;
+    out = new_act(H, W, r.Cout);
+    {
+      Epi ep;
+      ep.rows_per_sample = HW;
+      ep.out = out.p;
+      ep.out_ld = r.Cout;
+      std::vector<ASrc> srcs{ASrc{a2.p, a2.C, a2.C, 9, 1, H, W}};
+      if (r.skip_conv) {
+        for (auto& s : in) srcs.push_back(ASrc{s.p, s.C, s.C, 1, 1, H, W});
+      } else {
+        if (in.size() != 1 || in[0].C != r.Cout) { err = "resblock: identity skip needs a single source"; return false; }
+        ep.residual = in[0].p;
+        ep.res_ld = in[0].C;
+      }
+      if (!gemm_op(ops, B * HW, true, H, W, srcs, r.conv2, ep)) return false;
+    }
+    return true;
+  }
+
+  // ---- SpatialTransformer (unet.py:381-412, 337-345 ; unetPhosc.py:282-300, 241-246) ----
+  bool st_block(std::vector<Op>& ops, const STL& s, const Act& x_in, const std::vector<bf16*>& kv, Act& out) {
+    const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = s.heads * s.dh;
+    const int Ltot = plan->Ltot;
+    Act g;
+    if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
+    Act x = new_act(H, W, C);
+    {
+      Epi ep;
+      ep.out = x.p;
+      ep.out_ld = C;
+      if (!gemm_op(ops, M, false, 0, 0, {ASrc{g.p, g.C, g.C, 1, 1, H, W}}, s.proj_in, ep)) return false;
+    }
+    Act n = new_act(H, W, C);
+    Act o = new_act(H, W, C);
+    for (auto& t : s.blocks) {
+      // --- attn1 ---
+      Act x1 = new_act(H, W, C);
+      if (e->cfg.variant == WD_VARIANT_PHOSC) {
+        ln_op(ops, x.p, n.p, t.ln1, M);
+        bf16* qkv = A.alloc<bf16>(static_cast<size_t>(M) * 3 * C);
+        Epi ep;
+        ep.out = qkv;
+        ep.out_ld = 3 * C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a1_q, ep)) return false;
+        attn_op(ops, qkv, 3 * C, qkv + C, qkv + 2 * C, 3 * C, o.p, C, HW, HW, s.heads, s.dh);
+      } else {
+        ln_op(ops, x.p, n.p, t.ln2, M);  // unet.py:337 applies norm2 before attn1
+        bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
+        Epi ep;
+        ep.out = q;
+        ep.out_ld = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a1_q, ep)) return false;
+        attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+      }
+      {
+        Epi ep;
+        ep.out = x1.p;
+        ep.out_ld = C;
+        ep.residual = x.p;
+        ep.res_ld = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a1_out, ep)) return false;
+      }
+      // --- attn2 (cross) ---
+      Act x2 = new_act(H, W, C);
+      ln_op(ops, x1.p, n.p, t.ln2, M);
+      {
+        bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
+        Epi ep;
+        ep.out = q;
+        ep.out_ld = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a2_q, ep)) return false;
+        attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+        Epi ep2;
+        ep2.out = x2.p;
+        ep2.out_ld = C;
+        ep2.residual = x1.p;
+        ep2.res_ld = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a2_out, ep2)) return false;
+      }
+      // --- GEGLU feed-forward ---
+      Act x3 = new_act(H, W, C);
+      ln_op(ops, x2.p, n.p, t.ln3, M);
+      {
+        bf16* gg = A.alloc<bf16>(static_cast<size_t>(M) * 4 * C);
+        Epi ep;
+        ep.out = gg;
+        ep.out_ld = 4 * C;
+        ep.geglu = 1;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.ff_proj, ep)) return false;
+        Epi ep2;
+        ep2.out = x3.p;
+        ep2.out_ld = C;
+        ep2.residual = x2.p;
+        ep2.res_ld = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{gg, 4 * C, 4 * C, 1, 1, H, W}}, t.ff_out, ep2)) return false;
+      }
+      x = x3;
+    }
+    out = new_act(H, W, s.C);
+    Epi ep;
+    ep.out = out.p;
+    ep.out_ld = s.C;
+    ep.residual = x_in.p;
+    ep.res_ld = x_in.C;
+    return gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W}}, s.proj_out, ep);
+  }
+
+  bool build() {
+    const wd_config& c = e->cfg;
+    const int mc = c.model_channels, ted = e->time_dim, D = c.context_dim;
+    const int L = plan->L, Ltot = plan->Ltot;
+    auto& cops = plan->ctx_ops;
+    auto& sops = plan->step_ops;
+
+    // ================= context (time-invariant) =================
+    bf16* ctx = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * D);
+    {
+      const int nseg = c.phosc_len > 0 ? 2 : 1;
+      for (int seg = 0; seg < nseg; ++seg) {
+        const int Ls = seg == 0 ? L : c.phosc_len;
+        const int row_off = seg == 0 ? 0 : L;
+        float* emb = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        float* q = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        float* k = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        float* v = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        // unet.py:872 always adds the PE; unetPhosc.py:726-729 only when the sequence fits max_seq_len
+        const int add_pe = (c.variant == WD_VARIANT_UNET) ? 1 : (Ls <= c.max_seq_len ? 1 : 0);
+        if (add_pe && Ls > c.max_seq_len) { err = "context longer than max_seq_len"; return false; }
+        Op op;
+        memset(&op, 0, sizeof(op));
+        op.kind = OP_EMBED;
+        op.emb = {seg, e->we_E, c.vocab_size, e->we_pe, add_pe, emb, B, Ls, D};
+        cops.push_back(op);
+        const float* Ws[3] = {e->we_qw, e->we_kw, e->we_vw};
+        const float* bs[3] = {e->we_qb, e->we_kb, e->we_vb};
+        float* outs[3] = {q, k, v};
+        for (int i = 0; i < 3; ++i) {
+          Op lo;
+          memset(&lo, 0, sizeof(lo));
+          lo.kind = OP_LINF32;
+          lo.lin = {emb, Ws[i], bs[i], outs[i], B * Ls, D, D};
+          cops.push_back(lo);
+        }
+        Op wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.kind = OP_WORDATTN;
+        wa.wa = {q, k, v, ctx, B, Ls, D, Ltot, row_off};
+        cops.push_back(wa);
+      }
+    }
+    std::vector<bf16*> kv(e->n_kv, nullptr);
+    for (int i = 0; i < e->n_kv; ++i) {
+      const GemmW& w = *e->kv_weights[i];
+      kv[i] = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * w.N);
+      Epi ep;
+      ep.out = kv[i];
+      ep.out_ld = w.N;
+      if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, w, ep)) return false;
+    }
+
+    // ================= per-step =================
+    bf16* temb = A.alloc<bf16>(static_cast<size_t>(B) * mc);
+    bf16* h1 = A.alloc<bf16>(static_cast<size_t>(B) * ted);
+    bf16* emb_act = A.alloc<bf16>(static_cast<size_t>(B) * ted);
+    float* emb_out = A.alloc<float>(static_cast<size_t>(B) * e->emb_all.N);
+    {
+      Op op;
+      memset(&op, 0, sizeof(op));
+      op.kind = OP_TEMB;
+      op.temb = {temb, B, mc};
+      sops.push_back(op);
+      Epi ep;
+      ep.out = h1;
+      ep.out_ld = ted;
+      ep.act = ACT_SILU;
+      if (!gemm_op(sops, B, false, 0, 0, {ASrc{temb, mc, mc, 1, 1, 1, 1}}, e->te0, ep)) return false;
+      Epi ep2;
+      ep2.out = emb_act;
+      ep2.out_ld = ted;
+      ep2.act = ACT_SILU;  // every consumer applies SiLU first (emb_layers.0, unet.py:609-610)
+      int patch = P_NONE;
+      if (c.num_classes > 0 && c.add_label_emb) {
+        ep2.rowbias = e->label_emb;
+        ep2.rb_ld = ted;
+        ep2.rows_per_sample = 1;
+        patch = P_Y;
+      }
+      if (!gemm_op(sops, B, false, 0, 0, {ASrc{h1, ted, ted, 1, 1, 1, 1}}, e->te2, ep2, patch)) return false;
+      Epi ep3;
+      ep3.out = emb_out;
+      ep3.out_ld = e->emb_all.N;
+      ep3.out_f32 = 1;
+      if (!gemm_op(sops, B, false, 0, 0, {ASrc{emb_act, ted, ted, 1, 1, 1, 1}}, e->emb_all, ep3)) return false;
+    }
+    const int emb_ld = e->emb_all.N;
+
+    std::vector<Act> hs;
+    Act h{nullptr, 0, 0, 0};
+    auto run_block = [&](const Block& blk, std::vector<Act> in) -> bool {
+      for (const Layer& l : blk) {
+        Act out;
+        switch (l.kind) {
+          case L_CONVIN: {
+            out = new_act(c.latent_h, c.latent_w, mc);
+            Op op;
+            memset(&op, 0, sizeof(op));
+            op.kind = OP_CONV_IN;
+            op.cin = {e->conv_in_w, e->conv_in_b, out.p, B, c.latent_h, c.latent_w, mc};
+            sops.push_back(op);
+            break;
+          }
+          case L_RES:
+            if (!res_block(sops, e->res[l.idx], in, emb_out, emb_ld, out)) return false;
+            break;
+          case L_ST:
+            if (!st_block(sops, e->st[l.idx], in[0], kv, out)) return false;
+            break;
+          case L_DOWN: {
+            const Act& x = in[0];
+            if (x.H % 2 || x.W % 2) { err = "downsample needs even spatial size"; return false; }
+            out = new_act(x.H / 2, x.W / 2, x.C);
+            Epi ep;
+            ep.out = out.p;
+            ep.out_ld = x.C;
+            ep.rows_per_sample = out.H * out.W;
+            if (!gemm_op(sops, B * out.H * out.W, true, out.H, out.W, {ASrc{x.p, x.C, x.C, 9, 2, x.H, x.W}},
+                         e->samp[l.idx].conv, ep))
+              return false;
+            break;
+          }
+          case L_UP: {
+            const Act& x = in[0];
+            Act up = new_act(x.H * 2, x.W * 2, x.C);
+            Op op;
+            memset(&op, 0, sizeof(op));
+            op.kind = OP_UPSAMPLE;
+            op.up = {x.p, up.p, B, x.H, x.W, x.C};
+            sops.push_back(op);
+            out = new_act(up.H, up.W, x.C);
+            Epi ep;
+            ep.out = out.p;
+            ep.out_ld = x.C;
+            ep.rows_per_sample = up.H * up.W;
+            if (!gemm_op(sops, B * up.H * up.W, true, up.H, up.W, {ASrc{up.p, up.C, up.C, 9, 1, up.H, up.W}},
+                         e->samp[l.idx].conv, ep))
+              return false;
+            break;
+          }
+        }
+        in = {out};
+        h = out;
+      }
+      return true;
+    };
+
+    for (auto& blk : e->input_blocks) {
+      if (!run_block(blk, h.p ? std::vector<Act>{h} : std::vector<Act>{})) return false;
+      hs.push_back(h);
+    }
+    if (!run_block(e->middle, {h})) return false;
+    for (auto& blk : e->output_blocks) {
+      Act skip = hs.back();
+      hs.pop_back();
+      if (skip.H != h.H || skip.W != h.W) { err = "skip connection spatial mismatch"; return false; }
+      if (!run_block(blk, {h, skip})) return false;
+    }
+    // out: GN + SiLU, then conv_out fused with the sampler update
+    Act a;
+    if (!gn_op(sops, {h}, e->out_gn, 1e-5f, 1, a)) return false;
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_CONV_OUT;
+    op.cout_ = {a.p, e->conv_out_w, e->conv_out_b, B, a.H, a.W, a.C};
+    sops.push_back(op);
+    plan->bytes = A.used;
+    return true;
+  }
+};
+
+int ensure_plan(wd_engine* e, int B, int L, Plan** out) {
+  if (B < 1) return fail(WD_ERR_INVALID, "batch must be >= 1");
+  if (L < 1) return fail(WD_ERR_INVALID, "context length must be >= 1");
+  auto key = std::make_pair(B, L);
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) {
+    *out = it->second.get();
+    return WD_OK;
+  }
+  std::unique_ptr<Plan> p(new Plan());
+  p->B = B;
+  p->L = L;
+  p->Ltot = L + (e->cfg.phosc_len > 0 ? e->cfg.phosc_len : 0);
+  {
+    Plan tmp = *p;
+    PlanBuilder pb{e, &tmp, Arena(), true, B, ""};
+    if (!pb.build()) return fail(WD_ERR_UNSUPPORTED, "plan: %s", pb.err.c_str());
+    p->bytes = tmp.bytes;
+  }
+  if (p->bytes > e->acap) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (e->abase) CUDA_TRY(cudaFree(e->abase));
+    e->abase = nullptr;
+    e->acap = 0;
+    e->plans.clear();
+    e->cur = nullptr;
+    CUDA_TRY(cudaMalloc(&e->abase, p->bytes));
+    e->acap = p->bytes;
+  }
+  Arena A;
+  A.base = e->abase;
+  PlanBuilder pb{e, p.get(), A, false, B, ""};
+  if (!pb.build()) return fail(WD_ERR_UNSUPPORTED, "plan: %s", pb.err.c_str());
+  *out = p.get();
+  e->plans[key] = std::move(p);
+  return WD_OK;
+}
+
+struct RunCtx {
+  const float* x = nullptr;
+  const long long* t_dev = nullptr;
+  long long t_scalar = 0;
+  const long long* y = nullptr;
+  const long long* ctx_tokens = nullptr;
+  const int* phosc = nullptr;
+  // conv_out
+  float* eps_out = nullptr;
+  float* x_rw = nullptr;
+  const float* noise = nullptr;
+  int use_philox = 0;
+  unsigned long long seed = 0, sample_offset = 0;
+  int step_index = 0;
+  float4 coef = make_float4(0, 0, 0, 0);
+  int mode = STEP_EPS_ONLY;
+};
+
+int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStream_t s) {
+  int n = 0;
+  for (const Op& op : ops) {
+    cudaError_t err = cudaSuccess;
+    switch (op.kind) {
+      case OP_TEMB:
+        err = timestep_embed_launch(rc.t_dev, rc.t_scalar, op.temb.out, op.temb.B, op.temb.dim, s);
+        break;
+      case OP_GEMM:
+        if (op.patch == P_Y) {
+          if (!rc.y) return fail(WD_ERR_INVALID, "y (writer ids) is required by this model");
+          GemmLaunch L = op.gemm;
+          L.args.rowbias_idx = rc.y;
+          err = gemm_tc_launch(L, s);
+        } else {
+          err = gemm_tc_launch(op.gemm, s);
+        }
+        break;
+      case OP_GN:
+        err = groupnorm_launch(op.gn, op.gn_B, op.gn_nslab, s);
+        break;
+      case OP_LN:
+        err = layernorm_launch(op.ln.x, op.ln.out, op.ln.g, op.ln.b, op.ln.M, op.ln.C, op.ln.eps, s);
+        break;
+      case OP_ATTN_SMALL:
+        err = attn_small_launch(op.as, e->cur->B, s);
+        break;
+      case OP_ATTN_FLASH:
+        err = attn_flash_launch(op.af, e->cur->B, s);
+        break;
+      case OP_CONV_IN:
+        err = conv_in_launch(rc.x, op.cin.w, op.cin.bias, op.cin.out, op.cin.B, op.cin.H, op.cin.W, op.cin.Cout, s);
+        break;
+      case OP_CONV_OUT: {
+        ConvOutArgs a;
+        a.h = op.cout_.h;
+        a.w_packed = op.cout_.w;
+        a.bias = op.cout_.bias;
+        a.eps_out = rc.eps_out;
+        a.x = rc.x_rw;
+        a.noise = rc.noise;
+        a.use_philox = rc.use_philox;
+        a.seed = rc.seed;
+        a.sample_offset = rc.sample_offset;
+        a.step_index = rc.step_index;
+        a.coef = rc.coef;
+        a.mode = rc.mode;
+        a.B = op.cout_.B;
+        a.H = op.cout_.H;
+        a.W = op.cout_.W;
+        a.C = op.cout_.C;
+        err = conv_out_step_launch(a, s);
+        break;
+      }
+      case OP_UPSAMPLE:
+        err = upsample2x_launch(op.up.x, op.up.out, op.up.B, op.up.H, op.up.W, op.up.C, s);
+        break;
+      case OP_EMBED:
+        if (op.emb.which == 0)
+          err = embed_tokens_launch(rc.ctx_tokens, 1, op.emb.E, op.emb.vocab, op.emb.pe, op.emb.add_pe, op.emb.out,
+                                    op.emb.B, op.emb.L, op.emb.D, s);
+        else {
+          if (!rc.phosc) return fail(WD_ERR_INVALID, "phoscLabels are required by this model");
+          err = embed_tokens_launch(rc.phosc, 0, op.emb.E, op.emb.vocab, op.emb.pe, op.emb.add_pe, op.emb.out, op.emb.B,
+                                    op.emb.L, op.emb.D, s);
+        }
+        break;
+      case OP_LINF32:
+        err = linear_f32_launch(op.lin.x, op.lin.W, op.lin.b, op.lin.out, op.lin.M, op.lin.N, op.lin.K, s);
+        break;
+      case OP_WORDATTN:
+        err = word_attn_launch(op.wa.q, op.wa.k, op.wa.v, op.wa.ctx, nullptr, op.wa.B, op.wa.L, op.wa.D, op.wa.Ltot,
+                               op.wa.row_off, s);
+        break;
+    }
+    if (err != cudaSuccess) return fail(WD_ERR_CUDA, "launch of op kind %d failed: %s", (int)op.kind, cudaGetErrorString(err));
+    ++n;
+  }
+  e->last_launches = n;
+  return WD_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// C ABI: hot path
+// ----------------------------------------------------------------------------------------------
+extern "C" int wd_engine_reserve(wd_engine* e, int batch) {
+  if (!e) return fail(WD_ERR_INVALID, "null engine");
+  Plan* p = nullptr;
+  return ensure_plan(e, batch, e->cfg.max_seq_len, &p);
+}
+
+extern "C" int wd_encode_context(wd_engine* e, int batch, const int64_t* ctx_tokens, int L, const int32_t* phosc,
+                                 void* stream) {
+  if (!e || !ctx_tokens) return fail(WD_ERR_INVALID, "null argument");
+  Plan* p = nullptr;
+  int rc = ensure_plan(e, batch, L, &p);
+  if (rc) return rc;
+  e->cur = p;
+  RunCtx r;
+  r.ctx_tokens = reinterpret_cast<const long long*>(ctx_tokens);
+  r.phosc = phosc;
+  rc = run_ops(e, p->ctx_ops, r, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  p->context_valid = true;
+  return WD_OK;
+}
+
+static int check_ready(wd_engine* e, int batch) {
+  if (!e) return fail(WD_ERR_INVALID, "null engine");
+  if (!e->cur || !e->cur->context_valid) return fail(WD_ERR_STATE, "wd_encode_context must run before the UNet");
+  if (e->cur->B != batch) return fail(WD_ERR_STATE, "batch %d does not match the encoded context (%d)", batch, e->cur->B);
+  return WD_OK;
+}
+
+extern "C" int wd_unet_eval(wd_engine* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar,
+                            const int64_t* y, float* eps_out, void* stream) {
+  int rc = check_ready(e, batch);
+  if (rc) return rc;
+  if (!x || !eps_out) return fail(WD_ERR_INVALID, "null argument");
+  RunCtx r;
+  r.x = x;
+  r.t_dev = reinterpret_cast<const long long*>(timesteps);
+  r.t_scalar = t_scalar;
+  r.y = reinterpret_cast<const long long*>(y);
+  r.eps_out = eps_out;
+  r.mode = STEP_EPS_ONLY;
+  return run_ops(e, e->cur->step_ops, r, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scalar, const int64_t* y, int mode,
+                               const float* coef4_host, const float* noise, int use_philox, uint64_t seed,
+                               uint64_t sample_offset, int step_index, float* eps_out, void* stream) {
+  int rc = check_ready(e, batch);
+  if (rc) return rc;
+  if (!x || !coef4_host) return fail(WD_ERR_INVALID, "null argument");
+  if (mode != WD_STEP_DDPM && mode != WD_STEP_DDIM && mode != WD_STEP_EPS_ONLY) return fail(WD_ERR_INVALID, "bad mode");
+  RunCtx r;
+  r.x = x;
+  r.x_rw = x;
+  r.t_scalar = t_scalar;
+  r.y = reinterpret_cast<const long long*>(y);
+  r.eps_out = eps_out;
+  r.noise = noise;
+  r.use_philox = use_philox;
+  r.seed = seed;
+  r.sample_offset = sample_offset;
+  r.step_index = step_index;
+  r.coef = make_float4(coef4_host[0], coef4_host[1], coef4_host[2], coef4_host[3]);
+  r.mode = mode;
+  return run_ops(e, e->cur->step_ops, r, static_cast<cudaStream_t>(stream));
+}
+
+// ----------------------------------------------------------------------------------------------
+// C ABI: single operators (parity tests)
+// ----------------------------------------------------------------------------------------------
+extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, const float* beta, int B, int HW, int C,
+                               int groups, float eps, int silu, void* stream) {
+  if (C % groups) return fail(WD_ERR_INVALID, "C %% groups");
+  const int cpg = C / groups;
+  int Cs = C;
+  auto fits = [&](int cs) { return static_cast<size_t>(HW) * cs * 2 + 8 * cs * 4 + cs * 4 + 1024 <= 200 * 1024; };
+  while (!fits(Cs)) {
+    if (Cs % 2 || (Cs / 2) % cpg || (Cs / 2) % 8) return fail(WD_ERR_UNSUPPORTED, "groupnorm: cannot tile");
+    Cs /= 2;
+  }
+  const int nslab = C / Cs;
+  if (nslab > 8 || Cs % 8) return fail(WD_ERR_UNSUPPORTED, "groupnorm: unsupported channel count");
+  GroupNormArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < nslab; ++i) {
+    a.x[i] = static_cast<const bf16*>(x) + i * Cs;
+    a.x_ld[i] = C;
+  }
+  a.out = static_cast<bf16*>(out);
+  a.out_ld = C;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.HW = HW;
+  a.Cs = Cs;
+  a.cpg = cpg;
+  a.eps = eps;
+  a.silu = silu;
+  CUDA_TRY(groupnorm_launch(a, B, nslab, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_layernorm(const void* x, void* out, const float* gamma, const float* beta, int M, int C, float eps,
+                               void* stream) {
+  CUDA_TRY(layernorm_launch(static_cast<const bf16*>(x), static_cast<bf16*>(out), gamma, beta, M, C, eps,
+                            static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, const void* residual, void* out, int M, int N,
+                          int K, int act_silu, int geglu, int out_f32, void* stream) {
+  if (K % GEMM_BLOCK_K || N % gemm_tc_block_n()) return fail(WD_ERR_UNSUPPORTED, "gemm: K %% 64 or N %% %d", gemm_tc_block_n());
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  GemmArgs& a = L.args;
+  a.M = M;
+  a.N = N;
+  a.num_src = 1;
+  a.taps[0] = 1;
+  a.chunks[0] = K / GEMM_BLOCK_K;
+  a.stride[0] = 1;
+  a.conv = 0;
+  a.Wout = 1;
+  a.HWout = 1;
+  a.bias = bias;
+  a.rows_per_sample = 1;
+  a.residual = static_cast<const bf16*>(residual);
+  const int out_cols = geglu ? N / 2 : N;
+  a.res_ld = out_cols;
+  a.out = out;
+  a.out_ld = out_cols;
+  a.out_f32 = out_f32;
+  a.act = act_silu ? ACT_SILU : ACT_NONE;
+  a.geglu = geglu;
+  if (!tmap_encode_2d_bf16(&L.mapA[0], a_, K, M, K, GEMM_BLOCK_K, GEMM_BLOCK_M)) return fail(WD_ERR_CUDA, "tensor map A");
+  L.mapA[1] = L.mapA[2] = L.mapA[0];
+  if (!tmap_encode_2d_bf16(&L.mapB, w, K, N, K, GEMM_BLOCK_K, gemm_tc_block_n())) return fail(WD_ERR_CUDA, "tensor map B");
+  CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_conv3x3(const void* x, const void* w_packed, const float* bias, const float* rowbias, int rb_ld,
+                             const void* residual, void* out, int B, int H, int W, int Cin, int Cout, int stride,
+                             void* stream) {
+  if (Cin % GEMM_BLOCK_K || Cout % gemm_tc_block_n()) return fail(WD_ERR_UNSUPPORTED, "conv3x3: channel counts");
+  if (stride != 1 && stride != 2) return fail(WD_ERR_INVALID, "stride");
+  const int Ho = H / stride, Wo = W / stride, HWo = Ho * Wo;
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  GemmArgs& a = L.args;
+  a.M = B * HWo;
+  a.N = Cout;
+  a.num_src = 1;
+  a.taps[0] = 9;
+  a.chunks[0] = Cin / GEMM_BLOCK_K;
+  a.stride[0] = stride;
+  a.conv = 1;
+  a.Wout = Wo;
+  a.HWout = HWo;
+  a.bias = bias;
+  a.rowbias = rowbias;
+  a.rb_ld = rb_ld;
+  a.rows_per_sample = HWo;
+  a.residual = static_cast<const bf16*>(residual);
+  a.res_ld = Cout;
+  a.out = out;
+  a.out_ld = Cout;
+  uint32_t bw, bh, bnn;
+  if (HWo >= GEMM_BLOCK_M) {
+    if (HWo % GEMM_BLOCK_M || GEMM_BLOCK_M % Wo) return fail(WD_ERR_UNSUPPORTED, "conv3x3: spatial size");
+    bw = Wo * stride;
+    bh = (GEMM_BLOCK_M / Wo) * stride;
+    bnn = 1;
+  } else {
+    if (GEMM_BLOCK_M % HWo) return fail(WD_ERR_UNSUPPORTED, "conv3x3: spatial size");
+    bw = W;
+    bh = H;
+    bnn = GEMM_BLOCK_M / HWo;
+  }
+  if (!tmap_encode_4d_bf16(&L.mapA[0], x, Cin, W, H, B, Cin, GEMM_BLOCK_K, bw, bh, bnn, stride))
+    return fail(WD_ERR_CUDA, "tensor map A");
+  L.mapA[1] = L.mapA[2] = L.mapA[0];
+  if (!tmap_encode_2d_bf16(&L.mapB, w_packed, 9 * Cin, Cout, 9 * Cin, GEMM_BLOCK_K, gemm_tc_block_n()))
+    return fail(WD_ERR_CUDA, "tensor map B");
+  CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_pack_conv3x3(const float* w, void* dst, int Cout, int Cin, void* stream) {
+  CUDA_TRY(repack_conv3x3_launch(w, static_cast<bf16*>(dst), Cout, Cin, 9 * Cin, 0, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+extern "C" int wd_op_pack_linear(const float* w, void* dst, int N, int K, int geglu_perm, void* stream) {
+  CUDA_TRY(repack_linear_launch(w, static_cast<bf16*>(dst), N, K, K, 0, 0, geglu_perm ? gemm_tc_block_n() : 0,
+                                static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+extern "C" int wd_op_pack_vec_geglu(const float* v, float* dst, int N, void* stream) {
+  CUDA_TRY(repack_vec_launch(v, dst, N, 0, gemm_tc_block_n(), 0, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_attention_small(const void* q, const void* k, const void* v, void* out, float* probs, int B, int Sq,
+                                     int L, int heads, float scale, void* stream) {
+  const int C = heads * 80;
+  AttnSmallArgs a{static_cast<const bf16*>(q), C, static_cast<const bf16*>(k), static_cast<const bf16*>(v), C,
+                  static_cast<bf16*>(out), C, probs, Sq, L, heads, scale};
+  CUDA_TRY(attn_small_launch(a, B, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_attention(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B,
+                               int Sq, int Skv, int heads, float scale, void* stream) {
+  AttnFlashArgs a{static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), static_cast<const bf16*>(v), ldkv,
+                  static_cast<bf16*>(out), ldo, Sq, Skv, heads, scale};
+  CUDA_TRY(attn_flash_launch(a, B, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}

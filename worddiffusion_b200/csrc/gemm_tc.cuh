@@ -1,0 +1,66 @@
+// Implicit-GEMM on the 5th-gen tensor cores (tcgen05 + TMEM accumulators + TMA operand staging).
+//
+// One kernel serves every dense contraction on the WordDiffusion hot path:
+//   * ResBlock / Upsample / Downsample 3x3 convolutions (reference unet.py:595,621,488,540):
+//       A rows are gathered straight from the NHWC bf16 activation by 4-D TMA boxes, one box per
+//       filter tap with shifted (w,h) start coordinates; out-of-bounds rows are zero-filled by the TMA
+//       unit, which is exactly the conv's zero padding.  No im2col buffer exists.
+//   * 1x1 convolutions and nn.Linear (unet.py:364,375,632,175-183,125,145,611,1202-1204): plain 2-D TMA.
+//   * "K-concatenated" fusions: up to three A sources are walked back to back along K, so the
+//       640->320 skip 1x1 conv of the decoder ResBlocks (unet.py:632,671) accumulates into the same TMEM
+//       tile as the block's second 3x3 conv.
+// Epilogue (TMEM -> registers -> global) fuses: +bias[N], +row-bias[sample,N] (timestep-embedding add,
+// unet.py:657-666), +residual, SiLU, GEGLU (unet.py:127-129) and the bf16 / fp32 store.
+#pragma once
+#include "common.cuh"
+
+namespace wd {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_THREADS = 192;  // warp0: TMA producer, warp1: TMEM alloc + MMA issuer, warps2-5: epilogue
+constexpr int GEMM_MAX_SRC = 3;
+
+enum GemmAct : int { ACT_NONE = 0, ACT_SILU = 1 };
+
+struct GemmArgs {
+  int M;  // rows (pixels / tokens)
+  int N;  // accumulator columns (weight rows)
+  int num_src;
+  int taps[GEMM_MAX_SRC];    // 1 or 9
+  int chunks[GEMM_MAX_SRC];  // channels / 64
+  int stride[GEMM_MAX_SRC];  // conv stride of that source (1 or 2)
+  int conv;                  // 1: 4-D (c,w,h,n) coordinates, 0: 2-D (c, row)
+  int Wout;                  // output width  (conv)
+  int HWout;                 // output pixels per image (conv)
+  // ---- epilogue ----
+  const float* bias;             // [N] or null (already permuted for GEGLU)
+  const float* rowbias;          // [rows, rb_ld] fp32 or null
+  const long long* rowbias_idx;  // optional: row = rowbias_idx[m / rows_per_sample]
+  int rb_ld;
+  int rows_per_sample;
+  const __nv_bfloat16* residual;  // [M, res_ld] or null
+  int res_ld;
+  void* out;  // bf16 (or fp32 when out_f32) [M, out_ld]
+  int out_ld;
+  int out_f32;
+  int act;
+  int geglu;  // 1: tile columns [0,BN/2) are values, [BN/2,BN) gates; writes BN/2 columns per tile
+};
+
+struct GemmLaunch {
+  CUtensorMap mapA[GEMM_MAX_SRC];
+  CUtensorMap mapB;
+  GemmArgs args;
+};
+
+// Host helpers (gemm_tc.cu)
+bool tmap_encode_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                         uint32_t box_inner, uint32_t box_rows);
+bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                         uint64_t pix_stride_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n,
+                         uint32_t stride_wh);
+cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);
+int gemm_tc_block_n();
+
+}  // namespace wd

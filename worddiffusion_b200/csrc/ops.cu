@@ -1,0 +1,748 @@
+// HBM-/latency-bound kernels of the WordDiffusion hot path.  All activations are NHWC bf16
+// ([B, H*W, C] == token-major), statistics and accumulators are fp32.
+#include "ops.cuh"
+
+#include <mutex>
+
+namespace wd {
+
+// =====================================================================================================
+// GroupNorm (+SiLU).  One CTA = one (sample, channel slab); the slab lives in shared memory, so HBM sees
+// exactly one read and one write of the activation.  Two-pass (mean, then centred variance) in fp32.
+// Thread t owns vector column t % (Cs/8) (8 channels) and pixel rows t / (Cs/8), stepping by R.
+// =====================================================================================================
+__global__ void __launch_bounds__(1024) groupnorm_kernel(const GroupNormArgs a) {
+  extern __shared__ uint4 gn_smem[];
+  const int b = blockIdx.x, slab = blockIdx.y;
+  const int Cs = a.Cs, HW = a.HW, cpg = a.cpg;
+  const int nv = Cs >> 3;
+  const int R = blockDim.x / nv;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int ng = Cs / cpg;
+
+  uint4* sdata = gn_smem;                                  // [HW][nv]
+  float* part = reinterpret_cast<float*>(sdata + HW * nv);  // [R][Cs]
+  float* chan = part + R * Cs;                              // [Cs]
+  float* gmean = chan + Cs;                                 // [ng]
+  float* grstd = gmean + ng;                                // [ng]
+
+  const int ld = a.x_ld[slab];
+  const __nv_bfloat16* xb = a.x[slab] + static_cast<size_t>(b) * HW * ld;
+
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int p = rl; p < HW; p += R) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
+    sdata[p * nv + col] = v;
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      s[2 * j] += f.x;
+      s[2 * j + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl * Cs + col * 8 + j] = s[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += part[r * Cs + c];
+    chan[c] = t;
+  }
+  __syncthreads();
+  const float inv_n = 1.0f / static_cast<float>(cpg * HW);
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    float t = 0.f;
+    for (int c = 0; c < cpg; ++c) t += chan[g * cpg + c];
+    gmean[g] = t * inv_n;
+  }
+  __syncthreads();
+
+  float mu[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = gmean[(col * 8 + j) / cpg];
+    s[j] = 0.f;
+  }
+  for (int p = rl; p < HW; p += R) {
+    const uint4 v = sdata[p * nv + col];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      const float d0 = f.x - mu[2 * j], d1 = f.y - mu[2 * j + 1];
+      s[2 * j] += d0 * d0;
+      s[2 * j + 1] += d1 * d1;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl * Cs + col * 8 + j] = s[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += part[r * Cs + c];
+    chan[c] = t;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    float t = 0.f;
+    for (int c = 0; c < cpg; ++c) t += chan[g * cpg + c];
+    grstd[g] = rsqrtf(t * inv_n + a.eps);
+  }
+  __syncthreads();
+
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = col * 8 + j;
+    const float rstd = grstd[c / cpg];
+    const float g = __ldg(a.gamma + slab * Cs + c), be = __ldg(a.beta + slab * Cs + c);
+    sc[j] = rstd * g;
+    sh[j] = be - mu[j] * sc[j];
+  }
+  __nv_bfloat16* ob = a.out + static_cast<size_t>(b) * HW * a.out_ld + slab * Cs;
+  for (int p = rl; p < HW; p += R) {
+    const uint4 v = sdata[p * nv + col];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      float y0 = f.x * sc[2 * j] + sh[2 * j];
+      float y1 = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+      if (a.silu) {
+        y0 = silu_f(y0);
+        y1 = silu_f(y1);
+      }
+      o[j] = pack_bf16x2(y0, y1);
+    }
+    reinterpret_cast<uint4*>(ob + static_cast<size_t>(p) * a.out_ld)[col] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s) {
+  const int nv = a.Cs / 8;
+  if (a.Cs % 8 || a.Cs % a.cpg || nv > 1024) return cudaErrorInvalidValue;
+  int R = 1024 / nv;
+  if (R > 8) R = 8;
+  if (R > a.HW) R = a.HW;
+  const int threads = nv * R;
+  const size_t smem = static_cast<size_t>(a.HW) * a.Cs * 2 + static_cast<size_t>(R) * a.Cs * 4 + a.Cs * 4 +
+                      2 * (a.Cs / a.cpg) * 4 + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(groupnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  groupnorm_kernel<<<dim3(B, nslab), threads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// LayerNorm: one warp per token, fp32 two-pass in registers, bf16 in/out.
+// =====================================================================================================
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int M, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * C);
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) {
+      const uint4 v = __ldg(xr + vi);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(u[j]);
+        f[i][2 * j] = t.x;
+        f[i][2 * j + 1] = t.y;
+        sum += t.x + t.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(C);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        var += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(warp) * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2 + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2 + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (f[i][j] - mean) * rstd * g[j] + bb[j];
+      orow[vi] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                            pack_bf16x2(y[6], y[7]));
+    }
+  }
+}
+
+cudaError_t layernorm_launch(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta, int M,
+                             int C, float eps, cudaStream_t s) {
+  if (C % 8 || C > 8 * 32 * 4) return cudaErrorInvalidValue;
+  const int warps_per_block = 8;
+  const int blocks = (M + warps_per_block - 1) / warps_per_block;
+  if (C <= 8 * 32 * 2)
+    layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps);
+  else
+    layernorm_kernel<4><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Attention over a short context (L <= 16): one thread per (query token, head); K/V of the sample staged
+// in shared memory as fp32.  softmax(q k^T * scale) v, exactly the reference op order (unet.py:195-270).
+// =====================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(128) attn_small_kernel(const AttnSmallArgs a) {
+  extern __shared__ float as_smem[];
+  const int b = blockIdx.y;
+  const int C = a.heads * DH;
+  float* sk = as_smem;           // [L][C]
+  float* sv = as_smem + a.L * C;  // [L][C]
+  const __nv_bfloat16* kb = a.k + static_cast<size_t>(b) * a.L * a.kv_ld;
+  const __nv_bfloat16* vb = a.v + static_cast<size_t>(b) * a.L * a.kv_ld;
+  for (int i = threadIdx.x; i < a.L * C; i += blockDim.x) {
+    const int l = i / C, c = i % C;
+    sk[i] = __bfloat162float(kb[static_cast<size_t>(l) * a.kv_ld + c]);
+    sv[i] = __bfloat162float(vb[static_cast<size_t>(l) * a.kv_ld + c]);
+  }
+  __syncthreads();
+  const int tokens_per_block = blockDim.x / a.heads;
+  const int tok = blockIdx.x * tokens_per_block + threadIdx.x / a.heads;
+  const int h = threadIdx.x % a.heads;
+  if (tok >= a.Sq) return;
+
+  float q[DH];
+  const uint4* qp = reinterpret_cast<const uint4*>(a.q + (static_cast<size_t>(b) * a.Sq + tok) * a.q_ld + h * DH);
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    const uint4 v = __ldg(qp + i);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_bf16x2(u[j]);
+      q[i * 8 + 2 * j] = t.x;
+      q[i * 8 + 2 * j + 1] = t.y;
+    }
+  }
+  float sc[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    if (l < a.L) {
+      const float* kr = sk + l * C + h * DH;
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) d += q[i] * kr[i];
+      sc[l] = d * a.scale;
+      mx = fmaxf(mx, sc[l]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    if (l < a.L) {
+      sc[l] = __expf(sc[l] - mx);
+      den += sc[l];
+    }
+  }
+  const float inv = 1.0f / den;
+  if (a.probs) {
+    float* pp = a.probs + ((static_cast<size_t>(b) * a.heads + h) * a.Sq + tok) * a.L;
+#pragma unroll
+    for (int l = 0; l < 16; ++l)
+      if (l < a.L) pp[l] = sc[l] * inv;
+  }
+  float o[DH];
+#pragma unroll
+  for (int i = 0; i < DH; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    if (l < a.L) {
+      const float p = sc[l] * inv;
+      const float* vr = sv + l * C + h * DH;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o[i] += p * vr[i];
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(b) * a.Sq + tok) * a.out_ld + h * DH);
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i)
+    op[i] = make_uint4(pack_bf16x2(o[i * 8], o[i * 8 + 1]), pack_bf16x2(o[i * 8 + 2], o[i * 8 + 3]),
+                       pack_bf16x2(o[i * 8 + 4], o[i * 8 + 5]), pack_bf16x2(o[i * 8 + 6], o[i * 8 + 7]));
+}
+
+cudaError_t attn_small_launch(const AttnSmallArgs& a, int B, cudaStream_t s) {
+  if (a.L > 16 || a.L < 1 || 128 % a.heads) return cudaErrorInvalidValue;
+  const int C = a.heads * 80;
+  const size_t smem = static_cast<size_t>(2) * a.L * C * sizeof(float);
+  const int tpb = 128 / a.heads;
+  dim3 grid((a.Sq + tpb - 1) / tpb, B);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_small_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  if (smem > 100 * 1024) return cudaErrorInvalidValue;
+  attn_small_kernel<80><<<grid, 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Sinusoidal timestep embedding: out[b] = [cos(t f_0..f_{h-1}) | sin(t f_0..f_{h-1})], f_i = exp(-ln(1e4) i / h)
+// =====================================================================================================
+__global__ void timestep_embed_kernel(const long long* __restrict__ t_dev, long long t_scalar,
+                                      __nv_bfloat16* __restrict__ out, int B, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx % half;
+  const float t = static_cast<float>(t_dev ? t_dev[b] : t_scalar);
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+  const float arg = t * freq;
+  out[static_cast<size_t>(b) * dim + i] = __float2bfloat16(cosf(arg));
+  out[static_cast<size_t>(b) * dim + half + i] = __float2bfloat16(sinf(arg));
+}
+
+cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __nv_bfloat16* out, int B, int dim,
+                                  cudaStream_t s) {
+  if (dim % 2) return cudaErrorInvalidValue;
+  const int n = B * (dim / 2);
+  timestep_embed_kernel<<<(n + 255) / 256, 256, 0, s>>>(t_dev, t_scalar, out, B, dim);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// conv_in: 3x3 pad 1, Cin = 4, fp32 NCHW latent -> bf16 NHWC.  One CTA per image row.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                      int H, int W, int Cout) {
+  extern __shared__ float ci_smem[];
+  float* sw = ci_smem;               // [36][Cout]
+  float* sp = ci_smem + 36 * Cout;    // [4][3][W+2]
+  const int y = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) sw[i] = __ldg(wp + i);
+  const int PW = W + 2;
+  for (int i = threadIdx.x; i < 12 * PW; i += blockDim.x) {
+    const int c = i / (3 * PW), r = (i / PW) % 3, xx = i % PW;
+    const int yy = y + r - 1, xs = xx - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = __ldg(x + ((static_cast<size_t>(b) * 4 + c) * H + yy) * W + xs);
+    sp[i] = v;
+  }
+  __syncthreads();
+  const int nv = Cout >> 3;
+  for (int item = threadIdx.x; item < W * nv; item += blockDim.x) {
+    const int px = item / nv, cv = item % nv;
+    float acc[8];
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2 + 1);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float xv = sp[(c * 3 + r) * PW + px + d];
+          const float4 w0 = reinterpret_cast<const float4*>(sw + (c * 9 + r * 3 + d) * Cout)[cv * 2];
+          const float4 w1 = reinterpret_cast<const float4*>(sw + (c * 9 + r * 3 + d) * Cout)[cv * 2 + 1];
+          acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+          acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+        }
+    uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + y) * W + px) * Cout) + cv;
+    *op = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                     pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+cudaError_t conv_in_launch(const float* x, const float* w_packed, const float* bias, __nv_bfloat16* out, int B, int H,
+                           int W, int Cout, cudaStream_t s) {
+  if (Cout % 8) return cudaErrorInvalidValue;
+  const size_t smem = (static_cast<size_t>(36) * Cout + 12 * (W + 2)) * sizeof(float);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  conv_in_kernel<<<dim3(H, B), 256, smem, s>>>(x, w_packed, bias, out, H, W, Cout);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Philox4x32-10 + Box-Muller: counter-based N(0,1) keyed by (seed, step, global element) so that the
+// noise of a latent does not depend on how the batch is sharded over GPUs.
+// =====================================================================================================
+WD_DEVINL void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+WD_DEVINL float philox_normal(unsigned long long seed, unsigned long long elem, uint32_t step) {
+  uint32_t c[4] = {static_cast<uint32_t>(elem), static_cast<uint32_t>(elem >> 32), step, 0x5744u /*'WD'*/};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
+// =====================================================================================================
+// conv_out (3x3, C -> 4, HBM-bound on the activation read) fused with the sampler update:
+//   DDPM (train.py:229-236):  x <- 1/sqrt(a) * (x - (1-a)/sqrt(1-ah) * eps) + sqrt(b) * z
+//   DDIM eta=0             :  x0 = (x - sqrt(1-ah_t) eps) / sqrt(ah_t);  x <- sqrt(ah_p) x0 + sqrt(1-ah_p) eps
+// One CTA per image row, one warp per output pixel (lanes split the channels, coalesced 128 B reads).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) conv_out_step_kernel(const ConvOutArgs a) {
+  extern __shared__ float co_smem[];  // [9][C][4]
+  const int y = blockIdx.x, b = blockIdx.y;
+  const int C = a.C, H = a.H, W = a.W;
+  for (int i = threadIdx.x; i < 9 * C * 4; i += blockDim.x) co_smem[i] = __ldg(a.w_packed + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = C >> 1;
+  for (int px = warp; px < W; px += (blockDim.x >> 5)) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const uint32_t* hp = reinterpret_cast<const uint32_t*>(a.h + ((static_cast<size_t>(b) * H + yy) * W + xx) * C);
+      const float4* wt = reinterpret_cast<const float4*>(co_smem + static_cast<size_t>(tap) * C * 4);
+      for (int pr = lane; pr < npairs; pr += 32) {
+        const float2 f = unpack_bf16x2(__ldg(hp + pr));
+        const float4 w0 = wt[2 * pr], w1 = wt[2 * pr + 1];
+        acc[0] += f.x * w0.x + f.y * w1.x;
+        acc[1] += f.x * w0.y + f.y * w1.y;
+        acc[2] += f.x * w0.z + f.y * w1.z;
+        acc[3] += f.x * w0.w + f.y * w1.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane < 4) {
+      const int o = lane;
+      const float eps = (o == 0 ? acc[0] : o == 1 ? acc[1] : o == 2 ? acc[2] : acc[3]) + __ldg(a.bias + o);
+      const size_t idx = ((static_cast<size_t>(b) * 4 + o) * H + y) * W + px;
+      if (a.eps_out) a.eps_out[idx] = eps;
+      if (a.mode == STEP_DDPM) {
+        float z = 0.f;
+        if (a.noise)
+          z = __ldg(a.noise + idx);
+        else if (a.use_philox)
+          z = philox_normal(a.seed, a.sample_offset * (4ull * H * W) + idx, static_cast<uint32_t>(a.step_index));
+        const float xv = a.x[idx];
+        // same op order as the reference expression, no FMA contraction
+        const float inner = __fsub_rn(xv, __fmul_rn(a.coef.y, eps));
+        a.x[idx] = __fadd_rn(__fmul_rn(a.coef.x, inner), __fmul_rn(a.coef.z, z));
+      } else if (a.mode == STEP_DDIM) {
+        const float xv = a.x[idx];
+        const float x0 = __fmul_rn(__fsub_rn(xv, __fmul_rn(a.coef.y, eps)), a.coef.x);
+        a.x[idx] = __fadd_rn(__fmul_rn(a.coef.z, x0), __fmul_rn(a.coef.w, eps));
+      }
+    }
+  }
+}
+
+cudaError_t conv_out_step_launch(const ConvOutArgs& a, cudaStream_t s) {
+  if (a.C % 2) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(9) * a.C * 4 * sizeof(float);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_out_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  conv_out_step_kernel<<<dim3(a.H, a.B), 256, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// nearest 2x upsample, NHWC bf16
+// =====================================================================================================
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * nv;
+  if (idx >= total) return;
+  const int v = idx % nv;
+  size_t p = idx / nv;
+  const int ox = p % (2 * W);
+  p /= (2 * W);
+  const int oy = p % (2 * H);
+  const int b = p / (2 * H);
+  out[idx] = __ldg(x + ((static_cast<size_t>(b) * H + (oy >> 1)) * W + (ox >> 1)) * nv + v);
+}
+cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// weight repacking
+// =====================================================================================================
+WD_DEVINL int geglu_perm(int n, int N, int bn) {
+  // rows [0, N/2) are values, [N/2, N) gates (torch chunk(2), unet.py:128).  Tile t of width bn holds
+  // values t*bn/2 .. in its first half and the matching gates in its second half.
+  const int half = bn / 2, Nh = N / 2;
+  const bool gate = n >= Nh;
+  const int j = gate ? n - Nh : n;
+  return (j / half) * bn + (gate ? half : 0) + (j % half);
+}
+
+__global__ void repack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
+                                      int ldk, int k_off) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(Cout) * Cin * 9;
+  if (idx >= total) return;
+  const int tap = idx % 9;
+  const int c = (idx / 9) % Cin;
+  const int n = idx / (9 * static_cast<size_t>(Cin));
+  dst[static_cast<size_t>(n) * ldk + k_off + tap * Cin + c] = __float2bfloat16(w[idx]);
+}
+cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off,
+                                  cudaStream_t s) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * 9;
+  repack_conv3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ldk, k_off);
+  return cudaGetLastError();
+}
+
+__global__ void repack_linear_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int N, int K,
+                                     int ldk, int k_off, int n_off, int geglu_bn) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(N) * K) return;
+  const int k = idx % K, n = idx / K;
+  const int nn = geglu_bn ? geglu_perm(n, N, geglu_bn) : n;
+  dst[static_cast<size_t>(nn + n_off) * ldk + k_off + k] = __float2bfloat16(w[idx]);
+}
+cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int K, int ldk, int k_off, int n_off,
+                                 int geglu_bn, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * K;
+  repack_linear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, N, K, ldk, k_off, n_off,
+                                                                                    geglu_bn);
+  return cudaGetLastError();
+}
+
+__global__ void repack_vec_kernel(const float* __restrict__ v, float* __restrict__ dst, int N, int n_off, int geglu_bn,
+                                  int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int nn = (geglu_bn ? geglu_perm(n, N, geglu_bn) : n) + n_off;
+  dst[nn] = accumulate ? dst[nn] + v[n] : v[n];
+}
+cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
+                              cudaStream_t s) {
+  repack_vec_kernel<<<(N + 255) / 256, 256, 0, s>>>(v, dst, N, n_off, geglu_bn, accumulate);
+  return cudaGetLastError();
+}
+
+__global__ void repack_conv_in_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin * 9) return;
+  const int k = idx % (Cin * 9), n = idx / (Cin * 9);
+  dst[k * Cout + n] = w[idx];
+}
+cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s) {
+  const int total = Cout * Cin * 9;
+  repack_conv_in_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cin);
+  return cudaGetLastError();
+}
+
+__global__ void repack_conv_out_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * C * 9) return;
+  const int tap = idx % 9, c = (idx / 9) % C, o = idx / (9 * C);
+  dst[(tap * C + c) * Cout + o] = w[idx];
+}
+cudaError_t repack_conv_out_launch(const float* w, float* dst, int Cout, int C, cudaStream_t s) {
+  const int total = Cout * C * 9;
+  repack_conv_out_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, C);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// fp32 context encoder (time-invariant; runs once per trajectory).  Kept in fp32 because the reference's
+// Word_Attention softmax is unscaled (unet.py:831-832) and therefore close to one-hot.
+// =====================================================================================================
+__global__ void embed_tokens_kernel(const void* __restrict__ tokens, int is_i64, const float* __restrict__ E, int vocab,
+                                    const float* __restrict__ pe, int add_pe, float* __restrict__ out, int B, int L,
+                                    int D) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * L * D) return;
+  const int d = idx % D;
+  const size_t bl = idx / D;
+  const int l = bl % L;
+  long long tok = is_i64 ? static_cast<const long long*>(tokens)[bl] : static_cast<const int*>(tokens)[bl];
+  if (tok < 0 || tok >= vocab) __trap();  // nn.Embedding raises on out-of-range ids
+  float v = __ldg(E + tok * D + d);
+  if (add_pe) v += __ldg(pe + static_cast<size_t>(l) * D + d);
+  out[idx] = v;
+}
+cudaError_t embed_tokens_launch(const void* tokens, int tokens_are_i64, const float* E, int vocab, const float* pe,
+                                int add_pe, float* out, int B, int L, int D, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * L * D;
+  embed_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(tokens, tokens_are_i64, E, vocab, pe,
+                                                                                  add_pe, out, B, L, D);
+  return cudaGetLastError();
+}
+
+// 64x64 output tile, 256 threads, 4x4 outputs per thread, K tile 16.
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int M, int N, int K) {
+  __shared__ float sx[16][64 + 1];
+  __shared__ float sw[16][64 + 1];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i / 16, kk = i % 16;
+      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+      sx[kk][r] = (m < M && k < K) ? __ldg(x + static_cast<size_t>(m) * K + k) : 0.f;
+      sw[kk][r] = (n < N && k < K) ? __ldg(Wt + static_cast<size_t>(n) * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float xa[4], wb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xa[i] = sx[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wb[j] = sw[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += xa[i] * wb[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) out[static_cast<size_t>(m) * N + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+    }
+  }
+}
+cudaError_t linear_f32_launch(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
+                              cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  linear_f32_kernel<<<grid, 256, 0, s>>>(x, W, b, out, M, N, K);
+  return cudaGetLastError();
+}
+
+// One warp per query row; scores kept in shared memory; unscaled softmax(q k^T) v.
+__global__ void __launch_bounds__(128) word_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                        const float* __restrict__ v, __nv_bfloat16* __restrict__ ctx,
+                                                        float* __restrict__ ctx_f32, int L, int D, int Ltot,
+                                                        int row_off) {
+  extern __shared__ float wa_smem[];  // [4][L] scores + [4][D] query
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int qi = blockIdx.x * 4 + warp;
+  if (qi >= L) return;
+  float* sc = wa_smem + warp * L;
+  float* sq = wa_smem + 4 * L + warp * D;
+  const float* qr = q + (static_cast<size_t>(b) * L + qi) * D;
+  for (int d = lane; d < D; d += 32) sq[d] = __ldg(qr + d);
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = 0; j < L; ++j) {
+    const float* kr = k + (static_cast<size_t>(b) * L + j) * D;
+    float dsum = 0.f;
+    for (int d = lane; d < D; d += 32) dsum += sq[d] * __ldg(kr + d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) sc[j] = dsum;
+    mx = fmaxf(mx, dsum);
+  }
+  __syncwarp();
+  float den = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    den += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  __syncwarp();
+  const float inv = 1.0f / den;
+  const size_t orow = (static_cast<size_t>(b) * Ltot + row_off + qi) * D;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    float acc = 0.f;
+    if (d < D) {
+      for (int j = 0; j < L; ++j) acc += sc[j] * __ldg(v + (static_cast<size_t>(b) * L + j) * D + d);
+      acc *= inv;
+      if (ctx) ctx[orow + d] = __float2bfloat16(acc);
+      if (ctx_f32) ctx_f32[orow + d] = acc;
+    }
+  }
+}
+cudaError_t word_attn_launch(const float* q, const float* k, const float* v, __nv_bfloat16* ctx_out, float* ctx_out_f32,
+                             int B, int L, int D, int Ltot, int row_off, cudaStream_t s) {
+  const size_t smem = (static_cast<size_t>(4) * L + 4 * D) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  dim3 grid((L + 3) / 4, B);
+  word_attn_kernel<<<grid, 128, smem, s>>>(q, k, v, ctx_out, ctx_out_f32, L, D, Ltot, row_off);
+  return cudaGetLastError();
+}
+
+}  // namespace wd

@@ -1,0 +1,112 @@
+// Non-GEMM kernels of the WordDiffusion hot path (HBM / latency bound work).  See ops.cu.
+#pragma once
+#include "common.cuh"
+
+namespace wd {
+
+// ---------------- GroupNorm (+SiLU), NHWC bf16 -> NHWC bf16 (reference unet.py:429-431,161-162) ----------------
+struct GroupNormArgs {
+  const __nv_bfloat16* x[2];  // per channel slab: source tensor (already offset to its first channel)
+  int x_ld[2];                // pixel stride (elements) of each source
+  __nv_bfloat16* out;         // [B, HW, out_ld]; slab s writes channels [s*Cs, (s+1)*Cs)
+  int out_ld;
+  const float* gamma;  // [nslab*Cs]
+  const float* beta;
+  int HW;
+  int Cs;   // channels per slab (multiple of 8, contains whole groups)
+  int cpg;  // channels per group
+  float eps;
+  int silu;
+};
+cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
+
+// ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------
+cudaError_t layernorm_launch(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta, int M,
+                             int C, float eps, cudaStream_t s);
+
+// ---------------- attention with a short key/value sequence (char context, L <= 16), unet.py:185-279 ----------------
+struct AttnSmallArgs {
+  const __nv_bfloat16* q;  // [B, Sq, q_ld]
+  int q_ld;
+  const __nv_bfloat16* k;  // [B, L, kv_ld]
+  const __nv_bfloat16* v;
+  int kv_ld;
+  __nv_bfloat16* out;  // [B, Sq, out_ld]
+  int out_ld;
+  float* probs;  // optional [B, heads, Sq, L] fp32 (attention maps), may be null
+  int Sq, L, heads;
+  float scale;
+};
+cudaError_t attn_small_launch(const AttnSmallArgs& a, int B, cudaStream_t s);
+
+// ---------------- flash-style attention, general Skv (self-attention 256/64 tokens, PHOSC context 779) ----------------
+struct AttnFlashArgs {
+  const __nv_bfloat16* q;  // [B, Sq, q_ld]
+  int q_ld;
+  const __nv_bfloat16* k;  // [B, Skv, kv_ld]
+  const __nv_bfloat16* v;
+  int kv_ld;
+  __nv_bfloat16* out;
+  int out_ld;
+  int Sq, Skv, heads;
+  float scale;
+};
+cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s);
+
+// ---------------- sinusoidal timestep embedding (unet.py:96-116) ----------------
+// t_dev: per-sample int64 timesteps, or null -> every row uses t_scalar.  out bf16 [B, dim]
+cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __nv_bfloat16* out, int B, int dim,
+                                  cudaStream_t s);
+
+// ---------------- conv_in: 3x3, Cin=4 fp32 NCHW -> bf16 NHWC (unet.py:1251) ----------------
+cudaError_t conv_in_launch(const float* x, const float* w_packed /*[36][Cout]*/, const float* bias, __nv_bfloat16* out,
+                           int B, int H, int W, int Cout, cudaStream_t s);
+
+// ---------------- conv_out (3x3, C -> 4) fused with the sampler update (unet.py:1457; train.py:229-236) ----------------
+enum StepMode : int { STEP_EPS_ONLY = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
+struct ConvOutArgs {
+  const __nv_bfloat16* h;  // GN+SiLU'd activation, NHWC bf16 [B,H,W,C]
+  const float* w_packed;   // [9][C][4]
+  const float* bias;       // [4]
+  float* eps_out;          // fp32 NCHW [B,4,H,W] or null
+  float* x;                // fp32 NCHW latent, updated in place when mode != EPS_ONLY
+  const float* noise;      // fp32 NCHW or null
+  int use_philox;
+  unsigned long long seed;
+  unsigned long long sample_offset;  // global index of sample 0 of this shard (GPU-count invariant noise)
+  int step_index;
+  float4 coef;
+  int mode;
+  int B, H, W, C;
+};
+cudaError_t conv_out_step_launch(const ConvOutArgs& a, cudaStream_t s);
+
+// ---------------- nearest 2x upsample NHWC bf16 (unet.py:497) ----------------
+cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
+
+// ---------------- weight repacking (fp32 state_dict tensors -> packed bf16 / fp32 layouts) ----------------
+// conv3x3 weight [Cout, Cin, 3, 3] -> dst[n, k_off + tap*Cin + c]   (row stride ldk)
+cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off,
+                                  cudaStream_t s);
+// linear / 1x1 weight [N, K] -> dst[perm(n) + n_off, k_off + k]; geglu_bn > 0 applies the value/gate tile permutation
+cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int K, int ldk, int k_off, int n_off,
+                                 int geglu_bn, cudaStream_t s);
+// vector [N] -> dst[perm(n) + n_off] (accumulate: dst += src)
+cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
+                              cudaStream_t s);
+// conv_in weight [Cout,4,3,3] -> [36][Cout];  conv_out weight [4,C,3,3] -> [9][C][4]
+cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s);
+cudaError_t repack_conv_out_launch(const float* w, float* dst, int Cout, int C, cudaStream_t s);
+
+// ---------------- fp32 context encoder (unet.py:815-882) ----------------
+// tokens [B, L] (int64 or int32) -> emb[B, L, D] = E[token] (+ pe[l] when add_pe)
+cudaError_t embed_tokens_launch(const void* tokens, int tokens_are_i64, const float* E, int vocab, const float* pe,
+                                int add_pe, float* out, int B, int L, int D, cudaStream_t s);
+// out[m, n] = sum_k x[m,k] W[n,k] + b[n]   (fp32 SIMT)
+cudaError_t linear_f32_launch(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
+                              cudaStream_t s);
+// unscaled single-head softmax(Q K^T) V, fp32; writes bf16 ctx rows [b, row_off + l, :] of a [B, Ltot, D] tensor
+cudaError_t word_attn_launch(const float* q, const float* k, const float* v, __nv_bfloat16* ctx_out, float* ctx_out_f32,
+                             int B, int L, int D, int Ltot, int row_off, cudaStream_t s);
+
+}  // namespace wd

@@ -1,0 +1,194 @@
+"""Sampling / noising loops around the B200 UNet engine -- the host side of reference ``train.Diffusion``
+(train.py:174-251; keyword-correct variant trainModifyCondition.py:545-622).
+
+What changes against the reference loop, and why:
+  * the per-step update ``x <- 1/sqrt(a)(x - (1-a)/sqrt(1-ah) eps) + sqrt(b) z`` (train.py:229-236) runs inside the
+    epilogue of the UNet's output convolution (``wd_sampler_step``): no separate elementwise kernels, no H2D copy of ``t``;
+  * the character / PHOSC context and every cross-attention K/V projection are encoded once per trajectory
+    (they do not depend on ``t``; the reference recomputes them every step);
+  * the reference evaluates the UNet twice per step and lerps the two identical results (train.py:223-228,
+    ``torch.lerp(u, u, w) == u``): one evaluation is made here;
+  * noise is either supplied by the caller (parity runs) or drawn in-kernel from Philox keyed by
+    (seed, step, global latent index), so a latent's trajectory does not depend on the number of GPUs.
+"""
+import numpy as np
+import torch
+
+from ._lib import STEP_DDIM, STEP_DDPM
+
+MAX_CHARS = 10
+C_CLASSES = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
+LETTER2INDEX = {c: i for i, c in enumerate(C_CLASSES)}
+PAD_TOKEN = 52
+NUM_TOKENS = 1
+
+
+def label_padding(labels, num_tokens=NUM_TOKENS, max_len=MAX_CHARS):
+    """train.py:42-52: letters -> index + num_tokens, right-padded with PAD_TOKEN (52) to ``max_len``.
+    (As in the reference, 'z' -> 51 + 1 collides with the PAD id.)"""
+    ll = [LETTER2INDEX[c] + num_tokens for c in labels]
+    if len(ll) > max_len:
+        raise ValueError(f"word '{labels}' is longer than {max_len} characters")
+    return ll + [PAD_TOKEN] * (max_len - len(ll))
+
+
+class Diffusion:
+    def __init__(self, noise_steps=1000, beta_start=1e-4, beta_end=0.02, img_size=(64, 256), args=None, device=None):
+        self.noise_steps = noise_steps
+        self.beta_start = beta_start
+        self.beta_end = beta_end
+        self.device = torch.device(device if device is not None else (args.device if args is not None else "cuda:0"))
+        self.beta = self.prepare_noise_schedule().to(self.device)
+        self.alpha = 1.0 - self.beta
+        self.alpha_hat = torch.cumprod(self.alpha, dim=0)
+        self.img_size = img_size
+        # host copies of the per-step coefficients, computed with the same fp32 torch ops as train.py:229-236
+        a, ah, b = self.alpha.cpu(), self.alpha_hat.cpu(), self.beta.cpu()
+        self._ddpm_coef = torch.stack([1 / torch.sqrt(a), (1 - a) / torch.sqrt(1 - ah), torch.sqrt(b),
+                                       torch.zeros_like(a)], dim=1).numpy()
+        self._ah64 = ah.double().numpy()
+
+    def prepare_noise_schedule(self):
+        return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
+
+    def noise_images(self, x, t):
+        """train.py:190-194."""
+        sqrt_alpha_hat = torch.sqrt(self.alpha_hat[t])[:, None, None, None]
+        sqrt_one_minus_alpha_hat = torch.sqrt(1 - self.alpha_hat[t])[:, None, None, None]
+        eps = torch.randn_like(x)
+        return sqrt_alpha_hat * x + sqrt_one_minus_alpha_hat * eps, eps
+
+    def sample_timesteps(self, n):
+        """train.py:196-197."""
+        return torch.randint(low=1, high=self.noise_steps, size=(n,))
+
+    # ------------------------------------------------------------------ latent-space samplers (the hot path)
+    def _prepare(self, model, context, labels, phosc, n):
+        eng = model.engine(self.device, latent_hw=(self.img_size[0] // 8, self.img_size[1] // 8))
+        eng.encode_context(context, phosc if model._phosc_len() else None)
+        y = labels.to(device=self.device, dtype=torch.int64).contiguous() if labels is not None else None
+        if y is not None and y.shape[0] != n:
+            y = y[:n].contiguous()
+        return eng, y
+
+    @torch.no_grad()
+    def sample_latents(self, model, context, labels, phosc=None, x_T=None, noise=None, seed=0, sample_offset=0,
+                       return_eps_trace=False, on_step=None):
+        """DDPM ancestral sampling of latents (train.py:217-236), i = T-1 .. 1, one fused UNet+update launch
+        sequence per step.  ``noise``: optional [T, n, 4, h, w] tensor, ``noise[i]`` is used at step i (parity runs);
+        otherwise in-kernel Philox(seed).  Returns x_0-scale latents (before the 1/0.18215 VAE rescale)."""
+        n = context.shape[0]
+        eng, y = self._prepare(model, context, labels, phosc, n)
+        h, w = self.img_size[0] // 8, self.img_size[1] // 8
+        if x_T is None:
+            g = torch.Generator(device=self.device).manual_seed(int(seed))
+            x = torch.randn((n, 4, h, w), device=self.device, generator=g)
+        else:
+            x = x_T.to(device=self.device, dtype=torch.float32).clone().contiguous()
+        trace = [] if return_eps_trace else None
+        for i in reversed(range(1, self.noise_steps)):
+            z = None
+            if noise is not None and i > 1:
+                z = noise[i].to(device=self.device, dtype=torch.float32).contiguous()
+            eps_out = torch.empty_like(x) if return_eps_trace else None
+            eng.sampler_step(x, i, y, STEP_DDPM, self._ddpm_coef[i], noise=z,
+                             philox_seed=(seed if (noise is None and i > 1) else None),
+                             sample_offset=sample_offset, step_index=i, eps_out=eps_out)
+            if return_eps_trace:
+                trace.append(eps_out)
+            if on_step is not None:
+                on_step(i, x)
+        return (x, trace) if return_eps_trace else x
+
+    def ddim_timesteps(self, num_steps):
+        stride = self.noise_steps // num_steps
+        return list(range(0, self.noise_steps, stride))[:num_steps][::-1]
+
+    def ddim_coef(self, t, t_prev):
+        a_t = self._ah64[t]
+        a_p = self._ah64[t_prev] if t_prev >= 0 else 1.0
+        return np.array([1.0 / np.sqrt(a_t), np.sqrt(1 - a_t), np.sqrt(a_p), np.sqrt(1 - a_p)], dtype=np.float32)
+
+    @torch.no_grad()
+    def ddim_sample_latents(self, model, context, labels, phosc=None, num_steps=50, x_T=None, seed=0):
+        """Deterministic DDIM (eta = 0) over ``num_steps`` evenly strided timesteps of the reference schedule.
+        Not present in the reference; specified by oracle/diffusion_oracle.py."""
+        n = context.shape[0]
+        eng, y = self._prepare(model, context, labels, phosc, n)
+        h, w = self.img_size[0] // 8, self.img_size[1] // 8
+        if x_T is None:
+            g = torch.Generator(device=self.device).manual_seed(int(seed))
+            x = torch.randn((n, 4, h, w), device=self.device, generator=g)
+        else:
+            x = x_T.to(device=self.device, dtype=torch.float32).clone().contiguous()
+        ts = self.ddim_timesteps(num_steps)
+        for k, t in enumerate(ts):
+            t_prev = ts[k + 1] if k + 1 < len(ts) else -1
+            eng.sampler_step(x, t, y, STEP_DDIM, self.ddim_coef(t, t_prev), step_index=k)
+        return x
+
+    # ------------------------------------------------------------------ reference-shaped entry point
+    @torch.no_grad()
+    def sampling(self, model, vae, n, x_text, labels, args=None, mix_rate=None, cfg_scale=3, phosc=None, seed=0):
+        """Same call shape as train.Diffusion.sampling (train.py:200-251).  The VAE decode at the end is outside the hot
+        path: with ``vae=None`` the scaled latents ``x / 0.18215`` are returned instead of images."""
+        if mix_rate is not None:
+            raise NotImplementedError("style interpolation (mix_rate) is not implemented")
+        toks = torch.tensor([label_padding(x_text)] * n, dtype=torch.int64, device=self.device)
+        x = self.sample_latents(model, toks, labels, phosc=phosc, seed=seed)
+        latents = 1 / 0.18215 * x
+        if vae is None:
+            return latents
+        image = vae.decode(latents).sample
+        image = (image / 2 + 0.5).clamp(0, 1)
+        return image
+
+    # ------------------------------------------------------------------ multi-GPU: shard the batch, gather the latents
+    @torch.no_grad()
+    def sample_latents_sharded(self, model, context, labels, phosc=None, seed=0, ddim_steps=None, group=None):
+        """Every rank holds the full conditioning [N, ...]; rank r samples the contiguous slice r of the batch and one
+        all-gather returns all N latents on every rank.  Philox noise is keyed by the *global*
+        latent index, so the result does not depend on the world size."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        N = context.shape[0]
+        lo, hi = shard_bounds(N, world, rank)
+        ph = phosc[lo:hi] if phosc is not None else None
+        lab = labels[lo:hi] if labels is not None else None
+        if ddim_steps:
+            # x_T must also be independent of the sharding: draw it from the same counter-based stream
+            xT = philox_like_normal((N, 4, self.img_size[0] // 8, self.img_size[1] // 8), seed, self.device)[lo:hi]
+            x = self.ddim_sample_latents(model, context[lo:hi], lab, phosc=ph, num_steps=ddim_steps, x_T=xT)
+        else:
+            xT = philox_like_normal((N, 4, self.img_size[0] // 8, self.img_size[1] // 8), seed, self.device)[lo:hi]
+            x = self.sample_latents(model, context[lo:hi], lab, phosc=ph, x_T=xT, seed=seed, sample_offset=lo)
+        return all_gather_latents(x, N, world, group)
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous, balanced split of ``n`` latents over ``world`` ranks (first ``n % world`` ranks get one more)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def philox_like_normal(shape, seed, device):
+    """Initial noise that is a pure function of (seed, global index): generated for the full batch on every rank."""
+    g = torch.Generator(device="cpu").manual_seed(int(seed))
+    return torch.randn(shape, generator=g).to(device)
+
+
+def all_gather_latents(x_local, n_total, world, group=None):
+    """One collective per trajectory: all-gather of the [n/world, 4, h, w] fp32 shards (NCCL on GPUs, gloo in tests)."""
+    import torch.distributed as dist
+    if world == 1 or not dist.is_initialized():
+        return x_local
+    sizes = [shard_bounds(n_total, world, r) for r in range(world)]
+    max_n = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_n,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    pad[: x_local.shape[0]] = x_local
+    out = torch.empty((world * max_n,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = [out[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,147 @@
+"""Python handle of the C++ engine (``csrc/engine.cu``): owns one ``wd_engine``, keeps its packed weights in sync
+with the ``nn.Module`` parameters and forwards the hot-path calls through ctypes.  PyTorch is only used for device
+memory and streams here."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import WdConfig, check, lib
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class HotPathEngine:
+    def __init__(self, *, variant, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 channel_mult, num_heads, num_head_channels, transformer_depth, context_dim, vocab_size, num_classes,
+                 max_seq_len, latent_hw, add_label_emb, phosc_len, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WdError("worddiffusion_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        cfg = WdConfig()
+        cfg.variant = variant
+        cfg.in_channels, cfg.model_channels, cfg.out_channels = in_channels, model_channels, out_channels
+        cfg.num_res_blocks = num_res_blocks
+        cfg.n_channel_mult = len(channel_mult)
+        for i, m in enumerate(channel_mult):
+            cfg.channel_mult[i] = int(m)
+        ar = sorted(set(int(a) for a in attention_resolutions))
+        cfg.n_attention_resolutions = len(ar)
+        for i, a in enumerate(ar):
+            cfg.attention_resolutions[i] = a
+        cfg.num_heads, cfg.num_head_channels = num_heads, num_head_channels
+        cfg.transformer_depth = transformer_depth
+        cfg.context_dim, cfg.vocab_size = context_dim, vocab_size
+        cfg.num_classes = num_classes or 0
+        cfg.max_seq_len = max_seq_len
+        cfg.latent_h, cfg.latent_w = latent_hw
+        cfg.add_label_emb = 1 if add_label_emb else 0
+        cfg.phosc_len = phosc_len
+        self.cfg = cfg
+        self.latent_hw = tuple(latent_hw)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().wd_engine_create(C.byref(cfg), C.byref(self._h)), "wd_engine_create")
+        self._weights_sig = None
+        self._ctx_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().wd_engine_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    @staticmethod
+    def weights_signature(named_params):
+        return tuple((p.data_ptr(), p._version) for _, p in named_params)
+
+    def load_state(self, named_tensors, pos_encoding):
+        """named_tensors: iterable of (state_dict key, tensor).  Repacks every tensor the forward reads."""
+        l = lib()
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr()
+            keep = []
+            for name, t in named_tensors:
+                src = t.detach()
+                if src.device != self.device or src.dtype != torch.float32 or not src.is_contiguous():
+                    src = src.to(device=self.device, dtype=torch.float32).contiguous()
+                keep.append(src)
+                shape = (C.c_int64 * max(src.dim(), 1))(*src.shape)
+                check(l.wd_engine_load_param(self._h, name.encode(), _ptr(src), shape, src.dim(), sp),
+                      f"load_param({name})")
+            pe = pos_encoding.to(device=self.device, dtype=torch.float32).contiguous()
+            check(l.wd_engine_set_pos_encoding(self._h, _ptr(pe), sp), "set_pos_encoding")
+            missing = l.wd_engine_finalize_params(self._h, sp)
+            if missing != 0:
+                msg = l.wd_last_error()
+                raise _lib.WdError(f"state_dict incomplete for the engine: {msg.decode() if msg else missing}")
+            torch.cuda.current_stream().synchronize()  # staging copies in `keep` may be freed after this
+        self._ctx_key = None
+
+    # ------------------------------------------------------------------ hot path
+    def encode_context(self, context, phosc=None):
+        """context: int64 [B, L] token ids; phosc: [B, 769] (any numeric dtype) or None."""
+        B, L = context.shape
+        ctx = context.to(device=self.device, dtype=torch.int64).contiguous()
+        ph = None
+        if self.cfg.phosc_len > 0:
+            if phosc is None:
+                raise _lib.WdError("this model needs phoscLabels")
+            ph = phosc.to(self.device).int().contiguous()  # reference: phoscLabels.int() (unetPhosc.py:1124)
+            if ph.shape != (B, self.cfg.phosc_len):
+                raise _lib.WdError(f"phoscLabels must be [{B}, {self.cfg.phosc_len}], got {tuple(ph.shape)}")
+        with torch.cuda.device(self.device):
+            check(lib().wd_encode_context(self._h, B, _ptr(ctx), L, _ptr(ph), _stream_ptr()), "wd_encode_context")
+        self._ctx_hold = (ctx, ph)
+        self._ctx_key = B
+
+    def unet_eval(self, x, timesteps, y, out=None):
+        B = x.shape[0]
+        if out is None:
+            out = torch.empty_like(x)
+        t_ptr, t_scalar = C.c_void_p(0), 0
+        if isinstance(timesteps, int):
+            t_scalar = timesteps
+        else:
+            timesteps = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
+            t_ptr = _ptr(timesteps)
+        with torch.cuda.device(self.device):
+            check(lib().wd_unet_eval(self._h, B, _ptr(x), t_ptr, t_scalar, _ptr(y), _ptr(out), _stream_ptr()),
+                  "wd_unet_eval")
+        return out
+
+    def sampler_step(self, x, t, y, mode, coef, noise=None, philox_seed=None, sample_offset=0, step_index=0,
+                     eps_out=None):
+        B = x.shape[0]
+        c4 = (C.c_float * 4)(*[float(v) for v in coef])
+        use_philox = 1 if (noise is None and philox_seed is not None) else 0
+        with torch.cuda.device(self.device):
+            check(lib().wd_sampler_step(self._h, B, _ptr(x), int(t), _ptr(y), mode, c4, _ptr(noise), use_philox,
+                                        int(philox_seed or 0), int(sample_offset), int(step_index), _ptr(eps_out),
+                                        _stream_ptr()), "wd_sampler_step")
+        return x
+
+    def reserve(self, batch):
+        with torch.cuda.device(self.device):
+            check(lib().wd_engine_reserve(self._h, batch), "wd_engine_reserve")
+
+    @property
+    def last_launch_count(self):
+        return lib().wd_engine_last_launch_count(self._h)
+
+    @property
+    def workspace_bytes(self):
+        return lib().wd_engine_workspace_bytes(self._h)
+
+    @property
+    def weight_bytes(self):
+        return lib().wd_engine_weight_bytes(self._h)

@@ -1,0 +1,134 @@
+"""Shared shell of the drop-in UNet modules: reference constructor arguments in, reference ``state_dict`` layout
+out, forward pass delegated to the sm_100a engine."""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .engine import HotPathEngine
+from .modules import CharacterEncoder, add_blocks
+
+
+def default_args(device="cuda:0", **over):
+    """The ``args`` namespace the reference constructors read (unet.py:1209-1217,1336,1468 / unetPhosc.py:1120)."""
+    ns = SimpleNamespace(device=device, interpolation=False, charLevelEmb=0, charImages=0, attentionMaps=0,
+                         ocrTraining=0, imgConditioned=0, wrdChrWrStyl=0, phosc=1, phos=0)
+    for k, v in over.items():
+        setattr(ns, k, v)
+    return ns
+
+
+class UNetBase(nn.Module):
+    VARIANT = None
+    PHOSC_LEN = 769  # 165 PHOS + 604 PHOC entries (ResPhoSCNetZSL/modules/utils/phos_generator.py:70-78, phoc_generator.py:78-90)
+
+    def _init_common(self, image_size, in_channels, model_channels, out_channels, num_res_blocks,
+                     attention_resolutions, dropout, channel_mult, conv_resample, dims, num_classes, use_checkpoint,
+                     use_fp16, num_heads, num_head_channels, num_heads_upsample, use_scale_shift_norm,
+                     resblock_updown, use_new_attention_order, use_spatial_transformer, transformer_depth,
+                     context_dim, vocab_size, n_embed, legacy, args, max_seq_len):
+        # ---- what the sm_100a path implements; everything else fails loudly (no silent fallback) ----
+        unsupported = []
+        if dims != 2: unsupported.append("dims != 2")
+        if not use_spatial_transformer: unsupported.append("use_spatial_transformer=False (AttentionBlock)")
+        if use_scale_shift_norm: unsupported.append("use_scale_shift_norm")
+        if resblock_updown: unsupported.append("resblock_updown")
+        if not conv_resample: unsupported.append("conv_resample=False")
+        if use_fp16: unsupported.append("use_fp16")
+        if n_embed is not None: unsupported.append("n_embed (id_predictor head)")
+        if legacy: unsupported.append("legacy")
+        if dropout: unsupported.append("dropout > 0")
+        if isinstance(context_dim, (list, tuple)): unsupported.append("per-level context_dim list")
+        if context_dim is None: unsupported.append("context_dim=None")
+        if args is None: unsupported.append("args=None")
+        if unsupported:
+            raise NotImplementedError("worddiffusion_b200 does not implement: " + ", ".join(unsupported))
+        if num_heads == -1 and num_head_channels == -1:
+            raise AssertionError("Either num_heads or num_head_channels has to be set")
+        self.args = args
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = tuple(attention_resolutions)
+        self.dropout = dropout
+        self.channel_mult = tuple(channel_mult)
+        self.conv_resample = conv_resample
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads if num_heads_upsample == -1 else num_heads_upsample
+        self.predict_codebook_ids = False
+        self.transformer_depth = transformer_depth
+        self.context_dim = context_dim
+        self.vocab_size = vocab_size
+        self.max_seq_len = max_seq_len
+        self.interpolation = args.interpolation
+        if self.interpolation:
+            raise NotImplementedError("worddiffusion_b200 does not implement args.interpolation (random style mixing)")
+        self._engine = None
+        self._engine_sig = None
+
+    def _build_tree(self, extra_before_blocks=None):
+        mc = self.model_channels
+        ted = mc * 4
+        self.time_embed = nn.Sequential(nn.Linear(mc, ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.word_emb = CharacterEncoder(self.vocab_size, self.context_dim, self.max_seq_len)
+        if extra_before_blocks is not None:
+            extra_before_blocks()
+        if self.num_classes is not None:
+            self.label_emb = nn.Embedding(self.num_classes, ted)
+        add_blocks(self, in_channels=self.in_channels, model_channels=mc, out_channels=self.out_channels,
+                   num_res_blocks=self.num_res_blocks, attention_resolutions=self.attention_resolutions,
+                   channel_mult=self.channel_mult, num_heads=self.num_heads,
+                   num_head_channels=self.num_head_channels, transformer_depth=self.transformer_depth,
+                   context_dim=self.context_dim, ted=ted)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _add_label_emb(self):
+        return self.num_classes is not None
+
+    def _phosc_len(self):
+        return 0
+
+    def engine(self, device=None, latent_hw=None):
+        """The B200 engine bound to this module's parameters (created / re-synchronised lazily)."""
+        p0 = next(self.parameters())
+        device = torch.device(device) if device is not None else p0.device
+        if device.type != "cuda":
+            raise _lib.WdError("worddiffusion_b200 has no CPU path: move the model and its inputs to a CUDA (B200) device")
+        latent_hw = tuple(latent_hw) if latent_hw is not None else (8, 32)
+        if self._engine is None or self._engine.device != device or self._engine.latent_hw != latent_hw:
+            self._engine = HotPathEngine(
+                variant=self.VARIANT, in_channels=self.in_channels, model_channels=self.model_channels,
+                out_channels=self.out_channels, num_res_blocks=self.num_res_blocks,
+                attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
+                num_heads=self.num_heads, num_head_channels=self.num_head_channels,
+                transformer_depth=self.transformer_depth, context_dim=self.context_dim, vocab_size=self.vocab_size,
+                num_classes=self.num_classes, max_seq_len=self.max_seq_len, latent_hw=latent_hw,
+                add_label_emb=self._add_label_emb(), phosc_len=self._phosc_len(), device=device)
+            self._engine_sig = None
+        sig = HotPathEngine.weights_signature(self.named_parameters())
+        if sig != self._engine_sig:
+            self._engine.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
+            self._engine_sig = sig
+        return self._engine
+
+    def _run(self, x, timesteps, context, y, phosc):
+        if context is None:
+            raise NotImplementedError("worddiffusion_b200 needs the character context (context=None is not implemented)")
+        if x.device.type != "cuda":
+            raise _lib.WdError("worddiffusion_b200 has no CPU path: inputs must live on a CUDA (B200) device")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise AssertionError(f"x must be [B, {self.in_channels}, H, W], got {tuple(x.shape)}")
+        eng = self.engine(x.device, latent_hw=x.shape[2:])
+        xin = x.to(torch.float32).contiguous()
+        if y is not None:
+            y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        eng.encode_context(context, phosc)
+        out = eng.unet_eval(xin, timesteps, y)
+        return out.type(x.dtype)
