@@ -1,0 +1,112 @@
+"""CPU: host-side mirror of the reference interface -- state_dict layout, constructor checks, tokenisation, sharding and
+the world_size-2 gather (gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import weights as W
+from worddiffusion_b200 import diffusion as D
+from worddiffusion_b200.unet import UNetModel, default_args
+from worddiffusion_b200.unetPhosc import UNetModelPhosc
+from worddiffusion_b200.unetPhosc2 import UNetModelPhosc as UNetModelPhosc2
+
+KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+          attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_classes=339, context_dim=320,
+          vocab_size=53, max_seq_len=10)
+
+
+@pytest.mark.parametrize("cls,variant", [(UNetModel, "unet"), (UNetModelPhosc, "unetPhosc"), (UNetModelPhosc2, "unetPhosc")])
+def test_state_dict_layout_matches_reference(cls, variant):
+    """Same keys, same order, same shapes as the reference modules (spec dumped from them by oracle/make_golden.py)."""
+    m = cls(args=default_args("cpu"), **KW)
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == W.load_spec(variant)
+    sd = W.make_state_dict(W.load_spec(variant))
+    m.load_state_dict(sd, strict=True)  # regenerateFromtrain2.py:1214 loads strict=True
+
+
+def test_fresh_model_has_reference_zero_init():
+    m = UNetModel(args=default_args("cpu"), **KW)
+    sd = m.state_dict()
+    for k in ("out.2.weight", "out.2.bias", "input_blocks.1.0.out_layers.3.weight", "input_blocks.1.1.proj_out.weight"):
+        assert float(sd[k].abs().max()) == 0.0, k  # zero_module, unet.py:152-158
+    assert float(sd["input_blocks.1.0.in_layers.2.weight"].abs().max()) > 0
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        UNetModel(args=default_args("cpu", attentionMaps=1), **KW)
+    with pytest.raises(NotImplementedError):
+        UNetModel(args=default_args("cpu"), **dict(KW, use_scale_shift_norm=True))
+    with pytest.raises(NotImplementedError):
+        UNetModelPhosc(args=default_args("cpu", interpolation=True), **KW)
+
+
+def test_label_padding_follows_reference():
+    # train.py:42-52: index + 1, padded with 52 to MAX_CHARS
+    assert D.label_padding("Ab") == [1, 28] + [52] * 8
+    assert D.label_padding("z")[0] == 52  # the reference's 'z'/PAD collision is preserved
+    with pytest.raises(ValueError):
+        D.label_padding("abcdefghijk")
+
+
+def test_shard_bounds_partition():
+    for n in (1, 7, 256, 1024, 1025):
+        for w in (1, 2, 4, 8):
+            spans = [D.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_schedule_and_coefficients():
+    d = D.Diffusion(noise_steps=1000, device="cpu")
+    assert d.beta.shape == (1000,)
+    i = 500
+    a, ah, b = d.alpha[i], d.alpha_hat[i], d.beta[i]
+    c = d._ddpm_coef[i]
+    assert c[0] == float(1 / torch.sqrt(a)) and c[1] == float((1 - a) / torch.sqrt(1 - ah)) and c[2] == float(torch.sqrt(b))
+    assert d.ddim_timesteps(50)[0] == 980 and d.ddim_timesteps(50)[-1] == 0
+    x = torch.randn(3, 4, 8, 32)
+    xt, eps = d.noise_images(x, torch.tensor([1, 10, 999]))
+    assert xt.shape == x.shape and eps.shape == x.shape
+    t = d.sample_timesteps(64)
+    assert int(t.min()) >= 1 and int(t.max()) <= 999
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_total * 4 * 8 * 32, dtype=torch.float32).reshape(n_total, 4, 8, 32)
+    lo, hi = D.shard_bounds(n_total, world, rank)
+    out = D.all_gather_latents(full[lo:hi].clone(), n_total, world)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_all_gather_latents_world2_gloo(n_total):
+    """The only collective on the sampling path: every rank ends with all N latents in global order (ragged split too)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -54,7 +54,8 @@ def build_library(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(run, jobs))
     if jobs or force or _stale(LIB_PATH, objs):
-        run([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart"])
+        # static cudart (nvcc default): the .so must not depend on a libcudart.so being on the loader path of the GPU box
+        run([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static"])
     return LIB_PATH
 
 
