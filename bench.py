@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the WordDiffusion denoising hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model unet|unetPhosc] [--batch B]
+
+A "step" is one DDPM denoising step of `Diffusion.sampling` (train.py:221-236) over one batch of synthetic latents:
+one conditional-UNet evaluation (unet.py:1499-1836) plus the sampler update, per GPU.  N = 1 workload: BASELINE.json
+configs[1] -- unet.UNetModel, batch 256 latents 4x8x32, bf16 tensor-core compute, fp32 sampler state.  N > 1: every rank
+runs its own batch of 256 (weak scaling, no per-step collective; one NCCL all-gather of the final latents closes the
+timed trajectory).
+
+`value` = latent-steps/s over all ranks with everything resident in HBM; `e2e` = the same through the drop-in
+nn.Module forward with HOST (pinned) inputs and a host read of the predicted noise every step.
+`--impl reference`: the reference's CPU path (the oracle port of it -- /root/reference cannot travel to the GPU box) on the
+host cores, bounded sample, same metric and unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "unet_denoise_latent_steps_per_sec"
+UNIT = "latent-steps/s"
+# algorithmic FLOPs per latent per UNet evaluation, step-dependent work only
+GFLOP_PER_LATENT = {"unet": 9.153, "unetPhosc": 10.559}
+MODEL_KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+                attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_classes=339, context_dim=320,
+                vocab_size=53, max_seq_len=10)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_throughput(model, seconds=12.0, batch=8, threads=None):
+    """The reference's CPU path (oracle port, fp32, torch CPU ops on `threads` host threads): latent-steps/s of
+    UNet evaluation + DDPM update on a bounded sample of the workload."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import unet_oracle as UO
+    import weights as W
+    from diffusion_oracle import DiffusionOracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    variant = "unet" if model == "unet" else "unetPhosc"
+    sd = W.make_state_dict(W.load_spec(variant), 1234)
+    inp = W.make_inputs(batch, seed=1234)
+    d = DiffusionOracle(1000)
+    x = inp["x"].clone()
+    phosc = inp["phosc"] if variant != "unet" else None
+    n, t0 = 0, None
+    i = 999
+    with torch.no_grad():
+        while True:
+            t = torch.full((batch,), i, dtype=torch.long)
+            # the reference re-encodes the context every step (unet.py:1626-1636): so does its port
+            eps = UO.unet_forward(sd, x, t, inp["context"], inp["y"], phosc=phosc, variant=variant)
+            x = d.ddpm_step(x, eps, i, torch.randn_like(x))
+            i -= 1
+            if t0 is None:       # first evaluation = warm-up
+                t0 = time.perf_counter()
+                continue
+            n += 1
+            el = time.perf_counter() - t0
+            if el >= seconds or i <= 1:
+                break
+    return dict(value=n * batch / el, unit=UNIT, cores=threads, kind="port",
+                sample=f"{n} DDPM steps of the {variant} oracle port at batch {batch} (fp32, torch CPU, {threads} threads, "
+                       f"{el:.1f} s), context re-encoded every step as in the reference")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 8
+    t0 = time.perf_counter()
+    cb = cpu_oracle_throughput(args.model, seconds=max(2.0, 3.0 * args.steps), batch=batch)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * batch / cb["value"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.model} DDPM denoise step (UNet eval + update), CPU oracle port of the reference, "
+                                  f"bounded sample batch {batch}", "batch_per_step": batch},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import weights as W
+    from worddiffusion_b200.diffusion import Diffusion, all_gather_latents
+    from worddiffusion_b200.unet import UNetModel, default_args
+    from worddiffusion_b200.unetPhosc import UNetModelPhosc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    B, K, Wm = args.batch, args.steps, args.warmup
+    variant = args.model
+    cls = UNetModel if variant == "unet" else UNetModelPhosc
+    model = cls(args=default_args(dev), **MODEL_KW)
+    model.load_state_dict(W.make_state_dict(W.load_spec(variant), 1234), strict=True)
+    model = model.to(dev).eval()
+    inp = W.make_inputs(B, seed=1234 + rank)
+    ctx = inp["context"].to(dev)
+    y = inp["y"].to(dev)
+    phosc = inp["phosc"].to(dev) if variant != "unet" else None
+    diff = Diffusion(noise_steps=1000, device=dev)
+    eng = model.engine(dev)
+    eng.encode_context(ctx, phosc)      # time-invariant conditioning: once per trajectory
+    x = inp["x"].to(dev).clone()
+    T = diff.noise_steps
+
+    def step(i, k):
+        eng.sampler_step(x, i, y, 1, diff._ddpm_coef[i], philox_seed=1234, sample_offset=rank * B, step_index=k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for k in range(Wm):
+        step(T - 1 - k, k)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    eng.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    ev0.record()
+    for k in range(K):
+        step(T - 1 - Wm - k, Wm + k)
+    if world > 1:
+        all_gather_latents(x, B * world, world)      # the trajectory's only collective
+    ev1.record()
+    barrier()
+    w1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop(w0, w1)
+    n_steps_prof, prof = eng.profile_read()
+    eng.set_profiling(False)
+    launches = eng.last_launch_count * K
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- end to end through the drop-in nn.Module with host buffers ----------------
+    hx = inp["x"].pin_memory()
+    ht = torch.full((B,), 500, dtype=torch.long).pin_memory()
+    hctx, hy = inp["context"].pin_memory(), inp["y"].pin_memory()
+    hph = inp["phosc"].pin_memory() if variant != "unet" else None
+    heps = torch.empty((B, 4, 8, 32), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dx = hx.to(dev, non_blocking=True)
+        dt = ht.to(dev, non_blocking=True)
+        dc = hctx.to(dev, non_blocking=True)
+        dy = hy.to(dev, non_blocking=True)
+        with torch.no_grad():
+            if variant == "unet":
+                e = model(dx, None, timesteps=dt, context=dc, y=dy)
+            else:
+                e = model(dx, hph.to(dev, non_blocking=True), timesteps=dt, context=dc, y=dy)
+        heps.copy_(e, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads heps on the host after every call
+
+    for _ in range(max(1, min(Wm, 3))):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = hx.numel() * 4 + ht.numel() * 8 + hctx.numel() * 8 + hy.numel() * 8 + (hph.numel() * 8 if hph is not None else 0)
+    d2h = heps.numel() * 4
+    e2e = {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms / K,
+           "api": "worddiffusion_b200.%s forward(x, timesteps, context, y) with pinned host tensors; context re-encoded "
+                  "per call" % ("unet.UNetModel" if variant == "unet" else "unetPhosc.UNetModelPhosc")}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline from the per-launch device times ----------------
+    peaks = load_peaks()
+    cls_t, cls_f, cls_b, cls_n = {}, {}, {}, {}
+    for kind, fl, by, msum in prof:
+        cls_t[kind] = cls_t.get(kind, 0.0) + msum / max(n_steps_prof, 1)
+        cls_f[kind] = cls_f.get(kind, 0.0) + fl
+        cls_b[kind] = cls_b.get(kind, 0.0) + by
+        cls_n[kind] = cls_n.get(kind, 0) + 1
+    total_t = sum(cls_t.values())
+    kernels = {}
+    for kname in cls_t:
+        tms = cls_t[kname]
+        kernels[kname] = {"launches_per_step": cls_n[kname], "ms_per_step": round(tms, 4),
+                          "share": round(tms / total_t, 4) if total_t else None,
+                          "tflops": round(cls_f[kname] / (tms * 1e-3) / 1e12, 2) if tms > 0 else None,
+                          "gbs": round(cls_b[kname] / (tms * 1e-3) / 1e9, 1) if tms > 0 else None}
+    g = "gemm_tc"
+    ach = cls_f[g] / (cls_t[g] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM: 3x3 convs, 1x1 convs, linears)", "bound": "tensor",
+                "achieved": round(ach, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sust"], 4),
+                "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                "flops_per_launch_avg": cls_f[g] / cls_n[g], "launches_per_step": cls_n[g],
+                "avg_launch_ms": round(cls_t[g] / cls_n[g], 5), "share_of_step": kernels[g]["share"], "traffic": None}
+    step_tf = B * GFLOP_PER_LATENT[variant] * 1e9 / (ms / K * 1e-3) / 1e12
+
+    cb = cpu_oracle_throughput(variant, seconds=args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic",
+           "config": {"workload": f"{variant} DDPM sampling step (UNet eval + fused sampler update), batch {B} latents 4x8x32 "
+                                  "per GPU, random-init weights (oracle/weights.py seed 1234)",
+                      "batch_per_gpu": B, "global_batch": B * world, "noise_steps": 1000,
+                      "l2": "inputs larger than L2: %.1f GB activation arena per step vs 126 MB L2" % (eng.workspace_bytes / 1e9)},
+           "unet_steps_per_sec": K / (ms * 1e-3), "word_latents_per_sec_999_steps": value / 999.0,
+           "step_tflops": round(step_tf, 1), "step_frac_of_bf16_sustained": round(step_tf / peaks["tf_sust"], 4),
+           "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
+    if cb is not None:
+        out["cpu_baseline"] = cb
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="unet", choices=["unet", "unetPhosc"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,15 @@ size_t wd_engine_weight_bytes(const wd_engine* e);
 /* kernels launched by the most recent wd_unet_eval / wd_sampler_step / wd_encode_context call */
 int wd_engine_last_launch_count(const wd_engine* e);
 
+/* ---- per-op device timing (bench.py's roofline leg) -------------------------------------------------------
+ * While enabled, every wd_unet_eval / wd_sampler_step records CUDA events on `stream` around each kernel launch of the
+ * step (at most 256 steps are kept).  wd_engine_profile_read synchronises the device and returns, per launch of the
+ * step plan: its kernel class (0 timestep-embed, 1 tcgen05 GEMM/conv, 2 GroupNorm, 3 LayerNorm, 4 short-context
+ * attention, 5 flash attention, 6 conv_in, 7 conv_out+sampler update, 8 upsample), its algorithmic FLOPs and bytes,
+ * and the summed milliseconds over the recorded steps.  Returns the number of launches per step (or < 0). */
+int wd_engine_set_profiling(wd_engine* e, int enable);
+int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double* flops, double* bytes, float* ms_sum, int* n_steps);
+
 /* ---- the hot path ------------------------------------------------------------------------------------ */
 /* Time-invariant conditioning: CharacterEncoder (+PHOSC tokens) and the K/V projections of every
  * cross-attention (unet.py:1626-1636,839-882,180-183 ; unetPhosc.py:1117-1130).

@@ -37,6 +37,9 @@ SIGNATURES = {
     "wd_engine_workspace_bytes": (C.c_size_t, [_P]),
     "wd_engine_weight_bytes": (C.c_size_t, [_P]),
     "wd_engine_last_launch_count": (_I, [_P]),
+    "wd_engine_set_profiling": (_I, [_P, _I]),
+    "wd_engine_profile_read": (_I, [_P, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(_F), C.POINTER(_I)]),
     "wd_encode_context": (_I, [_P, _I, _P, _I, _P, _P]),
     "wd_unet_eval": (_I, [_P, _I, _P, _P, _I64, _P, _P, _P]),
     "wd_sampler_step": (_I, [_P, _I, _P, _I64, _P, _I, C.POINTER(_F), _P, _I, _U64, _U64, _I, _P, _P]),

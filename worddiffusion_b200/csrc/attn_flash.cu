@@ -13,9 +13,7 @@ namespace wd {
 namespace {
 constexpr int DH = 80;
 constexpr int BQ = 64;       // queries per CTA
-constexpr int BK = 64;       // keys per tile
 constexpr int KS = DH + 8;   // K smem row stride (bf16) -> conflict-free B-fragment loads
-constexpr int VS = BK + 8;   // Vt smem row stride (bf16)
 
 WD_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -25,7 +23,10 @@ WD_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0
 }
 }  // namespace
 
+// BK = keys per tile: 64 for long key sequences, 16 for the 10-token character context (one tile, no rescaling pass)
+template <int BK>
 __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnFlashArgs a) {
+  constexpr int VS = BK + 8;  // Vt smem row stride (bf16)
   __shared__ __align__(16) __nv_bfloat16 sK[BK * KS];
   __shared__ __align__(16) __nv_bfloat16 sVt[DH * VS];
 
@@ -158,7 +159,10 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnFlashArgs a) 
 cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s) {
   if (a.Sq < 1 || a.Skv < 1 || a.q_ld % 8 || a.kv_ld % 8 || a.out_ld % 2) return cudaErrorInvalidValue;
   dim3 grid((a.Sq + BQ - 1) / BQ, a.heads, B);
-  attn_flash_kernel<<<grid, 128, 0, s>>>(a);
+  if (a.Skv <= 16)
+    attn_flash_kernel<16><<<grid, 128, 0, s>>>(a);
+  else
+    attn_flash_kernel<64><<<grid, 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 

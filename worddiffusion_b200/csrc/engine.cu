@@ -123,6 +123,8 @@ enum Patch { P_NONE = 0, P_Y = 1 };
 struct Op {
   OpKind kind;
   int patch = P_NONE;
+  double flops = 0;  // algorithmic work of this launch ("algorithmic work per op")
+  double bytes = 0;
   GemmLaunch gemm;
   GroupNormArgs gn;
   int gn_B = 0, gn_nslab = 0;
@@ -183,6 +185,10 @@ struct wd_engine {
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
   Plan* cur = nullptr;
   int last_launches = 0;
+  // per-op device timing (bench.py): events recorded on the launching stream around every op of a step
+  bool prof_on = false;
+  std::vector<std::vector<cudaEvent_t>> prof_steps;  // each: n_ops + 1 events
+  const Plan* prof_plan = nullptr;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -717,6 +723,8 @@ struct PlanBuilder {
       if (!ok) { err = "cuTensorMapEncodeTiled failed (A)"; return false; }
     }
     if (ktot != w.K) { err = "gemm: K mismatch between sources and weight"; return false; }
+    op.flops = 2.0 * M * static_cast<double>(w.N) * w.K;
+    op.bytes = 2.0 * (static_cast<double>(M) * w.K + static_cast<double>(w.N) * w.K + static_cast<double>(M) * (ep.geglu ? w.N / 2 : w.N));
     if (w.N % gemm_tc_block_n()) { err = "gemm: N must be a multiple of the N tile"; return false; }
     if (!dry) {
       for (size_t i = srcs.size(); i < GEMM_MAX_SRC; ++i) op.gemm.mapA[i] = op.gemm.mapA[0];
@@ -736,19 +744,14 @@ struct PlanBuilder {
     if (totalC != nw.C || totalC % 32) { err = "groupnorm: channel mismatch"; return false; }
     const int cpg = totalC / 32;
     const int H = srcs[0].H, W = srcs[0].W, HW = H * W;
-    // slab size: whole groups, multiple of 8 channels, fits in shared memory
-    int Cs = srcs[0].C;
+    // one slab per concatenated source: it must hold whole groups and whole 16-byte vectors
+    const int Cs = srcs[0].C;
     for (auto& s : srcs)
       if (s.C != Cs) { err = "groupnorm: concat sources must have equal channels"; return false; }
-    auto fits = [&](int cs) { return static_cast<size_t>(HW) * cs * 2 + 8 * cs * 4 + cs * 4 + 1024 <= 200 * 1024; };
-    while (!fits(Cs)) {
-      if (Cs % 2 || (Cs / 2) % cpg || (Cs / 2) % 8) { err = "groupnorm: cannot tile channels into shared memory"; return false; }
-      Cs /= 2;
-    }
-    if (Cs % cpg || Cs % 8) { err = "groupnorm: slab does not hold whole groups"; return false; }
-    const int per_src = srcs[0].C / Cs;
-    const int nslab = per_src * static_cast<int>(srcs.size());
-    if (nslab > 8) { err = "groupnorm: too many slabs"; return false; }
+    if (Cs % cpg || Cs % 8 || Cs / 8 * 8 > 1024) { err = "groupnorm: slab does not hold whole groups"; return false; }
+    const int per_src = 1;
+    const int nslab = static_cast<int>(srcs.size());
+    if (nslab > 2) { err = "groupnorm: too many slabs"; return false; }
     out = new_act(H, W, totalC);
     Op op;
     memset(&op, 0, sizeof(op));
@@ -767,8 +770,12 @@ struct PlanBuilder {
     op.gn.cpg = cpg;
     op.gn.eps = eps;
     op.gn.silu = silu;
+    op.gn.G = 32;
+    op.gn.nchunk = groupnorm_nchunk(HW);
+    op.gn.partial = A.alloc<float>(static_cast<size_t>(B) * 32 * GN_MAX_CHUNK * 2);
     op.gn_B = B;
     op.gn_nslab = nslab;
+    op.bytes = 4.0 * B * HW * totalC;  // bf16 read + bf16 write
     ops.push_back(op);
     return true;
   }
@@ -778,6 +785,7 @@ struct PlanBuilder {
     memset(&op, 0, sizeof(op));
     op.kind = OP_LN;
     op.ln = {x, out, nw.g, nw.b, M, nw.C, 1e-5f};
+    op.bytes = 4.0 * M * nw.C;
     ops.push_back(op);
   }
 
@@ -786,13 +794,12 @@ struct PlanBuilder {
     Op op;
     memset(&op, 0, sizeof(op));
     const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-    if (Skv <= 16) {
-      op.kind = OP_ATTN_SMALL;
-      op.as = AttnSmallArgs{q, q_ld, k, v, kv_ld, out, out_ld, nullptr, Sq, Skv, heads, scale};
-    } else {
-      op.kind = OP_ATTN_FLASH;
-      op.af = AttnFlashArgs{q, q_ld, k, v, kv_ld, out, out_ld, Sq, Skv, heads, scale};
-    }
+    // tensor-core flash kernel for every key length (16-key tile for the character context); the SIMT
+    // attn_small kernel only remains for the attention-probability output (wd_op_attention_small)
+    op.kind = OP_ATTN_FLASH;
+    op.af = AttnFlashArgs{q, q_ld, k, v, kv_ld, out, out_ld, Sq, Skv, heads, scale};
+    op.flops = 4.0 * B * heads * static_cast<double>(Sq) * Skv * dh;  // QK^T + PV
+    op.bytes = 2.0 * B * heads * dh * (2.0 * Sq + 2.0 * Skv);
     ops.push_back(op);
     return true;
   }
@@ -1022,6 +1029,8 @@ struct PlanBuilder {
             memset(&op, 0, sizeof(op));
             op.kind = OP_CONV_IN;
             op.cin = {e->conv_in_w, e->conv_in_b, out.p, B, c.latent_h, c.latent_w, mc};
+            op.flops = 2.0 * B * c.latent_h * c.latent_w * mc * 36;
+            op.bytes = static_cast<double>(B) * c.latent_h * c.latent_w * (4 * 4 + 2 * mc);
             sops.push_back(op);
             break;
           }
@@ -1051,6 +1060,7 @@ struct PlanBuilder {
             memset(&op, 0, sizeof(op));
             op.kind = OP_UPSAMPLE;
             op.up = {x.p, up.p, B, x.H, x.W, x.C};
+            op.bytes = 2.0 * B * x.H * x.W * x.C * 5;
             sops.push_back(op);
             out = new_act(up.H, up.W, x.C);
             Epi ep;
@@ -1087,6 +1097,8 @@ struct PlanBuilder {
     memset(&op, 0, sizeof(op));
     op.kind = OP_CONV_OUT;
     op.cout_ = {a.p, e->conv_out_w, e->conv_out_b, B, a.H, a.W, a.C};
+    op.flops = 2.0 * B * a.H * a.W * a.C * 9 * c.out_channels;
+    op.bytes = static_cast<double>(B) * a.H * a.W * (2.0 * a.C + 4.0 * c.out_channels * 4);  // h read; x in/out, noise, eps
     sops.push_back(op);
     plan->bytes = A.used;
     return true;
@@ -1150,9 +1162,23 @@ struct RunCtx {
 };
 
 int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStream_t s) {
-  int n = 0;
+  int n = 0, kernels = 0;
+  std::vector<cudaEvent_t>* ev = nullptr;
+  if (e->prof_on && &ops == &e->cur->step_ops && e->prof_steps.size() < 256) {
+    if (e->prof_plan != e->cur) {
+      for (auto& v : e->prof_steps)
+        for (auto x : v) cudaEventDestroy(x);
+      e->prof_steps.clear();
+      e->prof_plan = e->cur;
+    }
+    e->prof_steps.emplace_back(ops.size() + 1);
+    ev = &e->prof_steps.back();
+    for (auto& x : *ev)
+      if (cudaEventCreate(&x) != cudaSuccess) return fail(WD_ERR_CUDA, "cudaEventCreate");
+  }
   for (const Op& op : ops) {
     cudaError_t err = cudaSuccess;
+    if (ev) cudaEventRecord((*ev)[n], s);
     switch (op.kind) {
       case OP_TEMB:
         err = timestep_embed_launch(rc.t_dev, rc.t_scalar, op.temb.out, op.temb.B, op.temb.dim, s);
@@ -1226,8 +1252,10 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
     }
     if (err != cudaSuccess) return fail(WD_ERR_CUDA, "launch of op kind %d failed: %s", (int)op.kind, cudaGetErrorString(err));
     ++n;
+    kernels += (op.kind == OP_GN) ? 2 : 1;  // GroupNorm = statistics + apply
   }
-  e->last_launches = n;
+  if (ev) cudaEventRecord((*ev)[n], s);
+  e->last_launches = kernels;
   return WD_OK;
 }
 
@@ -1304,36 +1332,73 @@ extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scal
 }
 
 // ----------------------------------------------------------------------------------------------
+// C ABI: per-op device timing
+// ----------------------------------------------------------------------------------------------
+extern "C" int wd_engine_set_profiling(wd_engine* e, int enable) {
+  if (!e) return fail(WD_ERR_INVALID, "null engine");
+  e->prof_on = enable != 0;
+  if (!enable) {
+    for (auto& v : e->prof_steps)
+      for (auto x : v) cudaEventDestroy(x);
+    e->prof_steps.clear();
+    e->prof_plan = nullptr;
+  }
+  return WD_OK;
+}
+
+extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double* flops, double* bytes, float* ms_sum,
+                                      int* n_steps) {
+  if (!e || !e->prof_plan) return fail(WD_ERR_STATE, "no profiled step recorded");
+  const std::vector<Op>& ops = e->prof_plan->step_ops;
+  const int n = static_cast<int>(ops.size());
+  if (cap < n) return fail(WD_ERR_INVALID, "profile_read: capacity %d < %d ops", cap, n);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) {
+    kinds[i] = static_cast<int>(ops[i].kind);
+    flops[i] = ops[i].flops;
+    bytes[i] = ops[i].bytes;
+    ms_sum[i] = 0.f;
+  }
+  for (auto& v : e->prof_steps)
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+      ms_sum[i] += ms;
+    }
+  if (n_steps) *n_steps = static_cast<int>(e->prof_steps.size());
+  return n;
+}
+
+// ----------------------------------------------------------------------------------------------
 // C ABI: single operators (parity tests)
 // ----------------------------------------------------------------------------------------------
 extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, const float* beta, int B, int HW, int C,
                                int groups, float eps, int silu, void* stream) {
   if (C % groups) return fail(WD_ERR_INVALID, "C %% groups");
   const int cpg = C / groups;
-  int Cs = C;
-  auto fits = [&](int cs) { return static_cast<size_t>(HW) * cs * 2 + 8 * cs * 4 + cs * 4 + 1024 <= 200 * 1024; };
-  while (!fits(Cs)) {
-    if (Cs % 2 || (Cs / 2) % cpg || (Cs / 2) % 8) return fail(WD_ERR_UNSUPPORTED, "groupnorm: cannot tile");
-    Cs /= 2;
-  }
-  const int nslab = C / Cs;
-  if (nslab > 8 || Cs % 8) return fail(WD_ERR_UNSUPPORTED, "groupnorm: unsupported channel count");
+  if (C % 8 || C / 8 * 8 > 1024) return fail(WD_ERR_UNSUPPORTED, "groupnorm: unsupported channel count");
   GroupNormArgs a;
   memset(&a, 0, sizeof(a));
-  for (int i = 0; i < nslab; ++i) {
-    a.x[i] = static_cast<const bf16*>(x) + i * Cs;
-    a.x_ld[i] = C;
-  }
+  a.x[0] = static_cast<const bf16*>(x);
+  a.x_ld[0] = C;
   a.out = static_cast<bf16*>(out);
   a.out_ld = C;
   a.gamma = gamma;
   a.beta = beta;
   a.HW = HW;
-  a.Cs = Cs;
+  a.Cs = C;
   a.cpg = cpg;
   a.eps = eps;
   a.silu = silu;
+  a.G = groups;
+  a.nchunk = groupnorm_nchunk(HW);
+  const int nslab = 1;
+  float* partial = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * groups * GN_MAX_CHUNK * 2 * sizeof(float),
+                           static_cast<cudaStream_t>(stream)));
+  a.partial = partial;
   CUDA_TRY(groupnorm_launch(a, B, nslab, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(cudaFreeAsync(partial, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 

@@ -7,104 +7,106 @@
 namespace wd {
 
 // =====================================================================================================
-// GroupNorm (+SiLU).  One CTA = one (sample, channel slab); the slab lives in shared memory, so HBM sees
-// exactly one read and one write of the activation.  Two-pass (mean, then centred variance) in fp32.
+// GroupNorm (+SiLU), two launches, no atomics (bit-reproducible):
+//   stats : grid (B, slab, chunk).  A CTA reduces its pixel chunk of one (sample, channel slab) to per-group
+//           {sum, sum of squares} in fp32 and writes them to partial[b][group][chunk][2].
+//   apply : same grid.  Every thread folds the chunk partials of its (<= 2) groups in a fixed order, forms the
+//           per-channel scale/shift once and streams its rows: y = silu(x * sc + sh), 16-byte loads and stores.
+// The tensor was just written by the producing GEMM epilogue, so the second read normally hits the 126 MB L2;
+// HBM sees about one read and one write of the activation (4 algorithmic bytes per element).
 // Thread t owns vector column t % (Cs/8) (8 channels) and pixel rows t / (Cs/8), stepping by R.
 // =====================================================================================================
-__global__ void __launch_bounds__(1024) groupnorm_kernel(const GroupNormArgs a) {
-  extern __shared__ uint4 gn_smem[];
-  const int b = blockIdx.x, slab = blockIdx.y;
-  const int Cs = a.Cs, HW = a.HW, cpg = a.cpg;
+constexpr int GN_R = 8;
+
+__global__ void __launch_bounds__(1024) groupnorm_stats_kernel(const GroupNormArgs a) {
+  extern __shared__ float gn_part[];  // [2][R][Cs]
+  const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
+  const int Cs = a.Cs, cpg = a.cpg;
   const int nv = Cs >> 3;
   const int R = blockDim.x / nv;
   const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
   const int ng = Cs / cpg;
-
-  uint4* sdata = gn_smem;                                  // [HW][nv]
-  float* part = reinterpret_cast<float*>(sdata + HW * nv);  // [R][Cs]
-  float* chan = part + R * Cs;                              // [Cs]
-  float* gmean = chan + Cs;                                 // [ng]
-  float* grstd = gmean + ng;                                // [ng]
-
+  const int P = a.HW / a.nchunk;
   const int ld = a.x_ld[slab];
-  const __nv_bfloat16* xb = a.x[slab] + static_cast<size_t>(b) * HW * ld;
+  const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
 
-  float s[8];
+  float s[8], q[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = 0.f;
-  for (int p = rl; p < HW; p += R) {
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (int p = rl; p < P; p += R) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
-    sdata[p * nv + col] = v;
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(u[j]);
       s[2 * j] += f.x;
       s[2 * j + 1] += f.y;
+      q[2 * j] += f.x * f.x;
+      q[2 * j + 1] += f.y * f.y;
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) part[rl * Cs + col * 8 + j] = s[j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
-    float t = 0.f;
-    for (int r = 0; r < R; ++r) t += part[r * Cs + c];
-    chan[c] = t;
-  }
-  __syncthreads();
-  const float inv_n = 1.0f / static_cast<float>(cpg * HW);
-  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
-    float t = 0.f;
-    for (int c = 0; c < cpg; ++c) t += chan[g * cpg + c];
-    gmean[g] = t * inv_n;
-  }
-  __syncthreads();
-
-  float mu[8];
+  float* ps = gn_part;
+  float* pq = gn_part + R * Cs;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    mu[j] = gmean[(col * 8 + j) / cpg];
-    s[j] = 0.f;
+    ps[rl * Cs + col * 8 + j] = s[j];
+    pq[rl * Cs + col * 8 + j] = q[j];
   }
-  for (int p = rl; p < HW; p += R) {
-    const uint4 v = sdata[p * nv + col];
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(u[j]);
-      const float d0 = f.x - mu[2 * j], d1 = f.y - mu[2 * j + 1];
-      s[2 * j] += d0 * d0;
-      s[2 * j + 1] += d1 * d1;
+  __syncthreads();
+  // one thread per (group, {sum, sumsq}): fixed summation order
+  for (int i = threadIdx.x; i < 2 * ng; i += blockDim.x) {
+    const int g = i >> 1, which = i & 1;
+    const float* src = which ? pq : ps;
+    float t = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      float tc = 0.f;
+      for (int r = 0; r < R; ++r) tc += src[r * Cs + g * cpg + c];
+      t += tc;
     }
+    a.partial[((static_cast<size_t>(b) * a.G + slab * ng + g) * a.nchunk + chunk) * 2 + which] = t;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) part[rl * Cs + col * 8 + j] = s[j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
-    float t = 0.f;
-    for (int r = 0; r < R; ++r) t += part[r * Cs + c];
-    chan[c] = t;
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
-    float t = 0.f;
-    for (int c = 0; c < cpg; ++c) t += chan[g * cpg + c];
-    grstd[g] = rsqrtf(t * inv_n + a.eps);
-  }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormArgs a) {
+  const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
+  const int Cs = a.Cs, cpg = a.cpg;
+  const int nv = Cs >> 3;
+  const int R = blockDim.x / nv;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int ng = Cs / cpg;
+  const int P = a.HW / a.nchunk;
+  const int ld = a.x_ld[slab];
+  const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
 
   float sc[8], sh[8];
+  {
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = col * 8 + j;
-    const float rstd = grstd[c / cpg];
-    const float g = __ldg(a.gamma + slab * Cs + c), be = __ldg(a.beta + slab * Cs + c);
-    sc[j] = rstd * g;
-    sh[j] = be - mu[j] * sc[j];
+    for (int j = 0; j < 8; ++j) {
+      const int c = col * 8 + j;
+      const int g = c / cpg;
+      if (g != g_prev) {
+        const float* pp = a.partial + (static_cast<size_t>(b) * a.G + slab * ng + g) * a.nchunk * 2;
+        float S = 0.f, Q = 0.f;
+        for (int k = 0; k < a.nchunk; ++k) {
+          S += __ldg(pp + 2 * k);
+          Q += __ldg(pp + 2 * k + 1);
+        }
+        mean = S * inv_n;
+        const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+        rstd = rsqrtf(var + a.eps);
+        g_prev = g;
+      }
+      const float gm = __ldg(a.gamma + slab * Cs + c), be = __ldg(a.beta + slab * Cs + c);
+      sc[j] = rstd * gm;
+      sh[j] = be - mean * sc[j];
+    }
   }
-  __nv_bfloat16* ob = a.out + static_cast<size_t>(b) * HW * a.out_ld + slab * Cs;
-  for (int p = rl; p < HW; p += R) {
-    const uint4 v = sdata[p * nv + col];
+  const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
+  __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.out_ld + slab * Cs;
+  for (int p = rl; p < P; p += R) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
@@ -122,23 +124,24 @@ __global__ void __launch_bounds__(1024) groupnorm_kernel(const GroupNormArgs a) 
   }
 }
 
+int groupnorm_nchunk(int HW) {
+  int n = 1;
+  while (n < GN_MAX_CHUNK && HW % (2 * n) == 0 && HW / (2 * n) >= 4 * GN_R) n *= 2;
+  return n;
+}
+
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s) {
   const int nv = a.Cs / 8;
-  if (a.Cs % 8 || a.Cs % a.cpg || nv > 1024) return cudaErrorInvalidValue;
-  int R = 1024 / nv;
-  if (R > 8) R = 8;
-  if (R > a.HW) R = a.HW;
-  const int threads = nv * R;
-  const size_t smem = static_cast<size_t>(a.HW) * a.Cs * 2 + static_cast<size_t>(R) * a.Cs * 4 + a.Cs * 4 +
-                      2 * (a.Cs / a.cpg) * 4 + 64;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(groupnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
-  groupnorm_kernel<<<dim3(B, nslab), threads, smem, s>>>(a);
+  if (a.Cs % 8 || a.Cs % a.cpg || nv * GN_R > 1024 || !a.partial || a.nchunk < 1 || a.HW % a.nchunk)
+    return cudaErrorInvalidValue;
+  const int threads = nv * GN_R;
+  const size_t smem = static_cast<size_t>(2) * GN_R * a.Cs * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  dim3 grid(B, nslab, a.nchunk);
+  groupnorm_stats_kernel<<<grid, threads, smem, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  groupnorm_apply_kernel<<<grid, threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,13 @@ struct GroupNormArgs {
   int cpg;  // channels per group
   float eps;
   int silu;
+  float* partial;  // scratch [B][G][nchunk][2] fp32: per-chunk {sum, sum of squares} of every group
+  int G;           // groups over all slabs
+  int nchunk;      // pixel chunks per sample (groupnorm_nchunk(HW))
 };
+constexpr int GN_MAX_CHUNK = 8;
+int groupnorm_nchunk(int HW);
+// two launches: statistics, then normalise (+SiLU)
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
 
 // ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------

@@ -130,6 +130,20 @@ class HotPathEngine:
                                         _stream_ptr()), "wd_sampler_step")
         return x
 
+    OP_KINDS = ("timestep_embed", "gemm_tc", "groupnorm", "layernorm", "attn_small", "attn_flash", "conv_in",
+                "conv_out_step", "upsample")
+
+    def set_profiling(self, on):
+        check(lib().wd_engine_set_profiling(self._h, 1 if on else 0), "wd_engine_set_profiling")
+
+    def profile_read(self):
+        """-> (n_steps, [(kind_name, flops, bytes, ms_sum)] per launch of the step plan)."""
+        cap = 1024
+        kinds, fl, by = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        ms, ns = (C.c_float * cap)(), C.c_int(0)
+        n = check(lib().wd_engine_profile_read(self._h, cap, kinds, fl, by, ms, C.byref(ns)), "wd_engine_profile_read")
+        return ns.value, [(self.OP_KINDS[kinds[i]], fl[i], by[i], ms[i]) for i in range(n)]
+
     def reserve(self, batch):
         with torch.cuda.device(self.device):
             check(lib().wd_engine_reserve(self._h, batch), "wd_engine_reserve")
