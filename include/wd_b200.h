@@ -87,7 +87,8 @@ int wd_engine_last_launch_count(const wd_engine* e);
  * While enabled, every wd_unet_eval / wd_sampler_step records CUDA events on `stream` around each kernel launch of the
  * step (at most 256 steps are kept).  wd_engine_profile_read synchronises the device and returns, per launch of the
  * step plan: its kernel class (0 timestep-embed, 1 tcgen05 GEMM/conv, 2 GroupNorm, 3 LayerNorm, 4 short-context
- * attention, 5 flash attention, 6 conv_in, 7 conv_out+sampler update, 8 upsample), its algorithmic FLOPs and bytes,
+ * attention, 5 flash attention, 6 conv_in, 7 GroupNorm statistics, 8 upsample; the output conv + sampler update is a
+ * class-1 launch), its algorithmic FLOPs and bytes,
  * and the summed milliseconds over the recorded steps.  Returns the number of launches per step (or < 0). */
 int wd_engine_set_profiling(wd_engine* e, int enable);
 int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double* flops, double* bytes, float* ms_sum, int* n_steps);

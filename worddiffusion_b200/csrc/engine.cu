@@ -104,7 +104,7 @@ struct Layer {
 };
 typedef std::vector<Layer> Block;
 
-enum SlotKind { S_VEC, S_CONV3, S_LIN, S_CONV_IN, S_CONV_OUT, S_F32 };
+enum SlotKind { S_VEC, S_CONV3, S_LIN, S_CONV_IN, S_F32 };
 struct Slot {
   SlotKind kind;
   void* dst;
@@ -117,9 +117,9 @@ struct Slot {
 // ----------------------------------------------------------------------------------------------
 // launch plan
 // ----------------------------------------------------------------------------------------------
-enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_CONV_OUT, OP_UPSAMPLE,
+enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_GNSTATS, OP_UPSAMPLE,
               OP_EMBED, OP_LINF32, OP_WORDATTN };
-enum Patch { P_NONE = 0, P_Y = 1 };
+enum Patch { P_NONE = 0, P_Y = 1, P_SAMPLER = 2 };
 struct Op {
   OpKind kind;
   int patch = P_NONE;
@@ -127,13 +127,13 @@ struct Op {
   double bytes = 0;
   GemmLaunch gemm;
   GroupNormArgs gn;
+  GroupNormStatsArgs gs;
   int gn_B = 0, gn_nslab = 0;
   struct { const bf16* x; bf16* out; const float* g; const float* b; int M, C; float eps; } ln;
   AttnSmallArgs as;
   AttnFlashArgs af;
   struct { bf16* out; int B, dim; } temb;
   struct { const float* w; const float* bias; bf16* out; int B, H, W, Cout; } cin;
-  struct { const bf16* h; const float* w; const float* bias; int B, H, W, C; } cout_;
   struct { const bf16* x; bf16* out; int B, H, W, C; } up;
   struct { int which; const float* E; int vocab; const float* pe; int add_pe; float* out; int B, L, D; } emb;
   struct { const float* x; const float* W; const float* b; float* out; int M, N, K; } lin;
@@ -151,6 +151,8 @@ struct Plan {
 struct Act {
   bf16* p;
   int C, H, W;
+  float* stats;  // GroupNorm partial statistics of this tensor: [B][32][pslots][2] fp32 (groups of C/32 channels)
+  int pslots;    // 0: not computed
 };
 
 struct wd_engine {
@@ -171,8 +173,7 @@ struct wd_engine {
   float* conv_in_w = nullptr;
   float* conv_in_b = nullptr;
   NormW out_gn;
-  float* conv_out_w = nullptr;
-  float* conv_out_b = nullptr;
+  GemmW conv_out;  // [16, 9*C] bf16, rows >= out_channels are zero
   // context encoder (fp32)
   float *we_E = nullptr, *we_qw = nullptr, *we_qb = nullptr, *we_kw = nullptr, *we_kb = nullptr, *we_vw = nullptr,
         *we_vb = nullptr, *we_pe = nullptr;
@@ -441,10 +442,12 @@ struct Builder {
     }
     // out, unet.py:1454-1458
     e->out_gn = norm("out.0", ch);
-    e->conv_out_w = A.alloc<float>(static_cast<size_t>(9) * ch * c.out_channels);
-    e->conv_out_b = A.alloc<float>(c.out_channels);
-    slot("out.2.weight", S_CONV_OUT, e->conv_out_w, static_cast<int64_t>(c.out_channels) * ch * 9, c.out_channels, ch);
-    slot("out.2.bias", S_VEC, e->conv_out_b, c.out_channels);
+    e->conv_out.N = GEMM_BLOCK_N_OUT;
+    e->conv_out.K = 9 * ch;
+    e->conv_out.w = A.alloc<bf16>(static_cast<size_t>(GEMM_BLOCK_N_OUT) * 9 * ch);
+    e->conv_out.bias = A.alloc<float>(GEMM_BLOCK_N_OUT);
+    slot("out.2.weight", S_CONV3, e->conv_out.w, static_cast<int64_t>(c.out_channels) * ch * 9, c.out_channels, ch, 9 * ch, 0);
+    slot("out.2.bias", S_VEC, e->conv_out.bias, c.out_channels);
 
     // fused emb_layers GEMM: [sum Cout, time_dim]
     e->emb_all.N = emb_cols;
@@ -588,9 +591,6 @@ extern "C" int wd_engine_load_param(wd_engine* e, const char* name, const float*
     case S_CONV_IN:
       CUDA_TRY(repack_conv_in_launch(src, static_cast<float*>(sl.dst), sl.N, sl.K, s));
       break;
-    case S_CONV_OUT:
-      CUDA_TRY(repack_conv_out_launch(src, static_cast<float*>(sl.dst), sl.N, sl.K, s));
-      break;
   }
   sl.loaded = true;
   return WD_OK;
@@ -653,6 +653,8 @@ struct Epi {
   int out_f32 = 0;
   int act = 0;
   int geglu = 0;
+  Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
+  int epi = EPI_STD;
 };
 
 struct PlanBuilder {
@@ -663,7 +665,27 @@ struct PlanBuilder {
   int B;
   std::string err;
 
-  Act new_act(int H, int W, int C) { return Act{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W}; }
+  Act new_act(int H, int W, int C) {
+    Act a{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W, nullptr, 0};
+    a.stats = A.alloc<float>(static_cast<size_t>(B) * 32 * 8 * 2);
+    return a;
+  }
+  // can the GEMM epilogue emit the GroupNorm partials of an [B, H*W, C] output?  (16 groups of 10 columns per 160-wide tile)
+  static bool epilogue_stats_ok(int HW, int C) { return C % 32 == 0 && C / 32 == 10 && HW % 32 == 0 && HW / 32 <= 8; }
+  // make sure `a` carries GroupNorm partials: free when the producing GEMM wrote them, else one reduction kernel
+  bool ensure_stats(std::vector<Op>& ops, Act& a) {
+    if (a.pslots) return true;
+    if (a.C % 32 || a.C % 8) { err = "groupnorm: channels must be a multiple of 32"; return false; }
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_GNSTATS;
+    a.pslots = groupnorm_stats_slots(a.H * a.W);
+    op.gs = GroupNormStatsArgs{a.p, a.C, a.stats, a.H * a.W, a.C, a.C / 32, a.pslots};
+    op.gn_B = B;
+    op.bytes = 2.0 * B * a.H * a.W * a.C;
+    ops.push_back(op);
+    return true;
+  }
 
   bool gemm_op(std::vector<Op>& ops, int M, bool conv, int Hout, int Wout, const std::vector<ASrc>& srcs, const GemmW& w,
                const Epi& ep, int patch = P_NONE) {
@@ -690,6 +712,12 @@ struct PlanBuilder {
     a.out_f32 = ep.out_f32;
     a.act = ep.act;
     a.geglu = ep.geglu;
+    a.epi = ep.epi;
+    if (ep.stats_for && epilogue_stats_ok(ep.rows_per_sample, w.N) && ep.stats_for->C == w.N) {
+      a.gn_partial = ep.stats_for->stats;
+      a.gn_cpg = 10;
+      ep.stats_for->pslots = ep.rows_per_sample / 32;
+    }
     int ktot = 0;
     if (srcs.empty() || srcs.size() > GEMM_MAX_SRC) { err = "gemm: bad source count"; return false; }
     for (size_t i = 0; i < srcs.size(); ++i) {
@@ -725,15 +753,17 @@ struct PlanBuilder {
     if (ktot != w.K) { err = "gemm: K mismatch between sources and weight"; return false; }
     op.flops = 2.0 * M * static_cast<double>(w.N) * w.K;
     op.bytes = 2.0 * (static_cast<double>(M) * w.K + static_cast<double>(w.N) * w.K + static_cast<double>(M) * (ep.geglu ? w.N / 2 : w.N));
-    if (w.N % gemm_tc_block_n()) { err = "gemm: N must be a multiple of the N tile"; return false; }
+    const int bn = (ep.epi == EPI_SAMPLER) ? GEMM_BLOCK_N_OUT : gemm_tc_block_n();
+    if (w.N % bn) { err = "gemm: N must be a multiple of the N tile"; return false; }
     if (!dry) {
       for (size_t i = srcs.size(); i < GEMM_MAX_SRC; ++i) op.gemm.mapA[i] = op.gemm.mapA[0];
-      if (!tmap_encode_2d_bf16(&op.gemm.mapB, w.w, w.K, w.N, w.K, GEMM_BLOCK_K, gemm_tc_block_n())) {
+      if (!tmap_encode_2d_bf16(&op.gemm.mapB, w.w, w.K, w.N, w.K, GEMM_BLOCK_K, bn)) {
         err = "cuTensorMapEncodeTiled failed (B)";
         return false;
       }
     }
     ops.push_back(op);
+    if (ep.stats_for && !ensure_stats(ops, *ep.stats_for)) return false;
     return true;
   }
 
@@ -770,9 +800,13 @@ struct PlanBuilder {
     op.gn.cpg = cpg;
     op.gn.eps = eps;
     op.gn.silu = silu;
-    op.gn.G = 32;
-    op.gn.nchunk = groupnorm_nchunk(HW);
-    op.gn.partial = A.alloc<float>(static_cast<size_t>(B) * 32 * GN_MAX_CHUNK * 2);
+    op.gn.pcpg = Cs / 32;
+    op.gn.nchunk = groupnorm_stats_slots(HW);
+    for (int i = 0; i < nslab; ++i) {
+      if (!srcs[i].pslots) { err = "groupnorm: source tensor carries no statistics"; return false; }
+      op.gn.partial[i] = srcs[i].stats;
+      op.gn.pslots[i] = srcs[i].pslots;
+    }
     op.gn_B = B;
     op.gn_nslab = nslab;
     op.bytes = 4.0 * B * HW * totalC;  // bf16 read + bf16 write
@@ -817,6 +851,7 @@ struct PlanBuilder {
       ep.rows_per_sample = HW;
       ep.out = h2.p;
       ep.out_ld = r.Cout;
+      ep.stats_for = &h2;
       if (!gemm_op(ops, B * HW, true, H, W, {ASrc{a1.p, a1.C, a1.C, 9, 1, H, W}}, r.conv1, ep)) return false;
     }
     Act a2;
@@ -827,6 +862,7 @@ struct PlanBuilder {
       ep.rows_per_sample = HW;
       ep.out = out.p;
       ep.out_ld = r.Cout;
+      ep.stats_for = &out;
       std::vector<ASrc> srcs{ASrc{a2.p, a2.C, a2.C, 9, 1, H, W}};
       if (r.skip_conv) {
         for (auto& s : in) srcs.push_back(ASrc{s.p, s.C, s.C, 1, 1, H, W});
@@ -925,6 +961,8 @@ struct PlanBuilder {
     ep.out_ld = s.C;
     ep.residual = x_in.p;
     ep.res_ld = x_in.C;
+    ep.rows_per_sample = HW;
+    ep.stats_for = &out;
     return gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W}}, s.proj_out, ep);
   }
 
@@ -1032,6 +1070,7 @@ struct PlanBuilder {
             op.flops = 2.0 * B * c.latent_h * c.latent_w * mc * 36;
             op.bytes = static_cast<double>(B) * c.latent_h * c.latent_w * (4 * 4 + 2 * mc);
             sops.push_back(op);
+            if (!ensure_stats(sops, out)) return false;
             break;
           }
           case L_RES:
@@ -1048,6 +1087,7 @@ struct PlanBuilder {
             ep.out = out.p;
             ep.out_ld = x.C;
             ep.rows_per_sample = out.H * out.W;
+            ep.stats_for = &out;
             if (!gemm_op(sops, B * out.H * out.W, true, out.H, out.W, {ASrc{x.p, x.C, x.C, 9, 2, x.H, x.W}},
                          e->samp[l.idx].conv, ep))
               return false;
@@ -1067,6 +1107,7 @@ struct PlanBuilder {
             ep.out = out.p;
             ep.out_ld = x.C;
             ep.rows_per_sample = up.H * up.W;
+            ep.stats_for = &out;
             if (!gemm_op(sops, B * up.H * up.W, true, up.H, up.W, {ASrc{up.p, up.C, up.C, 9, 1, up.H, up.W}},
                          e->samp[l.idx].conv, ep))
               return false;
@@ -1093,13 +1134,17 @@ struct PlanBuilder {
     // out: GN + SiLU, then conv_out fused with the sampler update
     Act a;
     if (!gn_op(sops, {h}, e->out_gn, 1e-5f, 1, a)) return false;
-    Op op;
-    memset(&op, 0, sizeof(op));
-    op.kind = OP_CONV_OUT;
-    op.cout_ = {a.p, e->conv_out_w, e->conv_out_b, B, a.H, a.W, a.C};
-    op.flops = 2.0 * B * a.H * a.W * a.C * 9 * c.out_channels;
-    op.bytes = static_cast<double>(B) * a.H * a.W * (2.0 * a.C + 4.0 * c.out_channels * 4);  // h read; x in/out, noise, eps
-    sops.push_back(op);
+    {
+      // output conv 320 -> 4 on the tensor cores (16-column tile), epilogue = sampler update; x / eps / noise /
+      // coefficients are patched in per call (P_SAMPLER)
+      Epi ep;
+      ep.epi = EPI_SAMPLER;
+      ep.rows_per_sample = a.H * a.W;
+      if (!gemm_op(sops, B * a.H * a.W, true, a.H, a.W, {ASrc{a.p, a.C, a.C, 9, 1, a.H, a.W}}, e->conv_out, ep, P_SAMPLER))
+        return false;
+      sops.back().bytes = static_cast<double>(B) * a.H * a.W * (2.0 * a.C + 4.0 * c.out_channels * 4);  // h read; x in/out, noise, eps
+      sops.back().flops = 2.0 * B * a.H * a.W * a.C * 9 * c.out_channels;
+    }
     plan->bytes = A.used;
     return true;
   }
@@ -1189,6 +1234,18 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
           GemmLaunch L = op.gemm;
           L.args.rowbias_idx = rc.y;
           err = gemm_tc_launch(L, s);
+        } else if (op.patch == P_SAMPLER) {
+          GemmLaunch L = op.gemm;
+          L.args.eps_out = rc.eps_out;
+          L.args.x = rc.x_rw;
+          L.args.noise = rc.noise;
+          L.args.use_philox = rc.use_philox;
+          L.args.seed = rc.seed;
+          L.args.sample_offset = rc.sample_offset;
+          L.args.step_index = rc.step_index;
+          L.args.coef = rc.coef;
+          L.args.mode = rc.mode;
+          err = gemm_tc_launch(L, s);
         } else {
           err = gemm_tc_launch(op.gemm, s);
         }
@@ -1208,27 +1265,9 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
       case OP_CONV_IN:
         err = conv_in_launch(rc.x, op.cin.w, op.cin.bias, op.cin.out, op.cin.B, op.cin.H, op.cin.W, op.cin.Cout, s);
         break;
-      case OP_CONV_OUT: {
-        ConvOutArgs a;
-        a.h = op.cout_.h;
-        a.w_packed = op.cout_.w;
-        a.bias = op.cout_.bias;
-        a.eps_out = rc.eps_out;
-        a.x = rc.x_rw;
-        a.noise = rc.noise;
-        a.use_philox = rc.use_philox;
-        a.seed = rc.seed;
-        a.sample_offset = rc.sample_offset;
-        a.step_index = rc.step_index;
-        a.coef = rc.coef;
-        a.mode = rc.mode;
-        a.B = op.cout_.B;
-        a.H = op.cout_.H;
-        a.W = op.cout_.W;
-        a.C = op.cout_.C;
-        err = conv_out_step_launch(a, s);
+      case OP_GNSTATS:
+        err = groupnorm_stats_launch(op.gs, op.gn_B, s);
         break;
-      }
       case OP_UPSAMPLE:
         err = upsample2x_launch(op.up.x, op.up.out, op.up.B, op.up.H, op.up.W, op.up.C, s);
         break;
@@ -1252,7 +1291,7 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
     }
     if (err != cudaSuccess) return fail(WD_ERR_CUDA, "launch of op kind %d failed: %s", (int)op.kind, cudaGetErrorString(err));
     ++n;
-    kernels += (op.kind == OP_GN) ? 2 : 1;  // GroupNorm = statistics + apply
+    kernels += 1;
   }
   if (ev) cudaEventRecord((*ev)[n], s);
   e->last_launches = kernels;
@@ -1375,12 +1414,20 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
 extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, const float* beta, int B, int HW, int C,
                                int groups, float eps, int silu, void* stream) {
   if (C % groups) return fail(WD_ERR_INVALID, "C %% groups");
+  if (C % 8 || C > 1024) return fail(WD_ERR_UNSUPPORTED, "groupnorm: unsupported channel count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cpg = C / groups;
-  if (C % 8 || C / 8 * 8 > 1024) return fail(WD_ERR_UNSUPPORTED, "groupnorm: unsupported channel count");
+  const int slots = groupnorm_stats_slots(HW);
+  float* partial = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * groups * slots * 2 * sizeof(float), s));
+  GroupNormStatsArgs st{static_cast<const bf16*>(x), C, partial, HW, C, cpg, slots};
+  CUDA_TRY(groupnorm_stats_launch(st, B, s));
   GroupNormArgs a;
   memset(&a, 0, sizeof(a));
   a.x[0] = static_cast<const bf16*>(x);
   a.x_ld[0] = C;
+  a.partial[0] = partial;
+  a.pslots[0] = slots;
   a.out = static_cast<bf16*>(out);
   a.out_ld = C;
   a.gamma = gamma;
@@ -1388,17 +1435,12 @@ extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, con
   a.HW = HW;
   a.Cs = C;
   a.cpg = cpg;
+  a.pcpg = cpg;
   a.eps = eps;
   a.silu = silu;
-  a.G = groups;
-  a.nchunk = groupnorm_nchunk(HW);
-  const int nslab = 1;
-  float* partial = nullptr;
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * groups * GN_MAX_CHUNK * 2 * sizeof(float),
-                           static_cast<cudaStream_t>(stream)));
-  a.partial = partial;
-  CUDA_TRY(groupnorm_launch(a, B, nslab, static_cast<cudaStream_t>(stream)));
-  CUDA_TRY(cudaFreeAsync(partial, static_cast<cudaStream_t>(stream)));
+  a.nchunk = slots;
+  CUDA_TRY(groupnorm_launch(a, B, 1, s));
+  CUDA_TRY(cudaFreeAsync(partial, s));
   return WD_OK;
 }
 

@@ -1,6 +1,6 @@
 // Implicit-GEMM on the 5th-gen tensor cores (tcgen05 + TMEM accumulators + TMA operand staging).
 //
-// One kernel serves every dense contraction on the WordDiffusion hot path:
+// One persistent, warp-specialised kernel serves every dense contraction on the WordDiffusion hot path:
 //   * ResBlock / Upsample / Downsample 3x3 convolutions (reference unet.py:595,621,488,540):
 //       A rows are gathered straight from the NHWC bf16 activation by 4-D TMA boxes, one box per
 //       filter tap with shifted (w,h) start coordinates; out-of-bounds rows are zero-filled by the TMA
@@ -9,8 +9,14 @@
 //   * "K-concatenated" fusions: up to three A sources are walked back to back along K, so the
 //       640->320 skip 1x1 conv of the decoder ResBlocks (unet.py:632,671) accumulates into the same TMEM
 //       tile as the block's second 3x3 conv.
-// Epilogue (TMEM -> registers -> global) fuses: +bias[N], +row-bias[sample,N] (timestep-embedding add,
-// unet.py:657-666), +residual, SiLU, GEGLU (unet.py:127-129) and the bf16 / fp32 store.
+//   * the output convolution 320 -> 4 (unet.py:1457) with a 16-column tile whose epilogue applies the
+//       DDPM / DDIM update of train.py:229-236 and writes x_{t-1} (fp32 NCHW) directly.
+// Structure: grid = min(tiles, SMs) CTAs, 1 CTA / SM, tiles round-robin.  warp 0 = TMA producer (smem ring),
+// warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue.  The fp32 accumulator is double-buffered in
+// TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the MMAs of tile i+1.
+// Epilogue fusions: +bias[N], +row-bias[sample,N] (timestep-embedding add, unet.py:657-666), +residual, SiLU,
+// GEGLU (unet.py:127-129), bf16 / fp32 store, and per-(sample, group) GroupNorm partial statistics of the tensor
+// being written (consumed by groupnorm_apply_kernel; unet.py:429-431).
 #pragma once
 #include "common.cuh"
 
@@ -18,10 +24,14 @@ namespace wd {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_BLOCK_N = 160;  // 320 = 2 x 160; UMMA shape 128 x 160 x 16
+constexpr int GEMM_BLOCK_N_OUT = 16;  // output-conv tile (4 real columns)
 constexpr int GEMM_THREADS = 192;  // warp0: TMA producer, warp1: TMEM alloc + MMA issuer, warps2-5: epilogue
 constexpr int GEMM_MAX_SRC = 3;
 
 enum GemmAct : int { ACT_NONE = 0, ACT_SILU = 1 };
+enum GemmEpi : int { EPI_STD = 0, EPI_SAMPLER = 1 };
+enum StepMode : int { STEP_EPS_ONLY = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
 
 struct GemmArgs {
   int M;  // rows (pixels / tokens)
@@ -33,7 +43,8 @@ struct GemmArgs {
   int conv;                  // 1: 4-D (c,w,h,n) coordinates, 0: 2-D (c, row)
   int Wout;                  // output width  (conv)
   int HWout;                 // output pixels per image (conv)
-  // ---- epilogue ----
+  int epi;                   // GemmEpi
+  // ---- standard epilogue ----
   const float* bias;             // [N] or null (already permuted for GEGLU)
   const float* rowbias;          // [rows, rb_ld] fp32 or null
   const long long* rowbias_idx;  // optional: row = rowbias_idx[m / rows_per_sample]
@@ -46,6 +57,19 @@ struct GemmArgs {
   int out_f32;
   int act;
   int geglu;  // 1: tile columns [0,BN/2) are values, [BN/2,BN) gates; writes BN/2 columns per tile
+  // GroupNorm partial statistics of the written tensor: gn_partial[sample][N/gn_cpg groups][rows_per_sample/32][2]
+  float* gn_partial;  // null: off.  Needs gn_cpg == 10, rows_per_sample % 32 == 0
+  int gn_cpg;
+  // ---- sampler epilogue (EPI_SAMPLER; N tile = 16, columns 0..3 = predicted-noise channels) ----
+  float* eps_out;      // fp32 NCHW [B,4,H,W] or null
+  float* x;            // fp32 NCHW latent, updated in place when mode != STEP_EPS_ONLY
+  const float* noise;  // fp32 NCHW or null
+  int use_philox;
+  unsigned long long seed;
+  unsigned long long sample_offset;  // global index of sample 0 of this shard (GPU-count invariant noise)
+  int step_index;
+  float4 coef;
+  int mode;
 };
 
 struct GemmLaunch {
@@ -61,6 +85,6 @@ bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t 
                          uint64_t pix_stride_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n,
                          uint32_t stride_wh);
 cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);
-int gemm_tc_block_n();
+inline int gemm_tc_block_n() { return GEMM_BLOCK_N; }
 
 }  // namespace wd

@@ -7,50 +7,58 @@
 namespace wd {
 
 // =====================================================================================================
-// GroupNorm (+SiLU), two launches, no atomics (bit-reproducible):
-//   stats : grid (B, slab, chunk).  A CTA reduces its pixel chunk of one (sample, channel slab) to per-group
-//           {sum, sum of squares} in fp32 and writes them to partial[b][group][chunk][2].
-//   apply : same grid.  Every thread folds the chunk partials of its (<= 2) groups in a fixed order, forms the
-//           per-channel scale/shift once and streams its rows: y = silu(x * sc + sh), 16-byte loads and stores.
-// The tensor was just written by the producing GEMM epilogue, so the second read normally hits the 126 MB L2;
-// HBM sees about one read and one write of the activation (4 algorithmic bytes per element).
+// GroupNorm (+SiLU) in two parts, no atomics (bit-reproducible):
+//   statistics : per-tensor partial sums  partial[sample][32 groups][slots][{sum, sum of squares}]  (fp32) at the
+//                granularity of C/32 channels.  They are written by the epilogue of the tcgen05 GEMM that produces
+//                the tensor (gemm_tc.cu), or by groupnorm_stats_kernel for tensors produced elsewhere (conv_in).
+//   apply      : groupnorm_apply_kernel folds the slots of its (<= 2) groups in a fixed order, forms the
+//                per-channel scale/shift once and streams its rows: y = silu(x * sc + sh), 16-byte loads/stores,
+//                4 independent rows in flight per thread.  A GroupNorm over the channel concatenation of two tensors
+//                (decoder ResBlocks, unet.py:1750) reads each tensor's own partials and merges adjacent groups.
 // Thread t owns vector column t % (Cs/8) (8 channels) and pixel rows t / (Cs/8), stepping by R.
 // =====================================================================================================
 constexpr int GN_R = 8;
 
-__global__ void __launch_bounds__(1024) groupnorm_stats_kernel(const GroupNormArgs a) {
-  extern __shared__ float gn_part[];  // [2][R][Cs]
-  const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
-  const int Cs = a.Cs, cpg = a.cpg;
-  const int nv = Cs >> 3;
+__global__ void __launch_bounds__(1024) groupnorm_stats_kernel(const GroupNormStatsArgs a) {
+  extern __shared__ float gn_part[];  // [2][R][C]
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int C = a.C, cpg = a.pcpg;
+  const int nv = C >> 3;
   const int R = blockDim.x / nv;
   const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
-  const int ng = Cs / cpg;
-  const int P = a.HW / a.nchunk;
-  const int ld = a.x_ld[slab];
-  const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
+  const int ng = C / cpg;
+  const int P = a.HW / a.pslots;
+  const __nv_bfloat16* xb = a.x + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.ld;
 
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  for (int p = rl; p < P; p += R) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  for (int p0 = rl; p0 < P; p0 += 4 * R) {
+    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(u[j]);
-      s[2 * j] += f.x;
-      s[2 * j + 1] += f.y;
-      q[2 * j] += f.x * f.x;
-      q[2 * j + 1] += f.y * f.y;
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + i * R;
+      v[i] = (p < P) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * a.ld) + col) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        s[2 * j] += f.x;
+        s[2 * j + 1] += f.y;
+        q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+        q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+      }
     }
   }
   float* ps = gn_part;
-  float* pq = gn_part + R * Cs;
+  float* pq = gn_part + R * C;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    ps[rl * Cs + col * 8 + j] = s[j];
-    pq[rl * Cs + col * 8 + j] = q[j];
+    ps[rl * C + col * 8 + j] = s[j];
+    pq[rl * C + col * 8 + j] = q[j];
   }
   __syncthreads();
   // one thread per (group, {sum, sumsq}): fixed summation order
@@ -60,11 +68,27 @@ __global__ void __launch_bounds__(1024) groupnorm_stats_kernel(const GroupNormAr
     float t = 0.f;
     for (int c = 0; c < cpg; ++c) {
       float tc = 0.f;
-      for (int r = 0; r < R; ++r) tc += src[r * Cs + g * cpg + c];
+      for (int r = 0; r < R; ++r) tc += src[r * C + g * cpg + c];
       t += tc;
     }
-    a.partial[((static_cast<size_t>(b) * a.G + slab * ng + g) * a.nchunk + chunk) * 2 + which] = t;
+    a.partial[((static_cast<size_t>(b) * ng + g) * a.pslots + chunk) * 2 + which] = t;
   }
+}
+
+int groupnorm_stats_slots(int HW) {
+  int n = 1;
+  while (n < 8 && HW % (2 * n) == 0 && HW / (2 * n) >= 4 * GN_R) n *= 2;
+  return n;
+}
+
+cudaError_t groupnorm_stats_launch(const GroupNormStatsArgs& a, int B, cudaStream_t s) {
+  const int nv = a.C / 8;
+  if (a.C % 8 || a.C % a.pcpg || nv * GN_R > 1024 || !a.partial || a.pslots < 1 || a.HW % a.pslots)
+    return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(2) * GN_R * a.C * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  groupnorm_stats_kernel<<<dim3(B, a.pslots), nv * GN_R, smem, s>>>(a);
+  return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormArgs a) {
@@ -73,10 +97,13 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   const int nv = Cs >> 3;
   const int R = blockDim.x / nv;
   const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
-  const int ng = Cs / cpg;
   const int P = a.HW / a.nchunk;
   const int ld = a.x_ld[slab];
   const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
+  const int merge = cpg / a.pcpg;      // partial groups per GroupNorm group (1, or 2 for the concat GroupNorm)
+  const int PG = Cs / a.pcpg;          // partial groups of this source tensor
+  const int slots = a.pslots[slab];
+  const float* part = a.partial[slab] + static_cast<size_t>(b) * PG * slots * 2;
 
   float sc[8], sh[8];
   {
@@ -87,11 +114,11 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
       const int c = col * 8 + j;
       const int g = c / cpg;
       if (g != g_prev) {
-        const float* pp = a.partial + (static_cast<size_t>(b) * a.G + slab * ng + g) * a.nchunk * 2;
         float S = 0.f, Q = 0.f;
-        for (int k = 0; k < a.nchunk; ++k) {
-          S += __ldg(pp + 2 * k);
-          Q += __ldg(pp + 2 * k + 1);
+        for (int k = 0; k < merge * slots; ++k) {  // partial groups g*merge .. are contiguous: [pg][slot][2]
+          const float2 t = __ldg(reinterpret_cast<const float2*>(part) + static_cast<size_t>(g) * merge * slots + k);
+          S += t.x;
+          Q += t.y;
         }
         mean = S * inv_n;
         const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
@@ -105,43 +132,42 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   }
   const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
   __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.out_ld + slab * Cs;
-  for (int p = rl; p < P; p += R) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
+  for (int p0 = rl; p0 < P; p0 += 4 * R) {
+    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(u[j]);
-      float y0 = f.x * sc[2 * j] + sh[2 * j];
-      float y1 = f.y * sc[2 * j + 1] + sh[2 * j + 1];
-      if (a.silu) {
-        y0 = silu_f(y0);
-        y1 = silu_f(y1);
-      }
-      o[j] = pack_bf16x2(y0, y1);
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + i * R;
+      if (p < P) v[i] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
     }
-    reinterpret_cast<uint4*>(ob + static_cast<size_t>(p) * a.out_ld)[col] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + i * R;
+      if (p >= P) break;
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
+        float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+        if (a.silu) {
+          y0 = silu_f(y0);
+          y1 = silu_f(y1);
+        }
+        o[j] = pack_bf16x2(y0, y1);
+      }
+      reinterpret_cast<uint4*>(ob + static_cast<size_t>(p) * a.out_ld)[col] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
-}
-
-int groupnorm_nchunk(int HW) {
-  int n = 1;
-  while (n < GN_MAX_CHUNK && HW % (2 * n) == 0 && HW / (2 * n) >= 4 * GN_R) n *= 2;
-  return n;
 }
 
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s) {
   const int nv = a.Cs / 8;
-  if (a.Cs % 8 || a.Cs % a.cpg || nv * GN_R > 1024 || !a.partial || a.nchunk < 1 || a.HW % a.nchunk)
+  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || nv * GN_R > 1024 || a.nchunk < 1 || a.HW % a.nchunk)
     return cudaErrorInvalidValue;
-  const int threads = nv * GN_R;
-  const size_t smem = static_cast<size_t>(2) * GN_R * a.Cs * sizeof(float);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  dim3 grid(B, nslab, a.nchunk);
-  groupnorm_stats_kernel<<<grid, threads, smem, s>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  groupnorm_apply_kernel<<<grid, threads, 0, s>>>(a);
+  for (int i = 0; i < nslab; ++i)
+    if (!a.partial[i] || a.pslots[i] < 1) return cudaErrorInvalidValue;
+  groupnorm_apply_kernel<<<dim3(B, nslab, a.nchunk), nv * GN_R, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -411,103 +437,6 @@ cudaError_t conv_in_launch(const float* x, const float* w_packed, const float* b
 }
 
 // =====================================================================================================
-// Philox4x32-10 + Box-Muller: counter-based N(0,1) keyed by (seed, step, global element) so that the
-// noise of a latent does not depend on how the batch is sharded over GPUs.
-// =====================================================================================================
-WD_DEVINL void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-}
-WD_DEVINL float philox_normal(unsigned long long seed, unsigned long long elem, uint32_t step) {
-  uint32_t c[4] = {static_cast<uint32_t>(elem), static_cast<uint32_t>(elem >> 32), step, 0x5744u /*'WD'*/};
-  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  const float u1 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
-}
-
-// =====================================================================================================
-// conv_out (3x3, C -> 4, HBM-bound on the activation read) fused with the sampler update:
-//   DDPM (train.py:229-236):  x <- 1/sqrt(a) * (x - (1-a)/sqrt(1-ah) * eps) + sqrt(b) * z
-//   DDIM eta=0             :  x0 = (x - sqrt(1-ah_t) eps) / sqrt(ah_t);  x <- sqrt(ah_p) x0 + sqrt(1-ah_p) eps
-// One CTA per image row, one warp per output pixel (lanes split the channels, coalesced 128 B reads).
-// =====================================================================================================
-__global__ void __launch_bounds__(256) conv_out_step_kernel(const ConvOutArgs a) {
-  extern __shared__ float co_smem[];  // [9][C][4]
-  const int y = blockIdx.x, b = blockIdx.y;
-  const int C = a.C, H = a.H, W = a.W;
-  for (int i = threadIdx.x; i < 9 * C * 4; i += blockDim.x) co_smem[i] = __ldg(a.w_packed + i);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int npairs = C >> 1;
-  for (int px = warp; px < W; px += (blockDim.x >> 5)) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = px + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const uint32_t* hp = reinterpret_cast<const uint32_t*>(a.h + ((static_cast<size_t>(b) * H + yy) * W + xx) * C);
-      const float4* wt = reinterpret_cast<const float4*>(co_smem + static_cast<size_t>(tap) * C * 4);
-      for (int pr = lane; pr < npairs; pr += 32) {
-        const float2 f = unpack_bf16x2(__ldg(hp + pr));
-        const float4 w0 = wt[2 * pr], w1 = wt[2 * pr + 1];
-        acc[0] += f.x * w0.x + f.y * w1.x;
-        acc[1] += f.x * w0.y + f.y * w1.y;
-        acc[2] += f.x * w0.z + f.y * w1.z;
-        acc[3] += f.x * w0.w + f.y * w1.w;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    }
-    if (lane < 4) {
-      const int o = lane;
-      const float eps = (o == 0 ? acc[0] : o == 1 ? acc[1] : o == 2 ? acc[2] : acc[3]) + __ldg(a.bias + o);
-      const size_t idx = ((static_cast<size_t>(b) * 4 + o) * H + y) * W + px;
-      if (a.eps_out) a.eps_out[idx] = eps;
-      if (a.mode == STEP_DDPM) {
-        float z = 0.f;
-        if (a.noise)
-          z = __ldg(a.noise + idx);
-        else if (a.use_philox)
-          z = philox_normal(a.seed, a.sample_offset * (4ull * H * W) + idx, static_cast<uint32_t>(a.step_index));
-        const float xv = a.x[idx];
-        // same op order as the reference expression, no FMA contraction
-        const float inner = __fsub_rn(xv, __fmul_rn(a.coef.y, eps));
-        a.x[idx] = __fadd_rn(__fmul_rn(a.coef.x, inner), __fmul_rn(a.coef.z, z));
-      } else if (a.mode == STEP_DDIM) {
-        const float xv = a.x[idx];
-        const float x0 = __fmul_rn(__fsub_rn(xv, __fmul_rn(a.coef.y, eps)), a.coef.x);
-        a.x[idx] = __fadd_rn(__fmul_rn(a.coef.z, x0), __fmul_rn(a.coef.w, eps));
-      }
-    }
-  }
-}
-
-cudaError_t conv_out_step_launch(const ConvOutArgs& a, cudaStream_t s) {
-  if (a.C % 2) return cudaErrorInvalidValue;
-  const size_t smem = static_cast<size_t>(9) * a.C * 4 * sizeof(float);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_out_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
-  if (smem > 160 * 1024) return cudaErrorInvalidValue;
-  conv_out_step_kernel<<<dim3(a.H, a.B), 256, smem, s>>>(a);
-  return cudaGetLastError();
-}
-
-// =====================================================================================================
 // nearest 2x upsample, NHWC bf16
 // =====================================================================================================
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nv) {
@@ -597,18 +526,6 @@ __global__ void repack_conv_in_kernel(const float* __restrict__ w, float* __rest
 cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s) {
   const int total = Cout * Cin * 9;
   repack_conv_in_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cin);
-  return cudaGetLastError();
-}
-
-__global__ void repack_conv_out_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int C) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * C * 9) return;
-  const int tap = idx % 9, c = (idx / 9) % C, o = idx / (9 * C);
-  dst[(tap * C + c) * Cout + o] = w[idx];
-}
-cudaError_t repack_conv_out_launch(const float* w, float* dst, int Cout, int C, cudaStream_t s) {
-  const int total = Cout * C * 9;
-  repack_conv_out_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, C);
   return cudaGetLastError();
 }
 

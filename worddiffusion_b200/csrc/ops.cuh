@@ -1,29 +1,41 @@
 // Non-GEMM kernels of the WordDiffusion hot path (HBM / latency bound work).  See ops.cu.
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"  // StepMode
 
 namespace wd {
 
 // ---------------- GroupNorm (+SiLU), NHWC bf16 -> NHWC bf16 (reference unet.py:429-431,161-162) ----------------
+// Per-tensor partial statistics: partial[sample][C/pcpg groups][slots][2] fp32 ({sum, sum of squares}).
+struct GroupNormStatsArgs {
+  const __nv_bfloat16* x;  // [B, HW, ld]
+  int ld;
+  float* partial;
+  int HW, C;
+  int pcpg;    // channels per partial group
+  int pslots;  // pixel chunks per sample (groupnorm_stats_slots(HW))
+};
+int groupnorm_stats_slots(int HW);
+cudaError_t groupnorm_stats_launch(const GroupNormStatsArgs& a, int B, cudaStream_t s);
+
 struct GroupNormArgs {
-  const __nv_bfloat16* x[2];  // per channel slab: source tensor (already offset to its first channel)
+  const __nv_bfloat16* x[2];  // per channel slab: source tensor
   int x_ld[2];                // pixel stride (elements) of each source
+  const float* partial[2];    // partial statistics of each source tensor
+  int pslots[2];              // slots per (sample, partial group) of each source
   __nv_bfloat16* out;         // [B, HW, out_ld]; slab s writes channels [s*Cs, (s+1)*Cs)
   int out_ld;
   const float* gamma;  // [nslab*Cs]
   const float* beta;
   int HW;
-  int Cs;   // channels per slab (multiple of 8, contains whole groups)
-  int cpg;  // channels per group
+  int Cs;    // channels per slab (= channels of each source; multiple of 8, whole groups)
+  int cpg;   // channels per GroupNorm group
+  int pcpg;  // channels per partial-statistics group (cpg % pcpg == 0)
   float eps;
   int silu;
-  float* partial;  // scratch [B][G][nchunk][2] fp32: per-chunk {sum, sum of squares} of every group
-  int G;           // groups over all slabs
-  int nchunk;      // pixel chunks per sample (groupnorm_nchunk(HW))
+  int nchunk;  // pixel chunks per sample of the apply grid
 };
-constexpr int GN_MAX_CHUNK = 8;
-int groupnorm_nchunk(int HW);
-// two launches: statistics, then normalise (+SiLU)
+// normalise (+SiLU) from the partial statistics
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
 
 // ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------
@@ -68,25 +80,6 @@ cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __
 cudaError_t conv_in_launch(const float* x, const float* w_packed /*[36][Cout]*/, const float* bias, __nv_bfloat16* out,
                            int B, int H, int W, int Cout, cudaStream_t s);
 
-// ---------------- conv_out (3x3, C -> 4) fused with the sampler update (unet.py:1457; train.py:229-236) ----------------
-enum StepMode : int { STEP_EPS_ONLY = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
-struct ConvOutArgs {
-  const __nv_bfloat16* h;  // GN+SiLU'd activation, NHWC bf16 [B,H,W,C]
-  const float* w_packed;   // [9][C][4]
-  const float* bias;       // [4]
-  float* eps_out;          // fp32 NCHW [B,4,H,W] or null
-  float* x;                // fp32 NCHW latent, updated in place when mode != EPS_ONLY
-  const float* noise;      // fp32 NCHW or null
-  int use_philox;
-  unsigned long long seed;
-  unsigned long long sample_offset;  // global index of sample 0 of this shard (GPU-count invariant noise)
-  int step_index;
-  float4 coef;
-  int mode;
-  int B, H, W, C;
-};
-cudaError_t conv_out_step_launch(const ConvOutArgs& a, cudaStream_t s);
-
 // ---------------- nearest 2x upsample NHWC bf16 (unet.py:497) ----------------
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
 
@@ -100,9 +93,8 @@ cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int 
 // vector [N] -> dst[perm(n) + n_off] (accumulate: dst += src)
 cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
                               cudaStream_t s);
-// conv_in weight [Cout,4,3,3] -> [36][Cout];  conv_out weight [4,C,3,3] -> [9][C][4]
+// conv_in weight [Cout,4,3,3] -> [36][Cout]
 cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s);
-cudaError_t repack_conv_out_launch(const float* w, float* dst, int Cout, int C, cudaStream_t s);
 
 // ---------------- fp32 context encoder (unet.py:815-882) ----------------
 // tokens [B, L] (int64 or int32) -> emb[B, L, D] = E[token] (+ pe[l] when add_pe)
