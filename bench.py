@@ -282,6 +282,10 @@ def run_ours(args):
                           "share": round(tms / total_t, 4) if total_t else None,
                           "tflops": round(cls_f[kname] / (tms * 1e-3) / 1e12, 2) if tms > 0 else None,
                           "gbs": round(cls_b[kname] / (tms * 1e-3) / 1e9, 1) if tms > 0 else None}
+    if args.ops_out:
+        with open(args.ops_out, "w") as f:
+            json.dump([{"i": i, "kind": k, "gflop": fl / 1e9, "mbytes": by / 1e6, "us": 1e3 * msum / max(n_steps_prof, 1)}
+                       for i, (k, fl, by, msum) in enumerate(prof)], f, indent=0)
     g = "gemm_tc"
     ach = cls_f[g] / (cls_t[g] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM: 3x3 convs, 1x1 convs, linears)", "bound": "tensor",
@@ -318,6 +322,7 @@ def main():
     ap.add_argument("--model", default="unet", choices=["unet", "unetPhosc"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ops-out", default=None, help="write the per-launch device times of one step (JSON) to this path")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -133,7 +133,7 @@ struct Op {
   AttnSmallArgs as;
   AttnFlashArgs af;
   struct { bf16* out; int B, dim; } temb;
-  struct { const float* w; const float* bias; bf16* out; int B, H, W, Cout; } cin;
+  struct { bf16* out; int B, H, W; } cin;  // im2col of the latent
   struct { const bf16* x; bf16* out; int B, H, W, C; } up;
   struct { int which; const float* E; int vocab; const float* pe; int add_pe; float* out; int B, L, D; } emb;
   struct { const float* x; const float* W; const float* b; float* out; int M, N, K; } lin;
@@ -170,8 +170,7 @@ struct wd_engine {
   Block middle;
   GemmW te0, te2, emb_all;
   float* label_emb = nullptr;
-  float* conv_in_w = nullptr;
-  float* conv_in_b = nullptr;
+  GemmW conv_in;  // [model_channels, 128] bf16: im2col columns hi(36) | lo(36) | zero pad
   NormW out_gn;
   GemmW conv_out;  // [16, 9*C] bf16, rows >= out_channels are zero
   // context encoder (fp32)
@@ -308,7 +307,7 @@ struct Builder {
       t.a2_kv = kv_fused(tp + "attn2", inner, ctx_dim);
       t.a2_out = linear(tp + "attn2.to_out.0", inner, inner, true);
       t.ln3 = norm(tp + "norm3", inner);
-      t.ff_proj = linear(tp + "ff.net.0.proj", inner * 8, inner, true, bn);
+      t.ff_proj = linear(tp + "ff.net.0.proj", inner * 8, inner, true, gemm_geglu_block(inner * 8));
       t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
       s.blocks.push_back(t);
     }
@@ -377,10 +376,12 @@ struct Builder {
       slot("label_emb.weight", S_F32, e->label_emb, static_cast<int64_t>(c.num_classes) * ted);
     }
     // input_blocks.0.0 : conv_in
-    e->conv_in_w = A.alloc<float>(static_cast<size_t>(36) * mc);
-    e->conv_in_b = A.alloc<float>(mc);
-    slot("input_blocks.0.0.weight", S_CONV_IN, e->conv_in_w, static_cast<int64_t>(mc) * c.in_channels * 9, mc, c.in_channels);
-    slot("input_blocks.0.0.bias", S_VEC, e->conv_in_b, mc);
+    e->conv_in.N = mc;
+    e->conv_in.K = 128;
+    e->conv_in.w = A.alloc<bf16>(static_cast<size_t>(mc) * 128);
+    e->conv_in.bias = A.alloc<float>(mc);
+    slot("input_blocks.0.0.weight", S_CONV_IN, e->conv_in.w, static_cast<int64_t>(mc) * c.in_channels * 9, mc, c.in_channels);
+    slot("input_blocks.0.0.bias", S_VEC, e->conv_in.bias, mc);
     e->input_blocks.push_back(Block{Layer{L_CONVIN, 0}});
 
     int emb_cols = 0;
@@ -589,7 +590,7 @@ extern "C" int wd_engine_load_param(wd_engine* e, const char* name, const float*
       CUDA_TRY(repack_linear_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, sl.n_off, sl.geglu_bn, s));
       break;
     case S_CONV_IN:
-      CUDA_TRY(repack_conv_in_launch(src, static_cast<float*>(sl.dst), sl.N, sl.K, s));
+      CUDA_TRY(repack_conv_in_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, s));
       break;
   }
   sl.loaded = true;
@@ -755,10 +756,22 @@ struct PlanBuilder {
     op.bytes = 2.0 * (static_cast<double>(M) * w.K + static_cast<double>(w.N) * w.K + static_cast<double>(M) * (ep.geglu ? w.N / 2 : w.N));
     const int bn = (ep.epi == EPI_SAMPLER) ? GEMM_BLOCK_N_OUT : gemm_tc_block_n();
     if (w.N % bn) { err = "gemm: N must be a multiple of the N tile"; return false; }
+    const int b_box = gemm_b_box_rows(a);
     if (!dry) {
       for (size_t i = srcs.size(); i < GEMM_MAX_SRC; ++i) op.gemm.mapA[i] = op.gemm.mapA[0];
-      if (!tmap_encode_2d_bf16(&op.gemm.mapB, w.w, w.K, w.N, w.K, GEMM_BLOCK_K, bn)) {
+      if (!tmap_encode_2d_bf16(&op.gemm.mapB, w.w, w.K, w.N, w.K, GEMM_BLOCK_K, b_box)) {
         err = "cuTensorMapEncodeTiled failed (B)";
+        return false;
+      }
+      op.gemm.mapOut = op.gemm.mapB;
+      op.gemm.mapRes = op.gemm.mapB;
+      if (ep.epi != EPI_SAMPLER && !ep.out_f32 &&
+          !tmap_encode_out_bf16(&op.gemm.mapOut, ep.out, ep.geglu ? w.N / 2 : w.N, M, ep.out_ld)) {
+        err = "cuTensorMapEncodeTiled failed (out)";
+        return false;
+      }
+      if (ep.residual && !tmap_encode_out_bf16(&op.gemm.mapRes, ep.residual, w.N, M, ep.res_ld)) {
+        err = "cuTensorMapEncodeTiled failed (residual)";
         return false;
       }
     }
@@ -801,7 +814,7 @@ struct PlanBuilder {
     op.gn.eps = eps;
     op.gn.silu = silu;
     op.gn.pcpg = Cs / 32;
-    op.gn.nchunk = groupnorm_stats_slots(HW);
+    op.gn.nchunk = groupnorm_apply_chunks(HW);
     for (int i = 0; i < nslab; ++i) {
       if (!srcs[i].pslots) { err = "groupnorm: source tensor carries no statistics"; return false; }
       op.gn.partial[i] = srcs[i].stats;
@@ -1062,15 +1075,27 @@ struct PlanBuilder {
         Act out;
         switch (l.kind) {
           case L_CONVIN: {
+            // conv_in = im2col (hi/lo bf16 split of the fp32 latent) + tcgen05 GEMM with K = 128
             out = new_act(c.latent_h, c.latent_w, mc);
+            const int HW = c.latent_h * c.latent_w;
+            bf16* col = A.alloc<bf16>(static_cast<size_t>(B) * HW * 128);
             Op op;
             memset(&op, 0, sizeof(op));
             op.kind = OP_CONV_IN;
-            op.cin = {e->conv_in_w, e->conv_in_b, out.p, B, c.latent_h, c.latent_w, mc};
-            op.flops = 2.0 * B * c.latent_h * c.latent_w * mc * 36;
-            op.bytes = static_cast<double>(B) * c.latent_h * c.latent_w * (4 * 4 + 2 * mc);
+            op.cin = {col, B, c.latent_h, c.latent_w};
+            op.bytes = static_cast<double>(B) * HW * (4 * 4 + 2 * 128);
             sops.push_back(op);
-            if (!ensure_stats(sops, out)) return false;
+            Epi ep;
+            ep.out = out.p;
+            ep.out_ld = mc;
+            ep.rows_per_sample = HW;
+            ep.stats_for = &out;
+            if (!gemm_op(sops, B * HW, false, 0, 0, {ASrc{col, 128, 128, 1, 1, 1, 1}}, e->conv_in, ep)) return false;
+            for (auto it = sops.rbegin(); it != sops.rend(); ++it)
+              if (it->kind == OP_GEMM) {
+                it->flops = 2.0 * B * HW * mc * 36;  // algorithmic work of the 3x3x4 convolution, not of the padded K
+                break;
+              }
             break;
           }
           case L_RES:
@@ -1263,7 +1288,7 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
         err = attn_flash_launch(op.af, e->cur->B, s);
         break;
       case OP_CONV_IN:
-        err = conv_in_launch(rc.x, op.cin.w, op.cin.bias, op.cin.out, op.cin.B, op.cin.H, op.cin.W, op.cin.Cout, s);
+        err = conv_in_im2col_launch(rc.x, op.cin.out, op.cin.B, op.cin.H, op.cin.W, s);
         break;
       case OP_GNSTATS:
         err = groupnorm_stats_launch(op.gs, op.gn_B, s);
@@ -1438,7 +1463,7 @@ extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, con
   a.pcpg = cpg;
   a.eps = eps;
   a.silu = silu;
-  a.nchunk = slots;
+  a.nchunk = groupnorm_apply_chunks(HW);
   CUDA_TRY(groupnorm_launch(a, B, 1, s));
   CUDA_TRY(cudaFreeAsync(partial, s));
   return WD_OK;
@@ -1478,7 +1503,10 @@ extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, cons
   a.geglu = geglu;
   if (!tmap_encode_2d_bf16(&L.mapA[0], a_, K, M, K, GEMM_BLOCK_K, GEMM_BLOCK_M)) return fail(WD_ERR_CUDA, "tensor map A");
   L.mapA[1] = L.mapA[2] = L.mapA[0];
-  if (!tmap_encode_2d_bf16(&L.mapB, w, K, N, K, GEMM_BLOCK_K, gemm_tc_block_n())) return fail(WD_ERR_CUDA, "tensor map B");
+  if (!tmap_encode_2d_bf16(&L.mapB, w, K, N, K, GEMM_BLOCK_K, gemm_b_box_rows(a))) return fail(WD_ERR_CUDA, "tensor map B");
+  L.mapOut = L.mapRes = L.mapB;
+  if (!out_f32 && !tmap_encode_out_bf16(&L.mapOut, out, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map out");
+  if (residual && !tmap_encode_out_bf16(&L.mapRes, residual, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map residual");
   CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
@@ -1524,8 +1552,11 @@ extern "C" int wd_op_conv3x3(const void* x, const void* w_packed, const float* b
   if (!tmap_encode_4d_bf16(&L.mapA[0], x, Cin, W, H, B, Cin, GEMM_BLOCK_K, bw, bh, bnn, stride))
     return fail(WD_ERR_CUDA, "tensor map A");
   L.mapA[1] = L.mapA[2] = L.mapA[0];
-  if (!tmap_encode_2d_bf16(&L.mapB, w_packed, 9 * Cin, Cout, 9 * Cin, GEMM_BLOCK_K, gemm_tc_block_n()))
+  if (!tmap_encode_2d_bf16(&L.mapB, w_packed, 9 * Cin, Cout, 9 * Cin, GEMM_BLOCK_K, gemm_b_box_rows(a)))
     return fail(WD_ERR_CUDA, "tensor map B");
+  L.mapOut = L.mapRes = L.mapB;
+  if (!tmap_encode_out_bf16(&L.mapOut, out, Cout, a.M, Cout)) return fail(WD_ERR_CUDA, "tensor map out");
+  if (residual && !tmap_encode_out_bf16(&L.mapRes, residual, Cout, a.M, Cout)) return fail(WD_ERR_CUDA, "tensor map residual");
   CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
@@ -1535,12 +1566,12 @@ extern "C" int wd_op_pack_conv3x3(const float* w, void* dst, int Cout, int Cin, 
   return WD_OK;
 }
 extern "C" int wd_op_pack_linear(const float* w, void* dst, int N, int K, int geglu_perm, void* stream) {
-  CUDA_TRY(repack_linear_launch(w, static_cast<bf16*>(dst), N, K, K, 0, 0, geglu_perm ? gemm_tc_block_n() : 0,
+  CUDA_TRY(repack_linear_launch(w, static_cast<bf16*>(dst), N, K, K, 0, 0, geglu_perm ? gemm_geglu_block(N) : 0,
                                 static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 extern "C" int wd_op_pack_vec_geglu(const float* v, float* dst, int N, void* stream) {
-  CUDA_TRY(repack_vec_launch(v, dst, N, 0, gemm_tc_block_n(), 0, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(repack_vec_launch(v, dst, N, 0, gemm_geglu_block(N), 0, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 

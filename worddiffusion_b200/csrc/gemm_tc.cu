@@ -2,25 +2,33 @@
 #include "gemm_tc.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace wd {
 
-template <int BN>
+template <int BN, int STAGES_, int NSTG_>
 struct Cfg {
-  static constexpr int STAGES = (BN == GEMM_BLOCK_N) ? 6 : 8;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int NSTG = NSTG_;  // staging buffers per column half (0: the epilogue writes global memory directly)
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BN * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STRIDE = (BN == GEMM_BLOCK_N) ? 256 : 32;  // TMEM column offset of accumulator buffer 1
   static constexpr int TMEM_COLS = (BN == GEMM_BLOCK_N) ? 512 : 64;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;  // one dense [128][40] bf16 sub-tile
+  static constexpr int HALF_STG_BYTES = 2 * SUB_BYTES;             // 80 columns of one column half
+  static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// lane L ends with the sum over the warp's 32 lanes of v[L] (v is destroyed): 31 shuffles
-WD_DEVINL float warp_transpose_reduce32(float (&v)[32], int lane) {
+// lane L (< 16) ends with the sum over the warp's 32 lanes of v[L] (v is destroyed): 16 + 15 shuffles
+WD_DEVINL float warp_transpose_reduce16(float (&v)[16], int lane) {
+  // fold the upper 16 lanes onto the lower 16: afterwards lanes L and L^16 hold the same 16 sums
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int i = 0; i < s; ++i) {
@@ -32,25 +40,30 @@ WD_DEVINL float warp_transpose_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int STAGES, int NSTG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                const GemmArgs args) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, STAGES, NSTG>;
+  constexpr int NB = NSTG > 0 ? NSTG : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES;  // [half][NSTG][2 sub-tiles][128][40] bf16
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;      // [2 halves][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = args.N / BN;
   const int m_tiles = (args.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int total_tiles = n_tiles * m_tiles;
+  constexpr int EPI_ACTIVE_WARPS = (EPI == EPI_SAMPLER) ? 4 : GEMM_EPI_WARPS;
 
   int total_k = 0;
 #pragma unroll
@@ -62,14 +75,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (args.num_src > 1) tma_prefetch_desc(&mapA1);
     if (args.num_src > 2) tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapB);
+    if (NSTG > 0 && !args.out_f32) tma_prefetch_desc(&mapOut);
+    if (NSTG > 0 && args.residual) tma_prefetch_desc(&mapRes);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], EPI_ACTIVE_WARPS);  // one arrival per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -102,14 +118,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int dx = (taps == 9) ? tap % 3 - 1 : 0;
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              mbar_arrive_expect_tx(&full_bar[stage], ((args.dbg & 8) ? 0 : C::A_BYTES) + ((args.dbg & 4) ? 0 : C::B_BYTES));
               uint8_t* sA = smem + stage * C::STAGE_BYTES;
               uint8_t* sB = sA + C::A_BYTES;
-              if (args.conv)
-                tma_load_4d(sA, mapA, &full_bar[stage], ch * GEMM_BLOCK_K, dx, oh0 * st + dy, img);
-              else
-                tma_load_2d(sA, mapA, &full_bar[stage], ch * GEMM_BLOCK_K, m0);
-              tma_load_2d(sB, &mapB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+              if (!(args.dbg & 8)) {
+                if (args.conv)
+                  tma_load_4d(sA, mapA, &full_bar[stage], ch * GEMM_BLOCK_K, dx, oh0 * st + dy, img);
+                else
+                  tma_load_2d(sA, mapA, &full_bar[stage], ch * GEMM_BLOCK_K, m0);
+              }
+              if (!(args.dbg & 4)) tma_load_2d(sB, &mapB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
               ++kb;
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -135,10 +153,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + C::A_BYTES);
+          if (!(args.dbg & 16)) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field
+              umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -146,23 +166,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
     }
-  } else {
-    // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
-    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+  } else if (warp - 2 < EPI_ACTIVE_WARPS) {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;            // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int half = (warp - 2) >> 2;  // column half of the tile handled by this warp
     const int row = q * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int n_tile = tile % n_tiles;
-      const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
-      const int n0 = n_tile * BN;
-      const int m = m0 + row;
-      const bool valid = m < args.M;
-      mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
 
-      if constexpr (EPI == EPI_SAMPLER) {
+    if constexpr (EPI == EPI_SAMPLER) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int m = (tile / n_tiles) * GEMM_BLOCK_M + row;
+        const bool valid = m < args.M;
+        mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
         // ---- output conv: columns 0..3 = predicted noise of pixel m; fused sampler update (train.py:229-236) ----
         uint32_t v[16];
         tmem_ld_32x32b_x16(t_row, v);
@@ -195,138 +213,219 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
           }
         }
-      } else {
+      }
+    } else {
+      constexpr int HC = BN / 2;             // accumulator columns per warp (80)
+      constexpr int NSUB = HC / GEMM_SUB_N;  // staging sub-tiles per half: 2 (GEGLU fills only the first)
+      const bool leader = (q == 0) && (lane == 0);  // issues this half's TMA stores / residual loads
+      const int bar_id = 1 + half;
+      const bool use_stg = (NSTG > 0) && !args.out_f32;
+      const bool has_res = use_stg && args.residual != nullptr;
+      uint8_t* const stg_half = stg + half * NB * C::HALF_STG_BYTES;
+      uint64_t* const res_bar = res_full_bar + half * 2;
+
+      auto issue_res_load = [&](int tile_, int sb_) {
+        const int m0_ = (tile_ / n_tiles) * GEMM_BLOCK_M;
+        const int c0_ = (tile_ % n_tiles) * BN + half * HC;
+        mbar_arrive_expect_tx(&res_bar[sb_], C::HALF_STG_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+          tma_load_2d(stg_half + sb_ * C::HALF_STG_BYTES + s * C::SUB_BYTES, &mapRes, &res_bar[sb_],
+                      c0_ + s * GEMM_SUB_N, m0_);
+      };
+      if (has_res && leader && static_cast<int>(blockIdx.x) < total_tiles) issue_res_load(blockIdx.x, 0);
+
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int sb = it % NB;
+        const int n_tile = tile % n_tiles;
+        const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
+        const int n0 = n_tile * BN;
+        const int m = m0 + row;
+        const bool valid = m < args.M;
+        mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+
+        // ---- drain this warp's 32 x 80 accumulator block, then hand the TMEM buffer back to the MMA warp ----
+        uint32_t v[HC];
+        if (args.dbg & 256) {
+#pragma unroll
+          for (int c = 0; c < HC; ++c) v[c] = 0;
+        } else if (!args.geglu) {
+#pragma unroll
+          for (int c = 0; c < HC / 16; ++c) tmem_ld_32x32b_x16p(t_row + half * HC + c * 16, v + c * 16);
+        } else {
+          // values: tile columns [half*40, +40), gates: [80 + half*40, +40)
+          tmem_ld_32x32b_x16p(t_row + half * 40, v);
+          tmem_ld_32x32b_x16p(t_row + half * 40 + 16, v + 16);
+          tmem_ld_32x32b_x8(t_row + half * 40 + 32, v + 32);
+          tmem_ld_32x32b_x16p(t_row + HC + half * 40, v + 40);
+          tmem_ld_32x32b_x16p(t_row + HC + half * 40 + 16, v + 56);
+          tmem_ld_32x32b_x8(t_row + HC + half * 40 + 32, v + 72);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+
+        if (args.dbg & 2) continue;
         const int sample = valid ? (m / args.rows_per_sample) : 0;
         const float* rb = nullptr;
         if (args.rowbias) {
           const long long r = args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample);
           rb = args.rowbias + r * args.rb_ld;
         }
-        if (!args.geglu) {
-          constexpr int NCH = BN / 32;
-          float gs[32];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
+
+        // ---- staging buffer `sb` of this half must be free (its previous TMA store has read it) ----
+        if (use_stg) {
+          if (has_res) {
+            mbar_wait(&res_bar[sb], (it / NB) & 1);  // the residual tile has landed in the staging buffer
+          } else if (!(args.dbg & 64)) {
+            if (leader) {
+              if (NSTG > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            }
+            named_barrier_sync(bar_id, 128);
+          }
+        }
+        uint8_t* const srow = stg_half + sb * C::HALF_STG_BYTES + row * (GEMM_SUB_N * 2);
+
+        if (args.dbg & 128) {
+        } else if (!args.geglu) {
+          float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
           if (args.gn_partial) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gs[i] = 0.f;
+            for (int i = 0; i < 16; ++i) gs[i] = 0.f;
           }
+          const int nb = n0 + half * HC;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_row + c * 32, v);
-            tmem_ld_wait();
-            if (c == NCH - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            }
-            const int n = n0 + c * 32;
-            float f[32];
+          for (int c = 0; c < HC / 8; ++c) {  // 8 columns = one 16-byte staging chunk
+            float f[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c * 8 + j]);
             if (args.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + n + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8 + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             if (rb) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + n + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8 + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
-            if (args.residual && valid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(args.residual + static_cast<size_t>(m) * args.res_ld + n);
+            uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * C::SUB_BYTES + (c % 5) * 16);
+            if (has_res) {
+              const uint4 r4 = *sp;
+              const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {
-                const uint4 r4 = __ldg(rp + g4);
-                const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = unpack_bf16x2(ru[j]);
+                f[2 * j] += t.x;
+                f[2 * j + 1] += t.y;
+              }
+            } else if (args.residual && valid) {  // direct-store path with a residual (fp32 output): not used by the plan
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(args.residual + static_cast<size_t>(m) * args.res_ld + nb + c * 8));
+              const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = unpack_bf16x2(ru[j]);
-                  f[g4 * 8 + 2 * j] += t.x;
-                  f[g4 * 8 + 2 * j + 1] += t.y;
-                }
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = unpack_bf16x2(ru[j]);
+                f[2 * j] += t.x;
+                f[2 * j + 1] += t.y;
               }
             }
             if (args.act == ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
             }
             if (args.gn_partial) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int g = (c * 32 + j) / 10;  // compile-time after unrolling (BN = 160 -> 16 groups of 10)
+              for (int j = 0; j < 8; ++j) {
+                const int g = (c * 8 + j) / 10;  // compile-time after unrolling (80 columns -> 8 groups of 10)
                 const float x = valid ? f[j] : 0.f;
                 gs[2 * g] += x;
                 gs[2 * g + 1] = fmaf(x, x, gs[2 * g + 1]);
               }
             }
-            if (valid) {
+            if (use_stg) {
+              *sp = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            } else if (valid) {
               if (args.out_f32) {
-                float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + n);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
+                op[0] = make_float4(f[0], f[1], f[2], f[3]);
+                op[1] = make_float4(f[4], f[5], f[6], f[7]);
               } else {
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
+                *op = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
               }
             }
           }
           if (args.gn_partial) {
-            // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L keeps entry L
-            const float tot = warp_transpose_reduce32(gs, lane);
+            // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
+            const float tot = warp_transpose_reduce16(gs, lane);
             const int mw = m0 + q * 32;
-            if (mw < args.M) {
+            if (mw < args.M && lane < 16) {
               const int smp = mw / args.rows_per_sample;
               const int slot = (mw % args.rows_per_sample) >> 5;
               const int nslot = args.rows_per_sample >> 5;
               const int G = args.N / 10;
-              const int g = n_tile * (BN / 10) + (lane >> 1);
+              const int g = n_tile * (BN / 10) + half * (HC / 10) + (lane >> 1);
               args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
             }
           }
         } else {
-          constexpr int HALF = BN / 2;
+          // GEGLU: out = (value + bv) * gelu(gate + bg); 40 output columns per warp = one staging sub-tile
+          const int nbv = n0 + half * 40;       // bias index of the value columns inside the permuted layout
+          const int nbg = n0 + HC + half * 40;  // ... of the gate columns
 #pragma unroll
-          for (int c = 0; c < HALF / 16; ++c) {
-            uint32_t va[16], vg[16];
-            tmem_ld_32x32b_x16(t_row + c * 16, va);
-            tmem_ld_32x32b_x16(t_row + HALF + c * 16, vg);
-            tmem_ld_wait();
-            if (c == HALF / 16 - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          for (int c = 0; c < 5; ++c) {
+            float f[8];
+            float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0, bg0 = bv0, bg1 = bv0;
+            if (args.bias) {
+              bv0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8));
+              bv1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8 + 4));
+              bg0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8));
+              bg1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8 + 4));
             }
-            const int nb = n0 + c * 16;  // bias index of the value columns inside the permuted layout
-            float f[16];
+            const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+            const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-              if (args.bias) {
-                ba = __ldg(reinterpret_cast<const float4*>(args.bias + nb + j));
-                bg = __ldg(reinterpret_cast<const float4*>(args.bias + nb + HALF + j));
-              }
-              f[j] = (__uint_as_float(va[j]) + ba.x) * gelu_fast_f(__uint_as_float(vg[j]) + bg.x);
-              f[j + 1] = (__uint_as_float(va[j + 1]) + ba.y) * gelu_fast_f(__uint_as_float(vg[j + 1]) + bg.y);
-              f[j + 2] = (__uint_as_float(va[j + 2]) + ba.z) * gelu_fast_f(__uint_as_float(vg[j + 2]) + bg.z);
-              f[j + 3] = (__uint_as_float(va[j + 3]) + ba.w) * gelu_fast_f(__uint_as_float(vg[j + 3]) + bg.w);
+            for (int j = 0; j < 8; ++j)
+              f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
+            const uint4 o4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            if (use_stg) {
+              *reinterpret_cast<uint4*>(srow + c * 16) = o4;
+            } else if (valid) {
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + n_tile * HC + half * 40 + c * 8) = o4;
             }
-            if (valid) {
-              const int n_out = n_tile * HALF + c * 16;
-              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + n_out);
-              op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-              op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+        }
+
+        // ---- publish the staged half tile with TMA; prefetch the residual of this CTA's next tile ----
+        if (use_stg) {
+          if (!(args.dbg & 32)) fence_proxy_async();  // generic-proxy smem writes -> visible to the async proxy (TMA)
+          named_barrier_sync(bar_id, 128);
+          if (leader && !(args.dbg & 1)) {
+            const uint8_t* src = stg_half + sb * C::HALF_STG_BYTES;
+            if (!args.geglu) {
+#pragma unroll
+              for (int s = 0; s < NSUB; ++s)
+                tma_store_2d(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0);
+            } else {
+              tma_store_2d(&mapOut, src, n_tile * HC + half * 40, m0);
+            }
+            bulk_commit_group();
+            const int next = tile + gridDim.x;
+            if (has_res && next < total_tiles) {
+              // the buffer the next tile uses was last read by the store issued NSTG tiles before it
+              if (NSTG > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              issue_res_load(next, (it + 1) % NB);
             }
           }
         }
       }
+      if (use_stg && leader) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
     }
   }
 
@@ -386,6 +485,20 @@ bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {GEMM_SUB_N, GEMM_BLOCK_M};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(out) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -397,31 +510,67 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int STAGES, int NSTG>
 static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, STAGES, NSTG>;
+  static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
   const GemmArgs& a = L.args;
   if (a.N % BN != 0 || a.M <= 0) return cudaErrorInvalidValue;
   const int tiles = (a.N / BN) * ((a.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapB, a);
+  gemm_tc_kernel<BN, EPI, STAGES, NSTG><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
+                                                                                      L.mapB, L.mapOut, L.mapRes, a);
   return cudaGetLastError();
 }
 
-cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream) {
+static int gemm_dbg_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+bool gemm_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+bool gemm_uses_pair(const GemmArgs& a) { return gemm_pair_enabled() && gemm_pair_supported(a); }
+int gemm_b_box_rows(const GemmArgs& a) {
+  if (a.epi == EPI_SAMPLER) return GEMM_BLOCK_N_OUT;
+  return gemm_uses_pair(a) ? 80 : GEMM_BLOCK_N;
+}
+int gemm_geglu_block(int N) { return (gemm_pair_enabled() && N % GEMM_PAIR_BLOCK_N == 0) ? GEMM_PAIR_BLOCK_N : GEMM_BLOCK_N; }
+
+cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
+  GemmLaunch L = L0;
+  L.args.dbg = gemm_dbg_flags();
   const GemmArgs& a = L.args;
   if (a.epi == EPI_SAMPLER) {
     if (a.N != GEMM_BLOCK_N_OUT || !a.bias || !a.conv) return cudaErrorInvalidValue;
-    return launch_impl<GEMM_BLOCK_N_OUT, EPI_SAMPLER>(L, stream);
+    return launch_impl<GEMM_BLOCK_N_OUT, EPI_SAMPLER, 8, 0>(L, stream);
   }
   if (a.gn_partial && (a.gn_cpg != 10 || a.rows_per_sample % 32 || a.geglu || a.N % 10)) return cudaErrorInvalidValue;
-  return launch_impl<GEMM_BLOCK_N, EPI_STD>(L, stream);
+  if (a.geglu && a.residual) return cudaErrorInvalidValue;
+  if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
+  int total_k = 0;
+  for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
+  // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
+  // short K loops are epilogue / store bound: spend it on a second staging buffer
+  if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
+  return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 2>(L, stream);
 }
 
 }  // namespace wd

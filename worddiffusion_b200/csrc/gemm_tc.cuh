@@ -12,8 +12,15 @@
 //   * the output convolution 320 -> 4 (unet.py:1457) with a 16-column tile whose epilogue applies the
 //       DDPM / DDIM update of train.py:229-236 and writes x_{t-1} (fp32 NCHW) directly.
 // Structure: grid = min(tiles, SMs) CTAs, 1 CTA / SM, tiles round-robin.  warp 0 = TMA producer (smem ring),
-// warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue.  The fp32 accumulator is double-buffered in
-// TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the MMAs of tile i+1.
+// warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue.  The fp32 accumulator is double-buffered in
+// TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Epilogue: a warp may only read the TMEM lane quarter (warp % 4), so two warps share each quarter and split the
+// 160 tile columns 80/80 ("column halves"; the two halves are independent pipelines).  Each warp drains its 32 rows x 80
+// columns with five tcgen05.ld.x16 in flight, hands the accumulator back to the MMA warp, applies the fusions in
+// registers, and writes bf16 into a shared-memory staging tile made of dense [128 rows][40 columns] sub-tiles (80-byte
+// rows: bank-conflict-free for one-row-per-thread 16-byte accesses), which one elected thread per half stores with TMA
+// (cp.async.bulk.tensor, bulk groups).  A residual operand is prefetched by TMA into the same staging sub-tiles one tile
+// ahead and added in place.  Nothing on the output path is an uncoalesced per-thread global access.
 // Epilogue fusions: +bias[N], +row-bias[sample,N] (timestep-embedding add, unet.py:657-666), +residual, SiLU,
 // GEGLU (unet.py:127-129), bf16 / fp32 store, and per-(sample, group) GroupNorm partial statistics of the tensor
 // being written (consumed by groupnorm_apply_kernel; unet.py:429-431).
@@ -26,7 +33,9 @@ constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int GEMM_BLOCK_N = 160;  // 320 = 2 x 160; UMMA shape 128 x 160 x 16
 constexpr int GEMM_BLOCK_N_OUT = 16;  // output-conv tile (4 real columns)
-constexpr int GEMM_THREADS = 192;  // warp0: TMA producer, warp1: TMEM alloc + MMA issuer, warps2-5: epilogue
+constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0: TMA producer, warp1: TMEM alloc + MMA issuer, warps2-9: epilogue
+constexpr int GEMM_SUB_N = 40;      // staging / TMA-store sub-tile width (columns)
 constexpr int GEMM_MAX_SRC = 3;
 
 enum GemmAct : int { ACT_NONE = 0, ACT_SILU = 1 };
@@ -70,11 +79,14 @@ struct GemmArgs {
   int step_index;
   float4 coef;
   int mode;
+  int dbg;  // experiment switches (env WD_GEMM_DBG, tools/op_bench.py): 1 no TMA store, 2 no epilogue math, 4 no B loads
 };
 
 struct GemmLaunch {
   CUtensorMap mapA[GEMM_MAX_SRC];
   CUtensorMap mapB;
+  CUtensorMap mapOut;  // bf16 output [M, out columns], box {GEMM_SUB_N, GEMM_BLOCK_M}, no swizzle (unused: out_f32 / sampler)
+  CUtensorMap mapRes;  // residual, same box (unused when args.residual == nullptr)
   GemmArgs args;
 };
 
@@ -84,7 +96,19 @@ bool tmap_encode_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint6
 bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                          uint64_t pix_stride_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n,
                          uint32_t stride_wh);
+// output / residual tensor map of the staging sub-tiles
+bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems);
 cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);
-inline int gemm_tc_block_n() { return GEMM_BLOCK_N; }
+inline int gemm_tc_block_n() { return GEMM_BLOCK_N; }  // N granularity accepted by the GEMM entry points
+
+// ---- CTA-pair kernel (gemm_pair.cu): 256 x 320 tiles, tcgen05 cta_group::2 ----
+constexpr int GEMM_PAIR_BLOCK_N = 320;
+bool gemm_pair_enabled();                       // env WD_GEMM_PAIR (default on)
+bool gemm_pair_supported(const GemmArgs& a);    // shape / epilogue combination handled by the pair kernel
+cudaError_t gemm_pair_launch(const GemmLaunch& L, int num_sms, cudaStream_t stream);
+// which kernel gemm_tc_launch() picks decides two host-side layouts:
+bool gemm_uses_pair(const GemmArgs& a);         // -> B tensor-map box rows (gemm_b_box_rows) ...
+int gemm_b_box_rows(const GemmArgs& a);         // 16 (output conv), 80 (pair kernel), 160
+int gemm_geglu_block(int N);                    // ... and the value/gate interleave width of GEGLU weights (320 or 160)
 
 }  // namespace wd

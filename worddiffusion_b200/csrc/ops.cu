@@ -91,7 +91,10 @@ cudaError_t groupnorm_stats_launch(const GroupNormStatsArgs& a, int B, cudaStrea
   return cudaGetLastError();
 }
 
+constexpr int GN_APPLY_R = 16;  // pixel rows in flight per CTA pass (threads = Cs/8 * GN_APPLY_R)
+
 __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormArgs a) {
+  __shared__ float s_mean[128], s_rstd[128];
   const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
   const int Cs = a.Cs, cpg = a.cpg;
   const int nv = Cs >> 3;
@@ -99,35 +102,42 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
   const int P = a.HW / a.nchunk;
   const int ld = a.x_ld[slab];
-  const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
-  const int merge = cpg / a.pcpg;      // partial groups per GroupNorm group (1, or 2 for the concat GroupNorm)
-  const int PG = Cs / a.pcpg;          // partial groups of this source tensor
+  const int merge = cpg / a.pcpg;  // partial groups per GroupNorm group (1, or 2 for the concat GroupNorm)
+  const int PG = Cs / a.pcpg;      // partial groups of this source tensor
   const int slots = a.pslots[slab];
-  const float* part = a.partial[slab] + static_cast<size_t>(b) * PG * slots * 2;
+  const int ng = Cs / cpg;         // GroupNorm groups inside this slab (<= 128, checked by the launcher)
 
+  // one thread per group folds the partial sums in a fixed order (bit-reproducible), then everybody forms scale/shift
+  if (static_cast<int>(threadIdx.x) < ng) {
+    const float2* part = reinterpret_cast<const float2*>(a.partial[slab]) +
+                         (static_cast<size_t>(b) * PG + static_cast<size_t>(threadIdx.x) * merge) * slots;
+    float S = 0.f, Q = 0.f;
+    const int n = merge * slots;
+    for (int k = 0; k < n; ++k) {  // partial groups g*merge .. are contiguous: [pg][slot][2]
+      const float2 t = __ldg(part + k);
+      S += t.x;
+      Q += t.y;
+    }
+    const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
+    const float mean = S * inv_n;
+    const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+  }
+  __syncthreads();
   float sc[8], sh[8];
   {
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + slab * Cs) + col * 2);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + slab * Cs) + col * 2 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + slab * Cs) + col * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + slab * Cs) + col * 2 + 1);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = col * 8 + j;
-      const int g = c / cpg;
-      if (g != g_prev) {
-        float S = 0.f, Q = 0.f;
-        for (int k = 0; k < merge * slots; ++k) {  // partial groups g*merge .. are contiguous: [pg][slot][2]
-          const float2 t = __ldg(reinterpret_cast<const float2*>(part) + static_cast<size_t>(g) * merge * slots + k);
-          S += t.x;
-          Q += t.y;
-        }
-        mean = S * inv_n;
-        const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
-        rstd = rsqrtf(var + a.eps);
-        g_prev = g;
-      }
-      const float gm = __ldg(a.gamma + slab * Cs + c), be = __ldg(a.beta + slab * Cs + c);
-      sc[j] = rstd * gm;
-      sh[j] = be - mean * sc[j];
+      const int g = (col * 8 + j) / cpg;
+      sc[j] = s_rstd[g] * gm[j];
+      sh[j] = be[j] - s_mean[g] * sc[j];
     }
   }
   const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
@@ -161,13 +171,22 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   }
 }
 
+int groupnorm_apply_chunks(int HW) {
+  // 8 pixel rows per thread (two passes of 4 independent 16-byte loads) when the image is large enough
+  const int per = 8 * GN_APPLY_R;
+  return (HW >= 2 * per && HW % per == 0) ? HW / per : 1;
+}
+
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s) {
   const int nv = a.Cs / 8;
-  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || nv * GN_R > 1024 || a.nchunk < 1 || a.HW % a.nchunk)
+  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || a.nchunk < 1 || a.HW % a.nchunk)
     return cudaErrorInvalidValue;
+  int R = GN_APPLY_R;
+  while (R > 1 && nv * R > 1024) R >>= 1;
+  if (nv * R > 1024 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
   for (int i = 0; i < nslab; ++i)
     if (!a.partial[i] || a.pslots[i] < 1) return cudaErrorInvalidValue;
-  groupnorm_apply_kernel<<<dim3(B, nslab, a.nchunk), nv * GN_R, 0, s>>>(a);
+  groupnorm_apply_kernel<<<dim3(B, nslab, a.nchunk), nv * R, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -376,63 +395,51 @@ cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __
 }
 
 // =====================================================================================================
-// conv_in: 3x3 pad 1, Cin = 4, fp32 NCHW latent -> bf16 NHWC.  One CTA per image row.
+// conv_in (unet.py:1251): 3x3 pad 1, Cin = 4 on the tensor cores with fp32-class accuracy (the first layer's rounding
+// error propagates through the whole net: bf16 weights here alone cost 1.4e-3 of the 1e-2 budget).  This kernel builds
+// the im2col operand A[m, 128] bf16 from the fp32 NCHW latent, with x = x_hi + x_lo and w = w_hi + w_lo (bf16 pairs):
+//   columns  0..35  x_hi (j = c*9 + ky*3 + kx)   against weight columns w_hi
+//   columns 36..71  x_lo                          against w_hi
+//   columns 72..107 x_hi                          against w_lo
+// (the x_lo*w_lo term is ~2^-18 and dropped); columns 108..127 are zero.  One thread = 8 columns (16 B).
 // =====================================================================================================
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ wp,
-                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                      int H, int W, int Cout) {
-  extern __shared__ float ci_smem[];
-  float* sw = ci_smem;               // [36][Cout]
-  float* sp = ci_smem + 36 * Cout;    // [4][3][W+2]
-  const int y = blockIdx.x, b = blockIdx.y;
-  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) sw[i] = __ldg(wp + i);
-  const int PW = W + 2;
-  for (int i = threadIdx.x; i < 12 * PW; i += blockDim.x) {
-    const int c = i / (3 * PW), r = (i / PW) % 3, xx = i % PW;
-    const int yy = y + r - 1, xs = xx - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = __ldg(x + ((static_cast<size_t>(b) * 4 + c) * H + yy) * W + xs);
-    sp[i] = v;
+__global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             int B, int H, int W) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * W * 16;
+  if (idx >= total) return;
+  const int chunk = idx & 15;
+  const size_t m = idx >> 4;
+  const int px = m % W;
+  const int py = (m / W) % H;
+  const int b = m / (static_cast<size_t>(W) * H);
+  uint32_t o[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    float r[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = chunk * 8 + jj * 2 + e;
+      float val = 0.f;
+      if (k < 108) {
+        const int j = k % 36;
+        const int c = j / 9, ky = (j % 9) / 3, kx = j % 3;
+        const int yy = py + ky - 1, xx = px + kx - 1;
+        float xv = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv = __ldg(x + ((static_cast<size_t>(b) * 4 + c) * H + yy) * W + xx);
+        const float hi = __bfloat162float(__float2bfloat16(xv));
+        val = (k >= 36 && k < 72) ? xv - hi : hi;
+      }
+      r[e] = val;
+    }
+    o[jj] = pack_bf16x2(r[0], r[1]);
   }
-  __syncthreads();
-  const int nv = Cout >> 3;
-  for (int item = threadIdx.x; item < W * nv; item += blockDim.x) {
-    const int px = item / nv, cv = item % nv;
-    float acc[8];
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2);
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2 + 1);
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float xv = sp[(c * 3 + r) * PW + px + d];
-          const float4 w0 = reinterpret_cast<const float4*>(sw + (c * 9 + r * 3 + d) * Cout)[cv * 2];
-          const float4 w1 = reinterpret_cast<const float4*>(sw + (c * 9 + r * 3 + d) * Cout)[cv * 2 + 1];
-          acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-          acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
-        }
-    uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + y) * W + px) * Cout) + cv;
-    *op = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                     pack_bf16x2(acc[6], acc[7]));
-  }
+  reinterpret_cast<uint4*>(out)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-cudaError_t conv_in_launch(const float* x, const float* w_packed, const float* bias, __nv_bfloat16* out, int B, int H,
-                           int W, int Cout, cudaStream_t s) {
-  if (Cout % 8) return cudaErrorInvalidValue;
-  const size_t smem = (static_cast<size_t>(36) * Cout + 12 * (W + 2)) * sizeof(float);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
-  if (smem > 160 * 1024) return cudaErrorInvalidValue;
-  conv_in_kernel<<<dim3(H, B), 256, smem, s>>>(x, w_packed, bias, out, H, W, Cout);
+cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * H * W * 16;
+  conv_in_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, out, B, H, W);
   return cudaGetLastError();
 }
 
@@ -517,15 +524,23 @@ cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int 
   return cudaGetLastError();
 }
 
-__global__ void repack_conv_in_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin) {
+// conv_in weight [Cout, 4, 3, 3] fp32 -> bf16 [Cout, 128]: k = j and 36 + j hold w_hi[n][j], 72 + j holds w_lo, rest 0
+__global__ void repack_conv_in_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * Cin * 9) return;
-  const int k = idx % (Cin * 9), n = idx / (Cin * 9);
-  dst[k * Cout + n] = w[idx];
+  if (idx >= Cout * 128) return;
+  const int k = idx % 128, n = idx / 128;
+  float v = 0.f;
+  if (k < 108) {
+    const float wv = w[n * 36 + k % 36];
+    const float hi = __bfloat162float(__float2bfloat16(wv));
+    v = k < 72 ? hi : wv - hi;
+  }
+  dst[idx] = __float2bfloat16(v);
 }
-cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s) {
-  const int total = Cout * Cin * 9;
-  repack_conv_in_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout, Cin);
+cudaError_t repack_conv_in_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, cudaStream_t s) {
+  if (Cin != 4) return cudaErrorInvalidValue;
+  const int total = Cout * 128;
+  repack_conv_in_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, dst, Cout);
   return cudaGetLastError();
 }
 

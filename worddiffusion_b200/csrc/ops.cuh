@@ -36,6 +36,7 @@ struct GroupNormArgs {
   int nchunk;  // pixel chunks per sample of the apply grid
 };
 // normalise (+SiLU) from the partial statistics
+int groupnorm_apply_chunks(int HW);  // pixel chunks per sample of the apply grid (GroupNormArgs::nchunk)
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
 
 // ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------
@@ -76,9 +77,9 @@ cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s);
 cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __nv_bfloat16* out, int B, int dim,
                                   cudaStream_t s);
 
-// ---------------- conv_in: 3x3, Cin=4 fp32 NCHW -> bf16 NHWC (unet.py:1251) ----------------
-cudaError_t conv_in_launch(const float* x, const float* w_packed /*[36][Cout]*/, const float* bias, __nv_bfloat16* out,
-                           int B, int H, int W, int Cout, cudaStream_t s);
+// ---------------- conv_in (unet.py:1251): im2col of the fp32 NCHW latent into the bf16 GEMM operand [B*H*W, 128] ----------------
+// columns j = c*9+ky*3+kx: x_hi, 36 + j: x_lo (x - x_hi), 72 + j: x_hi again (pairs with w_lo), 108..127: zero
+cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
 
 // ---------------- nearest 2x upsample NHWC bf16 (unet.py:497) ----------------
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
@@ -93,8 +94,8 @@ cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int 
 // vector [N] -> dst[perm(n) + n_off] (accumulate: dst += src)
 cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
                               cudaStream_t s);
-// conv_in weight [Cout,4,3,3] -> [36][Cout]
-cudaError_t repack_conv_in_launch(const float* w, float* dst, int Cout, int Cin, cudaStream_t s);
+// conv_in weight [Cout,4,3,3] -> bf16 [Cout, 128]: w_hi | w_hi | w_lo | 0
+cudaError_t repack_conv_in_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, cudaStream_t s);
 
 // ---------------- fp32 context encoder (unet.py:815-882) ----------------
 // tokens [B, L] (int64 or int32) -> emb[B, L, D] = E[token] (+ pe[l] when add_pe)
