@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int M, int n_mm
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {  // elect.sync: no ELECT/BRA.U.ANY loop around each UTCHMMA
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t(N) >> 3) << 17) | ((uint32_t(M) >> 4) << 24);
     uint32_t phase = 0;
     for (int rep = 0; rep < 3; ++rep) {

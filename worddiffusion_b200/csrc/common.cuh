@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -78,6 +79,19 @@ WD_DEVINL float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// fp16 storage of the residual-stream tensors (11-bit mantissa; saturating, so an out-of-range value clamps to +-65504)
+WD_DEVINL uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+WD_DEVINL float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// 16-bit pair store/load with a run-time (warp-uniform) format switch
+WD_DEVINL uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+WD_DEVINL float2 unpack_16x2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier
@@ -324,6 +338,10 @@ WD_DEVINL uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// same, A,B = fp16 (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // Instruction descriptor, kind::f16: A,B = bf16 (K-major both), D = fp32, shape M x N (K = 16)
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t N) {
   return (1u << 4)         // c_format  = F32

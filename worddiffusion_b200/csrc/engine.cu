@@ -112,6 +112,7 @@ struct Slot {
   int N, K;  // S_LIN: [N,K]; S_CONV3: Cout, Cin
   int ldk, k_off, n_off, geglu_bn;
   bool loaded;
+  int as_f16;  // weight columns that multiply an fp16 (residual-stream) A source are stored as fp16
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -129,7 +130,7 @@ struct Op {
   GroupNormArgs gn;
   GroupNormStatsArgs gs;
   int gn_B = 0, gn_nslab = 0;
-  struct { const bf16* x; bf16* out; const float* g; const float* b; int M, C; float eps; } ln;
+  struct { const bf16* x; bf16* out; const float* g; const float* b; int M, C; float eps; int x_f16; } ln;
   AttnSmallArgs as;
   AttnFlashArgs af;
   struct { bf16* out; int B, dim; } temb;
@@ -153,6 +154,7 @@ struct Act {
   int C, H, W;
   float* stats;  // GroupNorm partial statistics of this tensor: [B][32][pslots][2] fp32 (groups of C/32 channels)
   int pslots;    // 0: not computed
+  bool f16;      // stored as fp16 (residual-stream tensors and tensors only read by norms), else bf16 (MMA operands)
 };
 
 struct wd_engine {
@@ -203,9 +205,9 @@ struct Builder {
   int bn;
 
   void slot(const std::string& name, SlotKind kind, void* dst, int64_t numel, int N = 0, int K = 0, int ldk = 0,
-            int k_off = 0, int n_off = 0, int geglu_bn = 0) {
+            int k_off = 0, int n_off = 0, int geglu_bn = 0, int as_f16 = 0) {
     if (dry) return;
-    Slot s{kind, dst, numel, N, K, ldk, k_off, n_off, geglu_bn, false};
+    Slot s{kind, dst, numel, N, K, ldk, k_off, n_off, geglu_bn, false, as_f16};
     e->slots[name] = s;
   }
   NormW norm(const std::string& pfx, int C) {
@@ -218,25 +220,25 @@ struct Builder {
     return n;
   }
   // nn.Linear / 1x1 conv [N, K] (+ optional bias)
-  GemmW linear(const std::string& pfx, int N, int K, bool bias, int geglu_bn = 0) {
+  GemmW linear(const std::string& pfx, int N, int K, bool bias, int geglu_bn = 0, int as_f16 = 0) {
     GemmW g;
     g.N = N;
     g.K = K;
     g.w = A.alloc<bf16>(static_cast<size_t>(N) * K);
-    slot(pfx + ".weight", S_LIN, g.w, static_cast<int64_t>(N) * K, N, K, K, 0, 0, geglu_bn);
+    slot(pfx + ".weight", S_LIN, g.w, static_cast<int64_t>(N) * K, N, K, K, 0, 0, geglu_bn, as_f16);
     if (bias) {
       g.bias = A.alloc<float>(N);
       slot(pfx + ".bias", S_VEC, g.bias, N, N, 0, 0, 0, 0, geglu_bn);
     }
     return g;
   }
-  GemmW conv3(const std::string& pfx, int Cout, int Cin, int extraK = 0) {
+  GemmW conv3(const std::string& pfx, int Cout, int Cin, int extraK = 0, int as_f16 = 0) {
     GemmW g;
     g.N = Cout;
     g.K = 9 * Cin + extraK;
     g.w = A.alloc<bf16>(static_cast<size_t>(g.N) * g.K);
     g.bias = A.alloc<float>(Cout);
-    slot(pfx + ".weight", S_CONV3, g.w, static_cast<int64_t>(Cout) * Cin * 9, Cout, Cin, g.K, 0);
+    slot(pfx + ".weight", S_CONV3, g.w, static_cast<int64_t>(Cout) * Cin * 9, Cout, Cin, g.K, 0, 0, 0, as_f16);
     return g;
   }
 
@@ -256,8 +258,9 @@ struct Builder {
     slot(pfx + "out_layers.3.bias", S_VEC, r.b_main, Cout);
     if (r.skip_conv) {
       r.b_skip = A.alloc<float>(Cout);
+      // the 1x1 skip conv reads the (fp16) residual-stream tensors directly: its K range of the fused weight is fp16
       slot(pfx + "skip_connection.weight", S_LIN, r.conv2.w, static_cast<int64_t>(Cout) * Cin, Cout, Cin, r.conv2.K,
-           9 * Cout, 0, 0);
+           9 * Cout, 0, 0, 1);
       slot(pfx + "skip_connection.bias", S_VEC, r.b_skip, Cout);
     }
     e->res.push_back(r);
@@ -311,7 +314,7 @@ struct Builder {
       t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
       s.blocks.push_back(t);
     }
-    s.proj_out = linear(pfx + "proj_out", C, inner, true);
+    s.proj_out = linear(pfx + "proj_out", C, inner, true, 0, 1);  // A operand = x3, a residual-stream (fp16) tensor
     e->st.push_back(s);
     return static_cast<int>(e->st.size()) - 1;
   }
@@ -319,7 +322,7 @@ struct Builder {
   int add_samp(const std::string& pfx, int C) {
     SampL s;
     s.C = C;
-    s.conv = conv3(pfx, C, C);
+    s.conv = conv3(pfx, C, C, 0, 1);  // Down/Upsample convs read residual-stream (fp16) tensors
     slot(pfx + ".bias", S_VEC, s.conv.bias, C);
     e->samp.push_back(s);
     return static_cast<int>(e->samp.size()) - 1;
@@ -447,7 +450,8 @@ struct Builder {
     e->conv_out.K = 9 * ch;
     e->conv_out.w = A.alloc<bf16>(static_cast<size_t>(GEMM_BLOCK_N_OUT) * 9 * ch);
     e->conv_out.bias = A.alloc<float>(GEMM_BLOCK_N_OUT);
-    slot("out.2.weight", S_CONV3, e->conv_out.w, static_cast<int64_t>(c.out_channels) * ch * 9, c.out_channels, ch, 9 * ch, 0);
+    slot("out.2.weight", S_CONV3, e->conv_out.w, static_cast<int64_t>(c.out_channels) * ch * 9, c.out_channels, ch, 9 * ch, 0, 0, 0,
+         2 /* hi rows 0..3, lo rows 4..7 */);
     slot("out.2.bias", S_VEC, e->conv_out.bias, c.out_channels);
 
     // fused emb_layers GEMM: [sum Cout, time_dim]
@@ -584,10 +588,11 @@ extern "C" int wd_engine_load_param(wd_engine* e, const char* name, const float*
       CUDA_TRY(cudaMemcpyAsync(sl.dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
       break;
     case S_CONV3:
-      CUDA_TRY(repack_conv3x3_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, s));
+      CUDA_TRY(repack_conv3x3_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, sl.as_f16, s));
       break;
     case S_LIN:
-      CUDA_TRY(repack_linear_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, sl.n_off, sl.geglu_bn, s));
+      CUDA_TRY(repack_linear_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, sl.ldk, sl.k_off, sl.n_off, sl.geglu_bn,
+                                    sl.as_f16, s));
       break;
     case S_CONV_IN:
       CUDA_TRY(repack_conv_in_launch(src, static_cast<bf16*>(sl.dst), sl.N, sl.K, s));
@@ -642,6 +647,7 @@ struct ASrc {
   int taps;
   int stride;
   int H, W;  // input spatial size (conv mode)
+  bool f16 = false;  // fp16 source (its weight columns are packed as fp16 too)
 };
 struct Epi {
   const float* rowbias = nullptr;
@@ -652,6 +658,8 @@ struct Epi {
   void* out = nullptr;
   int out_ld = 0;
   int out_f32 = 0;
+  int out_f16 = 0;
+  int res_f16 = 0;
   int act = 0;
   int geglu = 0;
   Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
@@ -666,8 +674,8 @@ struct PlanBuilder {
   int B;
   std::string err;
 
-  Act new_act(int H, int W, int C) {
-    Act a{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W, nullptr, 0};
+  Act new_act(int H, int W, int C, bool f16 = false) {
+    Act a{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W, nullptr, 0, f16};
     a.stats = A.alloc<float>(static_cast<size_t>(B) * 32 * 8 * 2);
     return a;
   }
@@ -681,7 +689,7 @@ struct PlanBuilder {
     memset(&op, 0, sizeof(op));
     op.kind = OP_GNSTATS;
     a.pslots = groupnorm_stats_slots(a.H * a.W);
-    op.gs = GroupNormStatsArgs{a.p, a.C, a.stats, a.H * a.W, a.C, a.C / 32, a.pslots};
+    op.gs = GroupNormStatsArgs{a.p, a.C, a.stats, a.H * a.W, a.C, a.C / 32, a.pslots, a.f16 ? 1 : 0};
     op.gn_B = B;
     op.bytes = 2.0 * B * a.H * a.W * a.C;
     ops.push_back(op);
@@ -711,6 +719,8 @@ struct PlanBuilder {
     a.out = ep.out;
     a.out_ld = ep.out_ld;
     a.out_f32 = ep.out_f32;
+    a.out_f16 = ep.out_f16;
+    a.res_f16 = ep.res_f16;
     a.act = ep.act;
     a.geglu = ep.geglu;
     a.epi = ep.epi;
@@ -727,6 +737,7 @@ struct PlanBuilder {
       a.taps[i] = s.taps;
       a.chunks[i] = s.C / GEMM_BLOCK_K;
       a.stride[i] = s.stride;
+      a.a_f16[i] = s.f16 ? 1 : 0;
       ktot += s.taps * s.C;
       if (dry) continue;
       bool ok;
@@ -803,6 +814,7 @@ struct PlanBuilder {
       const Act& s = srcs[i / per_src];
       op.gn.x[i] = s.p + (i % per_src) * Cs;
       op.gn.x_ld[i] = s.C;
+      op.gn.x_f16[i] = s.f16 ? 1 : 0;
     }
     op.gn.out = out.p;
     op.gn.out_ld = totalC;
@@ -827,11 +839,11 @@ struct PlanBuilder {
     return true;
   }
 
-  void ln_op(std::vector<Op>& ops, const bf16* x, bf16* out, const NormW& nw, int M) {
+  void ln_op(std::vector<Op>& ops, const Act& x, bf16* out, const NormW& nw, int M) {
     Op op;
     memset(&op, 0, sizeof(op));
     op.kind = OP_LN;
-    op.ln = {x, out, nw.g, nw.b, M, nw.C, 1e-5f};
+    op.ln = {x.p, out, nw.g, nw.b, M, nw.C, 1e-5f, x.f16 ? 1 : 0};
     op.bytes = 4.0 * M * nw.C;
     ops.push_back(op);
   }
@@ -856,7 +868,7 @@ struct PlanBuilder {
     const int H = in[0].H, W = in[0].W, HW = H * W;
     Act a1;
     if (!gn_op(ops, in, r.gn1, 1e-5f, 1, a1)) return false;
-    Act h2 = new_act(H, W, r.Cout);
+    Act h2 = new_act(H, W, r.Cout, true);  // only read by GroupNorm: fp16
     {
       Epi ep;
       ep.rowbias = emb_out + r.emb_off;
@@ -864,25 +876,31 @@ struct PlanBuilder {
       ep.rows_per_sample = HW;
       ep.out = h2.p;
       ep.out_ld = r.Cout;
+      ep.out_f16 = 1;
       ep.stats_for = &h2;
       if (!gemm_op(ops, B * HW, true, H, W, {ASrc{a1.p, a1.C, a1.C, 9, 1, H, W}}, r.conv1, ep)) return false;
     }
     Act a2;
     if (!gn_op(ops, {h2}, r.gn2, 1e-5f, 1, a2)) return false;
-    out = new_act(H, W, r.Cout);
+    out = new_act(H, W, r.Cout, true);  // residual stream: fp16
     {
       Epi ep;
       ep.rows_per_sample = HW;
       ep.out = out.p;
       ep.out_ld = r.Cout;
+      ep.out_f16 = 1;
       ep.stats_for = &out;
       std::vector<ASrc> srcs{ASrc{a2.p, a2.C, a2.C, 9, 1, H, W}};
       if (r.skip_conv) {
-        for (auto& s : in) srcs.push_back(ASrc{s.p, s.C, s.C, 1, 1, H, W});
+        for (auto& s : in) {
+          if (!s.f16) { err = "resblock: the fused skip conv expects fp16 residual-stream sources"; return false; }
+          srcs.push_back(ASrc{s.p, s.C, s.C, 1, 1, H, W, true});
+        }
       } else {
         if (in.size() != 1 || in[0].C != r.Cout) { err = "resblock: identity skip needs a single source"; return false; }
         ep.residual = in[0].p;
         ep.res_ld = in[0].C;
+        ep.res_f16 = in[0].f16 ? 1 : 0;
       }
       if (!gemm_op(ops, B * HW, true, H, W, srcs, r.conv2, ep)) return false;
     }
@@ -895,20 +913,21 @@ struct PlanBuilder {
     const int Ltot = plan->Ltot;
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
-    Act x = new_act(H, W, C);
+    Act x = new_act(H, W, C, true);  // token residual stream: fp16
     {
       Epi ep;
       ep.out = x.p;
       ep.out_ld = C;
+      ep.out_f16 = 1;
       if (!gemm_op(ops, M, false, 0, 0, {ASrc{g.p, g.C, g.C, 1, 1, H, W}}, s.proj_in, ep)) return false;
     }
     Act n = new_act(H, W, C);
     Act o = new_act(H, W, C);
     for (auto& t : s.blocks) {
       // --- attn1 ---
-      Act x1 = new_act(H, W, C);
+      Act x1 = new_act(H, W, C, true);
       if (e->cfg.variant == WD_VARIANT_PHOSC) {
-        ln_op(ops, x.p, n.p, t.ln1, M);
+        ln_op(ops, x, n.p, t.ln1, M);
         bf16* qkv = A.alloc<bf16>(static_cast<size_t>(M) * 3 * C);
         Epi ep;
         ep.out = qkv;
@@ -916,7 +935,7 @@ struct PlanBuilder {
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a1_q, ep)) return false;
         attn_op(ops, qkv, 3 * C, qkv + C, qkv + 2 * C, 3 * C, o.p, C, HW, HW, s.heads, s.dh);
       } else {
-        ln_op(ops, x.p, n.p, t.ln2, M);  // unet.py:337 applies norm2 before attn1
+        ln_op(ops, x, n.p, t.ln2, M);  // unet.py:337 applies norm2 before attn1
         bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
         ep.out = q;
@@ -928,13 +947,15 @@ struct PlanBuilder {
         Epi ep;
         ep.out = x1.p;
         ep.out_ld = C;
+        ep.out_f16 = 1;
         ep.residual = x.p;
         ep.res_ld = C;
+        ep.res_f16 = x.f16 ? 1 : 0;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a1_out, ep)) return false;
       }
       // --- attn2 (cross) ---
-      Act x2 = new_act(H, W, C);
-      ln_op(ops, x1.p, n.p, t.ln2, M);
+      Act x2 = new_act(H, W, C, true);
+      ln_op(ops, x1, n.p, t.ln2, M);
       {
         bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
@@ -945,13 +966,15 @@ struct PlanBuilder {
         Epi ep2;
         ep2.out = x2.p;
         ep2.out_ld = C;
+        ep2.out_f16 = 1;
         ep2.residual = x1.p;
         ep2.res_ld = C;
+        ep2.res_f16 = 1;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a2_out, ep2)) return false;
       }
       // --- GEGLU feed-forward ---
-      Act x3 = new_act(H, W, C);
-      ln_op(ops, x2.p, n.p, t.ln3, M);
+      Act x3 = new_act(H, W, C, true);
+      ln_op(ops, x2, n.p, t.ln3, M);
       {
         bf16* gg = A.alloc<bf16>(static_cast<size_t>(M) * 4 * C);
         Epi ep;
@@ -962,21 +985,26 @@ struct PlanBuilder {
         Epi ep2;
         ep2.out = x3.p;
         ep2.out_ld = C;
+        ep2.out_f16 = 1;
         ep2.residual = x2.p;
         ep2.res_ld = C;
+        ep2.res_f16 = 1;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{gg, 4 * C, 4 * C, 1, 1, H, W}}, t.ff_out, ep2)) return false;
       }
       x = x3;
     }
-    out = new_act(H, W, s.C);
+    out = new_act(H, W, s.C, true);
     Epi ep;
     ep.out = out.p;
     ep.out_ld = s.C;
+    ep.out_f16 = 1;
     ep.residual = x_in.p;
     ep.res_ld = x_in.C;
+    ep.res_f16 = x_in.f16 ? 1 : 0;
     ep.rows_per_sample = HW;
     ep.stats_for = &out;
-    return gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W}}, s.proj_out, ep);
+    if (!x.f16) { err = "spatial transformer: proj_out expects the fp16 token stream"; return false; }
+    return gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, s.proj_out, ep);
   }
 
   bool build() {
@@ -1076,7 +1104,7 @@ struct PlanBuilder {
         switch (l.kind) {
           case L_CONVIN: {
             // conv_in = im2col (hi/lo bf16 split of the fp32 latent) + tcgen05 GEMM with K = 128
-            out = new_act(c.latent_h, c.latent_w, mc);
+            out = new_act(c.latent_h, c.latent_w, mc, true);
             const int HW = c.latent_h * c.latent_w;
             bf16* col = A.alloc<bf16>(static_cast<size_t>(B) * HW * 128);
             Op op;
@@ -1088,6 +1116,7 @@ struct PlanBuilder {
             Epi ep;
             ep.out = out.p;
             ep.out_ld = mc;
+            ep.out_f16 = 1;
             ep.rows_per_sample = HW;
             ep.stats_for = &out;
             if (!gemm_op(sops, B * HW, false, 0, 0, {ASrc{col, 128, 128, 1, 1, 1, 1}}, e->conv_in, ep)) return false;
@@ -1107,33 +1136,37 @@ struct PlanBuilder {
           case L_DOWN: {
             const Act& x = in[0];
             if (x.H % 2 || x.W % 2) { err = "downsample needs even spatial size"; return false; }
-            out = new_act(x.H / 2, x.W / 2, x.C);
+            if (!x.f16) { err = "downsample expects an fp16 residual-stream input"; return false; }
+            out = new_act(x.H / 2, x.W / 2, x.C, true);
             Epi ep;
             ep.out = out.p;
             ep.out_ld = x.C;
+            ep.out_f16 = 1;
             ep.rows_per_sample = out.H * out.W;
             ep.stats_for = &out;
-            if (!gemm_op(sops, B * out.H * out.W, true, out.H, out.W, {ASrc{x.p, x.C, x.C, 9, 2, x.H, x.W}},
+            if (!gemm_op(sops, B * out.H * out.W, true, out.H, out.W, {ASrc{x.p, x.C, x.C, 9, 2, x.H, x.W, true}},
                          e->samp[l.idx].conv, ep))
               return false;
             break;
           }
           case L_UP: {
             const Act& x = in[0];
-            Act up = new_act(x.H * 2, x.W * 2, x.C);
+            if (!x.f16) { err = "upsample expects an fp16 residual-stream input"; return false; }
+            Act up = new_act(x.H * 2, x.W * 2, x.C, true);  // 16-bit copy, format-agnostic
             Op op;
             memset(&op, 0, sizeof(op));
             op.kind = OP_UPSAMPLE;
             op.up = {x.p, up.p, B, x.H, x.W, x.C};
             op.bytes = 2.0 * B * x.H * x.W * x.C * 5;
             sops.push_back(op);
-            out = new_act(up.H, up.W, x.C);
+            out = new_act(up.H, up.W, x.C, true);
             Epi ep;
             ep.out = out.p;
             ep.out_ld = x.C;
+            ep.out_f16 = 1;
             ep.rows_per_sample = up.H * up.W;
             ep.stats_for = &out;
-            if (!gemm_op(sops, B * up.H * up.W, true, up.H, up.W, {ASrc{up.p, up.C, up.C, 9, 1, up.H, up.W}},
+            if (!gemm_op(sops, B * up.H * up.W, true, up.H, up.W, {ASrc{up.p, up.C, up.C, 9, 1, up.H, up.W, true}},
                          e->samp[l.idx].conv, ep))
               return false;
             break;
@@ -1279,7 +1312,7 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
         err = groupnorm_launch(op.gn, op.gn_B, op.gn_nslab, s);
         break;
       case OP_LN:
-        err = layernorm_launch(op.ln.x, op.ln.out, op.ln.g, op.ln.b, op.ln.M, op.ln.C, op.ln.eps, s);
+        err = layernorm_launch(op.ln.x, op.ln.out, op.ln.g, op.ln.b, op.ln.M, op.ln.C, op.ln.eps, op.ln.x_f16, s);
         break;
       case OP_ATTN_SMALL:
         err = attn_small_launch(op.as, e->cur->B, s);
@@ -1445,7 +1478,7 @@ extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, con
   const int slots = groupnorm_stats_slots(HW);
   float* partial = nullptr;
   CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * groups * slots * 2 * sizeof(float), s));
-  GroupNormStatsArgs st{static_cast<const bf16*>(x), C, partial, HW, C, cpg, slots};
+  GroupNormStatsArgs st{static_cast<const bf16*>(x), C, partial, HW, C, cpg, slots, 0};
   CUDA_TRY(groupnorm_stats_launch(st, B, s));
   GroupNormArgs a;
   memset(&a, 0, sizeof(a));
@@ -1471,7 +1504,7 @@ extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, con
 
 extern "C" int wd_op_layernorm(const void* x, void* out, const float* gamma, const float* beta, int M, int C, float eps,
                                void* stream) {
-  CUDA_TRY(layernorm_launch(static_cast<const bf16*>(x), static_cast<bf16*>(out), gamma, beta, M, C, eps,
+  CUDA_TRY(layernorm_launch(static_cast<const bf16*>(x), static_cast<bf16*>(out), gamma, beta, M, C, eps, 0,
                             static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
@@ -1562,11 +1595,11 @@ extern "C" int wd_op_conv3x3(const void* x, const void* w_packed, const float* b
 }
 
 extern "C" int wd_op_pack_conv3x3(const float* w, void* dst, int Cout, int Cin, void* stream) {
-  CUDA_TRY(repack_conv3x3_launch(w, static_cast<bf16*>(dst), Cout, Cin, 9 * Cin, 0, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(repack_conv3x3_launch(w, static_cast<bf16*>(dst), Cout, Cin, 9 * Cin, 0, 0, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 extern "C" int wd_op_pack_linear(const float* w, void* dst, int N, int K, int geglu_perm, void* stream) {
-  CUDA_TRY(repack_linear_launch(w, static_cast<bf16*>(dst), N, K, K, 0, 0, geglu_perm ? gemm_geglu_block(N) : 0,
+  CUDA_TRY(repack_linear_launch(w, static_cast<bf16*>(dst), N, K, K, 0, 0, geglu_perm ? gemm_geglu_block(N) : 0, 0,
                                 static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }

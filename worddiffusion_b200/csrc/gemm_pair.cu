@@ -14,7 +14,9 @@
 // The 128 x 320 fp32 accumulator uses 320 of the 512 TMEM columns, so it is single-buffered: the epilogue hands TMEM back
 // as soon as its second (last) tcgen05.ld round has completed and finishes its arithmetic / stores under the next tile's
 // MMAs.  Epilogue structure is that of gemm_tc.cu (two warps per TMEM lane quarter, dense [128][40] bf16 staging
-// sub-tiles, TMA stores, TMA-prefetched residual), with two rounds of 80 columns per warp.
+// sub-tiles, TMA stores, TMA-prefetched residual), in two rounds of 80 columns per warp that reuse one 40 KB staging
+// buffer, so that five 36 KB operand stages fit (the ring must cover ~2 us of TMA latency at 36 KB per 640 MMA clocks).
+// bias / per-sample row-bias are staged once per tile in a per-warp shared-memory vector (no global loads in the loop).
 #include "gemm_tc.cuh"
 
 #include <cstdio>
@@ -26,13 +28,14 @@ namespace wd {
 namespace {
 
 constexpr int PAIR_BN = 320;        // tile columns (both CTAs)
-constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_STAGES = 5;
 constexpr int PAIR_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // 16 KB: this CTA's 128 rows
 constexpr int PAIR_BH_BYTES = 80 * GEMM_BLOCK_K * 2;               // 10 KB: 80 weight rows (half of a 160-column MMA)
 constexpr int PAIR_STAGE_BYTES = PAIR_A_BYTES + 2 * PAIR_BH_BYTES;  // 36 KB
 constexpr int PAIR_SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;       // dense [128][40] bf16
-constexpr int PAIR_STG_BYTES = 8 * PAIR_SUB_BYTES;                  // 80 KB: the CTA's whole 128 x 320 bf16 output tile
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_STG_BYTES + 1024 + 256;
+constexpr int PAIR_STG_BYTES = 4 * PAIR_SUB_BYTES;                  // 40 KB: one epilogue round = 128 rows x 2 halves x 80 columns
+constexpr int PAIR_VEC_BYTES = GEMM_EPI_WARPS * 160 * 4;            // per-warp bias / row-bias vector of its 160 accumulator columns
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_STG_BYTES + PAIR_VEC_BYTES + 256;
 constexpr int PAIR_TMEM_COLS = 512;
 static_assert(PAIR_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -59,10 +62,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                  const GemmArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + PAIR_STAGES * PAIR_STAGE_BYTES;  // [8 sub-tiles][128][40] bf16 (sub-tile s = columns 40 s ..)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + PAIR_STG_BYTES);  // leader's are used by both CTAs
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
+  uint8_t* stg = smem + PAIR_STAGES * PAIR_STAGE_BYTES;  // [2 halves][2 sub-tiles][128][40] bf16: one round of the tile
+  float* vecs = reinterpret_cast<float*>(stg + PAIR_STG_BYTES);  // [8 epilogue warps][160]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + PAIR_STG_BYTES + PAIR_VEC_BYTES);  // leader's are used by both CTAs
   uint64_t* empty_bar = full_bar + PAIR_STAGES;                            // local (multicast commit)
   uint64_t* tmem_full_bar = empty_bar + PAIR_STAGES;                       // local (multicast commit)
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;                            // leader's: 16 epilogue-warp arrivals
@@ -110,7 +115,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
+    // (elect.sync, not `lane == 0`: ptxas then knows exactly one lane is active and issues UTMALDG / UTCHMMA / UTCBAR
+    //  straight from uniform registers instead of wrapping each one in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -133,16 +140,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's full barrier
-              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+              if (is_leader)
+                mbar_arrive_expect_tx(&full_bar[stage], 2 * (((args.dbg & 8) ? 0 : PAIR_A_BYTES) + ((args.dbg & 4) ? 0 : 2 * PAIR_BH_BYTES)));
               uint8_t* sA = smem + stage * PAIR_STAGE_BYTES;
               uint8_t* sB = sA + PAIR_A_BYTES;
-              if (args.conv)
-                tma_load_4d_pair(sA, mapA, fb, ch * GEMM_BLOCK_K, dx, oh0 * st + dy, img);
-              else
-                tma_load_2d_pair(sA, mapA, fb, ch * GEMM_BLOCK_K, m0);
+              if (!(args.dbg & 8)) {
+                if (args.conv)
+                  tma_load_4d_pair(sA, mapA, fb, ch * GEMM_BLOCK_K, dx, oh0 * st + dy, img);
+                else
+                  tma_load_2d_pair(sA, mapA, fb, ch * GEMM_BLOCK_K, m0);
+              }
               // weight rows of MMA j (columns n0 + 160 j ..): this CTA supplies rows [80 rank, +80) of them
-              tma_load_2d_pair(sB, &mapB, fb, kb * GEMM_BLOCK_K, n0 + static_cast<int>(rank) * 80);
-              tma_load_2d_pair(sB + PAIR_BH_BYTES, &mapB, fb, kb * GEMM_BLOCK_K, n0 + 160 + static_cast<int>(rank) * 80);
+              if (!(args.dbg & 4)) {
+                tma_load_2d_pair(sB, &mapB, fb, kb * GEMM_BLOCK_K, n0 + static_cast<int>(rank) * 80);
+                tma_load_2d_pair(sB + PAIR_BH_BYTES, &mapB, fb, kb * GEMM_BLOCK_K, n0 + 160 + static_cast<int>(rank) * 80);
+              }
               ++kb;
               if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -152,8 +164,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA, single thread) ===========================
-    if (is_leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(2 * GEMM_BLOCK_M, 160);
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc_bf16 = make_idesc_bf16_f32(2 * GEMM_BLOCK_M, 160);
+      constexpr uint32_t idesc_f16 = make_idesc_f16_f32(2 * GEMM_BLOCK_M, 160);
+      int kend[GEMM_MAX_SRC];  // K-block index at which each source ends
+      {
+        int acc_k = 0;
+#pragma unroll
+        for (int s = 0; s < GEMM_MAX_SRC; ++s) {
+          if (s < args.num_src) acc_k += args.taps[s] * args.chunks[s];
+          kend[s] = acc_k;
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -161,16 +183,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait_cluster(tmem_empty_bar, (it & 1) ^ 1);  // both CTAs' epilogues have drained the accumulator
         tc_fence_after();
         for (int kb = 0; kb < total_k; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);  // CTA-scope acquire: a cluster-scope one costs a CCTL.IVALL (L1 flush) per K block
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * PAIR_STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
           const uint64_t b_desc0 = make_smem_desc_sw128(a_addr + PAIR_A_BYTES);
           const uint64_t b_desc1 = make_smem_desc_sw128(a_addr + PAIR_A_BYTES + PAIR_BH_BYTES);
+          const int src = kb < kend[0] ? 0 : (kb < kend[1] ? 1 : 2);
+          const uint32_t idesc = args.a_f16[src] ? idesc_f16 : idesc_bf16;
+          if (!(args.dbg & 16)) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc0 + 2 * k, idesc, (kb | k) != 0);
-            umma_f16_ss_pair(tmem_base + 160, a_desc + 2 * k, b_desc1 + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc0 + 2 * k, idesc, (kb | k) != 0);
+              umma_f16_ss_pair(tmem_base + 160, a_desc + 2 * k, b_desc1 + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs when these MMAs retire
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
@@ -183,23 +209,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int q = warp & 3;            // TMEM lane quarter
     const int half = (warp - 2) >> 2;  // column half: tile columns [160 half, +160)
     const int row = q * 32 + lane;
-    const bool leader_thr = (q == 0) && (lane == 0);  // issues this half's TMA stores / residual loads
+    const bool leader_warp = (q == 0);  // its elected lane issues this half's TMA stores / residual loads (elect.sync is
+                                        // deterministic, so the bulk async-groups always belong to the same thread)
     const int bar_id = 1 + half;
     const bool use_stg = !args.out_f32;
     const bool has_res = use_stg && args.residual != nullptr;
-    uint8_t* const stg_half = stg + half * 4 * PAIR_SUB_BYTES;  // 4 sub-tiles = 160 columns
+    uint8_t* const stg_half = stg + half * 2 * PAIR_SUB_BYTES;  // 2 sub-tiles = the 80 columns of one round
+    float* const wv = vecs + (warp - 2) * 160;
     const uint32_t te_addr = mapa_shared(smem_u32(tmem_empty_bar), 0);
-    const int out_half_cols = args.geglu ? 80 : 160;  // output columns written by this half per tile
+    const bool rb_warp_uniform = args.rowbias && (args.rows_per_sample % 32 == 0);
+    const bool out_f16 = args.out_f16 != 0, res_f16 = args.res_f16 != 0;
 
-    auto issue_res_load = [&](int tile_) {
+    // residual sub-tiles of (tile_, round rnd_) of this half -> staging
+    auto issue_res_load = [&](int tile_, int rnd_) {
       const int m0_ = (tile_ / n_tiles) * (2 * GEMM_BLOCK_M) + static_cast<int>(rank) * GEMM_BLOCK_M;
-      const int c0_ = (tile_ % n_tiles) * PAIR_BN + half * 160;
-      mbar_arrive_expect_tx(&res_full_bar[half], 4 * PAIR_SUB_BYTES);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        tma_load_2d(stg_half + s * PAIR_SUB_BYTES, &mapRes, &res_full_bar[half], c0_ + s * GEMM_SUB_N, m0_);
+      const int c0_ = (tile_ % n_tiles) * PAIR_BN + half * 160 + rnd_ * 80;
+      mbar_arrive_expect_tx(&res_full_bar[half], 2 * PAIR_SUB_BYTES);
+      tma_load_2d(stg_half, &mapRes, &res_full_bar[half], c0_, m0_);
+      tma_load_2d(stg_half + PAIR_SUB_BYTES, &mapRes, &res_full_bar[half], c0_ + GEMM_SUB_N, m0_);
     };
-    if (has_res && leader_thr && pair < total_tiles) issue_res_load(pair);
+    if (has_res && leader_warp && pair < total_tiles) {
+      if (elect_one()) issue_res_load(pair, 0);
+    }
 
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
@@ -208,25 +239,39 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int n0 = n_tile * PAIR_BN;
       const int m = m0 + row;
       const bool valid = m < args.M;
-      const int sample = valid ? (m / args.rows_per_sample) : 0;
-      const float* rb = nullptr;
-      if (args.rowbias) {
-        const long long r = args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample);
-        rb = args.rowbias + r * args.rb_ld;
+
+      // ---- per-warp vector of the additive per-column terms (bias + the warp's sample row of the row-bias) ----
+      const float* rb = nullptr;  // per-thread row-bias only when the rows of a warp can belong to different samples
+      {
+        const int mw = min(m0 + q * 32, args.M - 1);
+        const float* rbw = nullptr;
+        if (rb_warp_uniform) {
+          const int sw = mw / args.rows_per_sample;
+          rbw = args.rowbias + (args.rowbias_idx ? args.rowbias_idx[sw] : static_cast<long long>(sw)) * args.rb_ld;
+        } else if (args.rowbias) {
+          const int sample = valid ? (m / args.rows_per_sample) : 0;
+          rb = args.rowbias + (args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample)) * args.rb_ld;
+        }
+        __syncwarp();  // all lanes are done reading the previous tile's vector
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int c = lane + 32 * i;
+          // STD: accumulator column n0 + 160 half + c.  GEGLU: c < 80 -> value column 80 half + c, else its gate (+160)
+          const int col = args.geglu ? (n0 + half * 80 + (c < 80 ? c : c - 80 + 160)) : (n0 + half * 160 + c);
+          float x = args.bias ? __ldg(args.bias + col) : 0.f;
+          if (rbw) x += __ldg(rbw + col);
+          wv[c] = x;
+        }
+        __syncwarp();
       }
 
       mbar_wait(tmem_full_bar, it & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-      // the staging buffer of this half must be free: its previous TMA store has read it (or the residual has landed)
-      if (use_stg) {
-        if (has_res) {
-          mbar_wait(&res_full_bar[half], it & 1);
-        } else {
-          if (leader_thr) bulk_wait_group_read<0>();
-          named_barrier_sync(bar_id, 128);
-        }
+      if (args.dbg & 2) {  // experiment: no epilogue at all
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(te_addr);
+        continue;
       }
       uint8_t* const srow = stg_half + row * (GEMM_SUB_N * 2);
 
@@ -253,6 +298,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (lane == 0) mbar_arrive_cluster(te_addr);
         }
 
+        // ---- the staging buffer of this half must be free: its previous TMA store has read it / the residual has landed ----
+        if (use_stg) {
+          if (has_res) {
+            mbar_wait(&res_full_bar[half], (2 * it + rnd) & 1);
+          } else {
+            if (leader_warp) {
+              if (elect_one()) bulk_wait_group_read<0>();
+            }
+            named_barrier_sync(bar_id, 128);
+          }
+        }
+
         if (!args.geglu) {
           float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
           if (args.gn_partial) {
@@ -260,30 +317,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             for (int i = 0; i < 16; ++i) gs[i] = 0.f;
           }
           const int nb = n0 + half * 160 + rnd * 80;
+          const float* wvr = wv + rnd * 80;
 #pragma unroll
           for (int c = 0; c < 10; ++c) {  // 8 columns = one 16-byte staging chunk
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c * 8 + j]);
-            if (args.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8 + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
+            const float4 b0 = *reinterpret_cast<const float4*>(wvr + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(wvr + c * 8 + 4);
+            f[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
+            f[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
+            f[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
+            f[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
             if (rb) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8 + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8 + 4));
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
             }
-            uint4* sp = reinterpret_cast<uint4*>(srow + (rnd * 2 + c / 5) * PAIR_SUB_BYTES + (c % 5) * 16);
+            uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * PAIR_SUB_BYTES + (c % 5) * 16);
             if (has_res) {
               const uint4 r4 = *sp;
               const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_bf16x2(ru[j]);
+                const float2 t = unpack_16x2(ru[j], res_f16);
                 f[2 * j] += t.x;
                 f[2 * j + 1] += t.y;
               }
@@ -302,7 +358,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               }
             }
             if (use_stg) {
-              *sp = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *sp = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
             } else if (valid) {  // fp32 output (emb_layers GEMM): direct stores
               float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
               op[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -324,47 +380,50 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
         } else {
           // GEGLU: out = (value + bv) * gelu(gate + bg); 40 output columns per round = one staging sub-tile
-          const int nbv = n0 + half * 80 + rnd * 40;  // bias index of the value columns inside the permuted layout
-          const int nbg = nbv + 160;                  // ... of the gate columns
+          const float* wvv = wv + rnd * 40;        // biases of the value columns of this round
+          const float* wvg = wv + 80 + rnd * 40;   // ... of the gate columns
 #pragma unroll
           for (int c = 0; c < 5; ++c) {
             float f[8];
-            float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0, bg0 = bv0, bg1 = bv0;
-            if (args.bias) {
-              bv0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8));
-              bv1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8 + 4));
-              bg0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8));
-              bg1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8 + 4));
-            }
+            const float4 bv0 = *reinterpret_cast<const float4*>(wvv + c * 8), bv1 = *reinterpret_cast<const float4*>(wvv + c * 8 + 4);
+            const float4 bg0 = *reinterpret_cast<const float4*>(wvg + c * 8), bg1 = *reinterpret_cast<const float4*>(wvg + c * 8 + 4);
             const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
             const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
-            *reinterpret_cast<uint4*>(srow + rnd * PAIR_SUB_BYTES + c * 16) =
-                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(srow + c * 16) =
+                make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
           }
         }
-      }
 
-      // ---- publish the staged half tile with TMA; prefetch the residual of this CTA's next tile ----
-      if (use_stg) {
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the async proxy (TMA)
-        named_barrier_sync(bar_id, 128);
-        if (leader_thr) {
-          const int oc0 = args.geglu ? (n_tile * 160 + half * 80) : (n0 + half * 160);
-          const int nsub = out_half_cols / GEMM_SUB_N;
-          for (int s = 0; s < nsub; ++s) tma_store_2d(&mapOut, stg_half + s * PAIR_SUB_BYTES, oc0 + s * GEMM_SUB_N, m0);
-          bulk_commit_group();
-          const int next = tile + npairs;
-          if (has_res && next < total_tiles) {
-            bulk_wait_group_read<0>();  // the store above has read the staging buffer
-            issue_res_load(next);
+        // ---- publish the staged round with TMA; prefetch the residual of the next round ----
+        if (use_stg) {
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the async proxy (TMA)
+          named_barrier_sync(bar_id, 128);
+          if (leader_warp && elect_one()) {
+            if (!args.geglu) {
+              const int oc0 = n0 + half * 160 + rnd * 80;
+              tma_store_2d(&mapOut, stg_half, oc0, m0);
+              tma_store_2d(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0);
+            } else {
+              tma_store_2d(&mapOut, stg_half, n_tile * 160 + half * 80 + rnd * 40, m0);
+            }
+            bulk_commit_group();
+            if (has_res) {
+              const int nt = rnd == 0 ? tile : tile + npairs;
+              if (nt < total_tiles) {
+                bulk_wait_group_read<0>();  // the store above has read the staging buffer
+                issue_res_load(nt, rnd ^ 1);
+              }
+            }
           }
         }
       }
     }
-    if (use_stg && leader_thr) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
+    if (use_stg && leader_warp) {
+      if (elect_one()) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
+    }
   }
 
   tc_fence_before();
@@ -376,7 +435,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 bool gemm_pair_supported(const GemmArgs& a) {
   if (a.epi != EPI_STD) return false;
   if (a.N % PAIR_BN) return false;
-  if (a.geglu && (a.residual || a.out_f32 || a.gn_partial)) return false;
+  if (a.geglu) return false;  // the kernel implements it (value | gate per 320-column tile) but the weights are packed for 160-column tiles
   if (a.out_f32 && a.residual) return false;
   return true;
 }

@@ -19,7 +19,8 @@ struct Cfg {
   static constexpr int SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;  // one dense [128][40] bf16 sub-tile
   static constexpr int HALF_STG_BYTES = 2 * SUB_BYTES;             // 80 columns of one column half
   static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 80 * 4;  // per-warp bias / row-bias vector of its 80 accumulator columns
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + VEC_BYTES + 256 /*barriers*/;
 };
 
 // lane L (< 16) ends with the sum over the warp's 32 lanes of v[L] (v is destroyed): 16 + 15 shuffles
@@ -48,10 +49,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const GemmArgs args) {
   using C = Cfg<BN, STAGES, NSTG>;
   constexpr int NB = NSTG > 0 ? NSTG : 1;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
   uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES;  // [half][NSTG][2 sub-tiles][128][40] bf16
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES);
+  float* vecs = reinterpret_cast<float*>(stg + C::STG_BYTES);  // [8 epilogue warps][80]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES + C::VEC_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -96,7 +99,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // (elect.sync, not `lane == 0`: ptxas then knows exactly one lane is active and issues UTMALDG / UTCHMMA / UTCBAR
+    //  straight from uniform registers instead of wrapping each one in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -136,9 +141,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread) ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BLOCK_M, BN);
+    // =========================== MMA issuer (single elected thread) ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc_bf16 = make_idesc_bf16_f32(GEMM_BLOCK_M, BN);
+      constexpr uint32_t idesc_f16 = make_idesc_f16_f32(GEMM_BLOCK_M, BN);
+      int kend[GEMM_MAX_SRC];  // K-block index at which each source ends
+      {
+        int acc_k = 0;
+#pragma unroll
+        for (int s = 0; s < GEMM_MAX_SRC; ++s) {
+          if (s < args.num_src) acc_k += args.taps[s] * args.chunks[s];
+          kend[s] = acc_k;
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -149,10 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
         for (int kb = 0; kb < total_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+          if (!(args.dbg & 512)) tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + C::A_BYTES);
+          const int src = kb < kend[0] ? 0 : (kb < kend[1] ? 1 : 2);
+          const uint32_t idesc = args.a_f16[src] ? idesc_f16 : idesc_bf16;
           if (!(args.dbg & 16)) {
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
@@ -193,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const int b = m / HW, pix = m % HW;
 #pragma unroll
           for (int o = 0; o < 4; ++o) {
-            const float eps = __uint_as_float(v[o]) + __ldg(args.bias + o);
+            // columns 0..3: bf16 "hi" part of the weights, 4..7: their "lo" part (engine packs out.2.weight that way)
+            const float eps = (__uint_as_float(v[o]) + __uint_as_float(v[4 + o])) + __ldg(args.bias + o);
             const size_t idx = (static_cast<size_t>(b) * 4 + o) * HW + pix;
             if (args.eps_out) args.eps_out[idx] = eps;
             if (args.mode == STEP_DDPM) {
@@ -217,12 +235,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
       constexpr int HC = BN / 2;             // accumulator columns per warp (80)
       constexpr int NSUB = HC / GEMM_SUB_N;  // staging sub-tiles per half: 2 (GEGLU fills only the first)
-      const bool leader = (q == 0) && (lane == 0);  // issues this half's TMA stores / residual loads
+      const bool leader_warp = (q == 0);  // its elected lane issues this half's TMA stores / residual loads
       const int bar_id = 1 + half;
       const bool use_stg = (NSTG > 0) && !args.out_f32;
       const bool has_res = use_stg && args.residual != nullptr;
       uint8_t* const stg_half = stg + half * NB * C::HALF_STG_BYTES;
       uint64_t* const res_bar = res_full_bar + half * 2;
+      float* const wv = vecs + (warp - 2) * 80;
+      const bool out_f16 = args.out_f16 != 0, res_f16 = args.res_f16 != 0;
 
       auto issue_res_load = [&](int tile_, int sb_) {
         const int m0_ = (tile_ / n_tiles) * GEMM_BLOCK_M;
@@ -233,7 +253,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           tma_load_2d(stg_half + sb_ * C::HALF_STG_BYTES + s * C::SUB_BYTES, &mapRes, &res_bar[sb_],
                       c0_ + s * GEMM_SUB_N, m0_);
       };
-      if (has_res && leader && static_cast<int>(blockIdx.x) < total_tiles) issue_res_load(blockIdx.x, 0);
+      if (has_res && leader_warp && static_cast<int>(blockIdx.x) < total_tiles) {
+        if (elect_one()) issue_res_load(blockIdx.x, 0);
+      }
 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -243,6 +265,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n0 = n_tile * BN;
         const int m = m0 + row;
         const bool valid = m < args.M;
+        // ---- per-warp vector of the additive per-column terms (bias + the warp's sample row of the row-bias) ----
+        const float* rb = nullptr;  // per-thread row-bias only when the rows of a warp can belong to different samples
+        {
+          const int mw = min(m0 + q * 32, args.M - 1);
+          const float* rbw = nullptr;
+          if (args.rowbias && args.rows_per_sample % 32 == 0) {
+            const int sw = mw / args.rows_per_sample;
+            rbw = args.rowbias + (args.rowbias_idx ? args.rowbias_idx[sw] : static_cast<long long>(sw)) * args.rb_ld;
+          } else if (args.rowbias) {
+            const int sample = valid ? (m / args.rows_per_sample) : 0;
+            rb = args.rowbias + (args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample)) * args.rb_ld;
+          }
+          __syncwarp();  // all lanes are done reading the previous tile's vector
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c = lane + 32 * i;
+            if (c < HC) {
+              // STD: accumulator column n0 + 80 half + c.  GEGLU: c < 40 -> value column 40 half + c, else its gate (+80)
+              const int col = args.geglu ? (n0 + half * 40 + (c < 40 ? c : c - 40 + HC)) : (n0 + half * HC + c);
+              float x = args.bias ? __ldg(args.bias + col) : 0.f;
+              if (rbw) x += __ldg(rbw + col);
+              wv[c] = x;
+            }
+          }
+          __syncwarp();
+        }
+
         mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
@@ -270,20 +319,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
 
         if (args.dbg & 2) continue;
-        const int sample = valid ? (m / args.rows_per_sample) : 0;
-        const float* rb = nullptr;
-        if (args.rowbias) {
-          const long long r = args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample);
-          rb = args.rowbias + r * args.rb_ld;
-        }
 
         // ---- staging buffer `sb` of this half must be free (its previous TMA store has read it) ----
         if (use_stg) {
           if (has_res) {
             mbar_wait(&res_bar[sb], (it / NB) & 1);  // the residual tile has landed in the staging buffer
           } else if (!(args.dbg & 64)) {
-            if (leader) {
-              if (NSTG > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            if (leader_warp) {
+              if (elect_one()) {
+                if (NSTG > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              }
             }
             named_barrier_sync(bar_id, 128);
           }
@@ -301,13 +346,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < HC / 8; ++c) {  // 8 columns = one 16-byte staging chunk
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c * 8 + j]);
-            if (args.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + nb + c * 8 + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(wv + c * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(wv + c * 8 + 4);
+              f[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
+              f[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
+              f[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
+              f[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
             }
             if (rb) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
@@ -321,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_bf16x2(ru[j]);
+                const float2 t = unpack_16x2(ru[j], res_f16);
                 f[2 * j] += t.x;
                 f[2 * j + 1] += t.y;
               }
@@ -330,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_bf16x2(ru[j]);
+                const float2 t = unpack_16x2(ru[j], res_f16);
                 f[2 * j] += t.x;
                 f[2 * j + 1] += t.y;
               }
@@ -349,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               }
             }
             if (use_stg) {
-              *sp = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *sp = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
             } else if (valid) {
               if (args.out_f32) {
                 float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
@@ -357,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 op[1] = make_float4(f[4], f[5], f[6], f[7]);
               } else {
                 uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
-                *op = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                *op = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
               }
             }
           }
@@ -376,24 +421,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         } else {
           // GEGLU: out = (value + bv) * gelu(gate + bg); 40 output columns per warp = one staging sub-tile
-          const int nbv = n0 + half * 40;       // bias index of the value columns inside the permuted layout
-          const int nbg = n0 + HC + half * 40;  // ... of the gate columns
 #pragma unroll
           for (int c = 0; c < 5; ++c) {
             float f[8];
-            float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0, bg0 = bv0, bg1 = bv0;
-            if (args.bias) {
-              bv0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8));
-              bv1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbv + c * 8 + 4));
-              bg0 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8));
-              bg1 = __ldg(reinterpret_cast<const float4*>(args.bias + nbg + c * 8 + 4));
-            }
+            const float4 bv0 = *reinterpret_cast<const float4*>(wv + c * 8), bv1 = *reinterpret_cast<const float4*>(wv + c * 8 + 4);
+            const float4 bg0 = *reinterpret_cast<const float4*>(wv + 40 + c * 8), bg1 = *reinterpret_cast<const float4*>(wv + 40 + c * 8 + 4);
             const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
             const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
-            const uint4 o4 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            const uint4 o4 = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
             if (use_stg) {
               *reinterpret_cast<uint4*>(srow + c * 16) = o4;
             } else if (valid) {
@@ -406,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (use_stg) {
           if (!(args.dbg & 32)) fence_proxy_async();  // generic-proxy smem writes -> visible to the async proxy (TMA)
           named_barrier_sync(bar_id, 128);
-          if (leader && !(args.dbg & 1)) {
+          if (leader_warp && !(args.dbg & 1) && elect_one()) {
             const uint8_t* src = stg_half + sb * C::HALF_STG_BYTES;
             if (!args.geglu) {
 #pragma unroll
@@ -425,7 +463,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
       }
-      if (use_stg && leader) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
+      if (use_stg && leader_warp) {
+        if (elect_one()) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
+      }
     }
   }
 
@@ -547,12 +587,25 @@ bool gemm_pair_enabled() {
   }
   return v != 0;
 }
-bool gemm_uses_pair(const GemmArgs& a) { return gemm_pair_enabled() && gemm_pair_supported(a); }
+static int gemm_pair_min_kblocks() {  // env WD_GEMM_PAIR_MINK: plain (non-GEGLU) GEMMs with fewer 64-wide K blocks use the single-CTA kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_PAIR_MINK");
+    v = e ? atoi(e) : 40;  // measured (tools/op_bench.py): the pair kernel wins for the 3x3 convs (>= 45 K blocks) only
+  }
+  return v;
+}
+bool gemm_uses_pair(const GemmArgs& a) {
+  if (!gemm_pair_enabled() || !gemm_pair_supported(a)) return false;
+  int total_k = 0;
+  for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
+  return total_k >= gemm_pair_min_kblocks();
+}
 int gemm_b_box_rows(const GemmArgs& a) {
   if (a.epi == EPI_SAMPLER) return GEMM_BLOCK_N_OUT;
   return gemm_uses_pair(a) ? 80 : GEMM_BLOCK_N;
 }
-int gemm_geglu_block(int N) { return (gemm_pair_enabled() && N % GEMM_PAIR_BLOCK_N == 0) ? GEMM_PAIR_BLOCK_N : GEMM_BLOCK_N; }
+int gemm_geglu_block(int) { return GEMM_BLOCK_N; }  // GEGLU projections (K = 320) run on the single-CTA kernel: value | gate per 160-column tile
 
 cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   GemmLaunch L = L0;

@@ -49,6 +49,7 @@ struct GemmArgs {
   int taps[GEMM_MAX_SRC];    // 1 or 9
   int chunks[GEMM_MAX_SRC];  // channels / 64
   int stride[GEMM_MAX_SRC];  // conv stride of that source (1 or 2)
+  int a_f16[GEMM_MAX_SRC];   // 1: this source (and the weight columns it multiplies) is fp16, not bf16 (residual-stream tensors)
   int conv;                  // 1: 4-D (c,w,h,n) coordinates, 0: 2-D (c, row)
   int Wout;                  // output width  (conv)
   int HWout;                 // output pixels per image (conv)
@@ -64,6 +65,8 @@ struct GemmArgs {
   void* out;  // bf16 (or fp32 when out_f32) [M, out_ld]
   int out_ld;
   int out_f32;
+  int out_f16;  // 16-bit output format: 0 bf16 (MMA operands of later GEMMs), 1 fp16 (residual stream / tensors consumed by norms)
+  int res_f16;  // format of the residual tensor
   int act;
   int geglu;  // 1: tile columns [0,BN/2) are values, [BN/2,BN) gates; writes BN/2 columns per tile
   // GroupNorm partial statistics of the written tensor: gn_partial[sample][N/gn_cpg groups][rows_per_sample/32][2]

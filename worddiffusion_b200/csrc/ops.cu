@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(1024) groupnorm_stats_kernel(const GroupNormSt
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(u[j]);
+        const float2 f = unpack_16x2(u[j], a.x_f16 != 0);
         s[2 * j] += f.x;
         s[2 * j + 1] += f.y;
         q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   const int PG = Cs / a.pcpg;      // partial groups of this source tensor
   const int slots = a.pslots[slab];
   const int ng = Cs / cpg;         // GroupNorm groups inside this slab (<= 128, checked by the launcher)
+  const bool xf16 = a.x_f16[slab] != 0;
 
   // one thread per group folds the partial sums in a fixed order (bit-reproducible), then everybody forms scale/shift
   if (static_cast<int>(threadIdx.x) < ng) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(u[j]);
+        const float2 f = unpack_16x2(u[j], xf16);
         float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
         float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
         if (a.silu) {
@@ -197,7 +198,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                         __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, int M, int C, float eps) {
+                                                        const float* __restrict__ beta, int M, int C, float eps,
+                                                        int x_f16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(u[j]);
+        const float2 t = unpack_16x2(u[j], x_f16 != 0);
         f[i][2 * j] = t.x;
         f[i][2 * j + 1] = t.y;
         sum += t.x + t.y;
@@ -258,14 +260,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 }
 
 cudaError_t layernorm_launch(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta, int M,
-                             int C, float eps, cudaStream_t s) {
+                             int C, float eps, int x_f16, cudaStream_t s) {
   if (C % 8 || C > 8 * 32 * 4) return cudaErrorInvalidValue;
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
   if (C <= 8 * 32 * 2)
-    layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps);
+    layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps, x_f16);
   else
-    layernorm_kernel<4><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps);
+    layernorm_kernel<4><<<blocks, 256, 0, s>>>(x, out, gamma, beta, M, C, eps, x_f16);
   return cudaGetLastError();
 }
 
@@ -478,36 +480,50 @@ WD_DEVINL int geglu_perm(int n, int N, int bn) {
   return (j / half) * bn + (gate ? half : 0) + (j % half);
 }
 
+WD_DEVINL __nv_bfloat16 to_16(float v, int as_f16) {  // bf16, or the fp16 bit pattern in a 16-bit slot
+  if (!as_f16) return __float2bfloat16(v);
+  const __half h = __float2half_rn(v);
+  return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+
 __global__ void repack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
-                                      int ldk, int k_off) {
+                                      int ldk, int k_off, int as_f16) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(Cout) * Cin * 9;
   if (idx >= total) return;
   const int tap = idx % 9;
   const int c = (idx / 9) % Cin;
   const int n = idx / (9 * static_cast<size_t>(Cin));
-  dst[static_cast<size_t>(n) * ldk + k_off + tap * Cin + c] = __float2bfloat16(w[idx]);
+  if (as_f16 == 2) {
+    // output conv (N = 4 of a 16-column tile): bf16 hi part in row n, bf16 lo part (w - hi) in row n + 4; the epilogue
+    // adds the two accumulator columns, so the weights act with ~16 mantissa bits
+    const float hi = __bfloat162float(__float2bfloat16(w[idx]));
+    dst[static_cast<size_t>(n) * ldk + k_off + tap * Cin + c] = __float2bfloat16(hi);
+    dst[static_cast<size_t>(n + 4) * ldk + k_off + tap * Cin + c] = __float2bfloat16(w[idx] - hi);
+    return;
+  }
+  dst[static_cast<size_t>(n) * ldk + k_off + tap * Cin + c] = to_16(w[idx], as_f16);
 }
-cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off,
+cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off, int as_f16,
                                   cudaStream_t s) {
   const size_t total = static_cast<size_t>(Cout) * Cin * 9;
-  repack_conv3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ldk, k_off);
+  repack_conv3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, ldk, k_off, as_f16);
   return cudaGetLastError();
 }
 
 __global__ void repack_linear_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int N, int K,
-                                     int ldk, int k_off, int n_off, int geglu_bn) {
+                                     int ldk, int k_off, int n_off, int geglu_bn, int as_f16) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(N) * K) return;
   const int k = idx % K, n = idx / K;
   const int nn = geglu_bn ? geglu_perm(n, N, geglu_bn) : n;
-  dst[static_cast<size_t>(nn + n_off) * ldk + k_off + k] = __float2bfloat16(w[idx]);
+  dst[static_cast<size_t>(nn + n_off) * ldk + k_off + k] = to_16(w[idx], as_f16);
 }
 cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int K, int ldk, int k_off, int n_off,
-                                 int geglu_bn, cudaStream_t s) {
+                                 int geglu_bn, int as_f16, cudaStream_t s) {
   const size_t total = static_cast<size_t>(N) * K;
   repack_linear_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, N, K, ldk, k_off, n_off,
-                                                                                    geglu_bn);
+                                                                                    geglu_bn, as_f16);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@ struct GroupNormStatsArgs {
   int HW, C;
   int pcpg;    // channels per partial group
   int pslots;  // pixel chunks per sample (groupnorm_stats_slots(HW))
+  int x_f16;   // 1: x is fp16 (residual-stream tensor), 0: bf16
 };
 int groupnorm_stats_slots(int HW);
 cudaError_t groupnorm_stats_launch(const GroupNormStatsArgs& a, int B, cudaStream_t s);
@@ -34,6 +35,7 @@ struct GroupNormArgs {
   float eps;
   int silu;
   int nchunk;  // pixel chunks per sample of the apply grid
+  int x_f16[2];  // per source: 1 = fp16 input (residual-stream tensors), 0 = bf16.  The output is always bf16.
 };
 // normalise (+SiLU) from the partial statistics
 int groupnorm_apply_chunks(int HW);  // pixel chunks per sample of the apply grid (GroupNormArgs::nchunk)
@@ -41,7 +43,7 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
 
 // ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------
 cudaError_t layernorm_launch(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta, int M,
-                             int C, float eps, cudaStream_t s);
+                             int C, float eps, int x_f16, cudaStream_t s);
 
 // ---------------- attention with a short key/value sequence (char context, L <= 16), unet.py:185-279 ----------------
 struct AttnSmallArgs {
@@ -85,12 +87,13 @@ cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
 
 // ---------------- weight repacking (fp32 state_dict tensors -> packed bf16 / fp32 layouts) ----------------
-// conv3x3 weight [Cout, Cin, 3, 3] -> dst[n, k_off + tap*Cin + c]   (row stride ldk)
-cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off,
+// conv3x3 weight [Cout, Cin, 3, 3] -> dst[n, k_off + tap*Cin + c]   (row stride ldk); as_f16: store fp16 bit patterns
+// (weight columns that multiply an fp16 A source, see GemmArgs::a_f16)
+cudaError_t repack_conv3x3_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int ldk, int k_off, int as_f16,
                                   cudaStream_t s);
 // linear / 1x1 weight [N, K] -> dst[perm(n) + n_off, k_off + k]; geglu_bn > 0 applies the value/gate tile permutation
 cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int K, int ldk, int k_off, int n_off,
-                                 int geglu_bn, cudaStream_t s);
+                                 int geglu_bn, int as_f16, cudaStream_t s);
 // vector [N] -> dst[perm(n) + n_off] (accumulate: dst += src)
 cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
                               cudaStream_t s);
