@@ -18,6 +18,7 @@
 // buffer, so that five 36 KB operand stages fit (the ring must cover ~2 us of TMA latency at 36 KB per 640 MMA clocks).
 // bias / per-sample row-bias are staged once per tile in a per-warp shared-memory vector (no global loads in the loop).
 #include "gemm_tc.cuh"
+#include "epilogue.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -38,22 +39,6 @@ constexpr int PAIR_VEC_BYTES = GEMM_EPI_WARPS * 160 * 4;            // per-warp 
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_STG_BYTES + PAIR_VEC_BYTES + 256;
 constexpr int PAIR_TMEM_COLS = 512;
 static_assert(PAIR_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-
-WD_DEVINL float warp_transpose_reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
 
 }  // namespace
 
@@ -213,7 +198,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                         // deterministic, so the bulk async-groups always belong to the same thread)
     const int bar_id = 1 + half;
     const bool use_stg = !args.out_f32;
-    const bool has_res = use_stg && args.residual != nullptr;
+    // rare flavours (time-embedding GEMMs, operator tests): SiLU, fp32 output, per-thread row-bias rows, or a residual stored
+    // in another 16-bit format than the output -> generic run-time-flag epilogue, residual read from global memory
+    const bool slow_path = args.act != ACT_NONE || args.out_f32 || (args.rowbias && args.rows_per_sample % 32 != 0) ||
+                           (args.residual && (args.res_f16 != 0) != (args.out_f16 != 0));
+    const bool has_res = use_stg && args.residual != nullptr && !slow_path;  // residual TMA-prefetched into the staging tile
     uint8_t* const stg_half = stg + half * 2 * PAIR_SUB_BYTES;  // 2 sub-tiles = the 80 columns of one round
     float* const wv = vecs + (warp - 2) * 160;
     const uint32_t te_addr = mapa_shared(smem_u32(tmem_empty_bar), 0);
@@ -310,90 +299,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
         }
 
-        if (!args.geglu) {
-          float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
-          if (args.gn_partial) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) gs[i] = 0.f;
-          }
+        if (args.geglu) {
+          epi_geglu40(v, wv + rnd * 40, wv + 80 + rnd * 40, srow);
+        } else {
           const int nb = n0 + half * 160 + rnd * 80;
           const float* wvr = wv + rnd * 80;
+          if (slow_path) {
+            epi_round80_generic(v, wvr, rb ? rb + nb : nullptr, args.act == ACT_SILU,
+                                (args.residual && !has_res) ? args.residual + static_cast<size_t>(m) * args.res_ld + nb : nullptr,
+                                res_f16, use_stg, srow, PAIR_SUB_BYTES, args.out_f32 != 0, out_f16,
+                                args.out_f32 ? static_cast<void*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb)
+                                             : static_cast<void*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb),
+                                valid);
+          } else {
+            float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
 #pragma unroll
-          for (int c = 0; c < 10; ++c) {  // 8 columns = one 16-byte staging chunk
-            float f[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(wvr + c * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(wvr + c * 8 + 4);
-            f[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
-            f[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
-            f[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
-            f[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
-            if (rb) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8 + 4));
-              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-            }
-            uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * PAIR_SUB_BYTES + (c % 5) * 16);
-            if (has_res) {
-              const uint4 r4 = *sp;
-              const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_16x2(ru[j], res_f16);
-                f[2 * j] += t.x;
-                f[2 * j + 1] += t.y;
-              }
-            }
-            if (args.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-            }
+            for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, v, wvr, srow, PAIR_SUB_BYTES, valid, gs);
             if (args.gn_partial) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int g = (c * 8 + j) / 10;  // compile-time after unrolling (80 columns -> 8 groups of 10)
-                const float x = valid ? f[j] : 0.f;
-                gs[2 * g] += x;
-                gs[2 * g + 1] = fmaf(x, x, gs[2 * g + 1]);
+              // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
+              const float tot = warp_transpose_reduce16(gs, lane);
+              const int mw = m0 + q * 32;
+              if (mw < args.M && lane < 16) {
+                const int smp = mw / args.rows_per_sample;
+                const int slot = (mw % args.rows_per_sample) >> 5;
+                const int nslot = args.rows_per_sample >> 5;
+                const int G = args.N / 10;
+                const int g = (nb / 10) + (lane >> 1);
+                args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
               }
             }
-            if (use_stg) {
-              *sp = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
-            } else if (valid) {  // fp32 output (emb_layers GEMM): direct stores
-              float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
-              op[0] = make_float4(f[0], f[1], f[2], f[3]);
-              op[1] = make_float4(f[4], f[5], f[6], f[7]);
-            }
-          }
-          if (args.gn_partial) {
-            // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
-            const float tot = warp_transpose_reduce16(gs, lane);
-            const int mw = m0 + q * 32;
-            if (mw < args.M && lane < 16) {
-              const int smp = mw / args.rows_per_sample;
-              const int slot = (mw % args.rows_per_sample) >> 5;
-              const int nslot = args.rows_per_sample >> 5;
-              const int G = args.N / 10;
-              const int g = (nb / 10) + (lane >> 1);
-              args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
-            }
-          }
-        } else {
-          // GEGLU: out = (value + bv) * gelu(gate + bg); 40 output columns per round = one staging sub-tile
-          const float* wvv = wv + rnd * 40;        // biases of the value columns of this round
-          const float* wvg = wv + 80 + rnd * 40;   // ... of the gate columns
-#pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            float f[8];
-            const float4 bv0 = *reinterpret_cast<const float4*>(wvv + c * 8), bv1 = *reinterpret_cast<const float4*>(wvv + c * 8 + 4);
-            const float4 bg0 = *reinterpret_cast<const float4*>(wvg + c * 8), bg1 = *reinterpret_cast<const float4*>(wvg + c * 8 + 4);
-            const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
-            const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
-            *reinterpret_cast<uint4*>(srow + c * 16) =
-                make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
           }
         }
 

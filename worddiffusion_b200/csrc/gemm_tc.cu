@@ -1,5 +1,6 @@
 // Persistent warp-specialised tcgen05 implicit-GEMM kernel, see gemm_tc.cuh for the contract.
 #include "gemm_tc.cuh"
+#include "epilogue.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -7,59 +8,49 @@
 
 namespace wd {
 
-template <int BN, int STAGES_, int NSTG_>
+// WSK > 0: "weight-stationary" mode for short K (K <= 64 WSK): the CTA keeps its whole [BN x K] weight tile resident in
+// shared memory (loaded once), works on ONE n-tile for all its m-tiles, and the ring only streams A (16 KB per K block).
+// For K = 320 this halves the L2->SM operand traffic (100 KB of weights were re-streamed for every 80 KB of activations),
+// which is what bounds the 1x1 / Linear GEMMs of the transformer blocks (the per-SM TMA ingest rate, see gemm_pair.cu).
+template <int BN, int STAGES_, int NSTG_, int WSK_ = 0>
 struct Cfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int NSTG = NSTG_;  // staging buffers per column half (0: the epilogue writes global memory directly)
+  static constexpr int WSK = WSK_;
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BN * GEMM_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = WSK ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int BRES_BYTES = WSK * B_BYTES;  // resident weight tile
   static constexpr int ACC_STRIDE = (BN == GEMM_BLOCK_N) ? 256 : 32;  // TMEM column offset of accumulator buffer 1
   static constexpr int TMEM_COLS = (BN == GEMM_BLOCK_N) ? 512 : 64;
   static constexpr int SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;  // one dense [128][40] bf16 sub-tile
   static constexpr int HALF_STG_BYTES = 2 * SUB_BYTES;             // 80 columns of one column half
   static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
   static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 80 * 4;  // per-warp bias / row-bias vector of its 80 accumulator columns
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + VEC_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + 256 /*barriers*/;
 };
 
-// lane L (< 16) ends with the sum over the warp's 32 lanes of v[L] (v is destroyed): 16 + 15 shuffles
-WD_DEVINL float warp_transpose_reduce16(float (&v)[16], int lane) {
-  // fold the upper 16 lanes onto the lower 16: afterwards lanes L and L^16 hold the same 16 sums
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
-template <int BN, int EPI, int STAGES, int NSTG>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                const GemmArgs args) {
-  using C = Cfg<BN, STAGES, NSTG>;
+  using C = Cfg<BN, STAGES, NSTG, WSK>;
   constexpr int NB = NSTG > 0 ? NSTG : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
-  uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES;  // [half][NSTG][2 sub-tiles][128][40] bf16
+  uint8_t* bres = smem + C::STAGES * C::STAGE_BYTES;  // [WSK][BN x 64] resident weight tile (weight-stationary mode)
+  uint8_t* stg = bres + C::BRES_BYTES;                // [half][NSTG][2 sub-tiles][128][40] bf16
   float* vecs = reinterpret_cast<float*>(stg + C::STG_BYTES);  // [8 epilogue warps][80]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES + C::VEC_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint64_t* res_full_bar = tmem_empty_bar + 2;      // [2 halves][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 4);
+  uint64_t* bres_bar = res_full_bar + 4;            // resident weight tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +80,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(&tmem_empty_bar[i], EPI_ACTIVE_WARPS);  // one arrival per epilogue warp
     }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full_bar[i], 1);
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -104,6 +96,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (WSK > 0 && static_cast<int>(blockIdx.x) < total_tiles) {
+        // weight-stationary: gridDim.x is a multiple of n_tiles, so this CTA's n-tile never changes
+        const int n0 = (blockIdx.x % n_tiles) * BN;
+        mbar_arrive_expect_tx(bres_bar, total_k * C::B_BYTES);
+        for (int kb = 0; kb < total_k; ++kb) tma_load_2d(bres + kb * C::B_BYTES, &mapB, bres_bar, kb * GEMM_BLOCK_K, n0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
         const int n0 = (tile % n_tiles) * BN;
@@ -123,7 +121,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int dx = (taps == 9) ? tap % 3 - 1 : 0;
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], ((args.dbg & 8) ? 0 : C::A_BYTES) + ((args.dbg & 4) ? 0 : C::B_BYTES));
+              mbar_arrive_expect_tx(&full_bar[stage],
+                                    ((args.dbg & 8) ? 0 : C::A_BYTES) + ((WSK > 0 || (args.dbg & 4)) ? 0 : C::B_BYTES));
               uint8_t* sA = smem + stage * C::STAGE_BYTES;
               uint8_t* sB = sA + C::A_BYTES;
               if (!(args.dbg & 8)) {
@@ -132,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 else
                   tma_load_2d(sA, mapA, &full_bar[stage], ch * GEMM_BLOCK_K, m0);
               }
-              if (!(args.dbg & 4)) tma_load_2d(sB, &mapB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+              if (WSK == 0 && !(args.dbg & 4)) tma_load_2d(sB, &mapB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
               ++kb;
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -157,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (WSK > 0 && static_cast<int>(blockIdx.x) < total_tiles) mbar_wait(bres_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
@@ -167,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (!(args.dbg & 512)) tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + C::A_BYTES);
+          const uint64_t b_desc = make_smem_desc_sw128(WSK > 0 ? smem_u32(bres + kb * C::B_BYTES) : a_addr + C::A_BYTES);
           const int src = kb < kend[0] ? 0 : (kb < kend[1] ? 1 : 2);
           const uint32_t idesc = args.a_f16[src] ? idesc_f16 : idesc_bf16;
           if (!(args.dbg & 16)) {
@@ -238,7 +238,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const bool leader_warp = (q == 0);  // its elected lane issues this half's TMA stores / residual loads
       const int bar_id = 1 + half;
       const bool use_stg = (NSTG > 0) && !args.out_f32;
-      const bool has_res = use_stg && args.residual != nullptr;
+      // rare flavours (time-embedding GEMMs, operator tests): SiLU, fp32 output, per-thread row-bias rows, or a residual stored
+      // in another 16-bit format than the output -> generic run-time-flag epilogue, residual read from global memory
+      const bool slow_path = !use_stg || args.act != ACT_NONE || (args.rowbias && args.rows_per_sample % 32 != 0) ||
+                             (args.residual && (args.res_f16 != 0) != (args.out_f16 != 0));
+      const bool has_res = use_stg && args.residual != nullptr && !slow_path;  // residual TMA-prefetched into the staging tile
       uint8_t* const stg_half = stg + half * NB * C::HALF_STG_BYTES;
       uint64_t* const res_bar = res_full_bar + half * 2;
       float* const wv = vecs + (warp - 2) * 80;
@@ -336,106 +340,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint8_t* const srow = stg_half + sb * C::HALF_STG_BYTES + row * (GEMM_SUB_N * 2);
 
         if (args.dbg & 128) {
-        } else if (!args.geglu) {
-          float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
-          if (args.gn_partial) {
+        } else if (args.geglu) {
+          // values of this warp: tile columns [40 half, +40), gates 80 further; 40 output columns = one staging sub-tile
+          if (use_stg) epi_geglu40(v, wv, wv + 40, srow);  // (every GEGLU launch stages: gemm_tc_launch rejects geglu + fp32 output)
+        } else {
+          const int nb = n0 + half * HC;
+          if (slow_path) {
+            epi_round80_generic(v, wv, rb ? rb + nb : nullptr, args.act == ACT_SILU,
+                                (args.residual && !has_res) ? args.residual + static_cast<size_t>(m) * args.res_ld + nb : nullptr,
+                                res_f16, use_stg, srow, C::SUB_BYTES, args.out_f32 != 0, out_f16,
+                                args.out_f32 ? static_cast<void*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb)
+                                             : static_cast<void*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb),
+                                valid);
+          } else {
+            float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
 #pragma unroll
             for (int i = 0; i < 16; ++i) gs[i] = 0.f;
-          }
-          const int nb = n0 + half * HC;
-#pragma unroll
-          for (int c = 0; c < HC / 8; ++c) {  // 8 columns = one 16-byte staging chunk
-            float f[8];
-            {
-              const float4 b0 = *reinterpret_cast<const float4*>(wv + c * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(wv + c * 8 + 4);
-              f[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
-              f[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
-              f[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
-              f[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
-            }
-            if (rb) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + nb + c * 8 + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * C::SUB_BYTES + (c % 5) * 16);
-            if (has_res) {
-              const uint4 r4 = *sp;
-              const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_16x2(ru[j], res_f16);
-                f[2 * j] += t.x;
-                f[2 * j + 1] += t.y;
-              }
-            } else if (args.residual && valid) {  // direct-store path with a residual (fp32 output): not used by the plan
-              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(args.residual + static_cast<size_t>(m) * args.res_ld + nb + c * 8));
-              const uint32_t ru[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = unpack_16x2(ru[j], res_f16);
-                f[2 * j] += t.x;
-                f[2 * j + 1] += t.y;
-              }
-            }
-            if (args.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-            }
+            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, v, wv, srow, C::SUB_BYTES, valid, gs);
             if (args.gn_partial) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int g = (c * 8 + j) / 10;  // compile-time after unrolling (80 columns -> 8 groups of 10)
-                const float x = valid ? f[j] : 0.f;
-                gs[2 * g] += x;
-                gs[2 * g + 1] = fmaf(x, x, gs[2 * g + 1]);
+              // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
+              const float tot = warp_transpose_reduce16(gs, lane);
+              const int mw = m0 + q * 32;
+              if (mw < args.M && lane < 16) {
+                const int smp = mw / args.rows_per_sample;
+                const int slot = (mw % args.rows_per_sample) >> 5;
+                const int nslot = args.rows_per_sample >> 5;
+                const int G = args.N / 10;
+                const int g = n_tile * (BN / 10) + half * (HC / 10) + (lane >> 1);
+                args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
               }
-            }
-            if (use_stg) {
-              *sp = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
-            } else if (valid) {
-              if (args.out_f32) {
-                float4* op = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
-                op[0] = make_float4(f[0], f[1], f[2], f[3]);
-                op[1] = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb + c * 8);
-                *op = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
-              }
-            }
-          }
-          if (args.gn_partial) {
-            // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
-            const float tot = warp_transpose_reduce16(gs, lane);
-            const int mw = m0 + q * 32;
-            if (mw < args.M && lane < 16) {
-              const int smp = mw / args.rows_per_sample;
-              const int slot = (mw % args.rows_per_sample) >> 5;
-              const int nslot = args.rows_per_sample >> 5;
-              const int G = args.N / 10;
-              const int g = n_tile * (BN / 10) + half * (HC / 10) + (lane >> 1);
-              args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
-            }
-          }
-        } else {
-          // GEGLU: out = (value + bv) * gelu(gate + bg); 40 output columns per warp = one staging sub-tile
-#pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            float f[8];
-            const float4 bv0 = *reinterpret_cast<const float4*>(wv + c * 8), bv1 = *reinterpret_cast<const float4*>(wv + c * 8 + 4);
-            const float4 bg0 = *reinterpret_cast<const float4*>(wv + 40 + c * 8), bg1 = *reinterpret_cast<const float4*>(wv + 40 + c * 8 + 4);
-            const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
-            const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
-            const uint4 o4 = make_uint4(pack_16x2(f[0], f[1], out_f16), pack_16x2(f[2], f[3], out_f16), pack_16x2(f[4], f[5], out_f16), pack_16x2(f[6], f[7], out_f16));
-            if (use_stg) {
-              *reinterpret_cast<uint4*>(srow + c * 16) = o4;
-            } else if (valid) {
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + n_tile * HC + half * 40 + c * 8) = o4;
             }
           }
         }
@@ -550,23 +483,29 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, int STAGES, int NSTG>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0>
 static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES, NSTG>;
+  using C = Cfg<BN, STAGES, NSTG, WSK>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
   const GemmArgs& a = L.args;
   if (a.N % BN != 0 || a.M <= 0) return cudaErrorInvalidValue;
-  const int tiles = (a.N / BN) * ((a.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, EPI, STAGES, NSTG><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
-                                                                                      L.mapB, L.mapOut, L.mapRes, a);
+  const int n_tiles = a.N / BN;
+  const int tiles = n_tiles * ((a.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (WSK > 0) {
+    // one n-tile per CTA for its whole life: the grid is a multiple of n_tiles (tiles is one already)
+    if (n_tiles > num_sms()) return cudaErrorInvalidValue;
+    grid = (grid / n_tiles) * n_tiles;
+  }
+  gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
+                                                                                           L.mapB, L.mapOut, L.mapRes, a);
   return cudaGetLastError();
 }
 
@@ -579,6 +518,14 @@ static int gemm_dbg_flags() {
   return v;
 }
 
+static bool gemm_ws_enabled() {  // env WD_GEMM_WS (default on): weight-stationary mode for K <= 320
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_WS");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 bool gemm_pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -591,7 +538,7 @@ static int gemm_pair_min_kblocks() {  // env WD_GEMM_PAIR_MINK: plain (non-GEGLU
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WD_GEMM_PAIR_MINK");
-    v = e ? atoi(e) : 40;  // measured (tools/op_bench.py): the pair kernel wins for the 3x3 convs (>= 45 K blocks) only
+    v = e ? atoi(e) : 80;  // measured (tools/op_bench.py, bench.py): the pair kernel wins for the 640-channel 3x3 convs (>= 90 K blocks)
   }
   return v;
 }
@@ -616,13 +563,15 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
     return launch_impl<GEMM_BLOCK_N_OUT, EPI_SAMPLER, 8, 0>(L, stream);
   }
   if (a.gn_partial && (a.gn_cpg != 10 || a.rows_per_sample % 32 || a.geglu || a.N % 10)) return cudaErrorInvalidValue;
-  if (a.geglu && a.residual) return cudaErrorInvalidValue;
+  if (a.geglu && (a.residual || a.out_f32 || a.out_f16)) return cudaErrorInvalidValue;
   if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
   // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
   // short K loops are epilogue / store bound: spend it on a second staging buffer
   if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
+  if (gemm_ws_enabled() && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms())
+    return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1, 5>(L, stream);  // weight-stationary short-K GEMM
   return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 2>(L, stream);
 }
 
