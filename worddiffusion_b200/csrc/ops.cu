@@ -93,7 +93,9 @@ cudaError_t groupnorm_stats_launch(const GroupNormStatsArgs& a, int B, cudaStrea
 
 constexpr int GN_APPLY_R = 16;  // pixel rows in flight per CTA pass (threads = Cs/8 * GN_APPLY_R)
 
-__global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormArgs a) {
+// 640 threads (C/8 x 16 rows) and <= 51 registers: two CTAs per SM.  (With the default 1024-thread bound ptxas took 64
+// registers -> one CTA per SM, 31 % occupancy, and the kernel ran latency-bound at 1.3-2.3 TB/s: profiles/r01k.)
+__global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNormArgs a) {
   __shared__ float s_mean[128], s_rstd[128];
   const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
   const int Cs = a.Cs, cpg = a.cpg;
@@ -143,15 +145,16 @@ __global__ void __launch_bounds__(1024) groupnorm_apply_kernel(const GroupNormAr
   }
   const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
   __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.out_ld + slab * Cs;
-  for (int p0 = rl; p0 < P; p0 += 4 * R) {
-    uint4 v[4];
+  constexpr int INFL = 2;  // independent 16-byte loads in flight per thread (x 1280 resident threads per SM)
+  for (int p0 = rl; p0 < P; p0 += INFL * R) {
+    uint4 v[INFL];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < INFL; ++i) {
       const int p = p0 + i * R;
       if (p < P) v[i] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < INFL; ++i) {
       const int p = p0 + i * R;
       if (p >= P) break;
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -183,8 +186,8 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
   if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || a.nchunk < 1 || a.HW % a.nchunk)
     return cudaErrorInvalidValue;
   int R = GN_APPLY_R;
-  while (R > 1 && nv * R > 1024) R >>= 1;
-  if (nv * R > 1024 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
+  while (R > 1 && nv * R > 640) R >>= 1;
+  if (nv * R > 640 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
   for (int i = 0; i < nslab; ++i)
     if (!a.partial[i] || a.pslots[i] < 1) return cudaErrorInvalidValue;
   groupnorm_apply_kernel<<<dim3(B, nslab, a.nchunk), nv * R, 0, s>>>(a);
