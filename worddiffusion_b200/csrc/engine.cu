@@ -63,6 +63,18 @@ struct GemmW {
   bf16* w = nullptr;  // [N, K] bf16, K-major
   float* bias = nullptr;
   int N = 0, K = 0;
+  float* ln_s = nullptr;  // LayerNorm folded into this Linear: column sums of the gamma-scaled weights (GemmArgs::ln_s)
+};
+// one nn.Linear whose preceding LayerNorm is folded into it at finalize time (ops.cu: fold_ln_linear_kernel)
+struct LnFold {
+  const float* raw_w;  // fp32 [N, K] copy of the state_dict weight
+  const float* raw_b;  // fp32 [N] copy of the bias, or null
+  const float* gamma;
+  const float* beta;
+  bf16* dst;
+  float* s_out;
+  float* b_out;
+  int N, K, ldk, n_off, geglu_bn;
 };
 struct NormW {
   float* g = nullptr;
@@ -181,6 +193,7 @@ struct wd_engine {
   bool pe_set = false;
   int n_kv = 0;
   std::vector<GemmW*> kv_weights;  // per K/V buffer: the fused [to_k; to_v] weight
+  std::vector<LnFold> ln_folds;
   // activations
   char* abase = nullptr;
   size_t acap = 0;
@@ -231,6 +244,23 @@ struct Builder {
       slot(pfx + ".bias", S_VEC, g.bias, N, N, 0, 0, 0, 0, geglu_bn);
     }
     return g;
+  }
+  // nn.Linear(K, Nrows) whose input is LayerNorm `ln` of an fp16 token tensor: rows land at [n_off, n_off + Nrows) of `g`
+  // (g.w / g.bias / g.ln_s are allocated by the caller for fused weights, or here when g.w is null)
+  void linear_ln(GemmW& g, const std::string& pfx, int Nrows, int K, bool bias, const NormW& ln, int n_off = 0, int Ntotal = 0,
+                 int geglu_bn = 0) {
+    if (!g.w) {
+      g.N = Ntotal ? Ntotal : Nrows;
+      g.K = K;
+      g.w = A.alloc<bf16>(static_cast<size_t>(g.N) * K);
+      g.bias = A.alloc<float>(g.N);
+      g.ln_s = A.alloc<float>(g.N);
+    }
+    float* raw_w = A.alloc<float>(static_cast<size_t>(Nrows) * K);
+    float* raw_b = bias ? A.alloc<float>(Nrows) : nullptr;
+    slot(pfx + ".weight", S_F32, raw_w, static_cast<int64_t>(Nrows) * K);
+    if (bias) slot(pfx + ".bias", S_F32, raw_b, Nrows);
+    if (!dry) e->ln_folds.push_back(LnFold{raw_w, raw_b, ln.g, ln.b, g.w, g.ln_s, g.bias, Nrows, K, K, n_off, geglu_bn});
   }
   GemmW conv3(const std::string& pfx, int Cout, int Cin, int extraK = 0, int as_f16 = 0) {
     GemmW g;
@@ -290,27 +320,25 @@ struct Builder {
     for (int d = 0; d < e->cfg.transformer_depth; ++d) {
       const std::string tp = pfx + "transformer_blocks." + std::to_string(d) + ".";
       TBlockL t;
+      // the three LayerNorms are folded into the Linear that consumes them (q / qkv projections and the GEGLU projection)
+      if (e->cfg.variant == WD_VARIANT_PHOSC) t.ln1 = norm(tp + "norm1", inner);
+      t.ln2 = norm(tp + "norm2", inner);
+      t.ln3 = norm(tp + "norm3", inner);
       if (e->cfg.variant == WD_VARIANT_PHOSC) {
-        t.ln1 = norm(tp + "norm1", inner);
-        // self-attention: q, k, v all from the normalised tokens -> one N = 3*inner GEMM
-        t.a1_q.N = 3 * inner;
-        t.a1_q.K = inner;
-        t.a1_q.w = A.alloc<bf16>(static_cast<size_t>(3) * inner * inner);
-        slot(tp + "attn1.to_q.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, 0, 0);
-        slot(tp + "attn1.to_k.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, inner, 0);
-        slot(tp + "attn1.to_v.weight", S_LIN, t.a1_q.w, static_cast<int64_t>(inner) * inner, inner, inner, inner, 0, 2 * inner, 0);
+        // self-attention: q, k, v all from LN1(x) -> one N = 3*inner GEMM
+        linear_ln(t.a1_q, tp + "attn1.to_q", inner, inner, false, t.ln1, 0, 3 * inner);
+        linear_ln(t.a1_q, tp + "attn1.to_k", inner, inner, false, t.ln1, inner);
+        linear_ln(t.a1_q, tp + "attn1.to_v", inner, inner, false, t.ln1, 2 * inner);
       } else {
-        // unet.py:337-341 -- attn1 is a cross-attention over the context; norm1 is never applied
-        t.a1_q = linear(tp + "attn1.to_q", inner, inner, false);
+        // unet.py:337-341 -- attn1 is a cross-attention over the context, fed by norm2 (norm1 is never applied)
+        linear_ln(t.a1_q, tp + "attn1.to_q", inner, inner, false, t.ln2);
         t.a1_kv = kv_fused(tp + "attn1", inner, ctx_dim);
       }
       t.a1_out = linear(tp + "attn1.to_out.0", inner, inner, true);
-      t.ln2 = norm(tp + "norm2", inner);
-      t.a2_q = linear(tp + "attn2.to_q", inner, inner, false);
+      linear_ln(t.a2_q, tp + "attn2.to_q", inner, inner, false, t.ln2);
       t.a2_kv = kv_fused(tp + "attn2", inner, ctx_dim);
       t.a2_out = linear(tp + "attn2.to_out.0", inner, inner, true);
-      t.ln3 = norm(tp + "norm3", inner);
-      t.ff_proj = linear(tp + "ff.net.0.proj", inner * 8, inner, true, gemm_geglu_block(inner * 8));
+      linear_ln(t.ff_proj, tp + "ff.net.0.proj", inner * 8, inner, true, t.ln3, 0, 0, gemm_geglu_block(inner * 8));
       t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
       s.blocks.push_back(t);
     }
@@ -349,6 +377,7 @@ struct Builder {
     const int ted = mc * 4;
     e->time_dim = ted;
     e->res.clear();
+    e->ln_folds.clear();
     e->st.clear();
     e->samp.clear();
     e->input_blocks.clear();
@@ -628,6 +657,8 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
     fail(WD_ERR_STATE, "%d parameters not loaded (first: %s)", missing, first.c_str());
     return missing;
   }
+  for (auto& f : e->ln_folds)
+    CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
   for (auto& r : e->res) {
     CUDA_TRY(repack_vec_launch(r.b_main, r.conv2.bias, r.Cout, 0, 0, 0, s));
     if (r.skip_conv) CUDA_TRY(repack_vec_launch(r.b_skip, r.conv2.bias, r.Cout, 0, 0, 1, s));
@@ -662,6 +693,9 @@ struct Epi {
   int res_f16 = 0;
   int act = 0;
   int geglu = 0;
+  float* ln_out = nullptr;          // write LayerNorm row statistics of the output tensor
+  const float* ln_stats = nullptr;  // A is an un-normalised tensor with these row statistics (weights carry gamma, see GemmW::ln_s)
+  int ln_dim = 0;
   Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
   int epi = EPI_STD;
 };
@@ -721,6 +755,13 @@ struct PlanBuilder {
     a.out_f32 = ep.out_f32;
     a.out_f16 = ep.out_f16;
     a.res_f16 = ep.res_f16;
+    a.ln_out = ep.ln_out;
+    a.ln_stats = ep.ln_stats;
+    a.ln_slots = ep.ln_dim / 80;
+    a.ln_dim = ep.ln_dim;
+    a.ln_eps = 1e-5f;  // nn.LayerNorm default (unet.py:314-316)
+    a.ln_s = w.ln_s;
+    if (ep.ln_stats && (!w.ln_s || ep.ln_dim % 80)) { err = "gemm: LayerNorm folding needs folded weights and channels % 80 == 0"; return false; }
     a.act = ep.act;
     a.geglu = ep.geglu;
     a.epi = ep.epi;
@@ -913,34 +954,43 @@ struct PlanBuilder {
     const int Ltot = plan->Ltot;
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
+    if (C % 80) { err = "spatial transformer: inner channels must be a multiple of 80 (LayerNorm folding)"; return false; }
+    // LayerNorm is folded into the GEMMs around it: the producer of each token tensor writes per-row {sum, sum of squares}
+    // (4 column blocks of 80), the consumer GEMM reads the raw fp16 tensor with gamma-scaled weights and normalises in its epilogue
+    auto new_rowstats = [&]() { return A.alloc<float>(static_cast<size_t>(M) * (C / 80) * 2); };
     Act x = new_act(H, W, C, true);  // token residual stream: fp16
+    float* rs_x = new_rowstats();
     {
       Epi ep;
       ep.out = x.p;
       ep.out_ld = C;
       ep.out_f16 = 1;
+      ep.ln_out = rs_x;
       if (!gemm_op(ops, M, false, 0, 0, {ASrc{g.p, g.C, g.C, 1, 1, H, W}}, s.proj_in, ep)) return false;
     }
-    Act n = new_act(H, W, C);
     Act o = new_act(H, W, C);
-    for (auto& t : s.blocks) {
+    for (size_t bi = 0; bi < s.blocks.size(); ++bi) {
+      const TBlockL& t = s.blocks[bi];
       // --- attn1 ---
       Act x1 = new_act(H, W, C, true);
+      float* rs_x1 = new_rowstats();
       if (e->cfg.variant == WD_VARIANT_PHOSC) {
-        ln_op(ops, x, n.p, t.ln1, M);
         bf16* qkv = A.alloc<bf16>(static_cast<size_t>(M) * 3 * C);
         Epi ep;
         ep.out = qkv;
         ep.out_ld = 3 * C;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a1_q, ep)) return false;
+        ep.ln_stats = rs_x;  // LN1 (unetPhosc.py:241)
+        ep.ln_dim = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
         attn_op(ops, qkv, 3 * C, qkv + C, qkv + 2 * C, 3 * C, o.p, C, HW, HW, s.heads, s.dh);
       } else {
-        ln_op(ops, x, n.p, t.ln2, M);  // unet.py:337 applies norm2 before attn1
         bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
         ep.out = q;
         ep.out_ld = C;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a1_q, ep)) return false;
+        ep.ln_stats = rs_x;  // unet.py:337 applies norm2 before attn1
+        ep.ln_dim = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
         attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
       }
       {
@@ -950,18 +1000,21 @@ struct PlanBuilder {
         ep.out_f16 = 1;
         ep.residual = x.p;
         ep.res_ld = C;
-        ep.res_f16 = x.f16 ? 1 : 0;
+        ep.res_f16 = 1;
+        ep.ln_out = rs_x1;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a1_out, ep)) return false;
       }
       // --- attn2 (cross) ---
       Act x2 = new_act(H, W, C, true);
-      ln_op(ops, x1, n.p, t.ln2, M);
+      float* rs_x2 = new_rowstats();
       {
         bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
         ep.out = q;
         ep.out_ld = C;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.a2_q, ep)) return false;
+        ep.ln_stats = rs_x1;  // LN2
+        ep.ln_dim = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
         attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
         Epi ep2;
         ep2.out = x2.p;
@@ -970,18 +1023,21 @@ struct PlanBuilder {
         ep2.residual = x1.p;
         ep2.res_ld = C;
         ep2.res_f16 = 1;
+        ep2.ln_out = rs_x2;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{o.p, C, C, 1, 1, H, W}}, t.a2_out, ep2)) return false;
       }
       // --- GEGLU feed-forward ---
       Act x3 = new_act(H, W, C, true);
-      ln_op(ops, x2, n.p, t.ln3, M);
+      float* rs_x3 = (bi + 1 < s.blocks.size()) ? new_rowstats() : nullptr;  // only a further transformer block normalises x3
       {
         bf16* gg = A.alloc<bf16>(static_cast<size_t>(M) * 4 * C);
         Epi ep;
         ep.out = gg;
         ep.out_ld = 4 * C;
         ep.geglu = 1;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{n.p, C, C, 1, 1, H, W}}, t.ff_proj, ep)) return false;
+        ep.ln_stats = rs_x2;  // LN3
+        ep.ln_dim = C;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x2.p, C, C, 1, 1, H, W, true}}, t.ff_proj, ep)) return false;
         Epi ep2;
         ep2.out = x3.p;
         ep2.out_ld = C;
@@ -989,9 +1045,11 @@ struct PlanBuilder {
         ep2.residual = x2.p;
         ep2.res_ld = C;
         ep2.res_f16 = 1;
+        ep2.ln_out = rs_x3;
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{gg, 4 * C, 4 * C, 1, 1, H, W}}, t.ff_out, ep2)) return false;
       }
       x = x3;
+      rs_x = rs_x3;
     }
     out = new_act(H, W, s.C, true);
     Epi ep;

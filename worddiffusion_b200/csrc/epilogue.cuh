@@ -14,8 +14,10 @@ namespace wd {
 // srow: this thread's row in staging sub-tile 0 of the round (sub-tile 1 is `sub_stride` bytes further; a sub-tile row is
 // 40 columns = 5 chunks of 16 bytes).  RES: the staging chunk holds the residual (TMA-prefetched) and is added in place.
 // GN: accumulate GroupNorm partial sums gs[2g] += x, gs[2g+1] += x^2 over the 8 groups of 10 columns (invalid rows add 0).
-template <bool RES, bool GN, bool F16>
+// LNS: also return {sum x, sum x^2} of the thread's 80 values in gs[0], gs[1] (LayerNorm row statistics for the consumer GEMM).
+template <bool RES, bool GN, bool F16, bool LNS = false>
 WD_DEVINL void epi_round80(const uint32_t* v, const float* wvr, uint8_t* srow, int sub_stride, bool valid, float* gs) {
+  float ls = 0.f, lq = 0.f;
 #pragma unroll
   for (int c = 0; c < 10; ++c) {  // 8 columns = one 16-byte staging chunk
     float f[8];
@@ -45,16 +47,49 @@ WD_DEVINL void epi_round80(const uint32_t* v, const float* wvr, uint8_t* srow, i
         gs[2 * g + 1] = fmaf(x, x, gs[2 * g + 1]);
       }
     }
+    if constexpr (LNS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ls += f[j];
+        lq = fmaf(f[j], f[j], lq);
+      }
+    }
     if constexpr (F16)
       *sp = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
     else
       *sp = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
   }
+  if constexpr (LNS) {
+    gs[0] = ls;
+    gs[1] = lq;
+  }
+}
+
+// LayerNorm-consuming flavour: y = rstd * acc + (b'[c] - rstd*mu * s[c]); wvr = b', wsr = s (shared memory); bf16 out
+WD_DEVINL void epi_round80_lnc(const uint32_t* v, const float* wvr, const float* wsr, float rstd, float rstd_mu, uint8_t* srow,
+                               int sub_stride) {
+#pragma unroll
+  for (int c = 0; c < 10; ++c) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(wvr + c * 8), b1 = *reinterpret_cast<const float4*>(wvr + c * 8 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(wsr + c * 8), s1 = *reinterpret_cast<const float4*>(wsr + c * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(rstd, __uint_as_float(v[c * 8 + j]), fmaf(-rstd_mu, ss[j], bb[j]));
+    uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * sub_stride + (c % 5) * 16);
+    *sp = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
 }
 
 // run-time dispatch to the straight-line variants (flags are warp-uniform)
-WD_DEVINL void epi_round80_dispatch(bool res, bool gn, bool f16, const uint32_t* v, const float* wvr, uint8_t* srow,
+WD_DEVINL void epi_round80_dispatch(bool res, bool gn, bool f16, bool lns, const uint32_t* v, const float* wvr, uint8_t* srow,
                                     int sub_stride, bool valid, float* gs) {
+  if (lns) {  // row statistics for a following LayerNorm: only produced for the fp16 token stream, never together with GN
+    if (res) epi_round80<true, false, true, true>(v, wvr, srow, sub_stride, valid, gs);
+    else epi_round80<false, false, true, true>(v, wvr, srow, sub_stride, valid, gs);
+    return;
+  }
   const int sel = (res ? 4 : 0) | (gn ? 2 : 0) | (f16 ? 1 : 0);
   switch (sel) {
     case 0: epi_round80<false, false, false>(v, wvr, srow, sub_stride, valid, gs); break;
@@ -116,17 +151,33 @@ WD_DEVINL void epi_round80_generic(const uint32_t* v, const float* wvr, const fl
 
 // GEGLU (unet.py:127-129): out = (value + bv) * gelu(gate + bg) for 40 output columns; v[0..39] values, v[40..79] gates,
 // wv_val / wv_gate their biases; writes one staging sub-tile row (5 chunks), bf16.
-WD_DEVINL void epi_geglu40(const uint32_t* v, const float* wv_val, const float* wv_gate, uint8_t* srow) {
+// LNC: the A operand was the un-normalised tensor: value / gate = rstd * acc + (b' - rstd*mu * s) first (ws_* = s vectors).
+template <bool LNC>
+WD_DEVINL void epi_geglu40(const uint32_t* v, const float* wv_val, const float* wv_gate, uint8_t* srow, const float* ws_val = nullptr,
+                           const float* ws_gate = nullptr, float rstd = 1.f, float rstd_mu = 0.f) {
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
     float f[8];
     const float4 bv0 = *reinterpret_cast<const float4*>(wv_val + c * 8), bv1 = *reinterpret_cast<const float4*>(wv_val + c * 8 + 4);
     const float4 bg0 = *reinterpret_cast<const float4*>(wv_gate + c * 8), bg1 = *reinterpret_cast<const float4*>(wv_gate + c * 8 + 4);
-    const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
-    const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
+    float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+    float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
+    float sc = 1.f;
+    if constexpr (LNC) {
+      const float4 sv0 = *reinterpret_cast<const float4*>(ws_val + c * 8), sv1 = *reinterpret_cast<const float4*>(ws_val + c * 8 + 4);
+      const float4 sg0 = *reinterpret_cast<const float4*>(ws_gate + c * 8), sg1 = *reinterpret_cast<const float4*>(ws_gate + c * 8 + 4);
+      const float sv[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
+      const float sg[8] = {sg0.x, sg0.y, sg0.z, sg0.w, sg1.x, sg1.y, sg1.z, sg1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bv[j] = fmaf(-rstd_mu, sv[j], bv[j]);
+        bg[j] = fmaf(-rstd_mu, sg[j], bg[j]);
+      }
+      sc = rstd;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      f[j] = (__uint_as_float(v[c * 8 + j]) + bv[j]) * gelu_fast_f(__uint_as_float(v[40 + c * 8 + j]) + bg[j]);
+      f[j] = fmaf(sc, __uint_as_float(v[c * 8 + j]), bv[j]) * gelu_fast_f(fmaf(sc, __uint_as_float(v[40 + c * 8 + j]), bg[j]));
     *reinterpret_cast<uint4*>(srow + c * 16) =
         make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
   }

@@ -300,7 +300,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
 
         if (args.geglu) {
-          epi_geglu40(v, wv + rnd * 40, wv + 80 + rnd * 40, srow);
+          epi_geglu40<false>(v, wv + rnd * 40, wv + 80 + rnd * 40, srow);
         } else {
           const int nb = n0 + half * 160 + rnd * 80;
           const float* wvr = wv + rnd * 80;
@@ -315,7 +315,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
 #pragma unroll
             for (int i = 0; i < 16; ++i) gs[i] = 0.f;
-            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, v, wvr, srow, PAIR_SUB_BYTES, valid, gs);
+            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, false, v, wvr, srow, PAIR_SUB_BYTES, valid, gs);
             if (args.gn_partial) {
               // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
               const float tot = warp_transpose_reduce16(gs, lane);
@@ -370,6 +370,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 bool gemm_pair_supported(const GemmArgs& a) {
   if (a.epi != EPI_STD) return false;
   if (a.N % PAIR_BN) return false;
+  if (a.ln_out || a.ln_stats) return false;  // LayerNorm folding lives in the single-CTA kernel (K = 320 GEMMs)
   if (a.geglu) return false;  // the kernel implements it (value | gate per 320-column tile) but the weights are packed for 160-column tiles
   if (a.out_f32 && a.residual) return false;
   return true;

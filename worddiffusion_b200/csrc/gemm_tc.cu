@@ -26,7 +26,8 @@ struct Cfg {
   static constexpr int SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;  // one dense [128][40] bf16 sub-tile
   static constexpr int HALF_STG_BYTES = 2 * SUB_BYTES;             // 80 columns of one column half
   static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
-  static constexpr int VEC_BYTES = GEMM_EPI_WARPS * 80 * 4;  // per-warp bias / row-bias vector of its 80 accumulator columns
+  // per-warp bias / row-bias vector of its 80 accumulator columns (+ a second one, the LayerNorm column sums, in WS mode)
+  static constexpr int VEC_BYTES = (WSK ? 2 : 1) * GEMM_EPI_WARPS * 80 * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + 256 /*barriers*/;
 };
 
@@ -246,6 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint8_t* const stg_half = stg + half * NB * C::HALF_STG_BYTES;
       uint64_t* const res_bar = res_full_bar + half * 2;
       float* const wv = vecs + (warp - 2) * 80;
+      float* const wv2 = vecs + GEMM_EPI_WARPS * 80 + (warp - 2) * 80;  // WS mode only: ln_s of this warp's columns
+      const bool ln_consume = (WSK > 0) && args.ln_stats != nullptr;
       const bool out_f16 = args.out_f16 != 0, res_f16 = args.res_f16 != 0;
 
       auto issue_res_load = [&](int tile_, int sb_) {
@@ -291,9 +294,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               float x = args.bias ? __ldg(args.bias + col) : 0.f;
               if (rbw) x += __ldg(rbw + col);
               wv[c] = x;
+              if constexpr (WSK > 0) {
+                if (ln_consume) wv2[c] = __ldg(args.ln_s + col);
+              }
             }
           }
           __syncwarp();
+        }
+
+        float ln_rstd = 0.f, ln_rstd_mu = 0.f;
+        if (ln_consume && valid) {
+          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m) * args.ln_slots;
+          float S = 0.f, Q = 0.f;
+          for (int i = 0; i < args.ln_slots; ++i) {
+            const float2 t = __ldg(st + i);
+            S += t.x;
+            Q += t.y;
+          }
+          const float inv = 1.0f / static_cast<float>(args.ln_dim);
+          const float mu = S * inv;
+          ln_rstd = rsqrtf(fmaxf(Q * inv - mu * mu, 0.f) + args.ln_eps);
+          ln_rstd_mu = ln_rstd * mu;
         }
 
         mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
@@ -342,10 +363,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (args.dbg & 128) {
         } else if (args.geglu) {
           // values of this warp: tile columns [40 half, +40), gates 80 further; 40 output columns = one staging sub-tile
-          if (use_stg) epi_geglu40(v, wv, wv + 40, srow);  // (every GEGLU launch stages: gemm_tc_launch rejects geglu + fp32 output)
+          // (every GEGLU launch stages: gemm_tc_launch rejects geglu + fp32 output)
+          if (ln_consume) epi_geglu40<true>(v, wv, wv + 40, srow, wv2, wv2 + 40, ln_rstd, ln_rstd_mu);
+          else if (use_stg) epi_geglu40<false>(v, wv, wv + 40, srow);
         } else {
           const int nb = n0 + half * HC;
-          if (slow_path) {
+          if (ln_consume) {
+            epi_round80_lnc(v, wv, wv2, ln_rstd, ln_rstd_mu, srow, C::SUB_BYTES);
+          } else if (slow_path) {
             epi_round80_generic(v, wv, rb ? rb + nb : nullptr, args.act == ACT_SILU,
                                 (args.residual && !has_res) ? args.residual + static_cast<size_t>(m) * args.res_ld + nb : nullptr,
                                 res_f16, use_stg, srow, C::SUB_BYTES, args.out_f32 != 0, out_f16,
@@ -356,7 +381,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             float gs[16];  // GroupNorm partials: [2g] = sum, [2g+1] = sum of squares of group g (10 columns) of this row
 #pragma unroll
             for (int i = 0; i < 16; ++i) gs[i] = 0.f;
-            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, v, wv, srow, C::SUB_BYTES, valid, gs);
+            epi_round80_dispatch(has_res, args.gn_partial != nullptr, out_f16, args.ln_out != nullptr, v, wv, srow, C::SUB_BYTES,
+                                 valid, gs);
+            if (args.ln_out && valid)  // LayerNorm row statistics of the tensor being written (this thread's 80 columns)
+              *reinterpret_cast<float2*>(args.ln_out + (static_cast<size_t>(m) * (args.N / 80) + nb / 80) * 2) = make_float2(gs[0], gs[1]);
             if (args.gn_partial) {
               // rows of a warp belong to one sample (rows_per_sample % 32 == 0): reduce over the 32 rows, lane L < 16 keeps entry L
               const float tot = warp_transpose_reduce16(gs, lane);
@@ -564,14 +592,19 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   }
   if (a.gn_partial && (a.gn_cpg != 10 || a.rows_per_sample % 32 || a.geglu || a.N % 10)) return cudaErrorInvalidValue;
   if (a.geglu && (a.residual || a.out_f32 || a.out_f16)) return cudaErrorInvalidValue;
+  if (a.ln_out && (a.gn_partial || !a.out_f16 || a.out_f32 || a.geglu || a.act != ACT_NONE || a.N % 80)) return cudaErrorInvalidValue;
+  if (a.ln_stats && (a.residual || a.gn_partial || a.out_f32 || a.out_f16 || a.rowbias || a.act != ACT_NONE || !a.ln_s ||
+                     a.ln_slots < 1 || a.conv || a.num_src != 1))
+    return cudaErrorInvalidValue;
   if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
   // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
   // short K loops are epilogue / store bound: spend it on a second staging buffer
   if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
-  if (gemm_ws_enabled() && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms())
+  if ((gemm_ws_enabled() || a.ln_stats) && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms())
     return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1, 5>(L, stream);  // weight-stationary short-K GEMM
+  if (a.ln_stats) return cudaErrorInvalidValue;  // the LayerNorm-consuming epilogue exists in the weight-stationary build only
   return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 2>(L, stream);
 }
 

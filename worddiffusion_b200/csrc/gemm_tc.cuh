@@ -69,6 +69,17 @@ struct GemmArgs {
   int res_f16;  // format of the residual tensor
   int act;
   int geglu;  // 1: tile columns [0,BN/2) are values, [BN/2,BN) gates; writes BN/2 columns per tile
+  // LayerNorm folded into the GEMMs around it (unet.py:314-316 + the Linear that follows, e.g. :337 / :175):
+  //   producer side: ln_out != null -> every epilogue thread also writes {sum x, sum x^2} of its 80 output columns of its row:
+  //                  ln_out[(m * (N/80) + column_block) * 2 + {0,1}]   (fp32, before the 16-bit rounding)
+  //   consumer side: ln_stats != null -> A is the un-normalised tensor, the weights are gamma (.) W, and the epilogue applies
+  //                  y = rstd_m * (acc - mu_m * ln_s[n]) + bias[n]  with bias = W beta + b and ln_s[n] = sum_k gamma_k W[n,k]
+  float* ln_out;
+  const float* ln_stats;  // [M][ln_slots][2]
+  int ln_slots;           // 80-column blocks per row of the normalised tensor (its channels / 80)
+  int ln_dim;             // channels of the normalised tensor
+  float ln_eps;
+  const float* ln_s;      // [N]
   // GroupNorm partial statistics of the written tensor: gn_partial[sample][N/gn_cpg groups][rows_per_sample/32][2]
   float* gn_partial;  // null: off.  Needs gn_cpg == 10, rows_per_sample % 32 == 0
   int gn_cpg;

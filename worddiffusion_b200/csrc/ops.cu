@@ -110,6 +110,18 @@ __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNorm
   const int ng = Cs / cpg;         // GroupNorm groups inside this slab (<= 128, checked by the launcher)
   const bool xf16 = a.x_f16[slab] != 0;
 
+  const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
+  __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.out_ld + slab * Cs;
+  constexpr int INFL = 2;  // independent 16-byte loads in flight per thread (x 1280 resident threads per SM)
+
+  // the first rows do not depend on the statistics: get them in flight before the reduction below
+  uint4 v[INFL];
+#pragma unroll
+  for (int i = 0; i < INFL; ++i) {
+    const int p = rl + i * R;
+    if (p < P) v[i] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
+  }
+
   // one thread per group folds the partial sums in a fixed order (bit-reproducible), then everybody forms scale/shift
   if (static_cast<int>(threadIdx.x) < ng) {
     const float2* part = reinterpret_cast<const float2*>(a.partial[slab]) +
@@ -143,15 +155,13 @@ __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNorm
       sh[j] = be[j] - s_mean[g] * sc[j];
     }
   }
-  const __nv_bfloat16* xb = a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * ld;
-  __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P) * a.out_ld + slab * Cs;
-  constexpr int INFL = 2;  // independent 16-byte loads in flight per thread (x 1280 resident threads per SM)
   for (int p0 = rl; p0 < P; p0 += INFL * R) {
-    uint4 v[INFL];
+    if (p0 != rl) {
 #pragma unroll
-    for (int i = 0; i < INFL; ++i) {
-      const int p = p0 + i * R;
-      if (p < P) v[i] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
+      for (int i = 0; i < INFL; ++i) {
+        const int p = p0 + i * R;
+        if (p < P) v[i] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld) + col);
+      }
     }
 #pragma unroll
     for (int i = 0; i < INFL; ++i) {
@@ -176,7 +186,8 @@ __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNorm
 }
 
 int groupnorm_apply_chunks(int HW) {
-  // 8 pixel rows per thread (two passes of 4 independent 16-byte loads) when the image is large enough
+  // 8 pixel rows per thread (four passes of 2 independent 16-byte loads) when the image is large enough: finer chunks
+  // (more CTAs, each repeating the statistics preamble) measured slower (profiles/)
   const int per = 8 * GN_APPLY_R;
   return (HW >= 2 * per && HW % per == 0) ? HW / per : 1;
 }
@@ -540,6 +551,41 @@ __global__ void repack_vec_kernel(const float* __restrict__ v, float* __restrict
 cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
                               cudaStream_t s) {
   repack_vec_kernel<<<(N + 255) / 256, 256, 0, s>>>(v, dst, N, n_off, geglu_bn, accumulate);
+  return cudaGetLastError();
+}
+
+// LayerNorm folded into the Linear that follows it (gemm_tc.cuh, GemmArgs::ln_stats): one warp per weight row n
+//   W'[n,k] = fp16(gamma[k] W[n,k]),  s[n] = sum_k W'[n,k] (of the ROUNDED values the MMA will use),  b'[n] = sum_k beta[k] W[n,k] + b[n]
+__global__ void __launch_bounds__(256) fold_ln_linear_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ bias,
+                                                             __nv_bfloat16* __restrict__ dst, float* __restrict__ s_out,
+                                                             float* __restrict__ b_out, int N, int K, int ldk, int n_off,
+                                                             int geglu_bn) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int nn = (geglu_bn ? geglu_perm(n, N, geglu_bn) : n) + n_off;
+  float s = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[static_cast<size_t>(n) * K + k];
+    const __half h = __float2half_rn(gamma[k] * wv);
+    dst[static_cast<size_t>(nn) * ldk + k] = *reinterpret_cast<const __nv_bfloat16*>(&h);
+    s += __half2float(h);
+    b = fmaf(beta[k], wv, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    s_out[nn] = s;
+    b_out[nn] = b + (bias ? bias[n] : 0.f);
+  }
+}
+cudaError_t fold_ln_linear_launch(const float* w, const float* gamma, const float* beta, const float* bias, __nv_bfloat16* dst,
+                                  float* s_out, float* b_out, int N, int K, int ldk, int n_off, int geglu_bn, cudaStream_t s) {
+  fold_ln_linear_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(w, gamma, beta, bias, dst, s_out, b_out, N, K, ldk, n_off, geglu_bn);
   return cudaGetLastError();
 }
 

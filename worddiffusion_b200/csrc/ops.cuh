@@ -97,6 +97,10 @@ cudaError_t repack_linear_launch(const float* w, __nv_bfloat16* dst, int N, int 
 // vector [N] -> dst[perm(n) + n_off] (accumulate: dst += src)
 cudaError_t repack_vec_launch(const float* v, float* dst, int N, int n_off, int geglu_bn, int accumulate,
                               cudaStream_t s);
+// LayerNorm (gamma, beta over K) folded into nn.Linear(K, N): dst = fp16(gamma (.) W) at rows perm(n) + n_off,
+// s_out[n'] = row sums of the rounded weights, b_out[n'] = W beta + bias
+cudaError_t fold_ln_linear_launch(const float* w, const float* gamma, const float* beta, const float* bias, __nv_bfloat16* dst,
+                                  float* s_out, float* b_out, int N, int K, int ldk, int n_off, int geglu_bn, cudaStream_t s);
 // conv_in weight [Cout,4,3,3] -> bf16 [Cout, 128]: w_hi | w_hi | w_lo | 0
 cudaError_t repack_conv_in_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, cudaStream_t s);
 
