@@ -144,9 +144,11 @@ def test_attention_small(Sq, L):
     assert relerr(probs, p) < 1e-4
 
 
-@pytest.mark.parametrize("Sq,Skv", [(256, 256), (64, 64), (256, 779), (64, 779), (100, 70)])
+@pytest.mark.parametrize("Sq,Skv", [(256, 256), (64, 64), (256, 779), (64, 779), (100, 70), (256, 10), (64, 10), (100, 16),
+                                    (64, 1)])
 def test_attention_flash(Sq, Skv):
-    """Self-attention (256/64 tokens) and cross-attention over the 779-token char+PHOSC context (unetPhosc.py:176-196).
+    """Self-attention (256/64 tokens), cross-attention over the 779-token char+PHOSC context (unetPhosc.py:176-196) and over
+    the 10-token character context (Skv <= 16: the dedicated short-context kernel).
     P is rounded to bf16 before P.V (as flash kernels do): tolerance 2^-7."""
     B, heads, C = 2, 4, 320
     q, k, v = (bf(torch.randn(B, n, C, generator=g(40 + i))) for i, n in enumerate((Sq, Skv, Skv)))
