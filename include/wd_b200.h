@@ -141,6 +141,55 @@ int wd_op_attention(const void* q, int ldq, const void* k, const void* v, int ld
                     int Skv, int heads, float scale, void* stream);
 int wd_op_gemm_block_n(void);
 
+/* ==== training step (reference train.py:281-294; model = unet.UNetModel, train.py:403) ==================================
+ * predicted_noise = model(x_t, ..., timesteps=t, context=text_features, y=s_id); loss.backward(); optimizer.step();
+ * ema.step_ema().  The trainer BINDS the caller's fp32 parameter and gradient tensors (reference state_dict layout, e.g.
+ * the storage of torch nn.Parameters and of their .grad): it never owns master weights.  bf16 tensor-core packs of the
+ * parameters are refreshed by wd_trainer_sync_weights (call it after every optimizer step).  Gradients are ACCUMULATED
+ * (+=) into the bound buffers: zero them first (optimizer.zero_grad(), train.py:289). */
+typedef struct wd_trainer wd_trainer;
+int wd_trainer_create(const wd_config* cfg, wd_trainer** out);
+void wd_trainer_destroy(wd_trainer* t);
+/* name = reference state_dict key; w, grad: fp32 device tensors of `shape`.  Returns WD_IGNORED for parameters the
+ * reference forward never reads (they receive no gradient in the reference either: SURVEY 8a, a17). */
+int wd_trainer_bind_param(wd_trainer* t, const char* name, const float* w, float* grad, const int64_t* shape, int ndim);
+int wd_trainer_set_pos_encoding(wd_trainer* t, const float* pe, void* stream);
+int wd_trainer_sync_weights(wd_trainer* t, void* stream);
+/* forward of UNetModel.forward (unet.py:1499-1836) keeping every activation the backward pass needs.
+ * x: fp32 NCHW [B,4,H,W]; timesteps, y: int64 [B]; ctx_tokens: int64 [B,L]; eps_out: fp32 NCHW [B,4,H,W]. */
+int wd_trainer_forward(wd_trainer* t, int batch, const float* x, const int64_t* timesteps, const int64_t* y,
+                       const int64_t* ctx_tokens, int L, float* eps_out, void* stream);
+/* backward of the last wd_trainer_forward: d_eps = dLoss/d eps_out, fp32 NCHW [B,4,H,W] (for train.py:287's nn.MSELoss:
+ * 2 (eps - noise) / numel).  y / ctx_tokens: the same index tensors as in the forward call (embedding gradients). */
+int wd_trainer_backward(wd_trainer* t, const float* d_eps, const int64_t* y, const int64_t* ctx_tokens, void* stream);
+int wd_trainer_launch_counts(const wd_trainer* t, int* fwd, int* bwd);
+size_t wd_trainer_workspace_bytes(const wd_trainer* t);
+size_t wd_trainer_weight_bytes(const wd_trainer* t);
+/* torch.optim.AdamW step (train.py:405, lr 1e-4, default betas / eps / weight_decay) fused with the EMA update of
+ * train.py:140-170 over flat fp32 buffers.  step >= 1 (bias correction); grad_scale multiplies g (1/world_size after a
+ * sum all-reduce).  ema_mode 0: no EMA, 1: ema = p (EMA.reset_parameters during the 2000-step warm-up), 2: ema =
+ * ema_beta * ema + (1 - ema_beta) * p. */
+int wd_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float ema_beta, int ema_mode, float grad_scale, void* stream);
+
+/* ---- single backward operators (parity tests; same kernels as the trainer) ---- */
+/* dw[N,K] += dy[M,N]^T x[M,K] on tcgen05 (MN-major operands).  N % 320 == 0 (or N == 64), K >= 128, K % 64 == 0 */
+int wd_op_wgrad_linear(const void* x_bf16, const void* dy_bf16, float* dw, int M, int N, int K, void* stream);
+/* dw[Cout,Cin,3,3] += conv3x3 weight gradient; x NHWC [B,H,W,Cin], dy NHWC [B,H/stride,W/stride,Cout] */
+int wd_op_wgrad_conv3x3(const void* x_bf16, const void* dy_bf16, float* dw, int B, int H, int W, int Cin, int Cout, int stride,
+                        void* stream);
+/* transposed packs for the data-gradient GEMMs: wd_op_conv3x3(dy, pack_T(w)) = d x (stride 1), wd_op_gemm(dy, pack_T(w)) = d x */
+int wd_op_pack_conv3x3_t(const float* w_oihw, void* dst_bf16, int Cout, int Cin, void* stream);
+int wd_op_pack_linear_t(const float* w, void* dst_bf16, int N, int K, void* stream);
+int wd_op_groupnorm_bwd(const void* x_bf16, const void* dy_bf16, const float* gamma, const float* beta, void* dx_bf16,
+                        float* dgamma, float* dbeta, int B, int HW, int C, int groups, float eps, int silu, void* stream);
+int wd_op_layernorm_bwd(const void* x_bf16, const void* dy_bf16, const float* gamma, const void* add_bf16, void* dx_bf16,
+                        float* dgamma, float* dbeta, int M, int C, float eps, void* stream);
+int wd_op_geglu_fwd(const void* p_bf16, void* out_bf16, int M, int H, void* stream);
+int wd_op_geglu_bwd(const void* p_bf16, const void* dout_bf16, void* dp_bf16, int M, int H, void* stream);
+int wd_op_attention_small_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int B,
+                              int Sq, int L, int heads, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

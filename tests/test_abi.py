@@ -35,7 +35,8 @@ def test_header_symbols_are_bound_and_exported(lib_path):
 
 def test_library_has_no_torch_or_cudart_dependency(lib_path):
     out = subprocess.run(["ldd", lib_path], capture_output=True, text=True).stdout
-    assert "torch" not in out and "libcudart" not in out and "c10" not in out
+    names = " ".join(line.split()[0] for line in out.splitlines() if line.strip())  # library names only (load addresses are random hex)
+    assert "torch" not in names and "libcudart" not in names and "c10" not in names
 
 
 def test_version_and_error_string(lib_path):

@@ -53,6 +53,27 @@ SIGNATURES = {
     "wd_op_attention_small": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "wd_op_attention": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "wd_op_gemm_block_n": (_I, []),
+    # ---- training step ----
+    "wd_trainer_create": (_I, [C.POINTER(WdConfig), C.POINTER(_P)]),
+    "wd_trainer_destroy": (None, [_P]),
+    "wd_trainer_bind_param": (_I, [_P, C.c_char_p, _P, _P, C.POINTER(_I64), _I]),
+    "wd_trainer_set_pos_encoding": (_I, [_P, _P, _P]),
+    "wd_trainer_sync_weights": (_I, [_P, _P]),
+    "wd_trainer_forward": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "wd_trainer_backward": (_I, [_P, _P, _P, _P, _P]),
+    "wd_trainer_launch_counts": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "wd_trainer_workspace_bytes": (C.c_size_t, [_P]),
+    "wd_trainer_weight_bytes": (C.c_size_t, [_P]),
+    "wd_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, C.c_size_t, _F, _F, _F, _F, _F, _I, _F, _I, _F, _P]),
+    "wd_op_wgrad_linear": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "wd_op_wgrad_conv3x3": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "wd_op_pack_conv3x3_t": (_I, [_P, _P, _I, _I, _P]),
+    "wd_op_pack_linear_t": (_I, [_P, _P, _I, _I, _P]),
+    "wd_op_groupnorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "wd_op_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "wd_op_geglu_fwd": (_I, [_P, _P, _I, _I, _P]),
+    "wd_op_geglu_bwd": (_I, [_P, _P, _P, _I, _I, _P]),
+    "wd_op_attention_small_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
 }
 
 _lib = None

@@ -38,6 +38,11 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* wd_last_error(void) { return g_err.c_str(); }
+// shared with train.cu (engine_internal.h)
+int wd_set_error(int code, const char* msg) {
+  g_err = msg ? msg : "";
+  return code;
+}
 extern "C" int wd_version(void) { return 1; }
 extern "C" int wd_op_gemm_block_n(void) { return gemm_tc_block_n(); }
 

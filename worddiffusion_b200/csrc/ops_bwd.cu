@@ -1,0 +1,918 @@
+// Backward / training-only kernels, see ops_bwd.cuh.  All HBM-/latency-bound: 16-byte accesses, fp32 arithmetic.
+#include "ops_bwd.cuh"
+
+#include <mutex>
+
+namespace wd {
+
+namespace {
+
+WD_DEVINL void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16x2(u[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+WD_DEVINL uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+WD_DEVINL void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+// d/dz silu(z) = s (1 + z (1 - s)),  s = sigmoid(z)
+WD_DEVINL float silu_grad_f(float z) {
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
+
+}  // namespace
+
+// =====================================================================================================
+// GroupNorm (+SiLU) backward.  With g = dz * gamma (dz = dy * act'(z)), n = cpg * HW elements per (sample, group):
+//   dx = rstd * (g - mean_n(g) - xhat * mean_n(g * xhat)),   dgamma_c = sum dz * xhat,   dbeta_c = sum dz
+// Pass 1 reduces {sum dz, sum dz*xhat} per (sample, channel) into `ws` (no atomics); the group means are gamma-weighted
+// sums of those, formed in the preamble of pass 2.  Pass 3 folds ws over the batch into dgamma / dbeta.
+// =====================================================================================================
+constexpr int GNB_R = 16;
+
+// mean / rstd of the groups of one slab from the forward partial statistics (same fold order as groupnorm_apply_kernel)
+WD_DEVINL void gn_group_stats(const GroupNormBwdArgs& a, int b, int slab, int g, float& mean, float& rstd) {
+  const int merge = a.cpg / a.pcpg;
+  const int PG = a.Cs / a.pcpg;
+  const int slots = a.pslots[slab];
+  const float2* part = reinterpret_cast<const float2*>(a.partial[slab]) +
+                       (static_cast<size_t>(b) * PG + static_cast<size_t>(g) * merge) * slots;
+  float S = 0.f, Q = 0.f;
+  const int n = merge * slots;
+  for (int k = 0; k < n; ++k) {
+    const float2 t = __ldg(part + k);
+    S += t.x;
+    Q += t.y;
+  }
+  const float inv_n = 1.0f / static_cast<float>(a.cpg * a.HW);
+  mean = S * inv_n;
+  rstd = rsqrtf(fmaxf(Q * inv_n - mean * mean, 0.f) + a.eps);
+}
+
+__global__ void __launch_bounds__(640) gn_bwd_reduce_kernel(const GroupNormBwdArgs a) {
+  extern __shared__ float gnb_smem[];  // [R][Cs][2]
+  __shared__ float s_mean[128], s_rstd[128];
+  const int b = blockIdx.x, slab = blockIdx.y;
+  const int Cs = a.Cs, cpg = a.cpg;
+  const int nv = Cs >> 3;
+  const int R = blockDim.x / nv;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int ng = Cs / cpg;
+  if (static_cast<int>(threadIdx.x) < ng) gn_group_stats(a, b, slab, threadIdx.x, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+  __syncthreads();
+  float gm[8], be[8], mu[8], rs[8];
+  load8f(a.gamma + slab * Cs + col * 8, gm);
+  load8f(a.beta + slab * Cs + col * 8, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (col * 8 + j) / cpg;
+    mu[j] = s_mean[g];
+    rs[j] = s_rstd[g];
+  }
+  const bf16_t* xb = a.x[slab] + static_cast<size_t>(b) * a.HW * a.x_ld[slab];
+  const bf16_t* dyb = a.dy + static_cast<size_t>(b) * a.HW * a.dy_ld + slab * Cs;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  if (rl < R) {
+    for (int p = rl; p < a.HW; p += R) {
+      float x[8], dy[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * a.x_ld[slab]) + col), x);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(p) * a.dy_ld) + col), dy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mu[j]) * rs[j];
+        float dz = dy[j];
+        if (a.silu) dz *= silu_grad_f(fmaf(xh, gm[j], be[j]));
+        sa[j] += dz;
+        sb[j] = fmaf(dz, xh, sb[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gnb_smem[(rl * Cs + col * 8 + j) * 2] = sa[j];
+      gnb_smem[(rl * Cs + col * 8 + j) * 2 + 1] = sb[j];
+    }
+  }
+  __syncthreads();
+  const int Ctot = gridDim.y * Cs;
+  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += gnb_smem[r * Cs * 2 + i];
+    a.ws[(static_cast<size_t>(b) * Ctot + slab * Cs) * 2 + i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(640) gn_bwd_apply_kernel(const GroupNormBwdArgs a, int nchunk) {
+  __shared__ float s_mean[128], s_rstd[128], s_c1[128], s_c2[128];
+  const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
+  const int Cs = a.Cs, cpg = a.cpg;
+  const int nv = Cs >> 3;
+  const int R = blockDim.x / nv;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int ng = Cs / cpg;
+  const int Ctot = gridDim.y * Cs;
+  if (static_cast<int>(threadIdx.x) < ng) {
+    const int g = threadIdx.x;
+    gn_group_stats(a, b, slab, g, s_mean[g], s_rstd[g]);
+    const float* w = a.ws + (static_cast<size_t>(b) * Ctot + slab * Cs + g * cpg) * 2;
+    float S1 = 0.f, S2 = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      const float gmm = __ldg(a.gamma + slab * Cs + g * cpg + c);
+      S1 = fmaf(gmm, w[2 * c], S1);
+      S2 = fmaf(gmm, w[2 * c + 1], S2);
+    }
+    const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
+    s_c1[g] = S1 * inv_n;
+    s_c2[g] = S2 * inv_n;
+  }
+  __syncthreads();
+  if (rl >= R) return;
+  float gm[8], be[8], mu[8], rs[8], c1[8], c2[8];
+  load8f(a.gamma + slab * Cs + col * 8, gm);
+  load8f(a.beta + slab * Cs + col * 8, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (col * 8 + j) / cpg;
+    mu[j] = s_mean[g];
+    rs[j] = s_rstd[g];
+    c1[j] = s_c1[g];
+    c2[j] = s_c2[g];
+  }
+  const int P = a.HW / nchunk;
+  const size_t row0 = static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * P;
+  const bf16_t* xb = a.x[slab] + row0 * a.x_ld[slab];
+  const bf16_t* dyb = a.dy + row0 * a.dy_ld + slab * Cs;
+  bf16_t* dxb = a.dx[slab] + row0 * a.dx_ld[slab];
+  const bf16_t* addb = a.add[slab] ? a.add[slab] + row0 * a.add_ld[slab] : nullptr;
+  const bool acc = a.accumulate[slab] != 0;
+  for (int p = rl; p < P; p += R) {
+    float x[8], dy[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * a.x_ld[slab]) + col), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(p) * a.dy_ld) + col), dy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mu[j]) * rs[j];
+      float dz = dy[j];
+      if (a.silu) dz *= silu_grad_f(fmaf(xh, gm[j], be[j]));
+      o[j] = rs[j] * (dz * gm[j] - c1[j] - xh * c2[j]);
+    }
+    if (addb) {
+      float t[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(addb + static_cast<size_t>(p) * a.add_ld[slab]) + col), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dxb + static_cast<size_t>(p) * a.dx_ld[slab]) + col;
+    if (acc) {
+      float t[8];
+      unpack8(*dst, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j];
+    }
+    *dst = pack8(o);
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int B,
+                                    int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    sa += ws[(static_cast<size_t>(b) * C + c) * 2];
+    sb += ws[(static_cast<size_t>(b) * C + c) * 2 + 1];
+  }
+  dbeta[c] += sa;
+  dgamma[c] += sb;
+}
+
+cudaError_t groupnorm_bwd_launch(const GroupNormBwdArgs& a, int B, int nslab, cudaStream_t s) {
+  const int nv = a.Cs / 8;
+  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || nslab < 1 || nslab > 2 || !a.ws)
+    return cudaErrorInvalidValue;
+  int R = GNB_R;
+  while (R > 1 && nv * R > 640) R >>= 1;
+  if (nv * R > 640 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(R) * a.Cs * 2 * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  gn_bwd_reduce_kernel<<<dim3(B, nslab), nv * R, smem, s>>>(a);
+  const int per = 4 * R;
+  const int nchunk = (a.HW >= 2 * per && a.HW % per == 0) ? a.HW / per : 1;
+  gn_bwd_apply_kernel<<<dim3(B, nslab, nchunk), nv * R, 0, s>>>(a, nchunk);
+  const int C = nslab * a.Cs;
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(a.ws, a.dgamma, a.dbeta, B, C);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// LayerNorm backward: one warp per token (looping), per-lane register accumulators for dgamma / dbeta
+// =====================================================================================================
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16_t* __restrict__ x, const bf16_t* __restrict__ dy,
+                                                            const float* __restrict__ gamma, const bf16_t* __restrict__ add,
+                                                            bf16_t* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, int C, float eps) {
+  extern __shared__ float lnb_smem[];  // [2][C]
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int nv = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) lnb_smem[i] = 0.f;
+  __syncthreads();
+  float gm[MAXV][8], ag[MAXV][8], ab[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) load8f(gamma + vi * 8, gm[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  }
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + warp_in_block; tok < M; tok += warps_total) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(tok) * C);
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(tok) * C);
+    float f[MAXV][8], d[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nv) {
+        unpack8(__ldg(xr + vi), f[i]);
+        unpack8(__ldg(dr + vi), d[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[i][j];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (lane + 32 * i < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = f[i][j] - mean;
+          var += t * t;
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (lane + 32 * i < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (f[i][j] - mean) * rstd;
+          f[i][j] = xh;
+          ab[i][j] += d[i][j];
+          ag[i][j] = fmaf(d[i][j], xh, ag[i][j]);
+          const float g = d[i][j] * gm[i][j];
+          d[i][j] = g;
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= static_cast<float>(C);
+    s2 /= static_cast<float>(C);
+    uint4* orow = reinterpret_cast<uint4*>(dx + static_cast<size_t>(tok) * C);
+    const uint4* arow = add ? reinterpret_cast<const uint4*>(add + static_cast<size_t>(tok) * C) : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nv) {
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = rstd * (d[i][j] - s1 - f[i][j] * s2);
+        if (arow) {
+          float t[8];
+          unpack8(__ldg(arow + vi), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] += t[j];
+        }
+        orow[vi] = pack8(o8);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&lnb_smem[vi * 8 + j], ag[i][j]);
+        atomicAdd(&lnb_smem[C + vi * 8 + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, lnb_smem[i]);
+    atomicAdd(dbeta + i, lnb_smem[C + i]);
+  }
+}
+
+cudaError_t layernorm_bwd_launch(const bf16_t* x, const bf16_t* dy, const float* gamma, const bf16_t* add, bf16_t* dx,
+                                 float* dgamma, float* dbeta, int M, int C, float eps, cudaStream_t s) {
+  if (C % 8 || C > 8 * 32 * 4) return cudaErrorInvalidValue;
+  int blocks = (M + 31) / 32;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  if (C <= 8 * 32 * 2)
+    layernorm_bwd_kernel<2><<<blocks, 256, smem, s>>>(x, dy, gamma, add, dx, dgamma, dbeta, M, C, eps);
+  else
+    layernorm_bwd_kernel<4><<<blocks, 256, smem, s>>>(x, dy, gamma, add, dx, dgamma, dbeta, M, C, eps);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// GEGLU forward / backward (exact erf GELU, unet.py:127-129)
+// =====================================================================================================
+__global__ void geglu_fwd_kernel(const bf16_t* __restrict__ p, bf16_t* __restrict__ out, size_t total, int hv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t m = idx / hv;
+  const int v = idx % hv;
+  const uint4* row = reinterpret_cast<const uint4*>(p) + m * 2 * hv;
+  float a[8], g[8], o[8];
+  unpack8(__ldg(row + v), a);
+  unpack8(__ldg(row + hv + v), g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_erf_f(g[j]);
+  reinterpret_cast<uint4*>(out)[idx] = pack8(o);
+}
+__global__ void geglu_bwd_kernel(const bf16_t* __restrict__ p, const bf16_t* __restrict__ dout, bf16_t* __restrict__ dp,
+                                 size_t total, int hv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t m = idx / hv;
+  const int v = idx % hv;
+  const uint4* row = reinterpret_cast<const uint4*>(p) + m * 2 * hv;
+  float a[8], g[8], d[8], da[8], dg[8];
+  unpack8(__ldg(row + v), a);
+  unpack8(__ldg(row + hv + v), g);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + idx), d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float cdf = 0.5f * (1.0f + erff(g[j] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+    da[j] = d[j] * g[j] * cdf;
+    dg[j] = d[j] * a[j] * (cdf + g[j] * pdf);
+  }
+  uint4* orow = reinterpret_cast<uint4*>(dp) + m * 2 * hv;
+  orow[v] = pack8(da);
+  orow[hv + v] = pack8(dg);
+}
+cudaError_t geglu_fwd_launch(const bf16_t* p, bf16_t* out, int M, int H, cudaStream_t s) {
+  if (H % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(M) * (H / 8);
+  geglu_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(p, out, total, H / 8);
+  return cudaGetLastError();
+}
+cudaError_t geglu_bwd_launch(const bf16_t* p, const bf16_t* dout, bf16_t* dp, int M, int H, cudaStream_t s) {
+  if (H % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(M) * (H / 8);
+  geglu_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(p, dout, dp, total, H / 8);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// SiLU forward / backward
+// =====================================================================================================
+__global__ void silu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t nv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  float f[8];
+  unpack8(__ldg(x + idx), f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+  y[idx] = pack8(f);
+}
+__global__ void silu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, size_t nv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nv) return;
+  float f[8], d[8];
+  unpack8(__ldg(x + idx), f);
+  unpack8(__ldg(dy + idx), d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] *= silu_grad_f(f[j]);
+  dx[idx] = pack8(d);
+}
+cudaError_t silu_fwd_launch(const bf16_t* x, bf16_t* y, size_t n, cudaStream_t s) {
+  if (n % 8) return cudaErrorInvalidValue;
+  silu_fwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                                              reinterpret_cast<uint4*>(y), n / 8);
+  return cudaGetLastError();
+}
+cudaError_t silu_bwd_launch(const bf16_t* x, const bf16_t* dy, bf16_t* dx, size_t n, cudaStream_t s) {
+  if (n % 8) return cudaErrorInvalidValue;
+  silu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), n / 8);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Short-context cross-attention backward: one CTA per (head, sample).  Phase 1: one thread per query recomputes its
+// softmax row, forms dS and writes dq; phase 2: threads own (key, channel) outputs and reduce dK / dV over the queries.
+// =====================================================================================================
+constexpr int ASB_DH = 80;
+constexpr int ASB_ROW = 88;  // padded bf16 row (176 B): conflict-free 16-byte row reads
+constexpr int ASB_T = 256;
+
+__global__ void __launch_bounds__(ASB_T) attn_small_bwd_kernel(const AttnSmallBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t asb_smem[];
+  bf16_t* sQ = reinterpret_cast<bf16_t*>(asb_smem);                 // [256][88]
+  bf16_t* sDO = sQ + ASB_T * ASB_ROW;                              // [256][88]
+  float* sP = reinterpret_cast<float*>(sDO + ASB_T * ASB_ROW);     // [256][16]
+  float* sDS = sP + ASB_T * 16;                                    // [256][16]
+  float* sK = sDS + ASB_T * 16;                                    // [16][80]
+  float* sV = sK + 16 * ASB_DH;                                    // [16][80]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int L = a.L;
+  const int t = threadIdx.x;
+  for (int i = t; i < 16 * ASB_DH; i += ASB_T) {
+    const int l = i / ASB_DH, d = i % ASB_DH;
+    float kv = 0.f, vv = 0.f;
+    if (l < L) {
+      kv = __bfloat162float(a.k[(static_cast<size_t>(b) * L + l) * a.kv_ld + h * ASB_DH + d]);
+      vv = __bfloat162float(a.v[(static_cast<size_t>(b) * L + l) * a.kv_ld + h * ASB_DH + d]);
+    }
+    sK[i] = kv;
+    sV[i] = vv;
+  }
+  // phase-2 ownership: output o = t + 256 * i  ->  (l, d) = (o / 80, o % 80), o < L * 80
+  float accK[5], accV[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) accK[i] = accV[i] = 0.f;
+
+  for (int q0 = 0; q0 < a.Sq; q0 += ASB_T) {
+    const int nq = min(ASB_T, a.Sq - q0);
+    __syncthreads();  // previous chunk's phase 2 is done with the staging buffers (and sK/sV are written)
+    // cooperative, coalesced staging of the Q and dO rows of this (sample, head)
+    for (int i = t; i < nq * (ASB_DH / 8); i += ASB_T) {
+      const int r = i / (ASB_DH / 8), vcol = i % (ASB_DH / 8);
+      const size_t tok = static_cast<size_t>(b) * a.Sq + q0 + r;
+      *reinterpret_cast<uint4*>(sQ + r * ASB_ROW + vcol * 8) =
+          __ldg(reinterpret_cast<const uint4*>(a.q + tok * a.q_ld + h * ASB_DH) + vcol);
+      *reinterpret_cast<uint4*>(sDO + r * ASB_ROW + vcol * 8) =
+          __ldg(reinterpret_cast<const uint4*>(a.dout + tok * a.do_ld + h * ASB_DH) + vcol);
+    }
+    __syncthreads();
+    if (t < nq) {
+      float sc[16], dp[16];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) sc[l] = dp[l] = 0.f;
+#pragma unroll 2
+      for (int vcol = 0; vcol < ASB_DH / 8; ++vcol) {
+        float qf[8], df[8];
+        unpack8(*reinterpret_cast<const uint4*>(sQ + t * ASB_ROW + vcol * 8), qf);
+        unpack8(*reinterpret_cast<const uint4*>(sDO + t * ASB_ROW + vcol * 8), df);
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+          if (l < L) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sc[l] = fmaf(qf[j], sK[l * ASB_DH + vcol * 8 + j], sc[l]);
+              dp[l] = fmaf(df[j], sV[l * ASB_DH + vcol * 8 + j], dp[l]);
+            }
+          }
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int l = 0; l < 16; ++l)
+        if (l < L) {
+          sc[l] *= a.scale;
+          mx = fmaxf(mx, sc[l]);
+        }
+      float den = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l)
+        if (l < L) {
+          sc[l] = __expf(sc[l] - mx);
+          den += sc[l];
+        }
+      const float inv = 1.0f / den;
+      float delta = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l)
+        if (l < L) {
+          sc[l] *= inv;
+          delta = fmaf(sc[l], dp[l], delta);
+        }
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const float p = (l < L) ? sc[l] : 0.f;
+        const float ds = (l < L) ? p * (dp[l] - delta) * a.scale : 0.f;  // scale folded in: dq = ds K, dk = ds^T q
+        sP[t * 16 + l] = p;
+        sDS[t * 16 + l] = ds;
+        dp[l] = ds;
+      }
+      // dq = dS K
+      bf16_t* dqr = a.dq + (static_cast<size_t>(b) * a.Sq + q0 + t) * a.dq_ld + h * ASB_DH;
+#pragma unroll 2
+      for (int vcol = 0; vcol < ASB_DH / 8; ++vcol) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int l = 0; l < 16; ++l)
+          if (l < L) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(dp[l], sK[l * ASB_DH + vcol * 8 + j], o[j]);
+          }
+        reinterpret_cast<uint4*>(dqr)[vcol] = pack8(o);
+      }
+    }
+    __syncthreads();
+    // phase 2
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int o = t + ASB_T * i;
+      if (o < L * ASB_DH) {
+        const int l = o / ASB_DH, d = o % ASB_DH;
+        float ak = accK[i], av = accV[i];
+        for (int r = 0; r < nq; ++r) {
+          ak = fmaf(sDS[r * 16 + l], __bfloat162float(sQ[r * ASB_ROW + d]), ak);
+          av = fmaf(sP[r * 16 + l], __bfloat162float(sDO[r * ASB_ROW + d]), av);
+        }
+        accK[i] = ak;
+        accV[i] = av;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int o = t + ASB_T * i;
+    if (o < L * ASB_DH) {
+      const int l = o / ASB_DH, d = o % ASB_DH;
+      const size_t off = (static_cast<size_t>(b) * L + l) * a.dkv_ld + h * ASB_DH + d;
+      a.dk[off] = __float2bfloat16(accK[i]);
+      a.dv[off] = __float2bfloat16(accV[i]);
+    }
+  }
+}
+
+cudaError_t attn_small_bwd_launch(const AttnSmallBwdArgs& a, int B, cudaStream_t s) {
+  if (a.L < 1 || a.L > 16 || a.Sq < 1) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(2) * ASB_T * ASB_ROW * 2 + static_cast<size_t>(2) * ASB_T * 16 * 4 +
+                      static_cast<size_t>(2) * 16 * ASB_DH * 4;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [smem] {
+    attr_err = cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  attn_small_bwd_kernel<<<dim3(a.heads, B), ASB_T, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// column sums
+// =====================================================================================================
+__global__ void __launch_bounds__(512) colsum_kernel(const bf16_t* __restrict__ dy, int ld, int N, int rows_total,
+                                                     int rows_per_group, float* __restrict__ total,
+                                                     bf16_t* __restrict__ per_group, int pg_ld, int R) {
+  extern __shared__ float cs_smem[];  // [R][N]
+  const int nv = N >> 3;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int g = blockIdx.x;
+  const int r0 = g * rows_per_group;
+  const int r1 = min(r0 + rows_per_group, rows_total);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < R) {
+    for (int r = r0 + rl; r < r1; r += R) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * ld) + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs_smem[rl * N + col * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += cs_smem[r * N + c];
+    if (per_group) per_group[static_cast<size_t>(g) * pg_ld + c] = __float2bfloat16(t);
+    if (total) atomicAdd(total + c, t);
+  }
+}
+cudaError_t colsum_launch(const bf16_t* dy, int ld, int N, int groups, int rows_per_group, float* total, bf16_t* per_group,
+                          int pg_ld, cudaStream_t s) {
+  if (N % 8 || N / 8 > 512 || groups < 1) return cudaErrorInvalidValue;
+  const int nv = N / 8;
+  int R = 512 / nv;
+  if (R < 1) R = 1;
+  while (R > 1 && static_cast<size_t>(R) * N * 4 > 40 * 1024) --R;
+  if (static_cast<size_t>(R) * N * 4 > 48 * 1024) return cudaErrorInvalidValue;
+  if (R > rows_per_group) R = rows_per_group;
+  int threads = nv * R;
+  threads = (threads + 31) / 32 * 32;
+  colsum_kernel<<<groups, threads, static_cast<size_t>(R) * N * 4, s>>>(dy, ld, N, groups * rows_per_group, rows_per_group,
+                                                                        total, per_group, pg_ld, R);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// resampling
+// =====================================================================================================
+__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, uint4* __restrict__ dx, int B, int H, int W, int nv,
+                                      int accumulate) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * W * nv;
+  if (idx >= total) return;
+  const int v = idx % nv;
+  size_t p = idx / nv;
+  const int x = p % W;
+  p /= W;
+  const int y = p % H;
+  const int b = p / H;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dxx = 0; dxx < 2; ++dxx) {
+      float f[8];
+      unpack8(__ldg(dup + ((static_cast<size_t>(b) * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dxx) * nv + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += f[j];
+    }
+  if (accumulate) {
+    float f[8];
+    unpack8(dx[idx], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += f[j];
+  }
+  dx[idx] = pack8(o);
+}
+cudaError_t upsample2x_bwd_launch(const bf16_t* dup, bf16_t* dx, int B, int H, int W, int C, int accumulate, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(dup), reinterpret_cast<uint4*>(dx), B, H, W, C / 8, accumulate);
+  return cudaGetLastError();
+}
+
+__global__ void dilate2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nv) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * nv;
+  if (idx >= total) return;
+  const int v = idx % nv;
+  size_t p = idx / nv;
+  const int ox = p % (2 * W);
+  p /= (2 * W);
+  const int oy = p % (2 * H);
+  const int b = p / (2 * H);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (!(ox & 1) && !(oy & 1)) r = __ldg(x + ((static_cast<size_t>(b) * H + (oy >> 1)) * W + (ox >> 1)) * nv + v);
+  out[idx] = r;
+}
+cudaError_t dilate2x_launch(const bf16_t* x, bf16_t* out, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
+  dilate2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                                              reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// layout / dtype glue
+// =====================================================================================================
+__global__ void nchw4_to_tok64_kernel(const float* __restrict__ g, bf16_t* __restrict__ out, int B, int HW) {
+  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= static_cast<size_t>(B) * HW) return;
+  const size_t b = m / HW, pix = m % HW;
+  float f[8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) f[o] = __ldg(g + (b * 4 + o) * HW + pix);
+#pragma unroll
+  for (int o = 4; o < 8; ++o) f[o] = 0.f;
+  *reinterpret_cast<uint4*>(out + m * 64) = pack8(f);
+}
+cudaError_t nchw4_to_tok64_launch(const float* g, bf16_t* out, int B, int HW, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(B) * HW;
+  nchw4_to_tok64_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(g, out, B, HW);
+  return cudaGetLastError();
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16_t* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(x[i]);
+}
+cudaError_t f32_to_bf16_launch(const float* x, bf16_t* out, size_t n, cudaStream_t s) {
+  f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, out, n);
+  return cudaGetLastError();
+}
+
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, size_t nv,
+                                int accumulate) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  float o[8];
+  unpack8(__ldg(a + i), o);
+  if (b) {
+    float f[8];
+    unpack8(__ldg(b + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += f[j];
+  }
+  if (accumulate) {
+    float f[8];
+    unpack8(y[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += f[j];
+  }
+  y[i] = pack8(o);
+}
+cudaError_t add_bf16_launch(const bf16_t* a, const bf16_t* b, bf16_t* y, size_t n, int accumulate, cudaStream_t s) {
+  if (n % 8) return cudaErrorInvalidValue;
+  add_bf16_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(y), n / 8, accumulate);
+  return cudaGetLastError();
+}
+
+__global__ void scatter_add_rows_kernel(const bf16_t* __restrict__ rows, int ld, const void* __restrict__ idx, int idx_i64,
+                                        float* __restrict__ table, int nrows, int D, int table_rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(nrows) * D) return;
+  const int r = i / D, d = i % D;
+  const long long t = idx_i64 ? static_cast<const long long*>(idx)[r] : static_cast<const int*>(idx)[r];
+  if (t < 0 || t >= table_rows) __trap();
+  atomicAdd(table + t * D + d, __bfloat162float(rows[static_cast<size_t>(r) * ld + d]));
+}
+cudaError_t scatter_add_rows_launch(const bf16_t* rows, int ld, const void* idx, int idx_i64, float* table, int nrows, int D,
+                                    int table_rows, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(nrows) * D;
+  scatter_add_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(rows, ld, idx, idx_i64, table, nrows, D,
+                                                                                      table_rows);
+  return cudaGetLastError();
+}
+
+__global__ void conv_in_wgrad_fold_kernel(const float* __restrict__ g, float* __restrict__ dW, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 36) return;
+  const int n = i / 36, j = i % 36;
+  dW[i] += g[n * 128 + j] + g[n * 128 + 36 + j];
+}
+cudaError_t conv_in_wgrad_fold_launch(const float* g, float* dW, int N, cudaStream_t s) {
+  conv_in_wgrad_fold_kernel<<<(N * 36 + 255) / 256, 256, 0, s>>>(g, dW, N);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Word_Attention backward (fp32): ctx = softmax(q k^T) v, unscaled.  One CTA per sample, L <= 16.
+// =====================================================================================================
+__global__ void __launch_bounds__(512) word_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ v, const bf16_t* __restrict__ dctx,
+                                                            bf16_t* __restrict__ d_qkv, int L, int D, int Ltot, int row_off) {
+  __shared__ float sP[16][16], sDS[16][16];
+  const int b = blockIdx.x;
+  const float* qb = q + static_cast<size_t>(b) * L * D;
+  const float* kb = k + static_cast<size_t>(b) * L * D;
+  const float* vb = v + static_cast<size_t>(b) * L * D;
+  const bf16_t* db = dctx + (static_cast<size_t>(b) * Ltot + row_off) * D;
+  // scores and dP, one thread per (i, j)
+  for (int ij = threadIdx.x; ij < L * L; ij += blockDim.x) {
+    const int i = ij / L, j = ij % L;
+    float sdot = 0.f, pdot = 0.f;
+    for (int d = 0; d < D; ++d) {
+      sdot = fmaf(qb[i * D + d], kb[j * D + d], sdot);
+      pdot = fmaf(__bfloat162float(db[static_cast<size_t>(i) * D + d]), vb[j * D + d], pdot);
+    }
+    sP[i][j] = sdot;
+    sDS[i][j] = pdot;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < L) {
+    const int i = threadIdx.x;
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) mx = fmaxf(mx, sP[i][j]);
+    float den = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float e = expf(sP[i][j] - mx);
+      sP[i][j] = e;
+      den += e;
+    }
+    const float inv = 1.0f / den;
+    float delta = 0.f;
+    for (int j = 0; j < L; ++j) {
+      sP[i][j] *= inv;
+      delta = fmaf(sP[i][j], sDS[i][j], delta);
+    }
+    for (int j = 0; j < L; ++j) sDS[i][j] = sP[i][j] * (sDS[i][j] - delta);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int i = 0; i < L; ++i) {
+      float dq = 0.f, dk = 0.f, dv = 0.f;
+      for (int j = 0; j < L; ++j) {
+        dq = fmaf(sDS[i][j], kb[j * D + d], dq);
+        dk = fmaf(sDS[j][i], qb[j * D + d], dk);
+        dv = fmaf(sP[j][i], __bfloat162float(db[static_cast<size_t>(j) * D + d]), dv);
+      }
+      bf16_t* o = d_qkv + (static_cast<size_t>(b) * L + i) * 3 * D + d;
+      o[0] = __float2bfloat16(dq);
+      o[D] = __float2bfloat16(dk);
+      o[2 * D] = __float2bfloat16(dv);
+    }
+  }
+}
+cudaError_t word_attn_bwd_launch(const float* q, const float* k, const float* v, const bf16_t* dctx, bf16_t* d_qkv, int B,
+                                 int L, int D, int Ltot, int row_off, cudaStream_t s) {
+  if (L < 1 || L > 16) return cudaErrorInvalidValue;
+  int threads = D < 512 ? (D + 31) / 32 * 32 : 512;
+  if (threads < L * L) threads = (L * L + 31) / 32 * 32;
+  word_attn_bwd_kernel<<<B, threads, 0, s>>>(q, k, v, dctx, d_qkv, L, D, Ltot, row_off);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// transposed weight packs
+// =====================================================================================================
+__global__ void repack_linear_T_kernel(const float* __restrict__ w, bf16_t* __restrict__ dst, int N, int K, int ldn, int n_off,
+                                       int k_row_off) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(N) * K) return;
+  // consecutive threads walk n (coalesced writes; reads hit L2)
+  const int n = idx % N, k = idx / N;
+  dst[static_cast<size_t>(k_row_off + k) * ldn + n_off + n] = __float2bfloat16(w[static_cast<size_t>(n) * K + k]);
+}
+cudaError_t repack_linear_T_launch(const float* w, bf16_t* dst, int N, int K, int ldn, int n_off, int k_row_off, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * K;
+  repack_linear_T_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, N, K, ldn, n_off, k_row_off);
+  return cudaGetLastError();
+}
+
+__global__ void repack_conv3x3_T_kernel(const float* __restrict__ w, bf16_t* __restrict__ dst, int Cout, int Cin, int cout_pad) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(Cout) * Cin * 9;
+  if (idx >= total) return;
+  const int n = idx % Cout;
+  const int tap = (idx / Cout) % 9;
+  const int c = idx / (static_cast<size_t>(Cout) * 9);
+  dst[static_cast<size_t>(c) * 9 * cout_pad + (8 - tap) * cout_pad + n] =
+      __float2bfloat16(w[(static_cast<size_t>(n) * Cin + c) * 9 + tap]);
+}
+cudaError_t repack_conv3x3_T_launch(const float* w, bf16_t* dst, int Cout, int Cin, int cout_pad, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * 9;
+  repack_conv3x3_T_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, cout_pad);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// AdamW + EMA
+// =====================================================================================================
+__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ ema, size_t n, float lr, float beta1, float beta2,
+                                 float eps, float weight_decay, float bc1, float bc2_sqrt, float ema_beta, int ema_mode,
+                                 float grad_scale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gr = g[i] * grad_scale;
+  float pv = p[i];
+  pv *= (1.0f - lr * weight_decay);
+  const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+  const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pv -= (lr / bc1) * (mi / denom);
+  p[i] = pv;
+  if (ema_mode == 1) ema[i] = pv;
+  else if (ema_mode == 2) ema[i] = ema[i] * ema_beta + (1.0f - ema_beta) * pv;
+}
+cudaError_t adamw_ema_launch(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, float ema_beta, int ema_mode,
+                             float grad_scale, cudaStream_t s) {
+  if (step < 1) return cudaErrorInvalidValue;
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adamw_ema_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps,
+                                                                          weight_decay, bc1, sqrtf(bc2), ema_beta, ema_mode,
+                                                                          grad_scale);
+  return cudaGetLastError();
+}
+
+}  // namespace wd
