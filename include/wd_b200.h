@@ -163,6 +163,9 @@ int wd_trainer_forward(wd_trainer* t, int batch, const float* x, const int64_t* 
  * 2 (eps - noise) / numel).  y / ctx_tokens: the same index tensors as in the forward call (embedding gradients). */
 int wd_trainer_backward(wd_trainer* t, const float* d_eps, const int64_t* y, const int64_t* ctx_tokens, void* stream);
 int wd_trainer_launch_counts(const wd_trainer* t, int* fwd, int* bwd);
+/* test hook: copies a named intermediate of the last forward ("temb", "h1p", "h1", "embp", "emb_act" bf16 [B,*];
+ * "emb_out" fp32 [B, 8*320]; "ctx", "kv_all" bf16) into dst (device); `bytes` must match. */
+int wd_trainer_read_tensor(const wd_trainer* t, const char* name, void* dst, size_t bytes, void* stream);
 size_t wd_trainer_workspace_bytes(const wd_trainer* t);
 size_t wd_trainer_weight_bytes(const wd_trainer* t);
 /* torch.optim.AdamW step (train.py:405, lr 1e-4, default betas / eps / weight_decay) fused with the EMA update of

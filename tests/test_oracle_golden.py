@@ -119,3 +119,52 @@ def test_timestep_embedding_and_pe():
     pe = UO.positional_encoding(10, 320)
     assert pe[0, 0] == 0 and pe[0, 1] == 1
     assert math.isclose(float(pe[3, 5]), math.cos(3 / 10000 ** (5 / 320)), rel_tol=1e-6)  # odd index in the exponent
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training step (train.py:281-294): oracle autograd / AdamW / EMA vs the UNMODIFIED reference model + torch.optim.AdamW
+# ---------------------------------------------------------------------------------------------------------------
+def test_train_step_oracle_matches_reference(golden_dir, unet_sd):
+    import train_oracle as TO
+    g = np.load(os.path.join(golden_dir, "unet_train.npz"))
+    inp = W.make_inputs(2, seed=SEED)
+    noise = torch.from_numpy(g["noise"])
+    loss, _, grads = TO.unet_loss_and_grads(unet_sd, inp["x"], inp["t"], inp["context"], inp["y"], noise)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    names = list(unet_sd.keys())
+    n_none = 0
+    for i, n in enumerate(names):
+        if g["grad_norm"][i] < 0:
+            assert grads[n] is None, f"{n}: the reference gives no gradient"
+            n_none += 1
+            continue
+        a, b = TO.signature(grads[n], 77 + i)
+        assert abs(a - g["grad_norm"][i]) <= 2e-4 * g["grad_norm"][i] + 1e-9, n
+        assert abs(b - g["grad_proj"][i]) <= 2e-4 * g["grad_norm"][i] + 1e-9, n
+    assert n_none == 58  # parameters the reference forward never reads
+    for key in g.files:
+        if key.startswith("grad::"):
+            assert _relerr(grads[key[6:]], g[key]) < 2e-4, key
+    # AdamW step 1 (lr 1e-4, torch defaults) on those gradients
+    for i, n in enumerate(names):
+        p = unet_sd[n].clone()
+        if grads[n] is None:
+            assert g["upd_norm"][i] == 0.0  # torch skips parameters without grad (no weight decay either)
+            continue
+        if g["grad_norm"][i] < 1e-6:
+            continue  # a gradient that is pure rounding noise (e.g. the key bias under a softmax): sign(g) is arbitrary
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        TO.adamw_update(p, grads[n], m, v, 1)
+        a, b = TO.signature(p - unet_sd[n], 977 + i)
+        # the first Adam step is -lr * sign(g) (+ decay): elements whose gradient is ~0 may flip; compare norms loosely
+        assert abs(a - g["upd_norm"][i]) <= 2e-2 * g["upd_norm"][i] + 1e-9, n
+
+
+def test_ema_oracle_semantics():
+    import train_oracle as TO
+    p = torch.tensor([1.0, 2.0])
+    ema = torch.zeros(2)
+    TO.ema_update(ema, p, 0)            # warm-up: EMA.reset_parameters copies (train.py:162-165)
+    assert torch.equal(ema, p)
+    TO.ema_update(ema, p * 3, 2000)     # afterwards: old * beta + (1 - beta) * new (train.py:156-159)
+    assert torch.allclose(ema, p * 0.995 + 0.005 * p * 3)

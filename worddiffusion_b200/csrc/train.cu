@@ -147,6 +147,7 @@ struct TPlan {
   std::deque<TT> tensors;
   size_t bytes = 0;
   std::vector<std::pair<void*, size_t>> zero_on_bwd;  // scratch that must be zero when the backward pass starts
+  std::map<std::string, std::pair<const void*, size_t>> named;  // intermediates readable through wd_trainer_read_tensor (tests)
 };
 
 }  // namespace
@@ -441,7 +442,7 @@ struct TBuilder {
     for (const TRes& r : e->res) {
       job(PK_LIN, r.emb_w, e->emb_all_w, r.Cout, ted, ted, 0, r.emb_off);
       job(PK_LIN_T, r.emb_w, e->emb_all_wt, r.Cout, ted, emb_cols, r.emb_off, 0);
-      job(PK_VEC, r.emb_b, e->emb_all_b, r.Cout, 0, r.emb_off, 0, 0);
+      job(PK_VEC, r.emb_b, e->emb_all_b, r.Cout, 0, 0, r.emb_off, 0);
     }
     // fused context K/V projection of every cross-attention
     const int inner = e->st.empty() ? 0 : e->st[0].heads * e->st[0].dh;
@@ -1184,6 +1185,17 @@ struct TPlanBuilder {
       return true;
     });
     const int emb_ld = e->emb_cols;
+    if (!dry) {
+      plan->named["temb"] = {temb, static_cast<size_t>(B) * mc * 2};
+      plan->named["h1p"] = {h1p, static_cast<size_t>(B) * ted * 2};
+      plan->named["h1"] = {h1, static_cast<size_t>(B) * ted * 2};
+      plan->named["embp"] = {embp, static_cast<size_t>(B) * ted * 2};
+      plan->named["emb_act"] = {emb_act, static_cast<size_t>(B) * ted * 2};
+      plan->named["emb_out"] = {emb_out, static_cast<size_t>(B) * e->emb_cols * 4};
+      plan->named["ctx"] = {ctx, static_cast<size_t>(B) * L * D * 2};
+      plan->named["kv_all"] = {kv_all, static_cast<size_t>(B) * L * e->kv_cols * 2};
+      plan->named["d_emb_out"] = {d_emb_out, static_cast<size_t>(B) * e->emb_cols * 2};
+    }
 
     // ================= UNet body =================
     std::vector<TT*> hs;
@@ -1579,6 +1591,14 @@ extern "C" int wd_trainer_launch_counts(const wd_trainer* e, int* fwd, int* bwd)
   if (!e || !e->cur) return tfail(WD_ERR_STATE, "no plan");
   if (fwd) *fwd = static_cast<int>(e->cur->fwd.size());
   if (bwd) *bwd = static_cast<int>(e->cur->bwd.size());
+  return WD_OK;
+}
+extern "C" int wd_trainer_read_tensor(const wd_trainer* e, const char* name, void* dst, size_t bytes, void* stream) {
+  if (!e || !e->cur || !name || !dst) return tfail(WD_ERR_STATE, "no plan / null argument");
+  auto it = e->cur->named.find(name);
+  if (it == e->cur->named.end()) return tfail(WD_ERR_INVALID, "unknown tensor '%s'", name);
+  if (bytes != it->second.second) return tfail(WD_ERR_INVALID, "tensor '%s' holds %zu bytes, not %zu", name, it->second.second, bytes);
+  T_CUDA_TRY(cudaMemcpyAsync(dst, it->second.first, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 extern "C" size_t wd_trainer_workspace_bytes(const wd_trainer* e) { return e ? e->acap : 0; }

@@ -51,6 +51,9 @@ class HotPathEngine:
         self._weights_sig = None
         self._ctx_key = None
 
+    def __deepcopy__(self, memo):
+        return None  # copy.deepcopy(model) (train.py:410, the EMA model) gets its own engine lazily
+
     def __del__(self):
         try:
             if getattr(self, "_h", None) and self._h.value:

@@ -68,6 +68,9 @@ class TrainEngine:
         self.grad_views = {}
         self._hold = None
 
+    def __deepcopy__(self, memo):
+        return None  # copy.deepcopy(model) (train.py:410, the EMA model) gets its own engine lazily
+
     def __del__(self):
         try:
             if getattr(self, "_h", None) and self._h.value:
@@ -190,6 +193,25 @@ def unet_train_forward(module, x, timesteps, context, y):
     return _UNetTrainFn.apply(module, x, timesteps, context, y, *params)
 
 
+def allreduce_sum_(flat, group=None):
+    """Data-parallel gradient exchange (train.py --ddp): in-place SUM all-reduce of the flat gradient buffer.
+    Returns the world size (the optimizer kernel divides by it: DDP's gradient averaging)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    ws = dist.get_world_size(group)
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return ws
+
+
+def shard_batch(n, rank, world):
+    """Contiguous slice [lo, hi) of a global batch of n samples owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class FusedTrainStep:
     """Noise-prediction step with flat parameter storage and a fused AdamW + EMA update (train.py:281-294,140-170,405).
 
@@ -228,16 +250,13 @@ class FusedTrainStep:
         return 1
 
     def step(self, x_t, timesteps, context, y, noise):
-        import torch.distributed as dist
         eng = self.eng
         eps = eng.forward(x_t, timesteps, y, context)
         diff = eps - noise
         loss = (diff * diff).mean()                   # nn.MSELoss (train.py:287)
         d_eps = diff * (2.0 / diff.numel())
         eng.backward(d_eps)
-        ws = self.world_size()
-        if ws > 1:
-            dist.all_reduce(eng.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        ws = allreduce_sum_(eng.flat_grad, self.pg)
         self.t += 1
         # EMA.step_ema (train.py:161-167): copy during the warm-up, moving average afterwards
         ema_mode = 0 if self.ema is None else (1 if self.t <= self.step_start_ema else 2)
@@ -247,6 +266,7 @@ class FusedTrainStep:
                                           self.eps, self.weight_decay, self.t, self.ema_beta, ema_mode, 1.0 / ws,
                                           _stream_ptr()), "wd_adamw_ema_step")
         eng.sync_weights(force=True)
+        self.module._engine_sig = None  # the inference engine re-packs on its next call (the kernel wrote the parameters)
         return loss
 
     def ema_state_dict(self):

@@ -1,5 +1,6 @@
 """Drop-in for the reference ``unet.UNetModel`` (reference unet.py:1096-1836): same constructor, same ``forward``
 signature, same ``state_dict`` keys (264), B200 engine underneath."""
+import torch
 import torch.nn as nn
 
 from ._lib import VARIANT_UNET
@@ -44,4 +45,10 @@ class UNetModel(UNetBase):
                 charContextImages=None, original_context=None, or_images=None, mix_rate=None, **kwargs):
         if self.num_classes is not None:
             assert y.shape == (x.shape[0],)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # train.py:285: the noise-prediction step; gradients come from the hand-written backward (training.py)
+            from .training import unet_train_forward
+            if context is None:
+                raise NotImplementedError("worddiffusion_b200 needs the character context (context=None is not implemented)")
+            return unet_train_forward(self, x, timesteps, context, y).type(x.dtype)
         return self._run(x, timesteps, context, y, None)

@@ -72,6 +72,7 @@ class UNetBase(nn.Module):
             raise NotImplementedError("worddiffusion_b200 does not implement args.interpolation (random style mixing)")
         self._engine = None
         self._engine_sig = None
+        self._train_engine = None
 
     def _build_tree(self, extra_before_blocks=None):
         mc = self.model_channels
@@ -117,6 +118,17 @@ class UNetBase(nn.Module):
             self._engine.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
             self._engine_sig = sig
         return self._engine
+
+    def train_engine(self, device=None):
+        """The B200 training engine (forward + hand-written backward) bound to this module's parameters."""
+        from .training import TrainEngine
+        p0 = next(self.parameters())
+        device = torch.device(device) if device is not None else p0.device
+        if device.type != "cuda":
+            raise _lib.WdError("worddiffusion_b200 has no CPU path: move the model and its inputs to a CUDA (B200) device")
+        if self._train_engine is None or self._train_engine.device != device:
+            self._train_engine = TrainEngine(self, device)
+        return self._train_engine
 
     def _run(self, x, timesteps, context, y, phosc):
         if context is None:
