@@ -178,3 +178,16 @@ def test_fused_train_step_reduces_loss_and_tracks_ema():
     with torch.no_grad():
         e = m(x, None, timesteps=t, context=c, y=y)
     assert float(torch.nn.functional.mse_loss(noise, e)) < losses[0]
+
+
+def test_data_parallel_training_two_gpus():
+    """N = 2 ranks over NCCL (skipped on a single-GPU box): tools/ddp_check.py."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "ddp_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "DDP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

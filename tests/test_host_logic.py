@@ -110,3 +110,62 @@ def test_all_gather_latents_world2_gloo(n_total):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training, host side (train.py --ddp): batch sharding and the gradient exchange, world_size 2 over gloo
+# ---------------------------------------------------------------------------------------------------------------
+def test_train_shard_batch_partitions_the_global_batch():
+    from worddiffusion_b200.training import shard_batch
+    for n, world in [(224, 8), (224, 1), (10, 4), (7, 2), (3, 8)]:
+        spans = [shard_batch(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    assert shard_batch(224, 3, 8) == (84, 112)  # BASELINE config 4: 28 latents per GPU
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from worddiffusion_b200.training import allreduce_sum_
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.full((1000,), float(rank + 1))
+    ws = allreduce_sum_(flat)
+    q.put((rank, ws, bool(torch.equal(flat, torch.full((1000,), 3.0)))))
+    dist.destroy_process_group()
+
+
+def test_train_gradient_allreduce_world2_gloo():
+    """Gradient exchange of the training step: in-place SUM of the flat gradient buffer; the optimizer kernel divides by the
+    returned world size (DDP averaging)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, 2, True), (1, 2, True)]
+
+
+def test_train_allreduce_is_identity_without_process_group():
+    from worddiffusion_b200.training import allreduce_sum_
+    flat = torch.ones(10)
+    assert allreduce_sum_(flat) == 1 and torch.equal(flat, torch.ones(10))
+
+
+def test_training_module_refuses_cpu():
+    """No CPU fallback on the training path either."""
+    from worddiffusion_b200 import _lib
+    from worddiffusion_b200.unet import UNetModel, default_args
+    m = UNetModel(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+                  attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_classes=339, context_dim=320,
+                  vocab_size=53, max_seq_len=10, args=default_args("cpu"))
+    m.train()
+    x = torch.zeros(1, 4, 8, 32)
+    with pytest.raises(_lib.WdError):
+        m(x, None, timesteps=torch.tensor([5]), context=torch.ones(1, 10, dtype=torch.long), y=torch.tensor([1]))

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -1437,10 +1438,49 @@ int ensure_tplan(wd_trainer* e, int B, int L, TPlan** out) {
   return WD_OK;
 }
 
-int run_tops(const std::vector<TOp>& ops, const TRun& r, cudaStream_t s) {
+// env WD_TRAIN_PROF=1 (tools/train_bench.py): CUDA events around every launch, per-kernel-name totals printed to stderr
+bool train_prof_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TRAIN_PROF");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+int run_tops(const std::vector<TOp>& ops, const TRun& r, cudaStream_t s, const char* phase) {
+  const bool prof = train_prof_enabled();
+  std::vector<cudaEvent_t> ev;
+  if (prof) {
+    ev.resize(ops.size() + 1);
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], s);
+  }
+  size_t i = 0;
   for (const TOp& op : ops) {
     const cudaError_t err = op.fn(r, s);
     if (err != cudaSuccess) return tfail(WD_ERR_CUDA, "launch of '%s' failed: %s", op.what, cudaGetErrorString(err));
+    if (prof) cudaEventRecord(ev[i + 1], s);
+    ++i;
+  }
+  if (prof) {
+    cudaStreamSynchronize(s);
+    std::map<std::string, std::pair<double, int>> agg;
+    double total = 0;
+    for (size_t k = 0; k < ops.size(); ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+      auto& a = agg[ops[k].what];
+      a.first += ms;
+      a.second += 1;
+      total += ms;
+    }
+    fprintf(stderr, "[wd_train_prof] %s: %zu launches, %.3f ms\n", phase, ops.size(), total);
+    std::vector<std::pair<double, std::string>> order;
+    for (auto& kv : agg) order.push_back({kv.second.first, kv.first});
+    std::sort(order.rbegin(), order.rend());
+    for (auto& o : order)
+      fprintf(stderr, "[wd_train_prof]   %-24s x%-3d %8.3f ms  %5.1f%%\n", o.second.c_str(), agg[o.second].second, o.first, 100.0 * o.first / total);
+    for (auto& x : ev) cudaEventDestroy(x);
   }
   return WD_OK;
 }
@@ -1567,7 +1607,7 @@ extern "C" int wd_trainer_forward(wd_trainer* e, int batch, const float* x, cons
   r.y = reinterpret_cast<const long long*>(y);
   r.ctx = reinterpret_cast<const long long*>(ctx_tokens);
   r.eps_out = eps_out;
-  rc = run_tops(p->fwd, r, static_cast<cudaStream_t>(stream));
+  rc = run_tops(p->fwd, r, static_cast<cudaStream_t>(stream), "forward");
   if (rc) return rc;
   e->fwd_done = true;
   return WD_OK;
@@ -1582,7 +1622,7 @@ extern "C" int wd_trainer_backward(wd_trainer* e, const float* d_eps, const int6
   r.d_eps = d_eps;
   r.y = reinterpret_cast<const long long*>(y);
   r.ctx = reinterpret_cast<const long long*>(ctx_tokens);
-  const int rc = run_tops(e->cur->bwd, r, s);
+  const int rc = run_tops(e->cur->bwd, r, s, "backward");
   e->fwd_done = false;
   return rc;
 }
