@@ -34,6 +34,17 @@ MODEL_KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_cha
                 vocab_size=53, max_seq_len=10)
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by tools/summarize_ncu.py numbers of profiles/r01q_ncu_gemm_step_window.txt)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -144,6 +155,56 @@ def run_reference(args):
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(out), flush=True)
+
+
+def train_leg(args, world, rank, dev):
+    """BASELINE.json configs[3]: noise-prediction training step (train.py:281-294), global batch 224 sharded over the ranks
+    (strong scaling: 28 latents per GPU on 8 GPUs), forward + backward + NCCL gradient all-reduce + fused AdamW + EMA."""
+    import torch
+    import torch.distributed as dist
+    import weights as W
+    from worddiffusion_b200.diffusion import Diffusion
+    from worddiffusion_b200.training import FusedTrainStep, shard_batch
+    from worddiffusion_b200.unet import UNetModel, default_args
+    gb = args.train_batch
+    lo, hi = shard_batch(gb, rank, world)
+    m = UNetModel(args=default_args(dev), **MODEL_KW)
+    m.load_state_dict(W.make_state_dict(W.load_spec("unet"), 1234), strict=True)
+    m = m.to(dev).train()
+    step = FusedTrainStep(m, lr=1e-4)
+    diff = Diffusion(device=dev)
+    inp = W.make_inputs(gb, seed=4321)
+    lat = (torch.randn((gb, 4, 8, 32), generator=torch.Generator().manual_seed(99)) * 0.18215)[lo:hi].to(dev)
+    ctx, y = inp["context"][lo:hi].to(dev), inp["y"][lo:hi].to(dev)
+
+    def one():
+        t = diff.sample_timesteps(hi - lo).to(dev)
+        x_t, noise = diff.noise_images(lat, t)
+        return step.step(x_t, t, ctx, y, noise)
+
+    first = float(one())
+    for _ in range(3):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    f, b = step.eng.launch_counts
+    return {"metric": "train_latents_per_sec", "value": gb / (ms * 1e-3), "unit": "latents/s", "ms_per_step": ms,
+            "global_batch": gb, "batch_per_gpu": hi - lo, "scaling": "strong", "steps": args.train_steps,
+            "model_tflops": round(3 * (9.153 + 0.039) * 1e9 * gb / (ms * 1e-3) / 1e12, 1),
+            "gpu_launches_per_step": f + b + 1, "loss_first": first, "loss_last": float(loss),
+            "workload": "unet.UNetModel noise-prediction training step: forward + backward + gradient all-reduce + AdamW + EMA "
+                        "(bf16 tensor-core operands, fp32 master weights / accumulation)"}
 
 
 def run_ours(args):
@@ -293,8 +354,16 @@ def run_ours(args):
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                 "flops_per_launch_avg": cls_f[g] / cls_n[g], "launches_per_step": cls_n[g],
                 "avg_launch_ms": round(cls_t[g] / cls_n[g], 5), "share_of_step": kernels[g]["share"], "traffic": None}
+    tr = load_traffic()
+    if tr and variant == "unet" and B == tr.get("batch"):
+        roofline["traffic"] = tr["gemm_tc_kernel"]["dram_bytes_per_launch"]
+        roofline["traffic_source"] = tr["gemm_tc_kernel"]["source"]
+        roofline["algorithmic_bytes_per_launch_avg"] = cls_b[g] / cls_n[g]
     step_tf = B * GFLOP_PER_LATENT[variant] * 1e9 / (ms / K * 1e-3) / 1e12
 
+    train = None
+    if args.train_steps > 0 and variant == "unet":
+        train = train_leg(args, world, rank, dev)
     cb = cpu_oracle_throughput(variant, seconds=args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -308,6 +377,8 @@ def run_ours(args):
            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
     if cb is not None:
         out["cpu_baseline"] = cb
+    if train is not None:
+        out["train_step"] = train
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -323,6 +394,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ops-out", default=None, help="write the per-launch device times of one step (JSON) to this path")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the training leg (0: skip it)")
+    ap.add_argument("--train-batch", type=int, default=224, help="GLOBAL batch of the training leg (BASELINE config 4)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -36,9 +36,10 @@ WD_DEVINL float silu_grad_f(float z) {
 // GroupNorm (+SiLU) backward.  With g = dz * gamma (dz = dy * act'(z)), n = cpg * HW elements per (sample, group):
 //   dx = rstd * (g - mean_n(g) - xhat * mean_n(g * xhat)),   dgamma_c = sum dz * xhat,   dbeta_c = sum dz
 // Pass 1 reduces {sum dz, sum dz*xhat} per (sample, channel) into `ws` (no atomics); the group means are gamma-weighted
-// sums of those, formed in the preamble of pass 2.  Pass 3 folds ws over the batch into dgamma / dbeta.
+// sums of those, formed in the preamble of pass 2, whose first pixel chunk also adds its sample's share to dgamma / dbeta.
 // =====================================================================================================
 constexpr int GNB_R = 16;
+constexpr int GNB_MAX_RCHUNKS = 4;  // row chunks of the reduce pass (workspace = B * 4 * C * 2 floats)
 
 // mean / rstd of the groups of one slab from the forward partial statistics (same fold order as groupnorm_apply_kernel)
 WD_DEVINL void gn_group_stats(const GroupNormBwdArgs& a, int b, int slab, int g, float& mean, float& rstd) {
@@ -59,10 +60,10 @@ WD_DEVINL void gn_group_stats(const GroupNormBwdArgs& a, int b, int slab, int g,
   rstd = rsqrtf(fmaxf(Q * inv_n - mean * mean, 0.f) + a.eps);
 }
 
-__global__ void __launch_bounds__(640) gn_bwd_reduce_kernel(const GroupNormBwdArgs a) {
+__global__ void __launch_bounds__(640) gn_bwd_reduce_kernel(const GroupNormBwdArgs a, int rchunks) {
   extern __shared__ float gnb_smem[];  // [R][Cs][2]
   __shared__ float s_mean[128], s_rstd[128];
-  const int b = blockIdx.x, slab = blockIdx.y;
+  const int b = blockIdx.x, slab = blockIdx.y, rc = blockIdx.z;
   const int Cs = a.Cs, cpg = a.cpg;
   const int nv = Cs >> 3;
   const int R = blockDim.x / nv;
@@ -79,13 +80,15 @@ __global__ void __launch_bounds__(640) gn_bwd_reduce_kernel(const GroupNormBwdAr
     mu[j] = s_mean[g];
     rs[j] = s_rstd[g];
   }
-  const bf16_t* xb = a.x[slab] + static_cast<size_t>(b) * a.HW * a.x_ld[slab];
-  const bf16_t* dyb = a.dy + static_cast<size_t>(b) * a.HW * a.dy_ld + slab * Cs;
+  const int P = a.HW / rchunks;  // pixel rows of this CTA
+  const size_t row0 = static_cast<size_t>(b) * a.HW + static_cast<size_t>(rc) * P;
+  const bf16_t* xb = a.x[slab] + row0 * a.x_ld[slab];
+  const bf16_t* dyb = a.dy + row0 * a.dy_ld + slab * Cs;
   float sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
   if (rl < R) {
-    for (int p = rl; p < a.HW; p += R) {
+    for (int p = rl; p < P; p += R) {
       float x[8], dy[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * a.x_ld[slab]) + col), x);
       unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(p) * a.dy_ld) + col), dy);
@@ -109,12 +112,13 @@ __global__ void __launch_bounds__(640) gn_bwd_reduce_kernel(const GroupNormBwdAr
   for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) {
     float t = 0.f;
     for (int r = 0; r < R; ++r) t += gnb_smem[r * Cs * 2 + i];
-    a.ws[(static_cast<size_t>(b) * Ctot + slab * Cs) * 2 + i] = t;
+    a.ws[((static_cast<size_t>(b) * rchunks + rc) * Ctot + slab * Cs) * 2 + i] = t;  // ws[b][rchunk][channel][2]
   }
 }
 
-__global__ void __launch_bounds__(640) gn_bwd_apply_kernel(const GroupNormBwdArgs a, int nchunk) {
+__global__ void __launch_bounds__(640) gn_bwd_apply_kernel(const GroupNormBwdArgs a, int nchunk, int rchunks) {
   __shared__ float s_mean[128], s_rstd[128], s_c1[128], s_c2[128];
+  __shared__ float s_wa[1024], s_wb[1024];
   const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
   const int Cs = a.Cs, cpg = a.cpg;
   const int nv = Cs >> 3;
@@ -122,15 +126,30 @@ __global__ void __launch_bounds__(640) gn_bwd_apply_kernel(const GroupNormBwdArg
   const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
   const int ng = Cs / cpg;
   const int Ctot = gridDim.y * Cs;
+  // fold the row chunks of pass 1: one thread per channel (independent loads), gamma-weighted values to shared memory
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float wa = 0.f, wb = 0.f;
+    for (int r = 0; r < rchunks; ++r) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(a.ws) + (static_cast<size_t>(b) * rchunks + r) * Ctot + slab * Cs + c);
+      wa += w.x;
+      wb += w.y;
+    }
+    if (chunk == 0) {  // parameter gradients: dbeta_c += sum dz, dgamma_c += sum dz * xhat (this sample's share)
+      atomicAdd(a.dbeta + slab * Cs + c, wa);
+      atomicAdd(a.dgamma + slab * Cs + c, wb);
+    }
+    const float gmm = __ldg(a.gamma + slab * Cs + c);
+    s_wa[c] = gmm * wa;
+    s_wb[c] = gmm * wb;
+  }
+  if (static_cast<int>(threadIdx.x) < ng) gn_group_stats(a, b, slab, threadIdx.x, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+  __syncthreads();
   if (static_cast<int>(threadIdx.x) < ng) {
     const int g = threadIdx.x;
-    gn_group_stats(a, b, slab, g, s_mean[g], s_rstd[g]);
-    const float* w = a.ws + (static_cast<size_t>(b) * Ctot + slab * Cs + g * cpg) * 2;
     float S1 = 0.f, S2 = 0.f;
     for (int c = 0; c < cpg; ++c) {
-      const float gmm = __ldg(a.gamma + slab * Cs + g * cpg + c);
-      S1 = fmaf(gmm, w[2 * c], S1);
-      S2 = fmaf(gmm, w[2 * c + 1], S2);
+      S1 += s_wa[g * cpg + c];
+      S2 += s_wb[g * cpg + c];
     }
     const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
     s_c1[g] = S1 * inv_n;
@@ -184,34 +203,21 @@ __global__ void __launch_bounds__(640) gn_bwd_apply_kernel(const GroupNormBwdArg
   }
 }
 
-__global__ void gn_bwd_param_kernel(const float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int B,
-                                    int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sa = 0.f, sb = 0.f;
-  for (int b = 0; b < B; ++b) {
-    sa += ws[(static_cast<size_t>(b) * C + c) * 2];
-    sb += ws[(static_cast<size_t>(b) * C + c) * 2 + 1];
-  }
-  dbeta[c] += sa;
-  dgamma[c] += sb;
-}
-
 cudaError_t groupnorm_bwd_launch(const GroupNormBwdArgs& a, int B, int nslab, cudaStream_t s) {
   const int nv = a.Cs / 8;
-  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || nslab < 1 || nslab > 2 || !a.ws)
+  if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || a.Cs > 1024 || nslab < 1 || nslab > 2 || !a.ws)
     return cudaErrorInvalidValue;
   int R = GNB_R;
   while (R > 1 && nv * R > 640) R >>= 1;
   if (nv * R > 640 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(R) * a.Cs * 2 * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  gn_bwd_reduce_kernel<<<dim3(B, nslab), nv * R, smem, s>>>(a);
   const int per = 4 * R;
   const int nchunk = (a.HW >= 2 * per && a.HW % per == 0) ? a.HW / per : 1;
-  gn_bwd_apply_kernel<<<dim3(B, nslab, nchunk), nv * R, 0, s>>>(a, nchunk);
-  const int C = nslab * a.Cs;
-  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(a.ws, a.dgamma, a.dbeta, B, C);
+  int rchunks = nchunk < GNB_MAX_RCHUNKS ? nchunk : GNB_MAX_RCHUNKS;  // ws holds [B][rchunks][C][2] floats
+  while (a.HW % rchunks) --rchunks;
+  gn_bwd_reduce_kernel<<<dim3(B, nslab, rchunks), nv * R, smem, s>>>(a, rchunks);
+  gn_bwd_apply_kernel<<<dim3(B, nslab, nchunk), nv * R, 0, s>>>(a, nchunk, rchunks);
   return cudaGetLastError();
 }
 
@@ -434,14 +440,15 @@ cudaError_t silu_bwd_launch(const bf16_t* x, const bf16_t* dy, bf16_t* dx, size_
 // =====================================================================================================
 constexpr int ASB_DH = 80;
 constexpr int ASB_ROW = 88;  // padded bf16 row (176 B): conflict-free 16-byte row reads
-constexpr int ASB_T = 256;
+constexpr int ASB_T = 128;   // queries per chunk = threads per CTA (71 KB of shared memory: 3 CTAs / SM)
+constexpr int ASB_OWN = 16 * ASB_DH / ASB_T;  // (key, channel) outputs owned by a thread in phase 2
 
 __global__ void __launch_bounds__(ASB_T) attn_small_bwd_kernel(const AttnSmallBwdArgs a) {
   extern __shared__ __align__(16) uint8_t asb_smem[];
-  bf16_t* sQ = reinterpret_cast<bf16_t*>(asb_smem);                 // [256][88]
-  bf16_t* sDO = sQ + ASB_T * ASB_ROW;                              // [256][88]
-  float* sP = reinterpret_cast<float*>(sDO + ASB_T * ASB_ROW);     // [256][16]
-  float* sDS = sP + ASB_T * 16;                                    // [256][16]
+  bf16_t* sQ = reinterpret_cast<bf16_t*>(asb_smem);                 // [ASB_T][88]
+  bf16_t* sDO = sQ + ASB_T * ASB_ROW;                              // [ASB_T][88]
+  float* sP = reinterpret_cast<float*>(sDO + ASB_T * ASB_ROW);     // [ASB_T][16]
+  float* sDS = sP + ASB_T * 16;                                    // [ASB_T][16]
   float* sK = sDS + ASB_T * 16;                                    // [16][80]
   float* sV = sK + 16 * ASB_DH;                                    // [16][80]
   const int h = blockIdx.x, b = blockIdx.y;
@@ -457,10 +464,10 @@ __global__ void __launch_bounds__(ASB_T) attn_small_bwd_kernel(const AttnSmallBw
     sK[i] = kv;
     sV[i] = vv;
   }
-  // phase-2 ownership: output o = t + 256 * i  ->  (l, d) = (o / 80, o % 80), o < L * 80
-  float accK[5], accV[5];
+  // phase-2 ownership: output o = t + ASB_T * i  ->  (l, d) = (o / 80, o % 80), o < L * 80
+  float accK[ASB_OWN], accV[ASB_OWN];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) accK[i] = accV[i] = 0.f;
+  for (int i = 0; i < ASB_OWN; ++i) accK[i] = accV[i] = 0.f;
 
   for (int q0 = 0; q0 < a.Sq; q0 += ASB_T) {
     const int nq = min(ASB_T, a.Sq - q0);
@@ -544,22 +551,29 @@ __global__ void __launch_bounds__(ASB_T) attn_small_bwd_kernel(const AttnSmallBw
     __syncthreads();
     // phase 2
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < ASB_OWN; ++i) {
       const int o = t + ASB_T * i;
       if (o < L * ASB_DH) {
         const int l = o / ASB_DH, d = o % ASB_DH;
-        float ak = accK[i], av = accV[i];
-        for (int r = 0; r < nq; ++r) {
-          ak = fmaf(sDS[r * 16 + l], __bfloat162float(sQ[r * ASB_ROW + d]), ak);
-          av = fmaf(sP[r * 16 + l], __bfloat162float(sDO[r * ASB_ROW + d]), av);
+        float ak0 = 0.f, av0 = 0.f, ak1 = 0.f, av1 = 0.f;
+        int r = 0;
+        for (; r + 1 < nq; r += 2) {  // two independent accumulation chains
+          ak0 = fmaf(sDS[r * 16 + l], __bfloat162float(sQ[r * ASB_ROW + d]), ak0);
+          av0 = fmaf(sP[r * 16 + l], __bfloat162float(sDO[r * ASB_ROW + d]), av0);
+          ak1 = fmaf(sDS[(r + 1) * 16 + l], __bfloat162float(sQ[(r + 1) * ASB_ROW + d]), ak1);
+          av1 = fmaf(sP[(r + 1) * 16 + l], __bfloat162float(sDO[(r + 1) * ASB_ROW + d]), av1);
         }
-        accK[i] = ak;
-        accV[i] = av;
+        if (r < nq) {
+          ak0 = fmaf(sDS[r * 16 + l], __bfloat162float(sQ[r * ASB_ROW + d]), ak0);
+          av0 = fmaf(sP[r * 16 + l], __bfloat162float(sDO[r * ASB_ROW + d]), av0);
+        }
+        accK[i] += ak0 + ak1;
+        accV[i] += av0 + av1;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < ASB_OWN; ++i) {
     const int o = t + ASB_T * i;
     if (o < L * ASB_DH) {
       const int l = o / ASB_DH, d = o % ASB_DH;

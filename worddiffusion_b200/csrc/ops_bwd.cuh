@@ -21,7 +21,7 @@ struct GroupNormBwdArgs {
   int dy_ld;
   const float* gamma;       // [nslab*Cs]
   const float* beta;
-  float* ws;                // workspace [B][nslab*Cs][2] fp32: per-sample per-channel {sum dz, sum dz*xhat}
+  float* ws;                // workspace [B][4][nslab*Cs][2] fp32: per-sample (x <= 4 row chunks) per-channel {sum dz, sum dz*xhat}
   bf16_t* dx[2];            // gradient w.r.t. each source [B, HW, dx_ld]
   int dx_ld[2];
   const bf16_t* add[2];     // optional extra term added to dx (the branch that by-passes the norm), [B, HW, add_ld]

@@ -149,6 +149,17 @@ struct TPlan {
   size_t bytes = 0;
   std::vector<std::pair<void*, size_t>> zero_on_bwd;  // scratch that must be zero when the backward pass starts
   std::map<std::string, std::pair<const void*, size_t>> named;  // intermediates readable through wd_trainer_read_tensor (tests)
+  // per-call inputs / outputs are staged at fixed addresses so that the two launch lists can be replayed as CUDA graphs
+  float* in_x = nullptr;
+  long long *in_t = nullptr, *in_y = nullptr, *in_ctx = nullptr;
+  float* out_eps = nullptr;
+  float* in_deps = nullptr;
+  cudaGraphExec_t g_fwd = nullptr, g_bwd = nullptr;
+  int fwd_calls = 0, bwd_calls = 0;
+  ~TPlan() {
+    if (g_fwd) cudaGraphExecDestroy(g_fwd);
+    if (g_bwd) cudaGraphExecDestroy(g_bwd);
+  }
 };
 
 }  // namespace
@@ -663,7 +674,7 @@ struct TPlanBuilder {
     for (int g = 0; g < N / 320; ++g) dst.push_back(gw ? gw + static_cast<size_t>(g) * 320 * K : nullptr);
     return wgrad(ops, what, WX{x, K, x_ld, false, 1, 1, 1, 1}, dy, dy_ld, N, M, 0, 0, dst, K, 1, 0);
   }
-  void colsum(std::vector<TOp>& ops, const bf16* dy, int ld, int N, int M, float* total, int rows_per_group = 256,
+  void colsum(std::vector<TOp>& ops, const bf16* dy, int ld, int N, int M, float* total, int rows_per_group = 64,
               bf16* per_group = nullptr, int pg_ld = 0) {
     if (dry) return;
     const int groups = (M + rows_per_group - 1) / rows_per_group;
@@ -1045,6 +1056,12 @@ struct TPlanBuilder {
     const int Cmax = 2 * mc * 4;  // widest concat (bounded below by what the plan needs; checked by construction sizes)
     (void)Cmax;
 
+    plan->in_x = A.alloc<float>(static_cast<size_t>(M0) * c.in_channels);
+    plan->out_eps = A.alloc<float>(static_cast<size_t>(M0) * c.out_channels);
+    plan->in_deps = A.alloc<float>(static_cast<size_t>(M0) * c.out_channels);
+    plan->in_t = A.alloc<long long>(B);
+    plan->in_y = A.alloc<long long>(B);
+    plan->in_ctx = A.alloc<long long>(static_cast<size_t>(B) * L);
     // ---------------- shared scratch ----------------
     const size_t tokC = static_cast<size_t>(M0) * mc;
     scr_a = A.alloc<bf16>(tokC);
@@ -1485,6 +1502,45 @@ int run_tops(const std::vector<TOp>& ops, const TRun& r, cudaStream_t s, const c
   return WD_OK;
 }
 
+bool train_graph_enabled() {  // env WD_TRAIN_GRAPH (default on): replay the launch lists as CUDA graphs from the 2nd call on
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TRAIN_GRAPH");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0 && !train_prof_enabled();
+}
+// first call of a plan: eager (kernel attributes get set, errors surface per launch); second call: captured; then replayed
+int run_list(const std::vector<TOp>& ops, const TRun& r, cudaStream_t s, const char* phase, cudaGraphExec_t* exec, int* calls,
+             const std::vector<std::pair<void*, size_t>>* zero_first) {
+  ++*calls;
+  if (train_graph_enabled() && *exec) {
+    T_CUDA_TRY(cudaGraphLaunch(*exec, s));
+    return WD_OK;
+  }
+  const bool capture = train_graph_enabled() && *calls == 2;
+  if (capture) {
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return run_list(ops, r, s, phase, exec, &(*calls = 2), zero_first);  // cannot capture on this stream: stay eager
+    }
+  }
+  if (zero_first)
+    for (auto& z : *zero_first) T_CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+  const int rc = run_tops(ops, r, s, phase);
+  if (capture) {
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc) return rc;
+    if (ce != cudaSuccess || !g) return tfail(WD_ERR_CUDA, "graph capture of the %s list failed: %s", phase, cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) return tfail(WD_ERR_CUDA, "cudaGraphInstantiate (%s): %s", phase, cudaGetErrorString(ie));
+    T_CUDA_TRY(cudaGraphLaunch(*exec, s));
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------
@@ -1601,28 +1657,39 @@ extern "C" int wd_trainer_forward(wd_trainer* e, int batch, const float* x, cons
   int rc = ensure_tplan(e, batch, L, &p);
   if (rc) return rc;
   e->cur = p;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t HW = static_cast<size_t>(e->cfg.latent_h) * e->cfg.latent_w;
+  T_CUDA_TRY(cudaMemcpyAsync(p->in_x, x, static_cast<size_t>(batch) * e->cfg.in_channels * HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  T_CUDA_TRY(cudaMemcpyAsync(p->in_t, timesteps, static_cast<size_t>(batch) * 8, cudaMemcpyDeviceToDevice, s));
+  if (y) T_CUDA_TRY(cudaMemcpyAsync(p->in_y, y, static_cast<size_t>(batch) * 8, cudaMemcpyDeviceToDevice, s));
+  T_CUDA_TRY(cudaMemcpyAsync(p->in_ctx, ctx_tokens, static_cast<size_t>(batch) * L * 8, cudaMemcpyDeviceToDevice, s));
   TRun r;
-  r.x = x;
-  r.t = reinterpret_cast<const long long*>(timesteps);
-  r.y = reinterpret_cast<const long long*>(y);
-  r.ctx = reinterpret_cast<const long long*>(ctx_tokens);
-  r.eps_out = eps_out;
-  rc = run_tops(p->fwd, r, static_cast<cudaStream_t>(stream), "forward");
+  r.x = p->in_x;
+  r.t = p->in_t;
+  r.y = p->in_y;
+  r.ctx = p->in_ctx;
+  r.eps_out = p->out_eps;
+  rc = run_list(p->fwd, r, s, "forward", &p->g_fwd, &p->fwd_calls, nullptr);
   if (rc) return rc;
+  T_CUDA_TRY(cudaMemcpyAsync(eps_out, p->out_eps, static_cast<size_t>(batch) * e->cfg.out_channels * HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   e->fwd_done = true;
   return WD_OK;
 }
 
 extern "C" int wd_trainer_backward(wd_trainer* e, const float* d_eps, const int64_t* y, const int64_t* ctx_tokens, void* stream) {
-  if (!e || !d_eps || !ctx_tokens) return tfail(WD_ERR_INVALID, "null argument");
+  if (!e || !d_eps) return tfail(WD_ERR_INVALID, "null argument");
   if (!e->cur || !e->fwd_done) return tfail(WD_ERR_STATE, "wd_trainer_forward must run before wd_trainer_backward");
+  (void)y;           // the index tensors of the forward call are still staged in the plan
+  (void)ctx_tokens;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (auto& z : e->cur->zero_on_bwd) T_CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+  TPlan* p = e->cur;
+  const size_t HW = static_cast<size_t>(e->cfg.latent_h) * e->cfg.latent_w;
+  T_CUDA_TRY(cudaMemcpyAsync(p->in_deps, d_eps, static_cast<size_t>(p->B) * e->cfg.out_channels * HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   TRun r;
-  r.d_eps = d_eps;
-  r.y = reinterpret_cast<const long long*>(y);
-  r.ctx = reinterpret_cast<const long long*>(ctx_tokens);
-  const int rc = run_tops(e->cur->bwd, r, s, "backward");
+  r.d_eps = p->in_deps;
+  r.y = p->in_y;
+  r.ctx = p->in_ctx;
+  const int rc = run_list(p->bwd, r, s, "backward", &p->g_bwd, &p->bwd_calls, &p->zero_on_bwd);
   e->fwd_done = false;
   return rc;
 }
@@ -1743,7 +1810,7 @@ extern "C" int wd_op_groupnorm_bwd(const void* x, const void* dy, const float* g
   float* partial = nullptr;
   float* ws = nullptr;
   T_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), static_cast<size_t>(B) * groups * slots * 2 * sizeof(float), s));
-  T_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(B) * C * 2 * sizeof(float), s));
+  T_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), static_cast<size_t>(B) * 4 * C * 2 * sizeof(float), s));
   GroupNormStatsArgs st{static_cast<const bf16*>(x), C, partial, HW, C, cpg, slots, 0};
   T_CUDA_TRY(groupnorm_stats_launch(st, B, s));
   GroupNormBwdArgs a;
