@@ -136,6 +136,11 @@ int wd_op_pack_vec_geglu(const float* v, float* dst, int N, void* stream);
 /* softmax(q k^T scale) v with a short key sequence L <= 16; q [B,Sq,C], k,v [B,L,C], out [B,Sq,C] bf16; C = heads*80 */
 int wd_op_attention_small(const void* q, const void* k, const void* v, void* out, float* probs, int B, int Sq, int L,
                           int heads, float scale, void* stream);
+/* CrossAttention.forward (unet.py:185-207) for a short context with the to_q Linear fused in: out = softmax((a Wq^T + bias) K^T
+ * scale) V.  a [B*Sq, C] bf16, wq [C, C] bf16, kv [B, L, 2C] bf16 (K | V), out [B*Sq, C] bf16; C = heads*80 <= 320, Sq % 128 == 0,
+ * L <= 16.  The attention runs in the epilogue of the tcgen05 GEMM (q never reaches HBM). */
+int wd_op_q_ctx_attention(const void* a_bf16, const void* wq_bf16, const float* bias, const void* kv_bf16, void* out_bf16, int B,
+                          int Sq, int L, int heads, float scale, void* stream);
 /* flash-style attention, any Skv; q [B,Sq,ldq], k,v [B,Skv,ldkv] (row strides in elements) */
 int wd_op_attention(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int Sq,
                     int Skv, int heads, float scale, void* stream);

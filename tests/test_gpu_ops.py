@@ -144,6 +144,28 @@ def test_attention_small(Sq, L):
     assert relerr(probs, p) < 1e-4
 
 
+@pytest.mark.parametrize("B,Sq,L,heads,with_bias", [(3, 256, 10, 4, True), (5, 128, 10, 4, False), (2, 256, 12, 4, True), (2, 256, 16, 4, False),
+                                                    (2, 128, 1, 4, False), (150, 256, 10, 4, True)])
+def test_q_projection_ctx_attention_fused(B, Sq, L, heads, with_bias):
+    """to_q Linear + cross-attention over the short character context in ONE tcgen05 GEMM launch (the attention runs in the
+    epilogue on the fp32 accumulator, unet.py:175-207).  Reference: torch fp32 on the same bf16 operands; q stays fp32 in both."""
+    C = heads * 80
+    a = bf(torch.randn(B * Sq, C, generator=g(50)))
+    w = torch.randn(C, C, generator=g(51)) / math.sqrt(C)
+    wp = pack_linear(w)
+    bias = f32(torch.randn(C, generator=g(52)) * 0.2) if with_bias else None
+    kv = bf(torch.randn(B, L, 2 * C, generator=g(53)))
+    out = torch.full((B * Sq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    check(lib().wd_op_q_ctx_attention(P(a), P(wp), P(bias) if with_bias else None, P(kv), P(out), B, Sq, L, heads, 80 ** -0.5, S()),
+          "q_ctx_attention")
+    q = a.float() @ wp.float().t()
+    if with_bias:
+        q = q + bias
+    ref, _ = _attn_ref(q.reshape(B, Sq, C), kv[..., :C], kv[..., C:], heads)
+    assert not torch.isnan(out.float()).any()
+    assert relerr(out.float().reshape(B, Sq, C), ref) < BF16_STORE
+
+
 @pytest.mark.parametrize("Sq,Skv", [(256, 256), (64, 64), (256, 779), (64, 779), (100, 70), (256, 10), (64, 10), (100, 16),
                                     (64, 1)])
 def test_attention_flash(Sq, Skv):

@@ -51,6 +51,7 @@ SIGNATURES = {
     "wd_op_pack_linear": (_I, [_P, _P, _I, _I, _I, _P]),
     "wd_op_pack_vec_geglu": (_I, [_P, _P, _I, _P]),
     "wd_op_attention_small": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "wd_op_q_ctx_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "wd_op_attention": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "wd_op_gemm_block_n": (_I, []),
     # ---- training step ----

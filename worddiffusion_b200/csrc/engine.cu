@@ -4,6 +4,7 @@
 // descriptors are encoded once per plan), and exposes the C ABI of include/wd_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -703,6 +704,10 @@ struct Epi {
   int ln_dim = 0;
   Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
   int epi = EPI_STD;
+  // context attention fused into the to_q projection (GemmArgs::att_*): K / V rows [B, att_L, att_ld], `out` receives softmax(qK^T)V
+  const bf16* att_kv = nullptr;
+  int att_ld = 0, att_voff = 0, att_L = 0;
+  float att_scale = 0.f;
 };
 
 struct PlanBuilder {
@@ -770,6 +775,11 @@ struct PlanBuilder {
     a.act = ep.act;
     a.geglu = ep.geglu;
     a.epi = ep.epi;
+    a.att_kv = ep.att_kv;
+    a.att_ld = ep.att_ld;
+    a.att_voff = ep.att_voff;
+    a.att_L = ep.att_L;
+    a.att_scale = ep.att_scale;
     if (ep.stats_for && epilogue_stats_ok(ep.rows_per_sample, w.N) && ep.stats_for->C == w.N) {
       a.gn_partial = ep.stats_for->stats;
       a.gn_cpg = 10;
@@ -811,6 +821,10 @@ struct PlanBuilder {
     if (ktot != w.K) { err = "gemm: K mismatch between sources and weight"; return false; }
     op.flops = 2.0 * M * static_cast<double>(w.N) * w.K;
     op.bytes = 2.0 * (static_cast<double>(M) * w.K + static_cast<double>(w.N) * w.K + static_cast<double>(M) * (ep.geglu ? w.N / 2 : w.N));
+    if (ep.att_kv) {  // + QK^T and PV of the fused context attention, + the K / V rows
+      op.flops += 4.0 * M * static_cast<double>(w.N) * ep.att_L;
+      op.bytes += 2.0 * 2.0 * (static_cast<double>(M) / ep.rows_per_sample) * ep.att_L * w.N;
+    }
     const int bn = (ep.epi == EPI_SAMPLER) ? GEMM_BLOCK_N_OUT : gemm_tc_block_n();
     if (w.N % bn) { err = "gemm: N must be a multiple of the N tile"; return false; }
     const int b_box = gemm_b_box_rows(a);
@@ -953,6 +967,25 @@ struct PlanBuilder {
     return true;
   }
 
+  // The character-context attention (<= 12 keys, 80-channel heads) runs inside the epilogue of its to_q projection when every
+  // 128-row tile lies inside one sample (env WD_FUSE_CTX_ATTN=0 keeps the separate attention kernel for A/B measurements).
+  static bool fuse_ctx_attn(int HW, int Ltot, int dh) {
+    static int en = -1;
+    if (en < 0) {
+      const char* v = getenv("WD_FUSE_CTX_ATTN");
+      en = v ? (atoi(v) != 0) : 1;
+    }
+    return en && dh == 80 && Ltot >= 1 && Ltot <= GEMM_ATT_MAXL && HW % GEMM_BLOCK_M == 0;
+  }
+  static void set_ctx_attn(Epi& ep, const bf16* kvbuf, int C, int Ltot, int HW, int dh) {
+    ep.att_kv = kvbuf;
+    ep.att_ld = 2 * C;
+    ep.att_voff = C;
+    ep.att_L = Ltot;
+    ep.att_scale = 1.0f / sqrtf(static_cast<float>(dh));
+    ep.rows_per_sample = HW;
+  }
+
   // ---- SpatialTransformer (unet.py:381-412, 337-345 ; unetPhosc.py:282-300, 241-246) ----
   bool st_block(std::vector<Op>& ops, const STL& s, const Act& x_in, const std::vector<bf16*>& kv, Act& out) {
     const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = s.heads * s.dh;
@@ -989,14 +1022,21 @@ struct PlanBuilder {
         if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
         attn_op(ops, qkv, 3 * C, qkv + C, qkv + 2 * C, 3 * C, o.p, C, HW, HW, s.heads, s.dh);
       } else {
-        bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
-        ep.out = q;
-        ep.out_ld = C;
         ep.ln_stats = rs_x;  // unet.py:337 applies norm2 before attn1
         ep.ln_dim = C;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
-        attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+        if (fuse_ctx_attn(HW, Ltot, s.dh)) {
+          ep.out = o.p;
+          ep.out_ld = C;
+          set_ctx_attn(ep, kv[t.kv1], C, Ltot, HW, s.dh);
+          if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
+        } else {
+          bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
+          ep.out = q;
+          ep.out_ld = C;
+          if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
+          attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+        }
       }
       {
         Epi ep;
@@ -1013,14 +1053,21 @@ struct PlanBuilder {
       Act x2 = new_act(H, W, C, true);
       float* rs_x2 = new_rowstats();
       {
-        bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
         Epi ep;
-        ep.out = q;
-        ep.out_ld = C;
         ep.ln_stats = rs_x1;  // LN2
         ep.ln_dim = C;
-        if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
-        attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+        if (fuse_ctx_attn(HW, Ltot, s.dh)) {
+          ep.out = o.p;
+          ep.out_ld = C;
+          set_ctx_attn(ep, kv[t.kv2], C, Ltot, HW, s.dh);
+          if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
+        } else {
+          bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
+          ep.out = q;
+          ep.out_ld = C;
+          if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
+          attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+        }
         Epi ep2;
         ep2.out = x2.p;
         ep2.out_ld = C;
@@ -1604,6 +1651,42 @@ extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, cons
   if (!out_f32 && !tmap_encode_out_bf16(&L.mapOut, out, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map out");
   if (residual && !tmap_encode_out_bf16(&L.mapRes, residual, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map residual");
   CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+extern "C" int wd_op_q_ctx_attention(const void* a_, const void* wq, const float* bias, const void* kv, void* out, int B, int Sq,
+                                     int L, int heads, float scale, void* stream) {
+  const int C = heads * 80, M = B * Sq;
+  if (C % gemm_tc_block_n() || C % GEMM_BLOCK_K || C > 5 * GEMM_BLOCK_K)
+    return fail(WD_ERR_UNSUPPORTED, "q_ctx_attention: heads * 80 must be a multiple of %d and <= 320", gemm_tc_block_n());
+  if (Sq % GEMM_BLOCK_M || L < 1 || L > GEMM_ATT_MAXL)
+    return fail(WD_ERR_UNSUPPORTED, "q_ctx_attention: Sq %% 128 != 0 or L > %d", GEMM_ATT_MAXL);
+  GemmLaunch Lh;
+  memset(&Lh, 0, sizeof(Lh));
+  GemmArgs& a = Lh.args;
+  a.M = M;
+  a.N = C;
+  a.num_src = 1;
+  a.taps[0] = 1;
+  a.chunks[0] = C / GEMM_BLOCK_K;
+  a.stride[0] = 1;
+  a.Wout = 1;
+  a.HWout = 1;
+  a.bias = bias;
+  a.rows_per_sample = Sq;
+  a.out = out;
+  a.out_ld = C;
+  a.att_kv = static_cast<const bf16*>(kv);
+  a.att_ld = 2 * C;
+  a.att_voff = C;
+  a.att_L = L;
+  a.att_scale = scale;
+  if (!tmap_encode_2d_bf16(&Lh.mapA[0], a_, C, M, C, GEMM_BLOCK_K, GEMM_BLOCK_M)) return fail(WD_ERR_CUDA, "tensor map A");
+  Lh.mapA[1] = Lh.mapA[2] = Lh.mapA[0];
+  if (!tmap_encode_2d_bf16(&Lh.mapB, wq, C, C, C, GEMM_BLOCK_K, gemm_b_box_rows(a))) return fail(WD_ERR_CUDA, "tensor map B");
+  Lh.mapOut = Lh.mapRes = Lh.mapB;
+  if (!tmap_encode_out_bf16(&Lh.mapOut, out, C, M, C)) return fail(WD_ERR_CUDA, "tensor map out");
+  CUDA_TRY(gemm_tc_launch(Lh, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 

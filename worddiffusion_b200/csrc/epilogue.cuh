@@ -7,6 +7,7 @@
 // on anything else (profiles/).  One `switch` per round picks a straight-line variant instead.
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace wd {
 
@@ -180,6 +181,127 @@ WD_DEVINL void epi_geglu40(const uint32_t* v, const float* wv_val, const float* 
       f[j] = fmaf(sc, __uint_as_float(v[c * 8 + j]), bv[j]) * gelu_fast_f(fmaf(sc, __uint_as_float(v[40 + c * 8 + j]), bg[j]));
     *reinterpret_cast<uint4*>(srow + c * 16) =
         make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
+// Fused short-context cross-attention on the to_q accumulator (CrossAttention.forward, unet.py:185-207, with the <= 16 key /
+// value rows of the sample's character context).  v = the thread's 80 accumulator columns = q of one (row, head) before the
+// additive terms.  The warp (32 rows x one head) writes q as bf16 into its own rows of the staging tile, reads it back as
+// mma.sync A fragments (ldmatrix), forms S = q K^T (16 keys, padded rows are zero and masked), the softmax in the accumulator
+// layout (a row lives in one quad), and O = P V, which overwrites the q rows: the staging tile then holds the output and is
+// stored by TMA like any other epilogue.  sK / sV: bf16 [16][ATT_KP] rows of (sample, head) in shared memory.
+// (A first version kept q in registers and read K / V with broadcast LDS.128: 400 per warp and tile; the shared-memory
+// return path (128 B / clk / SM) made the launch 2.5x slower than the two kernels it replaces.)
+constexpr int ATT_KP = 88;  // K / V row pitch in elements (176 B: conflict-free fragment loads)
+
+WD_DEVINL void epi_mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// swarp: row 0 of this warp in staging sub-tile 0 (rows are 80 bytes = 40 columns; sub-tile 1 is `sub_stride` bytes further)
+template <bool LNC>
+WD_DEVINL void epi_ctx_attn80(const uint32_t* v, const float* wvr, const float* wsr, float rstd, float rstd_mu, float sl2,
+                              const __nv_bfloat16* sK, const __nv_bfloat16* sV, int L, uint8_t* swarp, int sub_stride, int lane) {
+  // ---- q (fp32, exact additive terms) -> bf16 -> own staging row ----
+  uint8_t* const srow = swarp + lane * (GEMM_SUB_N * 2);
+#pragma unroll
+  for (int c = 0; c < 10; ++c) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(wvr + c * 8), b1 = *reinterpret_cast<const float4*>(wvr + c * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    if constexpr (LNC) {
+      const float4 s0 = *reinterpret_cast<const float4*>(wsr + c * 8), s1 = *reinterpret_cast<const float4*>(wsr + c * 8 + 4);
+      const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(rstd, __uint_as_float(v[c * 8 + j]), fmaf(-rstd_mu, ss[j], bb[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c * 8 + j]) + bb[j];
+    }
+    *reinterpret_cast<uint4*>(srow + (c / 5) * sub_stride + (c % 5) * 16) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+  __syncwarp();
+  const int g = lane >> 2, tq = lane & 3;
+  // ---- K fragments (B operand of S = q K^T): both key octets, 5 k-steps ----
+  uint32_t kb[2][5][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const __nv_bfloat16* kr = sK + (nt * 8 + g) * ATT_KP + 2 * tq;
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      kb[nt][ks][0] = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
+      kb[nt][ks][1] = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    uint8_t* const mrow = swarp + (mt * 16) * (GEMM_SUB_N * 2);
+    // ---- q fragments of 16 rows (A operand): 8-column blocks never straddle the two 40-column sub-tiles ----
+    uint32_t qf[5][4];
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      const int c8 = ks * 2 + (lane >> 4);
+      const uint8_t* p = mrow + (lane & 15) * (GEMM_SUB_N * 2) + (c8 / 5) * sub_stride + (c8 % 5) * 16;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(qf[ks][0]), "=r"(qf[ks][1]), "=r"(qf[ks][2]), "=r"(qf[ks][3])
+                   : "r"(smem_u32(p)));
+    }
+    float sc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sc[nt][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) epi_mma_bf16_16816(sc[nt], qf[ks], kb[nt][ks][0], kb[nt][ks][1]);
+    }
+    // ---- softmax over the keys (rows g and g + 8 of the m-tile; a row lives in one quad) ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int key = nt * 8 + 2 * tq;
+      if (key >= L) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+      if (key + 1 >= L) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pf[4];  // P as one A fragment (k = 16 keys)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const float p0 = exp2f((sc[nt][0] - mx0) * sl2), p1 = exp2f((sc[nt][1] - mx0) * sl2);
+      const float p2 = exp2f((sc[nt][2] - mx1) * sl2), p3 = exp2f((sc[nt][3] - mx1) * sl2);
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      pf[nt * 2] = pack_bf16x2(p0, p1);
+      pf[nt * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    // ---- O = P V over the q rows of this m-tile (their fragments are in registers) ----
+    __syncwarp();
+#pragma unroll
+    for (int dt = 0; dt < 10; ++dt) {
+      uint32_t b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                   : "=r"(b0), "=r"(b1)
+                   : "r"(smem_u32(sV + (lane & 15) * ATT_KP + dt * 8)));
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      epi_mma_bf16_16816(o, pf, b0, b1);
+      uint8_t* const op = mrow + (dt / 5) * sub_stride + (dt % 5) * 16 + tq * 4;
+      *reinterpret_cast<uint32_t*>(op + g * (GEMM_SUB_N * 2)) = pack_bf16x2(o[0] * i0, o[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + (g + 8) * (GEMM_SUB_N * 2)) = pack_bf16x2(o[2] * i1, o[3] * i1);
+    }
   }
 }
 

@@ -12,7 +12,7 @@ namespace wd {
 // shared memory (loaded once), works on ONE n-tile for all its m-tiles, and the ring only streams A (16 KB per K block).
 // For K = 320 this halves the L2->SM operand traffic (100 KB of weights were re-streamed for every 80 KB of activations),
 // which is what bounds the 1x1 / Linear GEMMs of the transformer blocks (the per-SM TMA ingest rate, see gemm_pair.cu).
-template <int BN, int STAGES_, int NSTG_, int WSK_ = 0>
+template <int BN, int STAGES_, int NSTG_, int WSK_ = 0, int ATT_ = 0>
 struct Cfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int NSTG = NSTG_;  // staging buffers per column half (0: the epilogue writes global memory directly)
@@ -28,16 +28,18 @@ struct Cfg {
   static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
   // per-warp bias / row-bias vector of its 80 accumulator columns (+ a second one, the LayerNorm column sums, in WS mode)
   static constexpr int VEC_BYTES = (WSK ? 2 : 1) * GEMM_EPI_WARPS * 80 * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + 256 /*barriers*/;
+  // fused context attention: bf16 K and V rows [16][ATT_KP] of the tile's sample, one (K, V) pair per column half (= head)
+  static constexpr int KV_BYTES = ATT_ ? 2 * 2 * 16 * ATT_KP * 2 : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + KV_BYTES + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK, int ATT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                const GemmArgs args) {
-  using C = Cfg<BN, STAGES, NSTG, WSK>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT>;
   constexpr int NB = NSTG > 0 ? NSTG : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -45,7 +47,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint8_t* bres = smem + C::STAGES * C::STAGE_BYTES;  // [WSK][BN x 64] resident weight tile (weight-stationary mode)
   uint8_t* stg = bres + C::BRES_BYTES;                // [half][NSTG][2 sub-tiles][128][40] bf16
   float* vecs = reinterpret_cast<float*>(stg + C::STG_BYTES);  // [8 epilogue warps][80]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES + C::VEC_BYTES);
+  __nv_bfloat16* kvs = reinterpret_cast<__nv_bfloat16*>(stg + C::STG_BYTES + C::VEC_BYTES);  // [half][K|V][16][ATT_KP] (ATT builds)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + C::STG_BYTES + C::VEC_BYTES + C::KV_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -317,6 +320,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           ln_rstd_mu = ln_rstd * mu;
         }
 
+        if constexpr (ATT) {
+          // K / V rows of (sample of this tile, head of this column half) -> shared memory, rows >= L zeroed.  The four warps of
+          // the half passed the post-staging barrier of the previous tile after their last read of the buffer; the barrier in
+          // front of the epilogue arithmetic below publishes the new contents.
+          const int L = args.att_L;
+          const int sample = m0 / args.rows_per_sample;
+          const int head = (n0 + half * HC) / 80;
+          const __nv_bfloat16* src = args.att_kv + static_cast<size_t>(sample) * L * args.att_ld + head * 80;
+          __nv_bfloat16* dst = kvs + half * (2 * 16 * ATT_KP);
+          for (int idx = q * 32 + lane; idx < 2 * 16 * 10; idx += 128) {
+            const int sel = idx / 160, r = idx % 160, j = r / 10, ch = r % 10;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (j < L) u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(j) * args.att_ld + sel * args.att_voff) + ch);
+            *reinterpret_cast<uint4*>(dst + (sel * 16 + j) * ATT_KP + ch * 8) = u;
+          }
+        }
+
         mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
@@ -349,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (use_stg) {
           if (has_res) {
             mbar_wait(&res_bar[sb], (it / NB) & 1);  // the residual tile has landed in the staging buffer
-          } else if (!(args.dbg & 64)) {
+          } else if (ATT || !(args.dbg & 64)) {
             if (leader_warp) {
               if (elect_one()) {
                 if (NSTG > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
@@ -361,6 +381,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint8_t* const srow = stg_half + sb * C::HALF_STG_BYTES + row * (GEMM_SUB_N * 2);
 
         if (args.dbg & 128) {
+        } else if (ATT) {
+          if constexpr (ATT) {
+            const __nv_bfloat16* sK = kvs + half * (2 * 16 * ATT_KP);
+            const float sl2 = args.att_scale * 1.4426950408889634f;  // scale * log2(e): the softmax runs on exp2
+            uint8_t* const swarp = stg_half + sb * C::HALF_STG_BYTES + (q * 32) * (GEMM_SUB_N * 2);
+            if (ln_consume) epi_ctx_attn80<true>(v, wv, wv2, ln_rstd, ln_rstd_mu, sl2, sK, sK + 16 * ATT_KP, args.att_L, swarp, C::SUB_BYTES, lane);
+            else epi_ctx_attn80<false>(v, wv, wv2, 1.f, 0.f, sl2, sK, sK + 16 * ATT_KP, args.att_L, swarp, C::SUB_BYTES, lane);
+          }
         } else if (args.geglu) {
           // values of this warp: tile columns [40 half, +40), gates 80 further; 40 output columns = one staging sub-tile
           // (every GEGLU launch stages: gemm_tc_launch rejects geglu + fp32 output)
@@ -511,14 +539,14 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0, int ATT = 0>
 static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES, NSTG, WSK>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
@@ -532,7 +560,7 @@ static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
     if (n_tiles > num_sms()) return cudaErrorInvalidValue;
     grid = (grid / n_tiles) * n_tiles;
   }
-  gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
+  gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
                                                                                            L.mapB, L.mapOut, L.mapRes, a);
   return cudaGetLastError();
 }
@@ -596,9 +624,17 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   if (a.ln_stats && (a.residual || a.gn_partial || a.out_f32 || a.out_f16 || a.rowbias || a.act != ACT_NONE || !a.ln_s ||
                      a.ln_slots < 1 || a.conv || a.num_src != 1))
     return cudaErrorInvalidValue;
-  if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
+  if (a.att_kv) {
+    // to_q projection with the context attention in its epilogue: weight-stationary build only, whole tiles inside one sample
+    if (a.conv || a.num_src != 1 || total_k > 5 || a.N % 80 || a.N / GEMM_BLOCK_N > num_sms() || a.M % GEMM_BLOCK_M ||
+        a.rows_per_sample % GEMM_BLOCK_M || a.att_L < 1 || a.att_L > GEMM_ATT_MAXL || a.att_ld % 8 || a.att_voff % 8 || a.residual ||
+        a.gn_partial || a.ln_out || a.out_f32 || a.out_f16 || a.rowbias || a.geglu || a.act != ACT_NONE || (a.ln_stats && !a.ln_s))
+      return cudaErrorInvalidValue;
+    return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 1>(L, stream);
+  }
+  if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
   // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
   // short K loops are epilogue / store bound: spend it on a second staging buffer
   if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);

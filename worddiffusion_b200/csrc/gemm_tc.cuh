@@ -37,6 +37,7 @@ constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quarter
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0: TMA producer, warp1: TMEM alloc + MMA issuer, warps2-9: epilogue
 constexpr int GEMM_SUB_N = 40;      // staging / TMA-store sub-tile width (columns)
 constexpr int GEMM_MAX_SRC = 3;
+constexpr int GEMM_ATT_MAXL = 16;  // longest key sequence of the fused context-attention epilogue
 
 enum GemmAct : int { ACT_NONE = 0, ACT_SILU = 1 };
 enum GemmEpi : int { EPI_STD = 0, EPI_SAMPLER = 1 };
@@ -80,6 +81,15 @@ struct GemmArgs {
   int ln_dim;             // channels of the normalised tensor
   float ln_eps;
   const float* ln_s;      // [N]
+  // Fused short-context cross-attention (unet.py:185-207 with the 10-token character context): the GEMM is the to_q projection
+  // (N = heads * 80); each epilogue thread holds the 80 q values of one (row, head) and computes softmax(q K^T scale) V against
+  // the sample's precomputed K / V rows, so q never reaches HBM.  att_kv: bf16 [samples, att_L, att_ld], K of head h at column
+  // 80 h, V at column att_voff + 80 h.  Needs the weight-stationary build, rows_per_sample % 128 == 0, M % 128 == 0, att_L <= 16.
+  const __nv_bfloat16* att_kv;  // null: off
+  int att_ld;
+  int att_voff;
+  int att_L;
+  float att_scale;
   // GroupNorm partial statistics of the written tensor: gn_partial[sample][N/gn_cpg groups][rows_per_sample/32][2]
   float* gn_partial;  // null: off.  Needs gn_cpg == 10, rows_per_sample % 32 == 0
   int gn_cpg;
