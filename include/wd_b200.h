@@ -126,6 +126,10 @@ int wd_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, cons
  * geglu: W rows are nn.Linear(K, N) of GEGLU.proj in packed (tile-permuted) order, out is [M, N/2]. */
 int wd_op_gemm(const void* a_bf16, const void* w_bf16, const float* bias, const void* residual_bf16, void* out, int M,
                int N, int K, int act_silu, int geglu, int out_f32, void* stream);
+/* the residual-stream flavour of the transformer blocks (unet.py:337-345: x = attn(norm(x)) + x): A, W bf16; residual and out
+ * fp16 [M,N].  For K <= 320 the residual rides through the operand ring as extra K blocks against an identity tile. */
+int wd_op_gemm_f16(const void* a_bf16, const void* w_bf16, const float* bias, const void* residual_f16, void* out_f16, int M, int N,
+                   int K, void* stream);
 /* 3x3 conv, pad 1, stride 1|2, NHWC bf16, weights pre-packed [Cout, 9*Cin] by wd_op_pack_conv3x3 */
 int wd_op_conv3x3(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* rowbias, int rb_ld,
                   const void* residual_bf16, void* out_bf16, int B, int H, int W, int Cin, int Cout, int stride, void* stream);

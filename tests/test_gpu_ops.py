@@ -50,6 +50,22 @@ def test_gemm_epilogues():
     assert o.dtype == torch.float32 and relerr(o, base + bias) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 320, 320), (300, 320, 320), (20000, 320, 320), (256, 320, 1280), (256, 640, 192)])
+def test_gemm_fp16_residual_stream(M, N, K):
+    """Linear + residual on the fp16 token stream (unet.py:337-345).  K <= 320: the residual is accumulated on the tensor pipe as
+    extra K blocks against an identity tile (GemmArgs::res_k); K = 1280: the TMA-prefetched residual epilogue."""
+    a = bf(torch.randn(M, K, generator=g(60)))
+    w = torch.randn(N, K, generator=g(61)) / math.sqrt(K)
+    wp = pack_linear(w)
+    bias = f32(torch.randn(N, generator=g(62)))
+    res = (torch.randn(M, N, generator=g(63)) * 3).to(device=DEV, dtype=torch.float16)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    check(lib().wd_op_gemm_f16(P(a), P(wp), P(bias), P(res), P(out), M, N, K, S()), "gemm_f16")
+    ref = a.float() @ wp.float().t() + bias + res.float()
+    assert not torch.isnan(out.float()).any()
+    assert relerr(out.float(), ref) < 2 ** -10  # fp16 storage: 11 significant bits
+
+
 def test_gemm_geglu():
     """GEGLU (unet.py:122-129): proj -> chunk(2) -> a * gelu(gate), exact erf GELU."""
     M, K, inner = 256, 320, 1280

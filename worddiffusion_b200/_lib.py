@@ -46,6 +46,7 @@ SIGNATURES = {
     "wd_op_groupnorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "wd_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "wd_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "wd_op_gemm_f16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "wd_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wd_op_pack_conv3x3": (_I, [_P, _P, _I, _I, _P]),
     "wd_op_pack_linear": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -26,6 +26,17 @@ WD_DEVINL bool elect_one() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the sampling step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled -- and run their prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, the resident weight tile of the weight-stationary GEMMs) -- while the previous
+// kernel of the stream drains.  pdl_wait() blocks until the previous kernel has COMPLETED and its writes are visible; it
+// must precede the first access to memory another kernel of the step produces or still reads.  It is a no-op when the
+// kernel was launched without the attribute.  pdl_trigger() lets the next kernel start launching.
+// ----------------------------------------------------------------------------------------------
+WD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+WD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // MUFU.RCP (rel. error ~2^-23): the IEEE division / __frcp_rn expand to ~8 instructions plus a slow-path call
 WD_DEVINL float rcp_fast(float x) {
   float r;
@@ -352,6 +363,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t 
          | (0u << 16)      // b_major   = K
          | ((N >> 3) << 17)
          | ((M >> 4) << 24);
+}
+
+// Host side of PDL: launch `kernel` with the programmatic-stream-serialization attribute (env WD_PDL=0 disables it).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace wd

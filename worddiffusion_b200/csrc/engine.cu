@@ -845,6 +845,7 @@ struct PlanBuilder {
         err = "cuTensorMapEncodeTiled failed (residual)";
         return false;
       }
+      if (!gemm_prepare_res_k(op.gemm)) { err = "cuTensorMapEncodeTiled failed (residual as K blocks)"; return false; }
     }
     ops.push_back(op);
     if (ep.stats_for && !ensure_stats(ops, *ep.stats_for)) return false;
@@ -1619,8 +1620,18 @@ extern "C" int wd_op_layernorm(const void* x, void* out, const float* gamma, con
   return WD_OK;
 }
 
+static int op_gemm_impl(const void* a_, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K,
+                        int act_silu, int geglu, int out_f32, int res_f16, int out_f16, void* stream);
 extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, const void* residual, void* out, int M, int N,
                           int K, int act_silu, int geglu, int out_f32, void* stream) {
+  return op_gemm_impl(a_, w, bias, residual, out, M, N, K, act_silu, geglu, out_f32, 0, 0, stream);
+}
+extern "C" int wd_op_gemm_f16(const void* a_, const void* w, const float* bias, const void* residual_f16, void* out_f16, int M,
+                              int N, int K, void* stream) {
+  return op_gemm_impl(a_, w, bias, residual_f16, out_f16, M, N, K, 0, 0, 0, 1, 1, stream);
+}
+static int op_gemm_impl(const void* a_, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K,
+                        int act_silu, int geglu, int out_f32, int res_f16, int out_f16, void* stream) {
   if (K % GEMM_BLOCK_K || N % gemm_tc_block_n()) return fail(WD_ERR_UNSUPPORTED, "gemm: K %% 64 or N %% %d", gemm_tc_block_n());
   GemmLaunch L;
   memset(&L, 0, sizeof(L));
@@ -1642,6 +1653,8 @@ extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, cons
   a.out = out;
   a.out_ld = out_cols;
   a.out_f32 = out_f32;
+  a.res_f16 = res_f16;
+  a.out_f16 = out_f16;
   a.act = act_silu ? ACT_SILU : ACT_NONE;
   a.geglu = geglu;
   if (!tmap_encode_2d_bf16(&L.mapA[0], a_, K, M, K, GEMM_BLOCK_K, GEMM_BLOCK_M)) return fail(WD_ERR_CUDA, "tensor map A");
@@ -1650,6 +1663,7 @@ extern "C" int wd_op_gemm(const void* a_, const void* w, const float* bias, cons
   L.mapOut = L.mapRes = L.mapB;
   if (!out_f32 && !tmap_encode_out_bf16(&L.mapOut, out, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map out");
   if (residual && !tmap_encode_out_bf16(&L.mapRes, residual, out_cols, M, out_cols)) return fail(WD_ERR_CUDA, "tensor map residual");
+  if (!gemm_prepare_res_k(L)) return fail(WD_ERR_CUDA, "tensor map residual (K blocks)");
   CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }

@@ -97,6 +97,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // PDL (common.cuh): the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
@@ -388,9 +390,8 @@ cudaError_t gemm_pair_launch(const GemmLaunch& L, int num_sms, cudaStream_t stre
   const int tiles = (a.N / PAIR_BN) * ((a.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
   const int max_pairs = num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm_pair_kernel<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2], L.mapB, L.mapOut,
-                                                                        L.mapRes, a);
-  return cudaGetLastError();
+  return launch_pdl(gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, L.mapA[0], L.mapA[1], L.mapA[2],
+                    L.mapB, L.mapOut, L.mapRes, a);
 }
 
 }  // namespace wd

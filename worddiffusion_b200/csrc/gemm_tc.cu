@@ -5,14 +5,28 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 namespace wd {
+
+// dbg & 1024: clock64 stamps of the epilogue phases of (CTA 0, leader warp of column half 0), 12 per tile (tools/gemm_trace.py)
+__device__ unsigned long long g_gemm_trace[12 * 64];
+__device__ unsigned long long g_gemm_cta_times[4 * 160];  // per CTA: globaltimer at entry, after the prologue, after pdl_wait, at exit
+WD_DEVINL unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define WD_TRACE(slot)                                                                                  \
+  do {                                                                                                  \
+    if ((args.dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 64) g_gemm_trace[it * 12 + (slot)] = clock64(); \
+  } while (0)
 
 // WSK > 0: "weight-stationary" mode for short K (K <= 64 WSK): the CTA keeps its whole [BN x K] weight tile resident in
 // shared memory (loaded once), works on ONE n-tile for all its m-tiles, and the ring only streams A (16 KB per K block).
 // For K = 320 this halves the L2->SM operand traffic (100 KB of weights were re-streamed for every 80 KB of activations),
 // which is what bounds the 1x1 / Linear GEMMs of the transformer blocks (the per-SM TMA ingest rate, see gemm_pair.cu).
-template <int BN, int STAGES_, int NSTG_, int WSK_ = 0, int ATT_ = 0>
+template <int BN, int STAGES_, int NSTG_, int WSK_ = 0, int ATT_ = 0, int RESK_ = 0>
 struct Cfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int NSTG = NSTG_;  // staging buffers per column half (0: the epilogue writes global memory directly)
@@ -20,7 +34,8 @@ struct Cfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BN * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = WSK ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int BRES_BYTES = WSK * B_BYTES;  // resident weight tile
+  static constexpr int IDENT_BYTES = RESK_ ? 64 * GEMM_BLOCK_K * 2 : 0;  // 64 x 64 fp16 identity tile (GemmArgs::res_k)
+  static constexpr int BRES_BYTES = WSK * B_BYTES + IDENT_BYTES;  // resident weight tile (+ identity)
   static constexpr int ACC_STRIDE = (BN == GEMM_BLOCK_N) ? 256 : 32;  // TMEM column offset of accumulator buffer 1
   static constexpr int TMEM_COLS = (BN == GEMM_BLOCK_N) ? 512 : 64;
   static constexpr int SUB_BYTES = GEMM_BLOCK_M * GEMM_SUB_N * 2;  // one dense [128][40] bf16 sub-tile
@@ -33,16 +48,17 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + KV_BYTES + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK, int ATT>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK, int ATT, int RESK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                const GemmArgs args) {
-  using C = Cfg<BN, STAGES, NSTG, WSK, ATT>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK>;
   constexpr int NB = NSTG > 0 ? NSTG : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
+  if ((args.dbg & 1024) && threadIdx.x == 64 && blockIdx.x < 160) g_gemm_cta_times[blockIdx.x * 4 + 0] = gtimer();
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
   uint8_t* bres = smem + C::STAGES * C::STAGE_BYTES;  // [WSK][BN x 64] resident weight tile (weight-stationary mode)
   uint8_t* stg = bres + C::BRES_BYTES;                // [half][NSTG][2 sub-tiles][128][40] bf16
@@ -74,7 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (args.num_src > 2) tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapB);
     if (NSTG > 0 && !args.out_f32) tma_prefetch_desc(&mapOut);
-    if (NSTG > 0 && args.residual) tma_prefetch_desc(&mapRes);
+    if (NSTG > 0 && args.residual && !(RESK && args.res_k)) tma_prefetch_desc(&mapRes);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -92,6 +108,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if ((args.dbg & 1024) && threadIdx.x == 64 && blockIdx.x < 160) g_gemm_cta_times[blockIdx.x * 4 + 1] = gtimer();
+  pdl_trigger();
+  // PDL: everything above (and the resident weight tile below) touches only static data; every other global access of this
+  // kernel -- operand loads, statistics / residual / row-bias reads, all output writes -- comes after pdl_wait()
+  if (warp != 0) pdl_wait();
+  if ((args.dbg & 1024) && threadIdx.x == 64 && blockIdx.x < 160) g_gemm_cta_times[blockIdx.x * 4 + 2] = gtimer();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -103,9 +125,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (WSK > 0 && static_cast<int>(blockIdx.x) < total_tiles) {
         // weight-stationary: gridDim.x is a multiple of n_tiles, so this CTA's n-tile never changes
         const int n0 = (blockIdx.x % n_tiles) * BN;
-        mbar_arrive_expect_tx(bres_bar, total_k * C::B_BYTES);
+        mbar_arrive_expect_tx(bres_bar, total_k * C::B_BYTES + C::IDENT_BYTES);
         for (int kb = 0; kb < total_k; ++kb) tma_load_2d(bres + kb * C::B_BYTES, &mapB, bres_bar, kb * GEMM_BLOCK_K, n0);
+        if constexpr (RESK) tma_load_2d(bres + WSK * C::B_BYTES, &mapA2, bres_bar, 0, 0);
       }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
         const int n0 = (tile % n_tiles) * BN;
@@ -139,6 +163,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               ++kb;
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+          }
+        }
+        if constexpr (RESK) {
+          // residual K blocks: only the 64-channel blocks that overlap this tile's BN output columns
+          for (int rb = n0 / GEMM_BLOCK_K; rb * GEMM_BLOCK_K < n0 + BN; ++rb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES);
+            tma_load_2d(smem + stage * C::STAGE_BYTES, &mapA1, &full_bar[stage], rb * GEMM_BLOCK_K, m0);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -183,6 +216,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (RESK) {
+          // acc[:, c] += residual[:, n0 + c]: residual block rb (channels 64 rb ..) times the rows of the identity tile that
+          // select the overlap with [n0, n0 + BN): an N = 64 or 32 MMA into the matching accumulator columns
+          const int n0 = (tile % n_tiles) * BN;
+          for (int rb = n0 / GEMM_BLOCK_K; rb * GEMM_BLOCK_K < n0 + BN; ++rb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const int lo = max(rb * GEMM_BLOCK_K, n0), hi = min(rb * GEMM_BLOCK_K + GEMM_BLOCK_K, n0 + BN);
+            const uint32_t nn = static_cast<uint32_t>(hi - lo);  // 64 or 32
+            const uint32_t idesc = (1u << 4) | ((nn >> 3) << 17) | ((GEMM_BLOCK_M >> 4) << 24);  // fp16 x fp16 -> fp32, 128 x nn
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + stage * C::STAGE_BYTES));
+            const uint64_t b_desc =
+                make_smem_desc_sw128(smem_u32(bres + WSK * C::B_BYTES + (lo - rb * GEMM_BLOCK_K) * (GEMM_BLOCK_K * 2)));
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+              umma_f16_ss(d_tmem + static_cast<uint32_t>(lo - n0), a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -245,8 +298,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       // rare flavours (time-embedding GEMMs, operator tests): SiLU, fp32 output, per-thread row-bias rows, or a residual stored
       // in another 16-bit format than the output -> generic run-time-flag epilogue, residual read from global memory
       const bool slow_path = !use_stg || args.act != ACT_NONE || (args.rowbias && args.rows_per_sample % 32 != 0) ||
-                             (args.residual && (args.res_f16 != 0) != (args.out_f16 != 0));
-      const bool has_res = use_stg && args.residual != nullptr && !slow_path;  // residual TMA-prefetched into the staging tile
+                             (args.residual && !(RESK && args.res_k) && (args.res_f16 != 0) != (args.out_f16 != 0));
+      const bool has_res = use_stg && args.residual != nullptr && !slow_path && !(RESK && args.res_k);
       uint8_t* const stg_half = stg + half * NB * C::HALF_STG_BYTES;
       uint64_t* const res_bar = res_full_bar + half * 2;
       float* const wv = vecs + (warp - 2) * 80;
@@ -275,6 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n0 = n_tile * BN;
         const int m = m0 + row;
         const bool valid = m < args.M;
+        WD_TRACE(0);
         // ---- per-warp vector of the additive per-column terms (bias + the warp's sample row of the row-bias) ----
         const float* rb = nullptr;  // per-thread row-bias only when the rows of a warp can belong to different samples
         {
@@ -287,7 +341,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int sample = valid ? (m / args.rows_per_sample) : 0;
             rb = args.rowbias + (args.rowbias_idx ? args.rowbias_idx[sample] : static_cast<long long>(sample)) * args.rb_ld;
           }
+          // weight-stationary CTAs keep their n-tile: without a row-bias the vector is the same for every tile of the CTA
+          const bool vec_static = (WSK > 0) && args.rowbias == nullptr;
           __syncwarp();  // all lanes are done reading the previous tile's vector
+          if (!vec_static || it == 0) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int c = lane + 32 * i;
@@ -302,9 +359,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               }
             }
           }
+          }
           __syncwarp();
         }
 
+        WD_TRACE(1);
         float ln_rstd = 0.f, ln_rstd_mu = 0.f;
         if (ln_consume && valid) {
           const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m) * args.ln_slots;
@@ -337,8 +396,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
 
+        WD_TRACE(2);
         mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
         tc_fence_after();
+        WD_TRACE(3);
         const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
 
         // ---- drain this warp's 32 x 80 accumulator block, then hand the TMEM buffer back to the MMA warp ----
@@ -362,6 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        WD_TRACE(4);
 
         if (args.dbg & 2) continue;
 
@@ -379,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         uint8_t* const srow = stg_half + sb * C::HALF_STG_BYTES + row * (GEMM_SUB_N * 2);
+        WD_TRACE(5);
 
         if (args.dbg & 128) {
         } else if (ATT) {
@@ -400,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             epi_round80_lnc(v, wv, wv2, ln_rstd, ln_rstd_mu, srow, C::SUB_BYTES);
           } else if (slow_path) {
             epi_round80_generic(v, wv, rb ? rb + nb : nullptr, args.act == ACT_SILU,
-                                (args.residual && !has_res) ? args.residual + static_cast<size_t>(m) * args.res_ld + nb : nullptr,
+                                (args.residual && !has_res && !(RESK && args.res_k)) ? args.residual + static_cast<size_t>(m) * args.res_ld + nb : nullptr,
                                 res_f16, use_stg, srow, C::SUB_BYTES, args.out_f32 != 0, out_f16,
                                 args.out_f32 ? static_cast<void*>(static_cast<float*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb)
                                              : static_cast<void*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(m) * args.out_ld + nb),
@@ -430,9 +493,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
 
         // ---- publish the staged half tile with TMA; prefetch the residual of this CTA's next tile ----
+        WD_TRACE(6);
         if (use_stg) {
           if (!(args.dbg & 32)) fence_proxy_async();  // generic-proxy smem writes -> visible to the async proxy (TMA)
           named_barrier_sync(bar_id, 128);
+          WD_TRACE(7);
           if (leader_warp && !(args.dbg & 1) && elect_one()) {
             const uint8_t* src = stg_half + sb * C::HALF_STG_BYTES;
             if (!args.geglu) {
@@ -450,6 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               issue_res_load(next, (it + 1) % NB);
             }
           }
+          WD_TRACE(8);
         }
       }
       if (use_stg && leader_warp) {
@@ -460,6 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if ((args.dbg & 1024) && threadIdx.x == 64 && blockIdx.x < 160) g_gemm_cta_times[blockIdx.x * 4 + 3] = gtimer();
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
@@ -539,14 +606,14 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0, int ATT = 0>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0, int ATT = 0, int RESK = 0>
 static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES, NSTG, WSK, ATT>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
@@ -560,11 +627,81 @@ static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
     if (n_tiles > num_sms()) return cudaErrorInvalidValue;
     grid = (grid / n_tiles) * n_tiles;
   }
-  gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(L.mapA[0], L.mapA[1], L.mapA[2],
-                                                                                           L.mapB, L.mapOut, L.mapRes, a);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, L.mapA[0],
+                    L.mapA[1], L.mapA[2], L.mapB, L.mapOut, L.mapRes, a);
 }
 
+static bool gemm_ws_enabled();
+// 64 x 64 fp16 identity (one per device), the B operand of the residual K blocks
+static const void* gemm_identity_f16() {
+  static void* ident[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!ident[dev]) {
+    std::vector<uint16_t> h(64 * 64, 0);
+    for (int i = 0; i < 64; ++i) h[i * 64 + i] = 0x3C00;  // 1.0 in fp16
+    void* d = nullptr;
+    if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    ident[dev] = d;
+  }
+  return ident[dev];
+}
+
+static bool gemm_res_k_enabled() {  // env WD_GEMM_RESK (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_RESK");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+bool gemm_prepare_res_k(GemmLaunch& L) {
+  GemmArgs& a = L.args;
+  a.res_k = 0;
+  int total_k = 0;
+  for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
+  // the weight-stationary launch of gemm_tc_launch(), an fp16 residual covering the N output columns, 16-bit staged output
+  if (!gemm_res_k_enabled() || !gemm_ws_enabled() || !a.residual || !a.res_f16 || a.epi != EPI_STD || a.conv || a.num_src != 1 ||
+      total_k > 5 || a.N / GEMM_BLOCK_N > num_sms() || a.N % GEMM_BLOCK_K % 32 || a.out_f32 || a.geglu || a.act != ACT_NONE ||
+      a.att_kv || a.res_ld % 8 || (a.rowbias && a.rows_per_sample % 32 != 0) || gemm_uses_pair(a))
+    return true;
+  const void* ident = gemm_identity_f16();
+  if (!ident) return false;
+  // residual [M, N] (row stride res_ld) as an A operand: 64-channel x 128-row SWIZZLE_128B boxes; columns beyond N are zero-filled
+  if (!tmap_encode_2d_bf16(&L.mapA[1], a.residual, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M), static_cast<uint64_t>(a.res_ld),
+                           GEMM_BLOCK_K, GEMM_BLOCK_M))
+    return false;
+  if (!tmap_encode_2d_bf16(&L.mapA[2], ident, 64, 64, 64, GEMM_BLOCK_K, 64)) return false;
+  a.res_k = 1;
+  return true;
+}
+
+}  // namespace wd
+// debug aid (not part of the product ABI): copies the clock64 stamps recorded under WD_GEMM_DBG & 1024
+extern "C" int wdx_gemm_trace_read(unsigned long long* host, int n) {
+  if (n > 12 * 64) n = 12 * 64;
+  return cudaMemcpyFromSymbol(host, wd::g_gemm_trace, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
+}
+extern "C" int wdx_gemm_cta_times_read(unsigned long long* host) {
+  return cudaMemcpyFromSymbol(host, wd::g_gemm_cta_times, sizeof(unsigned long long) * 4 * 160) == cudaSuccess ? 0 : -1;
+}
+extern "C" int wdx_gemm_trace_clear(void) {
+  static unsigned long long z[12 * 64] = {0};
+  return cudaMemcpyToSymbol(wd::g_gemm_trace, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+namespace wd {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 static int gemm_dbg_flags() {
   static int v = -1;
   if (v < 0) {
@@ -638,8 +775,11 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
   // short K loops are epilogue / store bound: spend it on a second staging buffer
   if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
-  if ((gemm_ws_enabled() || a.ln_stats) && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms())
+  if ((gemm_ws_enabled() || a.ln_stats) && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms()) {
+    if (a.res_k) return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 0, 1>(L, stream);  // + residual as identity K blocks
     return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1, 5>(L, stream);  // weight-stationary short-K GEMM
+  }
+  if (a.res_k) return cudaErrorInvalidValue;
   if (a.ln_stats) return cudaErrorInvalidValue;  // the LayerNorm-consuming epilogue exists in the weight-stationary build only
   return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 2>(L, stream);
 }

@@ -68,6 +68,12 @@ struct GemmArgs {
   int out_f32;
   int out_f16;  // 16-bit output format: 0 bf16 (MMA operands of later GEMMs), 1 fp16 (residual stream / tensors consumed by norms)
   int res_f16;  // format of the residual tensor
+  // Residual folded into the accumulator (weight-stationary build, fp16 residual): the residual tensor is streamed through the
+  // operand ring as extra K blocks that multiply a 64 x 64 fp16 IDENTITY tile, so `acc += residual` happens on the tensor
+  // pipe and the epilogue never waits for a residual tile (the TMA-prefetched residual arrived late: ncu showed a quarter of
+  // all warp samples of the K = 320 GEMMs on that wait).  Set by gemm_prepare_res_k(); mapA[1] = residual as an A operand,
+  // mapA[2] = the identity tile.
+  int res_k;
   int act;
   int geglu;  // 1: tile columns [0,BN/2) are values, [BN/2,BN) gates; writes BN/2 columns per tile
   // LayerNorm folded into the GEMMs around it (unet.py:314-316 + the Linear that follows, e.g. :337 / :175):
@@ -115,6 +121,9 @@ struct GemmLaunch {
 };
 
 // Host helpers (gemm_tc.cu)
+// If the launch qualifies (see GemmArgs::res_k), encodes L.mapA[1] / L.mapA[2] and sets args.res_k.  Call after the sources,
+// epilogue fields and args.residual / res_ld are final.  Returns false only when a tensor map cannot be encoded.
+bool gemm_prepare_res_k(GemmLaunch& L);
 bool tmap_encode_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
                          uint32_t box_inner, uint32_t box_rows);
 bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,

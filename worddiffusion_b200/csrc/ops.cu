@@ -97,6 +97,8 @@ constexpr int GN_APPLY_R = 16;  // pixel rows in flight per CTA pass (threads = 
 // registers -> one CTA per SM, 31 % occupancy, and the kernel ran latency-bound at 1.3-2.3 TB/s: profiles/r01k.)
 __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNormArgs a) {
   __shared__ float s_mean[128], s_rstd[128];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, slab = blockIdx.y, chunk = blockIdx.z;
   const int Cs = a.Cs, cpg = a.cpg;
   const int nv = Cs >> 3;
@@ -201,8 +203,7 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
   if (nv * R > 640 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
   for (int i = 0; i < nslab; ++i)
     if (!a.partial[i] || a.pslots[i] < 1) return cudaErrorInvalidValue;
-  groupnorm_apply_kernel<<<dim3(B, nslab, a.nchunk), nv * R, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(groupnorm_apply_kernel, dim3(B, nslab, a.nchunk), dim3(nv * R), 0, s, a);
 }
 
 // =====================================================================================================
@@ -393,6 +394,8 @@ __global__ void timestep_embed_kernel(const long long* __restrict__ t_dev, long 
                                       __nv_bfloat16* __restrict__ out, int B, int dim) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
+  pdl_trigger();
+  pdl_wait();
   if (idx >= B * half) return;
   const int b = idx / half, i = idx % half;
   const float t = static_cast<float>(t_dev ? t_dev[b] : t_scalar);
@@ -406,8 +409,7 @@ cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __
                                   cudaStream_t s) {
   if (dim % 2) return cudaErrorInvalidValue;
   const int n = B * (dim / 2);
-  timestep_embed_kernel<<<(n + 255) / 256, 256, 0, s>>>(t_dev, t_scalar, out, B, dim);
-  return cudaGetLastError();
+  return launch_pdl(timestep_embed_kernel, dim3((n + 255) / 256), dim3(256), 0, s, t_dev, t_scalar, out, B, dim);
 }
 
 // =====================================================================================================
@@ -423,6 +425,8 @@ __global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __rest
                                                              int B, int H, int W) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(B) * H * W * 16;
+  pdl_trigger();
+  pdl_wait();
   if (idx >= total) return;
   const int chunk = idx & 15;
   const size_t m = idx >> 4;
@@ -455,8 +459,7 @@ __global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __rest
 
 cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W * 16;
-  conv_in_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, out, B, H, W);
-  return cudaGetLastError();
+  return launch_pdl(conv_in_im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, x, out, B, H, W);
 }
 
 // =====================================================================================================
@@ -465,6 +468,8 @@ cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nv) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(B) * 4 * H * W * nv;
+  pdl_trigger();
+  pdl_wait();
   if (idx >= total) return;
   const int v = idx % nv;
   size_t p = idx / nv;
@@ -477,9 +482,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
-  return cudaGetLastError();
+  return launch_pdl(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s,
+                    reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
 }
 
 // =====================================================================================================
