@@ -194,3 +194,36 @@ def test_philox_noise_moments_and_shard_invariance(unet):
     eng.sampler_step(x, 5, big["y"], 1, [0.0, 0.0, 1.0, 0.0], philox_seed=123, step_index=9)
     assert abs(float(x.mean())) < 0.02 and abs(float(x.std()) - 1.0) < 0.02
     assert abs(float((x ** 4).mean()) - 3.0) < 0.15
+
+
+def test_context_cache_and_weight_updates(unet):
+    """forward() re-encodes the conditioning only when the context tensor object / its in-place version changes, and
+    re-packs the weights when a parameter changes (the cached parameter list must not hide either)."""
+    m, sd = unet
+    inp = _cuda(W.make_inputs(3, seed=77))
+    ctx = inp["context"].clone()
+
+    def run(c):
+        with torch.no_grad():
+            return m(inp["x"], None, timesteps=inp["t"], context=c, y=inp["y"]).clone()
+    e1 = run(ctx)
+    e2 = run(ctx)                      # same object, same version: cached conditioning
+    assert torch.equal(e1, e2)
+    ctx2 = ctx.clone()
+    ctx2[:, 0] = (ctx2[:, 0] % 50) + 1
+    e3 = run(ctx2)                     # new object
+    assert not torch.equal(e1, e3)
+    ctx.copy_(ctx2)                    # in-place update of the first object bumps its version
+    e4 = run(ctx)
+    assert torch.equal(e3, e4)
+    ref = UO.unet_forward(sd, inp["x"].cpu(), inp["t"].cpu(), ctx2.cpu(), inp["y"].cpu(), variant="unet")
+    assert relerr(e4, ref) < TOL_BF16
+    # a parameter changed in place -> new packed weights -> different output; restoring it restores the output
+    w = m.out[2].bias
+    with torch.no_grad():
+        w.add_(1.0)
+    e5 = run(ctx)
+    assert float((e5 - e4).mean()) > 0.5
+    with torch.no_grad():
+        w.sub_(1.0)
+    assert torch.allclose(run(ctx), e4, atol=1e-5)

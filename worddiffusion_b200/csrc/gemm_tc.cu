@@ -26,7 +26,7 @@ WD_DEVINL unsigned long long gtimer() {
 // shared memory (loaded once), works on ONE n-tile for all its m-tiles, and the ring only streams A (16 KB per K block).
 // For K = 320 this halves the L2->SM operand traffic (100 KB of weights were re-streamed for every 80 KB of activations),
 // which is what bounds the 1x1 / Linear GEMMs of the transformer blocks (the per-SM TMA ingest rate, see gemm_pair.cu).
-template <int BN, int STAGES_, int NSTG_, int WSK_ = 0, int ATT_ = 0, int RESK_ = 0>
+template <int BN, int STAGES_, int NSTG_, int WSK_ = 0, int ATT_ = 0, int RESK_ = 0, int GRP_ = 0>
 struct Cfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int NSTG = NSTG_;  // staging buffers per column half (0: the epilogue writes global memory directly)
@@ -42,19 +42,20 @@ struct Cfg {
   static constexpr int HALF_STG_BYTES = 2 * SUB_BYTES;             // 80 columns of one column half
   static constexpr int STG_BYTES = 2 * NSTG * HALF_STG_BYTES;
   // per-warp bias / row-bias vector of its 80 accumulator columns (+ a second one, the LayerNorm column sums, in WS mode)
-  static constexpr int VEC_BYTES = (WSK ? 2 : 1) * GEMM_EPI_WARPS * 80 * 4;
+  // (GRP: a warp handles both column halves of its tiles -> 160 entries per vector)
+  static constexpr int VEC_BYTES = (WSK ? 2 : 1) * GEMM_EPI_WARPS * 80 * 4 * (GRP_ ? 2 : 1);
   // fused context attention: bf16 K and V rows [16][ATT_KP] of the tile's sample, one (K, V) pair per column half (= head)
   static constexpr int KV_BYTES = ATT_ ? 2 * 2 * 16 * ATT_KP * 2 : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + VEC_BYTES + KV_BYTES + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK, int ATT, int RESK>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK, int ATT, int RESK, int GRP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                const GemmArgs args) {
-  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK, GRP>;
   constexpr int NB = NSTG > 0 ? NSTG : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -97,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], EPI_ACTIVE_WARPS);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], GRP ? 4 : EPI_ACTIVE_WARPS);  // one arrival per epilogue warp that drains the buffer
     }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full_bar[i], 1);
     mbar_init(bres_bar, 1);
@@ -247,7 +248,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int row = q * 32 + lane;
     int it = 0;
 
-    if constexpr (EPI == EPI_SAMPLER) {
+    if constexpr (GRP) {
+      // ============ GEGLU projection, alternating warp groups (weight-stationary build, LayerNorm-consuming or plain) ============
+      // The per-tile epilogue is a serial chain (accumulator ready -> TMEM drain -> GELU arithmetic -> staging -> TMA store,
+      // ~4000 cycles, tools/gemm_trace.py) while the MMAs of a 128 x 160 x 320 tile take ~3000: with all eight warps on every
+      // tile the chain bounded the launch.  Here warps 2-5 take the even tiles of the CTA and warps 6-9 the odd ones (TMEM
+      // buffer = group), each warp draining BOTH column halves of its rows in two passes, so two chains are in flight.
+      const int grp = half;
+      constexpr int HC = BN / 2;
+      uint8_t* const stg_g = stg + grp * C::HALF_STG_BYTES;  // [2 sub-tiles][128][40]: 80 output columns of the group's tile
+      float* const wv = vecs + (warp - 2) * 160;
+      float* const wv2 = vecs + GEMM_EPI_WARPS * 160 + (warp - 2) * 160;
+      const bool ln_consume = args.ln_stats != nullptr;
+      const int bar_id = 1 + grp;
+      const bool leader_warp = (q == 0);
+      for (int tile = blockIdx.x + grp * gridDim.x, itg = grp; tile < total_tiles; tile += 2 * gridDim.x, itg += 2) {
+        const int n_tile = tile % n_tiles;
+        const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
+        const int n0 = n_tile * BN;
+        const int m = m0 + row;
+        const bool valid = m < args.M;
+        if (itg == grp) {  // the CTA keeps its n-tile (weight-stationary) and there is no row-bias: one vector for all tiles
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const int c = lane + 32 * i;  // pass p = c / 80: values 40 p + [0, 40), then their gates (+80)
+            const int pp = c / 80, cc = c % 80;
+            const int col = n0 + pp * 40 + (cc < 40 ? cc : cc - 40 + HC);
+            wv[c] = args.bias ? __ldg(args.bias + col) : 0.f;
+            wv2[c] = ln_consume ? __ldg(args.ln_s + col) : 0.f;
+          }
+          __syncwarp();
+        }
+        float ln_rstd = 1.f, ln_rstd_mu = 0.f;
+        if (ln_consume && valid) {
+          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m) * args.ln_slots;
+          float S = 0.f, Q = 0.f;
+          for (int i = 0; i < args.ln_slots; ++i) {
+            const float2 t = __ldg(st + i);
+            S += t.x;
+            Q += t.y;
+          }
+          const float inv = 1.0f / static_cast<float>(args.ln_dim);
+          const float mu = S * inv;
+          ln_rstd = rsqrtf(fmaxf(Q * inv - mu * mu, 0.f) + args.ln_eps);
+          ln_rstd_mu = ln_rstd * mu;
+        }
+        mbar_wait(&tmem_full_bar[grp], (itg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + grp * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+        // the group's previous TMA store (two tiles ago) has read the staging buffer
+        if (leader_warp) {
+          if (elect_one()) bulk_wait_group_read<0>();
+        }
+        named_barrier_sync(bar_id, 128);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          uint32_t v[HC];
+          tmem_ld_32x32b_x16p(t_row + p * 40, v);
+          tmem_ld_32x32b_x16p(t_row + p * 40 + 16, v + 16);
+          tmem_ld_32x32b_x8(t_row + p * 40 + 32, v + 32);
+          tmem_ld_32x32b_x16p(t_row + HC + p * 40, v + 40);
+          tmem_ld_32x32b_x16p(t_row + HC + p * 40 + 16, v + 56);
+          tmem_ld_32x32b_x8(t_row + HC + p * 40 + 32, v + 72);
+          tmem_ld_wait();
+          if (p == 1) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[grp]);
+          }
+          uint8_t* const srow = stg_g + p * C::SUB_BYTES + row * (GEMM_SUB_N * 2);
+          if (ln_consume) epi_geglu40<true>(v, wv + p * 80, wv + p * 80 + 40, srow, wv2 + p * 80, wv2 + p * 80 + 40, ln_rstd, ln_rstd_mu);
+          else epi_geglu40<false>(v, wv + p * 80, wv + p * 80 + 40, srow);
+        }
+        fence_proxy_async();
+        named_barrier_sync(bar_id, 128);
+        if (leader_warp && elect_one()) {
+          tma_store_2d(&mapOut, stg_g, n_tile * HC, m0);
+          tma_store_2d(&mapOut, stg_g + C::SUB_BYTES, n_tile * HC + GEMM_SUB_N, m0);
+          bulk_commit_group();
+        }
+      }
+      if (leader_warp) {
+        if (elect_one()) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
+      }
+    } else if constexpr (EPI == EPI_SAMPLER) {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const int m = (tile / n_tiles) * GEMM_BLOCK_M + row;
@@ -606,14 +690,14 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0, int ATT = 0, int RESK = 0>
+template <int BN, int EPI, int STAGES, int NSTG, int WSK = 0, int ATT = 0, int RESK = 0, int GRP = 0>
 static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK>;
+  using C = Cfg<BN, STAGES, NSTG, WSK, ATT, RESK, GRP>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
@@ -627,7 +711,7 @@ static cudaError_t launch_impl(const GemmLaunch& L, cudaStream_t stream) {
     if (n_tiles > num_sms()) return cudaErrorInvalidValue;
     grid = (grid / n_tiles) * n_tiles;
   }
-  return launch_pdl(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, L.mapA[0],
+  return launch_pdl(gemm_tc_kernel<BN, EPI, STAGES, NSTG, WSK, ATT, RESK, GRP>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, L.mapA[0],
                     L.mapA[1], L.mapA[2], L.mapB, L.mapOut, L.mapRes, a);
 }
 
@@ -650,6 +734,14 @@ static const void* gemm_identity_f16() {
   return ident[dev];
 }
 
+static bool gemm_grp_enabled() {  // env WD_GEMM_GRP (default on): alternating epilogue warp groups for the GEGLU projection
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GEMM_GRP");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 static bool gemm_res_k_enabled() {  // env WD_GEMM_RESK (default on)
   static int v = -1;
   if (v < 0) {
@@ -777,6 +869,7 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
   if ((gemm_ws_enabled() || a.ln_stats) && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms()) {
     if (a.res_k) return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 0, 1>(L, stream);  // + residual as identity K blocks
+    if (a.geglu && !a.rowbias && gemm_grp_enabled()) return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 0, 0, 1>(L, stream);
     return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1, 5>(L, stream);  // weight-stationary short-K GEMM
   }
   if (a.res_k) return cudaErrorInvalidValue;

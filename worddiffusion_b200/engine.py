@@ -94,6 +94,14 @@ class HotPathEngine:
     def encode_context(self, context, phosc=None):
         """context: int64 [B, L] token ids; phosc: [B, 769] (any numeric dtype) or None."""
         B, L = context.shape
+        # The conditioning is time-invariant: a sampling loop passes the SAME tensor objects at every step (train.py:221-236),
+        # and re-encoding them is pure waste.  The key holds the tensors themselves (their storage cannot be recycled while
+        # cached) and their in-place version counters; a new tensor object, even with equal contents, is encoded again.
+        key = (context, context._version, phosc, None if phosc is None else phosc._version, B)
+        old = self._ctx_key
+        if (isinstance(old, tuple) and old[0] is context and old[1] == key[1] and old[2] is phosc and old[3] == key[3]
+                and old[4] == B and not getattr(self, "_ctx_dirty", False)):
+            return
         ctx = context.to(device=self.device, dtype=torch.int64).contiguous()
         ph = None
         if self.cfg.phosc_len > 0:
@@ -105,7 +113,8 @@ class HotPathEngine:
         with torch.cuda.device(self.device):
             check(lib().wd_encode_context(self._h, B, _ptr(ctx), L, _ptr(ph), _stream_ptr()), "wd_encode_context")
         self._ctx_hold = (ctx, ph)
-        self._ctx_key = B
+        self._ctx_key = key
+        self._ctx_dirty = False
 
     def unet_eval(self, x, timesteps, y, out=None):
         B = x.shape[0]
@@ -148,6 +157,7 @@ class HotPathEngine:
         return ns.value, [(self.OP_KINDS[kinds[i]], fl[i], by[i], ms[i]) for i in range(n)]
 
     def reserve(self, batch):
+        self._ctx_key = None
         with torch.cuda.device(self.device):
             check(lib().wd_engine_reserve(self._h, batch), "wd_engine_reserve")
 

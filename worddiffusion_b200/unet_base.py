@@ -113,11 +113,34 @@ class UNetBase(nn.Module):
                 num_classes=self.num_classes, max_seq_len=self.max_seq_len, latent_hw=latent_hw,
                 add_label_emb=self._add_label_emb(), phosc_len=self._phosc_len(), device=device)
             self._engine_sig = None
-        sig = HotPathEngine.weights_signature(self.named_parameters())
+        sig = self._weights_signature()
         if sig != self._engine_sig:
             self._engine.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
             self._engine_sig = sig
         return self._engine
+
+    def _weights_signature(self):
+        """(data_ptr, version) of every parameter: re-pack the engine's bf16 weights when any of them changed.  Walking the
+        module tree costs ~0.5 ms per call (264 parameters), more than the host side of a whole denoising step, so the
+        parameter list is cached; `_apply` (.to / .cuda / .float), `load_state_dict` and every 256th call rebuild it (a
+        Parameter OBJECT replaced by hand is picked up then; call `invalidate_engine()` to force it)."""
+        self._sig_calls = getattr(self, "_sig_calls", 0) + 1
+        plist = getattr(self, "_param_cache", None)
+        if plist is None or (self._sig_calls & 255) == 0:
+            plist = self._param_cache = list(self.parameters())
+        return HotPathEngine.weights_signature((None, p) for p in plist)
+
+    def invalidate_engine(self):
+        self._param_cache = None
+        self._engine_sig = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._param_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._param_cache = None
+        return super().load_state_dict(*args, **kwargs)
 
     def train_engine(self, device=None):
         """The B200 training engine (forward + hand-written backward) bound to this module's parameters."""
