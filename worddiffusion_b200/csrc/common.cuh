@@ -169,6 +169,17 @@ WD_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copies (no tensor map): global -> shared with mbarrier completion, shared -> global as a bulk group.
+// Addresses and sizes are multiples of 16 bytes.
+WD_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+WD_DEVINL void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
 WD_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N>

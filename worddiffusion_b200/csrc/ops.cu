@@ -2,6 +2,7 @@
 // ([B, H*W, C] == token-major), statistics and accumulators are fp32.
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace wd {
@@ -187,6 +188,166 @@ __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNorm
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Bulk-copy variant (the one the engine launches): persistent CTAs (two per SM), each walking a contiguous range of work
+// items = GNB_P pixel rows of one (sample, source tensor).  The rows of an item are contiguous in global memory (row stride
+// == channels), so ONE thread fetches each 20 KB item with cp.async.bulk into a 4-stage shared-memory ring, three items
+// ahead; the rows are normalised in place in shared memory and leave through bulk stores (one per item, or one per row when
+// the output interleaves two sources).  Loads of later items and stores of earlier ones overlap the arithmetic of the
+// current one, ~120 KB of loads are in flight per SM, and no registers are spent on staging.  (The register-staged kernel
+// above held 40 KB per SM and ran at 2.4 TB/s; a one-item-per-CTA bulk version moved its loads and stores in lockstep
+// waves and reached 2.7 TB/s: profiles/.)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GNB_P = 32;      // pixel rows per work item
+constexpr int GNB_R = 8;       // rows per pass (threads = Cs/8 * GNB_R)
+constexpr int GNB_STAGES = 4;
+
+// one 16-byte vector (8 channels): y = x * sc + sh (packed fp32 FMAs), SiLU as y / (1 + 2^(-y log2 e)) with packed adds /
+// multiplies: ~5.5 instructions per element.  (The first version spent ~20 per element -- run-time format / activation
+// switches inside the loop, scalar arithmetic -- and ncu showed the launch issue-bound at half the HBM rate: 53 % issue
+// slots, 49 % XU pipe at 3.2 TB/s.)
+template <bool SILU, bool XF16>
+WD_DEVINL uint4 gn_vec8(const uint4 v, const float2 (&sc2)[4], const float2 (&sh2)[4]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = XF16 ? unpack_f16x2(u[j]) : unpack_bf16x2(u[j]);
+    float2 y = __ffma2_rn(f, sc2[j], sh2[j]);
+    if constexpr (SILU) {
+      const float2 z = __fmul2_rn(y, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+      float2 e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(z.x));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(z.y));
+      const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+      float2 r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+      y = __fmul2_rn(y, r);
+    }
+    o[j] = pack_bf16x2(y.x, y.y);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(512, 2) groupnorm_apply_bulk_kernel(const GroupNormArgs a, int nslab, int n_items, int per_cta) {
+  extern __shared__ __align__(128) uint8_t gnb_smem[];
+  __shared__ float s_mean[128], s_rstd[128];
+  __shared__ __align__(8) uint64_t bars[GNB_STAGES];
+  const int Cs = a.Cs, cpg = a.cpg;
+  const int nv = Cs >> 3;
+  const int col = threadIdx.x % nv, rl = threadIdx.x / nv;
+  const int R = blockDim.x / nv;
+  const int merge = cpg / a.pcpg;
+  const int PG = Cs / a.pcpg;
+  const int ng = Cs / cpg;
+  const uint32_t row_bytes = static_cast<uint32_t>(Cs) * 2;
+  const uint32_t item_bytes = GNB_P * row_bytes;
+  const int first = blockIdx.x * per_cta;
+  const int last = min(first + per_cta, n_items);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GNB_STAGES; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  pdl_trigger();
+  pdl_wait();  // x and its statistics come from the previous kernel; our output may still be read by an earlier one
+  __syncthreads();
+  auto issue_load = [&](int item, int stage) {  // item -> (sample, slab, chunk); its rows are contiguous
+    const int chunk = item % a.nchunk, bs = item / a.nchunk;
+    const int slab = bs % nslab, b = bs / nslab;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.x[slab] + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * GNB_P) * Cs);
+    mbar_arrive_expect_tx(&bars[stage], item_bytes);
+    bulk_load_1d(gnb_smem + stage * item_bytes, src, item_bytes, &bars[stage]);
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GNB_STAGES - 1 && first + i < last; ++i) issue_load(first + i, i);
+  }
+  float2 sc2[4], sh2[4];
+  int cur_bs = -1;
+  for (int item = first, k = 0; item < last; ++item, ++k) {
+    const int chunk = item % a.nchunk, bs = item / a.nchunk;
+    const int slab = bs % nslab, b = bs / nslab;
+    if (bs != cur_bs) {
+      cur_bs = bs;
+      __syncthreads();  // everybody has formed scale/shift from the previous (sample, slab) statistics
+      // one thread per group folds the partial sums in a fixed order (bit-reproducible), then everybody forms scale/shift
+      if (static_cast<int>(threadIdx.x) < ng) {
+        const int slots = a.pslots[slab];
+        const float2* part = reinterpret_cast<const float2*>(a.partial[slab]) +
+                             (static_cast<size_t>(b) * PG + static_cast<size_t>(threadIdx.x) * merge) * slots;
+        float S = 0.f, Q = 0.f;
+        const int n = merge * slots;
+        for (int i = 0; i < n; ++i) {
+          const float2 t = __ldg(part + i);
+          S += t.x;
+          Q += t.y;
+        }
+        const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
+        const float mean = S * inv_n;
+        const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+      }
+      __syncthreads();
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + slab * Cs) + col * 2);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + slab * Cs) + col * 2 + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + slab * Cs) + col * 2);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + slab * Cs) + col * 2 + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g0i = (col * 8 + 2 * j) / cpg, g1i = (col * 8 + 2 * j + 1) / cpg;
+        sc2[j] = make_float2(s_rstd[g0i] * gm[2 * j], s_rstd[g1i] * gm[2 * j + 1]);
+        sh2[j] = make_float2(be[2 * j] - s_mean[g0i] * sc2[j].x, be[2 * j + 1] - s_mean[g1i] * sc2[j].y);
+      }
+    }
+    const int stage = k % GNB_STAGES;
+    const bool xf16 = a.x_f16[slab] != 0;
+    uint8_t* const sbase = gnb_smem + stage * item_bytes;
+    mbar_wait(&bars[stage], (k / GNB_STAGES) & 1);  // the item has landed
+    if (xf16) {
+      for (int p = rl; p < GNB_P; p += R) {
+        uint4* sp = reinterpret_cast<uint4*>(sbase + p * row_bytes) + col;
+        *sp = gn_vec8<SILU, true>(*sp, sc2, sh2);
+      }
+    } else {
+      for (int p = rl; p < GNB_P; p += R) {
+        uint4* sp = reinterpret_cast<uint4*>(sbase + p * row_bytes) + col;
+        *sp = gn_vec8<SILU, false>(*sp, sc2, sh2);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __nv_bfloat16* ob = a.out + (static_cast<size_t>(b) * a.HW + static_cast<size_t>(chunk) * GNB_P) * a.out_ld + slab * Cs;
+      if (a.out_ld == Cs) {
+        bulk_store_1d(ob, sbase, item_bytes);
+      } else {
+        for (int r = 0; r < GNB_P; ++r) bulk_store_1d(ob + static_cast<size_t>(r) * a.out_ld, sbase + r * row_bytes, row_bytes);
+      }
+      bulk_commit_group();
+      const int nxt = item + GNB_STAGES - 1;
+      if (nxt < last) {
+        bulk_wait_group_read<1>();  // the ring slot of item k+3 held item k-1: its store (the group before this one) has read it
+        issue_load(nxt, (k + GNB_STAGES - 1) % GNB_STAGES);
+      }
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_group_read<0>();  // shared memory must outlive the last stores' reads
+}
+
+static bool groupnorm_bulk_enabled() {  // env WD_GN_BULK (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GN_BULK");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 int groupnorm_apply_chunks(int HW) {
   // 8 pixel rows per thread (four passes of 2 independent 16-byte loads) when the image is large enough: finer chunks
   // (more CTAs, each repeating the statistics preamble) measured slower (profiles/)
@@ -198,6 +359,32 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
   const int nv = a.Cs / 8;
   if (a.Cs % 8 || a.Cs % a.cpg || a.cpg % a.pcpg || a.Cs / a.cpg > 128 || a.nchunk < 1 || a.HW % a.nchunk)
     return cudaErrorInvalidValue;
+  // bulk-copy kernel: contiguous source rows, whole 32-row items, a ring of <= 100 KB (two CTAs per SM)
+  const size_t ring = static_cast<size_t>(GNB_STAGES) * GNB_P * a.Cs * 2;
+  bool bulk = groupnorm_bulk_enabled() && a.HW % GNB_P == 0 && nv * GNB_R <= 512 && nv * GNB_R >= a.Cs / a.cpg && ring <= 100 * 1024 &&
+              a.out_ld % 8 == 0;
+  for (int i = 0; i < nslab; ++i) bulk = bulk && a.x_ld[i] == a.Cs && a.partial[i] && a.pslots[i] >= 1;
+  if (bulk) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    static int sms = 148;
+    std::call_once(once, [] {
+      attr_err = cudaFuncSetAttribute(groupnorm_apply_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(groupnorm_apply_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    GroupNormArgs a2 = a;
+    a2.nchunk = a.HW / GNB_P;
+    const int n_items = B * nslab * a2.nchunk;
+    const int per = (n_items + 2 * sms - 1) / (2 * sms);  // contiguous items per CTA: consecutive chunks share their statistics
+    const int grid = (n_items + per - 1) / per;
+    if (a.silu) return launch_pdl(groupnorm_apply_bulk_kernel<true>, dim3(grid), dim3(nv * GNB_R), ring, s, a2, nslab, n_items, per);
+    return launch_pdl(groupnorm_apply_bulk_kernel<false>, dim3(grid), dim3(nv * GNB_R), ring, s, a2, nslab, n_items, per);
+  }
   int R = GN_APPLY_R;
   while (R > 1 && nv * R > 640) R >>= 1;
   if (nv * R > 640 || nv * R < a.Cs / a.cpg) return cudaErrorInvalidValue;
