@@ -199,6 +199,11 @@ struct wd_engine {
   bool pe_set = false;
   int n_kv = 0;
   std::vector<GemmW*> kv_weights;  // per K/V buffer: the fused [to_k; to_v] weight
+  int kv_fused_count = 0;          // kv_fused() calls (counted by the dry layout pass): their weights share one pool, so the
+  bf16* kv_pool = nullptr;         //   K/V projections of ALL cross-attentions run as a single GEMM per trajectory
+  int kv_pool_next = 0;
+  // CharacterEncoder folded into lookup tables (finalize_params): T* = E W^T + b [vocab, D], P* = pe W^T [max_seq_len, D]
+  float *we_tq = nullptr, *we_tk = nullptr, *we_tv = nullptr, *we_pq = nullptr, *we_pk = nullptr, *we_pv = nullptr;
   std::vector<LnFold> ln_folds;
   // activations
   char* abase = nullptr;
@@ -308,7 +313,16 @@ struct Builder {
     GemmW g;
     g.N = 2 * inner;
     g.K = ctx_dim;
-    g.w = A.alloc<bf16>(static_cast<size_t>(g.N) * g.K);
+    const size_t elems = static_cast<size_t>(g.N) * g.K;
+    if ((elems * sizeof(bf16)) % 1024 != 0) {
+      g.w = A.alloc<bf16>(elems);
+    } else if (dry) {
+      ++e->kv_fused_count;
+      g.w = A.alloc<bf16>(elems);
+    } else {  // one contiguous pool in call order (same bytes as the dry pass: every slice is a whole number of 1 KB units)
+      if (!e->kv_pool) e->kv_pool = A.alloc<bf16>(elems * e->kv_fused_count);
+      g.w = e->kv_pool + elems * e->kv_pool_next++;
+    }
     slot(pfx + ".to_k.weight", S_LIN, g.w, static_cast<int64_t>(inner) * ctx_dim, inner, ctx_dim, ctx_dim, 0, 0, 0);
     slot(pfx + ".to_v.weight", S_LIN, g.w, static_cast<int64_t>(inner) * ctx_dim, inner, ctx_dim, ctx_dim, 0, inner, 0);
     return g;
@@ -403,6 +417,12 @@ struct Builder {
     e->we_kb = A.alloc<float>(D);
     e->we_vb = A.alloc<float>(D);
     e->we_pe = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
+    e->we_tq = A.alloc<float>(static_cast<size_t>(c.vocab_size) * D);
+    e->we_tk = A.alloc<float>(static_cast<size_t>(c.vocab_size) * D);
+    e->we_tv = A.alloc<float>(static_cast<size_t>(c.vocab_size) * D);
+    e->we_pq = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
+    e->we_pk = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
+    e->we_pv = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
     slot("word_emb.attention.linear_query.weight", S_F32, e->we_qw, static_cast<int64_t>(D) * D);
     slot("word_emb.attention.linear_query.bias", S_F32, e->we_qb, D);
     slot("word_emb.attention.linear_key.weight", S_F32, e->we_kw, static_cast<int64_t>(D) * D);
@@ -663,6 +683,22 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
     fail(WD_ERR_STATE, "%d parameters not loaded (first: %s)", missing, first.c_str());
     return missing;
   }
+  {
+    // CharacterEncoder (unet.py:839-882): q/k/v = Linear(E[token] + pe[position]) = (E W^T + b)[token] + (pe W^T)[position].  The
+    // inputs come from a finite vocabulary x position set, so the three fp32 Linears over [B, L, D] become two small tables
+    // each, built here once per weight load; per trajectory only a gather + add remains (the Linears were 180 of the 250 us
+    // the context encoding took at batch 256).
+    const wd_config& c = e->cfg;
+    const int D = c.context_dim;
+    const float* Ws[3] = {e->we_qw, e->we_kw, e->we_vw};
+    const float* bs[3] = {e->we_qb, e->we_kb, e->we_vb};
+    float* Ts[3] = {e->we_tq, e->we_tk, e->we_tv};
+    float* Ps[3] = {e->we_pq, e->we_pk, e->we_pv};
+    for (int i = 0; i < 3; ++i) {
+      CUDA_TRY(linear_f32_launch(e->we_E, Ws[i], bs[i], Ts[i], c.vocab_size, D, D, s));
+      CUDA_TRY(linear_f32_launch(e->we_pe, Ws[i], nullptr, Ps[i], c.max_seq_len, D, D, s));
+    }
+  }
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
   for (auto& r : e->res) {
@@ -717,6 +753,7 @@ struct PlanBuilder {
   bool dry;
   int B;
   std::string err;
+  int kv_ld = 0;  // row stride of the K/V buffers when all of them come from one pooled GEMM (0: each buffer is [.., 2C])
 
   Act new_act(int H, int W, int C, bool f16 = false) {
     Act a{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W, nullptr, 0, f16};
@@ -978,9 +1015,9 @@ struct PlanBuilder {
     }
     return en && dh == 80 && Ltot >= 1 && Ltot <= GEMM_ATT_MAXL && HW % GEMM_BLOCK_M == 0;
   }
-  static void set_ctx_attn(Epi& ep, const bf16* kvbuf, int C, int Ltot, int HW, int dh) {
+  static void set_ctx_attn(Epi& ep, const bf16* kvbuf, int C, int Ltot, int HW, int dh, int kv_ld) {
     ep.att_kv = kvbuf;
-    ep.att_ld = 2 * C;
+    ep.att_ld = kv_ld ? kv_ld : 2 * C;
     ep.att_voff = C;
     ep.att_L = Ltot;
     ep.att_scale = 1.0f / sqrtf(static_cast<float>(dh));
@@ -1029,14 +1066,14 @@ struct PlanBuilder {
         if (fuse_ctx_attn(HW, Ltot, s.dh)) {
           ep.out = o.p;
           ep.out_ld = C;
-          set_ctx_attn(ep, kv[t.kv1], C, Ltot, HW, s.dh);
+          set_ctx_attn(ep, kv[t.kv1], C, Ltot, HW, s.dh, kv_ld);
           if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
         } else {
           bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
           ep.out = q;
           ep.out_ld = C;
           if (!gemm_op(ops, M, false, 0, 0, {ASrc{x.p, C, C, 1, 1, H, W, true}}, t.a1_q, ep)) return false;
-          attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+          attn_op(ops, q, C, kv[t.kv1], kv[t.kv1] + C, kv_ld ? kv_ld : 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
         }
       }
       {
@@ -1060,14 +1097,14 @@ struct PlanBuilder {
         if (fuse_ctx_attn(HW, Ltot, s.dh)) {
           ep.out = o.p;
           ep.out_ld = C;
-          set_ctx_attn(ep, kv[t.kv2], C, Ltot, HW, s.dh);
+          set_ctx_attn(ep, kv[t.kv2], C, Ltot, HW, s.dh, kv_ld);
           if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
         } else {
           bf16* q = A.alloc<bf16>(static_cast<size_t>(M) * C);
           ep.out = q;
           ep.out_ld = C;
           if (!gemm_op(ops, M, false, 0, 0, {ASrc{x1.p, C, C, 1, 1, H, W, true}}, t.a2_q, ep)) return false;
-          attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
+          attn_op(ops, q, C, kv[t.kv2], kv[t.kv2] + C, kv_ld ? kv_ld : 2 * C, o.p, C, HW, Ltot, s.heads, s.dh);
         }
         Epi ep2;
         ep2.out = x2.p;
@@ -1132,27 +1169,22 @@ struct PlanBuilder {
       for (int seg = 0; seg < nseg; ++seg) {
         const int Ls = seg == 0 ? L : c.phosc_len;
         const int row_off = seg == 0 ? 0 : L;
-        float* emb = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         float* q = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         float* k = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         float* v = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         // unet.py:872 always adds the PE; unetPhosc.py:726-729 only when the sequence fits max_seq_len
         const int add_pe = (c.variant == WD_VARIANT_UNET) ? 1 : (Ls <= c.max_seq_len ? 1 : 0);
         if (add_pe && Ls > c.max_seq_len) { err = "context longer than max_seq_len"; return false; }
-        Op op;
-        memset(&op, 0, sizeof(op));
-        op.kind = OP_EMBED;
-        op.emb = {seg, e->we_E, c.vocab_size, e->we_pe, add_pe, emb, B, Ls, D};
-        cops.push_back(op);
-        const float* Ws[3] = {e->we_qw, e->we_kw, e->we_vw};
-        const float* bs[3] = {e->we_qb, e->we_kb, e->we_vb};
+        // q / k / v of Word_Attention straight from the folded tables (wd_engine_finalize_params): gather + add
+        const float* Ts[3] = {e->we_tq, e->we_tk, e->we_tv};
+        const float* Ps[3] = {e->we_pq, e->we_pk, e->we_pv};
         float* outs[3] = {q, k, v};
         for (int i = 0; i < 3; ++i) {
-          Op lo;
-          memset(&lo, 0, sizeof(lo));
-          lo.kind = OP_LINF32;
-          lo.lin = {emb, Ws[i], bs[i], outs[i], B * Ls, D, D};
-          cops.push_back(lo);
+          Op op;
+          memset(&op, 0, sizeof(op));
+          op.kind = OP_EMBED;
+          op.emb = {seg, Ts[i], c.vocab_size, Ps[i], add_pe, outs[i], B, Ls, D};
+          cops.push_back(op);
         }
         Op wa;
         memset(&wa, 0, sizeof(wa));
@@ -1162,13 +1194,36 @@ struct PlanBuilder {
       }
     }
     std::vector<bf16*> kv(e->n_kv, nullptr);
+    kv_ld = 0;
+    bool pooled = e->n_kv > 0;
     for (int i = 0; i < e->n_kv; ++i) {
       const GemmW& w = *e->kv_weights[i];
-      kv[i] = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * w.N);
+      const GemmW& w0 = *e->kv_weights[0];
+      pooled = pooled && !w.bias && w.N == w0.N && w.K == w0.K && w.w == w0.w + static_cast<size_t>(i) * w0.N * w0.K;
+    }
+    if (pooled) {
+      // the [to_k; to_v] weights of every cross-attention are contiguous: ONE GEMM [B*Ltot, D] x [n_kv*2C, D]^T per trajectory
+      const GemmW& w0 = *e->kv_weights[0];
+      GemmW wall;
+      wall.w = w0.w;
+      wall.N = w0.N * e->n_kv;
+      wall.K = w0.K;
+      kv_ld = wall.N;
+      bf16* all = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * wall.N);
+      for (int i = 0; i < e->n_kv; ++i) kv[i] = all + static_cast<size_t>(i) * w0.N;
       Epi ep;
-      ep.out = kv[i];
-      ep.out_ld = w.N;
-      if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, w, ep)) return false;
+      ep.out = all;
+      ep.out_ld = wall.N;
+      if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, wall, ep)) return false;
+    } else {
+      for (int i = 0; i < e->n_kv; ++i) {
+        const GemmW& w = *e->kv_weights[i];
+        kv[i] = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * w.N);
+        Epi ep;
+        ep.out = kv[i];
+        ep.out_ld = w.N;
+        if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, w, ep)) return false;
+      }
     }
 
     // ================= per-step =================
