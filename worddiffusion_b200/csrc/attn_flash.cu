@@ -288,6 +288,10 @@ __global__ void __launch_bounds__(128) attn_ctx_kernel(const AttnFlashArgs a) {
 
 cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s) {
   if (a.Sq < 1 || a.Skv < 1 || a.q_ld % 8 || a.kv_ld % 8 || a.out_ld % 2) return cudaErrorInvalidValue;
+  {
+    cudaError_t tc_err = cudaSuccess;
+    if (attn_tc_try_launch(a, B, s, &tc_err)) return tc_err;  // tcgen05 kernel for the long key sequences
+  }
   dim3 grid((a.Sq + BQ - 1) / BQ, a.heads, B);
   const int C = a.heads * DH;
   const size_t ctx_smem = static_cast<size_t>(64 + 32) * (C + 8) * 2;

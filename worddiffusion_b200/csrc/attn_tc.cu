@@ -1,0 +1,319 @@
+// Fused attention on the 5th-gen tensor cores (tcgen05 + TMEM) for d_head = 80: softmax(q k^T * d^-0.5) v
+// (reference unetPhosc.py:176-196).  Used for the 256 x 256 / 64 x 64 self-attention of UNetModelPhosc and for its
+// cross-attention over the 779-token char + PHOSC context.  The score matrix never reaches HBM (the reference materialises
+// [B*4, Sq, Skv] fp32).  The mma.sync flash kernel (attn_flash.cu) ran these launches at 96 TFLOP/s, 45 % of the unetPhosc step.
+//
+// One CTA = (128 query rows, head, sample); two CTAs per SM (112 KB of shared memory, 256 TMEM columns each), 192 threads:
+//   warp 0     TMA producer: Q once, then K tiles (pass 1) and K + V tiles (pass 2) of 64 keys through a 2-stage ring.  Every
+//              operand tile is a pair of SWIZZLE_128B boxes of 64 channels starting at the head's first channel: the second box
+//              over-fetches 48 channels of the next head (zero-filled past the tensor's last column), only its first 16 are used.
+//   warp 1     TMEM allocation + single-thread MMA issue.
+//                S = Q K^T : 128 x 64 x 16, five K steps (four in box 0, one in box 1), both operands K-major.
+//                O += P V  : 128 x 80 x 16, four K steps of 16 keys; P is K-major (written by the softmax warps), V is consumed
+//                            as an MN-major operand straight from its [key][channel] boxes (descriptor LBO = box pitch).
+//   warps 2-5  softmax, one query row per thread (= TMEM lane).  TWO PASSES over the keys instead of an online softmax: pass 1
+//              only reduces the row maximum of the scores, pass 2 recomputes S, forms P = exp2(scale log2e (S - max)) as bf16 in
+//              a swizzled shared-memory tile and accumulates the row sum.  O is therefore never rescaled in TMEM (an online
+//              softmax needs a tcgen05.ld / st round trip of the 128 x 80 accumulator whenever a maximum moves); the price is a
+//              second QK^T, which the tensor pipe has room for: the MUFU exponentials, not the MMAs, bound this kernel.
+//              S is double-buffered in TMEM, so QK^T of tile j+1 overlaps the exponentials of tile j.
+// Keys beyond Skv are zero-filled by TMA (3-D maps: channel, row, sample) and masked to -inf; query rows beyond Sq are
+// computed on zero-filled operands and not stored.
+#include "ops.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace wd {
+
+bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride_elems,
+                         uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows);  // gemm_tc.cu
+
+namespace {
+constexpr int AT_DH = 80;
+constexpr int AT_BM = 128;  // query rows per CTA
+constexpr int AT_BK = 64;   // keys per tile
+constexpr int AT_THREADS = 192;
+constexpr int AT_Q_BYTES = 2 * AT_BM * 128;   // two 64-channel boxes
+constexpr int AT_KV_BOX = AT_BK * 128;        // one 64-channel box of 64 keys
+constexpr int AT_STAGE_BYTES = 4 * AT_KV_BOX;  // K box0, K box1, V box0, V box1
+constexpr int AT_STAGES = 2;
+constexpr int AT_P_BYTES = AT_BM * 128;        // [128 rows][64 keys] bf16, K-major SWIZZLE_128B
+constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_P_BYTES + 256;  // 112.25 KB: two CTAs per SM
+constexpr int AT_TMEM_COLS = 256;  // S0 [0,64), S1 [64,128), O [128,208)
+
+struct AttnTcArgs {
+  __nv_bfloat16* out;
+  int out_ld;
+  int Sq, Skv, heads;
+  float sl2;  // scale * log2(e)
+};
+
+// MN-major SWIZZLE_128B operand made of [64 channel x 64 row] boxes (same encoding as wgrad_tc.cu): LBO = box pitch
+WD_DEVINL uint64_t at_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(AT_KV_BOX >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+WD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+               const __grid_constant__ CUtensorMap mapV, const AttnTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + AT_Q_BYTES;
+  uint8_t* sP = sKV + AT_STAGES * AT_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_empty = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;      // 1
+  uint64_t* p_empty = bars + 10;    // 1
+  uint64_t* o_full = bars + 11;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (a.Skv + AT_BK - 1) / AT_BK;
+  const int c_head = h * AT_DH;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      tma_load_3d(sQ, &mapQ, q_full, c_head, q0, b);
+      tma_load_3d(sQ + AT_BM * 128, &mapQ, q_full, c_head + 64, q0, b);
+      int u = 0;  // ring use counter over both passes
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < ntiles; ++j, ++u) {
+          const int st = u & 1;
+          mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1);
+          uint8_t* sK = sKV + st * AT_STAGE_BYTES;
+          mbar_arrive_expect_tx(&kv_full[st], pass == 0 ? 2 * AT_KV_BOX : 4 * AT_KV_BOX);
+          tma_load_3d(sK, &mapK, &kv_full[st], c_head, j * AT_BK, b);
+          tma_load_3d(sK + AT_KV_BOX, &mapK, &kv_full[st], c_head + 64, j * AT_BK, b);
+          if (pass == 1) {
+            tma_load_3d(sK + 2 * AT_KV_BOX, &mapV, &kv_full[st], c_head, j * AT_BK, b);
+            tma_load_3d(sK + 3 * AT_KV_BOX, &mapV, &kv_full[st], c_head + 64, j * AT_BK, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(AT_BM, AT_BK);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32(AT_BM, AT_DH) | (1u << 16);  // B (= V) is MN-major
+      const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ));
+      const uint64_t q_desc1 = make_smem_desc_sw128(smem_u32(sQ + AT_BM * 128));
+      const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP));
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      auto issue_qk = [&](int u) {  // u = ring / score-buffer use counter
+        const int st = u & 1;
+        mbar_wait(&kv_full[st], (u >> 1) & 1);
+        mbar_wait(&s_empty[st], ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + st * AT_STAGE_BYTES);
+        const uint64_t k_desc0 = make_smem_desc_sw128(k_addr);
+        const uint64_t k_desc1 = make_smem_desc_sw128(k_addr + AT_KV_BOX);
+        const uint32_t d_tmem = tmem_base + st * AT_BK;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, q_desc0 + 2 * k, k_desc0 + 2 * k, idesc_qk, k != 0);
+        umma_f16_ss(d_tmem, q_desc1, k_desc1, idesc_qk, 1u);
+        umma_commit(&s_full[st]);
+      };
+      int u = 0;
+      // ---- pass 1: scores only (row maxima) ----
+      for (int j = 0; j < ntiles; ++j, ++u) {
+        issue_qk(u);
+        umma_commit(&kv_empty[u & 1]);  // the K tile is free once these MMAs retire
+      }
+      // ---- pass 2: S(j+1) is issued ahead of P(j) V(j) ----
+      issue_qk(u);
+      for (int j = 0; j < ntiles; ++j, ++u) {
+        if (j + 1 < ntiles) issue_qk(u + 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + (u & 1) * AT_STAGE_BYTES + 2 * AT_KV_BOX);
+        const uint64_t v_desc = at_desc_mn_sw128(v_addr);
+#pragma unroll
+        for (int k = 0; k < AT_BK / 16; ++k)
+          umma_f16_ss(tmem_base + 2 * AT_BK, p_desc + 2 * k, v_desc + 128 * k, idesc_pv, (j | k) != 0);
+        umma_commit(&kv_empty[u & 1]);
+        umma_commit(p_empty);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // =========================== softmax warps (one query row per thread) ===========================
+    const int qd = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(qd * 32) << 16;
+    int u = 0;
+    // ---- pass 1: row maximum of the raw scores ----
+    float mx = -INFINITY;
+    for (int j = 0; j < ntiles; ++j, ++u) {
+      const int st = u & 1;
+      mbar_wait(&s_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld_32x32b_x32(tmem_base + t_lane + st * AT_BK + half * 32, v);
+        tmem_ld_wait();
+        const int key0 = j * AT_BK + half * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (key0 + c < a.Skv) mx = fmaxf(mx, __uint_as_float(v[c]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+    }
+    const float mxs = mx * a.sl2;
+    // ---- pass 2: P = exp2(sl2 S - max) -> bf16 swizzled tile, row sums ----
+    float l = 0.f;
+    uint8_t* const prow = sP + row * 128;
+    for (int j = 0; j < ntiles; ++j, ++u) {
+      const int st = u & 1;
+      mbar_wait(&s_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      uint32_t pk[32];  // 64 probabilities as bf16 pairs
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + t_lane + st * AT_BK + half * 32, v);
+        tmem_ld_wait();
+        const int key0 = j * AT_BK + half * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(v[c]), a.sl2, -mxs));
+          float p1 = exp2f(fmaf(__uint_as_float(v[c + 1]), a.sl2, -mxs));
+          if (key0 + c >= a.Skv) p0 = 0.f;
+          if (key0 + c + 1 >= a.Skv) p1 = 0.f;
+          l += p0 + p1;
+          pk[half * 16 + c / 2] = pack_bf16x2(p0, p1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);  // the score buffer may be overwritten by S(j+2)
+      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);  // P(j-1) V(j-1) has read the tile
+      // K-major SWIZZLE_128B: 16-byte chunk c16 of row r lives at chunk (c16 ^ (r & 7))
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16)
+        *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- O / l -> bf16 -> global ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int q = q0 + row;
+    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.Sq + q) * a.out_ld + c_head;
+#pragma unroll
+    for (int cb = 0; cb < AT_DH / 16; ++cb) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + t_lane + 2 * AT_BK + cb * 16, v);
+      tmem_ld_wait();
+      if (q < a.Sq) {
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+        o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+        o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+        o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+        reinterpret_cast<uint4*>(orow + cb * 16)[0] = o0;
+        reinterpret_cast<uint4*>(orow + cb * 16)[1] = o1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<AT_TMEM_COLS>(tmem_base);
+}
+
+bool attn_tc_enabled() {  // env WD_ATTN_TC (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_ATTN_TC");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+}  // namespace
+
+// true if the launch was taken (err holds its status); false -> the caller falls back to the mma.sync kernel
+bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError_t* err) {
+  const int C = a.heads * AT_DH;
+  if (!attn_tc_enabled() || a.Skv <= 16 || a.q_ld % 8 || a.kv_ld % 8 || a.out_ld % 8 ||
+      (reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
+       reinterpret_cast<uintptr_t>(a.out)) % 16)
+    return false;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) { *err = attr_err; return true; }
+  CUtensorMap mq, mk, mv;
+  // inner extent = the C channels of this operand (the over-fetching second box of the last head is zero-filled beyond it)
+  if (!tmap_encode_3d_bf16(&mq, a.q, C, a.Sq, B, a.q_ld, static_cast<uint64_t>(a.Sq) * a.q_ld, 64, AT_BM) ||
+      !tmap_encode_3d_bf16(&mk, a.k, C, a.Skv, B, a.kv_ld, static_cast<uint64_t>(a.Skv) * a.kv_ld, 64, AT_BK) ||
+      !tmap_encode_3d_bf16(&mv, a.v, C, a.Skv, B, a.kv_ld, static_cast<uint64_t>(a.Skv) * a.kv_ld, 64, AT_BK)) {
+    *err = cudaErrorInvalidValue;
+    return true;
+  }
+  AttnTcArgs ta{a.out, a.out_ld, a.Sq, a.Skv, a.heads, a.scale * 1.4426950408889634f};
+  *err = launch_pdl(attn_tc_kernel, dim3((a.Sq + AT_BM - 1) / AT_BM, a.heads, B), dim3(AT_THREADS), AT_SMEM_BYTES, s, mq, mk, mv, ta);
+  return true;
+}
+
+}  // namespace wd

@@ -665,6 +665,21 @@ bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride_elems,
+                         uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(3d) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
 bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return false;

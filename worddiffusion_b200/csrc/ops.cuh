@@ -73,6 +73,8 @@ struct AttnFlashArgs {
   float scale;
 };
 cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s);
+// tcgen05 attention (attn_tc.cu), Skv > 16: returns false when it does not take the launch (the mma.sync kernel runs instead)
+bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError_t* err);
 
 // ---------------- sinusoidal timestep embedding (unet.py:96-116) ----------------
 // t_dev: per-sample int64 timesteps, or null -> every row uses t_scalar.  out bf16 [B, dim]
