@@ -228,8 +228,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const int key0 = j * AT_BK + half * 32;
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[c]), a.sl2, -mxs));
-          float p1 = exp2f(fmaf(__uint_as_float(v[c + 1]), a.sl2, -mxs));
+          float p0, p1;  // MUFU.EX2 directly: the arguments are <= 0, no range fix-up is needed
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[c]), a.sl2, -mxs)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[c + 1]), a.sl2, -mxs)));
           if (key0 + c >= a.Skv) p0 = 0.f;
           if (key0 + c + 1 >= a.Skv) p1 = 0.f;
           l += p0 + p1;
