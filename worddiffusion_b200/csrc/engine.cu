@@ -204,6 +204,7 @@ struct wd_engine {
   int kv_pool_next = 0;
   // CharacterEncoder folded into lookup tables (finalize_params): T* = E W^T + b [vocab, D], P* = pe W^T [max_seq_len, D]
   float *we_tq = nullptr, *we_tk = nullptr, *we_tv = nullptr, *we_pq = nullptr, *we_pk = nullptr, *we_pv = nullptr;
+  float* we_gram = nullptr;  // TQ TK^T [vocab, vocab]: the scores of a position-free Word_Attention segment (ops.cu: word_attn_hist_kernel)
   std::vector<LnFold> ln_folds;
   // activations
   char* abase = nullptr;
@@ -423,6 +424,7 @@ struct Builder {
     e->we_pq = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
     e->we_pk = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
     e->we_pv = A.alloc<float>(static_cast<size_t>(c.max_seq_len) * D);
+    e->we_gram = A.alloc<float>(static_cast<size_t>(c.vocab_size) * c.vocab_size);
     slot("word_emb.attention.linear_query.weight", S_F32, e->we_qw, static_cast<int64_t>(D) * D);
     slot("word_emb.attention.linear_query.bias", S_F32, e->we_qb, D);
     slot("word_emb.attention.linear_key.weight", S_F32, e->we_kw, static_cast<int64_t>(D) * D);
@@ -698,6 +700,7 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
       CUDA_TRY(linear_f32_launch(e->we_E, Ws[i], bs[i], Ts[i], c.vocab_size, D, D, s));
       CUDA_TRY(linear_f32_launch(e->we_pe, Ws[i], nullptr, Ps[i], c.max_seq_len, D, D, s));
     }
+    CUDA_TRY(word_attn_gram_launch(e->we_tq, e->we_tk, e->we_gram, c.vocab_size, D, s));
   }
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
@@ -1169,12 +1172,23 @@ struct PlanBuilder {
       for (int seg = 0; seg < nseg; ++seg) {
         const int Ls = seg == 0 ? L : c.phosc_len;
         const int row_off = seg == 0 ? 0 : L;
-        float* q = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
-        float* k = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
-        float* v = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         // unet.py:872 always adds the PE; unetPhosc.py:726-729 only when the sequence fits max_seq_len
         const int add_pe = (c.variant == WD_VARIANT_UNET) ? 1 : (Ls <= c.max_seq_len ? 1 : 0);
         if (add_pe && Ls > c.max_seq_len) { err = "context longer than max_seq_len"; return false; }
+        if (!add_pe) {
+          // no positional term: the attention output depends only on each token's value and the sample's token histogram
+          Op wh;
+          memset(&wh, 0, sizeof(wh));
+          wh.kind = OP_WORDATTN;
+          wh.wa = {nullptr, nullptr, nullptr, ctx, B, Ls, D, Ltot, row_off};
+          wh.emb.which = seg;  // which token tensor (0: characters, 1: PHOSC)
+          wh.flops = 1;        // marks the histogram form
+          cops.push_back(wh);
+          continue;
+        }
+        float* q = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        float* k = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
+        float* v = A.alloc<float>(static_cast<size_t>(B) * Ls * D);
         // q / k / v of Word_Attention straight from the folded tables (wd_engine_finalize_params): gather + add
         const float* Ts[3] = {e->we_tq, e->we_tk, e->we_tv};
         const float* Ps[3] = {e->we_pq, e->we_pk, e->we_pv};
@@ -1509,6 +1523,13 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
         err = linear_f32_launch(op.lin.x, op.lin.W, op.lin.b, op.lin.out, op.lin.M, op.lin.N, op.lin.K, s);
         break;
       case OP_WORDATTN:
+        if (op.wa.q == nullptr) {  // histogram form (position-free segment)
+          const void* toks = op.emb.which == 0 ? static_cast<const void*>(rc.ctx_tokens) : static_cast<const void*>(rc.phosc);
+          if (!toks) return fail(WD_ERR_INVALID, "phoscLabels are required by this model");
+          err = word_attn_hist_launch(toks, op.emb.which == 0 ? 1 : 0, e->we_gram, e->we_tv, e->cfg.vocab_size, op.wa.ctx, op.wa.B, op.wa.L,
+                                      op.wa.D, op.wa.Ltot, op.wa.row_off, s);
+          break;
+        }
         err = word_attn_launch(op.wa.q, op.wa.k, op.wa.v, op.wa.ctx, nullptr, op.wa.B, op.wa.L, op.wa.D, op.wa.Ltot,
                                op.wa.row_off, s);
         break;

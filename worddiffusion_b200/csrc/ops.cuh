@@ -114,6 +114,10 @@ cudaError_t embed_tokens_launch(const void* tokens, int tokens_are_i64, const fl
 cudaError_t linear_f32_launch(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
                               cudaStream_t s);
 // unscaled single-head softmax(Q K^T) V, fp32; writes bf16 ctx rows [b, row_off + l, :] of a [B, Ltot, D] tensor
+// position-free segments (no positional encoding): histogram form, see ops.cu
+cudaError_t word_attn_hist_launch(const void* tokens, int tokens_are_i64, const float* G, const float* TV, int vocab,
+                                  __nv_bfloat16* ctx_out, int B, int L, int D, int Ltot, int row_off, cudaStream_t s);
+cudaError_t word_attn_gram_launch(const float* TQ, const float* TK, float* G, int vocab, int D, cudaStream_t s);
 cudaError_t word_attn_launch(const float* q, const float* k, const float* v, __nv_bfloat16* ctx_out, float* ctx_out_f32,
                              int B, int L, int D, int Ltot, int row_off, cudaStream_t s);
 
