@@ -115,6 +115,13 @@ int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scalar, const i
                     const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index,
                     float* eps_out, void* stream);
 
+/* The sampler update alone, with a predicted noise the caller kept: the reference's production generator evaluates the UNet only at
+ * some steps and re-uses the last eps in between (regenerateFromtrain2.py:536,615-618).  Same fp32 arithmetic and op order as the
+ * fused epilogue of wd_sampler_step.  x, eps, noise: fp32 [batch, elems_per_latent] device tensors; coef4_host / mode / noise /
+ * Philox arguments as in wd_sampler_step. */
+int wd_sampler_update(float* x, const float* eps, int batch, int elems_per_latent, int mode, const float* coef4_host,
+                      const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index, void* stream);
+
 /* ---- single operators (used by the parity tests; same kernels as the engine) -------------------------- */
 /* GroupNorm32(+SiLU) (unet.py:429-431,592-596): x,out bf16 NHWC [B,HW,C] */
 int wd_op_groupnorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta, int B, int HW, int C,

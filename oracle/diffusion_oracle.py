@@ -52,3 +52,28 @@ class DiffusionOracle:
         a_p = ah[t_prev] if t_prev >= 0 else torch.tensor(1.0, dtype=torch.float64)
         x0 = (x.double() - torch.sqrt(1 - a_t) * eps.double()) / torch.sqrt(a_t)
         return (torch.sqrt(a_p) * x0 + torch.sqrt(1 - a_p) * eps.double()).float()
+
+    # ---- reduced-call ("stale eps") sampler of the reference's production generator ----
+    @staticmethod
+    def reduced_call_predicate(i, noise_steps):
+        """regenerateFromtrain2.py:536 with fullSampling = 0: the UNet is evaluated when
+        ``i % 100 == 0 or i % 5 == 0 or i == T or i == T - 1`` (the epoch-dependent terms select multiples of 25 / 15 / 10,
+        all multiples of 5 already; ``epoch>50==0`` is a chained comparison that is always False); every other step
+        re-uses the last predicted noise."""
+        return i % 100 == 0 or i % 5 == 0 or i == noise_steps or i == noise_steps - 1
+
+    def reduced_call_sample(self, eps_fn, x_T):
+        """regenerateFromtrain2.py:520-618, fullSampling = 0: stale predicted noise between evaluations and the NOISE-FREE
+        update ``x <- 1/sqrt(a) (x - (1-a)/sqrt(1-ah) eps)`` (:615-618).  Returns (x_0, list of evaluated timesteps)."""
+        x = x_T.clone()
+        eps = None
+        called = []
+        for i in reversed(range(1, self.noise_steps)):
+            t = (torch.ones(x.shape[0]) * i).long()
+            if self.reduced_call_predicate(i, self.noise_steps):
+                eps = eps_fn(x, t)
+                called.append(i)
+            alpha = self.alpha[t][:, None, None, None]
+            alpha_hat = self.alpha_hat[t][:, None, None, None]
+            x = 1 / torch.sqrt(alpha) * (x - ((1 - alpha) / (torch.sqrt(1 - alpha_hat))) * eps)
+        return x, called

@@ -227,3 +227,19 @@ def test_context_cache_and_weight_updates(unet):
     with torch.no_grad():
         w.sub_(1.0)
     assert torch.allclose(run(ctx), e4, atol=1e-5)
+
+
+def test_reduced_call_sampler_vs_reference_golden(unet, golden_dir):
+    """The reference's production generator (stale eps, noise-free update; regenerateFromtrain2.py:520-618): UNet evaluations at
+    i = 11, 10, 5 of a T = 12 schedule, eight elementwise wd_sampler_update steps in between."""
+    m, _ = unet
+    g = np.load(os.path.join(golden_dir, "unet_reduced_T12.npz"))
+    inp = _cuda(W.make_inputs(2, seed=SEED))
+    d = Diffusion(noise_steps=12, device=DEV)
+    x, trace = d.sample_latents_reduced(m, inp["context"], inp["y"], x_T=torch.from_numpy(g["x_T"]), return_eps_trace=True)
+    assert [i for i, _ in trace] == list(g["called"])
+    for k, (_, e) in enumerate(trace):
+        assert relerr(e, torch.from_numpy(g["eps_steps"][k])) < TOL_BF16
+    err = relerr(x, torch.from_numpy(g["x_final"]))
+    print("reduced-call final latent err", err)
+    assert err < 2e-2

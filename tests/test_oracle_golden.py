@@ -168,3 +168,18 @@ def test_ema_oracle_semantics():
     assert torch.equal(ema, p)
     TO.ema_update(ema, p * 3, 2000)     # afterwards: old * beta + (1 - beta) * new (train.py:156-159)
     assert torch.allclose(ema, p * 0.995 + 0.005 * p * 3)
+
+
+def test_reduced_call_sampler_matches_reference_loop(golden_dir, unet_sd):
+    """regenerateFromtrain2.py:520-618 (fullSampling = 0): stale predicted noise between evaluations, noise-free update.
+    Fixture: literal transcription of that loop around the UNMODIFIED reference UNet (oracle/make_golden_reduced.py), T = 12."""
+    g = np.load(os.path.join(golden_dir, "unet_reduced_T12.npz"))
+    inp = W.make_inputs(2, seed=1234)
+    d = DiffusionOracle(noise_steps=12)
+    assert [i for i in reversed(range(1, 12)) if d.reduced_call_predicate(i, 12)] == list(g["called"]) == [11, 10, 5]
+
+    def eps_fn(x, t):
+        return UO.unet_forward(unet_sd, x, t, inp["context"], inp["y"], variant="unet")
+    x, called = d.reduced_call_sample(eps_fn, torch.from_numpy(g["x_T"]))
+    assert called == [11, 10, 5]
+    assert float((x - torch.from_numpy(g["x_final"])).abs().max()) < 1e-4

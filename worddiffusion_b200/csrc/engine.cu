@@ -1656,6 +1656,18 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
 // ----------------------------------------------------------------------------------------------
 // C ABI: single operators (parity tests)
 // ----------------------------------------------------------------------------------------------
+extern "C" int wd_sampler_update(float* x, const float* eps, int batch, int elems_per_latent, int mode, const float* coef4_host,
+                                 const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index,
+                                 void* stream) {
+  if (!x || !eps || !coef4_host || batch < 1 || elems_per_latent < 1) return fail(WD_ERR_INVALID, "sampler_update: null / empty argument");
+  if (mode != WD_STEP_DDPM && mode != WD_STEP_DDIM) return fail(WD_ERR_INVALID, "sampler_update: mode must be WD_STEP_DDPM or WD_STEP_DDIM");
+  const float4 coef = make_float4(coef4_host[0], coef4_host[1], coef4_host[2], coef4_host[3]);
+  CUDA_TRY(sampler_update_launch(x, eps, noise, use_philox, seed, sample_offset * static_cast<uint64_t>(elems_per_latent), step_index, coef,
+                                 mode == WD_STEP_DDPM ? STEP_DDPM : STEP_DDIM, static_cast<size_t>(batch) * elems_per_latent,
+                                 static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
 extern "C" int wd_op_groupnorm(const void* x, void* out, const float* gamma, const float* beta, int B, int HW, int C,
                                int groups, float eps, int silu, void* stream) {
   if (C % groups) return fail(WD_ERR_INVALID, "C %% groups");

@@ -650,6 +650,40 @@ cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int
 }
 
 // =====================================================================================================
+// Stand-alone sampler update for steps that re-use a predicted noise (the reference's reduced-call generator,
+// regenerateFromtrain2.py:536,615-618): the same fp32 arithmetic, in the same order, as the fused epilogue of the output
+// convolution (gemm_tc.cu, EPI_SAMPLER).  x, eps, noise: fp32 NCHW, elementwise.
+// =====================================================================================================
+__global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                                      int use_philox, unsigned long long seed, unsigned long long elem_offset, int step_index,
+                                      float4 coef, int mode, size_t n) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  if (idx >= n) return;
+  const float e = eps[idx];
+  const float xv = x[idx];
+  if (mode == STEP_DDPM) {
+    float z = 0.f;
+    if (noise)
+      z = __ldg(noise + idx);
+    else if (use_philox)
+      z = philox_normal(seed, elem_offset + idx, static_cast<uint32_t>(step_index));
+    const float inner = __fsub_rn(xv, __fmul_rn(coef.y, e));
+    x[idx] = __fadd_rn(__fmul_rn(coef.x, inner), __fmul_rn(coef.z, z));
+  } else if (mode == STEP_DDIM) {
+    const float x0 = __fmul_rn(__fsub_rn(xv, __fmul_rn(coef.y, e)), coef.x);
+    x[idx] = __fadd_rn(__fmul_rn(coef.z, x0), __fmul_rn(coef.w, e));
+  }
+}
+cudaError_t sampler_update_launch(float* x, const float* eps, const float* noise, int use_philox, unsigned long long seed,
+                                  unsigned long long elem_offset, int step_index, float4 coef, int mode, size_t n, cudaStream_t s) {
+  if (mode != STEP_DDPM && mode != STEP_DDIM) return cudaErrorInvalidValue;
+  return launch_pdl(sampler_update_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s, x, eps, noise, use_philox, seed,
+                    elem_offset, step_index, coef, mode, n);
+}
+
+// =====================================================================================================
 // nearest 2x upsample, NHWC bf16
 // =====================================================================================================
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nv) {

@@ -76,6 +76,10 @@ cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s);
 // tcgen05 attention (attn_tc.cu), Skv > 16: returns false when it does not take the launch (the mma.sync kernel runs instead)
 bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError_t* err);
 
+// ---------------- sampler update with a given (possibly stale) predicted noise; same arithmetic as the fused epilogue ----------------
+cudaError_t sampler_update_launch(float* x, const float* eps, const float* noise, int use_philox, unsigned long long seed,
+                                  unsigned long long elem_offset, int step_index, float4 coef, int mode, size_t n, cudaStream_t s);
+
 // ---------------- sinusoidal timestep embedding (unet.py:96-116) ----------------
 // t_dev: per-sample int64 timesteps, or null -> every row uses t_scalar.  out bf16 [B, dim]
 cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __nv_bfloat16* out, int B, int dim,

@@ -100,6 +100,43 @@ class Diffusion:
                 on_step(i, x)
         return (x, trace) if return_eps_trace else x
 
+    @staticmethod
+    def reduced_call_predicate(i, noise_steps):
+        """regenerateFromtrain2.py:536 (fullSampling = 0): evaluate the UNet when i % 100 == 0 or i % 5 == 0 or i == T - 1;
+        the epoch-dependent terms of the reference select multiples of 25 / 15 / 10, i.e. multiples of 5 already."""
+        return i % 100 == 0 or i % 5 == 0 or i == noise_steps or i == noise_steps - 1
+
+    @torch.no_grad()
+    def sample_latents_reduced(self, model, context, labels, phosc=None, x_T=None, seed=0, predicate=None,
+                               return_eps_trace=False):
+        """The reference's production generator (regenerateFromtrain2.py:520-618 with fullSampling = 0): the UNet is evaluated
+        only where ``predicate(i, T)`` holds (default: the reference's schedule, ~20 % of the steps), the last predicted noise
+        drives the steps in between, and the update carries no noise term (:615-618).  Evaluated steps run the fused
+        UNet + update launch sequence, the others one elementwise kernel."""
+        n = context.shape[0]
+        eng, y = self._prepare(model, context, labels, phosc, n)
+        h, w = self.img_size[0] // 8, self.img_size[1] // 8
+        if x_T is None:
+            g = torch.Generator(device=self.device).manual_seed(int(seed))
+            x = torch.randn((n, 4, h, w), device=self.device, generator=g)
+        else:
+            x = x_T.to(device=self.device, dtype=torch.float32).clone().contiguous()
+        pred = predicate or self.reduced_call_predicate
+        eps = torch.empty_like(x)
+        have_eps = False
+        trace = [] if return_eps_trace else None
+        for i in reversed(range(1, self.noise_steps)):
+            coef = self._ddpm_coef[i].copy()
+            coef[2] = 0.0  # no noise term
+            if pred(i, self.noise_steps) or not have_eps:
+                eng.sampler_step(x, i, y, STEP_DDPM, coef, step_index=i, eps_out=eps)
+                have_eps = True
+                if return_eps_trace:
+                    trace.append((i, eps.clone()))
+            else:
+                eng.sampler_update(x, eps, STEP_DDPM, coef, step_index=i)
+        return (x, trace) if return_eps_trace else x
+
     def ddim_timesteps(self, num_steps):
         stride = self.noise_steps // num_steps
         return list(range(0, self.noise_steps, stride))[:num_steps][::-1]

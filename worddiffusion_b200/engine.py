@@ -142,6 +142,17 @@ class HotPathEngine:
                                         _stream_ptr()), "wd_sampler_step")
         return x
 
+    def sampler_update(self, x, eps, mode, coef, noise=None, philox_seed=None, sample_offset=0, step_index=0):
+        """x <- update(x, eps) with a predicted noise the caller kept (reduced-call sampling); no UNet evaluation."""
+        B = x.shape[0]
+        c4 = (C.c_float * 4)(*[float(v) for v in coef])
+        use_philox = 1 if (noise is None and philox_seed is not None) else 0
+        with torch.cuda.device(self.device):
+            check(lib().wd_sampler_update(_ptr(x), _ptr(eps), B, x[0].numel(), mode, c4, _ptr(noise), use_philox,
+                                          int(philox_seed or 0), int(sample_offset), int(step_index), _stream_ptr()),
+                  "wd_sampler_update")
+        return x
+
     OP_KINDS = ("timestep_embed", "gemm_tc", "groupnorm", "layernorm", "attn_small", "attn_flash", "conv_in",
                 "groupnorm_stats", "upsample")
 
