@@ -115,6 +115,13 @@ int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scalar, const i
                     const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index,
                     float* eps_out, void* stream);
 
+/* PHOSC labels on the device (reference ResPhoSCNetZSL/modules/utils/phos_generator.py:59-78 + phoc_generator.py:17-90, 'eng'
+ * alphabet; the vector the reference's dataset / generator builds on the host and passes as `phoscLabels`, unetPhosc.py:1068).
+ * words: device bytes [batch, max_len], zero padded, spaces / underscores already removed; out: int32 [batch, 769] (165 PHOS
+ * counts ++ 604 PHOC bits); *bad_flag (device int, zeroed by the caller) becomes non-zero if a word holds a character outside
+ * a-zA-Z, for which the reference raises KeyError. */
+int wd_phosc_tokenize(const unsigned char* words, int batch, int max_len, int32_t* out, int32_t* bad_flag, void* stream);
+
 /* The sampler update alone, with a predicted noise the caller kept: the reference's production generator evaluates the UNet only at
  * some steps and re-uses the last eps in between (regenerateFromtrain2.py:536,615-618).  Same fp32 arithmetic and op order as the
  * fused epilogue of wd_sampler_step.  x, eps, noise: fp32 [batch, elems_per_latent] device tensors; coef4_host / mode / noise /

@@ -243,3 +243,37 @@ def test_reduced_call_sampler_vs_reference_golden(unet, golden_dir):
     err = relerr(x, torch.from_numpy(g["x_final"]))
     print("reduced-call final latent err", err)
     assert err < 2e-2
+
+
+def test_phosc_tokenizer_bit_exact(golden_dir):
+    """wd_phosc_tokenize vs the reference's generator outputs (golden) and vs the oracle on random words (lengths 1..14,
+    mixed case): integer work, bit-exact."""
+    import random
+
+    import phosc_oracle as P
+    from worddiffusion_b200.phosc import phosc_labels
+    g = np.load(os.path.join(golden_dir, "phosc_labels.npz"))
+    words = [str(w) for w in g["words"]]
+    out = phosc_labels(words, DEV).cpu().numpy()
+    assert (out == g["labels"]).all()
+    rng = random.Random(5)
+    rw = ["".join(rng.choice(P.LETTERS) for _ in range(rng.randint(1, 14))) for _ in range(300)] + ["get_ting", "a b"]
+    out = phosc_labels(rw, DEV).cpu().numpy()
+    for w, lab in zip(rw, out):
+        assert (P.phosc(w) == lab).all(), w
+    with pytest.raises(KeyError):
+        phosc_labels(["abc1"], DEV)
+
+
+def test_phosc_tokenizer_feeds_the_model(phosc):
+    """labels from the device tokenizer drive UNetModelPhosc like host-built ones (same eps as the oracle on the same labels)."""
+    import phosc_oracle as P
+    from worddiffusion_b200.phosc import phosc_labels
+    m, sd = phosc
+    inp = _cuda(W.make_inputs(2, seed=31))
+    lab = phosc_labels(["getting", "Stylist"], DEV)
+    with torch.no_grad():
+        eps = m(inp["x"], lab, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+    ref = UO.unet_forward(sd, inp["x"].cpu(), inp["t"].cpu(), inp["context"].cpu(), inp["y"].cpu(), variant="unetPhosc",
+                          phosc=torch.from_numpy(np.stack([P.phosc("getting"), P.phosc("Stylist")])))
+    assert relerr(eps, ref) < TOL_BF16

@@ -183,3 +183,16 @@ def test_reduced_call_sampler_matches_reference_loop(golden_dir, unet_sd):
     x, called = d.reduced_call_sample(eps_fn, torch.from_numpy(g["x_T"]))
     assert called == [11, 10, 5]
     assert float((x - torch.from_numpy(g["x_final"])).abs().max()) < 1e-4
+
+
+def test_phosc_oracle_matches_reference_generators(golden_dir):
+    """PHOS / PHOC pyramids of the reference's own generator functions (oracle/make_golden_phosc.py), bit-exact; the bigram part
+    the reference never sets stays zero."""
+    import phosc_oracle as P
+    g = np.load(os.path.join(golden_dir, "phosc_labels.npz"))
+    assert g["labels"].shape[1] == 769 and int(g["labels"][:, -100:].sum()) == 0
+    for w, lab in zip(g["words"], g["labels"]):
+        assert (P.phosc(str(w)) == lab).all(), str(w)
+    assert P.segments(7)[1:3] == [(0, 3), (3, 7)] and len(P.segments(3)) == 15
+    with pytest.raises(KeyError):
+        P.phosc("abc1")

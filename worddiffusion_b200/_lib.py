@@ -43,6 +43,7 @@ SIGNATURES = {
     "wd_encode_context": (_I, [_P, _I, _P, _I, _P, _P]),
     "wd_unet_eval": (_I, [_P, _I, _P, _P, _I64, _P, _P, _P]),
     "wd_sampler_step": (_I, [_P, _I, _P, _I64, _P, _I, C.POINTER(_F), _P, _I, _U64, _U64, _I, _P, _P]),
+    "wd_phosc_tokenize": (_I, [_P, _I, _I, _P, _P, _P]),
     "wd_sampler_update": (_I, [_P, _P, _I, _I, _I, C.POINTER(_F), _P, _I, _U64, _U64, _I, _P]),
     "wd_op_groupnorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "wd_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),

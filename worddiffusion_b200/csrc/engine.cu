@@ -1656,6 +1656,12 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
 // ----------------------------------------------------------------------------------------------
 // C ABI: single operators (parity tests)
 // ----------------------------------------------------------------------------------------------
+extern "C" int wd_phosc_tokenize(const unsigned char* words, int batch, int max_len, int32_t* out, int32_t* bad_flag, void* stream) {
+  if (!words || !out || !bad_flag) return fail(WD_ERR_INVALID, "phosc_tokenize: null argument");
+  CUDA_TRY(phosc_tokenize_launch(words, batch, max_len, out, bad_flag, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
 extern "C" int wd_sampler_update(float* x, const float* eps, int batch, int elems_per_latent, int mode, const float* coef4_host,
                                  const float* noise, int use_philox, uint64_t seed, uint64_t sample_offset, int step_index,
                                  void* stream) {

@@ -1,6 +1,7 @@
 // HBM-/latency-bound kernels of the WordDiffusion hot path.  All activations are NHWC bf16
 // ([B, H*W, C] == token-major), statistics and accumulators are fp32.
 #include "ops.cuh"
+#include "phosc_table.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -647,6 +648,62 @@ __global__ void __launch_bounds__(256) conv_in_im2col_kernel(const float* __rest
 cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * H * W * 16;
   return launch_pdl(conv_in_im2col_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, x, out, B, H, W);
+}
+
+// =====================================================================================================
+// PHOSC tokenizer (reference ResPhoSCNetZSL/modules/utils/phos_generator.py:59-78, phoc_generator.py:17-90, 'eng'): the step
+// in front of UNetModelPhosc -- words -> [B, 769] integer labels -- as integer work on the device.
+//   out[0,165)   PHOS: 11 shape counts of the whole word and of the segments of its 2..5-way splits (15 segments)
+//   out[165,669) PHOC: 36 presence bits [0-9a-z] of the lower-cased word per segment of the 2..5-way splits (14 segments)
+//   out[669,769) the 2 x 50 bigram bits, which the reference never sets (it looks single characters up in a bigram list)
+// words: [B, max_len] bytes, zero padded (the caller has removed ' ' and '_', trainGWModifyCondition.py:394).  One CTA per word.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) phosc_tokenize_kernel(const unsigned char* __restrict__ words, int max_len,
+                                                             int* __restrict__ out, int* __restrict__ bad) {
+  const unsigned char* w = words + static_cast<size_t>(blockIdx.x) * max_len;
+  int L = 0;
+  while (L < max_len && w[L] != 0) ++L;
+  for (int e = threadIdx.x; e < 769; e += blockDim.x) {
+    int val = 0;
+    if (e < 669) {
+      const bool is_phos = e < 165;
+      const int ee = is_phos ? e : e - 165;
+      const int width = is_phos ? PHOS_SHAPES : 36;
+      int seg = ee / width;
+      const int colx = ee % width;
+      if (!is_phos) ++seg;  // PHOC has no level-1 segment
+      // segment index -> (split, mul): seg 0 = whole word; then splits 2,3,4,5 with 2,3,4,5 segments each
+      int a = 0, b = L;
+      if (seg > 0) {
+        int split = 2, base = 1;
+        while (seg >= base + split) { base += split; ++split; }
+        const int mul = seg - base;
+        const int parts = L / split;
+        a = mul * parts;
+        b = (mul == split - 1) ? L : a + parts;
+      }
+      for (int i = a; i < b; ++i) {
+        const int ch = w[i];
+        if (is_phos) {
+          int li = -1;
+          if (ch >= 'a' && ch <= 'z') li = ch - 'a';
+          else if (ch >= 'A' && ch <= 'Z') li = 26 + ch - 'A';
+          if (li < 0) { atomicOr(bad, 1); continue; }  // the reference raises KeyError for a character outside a-zA-Z
+          val += PHOS_TABLE[li][colx];
+        } else {
+          const int lc = (ch >= 'A' && ch <= 'Z') ? ch - 'A' + 'a' : ch;
+          if (lc >= '0' && lc <= '9') { if (lc - '0' == colx) val = 1; }
+          else if (lc >= 'a' && lc <= 'z') { if (10 + lc - 'a' == colx) val = 1; }
+        }
+      }
+    }
+    out[static_cast<size_t>(blockIdx.x) * 769 + e] = val;
+  }
+}
+cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len, int* out, int* bad_flag, cudaStream_t s) {
+  if (B < 1 || max_len < 1) return cudaErrorInvalidValue;
+  phosc_tokenize_kernel<<<B, 256, 0, s>>>(words, max_len, out, bad_flag);
+  return cudaGetLastError();
 }
 
 // =====================================================================================================

@@ -76,6 +76,9 @@ cudaError_t attn_flash_launch(const AttnFlashArgs& a, int B, cudaStream_t s);
 // tcgen05 attention (attn_tc.cu), Skv > 16: returns false when it does not take the launch (the mma.sync kernel runs instead)
 bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError_t* err);
 
+// ---------------- PHOSC tokenizer: words [B, max_len] zero-padded bytes -> int32 [B, 769]; *bad_flag |= 1 on a non-letter ----------------
+cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len, int* out, int* bad_flag, cudaStream_t s);
+
 // ---------------- sampler update with a given (possibly stale) predicted noise; same arithmetic as the fused epilogue ----------------
 cudaError_t sampler_update_launch(float* x, const float* eps, const float* noise, int use_philox, unsigned long long seed,
                                   unsigned long long elem_offset, int step_index, float4 coef, int mode, size_t n, cudaStream_t s);
