@@ -3,19 +3,22 @@
 // cross-attention over the 779-token char + PHOSC context.  The score matrix never reaches HBM (the reference materialises
 // [B*4, Sq, Skv] fp32).  The mma.sync flash kernel (attn_flash.cu) ran these launches at 96 TFLOP/s, 45 % of the unetPhosc step.
 //
-// One CTA = (128 query rows, head, sample); two CTAs per SM (112 KB of shared memory, 256 TMEM columns each), 192 threads:
-//   warp 0     TMA producer: Q once, then K tiles (pass 1) and K + V tiles (pass 2) of 64 keys through a 2-stage ring.  Every
-//              operand tile is a pair of SWIZZLE_128B boxes of 64 channels starting at the head's first channel: the second box
-//              over-fetches 48 channels of the next head (zero-filled past the tensor's last column), only its first 16 are used.
+// One CTA = (MT x 128 query rows, head, sample).  MT = 2 when a sample's queries come in multiples of 256 (the 8 x 32 level): both
+// query tiles share every K / V tile -- the kernel is bound by L2 -> SM operand traffic, and this halves it -- 8 ring slots,
+// 224 KB of shared memory, one CTA per SM, 320 threads.  MT = 1 otherwise: 4 slots, 112 KB, two CTAs per SM, 192 threads.
+//   warp 0     TMA producer: Q once, then the K tiles (pass 1) and K, V tiles (pass 2) of 64 keys as UNITS through a ring of 16 KB
+//              slots (a K slot is released when its QK^T retires, a V slot after its PV).  Every operand tile is a pair of
+//              SWIZZLE_128B boxes of 64 channels starting at the head's first channel: the second box over-fetches 48 channels of
+//              the next head (zero-filled past the tensor's last column), only its first 16 are used.
 //   warp 1     TMEM allocation + single-thread MMA issue.
 //                S = Q K^T : 128 x 64 x 16, five K steps (four in box 0, one in box 1), both operands K-major.
 //                O += P V  : 128 x 80 x 16, four K steps of 16 keys; P is K-major (written by the softmax warps), V is consumed
 //                            as an MN-major operand straight from its [key][channel] boxes (descriptor LBO = box pitch).
-//   warps 2-5  softmax, one query row per thread (= TMEM lane).  TWO PASSES over the keys instead of an online softmax: pass 1
-//              only reduces the row maximum of the scores, pass 2 recomputes S, forms P = exp2(scale log2e (S - max)) as bf16 in
+//   warps 2..  softmax (four warps per M tile), one query row per thread (= TMEM lane).  TWO PASSES over the keys instead of an
+//              online softmax: pass 1 only reduces the row maximum of the scores, pass 2 recomputes S, forms P = exp2(scale log2e (S - max)) as bf16 in
 //              a swizzled shared-memory tile and accumulates the row sum.  O is therefore never rescaled in TMEM (an online
 //              softmax needs a tcgen05.ld / st round trip of the 128 x 80 accumulator whenever a maximum moves); the price is a
-//              second QK^T, which the tensor pipe has room for: the MUFU exponentials, not the MMAs, bound this kernel.
+//              second QK^T (and a second read of K), which the tensor pipe has room for.
 //              S is double-buffered in TMEM, so QK^T of tile j+1 overlaps the exponentials of tile j.
 // Keys beyond Skv are zero-filled by TMA (3-D maps: channel, row, sample) and masked to -inf; query rows beyond Sq are
 // computed on zero-filled operands and not stored.
@@ -31,16 +34,24 @@ bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint6
 
 namespace {
 constexpr int AT_DH = 80;
-constexpr int AT_BM = 128;  // query rows per CTA
+constexpr int AT_BM = 128;  // query rows per M tile
 constexpr int AT_BK = 64;   // keys per tile
-constexpr int AT_THREADS = 192;
-constexpr int AT_Q_BYTES = 2 * AT_BM * 128;   // two 64-channel boxes
-constexpr int AT_KV_BOX = AT_BK * 128;        // one 64-channel box of 64 keys
-constexpr int AT_STAGE_BYTES = 4 * AT_KV_BOX;  // K box0, K box1, V box0, V box1
-constexpr int AT_STAGES = 2;
-constexpr int AT_P_BYTES = AT_BM * 128;        // [128 rows][64 keys] bf16, K-major SWIZZLE_128B
-constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_P_BYTES + 256;  // 112.25 KB: two CTAs per SM
-constexpr int AT_TMEM_COLS = 256;  // S0 [0,64), S1 [64,128), O [128,208)
+constexpr int AT_KV_BOX = AT_BK * 128;   // one 64-channel box of 64 keys (8 KB)
+constexpr int AT_SLOT_BYTES = 2 * AT_KV_BOX;  // a K tile or a V tile: two boxes (16 KB)
+constexpr int AT_QT_BYTES = 2 * AT_BM * 128;  // Q of one M tile: two 64-channel boxes (32 KB)
+constexpr int AT_PT_BYTES = AT_BM * 128;      // P of one M tile: [128 rows][64 keys] bf16, K-major SWIZZLE_128B (16 KB)
+
+// MT = M tiles (of 128 query rows) per CTA.  MT = 1: 4 ring slots, 112 KB, two CTAs per SM (64-row levels, odd shapes).
+// MT = 2: both query tiles of a 256-token sample share every K / V tile (half the L2 -> SM operand traffic, which is what
+// bounds this kernel), 8 ring slots, 224 KB, one CTA per SM.
+template <int MT>
+struct ATCfg {
+  static constexpr int SLOTS = MT == 1 ? 4 : 8;
+  static constexpr int THREADS = 64 + 128 * MT;
+  static constexpr int SMEM_BYTES = MT * AT_QT_BYTES + SLOTS * AT_SLOT_BYTES + MT * AT_PT_BYTES + 256;
+  static constexpr int TMEM_COLS = MT == 1 ? 256 : 512;  // S[mt][buf] at (2 mt + buf) * 64, O[mt] at 2 MT * 64 + 80 mt
+  static constexpr int O_COL = 2 * MT * AT_BK;
+};
 
 struct AttnTcArgs {
   __nv_bfloat16* out;
@@ -68,28 +79,34 @@ WD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       : "memory");
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// Operand tiles travel through a ring of 16 KB slots as UNITS: pass 1: K(0), K(1), ...; pass 2: K(0), V(0), K(1), V(1), ...
+// Unit w lives in slot w % SLOTS (parity (w / SLOTS) & 1).  A K slot is released as soon as its QK^T has retired, a V slot after
+// its PV -- so in pass 1 SLOTS K tiles are in flight, in pass 2 SLOTS / 2 tiles.
+template <int MT>
+__global__ void __launch_bounds__(ATCfg<MT>::THREADS, MT == 1 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const AttnTcArgs a) {
+  using C = ATCfg<MT>;
+  constexpr int NS = C::SLOTS;
   extern __shared__ __align__(1024) uint8_t at_smem_raw[];
   uint8_t* smem = at_smem_raw;
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + AT_Q_BYTES;
-  uint8_t* sP = sKV + AT_STAGES * AT_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;      // 1
-  uint64_t* p_empty = bars + 10;    // 1
-  uint64_t* o_full = bars + 11;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* sRing = sQ + MT * AT_QT_BYTES;
+  uint8_t* sP = sRing + NS * AT_SLOT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + MT * AT_PT_BYTES);
+  uint64_t* u_full = bars;             // [NS]
+  uint64_t* u_empty = bars + NS;       // [NS]
+  uint64_t* s_full = bars + 2 * NS;    // [2]
+  uint64_t* s_empty = s_full + 2;      // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* q_full = p_empty + 1;
+  uint64_t* o_full = q_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (AT_BM * MT), h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (a.Skv + AT_BK - 1) / AT_BK;
   const int c_head = h * AT_DH;
 
@@ -97,19 +114,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&u_full[i], 1);
+      mbar_init(&u_empty[i], 1);
     }
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4 * MT);
+    }
+    mbar_init(p_full, 4 * MT);
     mbar_init(p_empty, 1);
+    mbar_init(q_full, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,23 +139,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_3d(sQ, &mapQ, q_full, c_head, q0, b);
-      tma_load_3d(sQ + AT_BM * 128, &mapQ, q_full, c_head + 64, q0, b);
-      int u = 0;  // ring use counter over both passes
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < ntiles; ++j, ++u) {
-          const int st = u & 1;
-          mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1);
-          uint8_t* sK = sKV + st * AT_STAGE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[st], pass == 0 ? 2 * AT_KV_BOX : 4 * AT_KV_BOX);
-          tma_load_3d(sK, &mapK, &kv_full[st], c_head, j * AT_BK, b);
-          tma_load_3d(sK + AT_KV_BOX, &mapK, &kv_full[st], c_head + 64, j * AT_BK, b);
-          if (pass == 1) {
-            tma_load_3d(sK + 2 * AT_KV_BOX, &mapV, &kv_full[st], c_head, j * AT_BK, b);
-            tma_load_3d(sK + 3 * AT_KV_BOX, &mapV, &kv_full[st], c_head + 64, j * AT_BK, b);
-          }
-        }
+      mbar_arrive_expect_tx(q_full, MT * AT_QT_BYTES);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        tma_load_3d(sQ + mt * AT_QT_BYTES, &mapQ, q_full, c_head, q0 + mt * AT_BM, b);
+        tma_load_3d(sQ + mt * AT_QT_BYTES + AT_BM * 128, &mapQ, q_full, c_head + 64, q0 + mt * AT_BM, b);
+      }
+      const int units = 3 * ntiles;
+      for (int w = 0; w < units; ++w) {
+        const int sl = w % NS;
+        // unit -> (operand, key tile): pass 1 holds K(w); pass 2 alternates K(j), V(j)
+        const bool is_v = w >= ntiles && ((w - ntiles) & 1);
+        const int j = w < ntiles ? w : (w - ntiles) >> 1;
+        mbar_wait(&u_empty[sl], ((w / NS) & 1) ^ 1);
+        uint8_t* dst = sRing + sl * AT_SLOT_BYTES;
+        mbar_arrive_expect_tx(&u_full[sl], AT_SLOT_BYTES);
+        const CUtensorMap* mp = is_v ? &mapV : &mapK;
+        tma_load_3d(dst, mp, &u_full[sl], c_head, j * AT_BK, b);
+        tma_load_3d(dst + AT_KV_BOX, mp, &u_full[sl], c_head + 64, j * AT_BK, b);
       }
     }
   } else if (warp == 1) {
@@ -144,63 +164,70 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16_f32(AT_BM, AT_BK);
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(AT_BM, AT_DH) | (1u << 16);  // B (= V) is MN-major
-      const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ));
-      const uint64_t q_desc1 = make_smem_desc_sw128(smem_u32(sQ + AT_BM * 128));
-      const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP));
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_qk = [&](int u) {  // u = ring / score-buffer use counter
-        const int st = u & 1;
-        mbar_wait(&kv_full[st], (u >> 1) & 1);
-        mbar_wait(&s_empty[st], ((u >> 1) & 1) ^ 1);
+      // QK^T of score-buffer use `u` (tile counter over both passes) from the K tile in ring unit `w`
+      auto issue_qk = [&](int u, int w) {
+        const int buf = u & 1, sl = w % NS;
+        mbar_wait(&u_full[sl], (w / NS) & 1);
+        mbar_wait(&s_empty[buf], ((u >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + st * AT_STAGE_BYTES);
+        const uint32_t k_addr = smem_u32(sRing + sl * AT_SLOT_BYTES);
         const uint64_t k_desc0 = make_smem_desc_sw128(k_addr);
         const uint64_t k_desc1 = make_smem_desc_sw128(k_addr + AT_KV_BOX);
-        const uint32_t d_tmem = tmem_base + st * AT_BK;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, q_desc0 + 2 * k, k_desc0 + 2 * k, idesc_qk, k != 0);
-        umma_f16_ss(d_tmem, q_desc1, k_desc1, idesc_qk, 1u);
-        umma_commit(&s_full[st]);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES));
+          const uint64_t q_desc1 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES + AT_BM * 128));
+          const uint32_t d_tmem = tmem_base + (2 * mt + buf) * AT_BK;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, q_desc0 + 2 * k, k_desc0 + 2 * k, idesc_qk, k != 0);
+          umma_f16_ss(d_tmem, q_desc1, k_desc1, idesc_qk, 1u);
+        }
+        umma_commit(&s_full[buf]);
+        umma_commit(&u_empty[sl]);  // the K tile is free once these MMAs retire
       };
       int u = 0;
       // ---- pass 1: scores only (row maxima) ----
-      for (int j = 0; j < ntiles; ++j, ++u) {
-        issue_qk(u);
-        umma_commit(&kv_empty[u & 1]);  // the K tile is free once these MMAs retire
-      }
+      for (int j = 0; j < ntiles; ++j, ++u) issue_qk(u, j);
       // ---- pass 2: S(j+1) is issued ahead of P(j) V(j) ----
-      issue_qk(u);
+      issue_qk(u, ntiles);
       for (int j = 0; j < ntiles; ++j, ++u) {
-        if (j + 1 < ntiles) issue_qk(u + 1);
+        if (j + 1 < ntiles) issue_qk(u + 1, ntiles + 2 * (j + 1));
+        const int wv = ntiles + 2 * j + 1, sl = wv % NS;
+        mbar_wait(&u_full[sl], (wv / NS) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + (u & 1) * AT_STAGE_BYTES + 2 * AT_KV_BOX);
-        const uint64_t v_desc = at_desc_mn_sw128(v_addr);
+        const uint64_t v_desc = at_desc_mn_sw128(smem_u32(sRing + sl * AT_SLOT_BYTES));
 #pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k)
-          umma_f16_ss(tmem_base + 2 * AT_BK, p_desc + 2 * k, v_desc + 128 * k, idesc_pv, (j | k) != 0);
-        umma_commit(&kv_empty[u & 1]);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP + mt * AT_PT_BYTES));
+#pragma unroll
+          for (int k = 0; k < AT_BK / 16; ++k)
+            umma_f16_ss(tmem_base + C::O_COL + mt * AT_DH, p_desc + 2 * k, v_desc + 128 * k, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(&u_empty[sl]);
         umma_commit(p_empty);
       }
       umma_commit(o_full);
     }
   } else {
     // =========================== softmax warps (one query row per thread) ===========================
-    const int qd = warp & 3;  // TMEM lane quarter this warp may access
+    const int mt = (warp - 2) >> 2;  // M tile of this warp
+    const int qd = warp & 3;         // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(qd * 32) << 16;
     int u = 0;
     // ---- pass 1: row maximum of the raw scores ----
     float mx = -INFINITY;
     for (int j = 0; j < ntiles; ++j, ++u) {
-      const int st = u & 1;
-      mbar_wait(&s_full[st], (u >> 1) & 1);
+      const int buf = u & 1;
+      mbar_wait(&s_full[buf], (u >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32b_x32(tmem_base + t_lane + st * AT_BK + half * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK + half * 32, v);
         tmem_ld_wait();
         const int key0 = j * AT_BK + half * 32;
 #pragma unroll
@@ -209,21 +236,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (lane == 0) mbar_arrive(&s_empty[buf]);
     }
     const float mxs = mx * a.sl2;
     // ---- pass 2: P = exp2(sl2 S - max) -> bf16 swizzled tile, row sums ----
     float l = 0.f;
-    uint8_t* const prow = sP + row * 128;
+    uint8_t* const prow = sP + mt * AT_PT_BYTES + row * 128;
     for (int j = 0; j < ntiles; ++j, ++u) {
-      const int st = u & 1;
-      mbar_wait(&s_full[st], (u >> 1) & 1);
+      const int buf = u & 1;
+      mbar_wait(&s_full[buf], (u >> 1) & 1);
       tc_fence_after();
       uint32_t pk[32];  // 64 probabilities as bf16 pairs
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + t_lane + st * AT_BK + half * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK + half * 32, v);
         tmem_ld_wait();
         const int key0 = j * AT_BK + half * 32;
 #pragma unroll
@@ -239,7 +266,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);  // the score buffer may be overwritten by S(j+2)
+      if (lane == 0) mbar_arrive(&s_empty[buf]);  // the score buffer may be overwritten by S(j+2)
       if (j > 0) mbar_wait(p_empty, (j - 1) & 1);  // P(j-1) V(j-1) has read the tile
       // K-major SWIZZLE_128B: 16-byte chunk c16 of row r lives at chunk (c16 ^ (r & 7))
 #pragma unroll
@@ -253,12 +280,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = 1.0f / l;
-    const int q = q0 + row;
+    const int q = q0 + mt * AT_BM + row;
     __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.Sq + q) * a.out_ld + c_head;
 #pragma unroll
     for (int cb = 0; cb < AT_DH / 16; ++cb) {
       uint32_t v[16];
-      tmem_ld_32x32b_x16(tmem_base + t_lane + 2 * AT_BK + cb * 16, v);
+      tmem_ld_32x32b_x16(tmem_base + t_lane + C::O_COL + mt * AT_DH + cb * 16, v);
       tmem_ld_wait();
       if (q < a.Sq) {
         uint4 o0, o1;
@@ -278,7 +305,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<AT_TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
 bool attn_tc_enabled() {  // env WD_ATTN_TC (default on)
@@ -301,9 +328,17 @@ bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATCfg<1>::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATCfg<2>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) { *err = attr_err; return true; }
+  static int mt2 = -1;  // env WD_ATTN_TC_MT2=0: always one M tile per CTA (A/B measurements)
+  if (mt2 < 0) {
+    const char* e = getenv("WD_ATTN_TC_MT2");
+    mt2 = e ? (atoi(e) != 0) : 1;
+  }
+  const bool two = mt2 && a.Sq % (2 * AT_BM) == 0;
   CUtensorMap mq, mk, mv;
   // inner extent = the C channels of this operand (the over-fetching second box of the last head is zero-filled beyond it)
   if (!tmap_encode_3d_bf16(&mq, a.q, C, a.Sq, B, a.q_ld, static_cast<uint64_t>(a.Sq) * a.q_ld, 64, AT_BM) ||
@@ -313,7 +348,11 @@ bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError
     return true;
   }
   AttnTcArgs ta{a.out, a.out_ld, a.Sq, a.Skv, a.heads, a.scale * 1.4426950408889634f};
-  *err = launch_pdl(attn_tc_kernel, dim3((a.Sq + AT_BM - 1) / AT_BM, a.heads, B), dim3(AT_THREADS), AT_SMEM_BYTES, s, mq, mk, mv, ta);
+  if (two)
+    *err = launch_pdl(attn_tc_kernel<2>, dim3(a.Sq / (2 * AT_BM), a.heads, B), dim3(ATCfg<2>::THREADS), ATCfg<2>::SMEM_BYTES, s, mq, mk, mv, ta);
+  else
+    *err = launch_pdl(attn_tc_kernel<1>, dim3((a.Sq + AT_BM - 1) / AT_BM, a.heads, B), dim3(ATCfg<1>::THREADS), ATCfg<1>::SMEM_BYTES, s, mq, mk,
+                      mv, ta);
   return true;
 }
 

@@ -137,11 +137,16 @@ struct Slot {
 // launch plan
 // ----------------------------------------------------------------------------------------------
 enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_GNSTATS, OP_UPSAMPLE,
-              OP_EMBED, OP_LINF32, OP_WORDATTN };
+              OP_EMBED, OP_LINF32, OP_WORDATTN, OP_EMBTBL };
+// step ops that exist in two flavours: the time-embedding MLP per step (per-row timesteps: wd_unet_eval) or the lookup in
+// the per-trajectory table (one timestep for the whole batch: wd_sampler_step)
+enum OpCond { COND_ALWAYS = 0, COND_NO_TABLE = 1, COND_TABLE = 2 };
+constexpr int TEMB_TABLE_ROWS = 1024;  // timesteps 0 .. 1023 (the reference schedules use T = 1000 / 600)
 enum Patch { P_NONE = 0, P_Y = 1, P_SAMPLER = 2 };
 struct Op {
   OpKind kind;
   int patch = P_NONE;
+  int cond = COND_ALWAYS;
   double flops = 0;  // algorithmic work of this launch ("algorithmic work per op")
   double bytes = 0;
   GemmLaunch gemm;
@@ -151,7 +156,8 @@ struct Op {
   struct { const bf16* x; bf16* out; const float* g; const float* b; int M, C; float eps; int x_f16; } ln;
   AttnSmallArgs as;
   AttnFlashArgs af;
-  struct { bf16* out; int B, dim; } temb;
+  struct { bf16* out; int B, dim; int table; } temb;  // table != 0: row b embeds t = b
+  struct { const float* table; bf16* out; int B, dim; int use_label; } etbl;
   struct { bf16* out; int B, H, W; } cin;  // im2col of the latent
   struct { const bf16* x; bf16* out; int B, H, W, C; } up;
   struct { int which; const float* E; int vocab; const float* pe; int add_pe; float* out; int B, L, D; } emb;
@@ -199,6 +205,7 @@ struct wd_engine {
   bool pe_set = false;
   int n_kv = 0;
   std::vector<GemmW*> kv_weights;  // per K/V buffer: the fused [to_k; to_v] weight
+  bool prof_used_table = false;    // flavour of the time-embedding ops in the profiled steps (wd_engine_profile_read)
   int kv_fused_count = 0;          // kv_fused() calls (counted by the dry layout pass): their weights share one pool, so the
   bf16* kv_pool = nullptr;         //   K/V projections of ALL cross-attentions run as a single GEMM per trajectory
   int kv_pool_next = 0;
@@ -1246,10 +1253,41 @@ struct PlanBuilder {
     bf16* emb_act = A.alloc<bf16>(static_cast<size_t>(B) * ted);
     float* emb_out = A.alloc<float>(static_cast<size_t>(B) * e->emb_all.N);
     {
+      // per-trajectory table of time_embed(t) for every timestep (fp32 [TEMB_TABLE_ROWS, ted]): part of the context ops
+      bf16* temb_t = A.alloc<bf16>(static_cast<size_t>(TEMB_TABLE_ROWS) * mc);
+      bf16* h1_t = A.alloc<bf16>(static_cast<size_t>(TEMB_TABLE_ROWS) * ted);
+      float* table = A.alloc<float>(static_cast<size_t>(TEMB_TABLE_ROWS) * ted);
+      {
+        Op op;
+        memset(&op, 0, sizeof(op));
+        op.kind = OP_TEMB;
+        op.temb = {temb_t, TEMB_TABLE_ROWS, mc, 1};
+        cops.push_back(op);
+        Epi ep;
+        ep.out = h1_t;
+        ep.out_ld = ted;
+        ep.act = ACT_SILU;
+        if (!gemm_op(cops, TEMB_TABLE_ROWS, false, 0, 0, {ASrc{temb_t, mc, mc, 1, 1, 1, 1}}, e->te0, ep)) return false;
+        Epi ep2;
+        ep2.out = table;
+        ep2.out_ld = ted;
+        ep2.out_f32 = 1;
+        if (!gemm_op(cops, TEMB_TABLE_ROWS, false, 0, 0, {ASrc{h1_t, ted, ted, 1, 1, 1, 1}}, e->te2, ep2)) return false;
+      }
+      {
+        Op op;
+        memset(&op, 0, sizeof(op));
+        op.kind = OP_EMBTBL;
+        op.cond = COND_TABLE;
+        op.etbl = {table, emb_act, B, ted, (c.num_classes > 0 && c.add_label_emb) ? 1 : 0};
+        op.bytes = 6.0 * B * ted;
+        sops.push_back(op);
+      }
+      const size_t first_general = sops.size();
       Op op;
       memset(&op, 0, sizeof(op));
       op.kind = OP_TEMB;
-      op.temb = {temb, B, mc};
+      op.temb = {temb, B, mc, 0};
       sops.push_back(op);
       Epi ep;
       ep.out = h1;
@@ -1268,6 +1306,7 @@ struct PlanBuilder {
         patch = P_Y;
       }
       if (!gemm_op(sops, B, false, 0, 0, {ASrc{h1, ted, ted, 1, 1, 1, 1}}, e->te2, ep2, patch)) return false;
+      for (size_t i = first_general; i < sops.size(); ++i) sops[i].cond = COND_NO_TABLE;
       Epi ep3;
       ep3.out = emb_out;
       ep3.out_ld = e->emb_all.N;
@@ -1444,6 +1483,15 @@ struct RunCtx {
   int mode = STEP_EPS_ONLY;
 };
 
+static bool temb_table_enabled() {  // env WD_TEMB_TABLE (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TEMB_TABLE");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStream_t s) {
   int n = 0, kernels = 0;
   std::vector<cudaEvent_t>* ev = nullptr;
@@ -1459,12 +1507,24 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
     for (auto& x : *ev)
       if (cudaEventCreate(&x) != cudaSuccess) return fail(WD_ERR_CUDA, "cudaEventCreate");
   }
+  const bool use_table = rc.t_dev == nullptr && rc.t_scalar >= 0 && rc.t_scalar < TEMB_TABLE_ROWS && temb_table_enabled();
+  if (ev) e->prof_used_table = use_table;
   for (const Op& op : ops) {
     cudaError_t err = cudaSuccess;
     if (ev) cudaEventRecord((*ev)[n], s);
+    if ((op.cond == COND_TABLE && !use_table) || (op.cond == COND_NO_TABLE && use_table)) {
+      ++n;
+      continue;
+    }
     switch (op.kind) {
       case OP_TEMB:
-        err = timestep_embed_launch(rc.t_dev, rc.t_scalar, op.temb.out, op.temb.B, op.temb.dim, s);
+        if (op.temb.table) err = timestep_embed_launch(nullptr, -1, op.temb.out, op.temb.B, op.temb.dim, s);
+        else err = timestep_embed_launch(rc.t_dev, rc.t_scalar, op.temb.out, op.temb.B, op.temb.dim, s);
+        break;
+      case OP_EMBTBL:
+        if (op.etbl.use_label && !rc.y) return fail(WD_ERR_INVALID, "y (writer ids) is required by this model");
+        err = emb_from_table_launch(op.etbl.table, rc.t_scalar, op.etbl.use_label ? e->label_emb : nullptr, rc.y, op.etbl.out, op.etbl.B,
+                                    op.etbl.dim, s);
         break;
       case OP_GEMM:
         if (op.patch == P_Y) {
@@ -1638,9 +1698,11 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
   if (cap < n) return fail(WD_ERR_INVALID, "profile_read: capacity %d < %d ops", cap, n);
   CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < n; ++i) {
-    kinds[i] = static_cast<int>(ops[i].kind);
-    flops[i] = ops[i].flops;
-    bytes[i] = ops[i].bytes;
+    // the table lookup reports as the timestep-embedding class; ops of the flavour the profiled steps skipped carry no work
+    const bool skipped = (ops[i].cond == COND_TABLE && !e->prof_used_table) || (ops[i].cond == COND_NO_TABLE && e->prof_used_table);
+    kinds[i] = ops[i].kind == OP_EMBTBL ? static_cast<int>(OP_TEMB) : static_cast<int>(ops[i].kind);
+    flops[i] = skipped ? 0.0 : ops[i].flops;
+    bytes[i] = skipped ? 0.0 : ops[i].bytes;
     ms_sum[i] = 0.f;
   }
   for (auto& v : e->prof_steps)

@@ -403,6 +403,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (has_res && leader_warp && static_cast<int>(blockIdx.x) < total_tiles) {
         if (elect_one()) issue_res_load(blockIdx.x, 0);
       }
+      uint4 att_pf[3];  // ATT builds: this thread's share of the next tile's K / V rows
+      auto att_fetch = [&](int m0_, int n0_) {
+        if constexpr (ATT) {
+          const int L = args.att_L;
+          const int sample = m0_ / args.rows_per_sample;
+          const int head = (n0_ + half * HC) / 80;
+          const __nv_bfloat16* src = args.att_kv + static_cast<size_t>(sample) * L * args.att_ld + head * 80;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int idx = q * 32 + lane + i * 128;
+            att_pf[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < 2 * 16 * 10) {
+              const int sel = idx / 160, r = idx % 160, j = r / 10, ch = r % 10;
+              if (j < L) att_pf[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(j) * args.att_ld + sel * args.att_voff) + ch);
+            }
+          }
+        }
+      };
+      if (ATT && static_cast<int>(blockIdx.x) < total_tiles)
+        att_fetch((static_cast<int>(blockIdx.x) / n_tiles) * GEMM_BLOCK_M, (static_cast<int>(blockIdx.x) % n_tiles) * BN);
 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -466,18 +486,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if constexpr (ATT) {
           // K / V rows of (sample of this tile, head of this column half) -> shared memory, rows >= L zeroed.  The four warps of
           // the half passed the post-staging barrier of the previous tile after their last read of the buffer; the barrier in
-          // front of the epilogue arithmetic below publishes the new contents.
-          const int L = args.att_L;
-          const int sample = m0 / args.rows_per_sample;
-          const int head = (n0 + half * HC) / 80;
-          const __nv_bfloat16* src = args.att_kv + static_cast<size_t>(sample) * L * args.att_ld + head * 80;
+          // front of the epilogue arithmetic below publishes the new contents.  The rows were fetched into registers one tile
+          // ahead (att_pf: 3 x 16 bytes per thread), so their global-load latency is not part of this tile's chain.
           __nv_bfloat16* dst = kvs + half * (2 * 16 * ATT_KP);
-          for (int idx = q * 32 + lane; idx < 2 * 16 * 10; idx += 128) {
-            const int sel = idx / 160, r = idx % 160, j = r / 10, ch = r % 10;
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
-            if (j < L) u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(j) * args.att_ld + sel * args.att_voff) + ch);
-            *reinterpret_cast<uint4*>(dst + (sel * 16 + j) * ATT_KP + ch * 8) = u;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int idx = q * 32 + lane + i * 128;
+            if (idx < 2 * 16 * 10) {
+              const int sel = idx / 160, r = idx % 160, j = r / 10, ch = r % 10;
+              *reinterpret_cast<uint4*>(dst + (sel * 16 + j) * ATT_KP + ch * 8) = att_pf[i];
+            }
           }
+          const int next = tile + gridDim.x;
+          if (next < total_tiles) att_fetch((next / n_tiles) * GEMM_BLOCK_M, (next % n_tiles) * BN);
         }
 
         WD_TRACE(2);

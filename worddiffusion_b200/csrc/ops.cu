@@ -586,7 +586,7 @@ __global__ void timestep_embed_kernel(const long long* __restrict__ t_dev, long 
   pdl_wait();
   if (idx >= B * half) return;
   const int b = idx / half, i = idx % half;
-  const float t = static_cast<float>(t_dev ? t_dev[b] : t_scalar);
+  const float t = static_cast<float>(t_dev ? t_dev[b] : (t_scalar < 0 ? static_cast<long long>(b) : t_scalar));  // t_scalar < 0: row b embeds t = b
   const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
   const float arg = t * freq;
   out[static_cast<size_t>(b) * dim + i] = __float2bfloat16(cosf(arg));
@@ -704,6 +704,28 @@ cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len
   if (B < 1 || max_len < 1) return cudaErrorInvalidValue;
   phosc_tokenize_kernel<<<B, 256, 0, s>>>(words, max_len, out, bad_flag);
   return cudaGetLastError();
+}
+
+// =====================================================================================================
+// emb_act[b] = SiLU(time_embed_table[t] + label_emb[y[b]])  (unet.py:1575-1581 + the SiLU every emb_layers starts with, :609-610).
+// The sampling loop evaluates all latents at ONE timestep: time_embed(t) comes from a per-trajectory table over all timesteps
+// (two small GEMMs per trajectory instead of two latency-bound GEMMs + the sinusoid kernel per step).
+// =====================================================================================================
+__global__ void emb_from_table_kernel(const float* __restrict__ table, long long t, const float* __restrict__ label_emb,
+                                      const long long* __restrict__ y, __nv_bfloat16* __restrict__ out, int B, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  if (idx >= B * dim) return;
+  const int b = idx / dim, d = idx % dim;
+  float v = __ldg(table + static_cast<size_t>(t) * dim + d);
+  if (label_emb) v += __ldg(label_emb + static_cast<size_t>(y[b]) * dim + d);
+  out[idx] = __float2bfloat16(silu_f(v));
+}
+cudaError_t emb_from_table_launch(const float* table, long long t, const float* label_emb, const long long* y, __nv_bfloat16* out,
+                                  int B, int dim, cudaStream_t s) {
+  if (label_emb && !y) return cudaErrorInvalidValue;
+  return launch_pdl(emb_from_table_kernel, dim3((B * dim + 255) / 256), dim3(256), 0, s, table, t, label_emb, y, out, B, dim);
 }
 
 // =====================================================================================================

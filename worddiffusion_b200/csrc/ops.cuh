@@ -79,6 +79,11 @@ bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError
 // ---------------- PHOSC tokenizer: words [B, max_len] zero-padded bytes -> int32 [B, 769]; *bad_flag |= 1 on a non-letter ----------------
 cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len, int* out, int* bad_flag, cudaStream_t s);
 
+// emb_act = SiLU(table[t] + label_emb[y]) -> bf16 [B, dim]; table fp32 [timesteps, dim] (timestep_embed_launch with t_scalar < 0
+// embeds t = row index, which is how the table's sinusoid rows are made)
+cudaError_t emb_from_table_launch(const float* table, long long t, const float* label_emb, const long long* y, __nv_bfloat16* out,
+                                  int B, int dim, cudaStream_t s);
+
 // ---------------- sampler update with a given (possibly stale) predicted noise; same arithmetic as the fused epilogue ----------------
 cudaError_t sampler_update_launch(float* x, const float* eps, const float* noise, int use_philox, unsigned long long seed,
                                   unsigned long long elem_offset, int step_index, float4 coef, int mode, size_t n, cudaStream_t s);
