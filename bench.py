@@ -226,6 +226,7 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL prints its version banner)
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     B, K, Wm = args.batch, args.steps, args.warmup
@@ -332,6 +333,12 @@ def run_ours(args):
            "api": "worddiffusion_b200.%s forward(x, timesteps, context, y) with pinned host tensors; context re-encoded "
                   "per call" % ("unet.UNetModel" if variant == "unet" else "unetPhosc.UNetModelPhosc")}
 
+    # training leg (configs[3]): EVERY rank takes part (sharded batch, gradient all-reduce) -- it must run before the
+    # non-zero ranks leave
+    train = None
+    if args.train_steps > 0 and variant == "unet":
+        train = train_leg(args, world, rank, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -373,9 +380,6 @@ def run_ours(args):
         roofline["algorithmic_bytes_per_launch_avg"] = cls_b[g] / cls_n[g]
     step_tf = B * GFLOP_PER_LATENT[variant] * 1e9 / (ms / K * 1e-3) / 1e12
 
-    train = None
-    if args.train_steps > 0 and variant == "unet":
-        train = train_leg(args, world, rank, dev)
     cb = cpu_oracle_throughput(variant, seconds=args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
