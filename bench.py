@@ -224,9 +224,14 @@ def run_ours(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    real_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL prints its version banner)
+        # stdout must carry exactly one JSON line, and NCCL writes its version banner to fd 1 when the first communicator is
+        # created: everything else goes to stderr, the JSON line to the saved descriptor
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     B, K, Wm = args.batch, args.steps, args.warmup
@@ -395,7 +400,11 @@ def run_ours(args):
         out["cpu_baseline"] = cb
     if train is not None:
         out["train_step"] = train
-    print(json.dumps(out), flush=True)
+    if real_stdout is not None:
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    else:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -3,9 +3,9 @@
 // cross-attention over the 779-token char + PHOSC context.  The score matrix never reaches HBM (the reference materialises
 // [B*4, Sq, Skv] fp32).  The mma.sync flash kernel (attn_flash.cu) ran these launches at 96 TFLOP/s, 45 % of the unetPhosc step.
 //
-// One CTA = (MT x 128 query rows, head, sample).  MT = 2 when a sample's queries come in multiples of 256 (the 8 x 32 level): both
-// query tiles share every K / V tile -- the kernel is bound by L2 -> SM operand traffic, and this halves it -- 8 ring slots,
-// 224 KB of shared memory, one CTA per SM, 320 threads.  MT = 1 otherwise: 4 slots, 112 KB, two CTAs per SM, 192 threads.
+// One CTA = (MT x 128 query rows, head, sample).  MT = 1 (default): 4 ring slots, 112 KB of shared memory, two CTAs per SM, 192
+// threads.  MT = 2 (env WD_ATTN_TC_MT2=1; both query tiles of a 256-token sample share every K / V tile, 8 slots, 224 KB, one CTA
+// per SM, 320 threads) halves the L2 -> SM operand traffic but measured slower: a lone CTA cannot hide its softmax <-> MMA chain.
 //   warp 0     TMA producer: Q once, then the K tiles (pass 1) and K, V tiles (pass 2) of 64 keys as UNITS through a ring of 16 KB
 //              slots (a K slot is released when its QK^T retires, a V slot after its PV).  Every operand tile is a pair of
 //              SWIZZLE_128B boxes of 64 channels starting at the head's first channel: the second box over-fetches 48 channels of
@@ -333,10 +333,12 @@ bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError
       attr_err = cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATCfg<2>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) { *err = attr_err; return true; }
-  static int mt2 = -1;  // env WD_ATTN_TC_MT2=0: always one M tile per CTA (A/B measurements)
+  // env WD_ATTN_TC_MT2=1 selects the 256-query CTA.  Default off: measured at batch 256 (unetPhosc, eight launches per step) the
+  // two-CTAs-per-SM MT = 1 build takes 0.86 ms, MT = 2 0.97 ms -- one CTA per SM cannot hide its own softmax <-> MMA ping-pong.
+  static int mt2 = -1;
   if (mt2 < 0) {
     const char* e = getenv("WD_ATTN_TC_MT2");
-    mt2 = e ? (atoi(e) != 0) : 1;
+    mt2 = e ? (atoi(e) != 0) : 0;
   }
   const bool two = mt2 && a.Sq % (2 * AT_BM) == 0;
   CUtensorMap mq, mk, mv;
