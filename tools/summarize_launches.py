@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel time and share of ONE DDPM step of
-bench.py (the launches from one timestep_embed kernel up to the next).  Usage: summarize_launches.py launches.csv [step]"""
+bench.py (the launches from the first kernel of a step -- the time-embedding table lookup, or the sinusoid kernel in builds
+without the table -- up to the next one).  Usage: summarize_launches.py launches.csv [step]"""
 import collections
 import csv
 import re
@@ -15,7 +16,9 @@ def main():
     rows = list(csv.DictReader(lines))
     names = [(re.sub(r"\(.*", "", r["Kernel Name"]).replace("wd::", "").replace("void ", ""),
               float(r["Metric Value"].replace(",", "")), r["Grid Size"], r["Block Size"]) for r in rows]
-    starts = [i for i, n in enumerate(names) if "timestep_embed" in n[0]]
+    starts = [i for i, n in enumerate(names) if "emb_from_table" in n[0]]
+    if len(starts) < which + 2:
+        starts = [i for i, n in enumerate(names) if "timestep_embed" in n[0]]
     lo, hi = starts[which], starts[which + 1]
     step = names[lo:hi]
     agg = collections.OrderedDict()
