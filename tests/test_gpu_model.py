@@ -277,3 +277,19 @@ def test_phosc_tokenizer_feeds_the_model(phosc):
     ref = UO.unet_forward(sd, inp["x"].cpu(), inp["t"].cpu(), inp["context"].cpu(), inp["y"].cpu(), variant="unetPhosc",
                           phosc=torch.from_numpy(np.stack([P.phosc("getting"), P.phosc("Stylist")])))
     assert relerr(eps, ref) < TOL_BF16
+
+
+def test_sampler_step_and_unet_eval_agree(unet):
+    """wd_sampler_step (one timestep for the batch: time embedding from the per-trajectory table) and wd_unet_eval (per-row
+    timesteps: the time-embedding MLP per call) are two launch sequences of the same function: same eps."""
+    m, _ = unet
+    inp = _cuda(W.make_inputs(5, seed=9))
+    d = Diffusion(noise_steps=1000, device=DEV)
+    eng = m.engine(DEV)
+    eng.encode_context(inp["context"])
+    for t in (1, 437, 999):
+        x = inp["x"].clone()
+        eps_a = torch.empty_like(x)
+        eng.sampler_step(x, t, inp["y"], 1, d._ddpm_coef[t], eps_out=eps_a)
+        eps_b = eng.unet_eval(inp["x"], torch.full((5,), t, device=DEV, dtype=torch.long), inp["y"])
+        assert relerr(eps_a, eps_b) < 2e-3, t
