@@ -171,6 +171,15 @@ struct Plan {
   std::vector<Op> step_ops;
   size_t bytes = 0;
   bool context_valid = false;
+  // CUDA graph of the sampling step (wd_sampler_step): valid for one set of caller pointers; the per-step scalars live in
+  // wd_engine::sp_dev.  graph_seen counts consecutive calls with the same pointers (capture happens on the second one).
+  cudaGraphExec_t graph = nullptr;
+  const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};  // x, eps_out, noise, y
+  int graph_seen = 0;
+  int graph_launches = 0;
+  ~Plan() {
+    if (graph) cudaGraphExecDestroy(graph);
+  }
 };
 
 struct Act {
@@ -205,6 +214,8 @@ struct wd_engine {
   bool pe_set = false;
   int n_kv = 0;
   std::vector<GemmW*> kv_weights;  // per K/V buffer: the fused [to_k; to_v] weight
+  StepParams* sp_dev = nullptr;    // device-resident per-step scalars of the graphed sampling step
+  cudaStream_t cap_stream = nullptr;  // private stream the step graph is captured on
   bool prof_used_table = false;    // flavour of the time-embedding ops in the profiled steps (wd_engine_profile_read)
   int kv_fused_count = 0;          // kv_fused() calls (counted by the dry layout pass): their weights share one pool, so the
   bf16* kv_pool = nullptr;         //   K/V projections of ALL cross-attentions run as a single GEMM per trajectory
@@ -623,6 +634,9 @@ extern "C" void wd_engine_destroy(wd_engine* e) {
   cudaDeviceSynchronize();
   if (e->wbase) cudaFree(e->wbase);
   if (e->abase) cudaFree(e->abase);
+  if (e->sp_dev) cudaFree(e->sp_dev);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  e->plans.clear();
   delete e;
 }
 
@@ -1466,6 +1480,7 @@ int ensure_plan(wd_engine* e, int B, int L, Plan** out) {
 }
 
 struct RunCtx {
+  const StepParams* sp = nullptr;  // graph capture / replay: per-step scalars are read from device memory
   const float* x = nullptr;
   const long long* t_dev = nullptr;
   long long t_scalar = 0;
@@ -1483,6 +1498,14 @@ struct RunCtx {
   int mode = STEP_EPS_ONLY;
 };
 
+static bool step_graph_enabled() {  // env WD_STEP_GRAPH (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_STEP_GRAPH");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 static bool temb_table_enabled() {  // env WD_TEMB_TABLE (default on)
   static int v = -1;
   if (v < 0) {
@@ -1523,8 +1546,8 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
         break;
       case OP_EMBTBL:
         if (op.etbl.use_label && !rc.y) return fail(WD_ERR_INVALID, "y (writer ids) is required by this model");
-        err = emb_from_table_launch(op.etbl.table, rc.t_scalar, op.etbl.use_label ? e->label_emb : nullptr, rc.y, op.etbl.out, op.etbl.B,
-                                    op.etbl.dim, s);
+        err = emb_from_table_launch(op.etbl.table, rc.t_scalar, rc.sp, op.etbl.use_label ? e->label_emb : nullptr, rc.y, op.etbl.out,
+                                    op.etbl.B, op.etbl.dim, s);
         break;
       case OP_GEMM:
         if (op.patch == P_Y) {
@@ -1543,6 +1566,7 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
           L.args.step_index = rc.step_index;
           L.args.coef = rc.coef;
           L.args.mode = rc.mode;
+          L.args.sp = rc.sp;
           err = gemm_tc_launch(L, s);
         } else {
           err = gemm_tc_launch(op.gemm, s);
@@ -1672,7 +1696,59 @@ extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scal
   r.step_index = step_index;
   r.coef = make_float4(coef4_host[0], coef4_host[1], coef4_host[2], coef4_host[3]);
   r.mode = mode;
-  return run_ops(e, e->cur->step_ops, r, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // ---- CUDA-graph replay of the launch sequence (79 kernels): the second consecutive call with the same caller pointers
+  // captures it, later ones replay it; the scalars that change per step travel through sp_dev.  Small batches are bound by
+  // the host's launch rate otherwise (1.0 ms/step at batch 1).  Needs the table flavour of the time embedding.
+  Plan* p = e->cur;
+  const void* key[4] = {x, eps_out, noise, y};
+  const bool graph_ok = step_graph_enabled() && !e->prof_on && t_scalar >= 0 && t_scalar < TEMB_TABLE_ROWS && temb_table_enabled();
+  if (!graph_ok) return run_ops(e, p->step_ops, r, s);
+  if (memcmp(key, p->graph_key, sizeof(key)) != 0) {
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    p->graph = nullptr;
+    memcpy(p->graph_key, key, sizeof(key));
+    p->graph_seen = 0;
+  }
+  if (++p->graph_seen == 1 || p->graph_seen < 0) return run_ops(e, p->step_ops, r, s);  // first call with these pointers: eager
+  if (!e->sp_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->sp_dev), sizeof(StepParams)));
+  StepParams sp;
+  sp.t = t_scalar;
+  sp.coef = r.coef;
+  sp.seed = seed;
+  sp.sample_offset = sample_offset;
+  sp.mode = mode;
+  sp.use_philox = use_philox;
+  sp.step_index = step_index;
+  sp.pad = 0;
+  CUDA_TRY(set_step_params_launch(e->sp_dev, sp, s));
+  if (!p->graph) {
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured); nothing runs
+    // during capture, the instantiated graph is launched on the caller's stream
+    r.sp = e->sp_dev;
+    cudaGraph_t g = nullptr;
+    cudaError_t ie = cudaErrorUnknown;
+    if (!e->cap_stream && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) e->cap_stream = nullptr;
+    if (e->cap_stream && cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rc2 = run_ops(e, p->step_ops, r, e->cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+      if (rc2 == WD_OK && ce == cudaSuccess && g) {
+        p->graph_launches = e->last_launches;
+        ie = cudaGraphInstantiate(&p->graph, g, 0);
+      }
+    }
+    if (g) cudaGraphDestroy(g);
+    if (ie != cudaSuccess) {  // capture is not available here: stay eager for these pointers
+      p->graph = nullptr;
+      p->graph_seen = -1000000000;
+      cudaGetLastError();
+      r.sp = nullptr;
+      return run_ops(e, p->step_ops, r, s);
+    }
+  }
+  CUDA_TRY(cudaGraphLaunch(p->graph, s));
+  e->last_launches = p->graph_launches;
+  return WD_OK;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -332,6 +332,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (elect_one()) bulk_wait_group_read<0>();  // smem must outlive the last TMA store's read
       }
     } else if constexpr (EPI == EPI_SAMPLER) {
+      // per-step quantities: kernel arguments, or (graph replay) the device-resident StepParams
+      const float4 coef = args.sp ? args.sp->coef : args.coef;
+      const int mode = args.sp ? args.sp->mode : args.mode;
+      const int use_philox = args.sp ? args.sp->use_philox : args.use_philox;
+      const unsigned long long seed = args.sp ? args.sp->seed : args.seed;
+      const unsigned long long sample_offset = args.sp ? args.sp->sample_offset : args.sample_offset;
+      const int step_index = args.sp ? args.sp->step_index : args.step_index;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const int m = (tile / n_tiles) * GEMM_BLOCK_M + row;
@@ -355,20 +362,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const float eps = (__uint_as_float(v[o]) + __uint_as_float(v[4 + o])) + __ldg(args.bias + o);
             const size_t idx = (static_cast<size_t>(b) * 4 + o) * HW + pix;
             if (args.eps_out) args.eps_out[idx] = eps;
-            if (args.mode == STEP_DDPM) {
+            if (mode == STEP_DDPM) {
               float z = 0.f;
               if (args.noise)
                 z = __ldg(args.noise + idx);
-              else if (args.use_philox)
-                z = philox_normal(args.seed, args.sample_offset * (4ull * HW) + idx, static_cast<uint32_t>(args.step_index));
+              else if (use_philox)
+                z = philox_normal(seed, sample_offset * (4ull * HW) + idx, static_cast<uint32_t>(step_index));
               const float xv = args.x[idx];
               // same op order as the reference expression, no FMA contraction
-              const float inner = __fsub_rn(xv, __fmul_rn(args.coef.y, eps));
-              args.x[idx] = __fadd_rn(__fmul_rn(args.coef.x, inner), __fmul_rn(args.coef.z, z));
-            } else if (args.mode == STEP_DDIM) {
+              const float inner = __fsub_rn(xv, __fmul_rn(coef.y, eps));
+              args.x[idx] = __fadd_rn(__fmul_rn(coef.x, inner), __fmul_rn(coef.z, z));
+            } else if (mode == STEP_DDIM) {
               const float xv = args.x[idx];
-              const float x0 = __fmul_rn(__fsub_rn(xv, __fmul_rn(args.coef.y, eps)), args.coef.x);
-              args.x[idx] = __fadd_rn(__fmul_rn(args.coef.z, x0), __fmul_rn(args.coef.w, eps));
+              const float x0 = __fmul_rn(__fsub_rn(xv, __fmul_rn(coef.y, eps)), coef.x);
+              args.x[idx] = __fadd_rn(__fmul_rn(coef.z, x0), __fmul_rn(coef.w, eps));
             }
           }
         }

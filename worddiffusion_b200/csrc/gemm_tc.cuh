@@ -43,6 +43,20 @@ enum GemmAct : int { ACT_NONE = 0, ACT_SILU = 1 };
 enum GemmEpi : int { EPI_STD = 0, EPI_SAMPLER = 1 };
 enum StepMode : int { STEP_EPS_ONLY = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
 
+// Per-step quantities of the sampling loop in DEVICE memory: a captured CUDA graph of the step cannot carry them as kernel
+// arguments (they change every step), so the graphed launch sequence reads them through a pointer that a tiny kernel refreshes
+// before each replay (engine.cu: wd_sampler_step).
+struct StepParams {
+  long long t;  // timestep of the whole batch
+  float4 coef;
+  unsigned long long seed;
+  unsigned long long sample_offset;
+  int mode;  // StepMode
+  int use_philox;
+  int step_index;
+  int pad;
+};
+
 struct GemmArgs {
   int M;  // rows (pixels / tokens)
   int N;  // accumulator columns (weight rows)
@@ -109,6 +123,7 @@ struct GemmArgs {
   int step_index;
   float4 coef;
   int mode;
+  const StepParams* sp;  // non-null (graph replay): coef / mode / Philox arguments come from *sp instead of the fields above
   int dbg;  // experiment switches (env WD_GEMM_DBG, tools/op_bench.py): 1 no TMA store, 2 no epilogue math, 4 no B loads
 };
 

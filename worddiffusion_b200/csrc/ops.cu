@@ -711,21 +711,29 @@ cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len
 // The sampling loop evaluates all latents at ONE timestep: time_embed(t) comes from a per-trajectory table over all timesteps
 // (two small GEMMs per trajectory instead of two latency-bound GEMMs + the sinusoid kernel per step).
 // =====================================================================================================
-__global__ void emb_from_table_kernel(const float* __restrict__ table, long long t, const float* __restrict__ label_emb,
-                                      const long long* __restrict__ y, __nv_bfloat16* __restrict__ out, int B, int dim) {
+__global__ void emb_from_table_kernel(const float* __restrict__ table, long long t, const StepParams* __restrict__ sp,
+                                      const float* __restrict__ label_emb, const long long* __restrict__ y,
+                                      __nv_bfloat16* __restrict__ out, int B, int dim) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_trigger();
   pdl_wait();
   if (idx >= B * dim) return;
+  if (sp) t = sp->t;  // graph replay: the timestep lives in device memory
   const int b = idx / dim, d = idx % dim;
   float v = __ldg(table + static_cast<size_t>(t) * dim + d);
   if (label_emb) v += __ldg(label_emb + static_cast<size_t>(y[b]) * dim + d);
   out[idx] = __float2bfloat16(silu_f(v));
 }
-cudaError_t emb_from_table_launch(const float* table, long long t, const float* label_emb, const long long* y, __nv_bfloat16* out,
-                                  int B, int dim, cudaStream_t s) {
+cudaError_t emb_from_table_launch(const float* table, long long t, const StepParams* sp, const float* label_emb, const long long* y,
+                                  __nv_bfloat16* out, int B, int dim, cudaStream_t s) {
   if (label_emb && !y) return cudaErrorInvalidValue;
-  return launch_pdl(emb_from_table_kernel, dim3((B * dim + 255) / 256), dim3(256), 0, s, table, t, label_emb, y, out, B, dim);
+  return launch_pdl(emb_from_table_kernel, dim3((B * dim + 255) / 256), dim3(256), 0, s, table, t, sp, label_emb, y, out, B, dim);
+}
+// refresh the device-resident step parameters (by-value kernel argument: no host staging buffer to keep alive)
+__global__ void set_step_params_kernel(StepParams* dst, const StepParams v) { *dst = v; }
+cudaError_t set_step_params_launch(StepParams* dst, const StepParams& v, cudaStream_t s) {
+  set_step_params_kernel<<<1, 1, 0, s>>>(dst, v);
+  return cudaGetLastError();
 }
 
 // =====================================================================================================

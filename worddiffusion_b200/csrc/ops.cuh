@@ -81,8 +81,9 @@ cudaError_t phosc_tokenize_launch(const unsigned char* words, int B, int max_len
 
 // emb_act = SiLU(table[t] + label_emb[y]) -> bf16 [B, dim]; table fp32 [timesteps, dim] (timestep_embed_launch with t_scalar < 0
 // embeds t = row index, which is how the table's sinusoid rows are made)
-cudaError_t emb_from_table_launch(const float* table, long long t, const float* label_emb, const long long* y, __nv_bfloat16* out,
-                                  int B, int dim, cudaStream_t s);
+cudaError_t emb_from_table_launch(const float* table, long long t, const StepParams* sp, const float* label_emb, const long long* y,
+                                  __nv_bfloat16* out, int B, int dim, cudaStream_t s);
+cudaError_t set_step_params_launch(StepParams* dst, const StepParams& v, cudaStream_t s);
 
 // ---------------- sampler update with a given (possibly stale) predicted noise; same arithmetic as the fused epilogue ----------------
 cudaError_t sampler_update_launch(float* x, const float* eps, const float* noise, int use_philox, unsigned long long seed,
