@@ -34,7 +34,10 @@ struct Cfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BN * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = WSK ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int IDENT_BYTES = RESK_ ? 64 * GEMM_BLOCK_K * 2 : 0;  // 64 x 64 fp16 identity tile (GemmArgs::res_k)
+  // 64 x 64 fp16 identity tile (GemmArgs::res_k): resident beside the weights in the weight-stationary build, streamed into the
+  // stage's B slot with each residual block otherwise
+  static constexpr int IDENT_TILE = 64 * GEMM_BLOCK_K * 2;
+  static constexpr int IDENT_BYTES = (RESK_ && WSK_) ? IDENT_TILE : 0;
   static constexpr int BRES_BYTES = WSK * B_BYTES + IDENT_BYTES;  // resident weight tile (+ identity)
   static constexpr int ACC_STRIDE = (BN == GEMM_BLOCK_N) ? 256 : 32;  // TMEM column offset of accumulator buffer 1
   static constexpr int TMEM_COLS = (BN == GEMM_BLOCK_N) ? 512 : 64;
@@ -128,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n0 = (blockIdx.x % n_tiles) * BN;
         mbar_arrive_expect_tx(bres_bar, total_k * C::B_BYTES + C::IDENT_BYTES);
         for (int kb = 0; kb < total_k; ++kb) tma_load_2d(bres + kb * C::B_BYTES, &mapB, bres_bar, kb * GEMM_BLOCK_K, n0);
-        if constexpr (RESK) tma_load_2d(bres + WSK * C::B_BYTES, &mapA2, bres_bar, 0, 0);
+        if constexpr (RESK && WSK > 0) tma_load_2d(bres + WSK * C::B_BYTES, &mapA2, bres_bar, 0, 0);
       }
       pdl_wait();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -170,8 +173,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           // residual K blocks: only the 64-channel blocks that overlap this tile's BN output columns
           for (int rb = n0 / GEMM_BLOCK_K; rb * GEMM_BLOCK_K < n0 + BN; ++rb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + (WSK > 0 ? 0 : C::IDENT_TILE));
             tma_load_2d(smem + stage * C::STAGE_BYTES, &mapA1, &full_bar[stage], rb * GEMM_BLOCK_K, m0);
+            if constexpr (WSK == 0) tma_load_2d(smem + stage * C::STAGE_BYTES + C::A_BYTES, &mapA2, &full_bar[stage], 0, 0);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -229,8 +233,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t nn = static_cast<uint32_t>(hi - lo);  // 64 or 32
             const uint32_t idesc = (1u << 4) | ((nn >> 3) << 17) | ((GEMM_BLOCK_M >> 4) << 24);  // fp16 x fp16 -> fp32, 128 x nn
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + stage * C::STAGE_BYTES));
-            const uint64_t b_desc =
-                make_smem_desc_sw128(smem_u32(bres + WSK * C::B_BYTES + (lo - rb * GEMM_BLOCK_K) * (GEMM_BLOCK_K * 2)));
+            const uint8_t* ident = WSK > 0 ? bres + WSK * C::B_BYTES : smem + stage * C::STAGE_BYTES + C::A_BYTES;
+            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(ident + (lo - rb * GEMM_BLOCK_K) * (GEMM_BLOCK_K * 2)));
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
               umma_f16_ss(d_tmem + static_cast<uint32_t>(lo - n0), a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
@@ -799,10 +803,13 @@ bool gemm_prepare_res_k(GemmLaunch& L) {
   a.res_k = 0;
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
-  // the weight-stationary launch of gemm_tc_launch(), an fp16 residual covering the N output columns, 16-bit staged output
-  if (!gemm_res_k_enabled() || !gemm_ws_enabled() || !a.residual || !a.res_f16 || a.epi != EPI_STD || a.conv || a.num_src != 1 ||
-      total_k > 5 || a.N / GEMM_BLOCK_N > num_sms() || a.N % GEMM_BLOCK_K % 32 || a.out_f32 || a.geglu || a.act != ACT_NONE ||
-      a.att_kv || a.res_ld % 8 || (a.rowbias && a.rows_per_sample % 32 != 0) || gemm_uses_pair(a))
+  // the weight-stationary launch of gemm_tc_launch() (K <= 320) or its long-K single-CTA launch (K >= 1024: ff_out), plain Linear,
+  // an fp16 residual covering the N output columns, 16-bit staged output
+  const bool ws_shape = gemm_ws_enabled() && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms();
+  const bool long_shape = total_k >= 16;
+  if (!gemm_res_k_enabled() || !(ws_shape || long_shape) || !a.residual || !a.res_f16 || a.epi != EPI_STD || a.conv || a.num_src != 1 ||
+      a.N % GEMM_BLOCK_K % 32 || a.out_f32 || a.geglu || a.act != ACT_NONE || a.ln_stats || a.att_kv || a.res_ld % 8 ||
+      (a.rowbias && a.rows_per_sample % 32 != 0) || gemm_uses_pair(a))
     return true;
   const void* ident = gemm_identity_f16();
   if (!ident) return false;
@@ -909,7 +916,10 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
   if (gemm_uses_pair(a)) return gemm_pair_launch(L, num_sms(), stream);
   // long K loops hide the epilogue behind the MMAs of the next tile: spend shared memory on operand stages;
   // short K loops are epilogue / store bound: spend it on a second staging buffer
-  if (total_k >= 16) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
+  if (total_k >= 16) {
+    if (a.res_k) return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1, 0, 0, 1>(L, stream);  // + residual as identity K blocks (streamed identity)
+    return launch_impl<GEMM_BLOCK_N, EPI_STD, 5, 1>(L, stream);
+  }
   if ((gemm_ws_enabled() || a.ln_stats) && !a.conv && a.num_src == 1 && total_k <= 5 && a.N / GEMM_BLOCK_N <= num_sms()) {
     if (a.res_k) return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 0, 1>(L, stream);  // + residual as identity K blocks
     if (a.geglu && !a.rowbias && gemm_grp_enabled()) return launch_impl<GEMM_BLOCK_N, EPI_STD, 4, 1, 5, 0, 0, 1>(L, stream);
