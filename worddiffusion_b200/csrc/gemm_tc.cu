@@ -869,19 +869,25 @@ bool gemm_pair_enabled() {
   }
   return v != 0;
 }
-static int gemm_pair_min_kblocks() {  // env WD_GEMM_PAIR_MINK: plain (non-GEGLU) GEMMs with fewer 64-wide K blocks use the single-CTA kernel
-  static int v = -1;
-  if (v < 0) {
+// Which GEMMs run on the CTA-pair kernel (256 x 320 tiles): by the number of 64-wide K blocks (env WD_GEMM_PAIR_MINK overrides).
+// Measured per op inside the step (bench.py --ops-out, r02a): the pair kernel wins from 50 K blocks on (conv2 + fused skip conv:
+// 123 -> 116 us, the 640-channel convs), and already from 40 on the 4 x 16 level (M = 16384), where 256 single-CTA tiles fill the
+// 148 SMs 1.73 times but 64 pair tiles fit one wave (36 -> 34 us, 41 -> 37 us); the 320-channel 3 x 3 convs of the 8 x 32 level
+// (45 K blocks, 6.9 waves of single-CTA tiles) stay on the single-CTA kernel.
+static int gemm_pair_min_kblocks(int M) {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("WD_GEMM_PAIR_MINK");
-    v = e ? atoi(e) : 80;  // measured (tools/op_bench.py, bench.py): the pair kernel wins for the 640-channel 3x3 convs (>= 90 K blocks)
+    v = e ? atoi(e) : -1;
   }
-  return v;
+  if (v >= 0) return v;
+  return M <= 32768 ? 40 : 50;
 }
 bool gemm_uses_pair(const GemmArgs& a) {
   if (!gemm_pair_enabled() || !gemm_pair_supported(a)) return false;
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
-  return total_k >= gemm_pair_min_kblocks();
+  return total_k >= gemm_pair_min_kblocks(a.M);
 }
 int gemm_b_box_rows(const GemmArgs& a) {
   if (a.epi == EPI_SAMPLER) return GEMM_BLOCK_N_OUT;
