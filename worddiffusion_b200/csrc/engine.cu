@@ -45,6 +45,8 @@ int wd_set_error(int code, const char* msg) {
   return code;
 }
 extern "C" int wd_version(void) { return 1; }
+static int op_gemm_impl(const void* a_, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K,
+                        int act_silu, int geglu, int out_f32, int res_f16, int out_f16, void* stream);
 extern "C" int wd_op_gemm_block_n(void) { return gemm_tc_block_n(); }
 
 // ----------------------------------------------------------------------------------------------
@@ -222,6 +224,7 @@ struct wd_engine {
   int kv_pool_next = 0;
   // CharacterEncoder folded into lookup tables (finalize_params): T* = E W^T + b [vocab, D], P* = pe W^T [max_seq_len, D]
   float *we_tq = nullptr, *we_tk = nullptr, *we_tv = nullptr, *we_pq = nullptr, *we_pk = nullptr, *we_pv = nullptr;
+  float* temb_table = nullptr;  // time_embed(t) for t < TEMB_TABLE_ROWS, fp32 [rows, 4 mc]: built once per weight load
   float* we_gram = nullptr;  // TQ TK^T [vocab, vocab]: the scores of a position-free Word_Attention segment (ops.cu: word_attn_hist_kernel)
   std::vector<LnFold> ln_folds;
   // activations
@@ -425,6 +428,7 @@ struct Builder {
 
     e->te0 = linear("time_embed.0", ted, mc, true);
     e->te2 = linear("time_embed.2", ted, ted, true);
+    e->temb_table = A.alloc<float>(static_cast<size_t>(TEMB_TABLE_ROWS) * ted);
     // CharacterEncoder (fp32)
     const int D = c.context_dim;
     e->we_E = A.alloc<float>(static_cast<size_t>(c.vocab_size) * D);
@@ -722,6 +726,21 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
       CUDA_TRY(linear_f32_launch(e->we_pe, Ws[i], nullptr, Ps[i], c.max_seq_len, D, D, s));
     }
     CUDA_TRY(word_attn_gram_launch(e->we_tq, e->we_tk, e->we_gram, c.vocab_size, D, s));
+    // time_embed(t) for every timestep (unet.py:1575-1576: Linear, SiLU, Linear of the sinusoid): weights only, so once per load
+    {
+      const int mc = c.model_channels, ted = e->time_dim;
+      bf16 *temb_t = nullptr, *h1_t = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&temb_t), static_cast<size_t>(TEMB_TABLE_ROWS) * mc * sizeof(bf16)));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h1_t), static_cast<size_t>(TEMB_TABLE_ROWS) * ted * sizeof(bf16)));
+      int rc = WD_OK;
+      if (timestep_embed_launch(nullptr, -1, temb_t, TEMB_TABLE_ROWS, mc, s) != cudaSuccess) rc = fail(WD_ERR_CUDA, "time-embedding table: sinusoid");
+      if (rc == WD_OK) rc = op_gemm_impl(temb_t, e->te0.w, e->te0.bias, nullptr, h1_t, TEMB_TABLE_ROWS, ted, mc, 1, 0, 0, 0, 0, s);
+      if (rc == WD_OK) rc = op_gemm_impl(h1_t, e->te2.w, e->te2.bias, nullptr, e->temb_table, TEMB_TABLE_ROWS, ted, ted, 0, 0, 1, 0, 0, s);
+      cudaStreamSynchronize(s);
+      cudaFree(temb_t);
+      cudaFree(h1_t);
+      if (rc != WD_OK) return rc;
+    }
   }
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
@@ -1267,27 +1286,7 @@ struct PlanBuilder {
     bf16* emb_act = A.alloc<bf16>(static_cast<size_t>(B) * ted);
     float* emb_out = A.alloc<float>(static_cast<size_t>(B) * e->emb_all.N);
     {
-      // per-trajectory table of time_embed(t) for every timestep (fp32 [TEMB_TABLE_ROWS, ted]): part of the context ops
-      bf16* temb_t = A.alloc<bf16>(static_cast<size_t>(TEMB_TABLE_ROWS) * mc);
-      bf16* h1_t = A.alloc<bf16>(static_cast<size_t>(TEMB_TABLE_ROWS) * ted);
-      float* table = A.alloc<float>(static_cast<size_t>(TEMB_TABLE_ROWS) * ted);
-      {
-        Op op;
-        memset(&op, 0, sizeof(op));
-        op.kind = OP_TEMB;
-        op.temb = {temb_t, TEMB_TABLE_ROWS, mc, 1};
-        cops.push_back(op);
-        Epi ep;
-        ep.out = h1_t;
-        ep.out_ld = ted;
-        ep.act = ACT_SILU;
-        if (!gemm_op(cops, TEMB_TABLE_ROWS, false, 0, 0, {ASrc{temb_t, mc, mc, 1, 1, 1, 1}}, e->te0, ep)) return false;
-        Epi ep2;
-        ep2.out = table;
-        ep2.out_ld = ted;
-        ep2.out_f32 = 1;
-        if (!gemm_op(cops, TEMB_TABLE_ROWS, false, 0, 0, {ASrc{h1_t, ted, ted, 1, 1, 1, 1}}, e->te2, ep2)) return false;
-      }
+      float* table = e->temb_table;  // time_embed(t) for every timestep, built at weight load (wd_engine_finalize_params)
       {
         Op op;
         memset(&op, 0, sizeof(op));
