@@ -173,15 +173,19 @@ struct Plan {
   std::vector<Op> step_ops;
   size_t bytes = 0;
   bool context_valid = false;
-  // CUDA graph of the sampling step (wd_sampler_step): valid for one set of caller pointers; the per-step scalars live in
-  // wd_engine::sp_dev.  graph_seen counts consecutive calls with the same pointers (capture happens on the second one).
-  cudaGraphExec_t graph = nullptr;
-  const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};  // x, eps_out, noise, y
-  int graph_seen = 0;
-  int graph_launches = 0;
-  ~Plan() {
-    if (graph) cudaGraphExecDestroy(graph);
-  }
+  // CUDA graphs of the step launch sequence, each valid for one set of caller pointers: g_step for wd_sampler_step (the
+  // per-step scalars live in wd_engine::sp_dev), g_eval for wd_unet_eval with per-row timesteps (the forward() path).
+  // `seen` counts consecutive calls with the same pointers: the first runs eagerly, the second captures, later ones replay.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int seen = 0;
+    int launches = 0;
+    ~GraphSlot() {
+      if (exec) cudaGraphExecDestroy(exec);
+    }
+  };
+  GraphSlot g_step, g_eval;
 };
 
 struct Act {
@@ -1660,6 +1664,51 @@ static int check_ready(wd_engine* e, int batch) {
   return WD_OK;
 }
 
+// Step launch sequence through a CUDA graph: the first call with a set of caller pointers runs eagerly (and warms every kernel
+// up), the second captures the sequence on a private stream (the caller's may be the legacy default stream, which cannot be
+// captured; nothing runs during capture) and instantiates it, later ones replay it on the caller's stream.  `sp`: per-step
+// scalars, refreshed in device memory by a one-thread kernel (by-value argument: no host staging buffer to keep alive) before
+// every replay.  Any failure to capture leaves the slot in eager mode.
+static int run_graphed(wd_engine* e, Plan* p, Plan::GraphSlot& g, RunCtx& r, const void* const key[4], const StepParams* sp,
+                       cudaStream_t s) {
+  if (memcmp(key, g.key, sizeof(g.key)) != 0) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    memcpy(g.key, key, sizeof(g.key));
+    g.seen = 0;
+  }
+  if (++g.seen == 1 || g.seen < 0) return run_ops(e, p->step_ops, r, s);
+  if (sp) {
+    if (!e->sp_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->sp_dev), sizeof(StepParams)));
+    CUDA_TRY(set_step_params_launch(e->sp_dev, *sp, s));
+  }
+  if (!g.exec) {
+    if (sp) r.sp = e->sp_dev;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ie = cudaErrorUnknown;
+    if (!e->cap_stream && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) e->cap_stream = nullptr;
+    if (e->cap_stream && cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rc2 = run_ops(e, p->step_ops, r, e->cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+      if (rc2 == WD_OK && ce == cudaSuccess && graph) {
+        g.launches = e->last_launches;
+        ie = cudaGraphInstantiate(&g.exec, graph, 0);
+      }
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {  // capture is not available here: stay eager for these pointers
+      g.exec = nullptr;
+      g.seen = -1000000000;
+      cudaGetLastError();
+      r.sp = nullptr;
+      return run_ops(e, p->step_ops, r, s);
+    }
+  }
+  CUDA_TRY(cudaGraphLaunch(g.exec, s));
+  e->last_launches = g.launches;
+  return WD_OK;
+}
+
 extern "C" int wd_unet_eval(wd_engine* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar,
                             const int64_t* y, float* eps_out, void* stream) {
   int rc = check_ready(e, batch);
@@ -1672,7 +1721,13 @@ extern "C" int wd_unet_eval(wd_engine* e, int batch, const float* x, const int64
   r.y = reinterpret_cast<const long long*>(y);
   r.eps_out = eps_out;
   r.mode = STEP_EPS_ONLY;
-  return run_ops(e, e->cur->step_ops, r, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // per-row timesteps (the forward() path): every argument of the sequence is a pointer, so the graph needs no StepParams
+  if (timesteps && step_graph_enabled() && !e->prof_on) {
+    const void* key[4] = {x, eps_out, timesteps, y};
+    return run_graphed(e, e->cur, e->cur->g_eval, r, key, nullptr, s);
+  }
+  return run_ops(e, e->cur->step_ops, r, s);
 }
 
 extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scalar, const int64_t* y, int mode,
@@ -1696,21 +1751,12 @@ extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scal
   r.coef = make_float4(coef4_host[0], coef4_host[1], coef4_host[2], coef4_host[3]);
   r.mode = mode;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // ---- CUDA-graph replay of the launch sequence (79 kernels): the second consecutive call with the same caller pointers
-  // captures it, later ones replay it; the scalars that change per step travel through sp_dev.  Small batches are bound by
-  // the host's launch rate otherwise (1.0 ms/step at batch 1).  Needs the table flavour of the time embedding.
+  // ---- CUDA-graph replay of the launch sequence (79 kernels); the scalars that change per step travel through sp_dev.  Small
+  // batches are bound by the host's launch rate otherwise.  Needs the table flavour of the time embedding.
   Plan* p = e->cur;
   const void* key[4] = {x, eps_out, noise, y};
   const bool graph_ok = step_graph_enabled() && !e->prof_on && t_scalar >= 0 && t_scalar < TEMB_TABLE_ROWS && temb_table_enabled();
   if (!graph_ok) return run_ops(e, p->step_ops, r, s);
-  if (memcmp(key, p->graph_key, sizeof(key)) != 0) {
-    if (p->graph) cudaGraphExecDestroy(p->graph);
-    p->graph = nullptr;
-    memcpy(p->graph_key, key, sizeof(key));
-    p->graph_seen = 0;
-  }
-  if (++p->graph_seen == 1 || p->graph_seen < 0) return run_ops(e, p->step_ops, r, s);  // first call with these pointers: eager
-  if (!e->sp_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->sp_dev), sizeof(StepParams)));
   StepParams sp;
   sp.t = t_scalar;
   sp.coef = r.coef;
@@ -1720,34 +1766,7 @@ extern "C" int wd_sampler_step(wd_engine* e, int batch, float* x, int64_t t_scal
   sp.use_philox = use_philox;
   sp.step_index = step_index;
   sp.pad = 0;
-  CUDA_TRY(set_step_params_launch(e->sp_dev, sp, s));
-  if (!p->graph) {
-    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured); nothing runs
-    // during capture, the instantiated graph is launched on the caller's stream
-    r.sp = e->sp_dev;
-    cudaGraph_t g = nullptr;
-    cudaError_t ie = cudaErrorUnknown;
-    if (!e->cap_stream && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) e->cap_stream = nullptr;
-    if (e->cap_stream && cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int rc2 = run_ops(e, p->step_ops, r, e->cap_stream);
-      const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
-      if (rc2 == WD_OK && ce == cudaSuccess && g) {
-        p->graph_launches = e->last_launches;
-        ie = cudaGraphInstantiate(&p->graph, g, 0);
-      }
-    }
-    if (g) cudaGraphDestroy(g);
-    if (ie != cudaSuccess) {  // capture is not available here: stay eager for these pointers
-      p->graph = nullptr;
-      p->graph_seen = -1000000000;
-      cudaGetLastError();
-      r.sp = nullptr;
-      return run_ops(e, p->step_ops, r, s);
-    }
-  }
-  CUDA_TRY(cudaGraphLaunch(p->graph, s));
-  e->last_launches = p->graph_launches;
-  return WD_OK;
+  return run_graphed(e, p, p->g_step, r, key, &sp, s);
 }
 
 // ----------------------------------------------------------------------------------------------
