@@ -26,8 +26,12 @@ WD_DEVINL void load8f(const float* p, float (&f)[8]) {
 }
 // d/dz silu(z) = s (1 + z (1 - s)),  s = sigmoid(z)
 WD_DEVINL float silu_grad_f(float z) {
-  const float s = 1.0f / (1.0f + __expf(-z));
-  return s * (1.0f + z * (1.0f - s));
+  // MUFU.EX2 + MUFU.RCP (rel. error ~2^-22): the IEEE division expands to ~8 instructions plus a slow-path call, and ncu
+  // showed the GroupNorm backward passes issue-bound, not HBM-bound
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  const float s = rcp_fast(1.0f + e);
+  return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
 }  // namespace
