@@ -266,6 +266,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const bool ln_consume = args.ln_stats != nullptr;
       const int bar_id = 1 + grp;
       const bool leader_warp = (q == 0);
+      float ln_S = 0.f, ln_Q = 0.f;
+      auto ln_fetch = [&](int m_) {
+        ln_S = 0.f;
+        ln_Q = 0.f;
+        if (ln_consume && m_ < args.M) {
+          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m_) * args.ln_slots;
+          for (int i = 0; i < args.ln_slots; ++i) {
+            const float2 t = __ldg(st + i);
+            ln_S += t.x;
+            ln_Q += t.y;
+          }
+        }
+      };
       for (int tile = blockIdx.x + grp * gridDim.x, itg = grp; tile < total_tiles; tile += 2 * gridDim.x, itg += 2) {
         const int n_tile = tile % n_tiles;
         const int m0 = (tile / n_tiles) * GEMM_BLOCK_M;
@@ -283,19 +296,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           __syncwarp();
         }
+        // LayerNorm row statistics of this tile: fetched one tile ahead (their load latency was part of every tile's chain)
+        if (itg == grp) ln_fetch(m);
         float ln_rstd = 1.f, ln_rstd_mu = 0.f;
         if (ln_consume && valid) {
-          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m) * args.ln_slots;
-          float S = 0.f, Q = 0.f;
-          for (int i = 0; i < args.ln_slots; ++i) {
-            const float2 t = __ldg(st + i);
-            S += t.x;
-            Q += t.y;
-          }
           const float inv = 1.0f / static_cast<float>(args.ln_dim);
-          const float mu = S * inv;
-          ln_rstd = rsqrtf(fmaxf(Q * inv - mu * mu, 0.f) + args.ln_eps);
+          const float mu = ln_S * inv;
+          ln_rstd = rsqrtf(fmaxf(ln_Q * inv - mu * mu, 0.f) + args.ln_eps);
           ln_rstd_mu = ln_rstd * mu;
+        }
+        {
+          const int next = tile + 2 * gridDim.x;
+          if (next < total_tiles) ln_fetch((next / n_tiles) * GEMM_BLOCK_M + row);
         }
         mbar_wait(&tmem_full_bar[grp], (itg >> 1) & 1);
         tc_fence_after();
@@ -414,6 +426,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (has_res && leader_warp && static_cast<int>(blockIdx.x) < total_tiles) {
         if (elect_one()) issue_res_load(blockIdx.x, 0);
       }
+      float std_ln_S = 0.f, std_ln_Q = 0.f;
+      auto std_ln_fetch = [&](int m_) {
+        std_ln_S = 0.f;
+        std_ln_Q = 0.f;
+        if (m_ < args.M) {
+          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m_) * args.ln_slots;
+          for (int i = 0; i < args.ln_slots; ++i) {
+            const float2 t = __ldg(st + i);
+            std_ln_S += t.x;
+            std_ln_Q += t.y;
+          }
+        }
+      };
       uint4 att_pf[3];  // ATT builds: this thread's share of the next tile's K / V rows
       auto att_fetch = [&](int m0_, int n0_) {
         if constexpr (ATT) {
@@ -479,19 +504,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
 
         WD_TRACE(1);
+        // LayerNorm row statistics: this tile's were fetched one tile ahead (std_ln_fetch), the next tile's are requested now
         float ln_rstd = 0.f, ln_rstd_mu = 0.f;
-        if (ln_consume && valid) {
-          const float2* st = reinterpret_cast<const float2*>(args.ln_stats) + static_cast<size_t>(m) * args.ln_slots;
-          float S = 0.f, Q = 0.f;
-          for (int i = 0; i < args.ln_slots; ++i) {
-            const float2 t = __ldg(st + i);
-            S += t.x;
-            Q += t.y;
+        if (ln_consume) {
+          if (it == 0) std_ln_fetch(m);
+          if (valid) {
+            const float inv = 1.0f / static_cast<float>(args.ln_dim);
+            const float mu = std_ln_S * inv;
+            ln_rstd = rsqrtf(fmaxf(std_ln_Q * inv - mu * mu, 0.f) + args.ln_eps);
+            ln_rstd_mu = ln_rstd * mu;
           }
-          const float inv = 1.0f / static_cast<float>(args.ln_dim);
-          const float mu = S * inv;
-          ln_rstd = rsqrtf(fmaxf(Q * inv - mu * mu, 0.f) + args.ln_eps);
-          ln_rstd_mu = ln_rstd * mu;
+          const int next = tile + gridDim.x;
+          if (next < total_tiles) std_ln_fetch((next / n_tiles) * GEMM_BLOCK_M + row);
         }
 
         if constexpr (ATT) {
