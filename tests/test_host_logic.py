@@ -169,3 +169,25 @@ def test_training_module_refuses_cpu():
     x = torch.zeros(1, 4, 8, 32)
     with pytest.raises(_lib.WdError):
         m(x, None, timesteps=torch.tensor([5]), context=torch.ones(1, 10, dtype=torch.long), y=torch.tensor([1]))
+
+
+def test_reduced_call_schedule_matches_oracle():
+    """The evaluation schedule of the reduced-call sampler (regenerateFromtrain2.py:536) is host logic: same predicate as the oracle
+    for every step of the reference's T = 1000 and T = 600 schedules; about a fifth of the steps evaluate the UNet."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from diffusion_oracle import DiffusionOracle
+    from worddiffusion_b200.diffusion import Diffusion
+    for T in (1000, 600, 12):
+        ours = [i for i in range(1, T) if Diffusion.reduced_call_predicate(i, T)]
+        ref = [i for i in range(1, T) if DiffusionOracle.reduced_call_predicate(i, T)]
+        assert ours == ref and (T - 1) in ours
+    assert 0.19 < len([i for i in range(1, 1000) if Diffusion.reduced_call_predicate(i, 1000)]) / 999 < 0.21
+
+
+def test_phosc_tokenizer_refuses_cpu_and_validates_words():
+    from worddiffusion_b200._lib import WdError
+    from worddiffusion_b200.phosc import PHOSC_LEN, phosc_labels
+    assert PHOSC_LEN == 165 + 604
+    with pytest.raises(WdError):
+        phosc_labels(["word"], "cpu")
