@@ -216,6 +216,31 @@ int wd_op_geglu_bwd(const void* p_bf16, const void* dout_bf16, void* dp_bf16, in
 int wd_op_attention_small_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int B,
                               int Sq, int L, int heads, float scale, void* stream);
 
+/* ==== fp32 mode (BASELINE.json north_star: "per-step predicted noise within ... 1e-4 (fp32 mode)"; configs[1] "fp32 and bf16") ====
+ * The same UNet evaluated with fp32 storage and fp32 FFMA arithmetic (csrc/f32_path.cu), as the reference does with
+ * use_fp16=False (unet.py:1193,1638): the accuracy mode beside the tcgen05 engine above.  Same call sequence as the engine:
+ * load every state_dict entry, set the positional encoding, encode the context once per trajectory, evaluate. */
+typedef struct wd_f32 wd_f32;
+int wd_f32_create(const wd_config* cfg, wd_f32** out);
+void wd_f32_destroy(wd_f32* e);
+/* copies the fp32 tensor (3x3 conv weights are repacked [Cout][tap][Cin]); every state_dict key is accepted */
+int wd_f32_load_param(wd_f32* e, const char* name, const float* src, const int64_t* shape, int ndim, void* stream);
+int wd_f32_set_pos_encoding(wd_f32* e, const float* pe, void* stream);
+/* CharacterEncoder (+ PHOSC tokens) in fp32 (unet.py:1626-1636,839-882 ; unetPhosc.py:1117-1130); synchronises `stream` once to
+ * report token ids outside the embedding table (the reference raises IndexError) */
+int wd_f32_encode_context(wd_f32* e, int batch, const int64_t* ctx_tokens, int L, const int32_t* phosc, void* stream);
+/* eps = UNetModel(x, timesteps, context, y) in fp32; arguments as wd_unet_eval */
+int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                     float* eps_out, void* stream);
+int wd_f32_last_launch_count(const wd_f32* e);
+size_t wd_f32_workspace_bytes(const wd_f32* e);
+/* single operators of the fp32 path (parity tests): 3x3 conv pad 1 (stride 1|2, or nearest-2x upsampling first), fp32 NHWC,
+ * weights in the state_dict layout [Cout,Cin,3,3]; softmax(q k^T scale) v with q [B,Sq,heads*d], k,v [B,Skv,heads*d] */
+int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W, int Cin,
+                      int Cout, int stride, int up, void* stream);
+int wd_f32_op_attention(const float* q, const float* k, const float* v, float* out, int B, int Sq, int Skv, int heads, int d,
+                        float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,162 @@
+"""GPU parity of the fp32 mode (csrc/f32_path.cu, ``model.precision = "fp32"``) through the drop-in nn.Module -> ctypes -> C ABI.
+Tolerance: BASELINE.json north_star -- fp32 mode, per-step predicted noise within 1e-4 max relative error (max |err| / max |ref|)
+of the reference; the references are the committed outputs of the UNMODIFIED reference modules (tests/golden) and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import unet_oracle as UO  # noqa: E402
+import weights as W  # noqa: E402
+from gpu_util import DEV, P, S, f32, relerr  # noqa: E402
+from worddiffusion_b200._lib import check, lib  # noqa: E402
+from worddiffusion_b200.diffusion import Diffusion  # noqa: E402
+from worddiffusion_b200.unet import UNetModel, default_args  # noqa: E402
+from worddiffusion_b200.unetPhosc import UNetModelPhosc  # noqa: E402
+
+SEED = 1234
+TOL_FP32 = 1e-4
+KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+          attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_classes=339, context_dim=320,
+          vocab_size=53, max_seq_len=10)
+
+
+def _model(cls, variant):
+    m = cls(args=default_args(DEV), **KW)
+    sd = W.make_state_dict(W.load_spec(variant), SEED)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    m.precision = "fp32"
+    return m, sd
+
+
+@pytest.fixture(scope="module")
+def unet():
+    return _model(UNetModel, "unet")
+
+
+@pytest.fixture(scope="module")
+def phosc():
+    return _model(UNetModelPhosc, "unetPhosc")
+
+
+def _cuda(inp):
+    return {k: v.to(DEV) for k, v in inp.items()}
+
+
+# ---------------------------------------------------------------- single operators
+@pytest.mark.parametrize("stride,up,Cin,Cout,B,H,W", [(1, 0, 8, 12, 3, 8, 32), (2, 0, 320, 64, 2, 8, 32), (1, 1, 16, 320, 2, 4, 16),
+                                                      (1, 0, 640, 320, 1, 4, 16)])
+def test_f32_conv3x3_operator(stride, up, Cin, Cout, B, H, W):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    xi = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    want = F.conv2d(xi.double(), w.double(), b.double(), stride=stride, padding=1).permute(0, 2, 3, 1)
+    out = torch.full(tuple(want.shape), float("nan"), device=DEV, dtype=torch.float32)
+    xd, wd, bd = f32(x.permute(0, 2, 3, 1)), f32(w), f32(b)  # named: a temporary would be recycled by the next allocation
+    check(lib().wd_f32_op_conv3x3(P(xd), P(wd), P(bd), P(out), B, H, W, Cin, Cout, stride, up, S()), "wd_f32_op_conv3x3")
+    assert relerr(out, want) < 2e-6
+
+
+@pytest.mark.parametrize("B,Sq,Skv,heads,d,scale", [(2, 64, 10, 4, 80, 80 ** -0.5), (1, 256, 779, 4, 80, 80 ** -0.5),
+                                                    (3, 10, 10, 1, 320, 1.0), (2, 37, 5, 2, 160, 0.3)])
+def test_f32_attention_operator(B, Sq, Skv, heads, d, scale):
+    g = torch.Generator().manual_seed(4)
+    q, k, v = (torch.randn(B, s, heads * d, generator=g) for s in (Sq, Skv, Skv))
+
+    def split(t):
+        return t.double().reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3)
+
+    attn = (split(q) @ split(k).transpose(-1, -2) * scale).softmax(-1)
+    want = (attn @ split(v)).permute(0, 2, 1, 3).reshape(B, Sq, heads * d)
+    out = torch.full((B, Sq, heads * d), float("nan"), device=DEV, dtype=torch.float32)
+    qd, kd, vd = f32(q), f32(k), f32(v)
+    check(lib().wd_f32_op_attention(P(qd), P(kd), P(vd), P(out), B, Sq, Skv, heads, d, scale, S()), "wd_f32_op_attention")
+    assert relerr(out, want) < 5e-6
+
+
+# ---------------------------------------------------------------- whole UNet
+def test_unet_fp32_vs_reference_golden(unet, golden_dir):
+    m, _ = unet
+    g = np.load(os.path.join(golden_dir, "unet_fwd.npz"))
+    inp = _cuda(W.make_inputs(2, seed=SEED))
+    with torch.no_grad():
+        eps = m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+    assert eps.shape == (2, 4, 8, 32) and eps.dtype == torch.float32
+    assert m._engine_f32.last_launch_count > 100 and m._engine is None  # the fp32 kernels ran, the bf16 engine was never built
+    err = relerr(eps, torch.from_numpy(g["eps"]))
+    print("unet fp32-mode eps max-rel err vs reference:", err)
+    assert err < TOL_FP32
+
+
+def test_unet_phosc_fp32_vs_reference_golden(phosc, golden_dir):
+    m, _ = phosc
+    g = np.load(os.path.join(golden_dir, "unetPhosc_fwd.npz"))
+    inp = _cuda(W.make_inputs(2, seed=SEED))
+    with torch.no_grad():
+        eps = m(inp["x"], inp["phosc"], timesteps=inp["t"], context=inp["context"], y=inp["y"])
+    err = relerr(eps, torch.from_numpy(g["eps"]))
+    print("unetPhosc fp32-mode eps max-rel err vs reference:", err)
+    assert err < TOL_FP32
+
+
+def test_unet_fp32_vs_oracle_fresh_inputs(unet):
+    m, sd = unet
+    inp = W.make_inputs(5, seed=99)
+    ci = _cuda(inp)
+    with torch.no_grad():
+        eps = m(ci["x"], None, timesteps=ci["t"], context=ci["context"], y=ci["y"])
+    ref = UO.unet_forward(sd, inp["x"], inp["t"], inp["context"], inp["y"], variant="unet")
+    err = relerr(eps, ref)
+    print("unet fp32-mode eps max-rel err vs oracle:", err)
+    assert err < TOL_FP32
+
+
+def test_ddpm_trajectory_fp32_vs_reference_golden(unet, golden_dir):
+    """T = 6 trajectory of train.py:217-236 with the reference's own pre-generated noise: per-step eps and final latent at 1e-4."""
+    m, _ = unet
+    g = np.load(os.path.join(golden_dir, "unet_ddpm_T6.npz"))
+    inp = _cuda(W.make_inputs(2, seed=SEED))
+    d = Diffusion(noise_steps=6, device=DEV)
+    x, trace = d.sample_latents(m, inp["context"], inp["y"], x_T=torch.from_numpy(g["x_T"]),
+                                noise=torch.from_numpy(g["noises"]), return_eps_trace=True)
+    for k, e in enumerate(trace):
+        err = relerr(e, torch.from_numpy(g["eps_steps"][k]))
+        print("step", k, "fp32-mode eps err", err)
+        assert err < TOL_FP32
+    err = relerr(x, torch.from_numpy(g["x_final"]))
+    print("fp32-mode final latent err", err)
+    assert err < TOL_FP32, "final latent after 5 steps, fp32 mode: 1e-4 of max |x|"
+
+
+def test_fp32_and_bf16_modes_agree(unet):
+    """The two precisions of the same module: the bf16 engine stays within its 1e-2 of the fp32 mode."""
+    m, _ = unet
+    inp = _cuda(W.make_inputs(4, seed=17))
+    with torch.no_grad():
+        e32 = m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+        m.precision = "bf16"
+        try:
+            e16 = m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+        finally:
+            m.precision = "fp32"
+    err = relerr(e16, e32)
+    print("bf16 engine vs fp32 mode:", err)
+    assert 0 < err < 1e-2
+
+
+def test_fp32_batch_invariance(unet):
+    m, _ = unet
+    big = _cuda(W.make_inputs(9, seed=21))
+    with torch.no_grad():
+        e_big = m(big["x"], None, timesteps=big["t"], context=big["context"], y=big["y"])
+        idx = torch.tensor([0, 4, 8], device=DEV)
+        e_small = m(big["x"][idx], None, timesteps=big["t"][idx], context=big["context"][idx], y=big["y"][idx])
+    assert torch.isfinite(e_big).all()
+    assert torch.equal(e_big[idx], e_small)

@@ -79,6 +79,17 @@ SIGNATURES = {
     "wd_op_geglu_fwd": (_I, [_P, _P, _I, _I, _P]),
     "wd_op_geglu_bwd": (_I, [_P, _P, _P, _I, _I, _P]),
     "wd_op_attention_small_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    # ---- fp32 mode ----
+    "wd_f32_create": (_I, [C.POINTER(WdConfig), C.POINTER(_P)]),
+    "wd_f32_destroy": (None, [_P]),
+    "wd_f32_load_param": (_I, [_P, C.c_char_p, _P, C.POINTER(_I64), _I, _P]),
+    "wd_f32_set_pos_encoding": (_I, [_P, _P, _P]),
+    "wd_f32_encode_context": (_I, [_P, _I, _P, _I, _P, _P]),
+    "wd_f32_unet_eval": (_I, [_P, _I, _P, _P, _I64, _P, _P, _P]),
+    "wd_f32_last_launch_count": (_I, [_P]),
+    "wd_f32_workspace_bytes": (C.c_size_t, [_P]),
+    "wd_f32_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "wd_f32_op_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
 }
 
 _lib = None

@@ -1,0 +1,990 @@
+// fp32 mode of the hot path (BASELINE.json north_star: "per-step predicted noise within ... 1e-4 (fp32 mode)"; configs[1]
+// "fp32 and bf16").  The reference computes everything in fp32 (use_fp16=False, unet.py:1193,1638): this file evaluates the same
+// UNet with fp32 storage and fp32 FFMA arithmetic -- no tensor cores, no 16-bit tensor anywhere -- so that the result can be held
+// against the reference at 1e-4.  It is the accuracy mode; the throughput mode is the tcgen05 engine (engine.cu).
+//
+// Layout: activations fp32 token-major [B*H*W, C] (NHWC), the latent in / eps out fp32 NCHW as at the reference seam.
+// Weights: nn.Linear / 1x1 conv as stored ([N, K]); 3x3 conv repacked once to [Cout][tap][Cin] (k = tap*Cin + c) so that a
+// 16-wide K block of the implicit GEMM is one contiguous channel run of one shifted pixel.
+// The walker recovers the layer sequence from the loaded state_dict keys (unet.py:1248-1458 builds them in this order).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wd_b200.h"
+#include "engine_internal.h"
+
+namespace {
+
+// =====================================================================================================
+// Implicit-GEMM / GEMM:  out[m, n] = act( sum_k A(m, k) W[n, k] + bias[n] + rowbias[sample(m), n] + residual[m, n] )
+// A(m, k): k = tap*Cin + c, pixel = shifted (stride / nearest-2x aware) input pixel of output pixel m, channel c from the
+// channel concatenation of up to two NHWC sources (torch.cat([h, hs.pop()], dim=1), unet.py:1750, is never materialised).
+// 128 x 64 output tile, BK = 16, 256 threads, 8 x 4 accumulators per thread, register-staged prefetch of the next K block.
+// =====================================================================================================
+struct GemmF32 {
+  const float* a1;
+  const float* a2;
+  int C1, C2;
+  int taps;  // 1: plain GEMM (pixel = m), 9: 3x3 pad 1
+  int Hin, Win, Hout, Wout;
+  int stride;  // conv stride (Downsample: 2, unet.py:540)
+  int up;      // nearest x2 before the conv (Upsample, unet.py:497)
+  int a_nchw;  // a1 is the fp32 NCHW latent (conv_in)
+  const float* w;
+  const float* bias;
+  const float* rowbias;
+  int rb_ld;
+  const float* residual;
+  float* out;
+  int out_nchw;
+  int M, N, K;
+  int act_silu;
+};
+
+constexpr int BM = 128, BN = 64, BK = 16, LDA_S = BM + 4, LDB_S = BN + 4;
+
+struct RowCtx {  // per-thread decode of its A row
+  int valid;
+  int b, oh, ow;
+  size_t pix;
+};
+
+__device__ __forceinline__ float4 load_a4(const GemmF32& g, const RowCtx& r, int k) {
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!r.valid || k >= g.K) return z;
+  const int Cin = g.C1 + g.C2;
+  int c = k;
+  size_t pix = r.pix;
+  int ih = 0, iw = 0;
+  if (g.taps != 1) {
+    const int tap = k / Cin;
+    c = k - tap * Cin;
+    const int kh = tap / 3, kw = tap - kh * 3;
+    ih = r.oh * g.stride + kh - 1;
+    iw = r.ow * g.stride + kw - 1;
+    const int Hs = g.up ? 2 * g.Hin : g.Hin, Ws = g.up ? 2 * g.Win : g.Win;
+    if (ih < 0 || ih >= Hs || iw < 0 || iw >= Ws) return z;
+    if (g.up) {
+      ih >>= 1;
+      iw >>= 1;
+    }
+    pix = (static_cast<size_t>(r.b) * g.Hin + ih) * g.Win + iw;
+  }
+  if (g.a_nchw) {  // C1 == 4 channels of one pixel, plane stride Hin*Win
+    const size_t plane = static_cast<size_t>(g.Hin) * g.Win;
+    const float* p = g.a1 + (static_cast<size_t>(r.b) * g.C1 + c) * plane + static_cast<size_t>(ih) * g.Win + iw;
+    return make_float4(p[0], p[plane], p[2 * plane], p[3 * plane]);
+  }
+  if (c < g.C1) return *reinterpret_cast<const float4*>(g.a1 + pix * g.C1 + c);
+  return *reinterpret_cast<const float4*>(g.a2 + pix * g.C2 + (c - g.C1));
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(256) f32_gemm_kernel(const GemmF32 g) {
+  __shared__ __align__(16) float As[BK][LDA_S];
+  __shared__ __align__(16) float Bs[BK][LDB_S];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // A staging: row am, float4 columns aq and aq + 2 of the 16-wide K block
+  const int am = tid & (BM - 1), aq = tid >> 7;
+  RowCtx r;
+  {
+    const int m = m0 + am;
+    r.valid = m < g.M;
+    r.b = r.oh = r.ow = 0;
+    r.pix = static_cast<size_t>(m);
+    if (r.valid && g.taps != 1) {
+      const int hw = g.Hout * g.Wout;
+      r.b = m / hw;
+      const int rem = m - r.b * hw;
+      r.oh = rem / g.Wout;
+      r.ow = rem - r.oh * g.Wout;
+    }
+  }
+  // B staging: weight row bn, float4 column bq
+  const int bn = tid & (BN - 1), bq = tid >> 6;
+  const bool b_ok = (n0 + bn) < g.N;
+  const float* wrow = g.w + static_cast<size_t>(b_ok ? n0 + bn : 0) * g.K;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float4 ra0 = load_a4(g, r, aq * 4), ra1 = load_a4(g, r, (aq + 2) * 4);
+  float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b_ok && bq * 4 < g.K) rb = *reinterpret_cast<const float4*>(wrow + bq * 4);
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    As[aq * 4 + 0][am] = ra0.x;
+    As[aq * 4 + 1][am] = ra0.y;
+    As[aq * 4 + 2][am] = ra0.z;
+    As[aq * 4 + 3][am] = ra0.w;
+    As[aq * 4 + 8][am] = ra1.x;
+    As[aq * 4 + 9][am] = ra1.y;
+    As[aq * 4 + 10][am] = ra1.z;
+    As[aq * 4 + 11][am] = ra1.w;
+    Bs[bq * 4 + 0][bn] = rb.x;
+    Bs[bq * 4 + 1][bn] = rb.y;
+    Bs[bq * 4 + 2][bn] = rb.z;
+    Bs[bq * 4 + 3][bn] = rb.w;
+    __syncthreads();
+    const int kn = k0 + BK;
+    if (kn < g.K) {
+      ra0 = load_a4(g, r, kn + aq * 4);
+      ra1 = load_a4(g, r, kn + (aq + 2) * 4);
+      rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b_ok && kn + bq * 4 < g.K) rb = *reinterpret_cast<const float4*>(wrow + kn + bq * 4);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a_lo = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a_hi = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int hw_out = g.Hout * g.Wout;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= g.M) continue;
+    const int sample = (g.rowbias || g.out_nchw) ? m / hw_out : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      if (g.rowbias) v += g.rowbias[static_cast<size_t>(sample) * g.rb_ld + n];
+      if (g.residual) v += g.residual[static_cast<size_t>(m) * g.N + n];
+      if (g.act_silu) v = silu_f(v);
+      if (g.out_nchw)
+        g.out[(static_cast<size_t>(sample) * g.N + n) * hw_out + (m - sample * hw_out)] = v;
+      else
+        g.out[static_cast<size_t>(m) * g.N + n] = v;
+    }
+  }
+}
+
+// =====================================================================================================
+// GroupNorm(32 groups) (+SiLU), unet.py:429-431 / 161-162, over the channel concatenation of up to two NHWC sources.
+// One CTA per (group, sample); mean, then the centred second moment (two passes), then the apply pass.
+// =====================================================================================================
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+__global__ void __launch_bounds__(256) f32_groupnorm_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1,
+                                                            int C2, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ out, int HW,
+                                                            int groups, float eps, int silu) {
+  __shared__ float red[32];
+  const int C = C1 + C2, cg = C / groups;
+  const int grp = blockIdx.x, b = blockIdx.y;
+  const int c0 = grp * cg;
+  const int n = HW * cg;
+  auto at = [&](int i) -> float {
+    const int p = i / cg, c = c0 + (i - p * cg);
+    const size_t pix = static_cast<size_t>(b) * HW + p;
+    return c < C1 ? a1[pix * C1 + c] : a2[pix * C2 + (c - C1)];
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += at(i);
+  const float mean = block_sum(s, red) / static_cast<float>(n);
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = at(i) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q, red) / static_cast<float>(n);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int p = i / cg, c = c0 + (i - p * cg);
+    float v = (at(i) - mean) * rstd * gamma[c] + beta[c];
+    if (silu) v = silu_f(v);
+    out[(static_cast<size_t>(b) * HW + p) * C + c] = v;
+  }
+}
+
+// nn.LayerNorm(C), eps 1e-5 (unet.py:314-316): one warp per token
+__global__ void __launch_bounds__(256) f32_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ out, int M,
+                                                            int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    q = fmaf(d, d, q);
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
+  float* orow = out + static_cast<size_t>(row) * C;
+  for (int c = lane; c < C; c += 32) orow[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+
+// =====================================================================================================
+// softmax(q k^T scale) v (CrossAttention.forward unet.py:185-207; Word_Attention unet.py:825-836 with heads = 1, scale = 1).
+// One warp per (query, head, sample); lane l owns channels l, l + 32, ...; keys in groups of four; online softmax in fp32.
+// =====================================================================================================
+template <int NPL>
+__global__ void __launch_bounds__(256) f32_attention_kernel(const float* __restrict__ q, size_t q_bs, int ldq,
+                                                            const float* __restrict__ k, const float* __restrict__ v,
+                                                            size_t kv_bs, int ldkv, float* __restrict__ out, size_t o_bs, int ldo,
+                                                            int B, int Sq, int Skv, int heads, int d, float scale) {
+  const size_t wid = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = static_cast<size_t>(B) * heads * Sq;
+  if (wid >= total) return;
+  const int qi = static_cast<int>(wid % Sq);
+  const int h = static_cast<int>((wid / Sq) % heads);
+  const int b = static_cast<int>(wid / (static_cast<size_t>(Sq) * heads));
+  const float* qp = q + b * q_bs + static_cast<size_t>(qi) * ldq + h * d;
+  const float* kp = k + b * kv_bs + h * d;
+  const float* vp = v + b * kv_bs + h * d;
+  float qr[NPL], o[NPL];
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int c = lane + 32 * j;
+    qr[j] = c < d ? qp[c] : 0.f;
+    o[j] = 0.f;
+  }
+  float mx = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < Skv; j0 += 4) {
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float part = 0.f;
+      if (j0 + u < Skv) {
+        const float* kr = kp + static_cast<size_t>(j0 + u) * ldkv;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int c = lane + 32 * j;
+          if (c < d) part = fmaf(qr[j], kr[c], part);
+        }
+      }
+      s[u] = part;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+    float mnew = mx;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = (j0 + u < Skv) ? s[u] * scale : -INFINITY;
+      mnew = fmaxf(mnew, s[u]);
+    }
+    const float corr = expf(mx - mnew);  // mx = -inf on the first group: exp(-inf) = 0
+    l *= corr;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) o[j] *= corr;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u >= Skv) continue;
+      const float p = expf(s[u] - mnew);
+      l += p;
+      const float* vr = vp + static_cast<size_t>(j0 + u) * ldkv;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < d) o[j] = fmaf(p, vr[c], o[j]);
+      }
+    }
+    mx = mnew;
+  }
+  float* op = out + b * o_bs + static_cast<size_t>(qi) * ldo + h * d;
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int c = lane + 32 * j;
+    if (c < d) op[c] = o[j] / l;
+  }
+}
+
+// ---- small elementwise kernels -------------------------------------------------------------------------
+// timestep_embedding (unet.py:96-116): [B, dim] = cat(cos(t f), sin(t f)), f_i = exp(-ln(1e4) i / half)
+__global__ void f32_timestep_kernel(const long long* __restrict__ t_dev, long long t_scalar, float* __restrict__ out, int B,
+                                    int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx - b * half;
+  const float t = static_cast<float>(t_dev ? t_dev[b] : t_scalar);
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+  const float arg = t * freq;
+  out[static_cast<size_t>(b) * dim + i] = cosf(arg);
+  out[static_cast<size_t>(b) * dim + half + i] = sinf(arg);
+}
+
+// emb = time_embed(...) (+ label_emb[y], unet.py:1578-1581); semb = SiLU(emb) (the first op of every ResBlock.emb_layers)
+__global__ void f32_emb_finish_kernel(float* __restrict__ emb, const float* __restrict__ label_w, const long long* __restrict__ y,
+                                      float* __restrict__ semb, int B, int D, int num_classes, int* __restrict__ bad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, c = idx - b * D;
+  float v = emb[idx];
+  if (label_w) {
+    const long long cls = y[b];
+    if (cls < 0 || cls >= num_classes) {
+      *bad = 1;
+    } else {
+      v += label_w[static_cast<size_t>(cls) * D + c];
+    }
+  }
+  emb[idx] = v;
+  semb[idx] = silu_f(v);
+}
+
+// GEGLU (unet.py:122-130): out[m, j] = p[m, j] * gelu(p[m, H + j]), exact erf GELU (F.gelu default)
+__global__ void f32_geglu_kernel(const float* __restrict__ p, float* __restrict__ out, size_t M, int H) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * H) return;
+  const size_t m = idx / H;
+  const int j = static_cast<int>(idx - m * H);
+  const float a = p[m * 2 * H + j], gt = p[m * 2 * H + H + j];
+  out[idx] = a * (0.5f * gt * (1.0f + erff(gt * 0.70710678118654752440f)));
+}
+
+// CharacterEncoder embedding (+ positional encoding), unet.py:851-872: tokens int64 or int32
+__global__ void f32_embed_tokens_kernel(const long long* __restrict__ tok64, const int* __restrict__ tok32,
+                                        const float* __restrict__ table, const float* __restrict__ pe, float* __restrict__ out,
+                                        int B, int L, int D, int vocab, int* __restrict__ bad) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * L * D) return;
+  const int c = static_cast<int>(idx % D);
+  const size_t row = idx / D;
+  const int pos = static_cast<int>(row % L);
+  const long long t = tok64 ? tok64[row] : static_cast<long long>(tok32[row]);
+  if (t < 0 || t >= vocab) {
+    *bad = 1;
+    out[idx] = 0.f;
+    return;
+  }
+  float v = table[static_cast<size_t>(t) * D + c];
+  if (pe) v += pe[static_cast<size_t>(pos) * D + c];
+  out[idx] = v;
+}
+
+// [Cout, Cin, 3, 3] -> [Cout][tap][Cin]
+__global__ void f32_pack_conv_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(Cout) * Cin * 9;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cin);
+  const int tap = static_cast<int>((idx / Cin) % 9);
+  const size_t n = idx / (static_cast<size_t>(Cin) * 9);
+  dst[idx] = w[(n * Cin + c) * 9 + tap];
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct Param {
+  float* p = nullptr;
+  size_t n = 0;
+  std::vector<int64_t> shape;
+  bool packed3x3 = false;
+};
+
+struct Act {  // token-major activation
+  float* p = nullptr;
+  int H = 0, W = 0, C = 0;
+};
+
+}  // namespace
+
+struct wd_f32 {
+  wd_config cfg{};
+  std::map<std::string, Param> params;
+  float* pe = nullptr;
+  // encoded context of the last wd_f32_encode_context
+  float* ctx = nullptr;
+  size_t ctx_cap = 0;
+  int ctx_B = 0, ctx_L = 0;
+  int* bad_flag = nullptr;
+  // activation arena (per eval, bump allocated)
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+  bool dry = false;
+  int launches = 0;
+  cudaStream_t s = nullptr;
+  std::string err;
+};
+
+namespace {
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(int code, const std::string& m) { throw Fail{code, m}; }
+
+const Param& P(wd_f32* e, const std::string& k) {
+  auto it = e->params.find(k);
+  if (it == e->params.end()) fail(WD_ERR_STATE, "fp32 path: state_dict key not loaded: " + k);
+  return it->second;
+}
+bool has(wd_f32* e, const std::string& k) { return e->params.count(k) != 0; }
+
+float* alloc(wd_f32* e, size_t floats) {
+  const size_t bytes = (floats * sizeof(float) + 255) & ~static_cast<size_t>(255);
+  const size_t off = e->arena_off;
+  e->arena_off += bytes;
+  if (e->dry) return reinterpret_cast<float*>(static_cast<uintptr_t>(256));  // never dereferenced
+  if (e->arena_off > e->arena_cap) fail(WD_ERR_STATE, "fp32 path: activation arena overflow");
+  return reinterpret_cast<float*>(e->arena + off);
+}
+
+void after_launch(wd_f32* e, const char* what) {
+  ++e->launches;
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: ") + what + ": " + cudaGetErrorString(ce));
+}
+
+// generic implicit GEMM launch
+struct ConvSpec {
+  int taps = 1, stride = 1, up = 0, a_nchw = 0, out_nchw = 0, silu = 0;
+};
+
+Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, const float* bias, const float* rowbias,
+         int rb_ld, const float* residual, const ConvSpec& cs, float* out_override = nullptr) {
+  GemmF32 g{};
+  g.a1 = a1.p;
+  g.a2 = a2 ? a2->p : nullptr;
+  g.C1 = a1.C;
+  g.C2 = a2 ? a2->C : 0;
+  if (a2 && (a2->H != a1.H || a2->W != a1.W)) fail(WD_ERR_INVALID, "fp32 path: concat sources differ in size");
+  if ((g.C1 & 3) || (g.C2 & 3)) fail(WD_ERR_UNSUPPORTED, "fp32 path: channel counts must be multiples of 4");
+  g.taps = cs.taps;
+  g.Hin = a1.H;
+  g.Win = a1.W;
+  g.stride = cs.stride;
+  g.up = cs.up;
+  g.Hout = cs.up ? a1.H * 2 : (cs.stride == 2 ? a1.H / 2 : a1.H);
+  g.Wout = cs.up ? a1.W * 2 : (cs.stride == 2 ? a1.W / 2 : a1.W);
+  g.a_nchw = cs.a_nchw;
+  g.w = w;
+  g.bias = bias;
+  g.rowbias = rowbias;
+  g.rb_ld = rb_ld;
+  g.residual = residual;
+  g.out_nchw = cs.out_nchw;
+  g.M = B * g.Hout * g.Wout;
+  g.N = N;
+  g.K = cs.taps * (g.C1 + g.C2);
+  g.act_silu = cs.silu;
+  Act o;
+  o.H = g.Hout;
+  o.W = g.Wout;
+  o.C = N;
+  o.p = out_override ? out_override : alloc(e, static_cast<size_t>(g.M) * N);
+  g.out = o.p;
+  if (!e->dry) {
+    dim3 grid((g.M + BM - 1) / BM, (N + BN - 1) / BN);
+    f32_gemm_kernel<<<grid, 256, 0, e->s>>>(g);
+    after_launch(e, "gemm");
+  }
+  return o;
+}
+
+// nn.Linear / 1x1 conv by state_dict prefix
+Act linear(wd_f32* e, const std::string& pfx, const Act& a, int B, bool bias, const float* residual = nullptr, int silu = 0,
+           const Act* a2 = nullptr) {
+  const Param& w = P(e, pfx + ".weight");
+  const int N = static_cast<int>(w.shape[0]);
+  int K = 1;
+  for (size_t i = 1; i < w.shape.size(); ++i) K *= static_cast<int>(w.shape[i]);
+  if (K != a.C + (a2 ? a2->C : 0)) fail(WD_ERR_INVALID, "fp32 path: " + pfx + ": input width does not match the weight");
+  ConvSpec cs;
+  cs.silu = silu;
+  return gemm(e, a, a2, B, w.p, N, bias ? P(e, pfx + ".bias").p : nullptr, nullptr, 0, residual, cs);
+}
+
+Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, const float* rowbias, int rb_ld,
+            const float* residual, int stride, int up) {
+  const Param& w = P(e, pfx + ".weight");
+  if (!w.packed3x3) fail(WD_ERR_INVALID, "fp32 path: " + pfx + " is not a 3x3 convolution");
+  if (w.shape[1] != a.C + (a2 ? a2->C : 0)) fail(WD_ERR_INVALID, "fp32 path: " + pfx + ": input channels do not match the weight");
+  ConvSpec cs;
+  cs.taps = 9;
+  cs.stride = stride;
+  cs.up = up;
+  return gemm(e, a, a2, B, w.p, static_cast<int>(w.shape[0]), P(e, pfx + ".bias").p, rowbias, rb_ld, residual, cs);
+}
+
+Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, float eps, int silu) {
+  Act o;
+  o.H = a.H;
+  o.W = a.W;
+  o.C = a.C + (a2 ? a2->C : 0);
+  if (o.C % 32) fail(WD_ERR_UNSUPPORTED, "fp32 path: GroupNorm32 needs channels % 32 == 0");
+  o.p = alloc(e, static_cast<size_t>(B) * a.H * a.W * o.C);
+  if (!e->dry) {
+    f32_groupnorm_kernel<<<dim3(32, B), 256, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, a.C, a2 ? a2->C : 0, P(e, pfx + ".weight").p,
+                                                       P(e, pfx + ".bias").p, o.p, a.H * a.W, 32, eps, silu);
+    after_launch(e, "groupnorm");
+  }
+  return o;
+}
+
+Act layernorm(wd_f32* e, const std::string& pfx, const Act& a, int B) {
+  Act o = a;
+  const int M = B * a.H * a.W;
+  o.p = alloc(e, static_cast<size_t>(M) * a.C);
+  if (!e->dry) {
+    f32_layernorm_kernel<<<(M + 7) / 8, 256, 0, e->s>>>(a.p, P(e, pfx + ".weight").p, P(e, pfx + ".bias").p, o.p, M, a.C, 1e-5f);
+    after_launch(e, "layernorm");
+  }
+  return o;
+}
+
+void attention(wd_f32* e, const float* q, size_t q_bs, int ldq, const float* k, const float* v, size_t kv_bs, int ldkv, float* out,
+               size_t o_bs, int ldo, int B, int Sq, int Skv, int heads, int d, float scale) {
+  if (e->dry) return;
+  const size_t warps = static_cast<size_t>(B) * heads * Sq;
+  const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+  if (d <= 96)
+    f32_attention_kernel<3><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
+  else if (d <= 160)
+    f32_attention_kernel<5><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
+  else if (d <= 320)
+    f32_attention_kernel<10><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
+  else
+    fail(WD_ERR_UNSUPPORTED, "fp32 path: attention head width > 320");
+  after_launch(e, "attention");
+}
+
+int heads_of(const wd_config& c, int ch) { return c.num_head_channels > 0 ? ch / c.num_head_channels : c.num_heads; }
+
+// CrossAttention.forward (unet.py:185-279 / unetPhosc.py:176-198); ctx == nullptr: self-attention.  Returns to_out(...) + residual
+Act cross_attention(wd_f32* e, const std::string& pfx, const Act& xq, int B, const Act* ctx, const float* residual) {
+  const Act& kvsrc = ctx ? *ctx : xq;
+  Act q = linear(e, pfx + "to_q", xq, B, false);
+  Act k = linear(e, pfx + "to_k", kvsrc, B, false);
+  Act v = linear(e, pfx + "to_v", kvsrc, B, false);
+  const int Sq = xq.H * xq.W, Skv = kvsrc.H * kvsrc.W, inner = q.C;
+  const int heads = heads_of(e->cfg, inner), d = inner / heads;
+  Act o = q;
+  o.p = alloc(e, static_cast<size_t>(B) * Sq * inner);
+  attention(e, q.p, static_cast<size_t>(Sq) * inner, inner, k.p, v.p, static_cast<size_t>(Skv) * inner, inner, o.p,
+            static_cast<size_t>(Sq) * inner, inner, B, Sq, Skv, heads, d, 1.0f / sqrtf(static_cast<float>(d)));
+  return linear(e, pfx + "to_out.0", o, B, true, residual);
+}
+
+// SpatialTransformer.forward (unet.py:381-412 / unetPhosc.py:282-300) with BasicTransformerBlock (unet.py:337-345 / unetPhosc.py:241-246)
+Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, const Act& ctx) {
+  Act n = groupnorm(e, pfx + "norm", x, nullptr, B, 1e-6f, 0);
+  Act t = linear(e, pfx + "proj_in", n, B, true);
+  for (int dpt = 0; dpt < e->cfg.transformer_depth; ++dpt) {
+    const std::string bp = pfx + "transformer_blocks." + std::to_string(dpt) + ".";
+    if (e->cfg.variant == WD_VARIANT_UNET) {
+      Act l1 = layernorm(e, bp + "norm2", t, B);
+      t = cross_attention(e, bp + "attn1.", l1, B, &ctx, t.p);
+      Act l2 = layernorm(e, bp + "norm2", t, B);
+      t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p);
+    } else {
+      Act l1 = layernorm(e, bp + "norm1", t, B);
+      t = cross_attention(e, bp + "attn1.", l1, B, nullptr, t.p);
+      Act l2 = layernorm(e, bp + "norm2", t, B);
+      t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p);
+    }
+    Act l3 = layernorm(e, bp + "norm3", t, B);
+    Act pr = linear(e, bp + "ff.net.0.proj", l3, B, true);
+    const int Hd = pr.C / 2;
+    const size_t M = static_cast<size_t>(B) * t.H * t.W;
+    Act gg = t;
+    gg.C = Hd;
+    gg.p = alloc(e, M * Hd);
+    if (!e->dry) {
+      f32_geglu_kernel<<<static_cast<unsigned>((M * Hd + 255) / 256), 256, 0, e->s>>>(pr.p, gg.p, M, Hd);
+      after_launch(e, "geglu");
+    }
+    t = linear(e, bp + "ff.net.2", gg, B, true, t.p);
+  }
+  return linear(e, pfx + "proj_out", t, B, true, x.p);
+}
+
+// ResBlock._forward (unet.py:646-671), input = channel concat of a (and a2)
+Act res_block(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, const Act& semb) {
+  Act g1 = groupnorm(e, pfx + "in_layers.0", a, a2, B, 1e-5f, 1);
+  Act eo = linear(e, pfx + "emb_layers.1", semb, B, true);
+  Act h1 = conv3x3(e, pfx + "in_layers.2", g1, nullptr, B, eo.p, eo.C, nullptr, 1, 0);
+  Act g2 = groupnorm(e, pfx + "out_layers.0", h1, nullptr, B, 1e-5f, 1);
+  const float* skip;
+  if (has(e, pfx + "skip_connection.weight")) {
+    skip = linear(e, pfx + "skip_connection", a, B, true, nullptr, 0, a2).p;
+  } else {
+    if (a2) fail(WD_ERR_INVALID, "fp32 path: ResBlock without skip_connection fed by a concatenation");
+    skip = a.p;
+  }
+  return conv3x3(e, pfx + "out_layers.3", g2, nullptr, B, nullptr, 0, skip, 1, 0);
+}
+
+// TimestepEmbedSequential.forward (unet.py:452-469): sub-layer kinds recovered from the keys
+Act run_block(wd_f32* e, const std::string& pfx, Act h, const Act* cat, int B, const Act& semb, const Act& ctx, const float* x_nchw) {
+  for (int j = 0;; ++j) {
+    const std::string p = pfx + std::to_string(j) + ".";
+    if (has(e, p + "in_layers.0.weight")) {
+      h = res_block(e, p, h, j == 0 ? cat : nullptr, B, semb);
+    } else if (has(e, p + "proj_in.weight")) {
+      h = spatial_transformer(e, p, h, B, ctx);
+    } else if (has(e, p + "op.weight")) {
+      h = conv3x3(e, p + "op", h, nullptr, B, nullptr, 0, nullptr, 2, 0);
+    } else if (has(e, p + "conv.weight")) {
+      h = conv3x3(e, p + "conv", h, nullptr, B, nullptr, 0, nullptr, 1, 1);
+    } else if (has(e, p + "weight")) {  // input_blocks.0.0: conv_in over the NCHW latent
+      const Param& w = P(e, p + "weight");
+      ConvSpec cs;
+      cs.taps = 9;
+      cs.a_nchw = 1;
+      Act lat;
+      lat.p = const_cast<float*>(x_nchw);
+      lat.H = e->cfg.latent_h;
+      lat.W = e->cfg.latent_w;
+      lat.C = e->cfg.in_channels;
+      if (lat.C != 4) fail(WD_ERR_UNSUPPORTED, "fp32 path: in_channels must be 4");
+      h = gemm(e, lat, nullptr, B, w.p, static_cast<int>(w.shape[0]), P(e, p + "bias").p, nullptr, 0, nullptr, cs);
+    } else {
+      if (j == 0) fail(WD_ERR_STATE, "fp32 path: empty block " + pfx);
+      break;
+    }
+  }
+  return h;
+}
+
+void encode_one(wd_f32* e, int B, const long long* tok64, const int* tok32, int L, bool use_pe, float* out, size_t o_bs) {
+  const int D = e->cfg.context_dim;
+  Act x;
+  x.H = 1;
+  x.W = L;
+  x.C = D;
+  x.p = alloc(e, static_cast<size_t>(B) * L * D);
+  if (!e->dry) {
+    const size_t n = static_cast<size_t>(B) * L * D;
+    f32_embed_tokens_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, e->s>>>(
+        tok64, tok32, P(e, "word_emb.embedding.weight").p, use_pe ? e->pe : nullptr, x.p, B, L, D, e->cfg.vocab_size, e->bad_flag);
+    after_launch(e, "embed_tokens");
+  }
+  Act q = linear(e, "word_emb.attention.linear_query", x, B, true);
+  Act k = linear(e, "word_emb.attention.linear_key", x, B, true);
+  Act v = linear(e, "word_emb.attention.linear_value", x, B, true);
+  attention(e, q.p, static_cast<size_t>(L) * D, D, k.p, v.p, static_cast<size_t>(L) * D, D, out, o_bs, D, B, L, L, 1, D, 1.0f);
+}
+
+void encode_context_impl(wd_f32* e, int B, const long long* tokens, int L, const int* phosc) {
+  const int D = e->cfg.context_dim;
+  const bool is_unet = e->cfg.variant == WD_VARIANT_UNET;
+  const int PL = (!is_unet && phosc) ? e->cfg.phosc_len : 0;
+  const int Lt = L + PL;
+  if (is_unet && L > e->cfg.max_seq_len) fail(WD_ERR_INVALID, "fp32 path: context longer than max_seq_len (unet.py:872 would fail to broadcast)");
+  const size_t o_bs = static_cast<size_t>(Lt) * D;
+  // CharacterEncoder (unet.py:851-874: PE always; unetPhosc.py:721-731: PE only if len <= max_seq_len)
+  encode_one(e, B, tokens, nullptr, L, is_unet || L <= e->cfg.max_seq_len, e->ctx, o_bs);
+  if (PL) encode_one(e, B, nullptr, phosc, PL, PL <= e->cfg.max_seq_len, e->ctx + static_cast<size_t>(L) * D, o_bs);
+}
+
+void unet_eval_impl(wd_f32* e, int B, const float* x, const long long* timesteps, long long t_scalar, const long long* y,
+                    float* eps_out) {
+  const wd_config& c = e->cfg;
+  const int mc = c.model_channels, ted = 4 * mc;
+  // a1 / a2: timestep embedding -> time_embed MLP (+ label embedding)
+  Act temb;
+  temb.H = temb.W = 1;
+  temb.C = mc;
+  temb.p = alloc(e, static_cast<size_t>(B) * mc);
+  if (!e->dry) {
+    f32_timestep_kernel<<<(B * (mc / 2) + 255) / 256, 256, 0, e->s>>>(timesteps, t_scalar, temb.p, B, mc);
+    after_launch(e, "timestep");
+  }
+  Act e1 = linear(e, "time_embed.0", temb, B, true, nullptr, 1);
+  Act emb = linear(e, "time_embed.2", e1, B, true);
+  Act semb = emb;
+  semb.p = alloc(e, static_cast<size_t>(B) * ted);
+  const bool use_label = c.add_label_emb && c.num_classes > 0;
+  if (use_label && !y) fail(WD_ERR_INVALID, "fp32 path: y is required (unet.py:1555)");
+  if (!e->dry) {
+    f32_emb_finish_kernel<<<(B * ted + 255) / 256, 256, 0, e->s>>>(emb.p, use_label ? P(e, "label_emb.weight").p : nullptr, y, semb.p,
+                                                                   B, ted, c.num_classes, e->bad_flag);
+    after_launch(e, "emb_finish");
+  }
+  Act ctx;
+  ctx.H = 1;
+  ctx.W = e->ctx_L;
+  ctx.C = c.context_dim;
+  ctx.p = e->ctx;
+
+  std::vector<Act> hs;
+  Act h{};
+  int i = 0;
+  for (;; ++i) {
+    const std::string p = "input_blocks." + std::to_string(i) + ".";
+    if (!(has(e, p + "0.weight") || has(e, p + "0.in_layers.0.weight") || has(e, p + "0.op.weight"))) break;
+    h = run_block(e, p, h, nullptr, B, semb, ctx, x);
+    hs.push_back(h);
+  }
+  if (hs.empty()) fail(WD_ERR_STATE, "fp32 path: no input_blocks loaded");
+  h = run_block(e, "middle_block.", h, nullptr, B, semb, ctx, x);
+  for (i = 0;; ++i) {
+    const std::string p = "output_blocks." + std::to_string(i) + ".";
+    if (!has(e, p + "0.in_layers.0.weight")) break;
+    if (hs.empty()) fail(WD_ERR_STATE, "fp32 path: more output blocks than skip tensors");
+    Act sk = hs.back();
+    hs.pop_back();
+    h = run_block(e, p, h, &sk, B, semb, ctx, x);
+  }
+  // out: GroupNorm32 -> SiLU -> conv3x3 (unet.py:1454-1458), written NCHW
+  Act g = groupnorm(e, "out.0", h, nullptr, B, 1e-5f, 1);
+  const Param& w = P(e, "out.2.weight");
+  ConvSpec cs;
+  cs.taps = 9;
+  cs.out_nchw = 1;
+  gemm(e, g, nullptr, B, w.p, static_cast<int>(w.shape[0]), P(e, "out.2.bias").p, nullptr, 0, nullptr, cs, eps_out);
+}
+
+int finish(wd_f32* e, const Fail& f) {
+  e->err = f.msg;
+  return wd_set_error(f.code, e->err.c_str());
+}
+
+int check_bad_flag(wd_f32* e, const char* what) {
+  int bad = 0;
+  if (cudaMemcpyAsync(&bad, e->bad_flag, sizeof(int), cudaMemcpyDeviceToHost, e->s) != cudaSuccess ||
+      cudaStreamSynchronize(e->s) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "fp32 path: reading the index-check flag failed");
+  if (bad) {
+    cudaMemsetAsync(e->bad_flag, 0, sizeof(int), e->s);
+    return wd_set_error(WD_ERR_INVALID, what);
+  }
+  return WD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wd_f32_create(const wd_config* cfg, wd_f32** out) {
+  if (!cfg || !out) return wd_set_error(WD_ERR_INVALID, "wd_f32_create: null argument");
+  int dev = 0;
+  cudaDeviceProp prop{};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_create: no CUDA device");
+  if (prop.major != 10) return wd_set_error(WD_ERR_UNSUPPORTED, "wd_f32_create: libwd_b200 is built for sm_100a only");
+  if (cfg->model_channels % 32 || cfg->context_dim % 4 || cfg->in_channels != 4)
+    return wd_set_error(WD_ERR_UNSUPPORTED, "wd_f32_create: unsupported channel configuration");
+  wd_f32* e = new wd_f32();
+  e->cfg = *cfg;
+  if (cudaMalloc(&e->bad_flag, sizeof(int)) != cudaSuccess || cudaMemset(e->bad_flag, 0, sizeof(int)) != cudaSuccess) {
+    delete e;
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_create: cudaMalloc failed");
+  }
+  *out = e;
+  return WD_OK;
+}
+
+void wd_f32_destroy(wd_f32* e) {
+  if (!e) return;
+  for (auto& kv : e->params) cudaFree(kv.second.p);
+  cudaFree(e->pe);
+  cudaFree(e->ctx);
+  cudaFree(e->arena);
+  cudaFree(e->bad_flag);
+  delete e;
+}
+
+int wd_f32_load_param(wd_f32* e, const char* name, const float* src, const int64_t* shape, int ndim, void* stream) {
+  if (!e || !name || !src || (ndim > 0 && !shape)) return wd_set_error(WD_ERR_INVALID, "wd_f32_load_param: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  size_t n = 1;
+  std::vector<int64_t> shp;
+  for (int i = 0; i < ndim; ++i) {
+    n *= static_cast<size_t>(shape[i]);
+    shp.push_back(shape[i]);
+  }
+  Param& p = e->params[name];
+  if (p.n != n) {
+    cudaFree(p.p);
+    p.p = nullptr;
+    if (cudaMalloc(&p.p, n * sizeof(float)) != cudaSuccess) {
+      e->params.erase(name);
+      return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc failed");
+    }
+    p.n = n;
+  }
+  p.shape = shp;
+  p.packed3x3 = ndim == 4 && shape[2] == 3 && shape[3] == 3;
+  cudaError_t ce;
+  if (p.packed3x3) {
+    f32_pack_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, p.p, static_cast<int>(shape[0]),
+                                                                               static_cast<int>(shape[1]));
+    ce = cudaGetLastError();
+  } else {
+    ce = cudaMemcpyAsync(p.p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  }
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+int wd_f32_set_pos_encoding(wd_f32* e, const float* pe, void* stream) {
+  if (!e || !pe) return wd_set_error(WD_ERR_INVALID, "wd_f32_set_pos_encoding: null argument");
+  const size_t n = static_cast<size_t>(e->cfg.max_seq_len) * e->cfg.context_dim;
+  if (!e->pe && cudaMalloc(&e->pe, n * sizeof(float)) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_set_pos_encoding: cudaMalloc failed");
+  if (cudaMemcpyAsync(e->pe, pe, n * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_set_pos_encoding: copy failed");
+  return WD_OK;
+}
+
+static int ensure_arena(wd_f32* e, size_t need) {
+  if (need <= e->arena_cap) return WD_OK;
+  if (e->arena) {
+    cudaDeviceSynchronize();
+    cudaFree(e->arena);
+    e->arena = nullptr;
+    e->arena_cap = 0;
+  }
+  if (cudaMalloc(&e->arena, need) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "fp32 path: activation arena cudaMalloc failed");
+  e->arena_cap = need;
+  return WD_OK;
+}
+
+int wd_f32_encode_context(wd_f32* e, int batch, const int64_t* ctx_tokens, int L, const int32_t* phosc, void* stream) {
+  if (!e || !ctx_tokens || batch <= 0 || L <= 0) return wd_set_error(WD_ERR_INVALID, "wd_f32_encode_context: invalid argument");
+  if (!e->pe) return wd_set_error(WD_ERR_STATE, "wd_f32_encode_context: positional encoding not set");
+  if (e->cfg.variant != WD_VARIANT_UNET && e->cfg.phosc_len > 0 && !phosc)
+    return wd_set_error(WD_ERR_INVALID, "wd_f32_encode_context: this model needs the PHOSC labels");
+  e->s = static_cast<cudaStream_t>(stream);
+  const int Lt = L + ((e->cfg.variant != WD_VARIANT_UNET && phosc) ? e->cfg.phosc_len : 0);
+  const size_t need = static_cast<size_t>(batch) * Lt * e->cfg.context_dim;
+  if (need > e->ctx_cap) {
+    cudaDeviceSynchronize();
+    cudaFree(e->ctx);
+    e->ctx = nullptr;
+    e->ctx_cap = 0;
+    if (cudaMalloc(&e->ctx, need * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_encode_context: cudaMalloc failed");
+    e->ctx_cap = need;
+  }
+  try {
+    e->dry = true;
+    e->arena_off = 0;
+    encode_context_impl(e, batch, reinterpret_cast<const long long*>(ctx_tokens), L, phosc);
+    const size_t need_arena = e->arena_off;
+    int rc = ensure_arena(e, need_arena);
+    if (rc != WD_OK) return rc;
+    e->dry = false;
+    e->arena_off = 0;
+    e->launches = 0;
+    encode_context_impl(e, batch, reinterpret_cast<const long long*>(ctx_tokens), L, phosc);
+  } catch (const Fail& f) {
+    e->dry = false;
+    return finish(e, f);
+  }
+  e->ctx_B = batch;
+  e->ctx_L = Lt;
+  return check_bad_flag(e, "wd_f32_encode_context: token id outside the embedding table");
+}
+
+int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                     float* eps_out, void* stream) {
+  if (!e || !x || !eps_out || batch <= 0) return wd_set_error(WD_ERR_INVALID, "wd_f32_unet_eval: invalid argument");
+  if (!e->ctx || e->ctx_B != batch) return wd_set_error(WD_ERR_STATE, "wd_f32_unet_eval: call wd_f32_encode_context for this batch first");
+  e->s = static_cast<cudaStream_t>(stream);
+  try {
+    e->dry = true;
+    e->arena_off = 0;
+    unet_eval_impl(e, batch, x, reinterpret_cast<const long long*>(timesteps), t_scalar, reinterpret_cast<const long long*>(y), eps_out);
+    const size_t need_arena = e->arena_off;
+    int rc = ensure_arena(e, need_arena);
+    if (rc != WD_OK) return rc;
+    e->dry = false;
+    e->arena_off = 0;
+    e->launches = 0;
+    unet_eval_impl(e, batch, x, reinterpret_cast<const long long*>(timesteps), t_scalar, reinterpret_cast<const long long*>(y), eps_out);
+  } catch (const Fail& f) {
+    e->dry = false;
+    return finish(e, f);
+  }
+  return WD_OK;
+}
+
+int wd_f32_last_launch_count(const wd_f32* e) { return e ? e->launches : 0; }
+size_t wd_f32_workspace_bytes(const wd_f32* e) { return e ? e->arena_cap : 0; }
+
+/* single operators of the fp32 path for the parity tests */
+int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W, int Cin,
+                      int Cout, int stride, int up, void* stream) {
+  if (!x_nhwc || !w_oihw || !out_nhwc || (Cin & 3)) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_conv3x3: invalid argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* wp = nullptr;
+  const size_t n = static_cast<size_t>(Cout) * Cin * 9;
+  if (cudaMalloc(&wp, n * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_op_conv3x3: cudaMalloc failed");
+  f32_pack_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(w_oihw, wp, Cout, Cin);
+  GemmF32 g{};
+  g.a1 = x_nhwc;
+  g.C1 = Cin;
+  g.taps = 9;
+  g.Hin = H;
+  g.Win = W;
+  g.stride = stride;
+  g.up = up;
+  g.Hout = up ? 2 * H : (stride == 2 ? H / 2 : H);
+  g.Wout = up ? 2 * W : (stride == 2 ? W / 2 : W);
+  g.w = wp;
+  g.bias = bias;
+  g.out = out_nhwc;
+  g.M = B * g.Hout * g.Wout;
+  g.N = Cout;
+  g.K = 9 * Cin;
+  f32_gemm_kernel<<<dim3((g.M + BM - 1) / BM, (Cout + BN - 1) / BN), 256, 0, s>>>(g);
+  const cudaError_t ce = cudaGetLastError();
+  cudaStreamSynchronize(s);
+  cudaFree(wp);
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+int wd_f32_op_attention(const float* q, const float* k, const float* v, float* out, int B, int Sq, int Skv, int heads, int d,
+                        float scale, void* stream) {
+  if (!q || !k || !v || !out || d > 320) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_attention: invalid argument");
+  wd_f32 tmp;
+  tmp.s = static_cast<cudaStream_t>(stream);
+  const int C = heads * d;
+  try {
+    attention(&tmp, q, static_cast<size_t>(Sq) * C, C, k, v, static_cast<size_t>(Skv) * C, C, out, static_cast<size_t>(Sq) * C, C, B, Sq,
+              Skv, heads, d, scale);
+  } catch (const Fail& f) {
+    return wd_set_error(f.code, f.msg.c_str());
+  }
+  return WD_OK;
+}
+
+}  // extern "C"

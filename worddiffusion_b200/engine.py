@@ -17,6 +17,32 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def make_config(*, variant, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, channel_mult,
+                num_heads, num_head_channels, transformer_depth, context_dim, vocab_size, num_classes, max_seq_len, latent_hw,
+                add_label_emb, phosc_len):
+    """``wd_config`` (include/wd_b200.h) from the reference constructor arguments (unet.py:1126-1156)."""
+    cfg = WdConfig()
+    cfg.variant = variant
+    cfg.in_channels, cfg.model_channels, cfg.out_channels = in_channels, model_channels, out_channels
+    cfg.num_res_blocks = num_res_blocks
+    cfg.n_channel_mult = len(channel_mult)
+    for i, m in enumerate(channel_mult):
+        cfg.channel_mult[i] = int(m)
+    ar = sorted(set(int(a) for a in attention_resolutions))
+    cfg.n_attention_resolutions = len(ar)
+    for i, a in enumerate(ar):
+        cfg.attention_resolutions[i] = a
+    cfg.num_heads, cfg.num_head_channels = num_heads, num_head_channels
+    cfg.transformer_depth = transformer_depth
+    cfg.context_dim, cfg.vocab_size = context_dim, vocab_size
+    cfg.num_classes = num_classes or 0
+    cfg.max_seq_len = max_seq_len
+    cfg.latent_h, cfg.latent_w = latent_hw
+    cfg.add_label_emb = 1 if add_label_emb else 0
+    cfg.phosc_len = phosc_len
+    return cfg
+
+
 class HotPathEngine:
     def __init__(self, *, variant, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  channel_mult, num_heads, num_head_channels, transformer_depth, context_dim, vocab_size, num_classes,
@@ -24,25 +50,12 @@ class HotPathEngine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.WdError("worddiffusion_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
-        cfg = WdConfig()
-        cfg.variant = variant
-        cfg.in_channels, cfg.model_channels, cfg.out_channels = in_channels, model_channels, out_channels
-        cfg.num_res_blocks = num_res_blocks
-        cfg.n_channel_mult = len(channel_mult)
-        for i, m in enumerate(channel_mult):
-            cfg.channel_mult[i] = int(m)
-        ar = sorted(set(int(a) for a in attention_resolutions))
-        cfg.n_attention_resolutions = len(ar)
-        for i, a in enumerate(ar):
-            cfg.attention_resolutions[i] = a
-        cfg.num_heads, cfg.num_head_channels = num_heads, num_head_channels
-        cfg.transformer_depth = transformer_depth
-        cfg.context_dim, cfg.vocab_size = context_dim, vocab_size
-        cfg.num_classes = num_classes or 0
-        cfg.max_seq_len = max_seq_len
-        cfg.latent_h, cfg.latent_w = latent_hw
-        cfg.add_label_emb = 1 if add_label_emb else 0
-        cfg.phosc_len = phosc_len
+        cfg = make_config(variant=variant, in_channels=in_channels, model_channels=model_channels, out_channels=out_channels,
+                          num_res_blocks=num_res_blocks, attention_resolutions=attention_resolutions,
+                          channel_mult=channel_mult, num_heads=num_heads, num_head_channels=num_head_channels,
+                          transformer_depth=transformer_depth, context_dim=context_dim, vocab_size=vocab_size,
+                          num_classes=num_classes, max_seq_len=max_seq_len, latent_hw=latent_hw,
+                          add_label_emb=add_label_emb, phosc_len=phosc_len)
         self.cfg = cfg
         self.latent_hw = tuple(latent_hw)
         self._h = C.c_void_p()
@@ -183,3 +196,101 @@ class HotPathEngine:
     @property
     def weight_bytes(self):
         return lib().wd_engine_weight_bytes(self._h)
+
+
+class F32Engine:
+    """fp32 mode of the hot path (``csrc/f32_path.cu``): the same UNet with fp32 storage and FFMA arithmetic, for the
+    north_star's 1e-4 tolerance.  Same interface as :class:`HotPathEngine` (``Diffusion`` drives either); the sampler update
+    is the separate ``wd_sampler_update`` kernel instead of the output conv's epilogue."""
+
+    def __init__(self, cfg, latent_hw, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WdError("worddiffusion_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        self.cfg = cfg
+        self.latent_hw = tuple(latent_hw)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_create(C.byref(cfg), C.byref(self._h)), "wd_f32_create")
+        self._ctx_key = None
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().wd_f32_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state(self, named_tensors, pos_encoding):
+        l = lib()
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr()
+            keep = []
+            for name, t in named_tensors:
+                src = t.detach()
+                if src.device != self.device or src.dtype != torch.float32 or not src.is_contiguous():
+                    src = src.to(device=self.device, dtype=torch.float32).contiguous()
+                keep.append(src)
+                shape = (C.c_int64 * max(src.dim(), 1))(*src.shape)
+                check(l.wd_f32_load_param(self._h, name.encode(), _ptr(src), shape, src.dim(), sp), f"f32 load_param({name})")
+            pe = pos_encoding.to(device=self.device, dtype=torch.float32).contiguous()
+            check(l.wd_f32_set_pos_encoding(self._h, _ptr(pe), sp), "wd_f32_set_pos_encoding")
+            torch.cuda.current_stream().synchronize()
+        self._ctx_key = None
+
+    def encode_context(self, context, phosc=None):
+        B, L = context.shape
+        key = (context, context._version, phosc, None if phosc is None else phosc._version, B)
+        old = self._ctx_key
+        if (isinstance(old, tuple) and old[0] is context and old[1] == key[1] and old[2] is phosc and old[3] == key[3]
+                and old[4] == B):
+            return
+        ctx = context.to(device=self.device, dtype=torch.int64).contiguous()
+        ph = None
+        if self.cfg.phosc_len > 0:
+            if phosc is None:
+                raise _lib.WdError("this model needs phoscLabels")
+            ph = phosc.to(self.device).int().contiguous()
+            if ph.shape != (B, self.cfg.phosc_len):
+                raise _lib.WdError(f"phoscLabels must be [{B}, {self.cfg.phosc_len}], got {tuple(ph.shape)}")
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_encode_context(self._h, B, _ptr(ctx), L, _ptr(ph), _stream_ptr()), "wd_f32_encode_context")
+        self._ctx_key = key
+
+    def unet_eval(self, x, timesteps, y, out=None):
+        B = x.shape[0]
+        if out is None:
+            out = torch.empty_like(x)
+        t_ptr, t_scalar = C.c_void_p(0), 0
+        if isinstance(timesteps, int):
+            t_scalar = timesteps
+        else:
+            timesteps = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
+            t_ptr = _ptr(timesteps)
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_unet_eval(self._h, B, _ptr(x), t_ptr, t_scalar, _ptr(y), _ptr(out), _stream_ptr()),
+                  "wd_f32_unet_eval")
+        return out
+
+    def sampler_step(self, x, t, y, mode, coef, noise=None, philox_seed=None, sample_offset=0, step_index=0,
+                     eps_out=None):
+        eps = self.unet_eval(x, int(t), y, out=eps_out)
+        return self.sampler_update(x, eps, mode, coef, noise=noise, philox_seed=philox_seed, sample_offset=sample_offset,
+                                   step_index=step_index)
+
+    sampler_update = HotPathEngine.sampler_update
+
+    def reserve(self, batch):
+        self._ctx_key = None
+
+    @property
+    def last_launch_count(self):
+        return lib().wd_f32_last_launch_count(self._h)
+
+    @property
+    def workspace_bytes(self):
+        return lib().wd_f32_workspace_bytes(self._h)

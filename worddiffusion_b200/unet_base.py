@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import HotPathEngine
+from .engine import F32Engine, HotPathEngine, make_config
 from .modules import CharacterEncoder, add_blocks
 
 
@@ -73,6 +73,11 @@ class UNetBase(nn.Module):
         self._engine = None
         self._engine_sig = None
         self._train_engine = None
+        self._engine_f32 = None
+        self._engine_f32_sig = None
+        # "bf16": the tcgen05 engine (bf16 operands, fp32 accumulation; 1e-2 of the reference).  "fp32": fp32 storage and FFMA
+        # arithmetic (1e-4 of the reference, north_star's fp32 mode).  Not a constructor argument: the reference has none.
+        self.precision = "bf16"
 
     def _build_tree(self, extra_before_blocks=None):
         mc = self.model_channels
@@ -103,6 +108,10 @@ class UNetBase(nn.Module):
         if device.type != "cuda":
             raise _lib.WdError("worddiffusion_b200 has no CPU path: move the model and its inputs to a CUDA (B200) device")
         latent_hw = tuple(latent_hw) if latent_hw is not None else (8, 32)
+        if self.precision == "fp32":
+            return self._f32_engine(device, latent_hw)
+        if self.precision != "bf16":
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
         if self._engine is None or self._engine.device != device or self._engine.latent_hw != latent_hw:
             self._engine = HotPathEngine(
                 variant=self.VARIANT, in_channels=self.in_channels, model_channels=self.model_channels,
@@ -119,6 +128,24 @@ class UNetBase(nn.Module):
             self._engine_sig = sig
         return self._engine
 
+    def _f32_engine(self, device, latent_hw):
+        if self._engine_f32 is None or self._engine_f32.device != device or self._engine_f32.latent_hw != latent_hw:
+            cfg = make_config(
+                variant=self.VARIANT, in_channels=self.in_channels, model_channels=self.model_channels,
+                out_channels=self.out_channels, num_res_blocks=self.num_res_blocks,
+                attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
+                num_heads=self.num_heads, num_head_channels=self.num_head_channels,
+                transformer_depth=self.transformer_depth, context_dim=self.context_dim, vocab_size=self.vocab_size,
+                num_classes=self.num_classes, max_seq_len=self.max_seq_len, latent_hw=latent_hw,
+                add_label_emb=self._add_label_emb(), phosc_len=self._phosc_len())
+            self._engine_f32 = F32Engine(cfg, latent_hw, device)
+            self._engine_f32_sig = None
+        sig = self._weights_signature()
+        if sig != self._engine_f32_sig:
+            self._engine_f32.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
+            self._engine_f32_sig = sig
+        return self._engine_f32
+
     def _weights_signature(self):
         """(data_ptr, version) of every parameter: re-pack the engine's bf16 weights when any of them changed.  Walking the
         module tree costs ~0.5 ms per call (264 parameters), more than the host side of a whole denoising step, so the
@@ -133,6 +160,7 @@ class UNetBase(nn.Module):
     def invalidate_engine(self):
         self._param_cache = None
         self._engine_sig = None
+        self._engine_f32_sig = None
 
     def _apply(self, fn, *args, **kwargs):
         self._param_cache = None
