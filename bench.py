@@ -207,6 +207,54 @@ def train_leg(args, world, rank, dev):
                         "(bf16 tensor-core operands, fp32 master weights / accumulation)"}
 
 
+def fp32_leg(args, model, diff, inp, dev, variant):
+    """BASELINE.json configs[1] asks for the batch-256 sampling step in fp32 as well: the same module with
+    ``precision = "fp32"`` (csrc/f32_path.cu: fp32 storage, FFMA arithmetic, 1e-4 of the reference).  Rank 0 only, a few steps."""
+    import torch
+    B = args.batch
+    ctx, y = inp["context"].to(dev), inp["y"].to(dev)
+    phosc = inp["phosc"].to(dev) if variant != "unet" else None
+    x = inp["x"].to(dev).clone()
+    t_probe = torch.full((B,), 500, dtype=torch.long, device=dev)
+    with torch.no_grad():   # the same evaluation in both precisions (bf16 engine first: the module is still in bf16 mode)
+        e16 = model(x, phosc, timesteps=t_probe, context=ctx, y=y) if variant != "unet" else \
+            model(x, None, timesteps=t_probe, context=ctx, y=y)
+    model.precision = "fp32"
+    try:
+        eng = model.engine(dev)
+        eng.encode_context(ctx, phosc)
+        T = diff.noise_steps
+
+        def step(i, k):
+            eng.sampler_step(x, i, y, 1, diff._ddpm_coef[i], philox_seed=1234, step_index=k)
+
+        step(T - 1, 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.fp32_steps):
+            step(T - 2 - k, 1 + k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.fp32_steps
+        with torch.no_grad():
+            e32 = model(inp["x"].to(dev), phosc, timesteps=t_probe, context=ctx, y=y) if variant != "unet" else \
+                model(inp["x"].to(dev), None, timesteps=t_probe, context=ctx, y=y)
+        launches = eng.last_launch_count
+        ws = eng.workspace_bytes
+    finally:
+        model.precision = "bf16"
+    tf = B * GFLOP_PER_LATENT[variant] * 1e9 / (ms * 1e-3) / 1e12
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    err = float((e16.double() - e32.double()).abs().max() / e32.double().abs().max())
+    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": args.fp32_steps, "dtype": "f32",
+            "step_tflops": round(tf, 2), "frac_of_fp32_ffma_peak": round(tf / peak, 4),
+            "fp32_ffma_peak_tflops": round(peak, 1), "gpu_launches_per_step": launches + 1,
+            "workspace_gb": round(ws / 1e9, 2), "bf16_engine_vs_fp32_mode_max_rel": err,
+            "workload": f"{variant} DDPM sampling step in fp32 mode (fp32 storage + FFMA kernels, separate sampler-update kernel), "
+                        f"batch {B}; parity 1e-4 vs the reference (tests/test_gpu_zfp32.py)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -349,6 +397,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    fp32 = fp32_leg(args, model, diff, inp, dev, variant) if args.fp32_steps > 0 else None
+
     # ---------------- roofline from the per-launch device times ----------------
     peaks = load_peaks()
     cls_t, cls_f, cls_b, cls_n = {}, {}, {}, {}
@@ -400,6 +450,8 @@ def run_ours(args):
         out["cpu_baseline"] = cb
     if train is not None:
         out["train_step"] = train
+    if fp32 is not None:
+        out["fp32_mode"] = fp32
     if real_stdout is not None:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
@@ -420,6 +472,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ops-out", default=None, help="write the per-launch device times of one step (JSON) to this path")
     ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the training leg (0: skip it)")
+    ap.add_argument("--fp32-steps", type=int, default=3, help="timed steps of the fp32-mode leg on rank 0 (0: skip it)")
     ap.add_argument("--train-batch", type=int, default=224, help="GLOBAL batch of the training leg (BASELINE config 4)")
     args = ap.parse_args()
     if args.warmup < 3:
