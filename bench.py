@@ -397,7 +397,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    fp32 = fp32_leg(args, model, diff, inp, dev, variant) if args.fp32_steps > 0 else None
+    # N = 1 only (like the CPU baseline): at N > 1 the other ranks have already left
+    fp32 = fp32_leg(args, model, diff, inp, dev, variant) if args.fp32_steps > 0 and world == 1 else None
 
     # ---------------- roofline from the per-launch device times ----------------
     peaks = load_peaks()

@@ -191,3 +191,24 @@ def test_phosc_tokenizer_refuses_cpu_and_validates_words():
     assert PHOSC_LEN == 165 + 604
     with pytest.raises(WdError):
         phosc_labels(["word"], "cpu")
+
+
+def test_precision_switch_host_logic():
+    """`precision` is an attribute (the reference constructor has no such argument): default bf16; both engines refuse a CPU device;
+    the wd_config built for either engine mirrors the constructor arguments (unet.py:1126-1156)."""
+    from worddiffusion_b200 import _lib
+    from worddiffusion_b200.engine import F32Engine, make_config
+    m = UNetModel(args=default_args("cpu"), **KW)
+    assert m.precision == "bf16"
+    m.precision = "fp32"
+    with pytest.raises(_lib.WdError):
+        m.engine()                      # parameters on the CPU: no CPU path in either precision
+    cfg = make_config(variant=_lib.VARIANT_PHOSC, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+                      attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_head_channels=-1, transformer_depth=1,
+                      context_dim=320, vocab_size=53, num_classes=339, max_seq_len=10, latent_hw=(8, 32), add_label_emb=True,
+                      phosc_len=769)
+    assert (cfg.variant, cfg.n_channel_mult, list(cfg.channel_mult)[:2], cfg.n_attention_resolutions, cfg.phosc_len) == \
+        (1, 2, [1, 1], 1, 769)
+    assert (cfg.latent_h, cfg.latent_w, cfg.num_classes, cfg.add_label_emb) == (8, 32, 339, 1)
+    with pytest.raises(_lib.WdError):
+        F32Engine(cfg, (8, 32), "cpu")
