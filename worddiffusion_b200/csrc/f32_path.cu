@@ -399,6 +399,102 @@ __global__ void __launch_bounds__(256) f32_attention_kernel(const float* __restr
   }
 }
 
+// Head width 80 (the UNet's 4 x 80 heads): one THREAD per query with q and the output row in registers, K/V tiles of 32 keys staged in
+// shared memory once per 128 queries and read as warp-wide broadcasts -- no shuffles, and K/V leave L2 once per CTA instead of once
+// per query (the warp-per-query kernel above re-read 640 B per (query, key) pair: ~0.5 TB of L1/L2 traffic per unetPhosc step).
+// Keys in groups of eight: one running-max update and one rescale of the output row per group.
+template <int D, int KT>
+__global__ void __launch_bounds__(128) f32_attention_tq_kernel(const float* __restrict__ q, size_t q_bs, int ldq,
+                                                               const float* __restrict__ k, const float* __restrict__ v, size_t kv_bs,
+                                                               int ldkv, float* __restrict__ out, size_t o_bs, int ldo, int Sq, int Skv,
+                                                               float scale) {
+  constexpr int D4 = D / 4;
+  __shared__ __align__(16) float Ks[KT][D];
+  __shared__ __align__(16) float Vs[KT][D];
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x * 128 + tid, h = blockIdx.y, b = blockIdx.z;
+  const bool active = qi < Sq;
+  float4 qr[D4], o[D4];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(q + b * q_bs + static_cast<size_t>(active ? qi : 0) * ldq + h * D);
+#pragma unroll
+    for (int c = 0; c < D4; ++c) {
+      qr[c] = active ? qp[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float* kb = k + b * kv_bs + h * D;
+  const float* vb = v + b * kv_bs + h * D;
+  float mx = -INFINITY, l = 0.f;
+  for (int t0 = 0; t0 < Skv; t0 += KT) {
+    __syncthreads();
+    for (int idx = tid; idx < KT * D4; idx += 128) {
+      const int j = idx / D4, c = idx - j * D4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (t0 + j < Skv) {
+        kk = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(t0 + j) * ldkv + c * 4);
+        vv = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(t0 + j) * ldkv + c * 4);
+      }
+      *reinterpret_cast<float4*>(&Ks[j][c * 4]) = kk;
+      *reinterpret_cast<float4*>(&Vs[j][c * 4]) = vv;
+    }
+    __syncthreads();
+    const int nk = min(KT, Skv - t0);
+    for (int j0 = 0; j0 < nk; j0 += 8) {
+      float sc[8];
+      float mnew = mx;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (j0 + u < nk) {
+#pragma unroll
+          for (int c = 0; c < D4; ++c) {
+            const float4 kk = *reinterpret_cast<const float4*>(&Ks[j0 + u][c * 4]);
+            a0 = fmaf(qr[c].x, kk.x, a0);
+            a1 = fmaf(qr[c].y, kk.y, a1);
+            a2 = fmaf(qr[c].z, kk.z, a2);
+            a3 = fmaf(qr[c].w, kk.w, a3);
+          }
+          sc[u] = ((a0 + a1) + (a2 + a3)) * scale;
+          mnew = fmaxf(mnew, sc[u]);
+        } else {
+          sc[u] = -INFINITY;
+        }
+      }
+      const float corr = expf(mx - mnew);  // first group: exp(-inf) = 0
+      l *= corr;
+#pragma unroll
+      for (int c = 0; c < D4; ++c) {
+        o[c].x *= corr;
+        o[c].y *= corr;
+        o[c].z *= corr;
+        o[c].w *= corr;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j0 + u < nk) {
+          const float p = expf(sc[u] - mnew);
+          l += p;
+#pragma unroll
+          for (int c = 0; c < D4; ++c) {
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j0 + u][c * 4]);
+            o[c].x = fmaf(p, vv.x, o[c].x);
+            o[c].y = fmaf(p, vv.y, o[c].y);
+            o[c].z = fmaf(p, vv.z, o[c].z);
+            o[c].w = fmaf(p, vv.w, o[c].w);
+          }
+        }
+      }
+      mx = mnew;
+    }
+  }
+  if (active) {
+    float4* op = reinterpret_cast<float4*>(out + b * o_bs + static_cast<size_t>(qi) * ldo + h * D);
+#pragma unroll
+    for (int c = 0; c < D4; ++c) op[c] = make_float4(o[c].x / l, o[c].y / l, o[c].z / l, o[c].w / l);
+  }
+}
+
 // ---- small elementwise kernels -------------------------------------------------------------------------
 // timestep_embedding (unet.py:96-116): [B, dim] = cat(cos(t f), sin(t f)), f_i = exp(-ln(1e4) i / half)
 __global__ void f32_timestep_kernel(const long long* __restrict__ t_dev, long long t_scalar, float* __restrict__ out, int B,
@@ -641,7 +737,10 @@ void attention(wd_f32* e, const float* q, size_t q_bs, int ldq, const float* k, 
   if (e->dry) return;
   const size_t warps = static_cast<size_t>(B) * heads * Sq;
   const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
-  if (d <= 96)
+  if (d == 80 && (ldq & 3) == 0 && (ldkv & 3) == 0 && (ldo & 3) == 0 && (q_bs & 3) == 0 && (kv_bs & 3) == 0 && (o_bs & 3) == 0)
+    f32_attention_tq_kernel<80, 32><<<dim3((Sq + 127) / 128, heads, B), 128, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, Sq,
+                                                                                     Skv, scale);
+  else if (d <= 96)
     f32_attention_kernel<3><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
   else if (d <= 160)
     f32_attention_kernel<5><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
