@@ -398,7 +398,13 @@ def run_ours(args):
         return
 
     # N = 1 only (like the CPU baseline): at N > 1 the other ranks have already left
-    fp32 = fp32_leg(args, model, diff, inp, dev, variant) if args.fp32_steps > 0 and world == 1 else None
+    fp32 = None
+    if args.fp32_steps > 0 and world == 1:
+        try:
+            fp32 = fp32_leg(args, model, diff, inp, dev, variant)
+        except Exception as ex:   # a side leg must not cost the headline line
+            fp32 = {"error": f"{type(ex).__name__}: {ex}"}
+            model.precision = "bf16"
 
     # ---------------- roofline from the per-launch device times ----------------
     peaks = load_peaks()

@@ -1074,6 +1074,9 @@ int wd_f32_encode_context(wd_f32* e, int batch, const int64_t* ctx_tokens, int L
   } catch (const Fail& f) {
     e->dry = false;
     return finish(e, f);
+  } catch (const std::exception& ex) {  // nothing may cross the C ABI
+    e->dry = false;
+    return wd_set_error(WD_ERR_STATE, ex.what());
   }
   e->ctx_B = batch;
   e->ctx_L = Lt;
@@ -1099,6 +1102,9 @@ int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timest
   } catch (const Fail& f) {
     e->dry = false;
     return finish(e, f);
+  } catch (const std::exception& ex) {  // nothing may cross the C ABI
+    e->dry = false;
+    return wd_set_error(WD_ERR_STATE, ex.what());
   }
   return WD_OK;
 }
