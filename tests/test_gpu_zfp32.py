@@ -160,3 +160,22 @@ def test_fp32_batch_invariance(unet):
         e_small = m(big["x"][idx], None, timesteps=big["t"][idx], context=big["context"][idx], y=big["y"][idx])
     assert torch.isfinite(e_big).all()
     assert torch.equal(e_big[idx], e_small)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", 1e-2)])
+@pytest.mark.parametrize("B,L", [(1, 10), (1, 7), (3, 4)])
+def test_ragged_context_length_and_single_latent(unet, precision, tol, B, L):
+    """Edge cases of the seam: one latent, and a context shorter than max_seq_len (unet.py:872 adds pe[:L]) -- both precisions."""
+    m, sd = unet
+    inp = W.make_inputs(B, seed=31 + L, L=L)
+    ci = _cuda(inp)
+    m.precision = precision
+    try:
+        with torch.no_grad():
+            eps = m(ci["x"], None, timesteps=ci["t"], context=ci["context"], y=ci["y"])
+    finally:
+        m.precision = "fp32"
+    ref = UO.unet_forward(sd, inp["x"], inp["t"], inp["context"], inp["y"], variant="unet")
+    err = relerr(eps, ref)
+    print(f"B={B} L={L} {precision}: eps max-rel err vs oracle {err:.3e}")
+    assert err < tol
