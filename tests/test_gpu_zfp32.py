@@ -179,3 +179,12 @@ def test_ragged_context_length_and_single_latent(unet, precision, tol, B, L):
     err = relerr(eps, ref)
     print(f"B={B} L={L} {precision}: eps max-rel err vs oracle {err:.3e}")
     assert err < tol
+
+
+def test_empty_batch_returns_empty(unet):
+    m, _ = unet
+    z = torch.zeros((0, 4, 8, 32), device=DEV)
+    with torch.no_grad():
+        out = m(z, None, timesteps=torch.zeros(0, dtype=torch.long, device=DEV),
+                context=torch.zeros((0, 10), dtype=torch.long, device=DEV), y=torch.zeros(0, dtype=torch.long, device=DEV))
+    assert out.shape == (0, 4, 8, 32)

@@ -188,6 +188,8 @@ class UNetBase(nn.Module):
             raise _lib.WdError("worddiffusion_b200 has no CPU path: inputs must live on a CUDA (B200) device")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise AssertionError(f"x must be [B, {self.in_channels}, H, W], got {tuple(x.shape)}")
+        if x.shape[0] == 0:   # an empty batch passes through every reference layer: [0, out_channels, H, W]
+            return x.new_empty((0, self.out_channels) + tuple(x.shape[2:]))
         eng = self.engine(x.device, latent_hw=x.shape[2:])
         xin = x.to(torch.float32).contiguous()
         if y is not None:
