@@ -232,6 +232,16 @@ int wd_f32_encode_context(wd_f32* e, int batch, const int64_t* ctx_tokens, int L
 /* eps = UNetModel(x, timesteps, context, y) in fp32; arguments as wd_unet_eval */
 int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
                      float* eps_out, void* stream);
+/* args.attentionMaps == 1 (unet.py:1336-1364,1645-1836; unet.UNetModel only): the same evaluation, keeping the attention
+ * probabilities of attn2 summed over the heads (CrossAttention returns attn, unet.py:276-279; UNetModel.forward sums it over dim 1,
+ * unet.py:1786) of the LAST SpatialTransformer of the input blocks (which = 0), of the middle block (1) and of the output blocks (2)
+ * until the next evaluation.  wd_f32_read_attention_map reports the stored map's H, W, L and, when dst != NULL, writes it
+ * nearest-upsampled by `scale` (the reference uses 8, 16, 8: unet.py:1787,1791,1795) as fp32 [B, H*scale, W*scale, L].
+ * wd_f32_read_context copies the encoded context [B, L, context_dim] (the fifth element of the reference's return tuple). */
+int wd_f32_unet_eval_maps(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                          float* eps_out, void* stream);
+int wd_f32_read_attention_map(wd_f32* e, int which, int scale, float* dst, int* H, int* W, int* L, void* stream);
+int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream);
 int wd_f32_last_launch_count(const wd_f32* e);
 size_t wd_f32_workspace_bytes(const wd_f32* e);
 /* single operators of the fp32 path (parity tests): 3x3 conv pad 1 (stride 1|2, or nearest-2x upsampling first), fp32 NHWC,

@@ -120,15 +120,18 @@ def transformer_block(sd, pfx, x, context, heads, variant):
     return x, attn
 
 
-def spatial_transformer(sd, pfx, x, context, heads, variant, depth=1):
-    """SpatialTransformer.forward, unet.py:381-412 / unetPhosc.py:282-300."""
+def spatial_transformer(sd, pfx, x, context, heads, variant, depth=1, maps=None):
+    """SpatialTransformer.forward, unet.py:381-412 / unetPhosc.py:282-300.  ``maps``: list that receives the attention
+    probabilities of the last block's attn2, [B, heads, h, w, Skv] (what the attentionMaps = 1 variant returns, unet.py:402-410)."""
     b, c, h, w = x.shape
     x_in = x
     x = group_norm(sd, pfx + "norm", x, 1e-6)
     x = F.conv2d(x, sd[pfx + "proj_in.weight"], sd[pfx + "proj_in.bias"])
     x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)
     for d in range(depth):
-        x, _ = transformer_block(sd, f"{pfx}transformer_blocks.{d}.", x, context, heads, variant)
+        x, attn = transformer_block(sd, f"{pfx}transformer_blocks.{d}.", x, context, heads, variant)
+    if maps is not None:
+        maps.append(attn.reshape(b, attn.shape[1], h, w, attn.shape[-1]))
     x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
     x = F.conv2d(x, sd[pfx + "proj_out.weight"], sd[pfx + "proj_out.bias"])
     return x + x_in
@@ -156,14 +159,14 @@ def _block_layers(sd, pfx):
     return kinds
 
 
-def _run_block(sd, pfx, h, emb, context, heads, variant):
+def _run_block(sd, pfx, h, emb, context, heads, variant, maps=None):
     """TimestepEmbedSequential.forward, unet.py:452-469."""
     for i, kind in enumerate(_block_layers(sd, pfx)):
         p = f"{pfx}{i}."
         if kind == "res":
             h = res_block(sd, p, h, emb)
         elif kind == "st":
-            h = spatial_transformer(sd, p, h, context, heads, variant)
+            h = spatial_transformer(sd, p, h, context, heads, variant, maps=maps)
         elif kind == "down":  # Downsample unet.py:549-551
             h = F.conv2d(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)
         elif kind == "up":    # Upsample unet.py:490-500
@@ -183,10 +186,39 @@ def encode_context(sd, context, phosc=None, *, variant="unet", max_seq_len=10):
     return ctx
 
 
+ATTENTION_MAP_SCALES = (8, 16, 8)  # unet.py:1787,1791,1795
+
+
+def canonical_state_dict(sd):
+    """attentionMaps = 1 stores the middle block as middle_block1.{0.0, 0.1, 1.0}.* (unet.py:1336-1364): same layers, same order
+    as middle_block.{0, 1, 2}.* -- returns ``sd`` under the attentionMaps = 0 names."""
+    ren = (("middle_block1.0.0.", "middle_block.0."), ("middle_block1.0.1.", "middle_block.1."),
+           ("middle_block1.1.0.", "middle_block.2."))
+    out = {}
+    for k, v in sd.items():
+        for old, new in ren:
+            if k.startswith(old):
+                k = new + k[len(old):]
+                break
+        out[k] = v
+    return out
+
+
+def finish_attention_map(attn, scale):
+    """unet.py:1786-1797: sum over heads, nearest-upsample (scale, scale): [B, heads, h, w, L] -> [B, scale h, scale w, L]."""
+    a = attn.sum(dim=1)
+    a = F.interpolate(a.permute(0, 3, 1, 2), scale_factor=(scale, scale), mode="nearest")
+    return a.permute(0, 2, 3, 1)
+
+
 def unet_forward(sd, x, timesteps, context, y, phosc=None, *, variant="unet", model_channels=320, heads=4,
-                 max_seq_len=10, add_label_emb=True, ctx_encoded=None):
-    """UNetModel.forward unet.py:1499-1836 (attentionMaps=0, ocrTraining=0) / UNetModelPhosc.forward unetPhosc.py:1068-1159.
-    ``sd``: fp32 CPU state_dict with the reference keys."""
+                 max_seq_len=10, add_label_emb=True, ctx_encoded=None, attention_maps=False):
+    """UNetModel.forward unet.py:1499-1836 (ocrTraining=0) / UNetModelPhosc.forward unetPhosc.py:1068-1159.
+    ``sd``: fp32 CPU state_dict with the reference keys.  ``attention_maps`` (args.attentionMaps = 1, unet.py only): returns
+    the reference's 5-tuple (eps, attn1, attn2, attn3, context) -- the maps of the last SpatialTransformer of the input blocks,
+    of the middle block and of the output blocks (unet.py:1660,1703,1716: each assignment overwrites the previous one)."""
+    sd = canonical_state_dict(sd)
+    m_in, m_mid, m_out = ([], [], []) if attention_maps else (None, None, None)
     t_emb = timestep_embedding(timesteps, model_channels)
     emb = _lin(sd, "time_embed.2", F.silu(_lin(sd, "time_embed.0", t_emb)))
     if add_label_emb and "label_emb.weight" in sd:
@@ -198,14 +230,18 @@ def unet_forward(sd, x, timesteps, context, y, phosc=None, *, variant="unet", mo
     i = 0
     while f"input_blocks.{i}.0.weight" in sd or f"input_blocks.{i}.0.in_layers.0.weight" in sd or \
             f"input_blocks.{i}.0.op.weight" in sd:
-        h = _run_block(sd, f"input_blocks.{i}.", h, emb, ctx, heads, variant)
+        h = _run_block(sd, f"input_blocks.{i}.", h, emb, ctx, heads, variant, maps=m_in)
         hs.append(h)
         i += 1
-    h = _run_block(sd, "middle_block.", h, emb, ctx, heads, variant)
+    h = _run_block(sd, "middle_block.", h, emb, ctx, heads, variant, maps=m_mid)
     i = 0
     while f"output_blocks.{i}.0.in_layers.0.weight" in sd:
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_block(sd, f"output_blocks.{i}.", h, emb, ctx, heads, variant)
+        h = _run_block(sd, f"output_blocks.{i}.", h, emb, ctx, heads, variant, maps=m_out)
         i += 1
     h = F.silu(group_norm(sd, "out.0", h, 1e-5))
-    return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+    eps = F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+    if not attention_maps:
+        return eps
+    a1, a2, a3 = (finish_attention_map(m[-1], s) for m, s in zip((m_in, m_mid, m_out), ATTENTION_MAP_SCALES))
+    return eps, a1, a2, a3, ctx

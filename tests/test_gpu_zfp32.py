@@ -188,3 +188,39 @@ def test_empty_batch_returns_empty(unet):
         out = m(z, None, timesteps=torch.zeros(0, dtype=torch.long, device=DEV),
                 context=torch.zeros((0, 10), dtype=torch.long, device=DEV), y=torch.zeros(0, dtype=torch.long, device=DEV))
     assert out.shape == (0, 4, 8, 32)
+
+
+def test_attention_maps_variant_vs_reference_golden(golden_dir):
+    """args.attentionMaps == 1 (unet.py:1336-1364,1645-1836): middle_block1 checkpoint layout, 5-tuple return, maps and context
+    against the UNMODIFIED reference's (oracle/make_golden_attnmaps.py)."""
+    ren = {"middle_block.0.": "middle_block1.0.0.", "middle_block.1.": "middle_block1.0.1.", "middle_block.2.": "middle_block1.1.0."}
+    sd1 = {}
+    for k, v in W.make_state_dict(W.load_spec("unet"), SEED).items():
+        for old, new in ren.items():
+            if k.startswith(old):
+                k = new + k[len(old):]
+                break
+        sd1[k] = v
+    m = UNetModel(args=default_args(DEV, attentionMaps=1), **KW)
+    m.load_state_dict(sd1, strict=True)
+    m = m.to(DEV).eval()
+    g = np.load(os.path.join(golden_dir, "unet_attnmaps.npz"))
+    g0 = np.load(os.path.join(golden_dir, "unet_fwd.npz"))
+    inp = _cuda(W.make_inputs(2, seed=SEED))
+    with torch.no_grad():
+        out = m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+    assert isinstance(out, tuple) and len(out) == 5
+    eps, a1, a2, a3, ctx = out
+    assert relerr(eps, torch.from_numpy(g0["eps"])) < TOL_FP32
+    assert ctx.shape == (2, 10, 320) and relerr(ctx, torch.from_numpy(g["context"])) < TOL_FP32
+    for a, key, s in zip((a1, a2, a3), ("attn1", "attn2", "attn3"), g["scales"]):
+        s = int(s)
+        assert a.shape == (2, 64, 256, 10) and a.dtype == torch.float32
+        sub = a[:, ::s, ::s]
+        assert torch.equal(sub.repeat_interleave(s, 1).repeat_interleave(s, 2), a)
+        err = relerr(sub, torch.from_numpy(g[key]))
+        print(key, "max-rel err vs reference:", err)
+        assert err < TOL_FP32
+    m.precision = "bf16"
+    with pytest.raises(NotImplementedError):
+        m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])

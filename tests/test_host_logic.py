@@ -38,7 +38,7 @@ def test_fresh_model_has_reference_zero_init():
 
 def test_unsupported_configurations_fail_loudly():
     with pytest.raises(NotImplementedError):
-        UNetModel(args=default_args("cpu", attentionMaps=1), **KW)
+        UNetModel(args=default_args("cpu", ocrTraining=1), **KW)
     with pytest.raises(NotImplementedError):
         UNetModel(args=default_args("cpu"), **dict(KW, use_scale_shift_norm=True))
     with pytest.raises(NotImplementedError):
@@ -212,3 +212,21 @@ def test_precision_switch_host_logic():
     assert (cfg.latent_h, cfg.latent_w, cfg.num_classes, cfg.add_label_emb) == (8, 32, 339, 1)
     with pytest.raises(_lib.WdError):
         F32Engine(cfg, (8, 32), "cpu")
+
+
+def test_attention_maps_variant_state_dict_layout():
+    """args.attentionMaps == 1 (unet.py:1336-1364): middle_block1.{0,1}.* instead of middle_block.* -- same keys, order and shapes
+    as the reference module built with that flag (spec dumped by oracle/make_golden_attnmaps.py); the engines see the layers
+    under the attentionMaps == 0 names, in the same order."""
+    import json
+    m = UNetModel(args=default_args("cpu", attentionMaps=1), **KW)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_spec_unet_attnmaps.json")) as f:
+        spec = [(k, tuple(sh)) for k, sh in json.load(f)]
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec
+    assert sum(k.startswith("middle_block1.") for k, _ in spec) == 54 and not any(k.startswith("middle_block.") for k, _ in spec)
+    assert [k for k, _ in m._engine_state_items()] == [k for k, _ in W.load_spec("unet")]
+    assert m.precision == "fp32"      # the maps are the attention probabilities: only the fp32 path materialises them
+    m.precision = "bf16"
+    x = torch.zeros(1, 4, 8, 32)
+    with pytest.raises(NotImplementedError):
+        m(x, None, timesteps=torch.tensor([1]), context=torch.zeros(1, 10, dtype=torch.long), y=torch.tensor([0]))

@@ -196,3 +196,32 @@ def test_phosc_oracle_matches_reference_generators(golden_dir):
     assert P.segments(7)[1:3] == [(0, 3), (3, 7)] and len(P.segments(3)) == 15
     with pytest.raises(KeyError):
         P.phosc("abc1")
+
+
+def test_oracle_attention_maps_vs_reference(golden_dir):
+    """args.attentionMaps == 1: the oracle's 5-tuple against the reference module's (oracle/make_golden_attnmaps.py).  The fixture
+    keeps one sample per nearest-upsampled block; the maps must be constant over each block."""
+    import unet_oracle as UO
+    import weights as W
+    g = np.load(os.path.join(golden_dir, "unet_attnmaps.npz"))
+    g0 = np.load(os.path.join(golden_dir, "unet_fwd.npz"))
+    sd = W.make_state_dict(W.load_spec("unet"), 1234)
+    ren = {"middle_block.0.": "middle_block1.0.0.", "middle_block.1.": "middle_block1.0.1.", "middle_block.2.": "middle_block1.1.0."}
+    sd1 = {}
+    for k, v in sd.items():   # the layout a checkpoint of the attentionMaps = 1 model has
+        for old, new in ren.items():
+            if k.startswith(old):
+                k = new + k[len(old):]
+                break
+        sd1[k] = v
+    inp = W.make_inputs(2, seed=1234)
+    eps, a1, a2, a3, ctx = UO.unet_forward(sd1, inp["x"], inp["t"], inp["context"], inp["y"], attention_maps=True)
+    assert float((eps - torch.from_numpy(g0["eps"])).abs().max()) < 1e-5
+    assert float((ctx - torch.from_numpy(g["context"])).abs().max()) < 1e-5
+    for a, key, s in zip((a1, a2, a3), ("attn1", "attn2", "attn3"), g["scales"]):
+        s = int(s)
+        assert a.shape == (2, 64, 256, 10)
+        sub = a[:, ::s, ::s]
+        assert torch.equal(sub.repeat_interleave(s, 1).repeat_interleave(s, 2), a)
+        assert float((sub - torch.from_numpy(g[key])).abs().max()) < 1e-5
+        assert float((a.sum(-1) - 4.0).abs().max()) < 1e-4    # four heads, each row of probabilities sums to one

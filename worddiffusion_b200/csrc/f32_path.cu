@@ -559,6 +559,63 @@ __global__ void f32_embed_tokens_kernel(const long long* __restrict__ tok64, con
   out[idx] = v;
 }
 
+// Attention probabilities summed over the heads (args.attentionMaps == 1: CrossAttention returns attn [B, heads, Sq, L],
+// unet.py:276-279, and UNetModel.forward sums it over the heads, unet.py:1786): out[b, i, j] = sum_h softmax_j(q_h[i] . k_h[j] scale).
+// One thread per (sample, query); L <= 32 (the character context).
+__global__ void __launch_bounds__(128) f32_attn_probs_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                             float* __restrict__ out, int B, int Sq, int L, int heads, int d,
+                                                             float scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Sq) return;
+  const int b = idx / Sq;
+  const int C = heads * d;
+  const float* qrow = q + static_cast<size_t>(idx) * C;
+  const float* kb = k + static_cast<size_t>(b) * L * C;
+  float acc[32], s[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int h = 0; h < heads; ++h) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = -INFINITY;
+      if (j < L) {
+        const float* kr = kb + static_cast<size_t>(j) * C + h * d;
+        float dot = 0.f;
+        for (int c = 0; c < d; ++c) dot = fmaf(qrow[h * d + c], kr[c], dot);
+        s[j] = dot * scale;
+        mx = fmaxf(mx, s[j]);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (j < L) ? expf(s[j] - mx) : 0.f;
+      sum += s[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += s[j] / sum;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < L) out[static_cast<size_t>(idx) * L + j] = acc[j];
+}
+
+// nearest-neighbour upsampling of a stored map (F.interpolate(..., scale_factor=(s, s), mode="nearest"), unet.py:1787-1797):
+// src [B, H, W, L] -> dst [B, H s, W s, L]
+__global__ void f32_upsample_map_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H, int W, int L, int sc) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * sc * W * sc * L;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % L);
+  size_t r = idx / L;
+  const int x = static_cast<int>(r % (W * sc));
+  r /= (W * sc);
+  const int y = static_cast<int>(r % (H * sc));
+  const int b = static_cast<int>(r / (H * sc));
+  dst[idx] = src[((static_cast<size_t>(b) * H + y / sc) * W + x / sc) * L + j];
+}
+
 // [Cout, Cin, 3, 3] -> [Cout][tap][Cin]
 __global__ void f32_pack_conv_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -596,6 +653,13 @@ struct wd_f32 {
   size_t ctx_cap = 0;
   int ctx_B = 0, ctx_L = 0;
   int* bad_flag = nullptr;
+  // args.attentionMaps == 1: head-summed attn2 probabilities [B, H*W, L] of the last SpatialTransformer of the input blocks (0),
+  // the middle block (1) and the output blocks (2); they live in the arena until the next evaluation
+  struct MapRec {
+    float* p = nullptr;
+    int H = 0, W = 0, L = 0;
+  } maps[3];
+  int want_maps = 0, section = 0, maps_B = 0;
   // activation arena (per eval, bump allocated)
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
@@ -754,13 +818,22 @@ void attention(wd_f32* e, const float* q, size_t q_bs, int ldq, const float* k, 
 int heads_of(const wd_config& c, int ch) { return c.num_head_channels > 0 ? ch / c.num_head_channels : c.num_heads; }
 
 // CrossAttention.forward (unet.py:185-279 / unetPhosc.py:176-198); ctx == nullptr: self-attention.  Returns to_out(...) + residual
-Act cross_attention(wd_f32* e, const std::string& pfx, const Act& xq, int B, const Act* ctx, const float* residual) {
+Act cross_attention(wd_f32* e, const std::string& pfx, const Act& xq, int B, const Act* ctx, const float* residual,
+                    float* probs_out = nullptr) {
   const Act& kvsrc = ctx ? *ctx : xq;
   Act q = linear(e, pfx + "to_q", xq, B, false);
   Act k = linear(e, pfx + "to_k", kvsrc, B, false);
   Act v = linear(e, pfx + "to_v", kvsrc, B, false);
   const int Sq = xq.H * xq.W, Skv = kvsrc.H * kvsrc.W, inner = q.C;
   const int heads = heads_of(e->cfg, inner), d = inner / heads;
+  if (probs_out) {
+    if (Skv > 32) fail(WD_ERR_UNSUPPORTED, "fp32 path: attention maps need a context of at most 32 tokens");
+    if (!e->dry) {
+      f32_attn_probs_kernel<<<(B * Sq + 127) / 128, 128, 0, e->s>>>(q.p, k.p, probs_out, B, Sq, Skv, heads, d,
+                                                                    1.0f / sqrtf(static_cast<float>(d)));
+      after_launch(e, "attn_probs");
+    }
+  }
   Act o = q;
   o.p = alloc(e, static_cast<size_t>(B) * Sq * inner);
   attention(e, q.p, static_cast<size_t>(Sq) * inner, inner, k.p, v.p, static_cast<size_t>(Skv) * inner, inner, o.p,
@@ -778,7 +851,17 @@ Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, 
       Act l1 = layernorm(e, bp + "norm2", t, B);
       t = cross_attention(e, bp + "attn1.", l1, B, &ctx, t.p);
       Act l2 = layernorm(e, bp + "norm2", t, B);
-      t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p);
+      float* probs = nullptr;
+      if (e->want_maps && dpt == e->cfg.transformer_depth - 1) {  // SpatialTransformer returns the LAST block's attn (unet.py:396-397)
+        const int L = ctx.H * ctx.W;
+        probs = alloc(e, static_cast<size_t>(B) * t.H * t.W * L);
+        wd_f32::MapRec& mr = e->maps[e->section];  // a later SpatialTransformer of the section overwrites (unet.py:1660,1716)
+        mr.p = probs;
+        mr.H = t.H;
+        mr.W = t.W;
+        mr.L = L;
+      }
+      t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p, probs);
     } else {
       Act l1 = layernorm(e, bp + "norm1", t, B);
       t = cross_attention(e, bp + "attn1.", l1, B, nullptr, t.p);
@@ -913,6 +996,8 @@ void unet_eval_impl(wd_f32* e, int B, const float* x, const long long* timesteps
   std::vector<Act> hs;
   Act h{};
   int i = 0;
+  e->section = 0;
+  for (int w = 0; w < 3; ++w) e->maps[w] = wd_f32::MapRec{};
   for (;; ++i) {
     const std::string p = "input_blocks." + std::to_string(i) + ".";
     if (!(has(e, p + "0.weight") || has(e, p + "0.in_layers.0.weight") || has(e, p + "0.op.weight"))) break;
@@ -920,7 +1005,9 @@ void unet_eval_impl(wd_f32* e, int B, const float* x, const long long* timesteps
     hs.push_back(h);
   }
   if (hs.empty()) fail(WD_ERR_STATE, "fp32 path: no input_blocks loaded");
+  e->section = 1;
   h = run_block(e, "middle_block.", h, nullptr, B, semb, ctx, x);
+  e->section = 2;
   for (i = 0;; ++i) {
     const std::string p = "output_blocks." + std::to_string(i) + ".";
     if (!has(e, p + "0.in_layers.0.weight")) break;
@@ -1083,11 +1170,15 @@ int wd_f32_encode_context(wd_f32* e, int batch, const int64_t* ctx_tokens, int L
   return check_bad_flag(e, "wd_f32_encode_context: token id outside the embedding table");
 }
 
-int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
-                     float* eps_out, void* stream) {
+static int unet_eval_common(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                            float* eps_out, void* stream, int want_maps) {
   if (!e || !x || !eps_out || batch <= 0) return wd_set_error(WD_ERR_INVALID, "wd_f32_unet_eval: invalid argument");
   if (!e->ctx || e->ctx_B != batch) return wd_set_error(WD_ERR_STATE, "wd_f32_unet_eval: call wd_f32_encode_context for this batch first");
+  if (want_maps && e->cfg.variant != WD_VARIANT_UNET)
+    return wd_set_error(WD_ERR_UNSUPPORTED, "wd_f32_unet_eval_maps: attention maps exist for unet.UNetModel only (unet.py:1645)");
   e->s = static_cast<cudaStream_t>(stream);
+  e->want_maps = want_maps;
+  e->maps_B = want_maps ? batch : 0;
   try {
     e->dry = true;
     e->arena_off = 0;
@@ -1106,6 +1197,42 @@ int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timest
     e->dry = false;
     return wd_set_error(WD_ERR_STATE, ex.what());
   }
+  return WD_OK;
+}
+
+int wd_f32_unet_eval(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                     float* eps_out, void* stream) {
+  return unet_eval_common(e, batch, x, timesteps, t_scalar, y, eps_out, stream, 0);
+}
+
+int wd_f32_unet_eval_maps(wd_f32* e, int batch, const float* x, const int64_t* timesteps, int64_t t_scalar, const int64_t* y,
+                          float* eps_out, void* stream) {
+  return unet_eval_common(e, batch, x, timesteps, t_scalar, y, eps_out, stream, 1);
+}
+
+int wd_f32_read_attention_map(wd_f32* e, int which, int scale, float* dst, int* H, int* W, int* L, void* stream) {
+  if (!e || which < 0 || which > 2 || scale < 1) return wd_set_error(WD_ERR_INVALID, "wd_f32_read_attention_map: invalid argument");
+  const wd_f32::MapRec& m = e->maps[which];
+  if (!e->maps_B || !m.p) return wd_set_error(WD_ERR_STATE, "wd_f32_read_attention_map: no map stored (call wd_f32_unet_eval_maps first)");
+  if (H) *H = m.H;
+  if (W) *W = m.W;
+  if (L) *L = m.L;
+  if (!dst) return WD_OK;
+  const size_t total = static_cast<size_t>(e->maps_B) * m.H * scale * m.W * scale * m.L;
+  f32_upsample_map_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      m.p, dst, e->maps_B, m.H, m.W, m.L, scale);
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream) {
+  if (!e || !dst) return wd_set_error(WD_ERR_INVALID, "wd_f32_read_context: null argument");
+  if (!e->ctx || !e->ctx_B) return wd_set_error(WD_ERR_STATE, "wd_f32_read_context: no context encoded");
+  const size_t have = static_cast<size_t>(e->ctx_B) * e->ctx_L * e->cfg.context_dim * sizeof(float);
+  if (bytes != have) return wd_set_error(WD_ERR_INVALID, "wd_f32_read_context: size mismatch");
+  if (cudaMemcpyAsync(dst, e->ctx, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_read_context: copy failed");
   return WD_OK;
 }
 

@@ -276,6 +276,36 @@ class F32Engine:
                   "wd_f32_unet_eval")
         return out
 
+    def unet_eval_maps(self, x, timesteps, y, scales):
+        """args.attentionMaps == 1 (unet.py:1645-1836): -> (eps, [attn1, attn2, attn3], context) with attn_i fp32
+        [B, H_i * scales[i], W_i * scales[i], L] and context fp32 [B, L, context_dim]."""
+        B = x.shape[0]
+        out = torch.empty_like(x)
+        t_ptr, t_scalar = C.c_void_p(0), 0
+        if isinstance(timesteps, int):
+            t_scalar = timesteps
+        else:
+            timesteps = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
+            t_ptr = _ptr(timesteps)
+        l = lib()
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr()
+            check(l.wd_f32_unet_eval_maps(self._h, B, _ptr(x), t_ptr, t_scalar, _ptr(y), _ptr(out), sp), "wd_f32_unet_eval_maps")
+            maps = []
+            L = 0
+            for which, sc in enumerate(scales):
+                H, W, Lc = C.c_int(0), C.c_int(0), C.c_int(0)
+                check(l.wd_f32_read_attention_map(self._h, which, int(sc), C.c_void_p(0), C.byref(H), C.byref(W), C.byref(Lc), sp),
+                      "wd_f32_read_attention_map")
+                m = torch.empty((B, H.value * sc, W.value * sc, Lc.value), device=self.device, dtype=torch.float32)
+                check(l.wd_f32_read_attention_map(self._h, which, int(sc), _ptr(m), None, None, None, sp),
+                      "wd_f32_read_attention_map")
+                maps.append(m)
+                L = Lc.value
+            ctx = torch.empty((B, L, self.cfg.context_dim), device=self.device, dtype=torch.float32)
+            check(l.wd_f32_read_context(self._h, _ptr(ctx), ctx.numel() * 4, sp), "wd_f32_read_context")
+        return out, maps, ctx
+
     def sampler_step(self, x, t, y, mode, coef, noise=None, philox_seed=None, sample_offset=0, step_index=0,
                      eps_out=None):
         eps = self.unet_eval(x, int(t), y, out=eps_out)

@@ -168,8 +168,10 @@ class TimestepEmbedSequential(nn.Sequential):
 
 
 def add_blocks(model, *, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
-               channel_mult, num_heads, num_head_channels, transformer_depth, context_dim, ted):
-    """Populates ``model`` with input_blocks / middle_block / output_blocks / out (same loops as unet.py:1248-1458)."""
+               channel_mult, num_heads, num_head_channels, transformer_depth, context_dim, ted, attention_maps_layout=False):
+    """Populates ``model`` with input_blocks / middle_block / output_blocks / out (same loops as unet.py:1248-1458).
+    ``attention_maps_layout``: args.attentionMaps == 1 registers the middle block as ``middle_block1`` = ModuleList([Res + ST],
+    [Res]) (unet.py:1336-1364), which renames 54 state_dict keys."""
     def heads_for(ch):
         if num_head_channels == -1:
             return num_heads, ch // num_heads
@@ -193,9 +195,15 @@ def add_blocks(model, *, in_channels, model_channels, out_channels, num_res_bloc
             chans.append(ch)
             ds *= 2
     h, d = heads_for(ch)
-    model.middle_block = TimestepEmbedSequential(
-        ResBlock(ch, ted), SpatialTransformer(ch, h, d, depth=transformer_depth, context_dim=context_dim),
-        ResBlock(ch, ted))
+    if attention_maps_layout:
+        model.middle_block1 = nn.ModuleList([
+            TimestepEmbedSequential(ResBlock(ch, ted),
+                                    SpatialTransformer(ch, h, d, depth=transformer_depth, context_dim=context_dim)),
+            TimestepEmbedSequential(ResBlock(ch, ted))])
+    else:
+        model.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, ted), SpatialTransformer(ch, h, d, depth=transformer_depth, context_dim=context_dim),
+            ResBlock(ch, ted))
     model.output_blocks = nn.ModuleList([])
     for level, mult in list(enumerate(channel_mult))[::-1]:
         for i in range(num_res_blocks + 1):

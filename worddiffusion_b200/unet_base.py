@@ -92,7 +92,7 @@ class UNetBase(nn.Module):
                    num_res_blocks=self.num_res_blocks, attention_resolutions=self.attention_resolutions,
                    channel_mult=self.channel_mult, num_heads=self.num_heads,
                    num_head_channels=self.num_head_channels, transformer_depth=self.transformer_depth,
-                   context_dim=self.context_dim, ted=ted)
+                   context_dim=self.context_dim, ted=ted, attention_maps_layout=self._attention_maps())
 
     # ------------------------------------------------------------------ engine plumbing
     def _add_label_emb(self):
@@ -100,6 +100,22 @@ class UNetBase(nn.Module):
 
     def _phosc_len(self):
         return 0
+
+    def _attention_maps(self):
+        return False
+
+    _MIDDLE_RENAMES = (("middle_block1.0.0.", "middle_block.0."), ("middle_block1.0.1.", "middle_block.1."),
+                       ("middle_block1.1.0.", "middle_block.2."))
+
+    def _engine_state_items(self):
+        """state_dict entries under the names the engines know: the attentionMaps = 1 layout (middle_block1.*, unet.py:1336-1364)
+        holds the same layers in the same order as middle_block.{0,1,2}.*."""
+        for k, v in self.state_dict().items():
+            for old, new in self._MIDDLE_RENAMES:
+                if k.startswith(old):
+                    k = new + k[len(old):]
+                    break
+            yield k, v
 
     def engine(self, device=None, latent_hw=None):
         """The B200 engine bound to this module's parameters (created / re-synchronised lazily)."""
@@ -124,7 +140,7 @@ class UNetBase(nn.Module):
             self._engine_sig = None
         sig = self._weights_signature()
         if sig != self._engine_sig:
-            self._engine.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
+            self._engine.load_state(self._engine_state_items(), self.word_emb.positional_encoding)
             self._engine_sig = sig
         return self._engine
 
@@ -142,7 +158,7 @@ class UNetBase(nn.Module):
             self._engine_f32_sig = None
         sig = self._weights_signature()
         if sig != self._engine_f32_sig:
-            self._engine_f32.load_state(self.state_dict().items(), self.word_emb.positional_encoding)
+            self._engine_f32.load_state(self._engine_state_items(), self.word_emb.positional_encoding)
             self._engine_f32_sig = sig
         return self._engine_f32
 
