@@ -7,6 +7,12 @@
 // Weights: nn.Linear / 1x1 conv as stored ([N, K]); 3x3 conv repacked once to [Cout][tap][Cin] (k = tap*Cin + c) so that a
 // 16-wide K block of the implicit GEMM is one contiguous channel run of one shifted pixel.
 // The walker recovers the layer sequence from the loaded state_dict keys (unet.py:1248-1458 builds them in this order).
+//
+// Kernels: f32_gemm_kernel (every contraction: implicit-GEMM 3x3 conv with stride / nearest-2x / two-source concat / NCHW latent
+// gather, Linear, 1x1 conv; fused bias, timestep-embedding row, residual, SiLU, NCHW store), f32_groupnorm_kernel (+SiLU),
+// f32_layernorm_kernel, f32_attention_tq_kernel (80-wide heads, thread per query over shared-memory K/V tiles),
+// f32_attention_kernel (warp per query: Word_Attention's single 320-wide head), f32_geglu_kernel, the embedding kernels, and for
+// args.attentionMaps == 1 f32_attn_probs_kernel + f32_upsample_map_kernel.  Measured: DESIGN.md section 6 (fp32 mode).
 #include <cuda_runtime.h>
 
 #include <cmath>
