@@ -224,3 +224,21 @@ def test_attention_maps_variant_vs_reference_golden(golden_dir):
     m.precision = "bf16"
     with pytest.raises(NotImplementedError):
         m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
+
+
+@pytest.mark.skipif(os.environ.get("WD_F32_TC_TEST") != "1",
+                    reason="the split-TF32 tcgen05 GEMM (csrc/f32_gemm_tc.cu) is opt-in until it has been measured: set WD_F32_TC_TEST=1")
+@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (256, 320, 320), (512, 320, 2880)])
+def test_f32_tc_gemm_operator(M, N, K):
+    """C = A W^T + bias through three kind::tf32 MMAs per K step on pre-split operands: fp32-class accuracy (vs fp64 torch)."""
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    want = a.double() @ w.double().t() + b.double()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    ad, wd_, bd = f32(a), f32(w), f32(b)
+    check(lib().wd_f32_op_gemm_tc(P(ad), P(wd_), P(bd), P(out), M, N, K, S()), "wd_f32_op_gemm_tc")
+    err = relerr(out, want)
+    print(f"split-TF32 tcgen05 GEMM {M}x{N}x{K}: max-rel err vs fp64 {err:.3e}")
+    assert err < 5e-6

@@ -1,0 +1,319 @@
+// fp32-class GEMM on the 5th-gen tensor cores: C[M,N] = A[M,K] W[N,K]^T with every fp32 operand split into two TF32 terms,
+//   a = a_hi + a_lo,  a_hi = tf32_rn(a) (low 13 mantissa bits zero),  a_lo = a - a_hi (exact in fp32),
+//   C = A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T        (the A_lo W_lo^T term is ~2^-22 and dropped)
+// as three tcgen05.mma.kind::tf32 per K step into one fp32 TMEM accumulator.  Per product the error is ~2^-21 (the hardware's own
+// tf32 conversion of a_lo / w_lo), i.e. fp32-class: DESIGN.md section 10 item 4 has the error budget that rules out a 2-term bf16
+// split for north_star's 1e-4.  The operands are PRE-SPLIT in memory (f32tc_split_kernel / f32tc_im2col_split_kernel write a_hi and
+// a_lo; weights are split once per load), so the result does not depend on how kind::tf32 converts its inputs.
+//
+// Kernel: one CTA = one 128 x 160 output tile, 192 threads: warp 0 = TMA producer (four SWIZZLE_128B boxes per 32-wide K block:
+// A_hi, A_lo 128 x 32, W_hi, W_lo 160 x 32 fp32 = 72 KB per stage, 3 stages), warp 1 = single-thread MMA issuer (12 MMAs
+// 128 x 160 x 8 per K block), warps 2-5 = epilogue (one TMEM lane quarter each; bias / per-sample row bias / residual / SiLU, fp32
+// stores of 64-byte row pieces).
+//
+// STATUS: opt-in (env WD_F32_TC=1 routes the fp32 mode's Linear / 1x1 / 3x3 contractions here).  Written at the end of the round
+// after the GPU budget was spent: compiled for sm_100a (ptxas), exercised by tests/test_gpu_zfp32.py::test_f32_tc_gemm_operator
+// only when WD_F32_TC_TEST=1 -- treat it as unmeasured until a profiles/ entry says otherwise.  The default fp32 mode is the FFMA
+// kernel of f32_path.cu.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+#include "f32_tc.h"
+
+namespace wd {
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 160, TC_BK = 32;  // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;  // 20 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_W_BYTES;  // 72 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256;  // + barriers / TMEM slot
+constexpr uint32_t TC_TMEM_COLS = 256;  // power of two >= 160
+
+// Instruction descriptor, kind::tf32: A, B = TF32 (format code 2), K-major both, D = fp32, shape M x N (K = 8)
+__host__ __device__ constexpr uint32_t make_idesc_tf32_f32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+WD_DEVINL void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct TcArgs {
+  int M, N, K;
+  const float* bias;
+  const float* rowbias;
+  int rb_ld;
+  int rows_per_sample;
+  const float* residual;
+  float* out;
+  int act_silu;
+};
+
+__global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                                                            const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+                                                            const TcArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* acc_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int nkb = args.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapWh);
+    tma_prefetch_desc(&mapWl);
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        uint8_t* s = smem + stage * TC_STAGE_BYTES;
+        tma_load_2d(s, &mapAh, &full_bar[stage], kb * TC_BK, m0);
+        tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kb * TC_BK, m0);
+        tma_load_2d(s + 2 * TC_A_BYTES, &mapWh, &full_bar[stage], kb * TC_BK, n0);
+        tma_load_2d(s + 2 * TC_A_BYTES + TC_W_BYTES, &mapWl, &full_bar[stage], kb * TC_BK, n0);
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32_f32(TC_BM, TC_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t s = smem_u32(smem + stage * TC_STAGE_BYTES);
+        const uint64_t ah = make_smem_desc_sw128(s), al = make_smem_desc_sw128(s + TC_A_BYTES);
+        const uint64_t wh = make_smem_desc_sw128(s + 2 * TC_A_BYTES), wl = make_smem_desc_sw128(s + 2 * TC_A_BYTES + TC_W_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          // advance 8 tf32 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field; small terms first
+          umma_tf32_ss(tmem_base, al + 2 * k, wh + 2 * k, idesc, (kb | k) != 0);
+          umma_tf32_ss(tmem_base, ah + 2 * k, wl + 2 * k, idesc, 1u);
+          umma_tf32_ss(tmem_base, ah + 2 * k, wh + 2 * k, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_bar);  // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32); thread = one output row
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int sample = args.rowbias ? m / args.rows_per_sample : 0;
+    float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
+    const float* rrow = args.residual ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
+    const float* rbrow = args.rowbias ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_row + c * 16, v);
+      tmem_ld_wait();
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(v[j]);
+        const int n = c * 16 + j;
+        if (args.bias) x += args.bias[n0 + n];
+        if (rbrow) x += rbrow[n];
+        if (rrow) x += rrow[n];
+        if (args.act_silu) x = x / (1.0f + expf(-x));
+        o[j] = x;
+      }
+      if (m < args.M) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + c * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+// a -> (tf32_rn(a), a - tf32_rn(a))
+WD_DEVINL float tf32_rn(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r & 0xFFFFE000u);
+}
+
+__global__ void f32tc_split_kernel(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(a)[i];
+  float4 h, l;
+  h.x = tf32_rn(v.x); l.x = v.x - h.x;
+  h.y = tf32_rn(v.y); l.y = v.y - h.y;
+  h.z = tf32_rn(v.z); l.z = v.z - h.z;
+  h.w = tf32_rn(v.w); l.w = v.w - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+// 3x3 pad-1 patch matrix of an NHWC fp32 tensor (channel concat of up to two sources), split: hi, lo [M, 9 (C1 + C2)], k = tap (C1 + C2) + c
+__global__ void f32tc_im2col_split_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2, int Hin, int Win,
+                                          int Hout, int Wout, int stride, int up, float* __restrict__ hi, float* __restrict__ lo,
+                                          size_t total4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int Cin = C1 + C2, K4 = 9 * Cin / 4;
+  const size_t m = i / K4;
+  const int k = static_cast<int>(i - m * K4) * 4;
+  const int tap = k / Cin, c = k - tap * Cin;
+  const int hw = Hout * Wout;
+  const int b = static_cast<int>(m / hw), rem = static_cast<int>(m - static_cast<size_t>(b) * hw);
+  const int oh = rem / Wout, ow = rem - oh * Wout;
+  int ih = oh * stride + tap / 3 - 1, iw = ow * stride + tap % 3 - 1;
+  const int Hs = up ? 2 * Hin : Hin, Ws = up ? 2 * Win : Win;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ih >= 0 && ih < Hs && iw >= 0 && iw < Ws) {
+    if (up) {
+      ih >>= 1;
+      iw >>= 1;
+    }
+    const size_t pix = (static_cast<size_t>(b) * Hin + ih) * Win + iw;
+    v = c < C1 ? *reinterpret_cast<const float4*>(a1 + pix * C1 + c) : *reinterpret_cast<const float4*>(a2 + pix * C2 + (c - C1));
+  }
+  float4 h, l;
+  h.x = tf32_rn(v.x); l.x = v.x - h.x;
+  h.y = tf32_rn(v.y); l.y = v.y - h.y;
+  h.z = tf32_rn(v.z); l.z = v.z - h.z;
+  h.w = tf32_rn(v.w); l.w = v.w - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// fp32 [rows, K] row-major, boxes of 32 columns x box_rows rows, SWIZZLE_128B
+bool tmap_f32(CUtensorMap* m, const float* base, uint64_t K, uint64_t rows, uint32_t box_rows) {
+  PFN_encodeTiled fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {K, rows};
+  cuuint64_t strides[1] = {K * 4};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool f32tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_F32_TC");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
+bool f32tc_shape_ok(int M, int N, int K) { return M > 0 && M % TC_BM == 0 && N % TC_BN == 0 && K % TC_BK == 0 && K >= TC_BK; }
+
+cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStream_t s) {
+  if (n & 3) return cudaErrorInvalidValue;
+  const size_t n4 = n / 4;
+  f32tc_split_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(a, hi, lo, n4);
+  return cudaGetLastError();
+}
+
+cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2, int B, int Hin, int Win, int stride, int up, float* hi,
+                               float* lo, cudaStream_t s) {
+  const int Hout = up ? 2 * Hin : (stride == 2 ? Hin / 2 : Hin), Wout = up ? 2 * Win : (stride == 2 ? Win / 2 : Win);
+  if (((C1 | C2) & 3) != 0) return cudaErrorInvalidValue;
+  const size_t total4 = static_cast<size_t>(B) * Hout * Wout * 9 * (C1 + C2) / 4;
+  f32tc_im2col_split_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, s>>>(a1, a2, C1, C2, Hin, Win, Hout, Wout, stride, up, hi, lo,
+                                                                                        total4);
+  return cudaGetLastError();
+}
+
+cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
+                       const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
+                       cudaStream_t s) {
+  if (!f32tc_shape_ok(M, N, K)) return cudaErrorInvalidValue;
+  CUtensorMap mAh, mAl, mWh, mWl;
+  if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, TC_BN) ||
+      !tmap_f32(&mWl, w_lo, K, N, TC_BN))
+    return cudaErrorInvalidValue;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  TcArgs a{};
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.bias = bias;
+  a.rowbias = rowbias;
+  a.rb_ld = rb_ld;
+  a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  a.residual = residual;
+  a.out = out;
+  a.act_silu = act_silu;
+  f32tc_gemm_kernel<<<dim3(M / TC_BM, N / TC_BN), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mWh, mWl, a);
+  return cudaGetLastError();
+}
+
+}  // namespace wd

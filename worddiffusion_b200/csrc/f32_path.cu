@@ -24,6 +24,7 @@
 
 #include "../../include/wd_b200.h"
 #include "engine_internal.h"
+#include "f32_tc.h"
 
 namespace {
 
@@ -641,6 +642,8 @@ struct Param {
   size_t n = 0;
   std::vector<int64_t> shape;
   bool packed3x3 = false;
+  float* hi = nullptr;  // TF32 split of p for the tensor-core GEMM (WD_F32_TC=1 only)
+  float* lo = nullptr;
 };
 
 struct Act {  // token-major activation
@@ -712,7 +715,8 @@ struct ConvSpec {
 };
 
 Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, const float* bias, const float* rowbias,
-         int rb_ld, const float* residual, const ConvSpec& cs, float* out_override = nullptr) {
+         int rb_ld, const float* residual, const ConvSpec& cs, float* out_override = nullptr, const float* w_hi = nullptr,
+         const float* w_lo = nullptr) {
   GemmF32 g{};
   g.a1 = a1.p;
   g.a2 = a2 ? a2->p : nullptr;
@@ -744,6 +748,24 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
   o.C = N;
   o.p = out_override ? out_override : alloc(e, static_cast<size_t>(g.M) * N);
   g.out = o.p;
+  // opt-in tensor-core route (split TF32, f32_gemm_tc.cu): operands are split into (hi, lo) pairs first -- a plain split for a
+  // Linear / 1x1 conv input, the split patch matrix for a 3x3 conv
+  if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K) && (cs.taps == 9 || !a2)) {
+    const size_t nA = static_cast<size_t>(g.M) * g.K;
+    float* a_hi = alloc(e, nA);
+    float* a_lo = alloc(e, nA);
+    if (!e->dry) {
+      cudaError_t ce = cs.taps == 9 ? wd::f32tc_im2col_split(a1.p, a2 ? a2->p : nullptr, g.C1, g.C2, B, a1.H, a1.W, cs.stride, cs.up, a_hi, a_lo, e->s)
+                                    : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
+      ++e->launches;
+      if (ce == cudaSuccess) {
+        ce = wd::f32tc_gemm(a_hi, a_lo, w_hi, w_lo, g.M, N, g.K, bias, rowbias, rb_ld, g.Hout * g.Wout, residual, o.p, cs.silu, e->s);
+        ++e->launches;
+      }
+      if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: tensor-core gemm: ") + cudaGetErrorString(ce));
+    }
+    return o;
+  }
   if (!e->dry) {
     launch_gemm(g, e->s);
     after_launch(e, "gemm");
@@ -761,7 +783,7 @@ Act linear(wd_f32* e, const std::string& pfx, const Act& a, int B, bool bias, co
   if (K != a.C + (a2 ? a2->C : 0)) fail(WD_ERR_INVALID, "fp32 path: " + pfx + ": input width does not match the weight");
   ConvSpec cs;
   cs.silu = silu;
-  return gemm(e, a, a2, B, w.p, N, bias ? P(e, pfx + ".bias").p : nullptr, nullptr, 0, residual, cs);
+  return gemm(e, a, a2, B, w.p, N, bias ? P(e, pfx + ".bias").p : nullptr, nullptr, 0, residual, cs, nullptr, w.hi, w.lo);
 }
 
 Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, const float* rowbias, int rb_ld,
@@ -773,7 +795,7 @@ Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int 
   cs.taps = 9;
   cs.stride = stride;
   cs.up = up;
-  return gemm(e, a, a2, B, w.p, static_cast<int>(w.shape[0]), P(e, pfx + ".bias").p, rowbias, rb_ld, residual, cs);
+  return gemm(e, a, a2, B, w.p, static_cast<int>(w.shape[0]), P(e, pfx + ".bias").p, rowbias, rb_ld, residual, cs, nullptr, w.hi, w.lo);
 }
 
 Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, float eps, int silu) {
@@ -1073,7 +1095,11 @@ int wd_f32_create(const wd_config* cfg, wd_f32** out) {
 
 void wd_f32_destroy(wd_f32* e) {
   if (!e) return;
-  for (auto& kv : e->params) cudaFree(kv.second.p);
+  for (auto& kv : e->params) {
+    cudaFree(kv.second.p);
+    cudaFree(kv.second.hi);
+    cudaFree(kv.second.lo);
+  }
   cudaFree(e->pe);
   cudaFree(e->ctx);
   cudaFree(e->arena);
@@ -1111,6 +1137,15 @@ int wd_f32_load_param(wd_f32* e, const char* name, const float* src, const int64
     ce = cudaMemcpyAsync(p.p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
   }
   if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  if (wd::f32tc_enabled() && ndim >= 2 && (n & 3) == 0) {  // TF32 split of every weight matrix for the tensor-core GEMM
+    cudaFree(p.hi);
+    cudaFree(p.lo);
+    p.hi = p.lo = nullptr;
+    if (cudaMalloc(&p.hi, n * sizeof(float)) != cudaSuccess || cudaMalloc(&p.lo, n * sizeof(float)) != cudaSuccess)
+      return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc of the TF32 split failed");
+    ce = wd::f32tc_split(p.p, p.hi, p.lo, n, s);
+    if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  }
   return WD_OK;
 }
 
@@ -1274,6 +1309,24 @@ int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bia
   const cudaError_t ce = cudaGetLastError();
   cudaStreamSynchronize(s);
   cudaFree(wp);
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+/* out[M,N] = A[M,K] W[N,K]^T + bias on the split-TF32 tensor-core kernel (f32_gemm_tc.cu); splits both operands itself */
+int wd_f32_op_gemm_tc(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, void* stream) {
+  if (!a || !w || !out || !wd::f32tc_shape_ok(M, N, K)) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_gemm_tc: need M % 128 == 0, N % 160 == 0, K % 32 == 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* buf = nullptr;
+  const size_t nA = static_cast<size_t>(M) * K, nW = static_cast<size_t>(N) * K;
+  if (cudaMalloc(&buf, 2 * (nA + nW) * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_op_gemm_tc: cudaMalloc failed");
+  float *ah = buf, *al = buf + nA, *wh = buf + 2 * nA, *wl = buf + 2 * nA + nW;
+  cudaError_t ce = wd::f32tc_split(a, ah, al, nA, s);
+  if (ce == cudaSuccess) ce = wd::f32tc_split(w, wh, wl, nW, s);
+  if (ce == cudaSuccess) ce = wd::f32tc_gemm(ah, al, wh, wl, M, N, K, bias, nullptr, 0, 1, nullptr, out, 0, s);
+  const cudaError_t se = cudaStreamSynchronize(s);
+  cudaFree(buf);
+  if (ce == cudaSuccess) ce = se;
   if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
   return WD_OK;
 }

@@ -1,0 +1,18 @@
+// Internal interface of the split-TF32 tensor-core GEMM (f32_gemm_tc.cu) used by the fp32 path (f32_path.cu).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace wd {
+bool f32tc_enabled();                        // env WD_F32_TC=1 (default off: the kernel has not been measured yet)
+bool f32tc_shape_ok(int M, int N, int K);    // M % 128 == 0, N % 160 == 0, K % 32 == 0
+// a[n] -> hi[n] = tf32_rn(a), lo[n] = a - hi   (n % 4 == 0)
+cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStream_t s);
+// 3x3 pad-1 patch matrix [B Hout Wout, 9 (C1 + C2)] of NHWC source(s), already split (stride 1|2, or nearest-2x first)
+cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2, int B, int Hin, int Win, int stride, int up, float* hi,
+                               float* lo, cudaStream_t s);
+// out[M,N] = act(A W^T + bias + rowbias[m / rows_per_sample] + residual), operands pre-split, all fp32 row-major
+cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
+                       const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
+                       cudaStream_t s);
+}  // namespace wd
