@@ -11,10 +11,11 @@
 // 128 x 160 x 8 per K block), warps 2-5 = epilogue (one TMEM lane quarter each; bias / per-sample row bias / residual / SiLU, fp32
 // stores of 64-byte row pieces).
 //
-// STATUS: opt-in (env WD_F32_TC=1 routes the fp32 mode's Linear / 1x1 / 3x3 contractions here).  Written at the end of the round
-// after the GPU budget was spent: compiled for sm_100a (ptxas), exercised by tests/test_gpu_zfp32.py::test_f32_tc_gemm_operator
-// only when WD_F32_TC_TEST=1 -- treat it as unmeasured until a profiles/ entry says otherwise.  The default fp32 mode is the FFMA
-// kernel of f32_path.cu.
+// STATUS: opt-in (env WD_F32_TC=1 routes the fp32 mode's Linear / 1x1 / 3x3 contractions here); the default fp32 mode is the FFMA
+// kernel of f32_path.cu.  First run on a B200 (profiles/r03h_split_tf32_gemm_first_run.log, tests/test_gpu_zfp32.py::
+// test_f32_tc_gemm_operator under WD_F32_TC_TEST=1): correct; max-rel error vs fp64 2.4e-7 at K = 32, 1.6e-6 at K = 320, 1.3e-5 at
+// K = 2880 -- the tensor core's fp32 accumulation truncates, so the error grows with K: the long-K convolutions need a two-level
+// accumulation (TMEM drained into fp32 registers every few hundred K) before this is fp32-class.  Not timed yet.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
