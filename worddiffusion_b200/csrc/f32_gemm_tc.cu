@@ -15,7 +15,9 @@
 // kernel of f32_path.cu.  First run on a B200 (profiles/r03h_split_tf32_gemm_first_run.log, tests/test_gpu_zfp32.py::
 // test_f32_tc_gemm_operator under WD_F32_TC_TEST=1): correct; max-rel error vs fp64 2.4e-7 at K = 32, 1.6e-6 at K = 320, 1.3e-5 at
 // K = 2880 -- the tensor core's fp32 accumulation truncates, so the error grows with K: the long-K convolutions need a two-level
-// accumulation (TMEM drained into fp32 registers every few hundred K) before this is fp32-class.  Not timed yet.
+// accumulation before this is fp32-class.  That second level was added AFTER the run (not yet executed on a GPU): K > 512 is cut into
+// chunks of 320 (blockIdx.z), each chunk's raw tile goes to a workspace and f32tc_reduce_kernel adds the chunks in fp32, in order
+// (deterministic), then applies the epilogue.  K <= 512 takes the code path that was run.  Not timed yet.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -37,6 +39,11 @@ constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;  // 20 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_W_BYTES;  // 72 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256;  // + barriers / TMEM slot
 constexpr uint32_t TC_TMEM_COLS = 256;  // power of two >= 160
+// The tensor core's fp32 accumulation truncates: the error of one TMEM accumulation grows with K (measured 1.6e-6 at K = 320,
+// 1.3e-5 at K = 2880).  Longer contractions are therefore cut into chunks of TC_SPLIT_KB K blocks (K = 320) whose partial tiles a
+// second kernel adds in fp32 (two-level accumulation).
+constexpr int TC_SPLIT_KB = 10;
+constexpr int TC_SPLIT_MIN_K = 512;
 
 // Instruction descriptor, kind::tf32: A, B = TF32 (format code 2), K-major both, D = fp32, shape M x N (K = 8)
 __host__ __device__ constexpr uint32_t make_idesc_tf32_f32(uint32_t M, uint32_t N) {
@@ -61,6 +68,10 @@ struct TcArgs {
   const float* residual;
   float* out;
   int act_silu;
+  // split-K (two-level accumulation): blockIdx.z accumulates K blocks [z kb_per_split, (z + 1) kb_per_split) in TMEM and writes the
+  // raw tile to partial + z M N; f32tc_reduce_kernel adds the partials in fp32, in order, and applies the epilogue
+  int kb_per_split;  // 0: no split
+  float* partial;
 };
 
 __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
@@ -75,7 +86,9 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
-  const int nkb = args.K / TC_BK;
+  const bool split = args.kb_per_split > 0;
+  const int kb0 = split ? static_cast<int>(blockIdx.z) * args.kb_per_split : 0;
+  const int nkb = split ? min(args.kb_per_split, args.K / TC_BK - kb0) : args.K / TC_BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapAh);
@@ -103,10 +116,11 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
         uint8_t* s = smem + stage * TC_STAGE_BYTES;
-        tma_load_2d(s, &mapAh, &full_bar[stage], kb * TC_BK, m0);
-        tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kb * TC_BK, m0);
-        tma_load_2d(s + 2 * TC_A_BYTES, &mapWh, &full_bar[stage], kb * TC_BK, n0);
-        tma_load_2d(s + 2 * TC_A_BYTES + TC_W_BYTES, &mapWl, &full_bar[stage], kb * TC_BK, n0);
+        const int kc = (kb0 + kb) * TC_BK;
+        tma_load_2d(s, &mapAh, &full_bar[stage], kc, m0);
+        tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kc, m0);
+        tma_load_2d(s + 2 * TC_A_BYTES, &mapWh, &full_bar[stage], kc, n0);
+        tma_load_2d(s + 2 * TC_A_BYTES + TC_W_BYTES, &mapWl, &full_bar[stage], kc, n0);
         if (++stage == TC_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -147,9 +161,11 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sample = args.rowbias ? m / args.rows_per_sample : 0;
-    float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
-    const float* rrow = args.residual ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
-    const float* rbrow = args.rowbias ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
+    float* orow = (split ? args.partial + static_cast<size_t>(blockIdx.z) * args.M * args.N : args.out) + static_cast<size_t>(m) * args.N + n0;
+    const float* rrow = (args.residual && !split) ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
+    const float* rbrow = (args.rowbias && !split) ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
+    const float* bias = split ? nullptr : args.bias;
+    const int act_silu = split ? 0 : args.act_silu;
 #pragma unroll 1
     for (int c = 0; c < TC_BN / 16; ++c) {
       uint32_t v[16];
@@ -160,10 +176,10 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
       for (int j = 0; j < 16; ++j) {
         float x = __uint_as_float(v[j]);
         const int n = c * 16 + j;
-        if (args.bias) x += args.bias[n0 + n];
+        if (bias) x += bias[n0 + n];
         if (rbrow) x += rbrow[n];
         if (rrow) x += rrow[n];
-        if (args.act_silu) x = x / (1.0f + expf(-x));
+        if (act_silu) x = x / (1.0f + expf(-x));
         o[j] = x;
       }
       if (m < args.M) {
@@ -175,6 +191,32 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+// second accumulation level of the split-K form: out = act(sum_z partial[z] + bias + rowbias + residual), z in order (deterministic)
+__global__ void f32tc_reduce_kernel(const TcArgs args, int splits) {
+  const size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t MN = static_cast<size_t>(args.M) * args.N;
+  if (i4 * 4 >= MN) return;
+  const size_t m = (i4 * 4) / args.N;
+  const int n = static_cast<int>(i4 * 4 - m * args.N);
+  float4 acc = reinterpret_cast<const float4*>(args.partial)[i4];
+  for (int z = 1; z < splits; ++z) {
+    const float4 p = reinterpret_cast<const float4*>(args.partial + static_cast<size_t>(z) * MN)[i4];
+    acc.x += p.x;
+    acc.y += p.y;
+    acc.z += p.z;
+    acc.w += p.w;
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (args.bias) v[j] += args.bias[n + j];
+    if (args.rowbias) v[j] += args.rowbias[(m / args.rows_per_sample) * args.rb_ld + n + j];
+    if (args.residual) v[j] += args.residual[m * args.N + n + j];
+    if (args.act_silu) v[j] = v[j] / (1.0f + expf(-v[j]));
+  }
+  reinterpret_cast<float4*>(args.out)[i4] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // a -> (tf32_rn(a), a - tf32_rn(a))
@@ -288,9 +330,11 @@ cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2,
   return cudaGetLastError();
 }
 
+int f32tc_splits(int K) { return K > TC_SPLIT_MIN_K ? (K / TC_BK + TC_SPLIT_KB - 1) / TC_SPLIT_KB : 1; }
+
 cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
                        const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
-                       cudaStream_t s) {
+                       float* partial_ws, cudaStream_t s) {
   if (!f32tc_shape_ok(M, N, K)) return cudaErrorInvalidValue;
   CUtensorMap mAh, mAl, mWh, mWl;
   if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, TC_BN) ||
@@ -313,7 +357,16 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
   a.residual = residual;
   a.out = out;
   a.act_silu = act_silu;
-  f32tc_gemm_kernel<<<dim3(M / TC_BM, N / TC_BN), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mWh, mWl, a);
+  const int splits = partial_ws ? f32tc_splits(K) : 1;
+  if (splits > 1) {
+    a.kb_per_split = TC_SPLIT_KB;
+    a.partial = partial_ws;
+  }
+  f32tc_gemm_kernel<<<dim3(M / TC_BM, N / TC_BN, splits), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mWh, mWl, a);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess || splits == 1) return ce;
+  const size_t n4 = static_cast<size_t>(M) * N / 4;
+  f32tc_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(a, splits);
   return cudaGetLastError();
 }
 

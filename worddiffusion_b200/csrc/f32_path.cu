@@ -754,12 +754,14 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
     const size_t nA = static_cast<size_t>(g.M) * g.K;
     float* a_hi = alloc(e, nA);
     float* a_lo = alloc(e, nA);
+    const int splits = wd::f32tc_splits(g.K);
+    float* ws = splits > 1 ? alloc(e, static_cast<size_t>(splits) * g.M * N) : nullptr;
     if (!e->dry) {
       cudaError_t ce = cs.taps == 9 ? wd::f32tc_im2col_split(a1.p, a2 ? a2->p : nullptr, g.C1, g.C2, B, a1.H, a1.W, cs.stride, cs.up, a_hi, a_lo, e->s)
                                     : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
       ++e->launches;
       if (ce == cudaSuccess) {
-        ce = wd::f32tc_gemm(a_hi, a_lo, w_hi, w_lo, g.M, N, g.K, bias, rowbias, rb_ld, g.Hout * g.Wout, residual, o.p, cs.silu, e->s);
+        ce = wd::f32tc_gemm(a_hi, a_lo, w_hi, w_lo, g.M, N, g.K, bias, rowbias, rb_ld, g.Hout * g.Wout, residual, o.p, cs.silu, ws, e->s);
         ++e->launches;
       }
       if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: tensor-core gemm: ") + cudaGetErrorString(ce));
@@ -1319,11 +1321,14 @@ int wd_f32_op_gemm_tc(const float* a, const float* w, const float* bias, float* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* buf = nullptr;
   const size_t nA = static_cast<size_t>(M) * K, nW = static_cast<size_t>(N) * K;
-  if (cudaMalloc(&buf, 2 * (nA + nW) * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_op_gemm_tc: cudaMalloc failed");
+  const int splits = wd::f32tc_splits(K);
+  const size_t nP = splits > 1 ? static_cast<size_t>(splits) * M * N : 0;
+  if (cudaMalloc(&buf, (2 * (nA + nW) + nP) * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_op_gemm_tc: cudaMalloc failed");
   float *ah = buf, *al = buf + nA, *wh = buf + 2 * nA, *wl = buf + 2 * nA + nW;
+  float* ws = nP ? buf + 2 * (nA + nW) : nullptr;
   cudaError_t ce = wd::f32tc_split(a, ah, al, nA, s);
   if (ce == cudaSuccess) ce = wd::f32tc_split(w, wh, wl, nW, s);
-  if (ce == cudaSuccess) ce = wd::f32tc_gemm(ah, al, wh, wl, M, N, K, bias, nullptr, 0, 1, nullptr, out, 0, s);
+  if (ce == cudaSuccess) ce = wd::f32tc_gemm(ah, al, wh, wl, M, N, K, bias, nullptr, 0, 1, nullptr, out, 0, ws, s);
   const cudaError_t se = cudaStreamSynchronize(s);
   cudaFree(buf);
   if (ce == cudaSuccess) ce = se;

@@ -11,8 +11,11 @@ cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStre
 // 3x3 pad-1 patch matrix [B Hout Wout, 9 (C1 + C2)] of NHWC source(s), already split (stride 1|2, or nearest-2x first)
 cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2, int B, int Hin, int Win, int stride, int up, float* hi,
                                float* lo, cudaStream_t s);
-// out[M,N] = act(A W^T + bias + rowbias[m / rows_per_sample] + residual), operands pre-split, all fp32 row-major
+// number of K chunks whose partial tiles are summed in fp32 (1: K is short enough for one TMEM accumulation)
+int f32tc_splits(int K);
+// out[M,N] = act(A W^T + bias + rowbias[m / rows_per_sample] + residual), operands pre-split, all fp32 row-major.
+// partial_ws: fp32 [f32tc_splits(K), M, N] workspace for the two-level accumulation, or null (single accumulation whatever K)
 cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
                        const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
-                       cudaStream_t s);
+                       float* partial_ws, cudaStream_t s);
 }  // namespace wd
