@@ -230,3 +230,34 @@ def test_attention_maps_variant_state_dict_layout():
     x = torch.zeros(1, 4, 8, 32)
     with pytest.raises(NotImplementedError):
         m(x, None, timesteps=torch.tensor([1]), context=torch.zeros(1, 10, dtype=torch.long), y=torch.tensor([0]))
+
+
+def test_tf32_split_arithmetic_the_tensor_core_fp32_route_relies_on():
+    """csrc/f32_gemm_tc.cu: a = hi + lo with hi = tf32_rn(a) (low 13 mantissa bits zero) and lo = a - hi EXACT in fp32; the three-term
+    product hi*whi + lo*whi + hi*wlo (each factor seen by the tensor core with at most 10 mantissa bits of lo / wlo kept) is within
+    ~2^-20 of a*w, whereas a two-term bf16 split leaves ~2^-16."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal(20000).astype(np.float32)
+    w = rng.standard_normal(20000).astype(np.float32)
+
+    def rn(x, drop):   # round-to-nearest (ties away, like cvt.rna) to a mantissa with `drop` low bits cleared
+        u = x.view(np.uint32).astype(np.uint64)
+        u = (u + (1 << (drop - 1))) & ~np.uint64((1 << drop) - 1)
+        return u.astype(np.uint32).view(np.float32)
+
+    def split(x, drop):
+        hi = rn(x, drop)
+        lo = (x - hi).astype(np.float32)
+        assert np.array_equal(hi.astype(np.float64) + lo.astype(np.float64), x.astype(np.float64))   # exact
+        assert np.all(np.abs(lo) <= np.abs(x) * 2.0 ** -(23 - drop) * 1.0001)
+        return hi, rn(lo, drop)     # the hardware keeps only the same mantissa width of lo
+
+    exact = a.astype(np.float64) * w.astype(np.float64)
+    errs = {}
+    for name, drop in (("tf32", 13), ("bf16", 16)):
+        ah, al = split(a, drop)
+        wh, wl = split(w, drop)
+        approx = (ah.astype(np.float64) * wh + al.astype(np.float64) * wh + ah.astype(np.float64) * wl)
+        errs[name] = float(np.max(np.abs(approx - exact) / np.abs(exact)))
+    assert errs["tf32"] < 2.0 ** -19 and errs["bf16"] > 2.0 ** -17, errs
