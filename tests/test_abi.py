@@ -72,3 +72,22 @@ def test_no_cpu_fallback():
         m(x, None, timesteps=torch.tensor([1]), context=torch.zeros(1, 10, dtype=torch.long), y=torch.tensor([0]))
     with pytest.raises(RuntimeError):
         m.input_blocks[1][0](x)  # parameter holders carry no arithmetic
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under worddiffusion_b200/ (Python or CUDA) may import, open or name oracle/ or
+    /root/reference; bench.py may execute the oracle only in its cpu_baseline / --impl reference legs."""
+    pkg = os.path.join(ROOT, "worddiffusion_b200")
+    pat = re.compile(r"^\s*(from|import)\s+\S*(oracle|ref_shims|weights)\b|/root/reference|sys\.path")
+    hits = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                for i, line in enumerate(open(os.path.join(d, f), errors="replace"), 1):
+                    if pat.search(line):
+                        hits.append(f"{f}:{i}: {line.strip()[:100]}")
+    assert not hits, hits
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # the only functions of bench.py that import the oracle's UNet are the CPU-baseline ones
+    assert bench.count("import unet_oracle") == 1
+    assert bench.split("import unet_oracle")[0].rsplit("\ndef ", 1)[1].startswith("cpu_oracle_throughput(")
