@@ -102,23 +102,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_throughput(model, seconds=12.0, batch=8, threads=None):
-    """The reference's CPU path (oracle port, fp32, torch CPU ops on `threads` host threads): latent-steps/s of
-    UNet evaluation + DDPM update on a bounded sample of the workload."""
-    import torch
+def _load_oracle():
+    """The oracle (test infrastructure) is imported HERE and only here: by the CPU-baseline / `--impl reference` legs and by the
+    labelled torch-eager comparator below -- never by the product path being measured."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import unet_oracle as UO
     import weights as W
     from diffusion_oracle import DiffusionOracle
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    variant = "unet" if model == "unet" else "unetPhosc"
+    return UO, W, DiffusionOracle
+
+
+def _cpu_sample(UO, W, DiffusionOracle, variant, batch, seconds):
+    """latent-steps/s of the oracle port at one batch size over about `seconds` of host time (first evaluation = warm-up)."""
+    import torch
     sd = W.make_state_dict(W.load_spec(variant), 1234)
     inp = W.make_inputs(batch, seed=1234)
     d = DiffusionOracle(1000)
     x = inp["x"].clone()
     phosc = inp["phosc"] if variant != "unet" else None
-    n, t0 = 0, None
+    n, t0, el = 0, None, 0.0
     i = 999
     with torch.no_grad():
         while True:
@@ -134,9 +136,74 @@ def cpu_oracle_throughput(model, seconds=12.0, batch=8, threads=None):
             el = time.perf_counter() - t0
             if el >= seconds or i <= 1:
                 break
-    return dict(value=n * batch / el, unit=UNIT, cores=threads, kind="port",
-                sample=f"{n} DDPM steps of the {variant} oracle port at batch {batch} (fp32, torch CPU, {threads} threads, "
-                       f"{el:.1f} s), context re-encoded every step as in the reference")
+    return n, el
+
+
+def cpu_oracle_throughput(model, seconds=12.0, batch=8, threads=None, sweep=True):
+    """The reference's CPU path (oracle port, fp32, torch CPU ops on `threads` host threads): latent-steps/s of
+    UNet evaluation + DDPM update on a bounded sample of the workload; plus short samples at batch 1 / 16 / 64 and
+    the BASELINE config-1 trajectory time (batch 1, 999 steps) extrapolated from the batch-1 rate."""
+    import torch
+    UO, W, DiffusionOracle = _load_oracle()
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    variant = "unet" if model == "unet" else "unetPhosc"
+    n, el = _cpu_sample(UO, W, DiffusionOracle, variant, batch, seconds)
+    out = dict(value=n * batch / el, unit=UNIT, cores=threads, kind="port",
+               sample=f"{n} DDPM steps of the {variant} oracle port at batch {batch} (fp32, torch CPU, {threads} threads, "
+                      f"{el:.1f} s), context re-encoded every step as in the reference")
+    if sweep:
+        by = {}
+        for b, sec in ((1, 3.0), (16, 4.0), (64, 6.0)):
+            nb, elb = _cpu_sample(UO, W, DiffusionOracle, variant, b, sec * seconds / 12.0)
+            by[str(b)] = {"latent_steps_per_sec": round(nb * b / elb, 2), "ms_per_unet_eval": round(1e3 * elb / nb, 2), "steps": nb}
+        out["by_batch"] = by
+        out["config1_trajectory_s_extrapolated"] = round(999.0 / by["1"]["latent_steps_per_sec"], 1)
+        out["config1"] = f"{variant}, batch 1, 999 DDPM steps on {threads} host threads, one UNet call per step (train.py:224-228 makes two)"
+    return out
+
+
+def gpu_eager_reference(model, batch, dev, steps=5):
+    """Labelled comparator, NOT the reference arm (SURVEY 8d / BASELINE.md section 4 "also report"): what a user of the reference gets
+    on this same B200 today -- the reference's forward as torch-eager ops (the oracle, a functional restatement that matches the
+    reference modules bit for bit on the CPU) with the weights on the GPU, once in fp32 with torch's defaults (TF32 convolutions
+    through cuDNN, fp32 matmuls) and once under autocast(bfloat16); same batch, context re-encoded every step as the reference
+    does, CUDA-event timed after a warm-up.  cuDNN / cuBLAS kernels: none of this repo's code runs here."""
+    import torch
+    UO, W, DiffusionOracle = _load_oracle()
+    variant = "unet" if model == "unet" else "unetPhosc"
+    sd = {k: v.to(dev) for k, v in W.make_state_dict(W.load_spec(variant), 1234).items()}
+    inp = {k: v.to(dev) for k, v in W.make_inputs(batch, seed=1234).items()}
+    phosc = inp["phosc"] if variant != "unet" else None
+    t = torch.full((batch,), 500, dtype=torch.long, device=dev)
+    res = {"label": "torch-eager oracle forward on the same GPU (cuDNN / cuBLAS); comparator only, not the reference arm",
+           "batch": batch, "model": variant}
+    ref32 = None
+    for name, ctxmgr in (("fp32_torch_defaults", None), ("autocast_bf16", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def run():
+            with torch.no_grad():
+                if ctxmgr is None:
+                    return UO.unet_forward(sd, inp["x"], t, inp["context"], inp["y"], phosc=phosc, variant=variant)
+                with ctxmgr:
+                    return UO.unet_forward(sd, inp["x"], t, inp["context"], inp["y"], phosc=phosc, variant=variant)
+        for _ in range(2):
+            out = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"ms_per_step": round(ms, 3), "latent_steps_per_sec": round(batch / (ms * 1e-3), 1)}
+        if ref32 is None:
+            ref32 = out.float()
+        else:
+            res[name]["max_rel_vs_fp32_eager"] = float((out.float() - ref32).abs().max() / ref32.abs().max())
+    del sd, inp
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
@@ -145,7 +212,7 @@ def run_reference(args):
         return
     batch = 8
     t0 = time.perf_counter()
-    cb = cpu_oracle_throughput(args.model, seconds=max(2.0, 3.0 * args.steps), batch=batch)
+    cb = cpu_oracle_throughput(args.model, seconds=max(2.0, 3.0 * args.steps), batch=batch, sweep=False)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * batch / cb["value"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -155,6 +222,93 @@ def run_reference(args):
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(out), flush=True)
+
+
+def _build_model(cls, variant, dev, W):
+    from worddiffusion_b200.unet_base import default_args
+    m = cls(args=default_args(dev), **MODEL_KW)
+    m.load_state_dict(W.make_state_dict(W.load_spec(variant), 1234), strict=True)
+    return m.to(dev).eval()
+
+
+def sharded_step_leg(model, variant, global_batch, world, rank, dev, steps, warmup, W):
+    """K DDPM steps of a GLOBAL batch split over the ranks (contiguous shards, Philox keyed by the global latent index, no
+    per-step collective) + the trajectory's all-gather, device-timed, max over ranks.  `strong_scaling`: BASELINE configs[1]'s
+    256 latents over N GPUs; `config3`: unetPhosc, 1024 latents over N GPUs (BASELINE configs[2])."""
+    import torch
+    import torch.distributed as dist
+    from worddiffusion_b200.diffusion import Diffusion, all_gather_latents, shard_bounds
+    lo, hi = shard_bounds(global_batch, world, rank)
+    inp = W.make_inputs(global_batch, seed=777)
+    ctx, y = inp["context"][lo:hi].to(dev), inp["y"][lo:hi].to(dev)
+    phosc = inp["phosc"][lo:hi].to(dev) if variant != "unet" else None
+    diff = Diffusion(noise_steps=1000, device=dev)
+    eng = model.engine(dev)
+    eng.encode_context(ctx, phosc)
+    x = inp["x"][lo:hi].to(dev).clone()
+    T = diff.noise_steps
+
+    def step(i, k):
+        eng.sampler_step(x, i, y, 1, diff._ddpm_coef[i], philox_seed=1234, sample_offset=lo, step_index=k)
+
+    for k in range(warmup):
+        step(T - 1 - k, k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        step(T - 1 - warmup - k, warmup + k)
+    if world > 1:
+        all_gather_latents(x, global_batch, world)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"metric": METRIC, "model": variant, "global_batch": global_batch, "batch_per_gpu": hi - lo, "n_gpus": world,
+            "scaling": "strong", "steps": steps, "ms_per_step": ms, "value": global_batch / (ms * 1e-3), "unit": UNIT,
+            "gpu_launches_per_step": eng.last_launch_count,
+            "step_tflops": round(global_batch * GFLOP_PER_LATENT[variant] * 1e9 / (ms * 1e-3) / 1e12, 1)}
+
+
+def ddim50_sweep_leg(model, world, rank, dev, batches, W):
+    """BASELINE configs[4]: DDIM eta = 0, 50 strided steps, unetPhosc2 (10 chars + 769 PHOSC tokens), GLOBAL batch sweep sharded
+    over the ranks; whole trajectories (context encoding, device-Philox x_T, 50 fused steps, all-gather), second run timed."""
+    import torch
+    import torch.distributed as dist
+    from worddiffusion_b200.diffusion import Diffusion
+    d = Diffusion(noise_steps=1000, device=dev)
+    rows = []
+    for N in batches:
+        if N < world:
+            continue
+        inp = W.make_inputs(N, seed=1234)
+        ctx, y, ph = inp["context"].to(dev), inp["y"].to(dev), inp["phosc"].to(dev)
+        ms = None
+        for rep in range(2):  # first trajectory = warm-up (plan + arena allocation for this batch)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            x = d.sample_latents_sharded(model, ctx, y, phosc=ph, seed=7, ddim_steps=50)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ok = bool(x.shape[0] == N and torch.isfinite(x).all())
+        rows.append({"global_batch": N, "n_gpus": world, "trajectory_ms": round(ms, 3), "word_latents_per_sec": round(N / (ms * 1e-3), 2),
+                     "latent_steps_per_sec": round(50 * N / (ms * 1e-3), 1), "finite": ok})
+        del x, ctx, y, ph
+    return {"workload": "unetPhosc2.UNetModelPhosc DDIM eta=0, 50 of 1000 timesteps, ctx 779 tokens; global batch sharded over the "
+                        "ranks, one all-gather per trajectory", "scaling": "strong", "rows": rows}
 
 
 def train_leg(args, world, rank, dev):
@@ -392,6 +546,29 @@ def run_ours(args):
     if args.train_steps > 0 and variant == "unet":
         train = train_leg(args, world, rank, dev)
 
+    # sharded sampling legs: every rank takes part.  strong scaling of the headline workload (N = 1: the headline itself),
+    # BASELINE configs[2] (unetPhosc, global 1024) and configs[4] (DDIM-50 sweep on unetPhosc2)
+    extra = {}
+    if variant == "unet" and not args.no_extra_legs:
+        try:
+            if world > 1:
+                extra["strong_scaling"] = sharded_step_leg(model, "unet", B, world, rank, dev, K, Wm, W)
+            else:
+                extra["strong_scaling"] = {"metric": METRIC, "model": "unet", "global_batch": B, "batch_per_gpu": B, "n_gpus": 1,
+                                           "scaling": "strong", "steps": K, "ms_per_step": ms / K, "value": value, "unit": UNIT,
+                                           "note": "N = 1: the headline run itself"}
+            from worddiffusion_b200.unetPhosc2 import UNetModelPhosc as UNetModelPhosc2
+            mp = _build_model(UNetModelPhosc, "unetPhosc", dev, W)
+            extra["config3_unetPhosc_b1024"] = sharded_step_leg(mp, "unetPhosc", 1024, world, rank, dev, max(5, K // 2), 3, W)
+            del mp
+            torch.cuda.empty_cache()
+            mp2 = _build_model(UNetModelPhosc2, "unetPhosc", dev, W)
+            extra["config5_ddim50_sweep"] = ddim50_sweep_leg(mp2, world, rank, dev, [int(b) for b in args.ddim_batches.split(",")], W)
+            del mp2
+            torch.cuda.empty_cache()
+        except Exception as ex:   # a side leg must not cost the headline line (every rank fails the same way: no hang)
+            extra["error"] = f"{type(ex).__name__}: {ex}"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -429,8 +606,10 @@ def run_ours(args):
     g = "gemm_tc"
     ach = cls_f[g] / (cls_t[g] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM: 3x3 convs, 1x1 convs, linears)", "bound": "tensor",
-                "achieved": round(ach, 2), "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sust"], 4),
-                "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                "achieved": round(ach, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_burst"], 4),
+                "peak_source": f"{peaks['src']} bf16 burst (MEASURED_PEAKS.json bf16_tflops): the timed region is tens of ms and the "
+                               "SM clock stays at its maximum (see `clocks`)",
+                "peak_sustained": peaks["tf_sust"], "frac_sustained": round(ach / peaks["tf_sust"], 4),
                 "flops_per_launch_avg": cls_f[g] / cls_n[g], "launches_per_step": cls_n[g],
                 "avg_launch_ms": round(cls_t[g] / cls_n[g], 5), "share_of_step": kernels[g]["share"], "traffic": None,
                 "timing": "CUDA events around every launch of the same K steps, run as a second pass right after the timed region "
@@ -451,7 +630,8 @@ def run_ours(args):
                       "batch_per_gpu": B, "global_batch": B * world, "noise_steps": 1000,
                       "l2": "inputs larger than L2: %.1f GB activation arena per step vs 126 MB L2" % (eng.workspace_bytes / 1e9)},
            "unet_steps_per_sec": K / (ms * 1e-3), "word_latents_per_sec_999_steps": value / 999.0,
-           "step_tflops": round(step_tf, 1), "step_frac_of_bf16_sustained": round(step_tf / peaks["tf_sust"], 4),
+           "step_tflops": round(step_tf, 1), "step_frac_of_bf16_burst": round(step_tf / peaks["tf_burst"], 4),
+           "step_frac_of_bf16_sustained": round(step_tf / peaks["tf_sust"], 4),
            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
     if cb is not None:
         out["cpu_baseline"] = cb
@@ -459,6 +639,12 @@ def run_ours(args):
         out["train_step"] = train
     if fp32 is not None:
         out["fp32_mode"] = fp32
+    out.update(extra)
+    if world == 1 and args.eager_steps > 0:
+        try:
+            out["gpu_eager_reference"] = gpu_eager_reference(variant, B, dev, steps=args.eager_steps)
+        except Exception as ex:
+            out["gpu_eager_reference"] = {"error": f"{type(ex).__name__}: {ex}"}
     if real_stdout is not None:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
@@ -481,6 +667,9 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the training leg (0: skip it)")
     ap.add_argument("--fp32-steps", type=int, default=3, help="timed steps of the fp32-mode leg on rank 0 (0: skip it)")
     ap.add_argument("--train-batch", type=int, default=224, help="GLOBAL batch of the training leg (BASELINE config 4)")
+    ap.add_argument("--eager-steps", type=int, default=5, help="timed steps of the torch-eager-on-GPU comparator (0: skip it)")
+    ap.add_argument("--ddim-batches", default="1,16,256,1024,4096", help="global batches of the DDIM-50 sweep leg (config 5)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip strong-scaling / config-3 / config-5 legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

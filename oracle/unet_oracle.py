@@ -19,7 +19,7 @@ import torch.nn.functional as F
 def timestep_embedding(timesteps, dim, max_period=10000):
     """unet.py:96-116 (unetPhosc.py:89-109)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device) / half)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -47,7 +47,7 @@ def character_encoder(sd, tokens, max_seq_len, always_pe):
     x = F.embedding(tokens, sd["word_emb.embedding.weight"])
     L, D = x.shape[1], x.shape[2]
     if always_pe or L <= max_seq_len:
-        x = x + positional_encoding(max_seq_len, D)[:L, :]
+        x = x + positional_encoding(max_seq_len, D)[:L, :].to(x.device)
     q = _lin(sd, "word_emb.attention.linear_query", x)
     k = _lin(sd, "word_emb.attention.linear_key", x)
     v = _lin(sd, "word_emb.attention.linear_value", x)

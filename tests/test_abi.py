@@ -88,6 +88,13 @@ def test_product_package_never_touches_the_oracle_or_the_reference():
                         hits.append(f"{f}:{i}: {line.strip()[:100]}")
     assert not hits, hits
     bench = open(os.path.join(ROOT, "bench.py")).read()
-    # the only functions of bench.py that import the oracle's UNet are the CPU-baseline ones
+    # bench.py imports the oracle's UNet in ONE place (_load_oracle), reached only from the CPU-baseline function (also the
+    # `--impl reference` arm) and from the labelled torch-eager comparator -- never from the measured product path
     assert bench.count("import unet_oracle") == 1
-    assert bench.split("import unet_oracle")[0].rsplit("\ndef ", 1)[1].startswith("cpu_oracle_throughput(")
+    assert bench.split("import unet_oracle")[0].rsplit("\ndef ", 1)[1].startswith("_load_oracle(")
+    callers = set()
+    for chunk in bench.split("\ndef ")[1:]:
+        name, body = chunk.split("(", 1)
+        if "_load_oracle()" in body:
+            callers.add(name)
+    assert callers == {"cpu_oracle_throughput", "gpu_eager_reference"}, callers

@@ -180,6 +180,76 @@ def test_fused_train_step_reduces_loss_and_tracks_ema():
     assert float(torch.nn.functional.mse_loss(noise, e)) < losses[0]
 
 
+def test_trainer_validates_every_extent():
+    """the C side copies batch * C * H * W floats from the pointers it is handed; a wrong latent size / ragged
+    conditioning must raise before any kernel runs, not read out of bounds."""
+    from worddiffusion_b200._lib import WdError
+    m, _ = _model()
+    eng = m.train_engine(DEV)
+    eng.bind()
+    eng.sync_weights()
+    inp = {k: v.to(DEV) for k, v in W.make_inputs(2, seed=1).items()}
+    with pytest.raises(WdError, match="trainer built for latents"):
+        eng.forward(torch.zeros(2, 4, 8, 16, device=DEV), inp["t"], inp["y"], inp["context"])
+    with pytest.raises(WdError, match="timesteps"):
+        eng.forward(inp["x"], inp["t"][:1], inp["y"], inp["context"])
+    with pytest.raises(WdError, match="y must be"):
+        eng.forward(inp["x"], inp["t"], inp["y"][:1], inp["context"])
+    with pytest.raises(WdError, match="context"):
+        eng.forward(inp["x"], inp["t"], inp["y"], inp["context"][:1])
+    eng.forward(inp["x"], inp["t"], inp["y"], inp["context"])
+    with pytest.raises(WdError, match="d_eps"):
+        eng.backward(torch.zeros(1, 4, 8, 32, device=DEV))
+
+
+def test_training_at_the_reference_default_latent_size():
+    """train.Diffusion defaults to img_size = (64, 128) -> 8 x 16 latents (train.py:175): the drop-in forward builds a trainer for
+    the latent size it is called with; eps and gradients vs the oracle's autograd."""
+    m, sd = _model()
+    B = 3
+    inp = W.make_inputs(B, seed=SEED + 31, latent=(4, 8, 16))
+    noise = torch.randn((B, 4, 8, 16), generator=torch.Generator().manual_seed(9))
+    loss, pred = _backward(m, inp, noise)
+    assert m._train_engine.latent_hw == (8, 16) and pred.shape == (B, 4, 8, 16)
+    ref_loss, ref_eps, ref = TO.unet_loss_and_grads(sd, inp["x"], inp["t"], inp["context"], inp["y"], noise)
+    assert relerr(pred.detach(), ref_eps) < 1.5e-2
+    errs = {n: _rel_l2(p.grad, ref[n]) for n, p in m.named_parameters() if ref[n] is not None and float(ref[n].norm()) >= 1e-6}
+    bad = {n: e for n, e in errs.items() if e >= GRAD_TOL}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    # back to 8 x 32: a new trainer, same parameters
+    inp2 = W.make_inputs(2, seed=SEED)
+    _backward(m, inp2, torch.randn((2, 4, 8, 32), generator=torch.Generator().manual_seed(1)))
+    assert m._train_engine.latent_hw == (8, 32)
+
+
+def test_fused_step_invalidates_both_inference_engines():
+    """the AdamW kernel writes the parameters without bumping torch's version counters; after a fused step the bf16
+    engine AND the fp32-mode engine must serve the updated weights (eps vs the oracle on the updated state_dict)."""
+    import unet_oracle as UO
+    m, _ = _model()
+    inp = W.make_inputs(2, seed=SEED + 7)
+    x, t, c, y = (inp[k].to(DEV) for k in ("x", "t", "context", "y"))
+    m.eval()
+    m.precision = "fp32"
+    with torch.no_grad():
+        e_before = m(x, None, timesteps=t, context=c, y=y).clone()   # builds the fp32 engine on the initial weights
+    m.train()
+    step = FusedTrainStep(m, lr=5e-4, use_ema=False)
+    noise = torch.randn((2, 4, 8, 32), generator=torch.Generator().manual_seed(6)).to(DEV)
+    for _ in range(3):
+        step.step(x, t, c, y, noise)
+    m.eval()
+    sd_now = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ref = UO.unet_forward(sd_now, inp["x"], inp["t"], inp["context"], inp["y"], variant="unet")
+    with torch.no_grad():
+        e32 = m(x, None, timesteps=t, context=c, y=y).clone()
+        m.precision = "bf16"
+        e16 = m(x, None, timesteps=t, context=c, y=y).clone()
+    assert relerr(e_before, ref) > 1e-2, "the steps did not move the weights enough for this test to mean anything"
+    assert relerr(e32, ref) < 1e-4
+    assert relerr(e16, ref) < 1e-2
+
+
 def test_data_parallel_training_two_gpus():
     """N = 2 ranks over NCCL (skipped on a single-GPU box): tools/ddp_check.py."""
     import subprocess

@@ -1,0 +1,138 @@
+"""GPU parity over whole sampling trajectories (north_star: "the final latent after a full trajectory within a stated
+tolerance"), through the drop-in nn.Module -> ctypes -> C ABI -> sm_100a kernels, against the CPU oracle:
+
+  * DDIM, 50 steps of T = 1000 (BASELINE config 5) on ``unetPhosc2.UNetModelPhosc`` (779-token context), batch 2;
+  * the full 999-step DDPM trajectory (BASELINE configs 1 / 2) on ``unet.UNetModel``, batch 1, pre-generated noise.
+
+Two numbers per run.  (1) Per-step predicted noise, *teacher-forced*: the oracle evaluates the UNet on the very latent the GPU
+path saw at that step, so the figure is the error of one evaluation -- the quantity north_star bounds by 1e-2 (bf16) / 1e-4
+(fp32 mode).  (2) Final latent, *free-running*: oracle trajectory vs GPU trajectory from the same x_T and the same noise; the
+per-step errors compound through the sampler recurrence, and the tolerance asserted is the one DESIGN.md section 5 states.
+Error measure everywhere: max |a - b| / max |b| (tests/gpu_util.relerr)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unet_oracle as UO  # noqa: E402
+import weights as W  # noqa: E402
+from diffusion_oracle import DiffusionOracle  # noqa: E402
+from gpu_util import DEV, relerr  # noqa: E402
+from worddiffusion_b200.diffusion import Diffusion  # noqa: E402
+from worddiffusion_b200.unet import UNetModel, default_args  # noqa: E402
+from worddiffusion_b200.unetPhosc2 import UNetModelPhosc as UNetModelPhosc2  # noqa: E402
+
+SEED = 1234
+KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1,
+          attention_resolutions=(1, 1), channel_mult=(1, 1), num_heads=4, num_classes=339, context_dim=320,
+          vocab_size=53, max_seq_len=10)
+# per-step predicted noise (north_star) and final latent after the trajectory
+TOL_EPS = {"bf16": 1e-2, "fp32": 1e-4}
+TOL_FINAL_DDIM50 = {"bf16": 3e-2, "fp32": 1e-4}
+TOL_FINAL_DDPM999 = {"bf16": 5e-2, "fp32": 5e-4}
+
+
+def _model(cls, variant):
+    m = cls(args=default_args(DEV), **KW)
+    sd = W.make_state_dict(W.load_spec(variant), SEED)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+@pytest.fixture(scope="module")
+def phosc2():
+    return _model(UNetModelPhosc2, "unetPhosc")
+
+
+@pytest.fixture(scope="module")
+def unet():
+    return _model(UNetModel, "unet")
+
+
+@pytest.fixture(scope="module")
+def ddim_oracle_run(phosc2):
+    """Free-running oracle DDIM-50 trajectory (fp32 UNet oracle, fp64 scheduler spec): computed once for both precisions."""
+    _, sd = phosc2
+    inp = W.make_inputs(2, seed=SEED + 50)
+    o = DiffusionOracle(1000)
+    ts = o.ddim_timesteps(50)
+    assert ts[0] == 980 and ts[-1] == 0 and len(ts) == 50
+    x = inp["x"].clone()
+    for k, t in enumerate(ts):
+        tp = ts[k + 1] if k + 1 < len(ts) else -1
+        eps = UO.unet_forward(sd, x, torch.full((2,), t, dtype=torch.long), inp["context"], inp["y"], phosc=inp["phosc"],
+                              variant="unetPhosc")
+        x = o.ddim_step(x, eps, t, tp)
+    return inp, ts, x
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_ddim50_trajectory_unetphosc2_vs_oracle(phosc2, ddim_oracle_run, precision):
+    m, sd = phosc2
+    inp, ts, x_ref = ddim_oracle_run
+    d = Diffusion(noise_steps=1000, device=DEV)
+    assert d.ddim_timesteps(50) == ts
+    seen = []
+    m.precision = precision
+    try:
+        x, trace = d.ddim_sample_latents(m, inp["context"].to(DEV), inp["y"].to(DEV), phosc=inp["phosc"].to(DEV), num_steps=50,
+                                         x_T=inp["x"].to(DEV), return_eps_trace=True,
+                                         on_step=lambda k, t, xx: seen.append(xx.detach().cpu().clone()))
+    finally:
+        m.precision = "bf16"
+    assert len(trace) == 50 and len(seen) == 50
+    worst = 0.0
+    for k, t in enumerate(ts):
+        ref = UO.unet_forward(sd, seen[k], torch.full((2,), t, dtype=torch.long), inp["context"], inp["y"], phosc=inp["phosc"],
+                              variant="unetPhosc")
+        e = relerr(trace[k], ref)
+        worst = max(worst, e)
+        assert e < TOL_EPS[precision], (precision, k, t, e)
+    err = relerr(x, x_ref)
+    print(f"DDIM-50 unetPhosc2 [{precision}]: worst per-step eps err {worst:.3e}, final latent err {err:.3e}")
+    assert torch.isfinite(x).all()
+    assert err < TOL_FINAL_DDIM50[precision], (precision, err)
+
+
+@pytest.fixture(scope="module")
+def ddpm_oracle_run(unet):
+    """Free-running oracle DDPM trajectory, all 999 steps of train.py:217-236 at batch 1 (about a minute of host time)."""
+    _, sd = unet
+    inp = W.make_inputs(1, seed=SEED + 999)
+    T = 1000
+    noises = torch.randn((T, 1, 4, 8, 32), generator=torch.Generator().manual_seed(SEED + 1))
+    o = DiffusionOracle(T)
+
+    def eps_fn(x, t):
+        return UO.unet_forward(sd, x, t, inp["context"], inp["y"], variant="unet")
+    x_ref = o.ddpm_sample(eps_fn, inp["x"], noises)
+    return inp, noises, x_ref
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ddpm_full_999_step_trajectory_vs_oracle(unet, ddpm_oracle_run, precision):
+    m, sd = unet
+    inp, noises, x_ref = ddpm_oracle_run
+    d = Diffusion(noise_steps=1000, device=DEV)
+    probe = {999: inp["x"].clone()}
+
+    def on_step(i, x):  # called AFTER step i: x is the input of step i - 1
+        if i - 1 >= 1 and ((i - 1) % 111 == 0 or i - 1 == 1):
+            probe[i - 1] = x.detach().cpu().clone()
+    m.precision = precision
+    try:
+        x, trace = d.sample_latents(m, inp["context"].to(DEV), inp["y"].to(DEV), x_T=inp["x"].to(DEV), noise=noises.to(DEV),
+                                    return_eps_trace=True, on_step=on_step)
+    finally:
+        m.precision = "bf16"
+    assert len(trace) == 999
+    worst = 0.0
+    for i, xin in sorted(probe.items()):
+        ref = UO.unet_forward(sd, xin, torch.full((1,), i, dtype=torch.long), inp["context"], inp["y"], variant="unet")
+        e = relerr(trace[999 - i], ref)  # trace[0] is step 999
+        worst = max(worst, e)
+        assert e < TOL_EPS[precision], (precision, i, e)
+    err = relerr(x, x_ref)
+    print(f"DDPM-999 unet [{precision}]: {len(probe)} teacher-forced steps, worst eps err {worst:.3e}, final latent err {err:.3e}")
+    assert torch.isfinite(x).all()
+    assert err < TOL_FINAL_DDPM999[precision], (precision, err)

@@ -261,3 +261,75 @@ def test_tf32_split_arithmetic_the_tensor_core_fp32_route_relies_on():
         approx = (ah.astype(np.float64) * wh + al.astype(np.float64) * wh + ah.astype(np.float64) * wl)
         errs[name] = float(np.max(np.abs(approx - exact) / np.abs(exact)))
     assert errs["tf32"] < 2.0 ** -19 and errs["bf16"] > 2.0 ** -17, errs
+
+
+def test_phosc_model_refuses_training_mode():
+    """in training mode UNetModelPhosc.forward used to run the inference engine and return a tensor without grad_fn
+    (a loss.backward() that trains nothing).  It must raise; eval() / no_grad() inference is unaffected (and then fails only
+    because this box has no GPU)."""
+    from worddiffusion_b200 import _lib
+    from worddiffusion_b200.unetPhosc import UNetModelPhosc
+    from worddiffusion_b200.unetPhosc2 import UNetModelPhosc as UNetModelPhosc2
+    x = torch.zeros(1, 4, 8, 32)
+    kw = dict(timesteps=torch.tensor([5]), context=torch.ones(1, 10, dtype=torch.long), y=torch.tensor([1]))
+    for cls in (UNetModelPhosc, UNetModelPhosc2):
+        m = cls(args=default_args("cpu"), **KW)
+        m.train()
+        with pytest.raises(NotImplementedError, match="training UNetModelPhosc"):
+            m(x, torch.zeros(1, 769), **kw)
+        with torch.no_grad(), pytest.raises(_lib.WdError):   # inference call shape is fine; only the device is not
+            m(x, torch.zeros(1, 769), **kw)
+        m.eval().requires_grad_(False)
+        with pytest.raises(_lib.WdError):
+            m(x, torch.zeros(1, 769), **kw)
+
+
+def test_ddim_timesteps_validation():
+    d = D.Diffusion(noise_steps=1000, device="cpu")
+    assert d.ddim_timesteps(1000) == list(range(999, -1, -1))
+    assert d.ddim_timesteps(30)[0] == 957 and len(d.ddim_timesteps(30)) == 30   # "leading" spacing: stride 33
+    for bad in (0, -3, 1001):
+        with pytest.raises(ValueError):
+            d.ddim_timesteps(bad)
+
+
+def test_parameter_cache_sees_replaced_parameters():
+    """The cached parameter walk of `_weights_signature` re-checks object identity on every call."""
+    m = UNetModel(args=default_args("cpu"), **KW)
+    s1 = m._weights_signature()
+    assert m._weights_signature() == s1
+    old = m.out[2].bias
+    m.out[2].bias = torch.nn.Parameter(old.detach().clone())
+    s2 = m._weights_signature()
+    assert s2 != s1 and len(s2) == len(s1)
+    with torch.no_grad():
+        m.out[2].bias.add_(1.0)          # in-place change: version counter
+    assert m._weights_signature() != s2
+    assert len(s1) == len(list(m.parameters()))
+
+
+def _empty_shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_total = 1                                      # fewer latents than ranks: rank 1 owns nothing
+    lo, hi = D.shard_bounds(n_total, world, rank)
+    full = torch.arange(n_total * 4 * 8 * 32, dtype=torch.float32).reshape(n_total, 4, 8, 32)
+    out = D.all_gather_latents(full[lo:hi].clone(), n_total, world)
+    q.put((rank, hi - lo, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+def test_all_gather_with_an_empty_shard_world2_gloo():
+    """with N < world size the rank without latents must still contribute (a zero-row pad) to the collective."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_empty_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, 1, True), (1, 0, True)]

@@ -138,6 +138,11 @@ class Diffusion:
         return (x, trace) if return_eps_trace else x
 
     def ddim_timesteps(self, num_steps):
+        """``num_steps`` timesteps ``0, s, 2s, ...`` with ``s = T // num_steps`` ("leading" spacing of the DDIM paper; the
+        specification is oracle/diffusion_oracle.py), highest first.  50 steps of T = 1000 start at t = 980."""
+        num_steps = int(num_steps)
+        if not 1 <= num_steps <= self.noise_steps:
+            raise ValueError(f"DDIM needs 1 <= num_steps <= noise_steps ({self.noise_steps}), got {num_steps}")
         stride = self.noise_steps // num_steps
         return list(range(0, self.noise_steps, stride))[:num_steps][::-1]
 
@@ -147,9 +152,11 @@ class Diffusion:
         return np.array([1.0 / np.sqrt(a_t), np.sqrt(1 - a_t), np.sqrt(a_p), np.sqrt(1 - a_p)], dtype=np.float32)
 
     @torch.no_grad()
-    def ddim_sample_latents(self, model, context, labels, phosc=None, num_steps=50, x_T=None, seed=0):
+    def ddim_sample_latents(self, model, context, labels, phosc=None, num_steps=50, x_T=None, seed=0,
+                            return_eps_trace=False, on_step=None):
         """Deterministic DDIM (eta = 0) over ``num_steps`` evenly strided timesteps of the reference schedule.
-        Not present in the reference; specified by oracle/diffusion_oracle.py."""
+        Not present in the reference; specified by oracle/diffusion_oracle.py.
+        ``on_step(k, t, x)`` is called BEFORE step k with the latent the UNet is about to see (parity tests)."""
         n = context.shape[0]
         eng, y = self._prepare(model, context, labels, phosc, n)
         h, w = self.img_size[0] // 8, self.img_size[1] // 8
@@ -159,10 +166,16 @@ class Diffusion:
         else:
             x = x_T.to(device=self.device, dtype=torch.float32).clone().contiguous()
         ts = self.ddim_timesteps(num_steps)
+        trace = [] if return_eps_trace else None
         for k, t in enumerate(ts):
             t_prev = ts[k + 1] if k + 1 < len(ts) else -1
-            eng.sampler_step(x, t, y, STEP_DDIM, self.ddim_coef(t, t_prev), step_index=k)
-        return x
+            if on_step is not None:
+                on_step(k, t, x)
+            eps_out = torch.empty_like(x) if return_eps_trace else None
+            eng.sampler_step(x, t, y, STEP_DDIM, self.ddim_coef(t, t_prev), step_index=k, eps_out=eps_out)
+            if return_eps_trace:
+                trace.append(eps_out)
+        return (x, trace) if return_eps_trace else x
 
     # ------------------------------------------------------------------ reference-shaped entry point
     @torch.no_grad()
@@ -191,14 +204,18 @@ class Diffusion:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         N = context.shape[0]
         lo, hi = shard_bounds(N, world, rank)
+        h, w = self.img_size[0] // 8, self.img_size[1] // 8
+        if hi == lo:
+            # more ranks than latents: this rank has nothing to sample but must still enter the collective
+            x = torch.empty((0, 4, h, w), device=self.device, dtype=torch.float32)
+            return all_gather_latents(x, N, world, group)
         ph = phosc[lo:hi] if phosc is not None else None
         lab = labels[lo:hi] if labels is not None else None
+        # x_T must also be independent of the sharding: every rank draws only ITS rows of the counter-based stream
+        xT = philox_normal_latents(hi - lo, (4, h, w), seed, lo, self.device)
         if ddim_steps:
-            # x_T must also be independent of the sharding: draw it from the same counter-based stream
-            xT = philox_like_normal((N, 4, self.img_size[0] // 8, self.img_size[1] // 8), seed, self.device)[lo:hi]
             x = self.ddim_sample_latents(model, context[lo:hi], lab, phosc=ph, num_steps=ddim_steps, x_T=xT)
         else:
-            xT = philox_like_normal((N, 4, self.img_size[0] // 8, self.img_size[1] // 8), seed, self.device)[lo:hi]
             x = self.sample_latents(model, context[lo:hi], lab, phosc=ph, x_T=xT, seed=seed, sample_offset=lo)
         return all_gather_latents(x, N, world, group)
 
@@ -210,10 +227,31 @@ def shard_bounds(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def philox_like_normal(shape, seed, device):
-    """Initial noise that is a pure function of (seed, global index): generated for the full batch on every rank."""
-    g = torch.Generator(device="cpu").manual_seed(int(seed))
-    return torch.randn(shape, generator=g).to(device)
+X_T_STREAM = 0x7FFFFFFF  # Philox "step" of the initial noise: no sampling step uses it (steps are < noise_steps)
+
+
+def philox_normal_latents(n, latent_shape, seed, sample_offset, device):
+    """``n`` initial latents x_T ~ N(0, I) drawn on the device from the sampler's own Philox4x32-10 stream, keyed by
+    (seed, X_T_STREAM, global latent index = sample_offset + row, element): a rank generates only its shard, and the rows do
+    not depend on how the batch is split.  Runs the ``wd_sampler_update`` kernel with coefficients that reduce it to
+    ``x <- 0 * (0 - 0) + 1 * z``."""
+    import ctypes as C
+
+    from ._lib import check, lib
+    device = torch.device(device)
+    if device.type != "cuda":
+        from ._lib import WdError
+        raise WdError("worddiffusion_b200 has no CPU path: the Philox stream lives in the CUDA library")
+    x = torch.zeros((n,) + tuple(latent_shape), device=device, dtype=torch.float32)
+    if n == 0:
+        return x
+    zeros = torch.zeros_like(x)
+    c4 = (C.c_float * 4)(0.0, 0.0, 1.0, 0.0)
+    with torch.cuda.device(device):
+        check(lib().wd_sampler_update(C.c_void_p(x.data_ptr()), C.c_void_p(zeros.data_ptr()), n, x[0].numel(), STEP_DDPM, c4,
+                                      C.c_void_p(0), 1, int(seed), int(sample_offset), X_T_STREAM,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "wd_sampler_update(x_T)")
+    return x
 
 
 def all_gather_latents(x_local, n_total, world, group=None):

@@ -33,8 +33,9 @@ def _ptr(t):
 class TrainEngine:
     """Handle of one ``wd_trainer`` bound to the parameters of a ``worddiffusion_b200.unet.UNetModel``."""
 
-    def __init__(self, module, device):
+    def __init__(self, module, device, latent_hw=(8, 32)):
         self.device = torch.device(device)
+        self.latent_hw = (int(latent_hw[0]), int(latent_hw[1]))
         if self.device.type != "cuda":
             raise _lib.WdError("worddiffusion_b200 trains on a CUDA (sm_100a) device only; there is no CPU path")
         self.module = module
@@ -54,7 +55,7 @@ class TrainEngine:
         cfg.context_dim, cfg.vocab_size = module.context_dim, module.vocab_size
         cfg.num_classes = module.num_classes or 0
         cfg.max_seq_len = module.max_seq_len
-        cfg.latent_h, cfg.latent_w = 8, 32
+        cfg.latent_h, cfg.latent_w = self.latent_hw
         cfg.add_label_emb = 1 if module._add_label_emb() else 0
         cfg.phosc_len = module._phosc_len()
         self.cfg = cfg
@@ -132,7 +133,21 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ step
     def forward(self, x, timesteps, y, context):
+        # the C side copies batch * C * H * W floats from / to these pointers: every extent is checked here
+        want = (self.module.in_channels,) + self.latent_hw
+        if x.dim() != 4 or tuple(x.shape[1:]) != want:
+            raise _lib.WdError(f"trainer built for latents [B, {want[0]}, {want[1]}, {want[2]}], got x {tuple(x.shape)} "
+                               "(module.train_engine(device, latent_hw) builds one for another size)")
         B = x.shape[0]
+        if B < 1:
+            raise _lib.WdError("empty training batch")
+        if timesteps.dim() != 1 or timesteps.shape[0] != B:
+            raise _lib.WdError(f"timesteps must be [{B}], got {tuple(timesteps.shape)}")
+        if context is None or context.dim() != 2 or context.shape[0] != B:
+            raise _lib.WdError(f"context must be [{B}, L] token ids, got {None if context is None else tuple(context.shape)}")
+        if self.cfg.add_label_emb:
+            if y is None or y.dim() != 1 or y.shape[0] != B:
+                raise _lib.WdError(f"y must be [{B}], got {None if y is None else tuple(y.shape)}")
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         t = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
         ctx = context.to(device=self.device, dtype=torch.int64).contiguous()
@@ -142,6 +157,7 @@ class TrainEngine:
             check(lib().wd_trainer_forward(self._h, B, _ptr(x), _ptr(t), _ptr(yy), _ptr(ctx), ctx.shape[1], _ptr(out),
                                            _stream_ptr()), "wd_trainer_forward")
         self._hold = (x, t, ctx, yy)
+        self._hold_shape = tuple(x.shape)
         return out
 
     def backward(self, d_eps, zero=True):
@@ -149,6 +165,8 @@ class TrainEngine:
         if self._hold is None:
             raise _lib.WdError("backward called without a forward")
         _, _, ctx, yy = self._hold
+        if tuple(d_eps.shape) != self._hold_shape:
+            raise _lib.WdError(f"d_eps must have the shape of the forward's x {self._hold_shape}, got {tuple(d_eps.shape)}")
         d = d_eps.to(device=self.device, dtype=torch.float32).contiguous()
         if zero:
             self.flat_grad.zero_()
@@ -172,7 +190,7 @@ class _UNetTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, timesteps, context, y, *params):
-        eng = module.train_engine(x.device)
+        eng = module.train_engine(x.device, x.shape[2:])
         eng.bind()
         eng.sync_weights()
         ctx.eng = eng
@@ -219,11 +237,11 @@ class FusedTrainStep:
     gradient is sum-all-reduced over NCCL and averaged (DDP semantics) before the update."""
 
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, ema_beta=0.995,
-                 step_start_ema=2000, process_group=None, use_ema=True):
+                 step_start_ema=2000, process_group=None, use_ema=True, latent_hw=(8, 32)):
         p0 = next(module.parameters())
         self.module = module
         self.device = p0.device
-        self.eng = module.train_engine(self.device)
+        self.eng = module.train_engine(self.device, latent_hw)
         self.eng.bind()
         eng = self.eng
         # move the live parameters into one flat fp32 buffer (same slices as the gradient buffer) and re-point them
@@ -266,7 +284,9 @@ class FusedTrainStep:
                                           self.eps, self.weight_decay, self.t, self.ema_beta, ema_mode, 1.0 / ws,
                                           _stream_ptr()), "wd_adamw_ema_step")
         eng.sync_weights(force=True)
-        self.module._engine_sig = None  # the inference engine re-packs on its next call (the kernel wrote the parameters)
+        # the kernel wrote the parameters behind torch's back (no _version bump): both inference engines (bf16 and fp32 mode)
+        # re-pack on their next call
+        self.module.invalidate_engine()
         return loss
 
     def ema_state_dict(self):

@@ -1,5 +1,7 @@
 """Drop-in for the reference ``unetPhosc.UNetModelPhosc`` (reference unetPhosc.py:751-1159): standard transformer
 block (self-attention, then cross-attention over chars + PHOSC tokens), 246 ``state_dict`` keys."""
+import torch
+
 from ._lib import VARIANT_PHOSC
 from .unet_base import UNetBase, default_args  # noqa: F401
 
@@ -34,4 +36,10 @@ class UNetModelPhosc(UNetBase):
                 assert y.shape == (x.shape[0],)       # unetPhosc2.py:1122
             elif y.shape[0] != x.shape[0]:
                 y = y[:x.shape[0]]                    # unetPhosc.py:1089-1090
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the training step is built for unet.UNetModel, the model train.py:403 trains; running the inference
+            # engine here would hand the caller a tensor without grad_fn and a loss.backward() that silently trains nothing
+            raise NotImplementedError(
+                "worddiffusion_b200: training UNetModelPhosc is not implemented (no backward for the 256-token self-attention "
+                "and the 779-token cross-attention); call model.eval() or wrap the call in torch.no_grad() for inference")
         return self._run(x, timesteps, context, y, phoscLabels if self._phosc_len() else None)

@@ -164,14 +164,25 @@ class UNetBase(nn.Module):
 
     def _weights_signature(self):
         """(data_ptr, version) of every parameter: re-pack the engine's bf16 weights when any of them changed.  Walking the
-        module tree costs ~0.5 ms per call (264 parameters), more than the host side of a whole denoising step, so the
-        parameter list is cached; `_apply` (.to / .cuda / .float), `load_state_dict` and every 256th call rebuild it (a
-        Parameter OBJECT replaced by hand is picked up then; call `invalidate_engine()` to force it)."""
-        self._sig_calls = getattr(self, "_sig_calls", 0) + 1
-        plist = getattr(self, "_param_cache", None)
-        if plist is None or (self._sig_calls & 255) == 0:
-            plist = self._param_cache = list(self.parameters())
-        return HotPathEngine.weights_signature((None, p) for p in plist)
+        module tree costs ~0.5 ms per call (264 parameters), more than the host side of a whole denoising step, so the walk is
+        cached as (owner module's ``_parameters`` dict, name, Parameter) triples and every call only re-checks that each dict
+        still holds the SAME Parameter object (~20 us): a Parameter replaced by hand (``m.out[2].bias = nn.Parameter(...)``)
+        is picked up by the very next forward.  `_apply` (.to / .cuda / .float) and `load_state_dict` drop the cache; a
+        sub-MODULE swapped after construction needs `invalidate_engine()`."""
+        cache = getattr(self, "_param_cache", None)
+        if cache is not None:
+            for owner, name, p in cache:
+                if owner.get(name) is not p:
+                    cache = None
+                    break
+        if cache is None:
+            cache = []
+            for mod in self.modules():
+                for name, p in mod._parameters.items():
+                    if p is not None:
+                        cache.append((mod._parameters, name, p))
+            self._param_cache = cache
+        return HotPathEngine.weights_signature((None, p) for _, _, p in cache)
 
     def invalidate_engine(self):
         self._param_cache = None
@@ -186,15 +197,18 @@ class UNetBase(nn.Module):
         self._param_cache = None
         return super().load_state_dict(*args, **kwargs)
 
-    def train_engine(self, device=None):
-        """The B200 training engine (forward + hand-written backward) bound to this module's parameters."""
+    def train_engine(self, device=None, latent_hw=None):
+        """The B200 training engine (forward + hand-written backward) bound to this module's parameters.  One trainer serves
+        one latent size (its plans and activation arena are laid out for it): a different ``latent_hw`` builds a new one."""
         from .training import TrainEngine
         p0 = next(self.parameters())
         device = torch.device(device) if device is not None else p0.device
         if device.type != "cuda":
             raise _lib.WdError("worddiffusion_b200 has no CPU path: move the model and its inputs to a CUDA (B200) device")
-        if self._train_engine is None or self._train_engine.device != device:
-            self._train_engine = TrainEngine(self, device)
+        latent_hw = tuple(int(v) for v in latent_hw) if latent_hw is not None else (
+            self._train_engine.latent_hw if self._train_engine is not None else (8, 32))
+        if self._train_engine is None or self._train_engine.device != device or self._train_engine.latent_hw != latent_hw:
+            self._train_engine = TrainEngine(self, device, latent_hw)
         return self._train_engine
 
     def _run(self, x, timesteps, context, y, phosc):
