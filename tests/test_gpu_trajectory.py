@@ -28,8 +28,10 @@ KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_channels=
           vocab_size=53, max_seq_len=10)
 # per-step predicted noise (north_star) and final latent after the trajectory
 TOL_EPS = {"bf16": 1e-2, "fp32": 1e-4}
-TOL_FINAL_DDIM50 = {"bf16": 3e-2, "fp32": 1e-4}
-TOL_FINAL_DDPM999 = {"bf16": 5e-2, "fp32": 5e-4}
+# measured on a B200 (profiles/R2a_gpu_tests.log): DDIM-50 bf16 7.9e-4 / fp32 1.3e-6; DDPM-999 bf16 6.8e-4 / fp32 1.2e-6 -- the sampler
+# recurrence contracts the per-step error (|d x_{t-1} / d eps| = (1-alpha)/sqrt(1-alpha_hat) << 1) instead of compounding it
+TOL_FINAL_DDIM50 = {"bf16": 5e-3, "fp32": 2e-5}
+TOL_FINAL_DDPM999 = {"bf16": 5e-3, "fp32": 2e-5}
 
 
 def _model(cls, variant):
