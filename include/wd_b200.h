@@ -164,6 +164,15 @@ int wd_op_attention(const void* q, int ldq, const void* k, const void* v, int ld
                     int Skv, int heads, float scale, void* stream);
 int wd_op_gemm_block_n(void);
 
+/* The whole transformer block of unet.UNetModel's SpatialTransformer as ONE kernel (csrc/tblock.cu; reference unet.py:337-345,
+ * 381-412: proj_in, two cross-attentions over the <= 16 context tokens fed by norm2, GEGLU feed-forward fed by norm3, proj_out +
+ * residual).  Operator form for the parity tests: tensors[25] = g (bf16 [B*HW,320] = GroupNorm(x_in)), x_in (fp16), ctx (bf16
+ * [B*L,320], the encoded context), then the 22 fp32 state_dict tensors of the block in the order listed at the definition.
+ * stage 0: out = the block's output (fp16 [B*HW,320]); 1..3: the LayerNorm-normalised residual stream (no affine part) after
+ * proj_in / attn1 / attn2; 4: the residual stream after the feed-forward.  gn_partial: GroupNorm partial sums of out or NULL. */
+int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int B, int HW, int L, int stage, void* out_f16,
+                      float* gn_partial, void* stream);
+
 /* ==== training step (reference train.py:281-294; model = unet.UNetModel, train.py:403) ==================================
  * predicted_noise = model(x_t, ..., timesteps=t, context=text_features, y=s_id); loss.backward(); optimizer.step();
  * ema.step_ema().  The trainer BINDS the caller's fp32 parameter and gradient tensors (reference state_dict layout, e.g.

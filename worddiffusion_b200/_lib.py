@@ -57,6 +57,7 @@ SIGNATURES = {
     "wd_op_q_ctx_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "wd_op_attention": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "wd_op_gemm_block_n": (_I, []),
+    "wd_op_tblock_unet": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _P, _P, _P]),
     # ---- training step ----
     "wd_trainer_create": (_I, [C.POINTER(WdConfig), C.POINTER(_P)]),
     "wd_trainer_destroy": (None, [_P]),

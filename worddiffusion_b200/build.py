@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libwd_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_pair.cu", "ops.cu", "attn_flash.cu", "attn_tc.cu", "engine.cu", "wgrad_tc.cu", "ops_bwd.cu", "train.cu", "f32_path.cu", "f32_gemm_tc.cu"]
-HEADERS = ["common.cuh", "gemm_tc.cuh", "ops.cuh", "wgrad_tc.cuh", "ops_bwd.cuh", "engine_internal.h", "epilogue.cuh", "f32_tc.h", os.path.join("..", "..", "include", "wd_b200.h")]
+SOURCES = ["gemm_tc.cu", "gemm_pair.cu", "ops.cu", "attn_flash.cu", "attn_tc.cu", "engine.cu", "wgrad_tc.cu", "ops_bwd.cu", "train.cu", "f32_path.cu", "f32_gemm_tc.cu", "tblock.cu"]
+HEADERS = ["common.cuh", "gemm_tc.cuh", "ops.cuh", "wgrad_tc.cuh", "ops_bwd.cuh", "engine_internal.h", "epilogue.cuh", "f32_tc.h", "tblock.cuh", os.path.join("..", "..", "include", "wd_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

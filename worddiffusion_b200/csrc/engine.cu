@@ -15,6 +15,7 @@
 #include "../../include/wd_b200.h"
 #include "gemm_tc.cuh"
 #include "ops.cuh"
+#include "tblock.cuh"
 
 using namespace wd;
 typedef __nv_bfloat16 bf16;
@@ -72,6 +73,8 @@ struct GemmW {
   float* bias = nullptr;
   int N = 0, K = 0;
   float* ln_s = nullptr;  // LayerNorm folded into this Linear: column sums of the gamma-scaled weights (GemmArgs::ln_s)
+  float* raw_w = nullptr;  // LayerNorm-folded Linears keep the fp32 state_dict tensors (the fold runs at finalize time)
+  float* raw_b = nullptr;
 };
 // one nn.Linear whose preceding LayerNorm is folded into it at finalize time (ops.cu: fold_ln_linear_kernel)
 struct LnFold {
@@ -106,6 +109,13 @@ struct TBlockL {
   GemmW a2_q, a2_kv, a2_out;
   GemmW ff_proj, ff_out;
   int kv1 = -1, kv2 = -1;  // index of the per-trajectory K/V buffer
+  // ---- fused transformer-block kernel (tblock.cu; unet.UNetModel only) ----
+  float *raw_k[2] = {nullptr, nullptr}, *raw_v[2] = {nullptr, nullptr}, *raw_o[2] = {nullptr, nullptr};  // fp32 to_k / to_v / to_out.0
+  bf16* w_fold = nullptr;   // [2 attentions][2560][320] rows of the pooled fold GEMM (tblock_fold_weights_launch)
+  float* u_fold = nullptr;  // [2][4][320]
+  int fold_idx = -1;        // position of this block's first attention in the pools
+  GemmW ff128;              // ff.net.0.proj with LayerNorm 3 folded in, value / gate rows interleaved per 64-column chunk
+  float* cb = nullptr;      // [4][320] cumulative residual-stream biases
 };
 struct STL {
   int C = 0, heads = 0, dh = 0;
@@ -139,7 +149,7 @@ struct Slot {
 // launch plan
 // ----------------------------------------------------------------------------------------------
 enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_GNSTATS, OP_UPSAMPLE,
-              OP_EMBED, OP_LINF32, OP_WORDATTN, OP_EMBTBL };
+              OP_EMBED, OP_LINF32, OP_WORDATTN, OP_EMBTBL, OP_TBLOCK, OP_TB_CVEC };
 // step ops that exist in two flavours: the time-embedding MLP per step (per-row timesteps: wd_unet_eval) or the lookup in
 // the per-trajectory table (one timestep for the whole batch: wd_sampler_step)
 enum OpCond { COND_ALWAYS = 0, COND_NO_TABLE = 1, COND_TABLE = 2 };
@@ -165,6 +175,8 @@ struct Op {
   struct { int which; const float* E; int vocab; const float* pe; int add_pe; float* out; int B, L, D; } emb;
   struct { const float* x; const float* W; const float* b; float* out; int M, N, K; } lin;
   struct { const float* q; const float* k; const float* v; bf16* ctx; int B, L, D, Ltot, row_off; } wa;
+  TBlockLaunch tb;
+  struct { const bf16* ctx; const float* u; float* out; int rows, heads; } cv;
 };
 
 struct Plan {
@@ -231,6 +243,12 @@ struct wd_engine {
   float* temb_table = nullptr;  // time_embed(t) for t < TEMB_TABLE_ROWS, fp32 [rows, 4 mc]: built once per weight load
   float* we_gram = nullptr;  // TQ TK^T [vocab, vocab]: the scores of a position-free Word_Attention segment (ops.cu: word_attn_hist_kernel)
   std::vector<LnFold> ln_folds;
+  // fused transformer block (tblock.cu): extra fp32 copies of state_dict tensors, and the pooled per-attention fold weights
+  std::unordered_multimap<std::string, float*> raw_extra;
+  int fold_count = 0;      // attentions with fold weights (counted by the dry layout pass)
+  int fold_next = 0;
+  bf16* fold_pool = nullptr;   // [fold_count][2560][320] bf16: ONE GEMM per trajectory produces every per-sample attention operand
+  float* u_pool = nullptr;     // [fold_count][4][320]
   // activations
   char* abase = nullptr;
   size_t acap = 0;
@@ -282,6 +300,12 @@ struct Builder {
     }
     return g;
   }
+  // an additional fp32 copy of a state_dict tensor (besides the destination of its slot)
+  float* raw_copy(const std::string& name, int64_t numel) {
+    float* p = A.alloc<float>(static_cast<size_t>(numel));
+    if (!dry) e->raw_extra.emplace(name, p);
+    return p;
+  }
   // nn.Linear(K, Nrows) whose input is LayerNorm `ln` of an fp16 token tensor: rows land at [n_off, n_off + Nrows) of `g`
   // (g.w / g.bias / g.ln_s are allocated by the caller for fused weights, or here when g.w is null)
   void linear_ln(GemmW& g, const std::string& pfx, int Nrows, int K, bool bias, const NormW& ln, int n_off = 0, int Ntotal = 0,
@@ -297,6 +321,8 @@ struct Builder {
     float* raw_b = bias ? A.alloc<float>(Nrows) : nullptr;
     slot(pfx + ".weight", S_F32, raw_w, static_cast<int64_t>(Nrows) * K);
     if (bias) slot(pfx + ".bias", S_F32, raw_b, Nrows);
+    g.raw_w = raw_w;
+    g.raw_b = raw_b;
     if (!dry) e->ln_folds.push_back(LnFold{raw_w, raw_b, ln.g, ln.b, g.w, g.ln_s, g.bias, Nrows, K, K, n_off, geglu_bn});
   }
   GemmW conv3(const std::string& pfx, int Cout, int Cin, int extraK = 0, int as_f16 = 0) {
@@ -386,6 +412,40 @@ struct Builder {
       t.a2_out = linear(tp + "attn2.to_out.0", inner, inner, true);
       linear_ln(t.ff_proj, tp + "ff.net.0.proj", inner * 8, inner, true, t.ln3, 0, 0, gemm_geglu_block(inner * 8));
       t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
+      if (e->cfg.variant == WD_VARIANT_UNET && inner == TB_C && heads == TB_HEADS && dh == TB_DH && ctx_dim == TB_C && C == TB_C) {
+        // operands of the fused transformer-block kernel (tblock.cuh)
+        for (int a = 0; a < 2; ++a) {
+          const std::string ap = tp + (a ? "attn2" : "attn1");
+          t.raw_k[a] = raw_copy(ap + ".to_k.weight", static_cast<int64_t>(inner) * ctx_dim);
+          t.raw_v[a] = raw_copy(ap + ".to_v.weight", static_cast<int64_t>(inner) * ctx_dim);
+          t.raw_o[a] = raw_copy(ap + ".to_out.0.weight", static_cast<int64_t>(inner) * inner);
+        }
+        const size_t fold_elems = static_cast<size_t>(2) * TB_FOLD_N * TB_C;
+        if (dry) {
+          e->fold_count += 2;
+          t.w_fold = A.alloc<bf16>(fold_elems);
+          t.u_fold = A.alloc<float>(2 * TB_HEADS * TB_C);
+        } else {
+          if (!e->fold_pool) {
+            e->fold_pool = A.alloc<bf16>(static_cast<size_t>(e->fold_count) * TB_FOLD_N * TB_C);
+            e->u_pool = A.alloc<float>(static_cast<size_t>(e->fold_count) * TB_HEADS * TB_C);
+          }
+          t.fold_idx = e->fold_next;
+          t.w_fold = e->fold_pool + static_cast<size_t>(e->fold_next) * TB_FOLD_N * TB_C;
+          t.u_fold = e->u_pool + static_cast<size_t>(e->fold_next) * TB_HEADS * TB_C;
+          e->fold_next += 2;
+        }
+        // second fold of ff.net.0.proj from the same fp32 tensors, value / gate rows interleaved per 64-column chunk
+        t.ff128.N = inner * 8;
+        t.ff128.K = inner;
+        t.ff128.w = A.alloc<bf16>(static_cast<size_t>(t.ff128.N) * inner);
+        t.ff128.bias = A.alloc<float>(t.ff128.N);
+        t.ff128.ln_s = A.alloc<float>(t.ff128.N);
+        if (!dry)
+          e->ln_folds.push_back(LnFold{t.ff_proj.raw_w, t.ff_proj.raw_b, t.ln3.g, t.ln3.b, t.ff128.w, t.ff128.ln_s, t.ff128.bias,
+                                       inner * 8, inner, inner, 0, 2 * TB_CHUNK});
+        t.cb = A.alloc<float>(4 * TB_C);
+      }
       s.blocks.push_back(t);
     }
     s.proj_out = linear(pfx + "proj_out", C, inner, true, 0, 1);  // A operand = x3, a residual-stream (fp16) tensor
@@ -424,6 +484,11 @@ struct Builder {
     e->time_dim = ted;
     e->res.clear();
     e->ln_folds.clear();
+    if (dry) e->fold_count = 0;
+    e->fold_next = 0;
+    e->fold_pool = nullptr;
+    e->u_pool = nullptr;
+    e->raw_extra.clear();
     e->st.clear();
     e->samp.clear();
     e->input_blocks.clear();
@@ -685,6 +750,9 @@ extern "C" int wd_engine_load_param(wd_engine* e, const char* name, const float*
       break;
   }
   sl.loaded = true;
+  auto extra = e->raw_extra.equal_range(name);
+  for (auto x = extra.first; x != extra.second; ++x)
+    CUDA_TRY(cudaMemcpyAsync(x->second, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return WD_OK;
 }
 
@@ -748,6 +816,20 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
   }
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
+  for (auto& st : e->st)
+    for (auto& t : st.blocks) {
+      if (!t.w_fold) continue;
+      // fused transformer block: W_fold / u of both cross-attentions (norm2 feeds both, unet.py:337-341), cumulative biases
+      const GemmW* q[2] = {&t.a1_q, &t.a2_q};
+      for (int a = 0; a < 2; ++a)
+        CUDA_TRY(tblock_fold_weights_launch(q[a]->raw_w, t.raw_k[a], t.raw_v[a], t.raw_o[a], t.ln2.g, t.ln2.b,
+                                            t.w_fold + static_cast<size_t>(a) * TB_FOLD_N * TB_C, t.u_fold + a * TB_HEADS * TB_C, s));
+      const float* add[4] = {st.proj_in.bias, t.a1_out.bias, t.a2_out.bias, t.ff_out.bias};
+      for (int i = 0; i < 4; ++i) {
+        if (i > 0) CUDA_TRY(repack_vec_launch(t.cb + (i - 1) * TB_C, t.cb + i * TB_C, TB_C, 0, 0, 0, s));
+        CUDA_TRY(repack_vec_launch(add[i], t.cb + i * TB_C, TB_C, 0, 0, i > 0 ? 1 : 0, s));
+      }
+    }
   for (auto& r : e->res) {
     CUDA_TRY(repack_vec_launch(r.b_main, r.conv2.bias, r.Cout, 0, 0, 0, s));
     if (r.skip_conv) CUDA_TRY(repack_vec_launch(r.b_skip, r.conv2.bias, r.Cout, 0, 0, 1, s));
@@ -801,6 +883,12 @@ struct PlanBuilder {
   int B;
   std::string err;
   int kv_ld = 0;  // row stride of the K/V buffers when all of them come from one pooled GEMM (0: each buffer is [.., 2C])
+  // fused transformer block: output of the pooled fold GEMM, fp16 [B * Ltot, fold_ld] (per attention: 1280 "M" ++ 1280 "N" columns),
+  // and the per-row score constants fp32 [B * Ltot, cvec_ld]
+  bf16* fold_out = nullptr;
+  int fold_ld = 0;
+  float* cvec_all = nullptr;
+  int cvec_ld = 0;
 
   Act new_act(int H, int W, int C, bool f16 = false) {
     Act a{A.alloc<bf16>(static_cast<size_t>(B) * H * W * C), C, H, W, nullptr, 0, f16};
@@ -1071,12 +1159,63 @@ struct PlanBuilder {
     ep.rows_per_sample = HW;
   }
 
+  // ---- the whole transformer block as ONE kernel (tblock.cu): unet.UNetModel, 128-token tiles inside one sample ----
+  bool st_block_fused(std::vector<Op>& ops, const STL& s, const TBlockL& t, const Act& x_in, const Act& g, Act& out) {
+    const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = TB_C;
+    const int Ltot = plan->Ltot;
+    out = new_act(H, W, C, true);
+    Op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = OP_TBLOCK;
+    TBlockArgs& a = op.tb.args;
+    a.M = M;
+    a.HW = HW;
+    a.L = Ltot;
+    a.cb = t.cb;
+    a.b_ff = t.ff128.bias;
+    a.cvec1 = cvec_all + static_cast<size_t>(t.fold_idx) * TB_HEADS;
+    a.cvec2 = cvec_all + static_cast<size_t>(t.fold_idx + 1) * TB_HEADS;
+    a.cvec_ld = cvec_ld;
+    a.b_po = s.proj_out.bias;
+    a.x_in = reinterpret_cast<const __half*>(x_in.p);
+    a.x_in_ld = x_in.C;
+    a.ln_eps = 1e-5f;  // nn.LayerNorm default (unet.py:314-316)
+    a.stage = 0;
+    if (epilogue_stats_ok(HW, C)) {
+      a.gn_partial = out.stats;
+      out.pslots = HW / 32;
+    }
+    // algorithmic work = the reference's ops (unet.py:337-345, 381-412): proj_in, 2 x (to_q, QK^T, PV, to_out), GEGLU ff, proj_out
+    const double lin = 2.0 * M * C * C;
+    op.flops = lin + 2.0 * (2.0 * lin + 4.0 * M * C * Ltot) + 2.0 * M * C * (8.0 * C) + 2.0 * M * (4.0 * C) * C + lin;
+    op.bytes = 2.0 * M * C * 3 + 2.0 * (3.0 * C * C + 12.0 * C * C) + 2.0 * 4 * (static_cast<double>(M) / HW) * Ltot * TB_HEADS * C;
+    if (!dry) {
+      bool ok = tmap_encode_2d_bf16(&op.tb.mapG, g.p, C, M, g.C, 64, TB_M) &&
+                tmap_encode_2d_bf16(&op.tb.mapWpi, s.proj_in.w, C, C, C, 64, 160) &&
+                tmap_encode_2d_bf16(&op.tb.mapW1, t.ff128.w, C, 8 * C, C, 64, 2 * TB_CHUNK) &&
+                tmap_encode_2d_bf16(&op.tb.mapW2, t.ff_out.w, 4 * C, C, 4 * C, 64, 160) &&
+                tmap_encode_2d_bf16(&op.tb.mapWpo, s.proj_out.w, C, C, C, 64, 160) &&
+                tmap_encode_2d_bf16(&op.tb.mapOut, out.p, C, M, C, 64, TB_M);
+      for (int i = 0; i < 4 && ok; ++i) {
+        const bf16* base = fold_out + static_cast<size_t>(t.fold_idx + i / 2) * TB_FOLD_N + (i & 1) * (TB_HEADS * TB_C);
+        ok = tmap_encode_3d_bf16(&op.tb.mapF[i], base, TB_HEADS * TB_C, Ltot, B, fold_ld, static_cast<uint64_t>(Ltot) * fold_ld, 64,
+                                 TB_KEYS);
+      }
+      if (!ok) { err = "cuTensorMapEncodeTiled failed (fused transformer block)"; return false; }
+    }
+    ops.push_back(op);
+    if (!out.pslots && !ensure_stats(ops, out)) return false;
+    return true;
+  }
+
   // ---- SpatialTransformer (unet.py:381-412, 337-345 ; unetPhosc.py:282-300, 241-246) ----
   bool st_block(std::vector<Op>& ops, const STL& s, const Act& x_in, const std::vector<bf16*>& kv, Act& out) {
     const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = s.heads * s.dh;
     const int Ltot = plan->Ltot;
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
+    if (fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && HW % TB_M == 0 && x_in.f16 && x_in.C == TB_C && s.C == TB_C)
+      return st_block_fused(ops, s, s.blocks[0], x_in, g, out);
     if (C % 80) { err = "spatial transformer: inner channels must be a multiple of 80 (LayerNorm folding)"; return false; }
     // LayerNorm is folded into the GEMMs around it: the producer of each token tensor writes per-row {sum, sum of squares}
     // (4 column blocks of 80), the consumer GEMM reads the raw fp16 tensor with gamma-scaled weights and normalises in its epilogue
@@ -1282,6 +1421,30 @@ struct PlanBuilder {
         ep.out_ld = w.N;
         if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, w, ep)) return false;
       }
+    }
+
+    // fused transformer blocks: every per-sample attention operand (M = Wq^T K^T and N = V Wout^T of each cross-attention) from
+    // ONE GEMM ctx [B L, D] x W_fold^T, plus the score constants; unet.UNetModel with a context of at most 16 tokens
+    fold_out = nullptr;
+    if (tblock_enabled() && e->fold_pool && e->fold_count > 0 && Ltot <= TB_KEYS && D == TB_C) {
+      GemmW wall;
+      wall.w = e->fold_pool;
+      wall.N = e->fold_count * TB_FOLD_N;
+      wall.K = TB_C;
+      fold_ld = wall.N;
+      fold_out = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * wall.N);
+      Epi ep;
+      ep.out = fold_out;
+      ep.out_ld = wall.N;
+      ep.out_f16 = 1;
+      if (!gemm_op(cops, B * Ltot, false, 0, 0, {ASrc{ctx, D, D, 1, 1, 1, 1}}, wall, ep)) return false;
+      cvec_ld = e->fold_count * TB_HEADS;
+      cvec_all = A.alloc<float>(static_cast<size_t>(B) * Ltot * cvec_ld);
+      Op cv;
+      memset(&cv, 0, sizeof(cv));
+      cv.kind = OP_TB_CVEC;
+      cv.cv = {ctx, e->u_pool, cvec_all, B * Ltot, cvec_ld};
+      cops.push_back(cv);
     }
 
     // ================= per-step =================
@@ -1518,6 +1681,17 @@ static bool temb_table_enabled() {  // env WD_TEMB_TABLE (default on)
   return v != 0;
 }
 
+static int engine_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStream_t s) {
   int n = 0, kernels = 0;
   std::vector<cudaEvent_t>* ev = nullptr;
@@ -1605,6 +1779,12 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
           err = embed_tokens_launch(rc.phosc, 0, op.emb.E, op.emb.vocab, op.emb.pe, op.emb.add_pe, op.emb.out, op.emb.B,
                                     op.emb.L, op.emb.D, s);
         }
+        break;
+      case OP_TBLOCK:
+        err = tblock_launch(op.tb, engine_num_sms(), s);
+        break;
+      case OP_TB_CVEC:
+        err = tblock_cvec_launch(op.cv.ctx, op.cv.u, op.cv.out, op.cv.rows, op.cv.heads, s);
         break;
       case OP_LINF32:
         err = linear_f32_launch(op.lin.x, op.lin.W, op.lin.b, op.lin.out, op.lin.M, op.lin.N, op.lin.K, s);
@@ -1794,7 +1974,8 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
   for (int i = 0; i < n; ++i) {
     // the table lookup reports as the timestep-embedding class; ops of the flavour the profiled steps skipped carry no work
     const bool skipped = (ops[i].cond == COND_TABLE && !e->prof_used_table) || (ops[i].cond == COND_NO_TABLE && e->prof_used_table);
-    kinds[i] = ops[i].kind == OP_EMBTBL ? static_cast<int>(OP_TEMB) : static_cast<int>(ops[i].kind);
+    // indices into engine.py's OP_KINDS: 0 .. 8 = OP_TEMB .. OP_UPSAMPLE, 9 = the fused transformer block
+    kinds[i] = ops[i].kind == OP_EMBTBL ? static_cast<int>(OP_TEMB) : (ops[i].kind == OP_TBLOCK ? 9 : static_cast<int>(ops[i].kind));
     flops[i] = skipped ? 0.0 : ops[i].flops;
     bytes[i] = skipped ? 0.0 : ops[i].bytes;
     ms_sum[i] = 0.f;
@@ -2033,4 +2214,80 @@ extern "C" int wd_op_attention(const void* q, int ldq, const void* k, const void
                   static_cast<bf16*>(out), ldo, Sq, Skv, heads, scale};
   CUDA_TRY(attn_flash_launch(a, B, static_cast<cudaStream_t>(stream)));
   return WD_OK;
+}
+
+// Fused transformer block as a single operator (tests/test_gpu_tblock.py).  tensors[] (device pointers, fp32 unless noted):
+//  0 g bf16 [M,320]   1 x_in fp16 [M,320]   2 ctx bf16 [B*L,320]
+//  3 proj_in.w [320,320]  4 proj_in.b  5 norm2.w  6 norm2.b  7 norm3.w  8 norm3.b
+//  9 attn1.to_q.w  10 attn1.to_k.w  11 attn1.to_v.w  12 attn1.to_out.0.w  13 attn1.to_out.0.b
+// 14 attn2.to_q.w  15 attn2.to_k.w  16 attn2.to_v.w  17 attn2.to_out.0.w  18 attn2.to_out.0.b
+// 19 ff.net.0.proj.w [2560,320]  20 ff.net.0.proj.b [2560]  21 ff.net.2.w [320,1280]  22 ff.net.2.b  23 proj_out.w  24 proj_out.b
+// stage: TBlockArgs::stage.  out: fp16 [M,320]; gn_partial: fp32 [B][32][HW/32][2] or NULL.  Synchronises the stream.
+extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int B, int HW, int L, int stage, void* out_f16,
+                                 float* gn_partial, void* stream) {
+  if (!tensors || n_tensors != 25 || !out_f16) return fail(WD_ERR_INVALID, "op_tblock_unet: expects 25 tensors");
+  for (int i = 0; i < 25; ++i)
+    if (!tensors[i]) return fail(WD_ERR_INVALID, "op_tblock_unet: tensor %d is null", i);
+  if (B < 1 || HW % TB_M || L < 1 || L > TB_KEYS || stage < 0 || stage > 4) return fail(WD_ERR_INVALID, "op_tblock_unet: bad shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto F = [&](int i) { return static_cast<const float*>(tensors[i]); };
+  const int C = TB_C, M = B * HW;
+  char* ws = nullptr;
+  Arena A;
+  const size_t need = 64ull << 20;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ws), need + static_cast<size_t>(B) * L * (2 * TB_FOLD_N * 2 + 64)));
+  A.base = ws;
+  int rc = WD_OK;
+  do {
+    bf16* w_pi = A.alloc<bf16>(C * C);
+    bf16* w_po = A.alloc<bf16>(C * C);
+    bf16* w_ff2 = A.alloc<bf16>(C * 4 * C);
+    bf16* w_ff1 = A.alloc<bf16>(8 * C * C);
+    float* b_ff1 = A.alloc<float>(8 * C);
+    float* s_ff1 = A.alloc<float>(8 * C);
+    bf16* w_fold = A.alloc<bf16>(static_cast<size_t>(2) * TB_FOLD_N * C);
+    float* u = A.alloc<float>(2 * TB_HEADS * C);
+    float* cb = A.alloc<float>(4 * C);
+    bf16* fold_out = A.alloc<bf16>(static_cast<size_t>(B) * L * 2 * TB_FOLD_N);
+    float* cvec = A.alloc<float>(static_cast<size_t>(B) * L * 2 * TB_HEADS);
+#define TB_TRY(x) if ((x) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "op_tblock_unet: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    TB_TRY(repack_linear_launch(F(3), w_pi, C, C, C, 0, 0, 0, 0, s));
+    TB_TRY(repack_linear_launch(F(23), w_po, C, C, C, 0, 0, 0, 1, s));
+    TB_TRY(repack_linear_launch(F(21), w_ff2, C, 4 * C, 4 * C, 0, 0, 0, 0, s));
+    TB_TRY(fold_ln_linear_launch(F(19), F(7), F(8), F(20), w_ff1, s_ff1, b_ff1, 8 * C, C, C, 0, 2 * TB_CHUNK, s));
+    for (int a = 0; a < 2; ++a)
+      TB_TRY(tblock_fold_weights_launch(F(9 + 5 * a), F(10 + 5 * a), F(11 + 5 * a), F(12 + 5 * a), F(5), F(6),
+                                        w_fold + static_cast<size_t>(a) * TB_FOLD_N * C, u + a * TB_HEADS * C, s));
+    if (rc != WD_OK) break;
+    const float* add[4] = {F(4), F(13), F(18), F(22)};
+    for (int i = 0; i < 4; ++i) {
+      if (i > 0) TB_TRY(repack_vec_launch(cb + (i - 1) * C, cb + i * C, C, 0, 0, 0, s));
+      TB_TRY(repack_vec_launch(add[i], cb + i * C, C, 0, 0, i > 0 ? 1 : 0, s));
+    }
+    if (rc != WD_OK) break;
+    rc = op_gemm_impl(tensors[2], w_fold, nullptr, nullptr, fold_out, B * L, 2 * TB_FOLD_N, C, 0, 0, 0, 0, 1, s);
+    if (rc != WD_OK) break;
+    TB_TRY(tblock_cvec_launch(static_cast<const bf16*>(tensors[2]), u, cvec, B * L, 2 * TB_HEADS, s));
+    TBlockLaunch T;
+    memset(&T, 0, sizeof(T));
+    TBlockArgs& a = T.args;
+    a.M = M; a.HW = HW; a.L = L; a.cb = cb; a.b_ff = b_ff1; a.cvec1 = cvec; a.cvec2 = cvec + TB_HEADS; a.cvec_ld = 2 * TB_HEADS;
+    a.b_po = F(24); a.x_in = static_cast<const __half*>(tensors[1]); a.x_in_ld = C; a.gn_partial = gn_partial; a.ln_eps = 1e-5f;
+    a.stage = stage;
+    const int fold_ld = 2 * TB_FOLD_N;
+    bool ok = tmap_encode_2d_bf16(&T.mapG, tensors[0], C, M, C, 64, TB_M) && tmap_encode_2d_bf16(&T.mapWpi, w_pi, C, C, C, 64, 160) &&
+              tmap_encode_2d_bf16(&T.mapW1, w_ff1, C, 8 * C, C, 64, 2 * TB_CHUNK) &&
+              tmap_encode_2d_bf16(&T.mapW2, w_ff2, 4 * C, C, 4 * C, 64, 160) && tmap_encode_2d_bf16(&T.mapWpo, w_po, C, C, C, 64, 160) &&
+              tmap_encode_2d_bf16(&T.mapOut, out_f16, C, M, C, 64, TB_M);
+    for (int i = 0; i < 4 && ok; ++i)
+      ok = tmap_encode_3d_bf16(&T.mapF[i], fold_out + static_cast<size_t>(i / 2) * TB_FOLD_N + (i & 1) * (TB_HEADS * C), TB_HEADS * C, L, B,
+                               fold_ld, static_cast<uint64_t>(L) * fold_ld, 64, TB_KEYS);
+    if (!ok) { rc = fail(WD_ERR_CUDA, "op_tblock_unet: cuTensorMapEncodeTiled failed"); break; }
+    TB_TRY(tblock_launch(T, engine_num_sms(), s));
+#undef TB_TRY
+  } while (0);
+  const cudaError_t se = cudaStreamSynchronize(s);
+  cudaFree(ws);
+  if (rc == WD_OK && se != cudaSuccess) rc = fail(WD_ERR_CUDA, "op_tblock_unet: %s", cudaGetErrorString(se));
+  return rc;
 }

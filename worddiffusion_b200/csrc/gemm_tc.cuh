@@ -144,6 +144,9 @@ bool tmap_encode_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint6
 bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                          uint64_t pix_stride_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n,
                          uint32_t stride_wh);
+// 3-D (inner, rows, batch) map with a {box_inner, box_rows, 1} SWIZZLE_128B box (attention operands, per-sample fold operands)
+bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride_elems,
+                         uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows);
 // output / residual tensor map of the staging sub-tiles
 bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems);
 cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);
