@@ -283,6 +283,12 @@ WD_DEVINL uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
 WD_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
+// same arrival with CTA-scope release (what CUTLASS' ClusterBarrier::arrive(cta_id) emits): no MEMBAR.ALL.GPU / ERRBAR in front of it.
+// Enough when what the waiter consumes after the arrival does not travel through the global-memory hierarchy: shared memory
+// written here and published with fence.proxy.async, or TMEM reads completed with tcgen05.wait::ld + tcgen05.fence.
+WD_DEVINL void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
 WD_DEVINL bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -1181,6 +1181,8 @@ struct PlanBuilder {
     a.x_in_ld = x_in.C;
     a.ln_eps = 1e-5f;  // nn.LayerNorm default (unet.py:314-316)
     a.stage = 0;
+    a.pair = tblock_use_pair(HW) ? 1 : 0;
+    const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
     if (epilogue_stats_ok(HW, C)) {
       a.gn_partial = out.stats;
       out.pslots = HW / 32;
@@ -1191,10 +1193,10 @@ struct PlanBuilder {
     op.bytes = 2.0 * M * C * 3 + 2.0 * (3.0 * C * C + 12.0 * C * C) + 2.0 * 4 * (static_cast<double>(M) / HW) * Ltot * TB_HEADS * C;
     if (!dry) {
       bool ok = tmap_encode_2d_bf16(&op.tb.mapG, g.p, C, M, g.C, 64, TB_M) &&
-                tmap_encode_2d_bf16(&op.tb.mapWpi, s.proj_in.w, C, C, C, 64, 160) &&
-                tmap_encode_2d_bf16(&op.tb.mapW1, t.ff128.w, C, 8 * C, C, 64, 2 * TB_CHUNK) &&
-                tmap_encode_2d_bf16(&op.tb.mapW2, t.ff_out.w, 4 * C, C, 4 * C, 64, 160) &&
-                tmap_encode_2d_bf16(&op.tb.mapWpo, s.proj_out.w, C, C, C, 64, 160) &&
+                tmap_encode_2d_bf16(&op.tb.mapWpi, s.proj_in.w, C, C, C, 64, wbox) &&
+                tmap_encode_2d_bf16(&op.tb.mapW1, t.ff128.w, C, 8 * C, C, 64, w1box) &&
+                tmap_encode_2d_bf16(&op.tb.mapW2, t.ff_out.w, 4 * C, C, 4 * C, 64, wbox) &&
+                tmap_encode_2d_bf16(&op.tb.mapWpo, s.proj_out.w, C, C, C, 64, wbox) &&
                 tmap_encode_2d_bf16(&op.tb.mapOut, out.p, C, M, C, 64, TB_M);
       for (int i = 0; i < 4 && ok; ++i) {
         const bf16* base = fold_out + static_cast<size_t>(t.fold_idx + i / 2) * TB_FOLD_N + (i & 1) * (TB_HEADS * TB_C);
@@ -2274,10 +2276,12 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     a.M = M; a.HW = HW; a.L = L; a.cb = cb; a.b_ff = b_ff1; a.cvec1 = cvec; a.cvec2 = cvec + TB_HEADS; a.cvec_ld = 2 * TB_HEADS;
     a.b_po = F(24); a.x_in = static_cast<const __half*>(tensors[1]); a.x_in_ld = C; a.gn_partial = gn_partial; a.ln_eps = 1e-5f;
     a.stage = stage;
+    a.pair = tblock_use_pair(HW) ? 1 : 0;
+    const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
     const int fold_ld = 2 * TB_FOLD_N;
-    bool ok = tmap_encode_2d_bf16(&T.mapG, tensors[0], C, M, C, 64, TB_M) && tmap_encode_2d_bf16(&T.mapWpi, w_pi, C, C, C, 64, 160) &&
-              tmap_encode_2d_bf16(&T.mapW1, w_ff1, C, 8 * C, C, 64, 2 * TB_CHUNK) &&
-              tmap_encode_2d_bf16(&T.mapW2, w_ff2, 4 * C, C, 4 * C, 64, 160) && tmap_encode_2d_bf16(&T.mapWpo, w_po, C, C, C, 64, 160) &&
+    bool ok = tmap_encode_2d_bf16(&T.mapG, tensors[0], C, M, C, 64, TB_M) && tmap_encode_2d_bf16(&T.mapWpi, w_pi, C, C, C, 64, wbox) &&
+              tmap_encode_2d_bf16(&T.mapW1, w_ff1, C, 8 * C, C, 64, w1box) &&
+              tmap_encode_2d_bf16(&T.mapW2, w_ff2, 4 * C, C, 4 * C, 64, wbox) && tmap_encode_2d_bf16(&T.mapWpo, w_po, C, C, C, 64, wbox) &&
               tmap_encode_2d_bf16(&T.mapOut, out_f16, C, M, C, 64, TB_M);
     for (int i = 0; i < 4 && ok; ++i)
       ok = tmap_encode_3d_bf16(&T.mapF[i], fold_out + static_cast<size_t>(i / 2) * TB_FOLD_N + (i & 1) * (TB_HEADS * C), TB_HEADS * C, L, B,

@@ -167,7 +167,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t phase = 0;
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
-        mbar_wait_cluster(tmem_empty_bar, (it & 1) ^ 1);  // both CTAs' epilogues have drained the accumulator
+        // both CTAs' epilogues have drained the accumulator.  CTA-scope acquire / release on both sides (mbar_arrive_remote): the
+        // cluster-scope forms put a MEMBAR.ALL.GPU in front of every epilogue warp's arrival (-2 % on the GEMM class, R2f)
+        mbar_wait(tmem_empty_bar, (it & 1) ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < total_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // CTA-scope acquire: a cluster-scope one costs a CCTL.IVALL (L1 flush) per K block
@@ -261,7 +263,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       if (args.dbg & 2) {  // experiment: no epilogue at all
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(te_addr);
+        if (lane == 0) mbar_arrive_remote(te_addr);
         continue;
       }
       uint8_t* const srow = stg_half + row * (GEMM_SUB_N * 2);
@@ -286,7 +288,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (rnd == 1) {  // accumulator fully read by this warp: hand TMEM back to the leader's MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(te_addr);
+          if (lane == 0) mbar_arrive_remote(te_addr);
         }
 
         // ---- the staging buffer of this half must be free: its previous TMA store has read it / the residual has landed ----

@@ -203,10 +203,12 @@ constexpr int GNB_P = 32;      // pixel rows per work item
 constexpr int GNB_R = 8;       // rows per pass (threads = Cs/8 * GNB_R)
 constexpr int GNB_STAGES = 4;
 
-// one 16-byte vector (8 channels): y = x * sc + sh (packed fp32 FMAs), SiLU as y / (1 + 2^(-y log2 e)) with packed adds /
-// multiplies: ~5.5 instructions per element.  (The first version spent ~20 per element -- run-time format / activation
-// switches inside the loop, scalar arithmetic -- and ncu showed the launch issue-bound at half the HBM rate: 53 % issue
-// slots, 49 % XU pipe at 3.2 TB/s.)
+// one 16-byte vector (8 channels): y = x * sc + sh (packed fp32 FMAs); SiLU as h + h tanh(h), h = y / 2, with ONE packed
+// tanh.approx.f16x2 per two elements (sc / sh arrive pre-halved when SILU): 3.5 instructions and half a MUFU operation per
+// element.  History: ~20 instructions per element (run-time format / activation switches, scalar arithmetic) ran issue-bound
+// at half the HBM rate; the ex2 + rcp form (5.5 instructions, two MUFU operations per element) kept the XU pipe 55 % busy
+// and the SiLU launches at 3.0-3.4 TB/s against 4.7 TB/s without SiLU (profiles/R2d_ncu_gn.txt).  tanh's absolute error
+// (2^-11, fp16 result) leaves |error| <= |h| 2^-11 on the output, below the bf16 rounding of the stored value for y > -4.
 template <bool SILU, bool XF16>
 WD_DEVINL uint4 gn_vec8(const uint4 v, const float2 (&sc2)[4], const float2 (&sh2)[4]) {
   const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -214,17 +216,11 @@ WD_DEVINL uint4 gn_vec8(const uint4 v, const float2 (&sc2)[4], const float2 (&sh
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = XF16 ? unpack_f16x2(u[j]) : unpack_bf16x2(u[j]);
-    float2 y = __ffma2_rn(f, sc2[j], sh2[j]);
+    float2 y = __ffma2_rn(f, sc2[j], sh2[j]);  // SILU: this is h = y / 2
     if constexpr (SILU) {
-      const float2 z = __fmul2_rn(y, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-      float2 e;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(z.x));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(z.y));
-      const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
-      float2 r;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
-      y = __fmul2_rn(y, r);
+      uint32_t h16 = pack_f16x2(y.x, y.y), t16;
+      asm("tanh.approx.f16x2 %0, %1;" : "=r"(t16) : "r"(h16));
+      y = __ffma2_rn(y, unpack_f16x2(t16), y);
     }
     o[j] = pack_bf16x2(y.x, y.y);
   }
@@ -303,6 +299,13 @@ __global__ void __launch_bounds__(512, 2) groupnorm_apply_bulk_kernel(const Grou
         const int g0i = (col * 8 + 2 * j) / cpg, g1i = (col * 8 + 2 * j + 1) / cpg;
         sc2[j] = make_float2(s_rstd[g0i] * gm[2 * j], s_rstd[g1i] * gm[2 * j + 1]);
         sh2[j] = make_float2(be[2 * j] - s_mean[g0i] * sc2[j].x, be[2 * j + 1] - s_mean[g1i] * sc2[j].y);
+      }
+      if constexpr (SILU) {  // gn_vec8 wants h = y / 2
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc2[j] = make_float2(0.5f * sc2[j].x, 0.5f * sc2[j].y);
+          sh2[j] = make_float2(0.5f * sh2[j].x, 0.5f * sh2[j].y);
+        }
       }
     }
     const int stage = k % GNB_STAGES;

@@ -9,6 +9,14 @@
 //               (the gamma / beta of the norms are folded into the weights that follow), softmax probabilities, GEGLU products.
 // TMEM (512 columns): [0, 320) residual stream X (fp32, accumulated in place by every residual branch), [320, 448) GEGLU
 // projection chunk, [448, 512) attention scores.
+//
+// CTA-pair build (PAIR, cta_group::2; used when a sample holds a multiple of 256 tokens).  ncu of the single-CTA build
+// (profiles/R2d_ncu_tblock.txt): tensor pipe 33 %, the MMA thread mostly waiting for weight units -- the feed-forward phase needs
+// 120 KB of weights per 1920 MMA clocks (62 B/clk) and one SM ingests less than that with 100 KB of loads in flight.  Two CTAs of
+// a cluster therefore share every weight unit: a tile is 256 tokens (128 rows per CTA: own operand copies, own TMEM lanes, own
+// epilogue warps), each CTA loads HALF of every weight unit (the N / 2 rows that tcgen05.mma.cta_group::2 reads from its shared
+// memory), the leader CTA issues all MMAs, commits are multicast to both CTAs and the epilogue -> MMA barriers live in the leader
+// (16 warp arrivals).  Weight bytes per token halve.
 #include "tblock.cuh"
 #include "epilogue.cuh"
 
@@ -16,27 +24,35 @@
 #include <mutex>
 
 namespace wd {
+// phase timeline (clock64) of CTA 0 under TBlockArgs::trace: [role 0 = MMA thread, 1 = epilogue warp 2 lane 0][tile < 8][stamp < 64]
+__device__ unsigned long long g_tb_trace[2 * 8 * 64];
 namespace {
+
+#define TB_STAMP(role, it_, idx)                                                                      \
+  do {                                                                                                \
+    if (args.trace && blockIdx.x == 0 && (it_) < 8) g_tb_trace[((role) * 8 + (it_)) * 64 + (idx)] = clock64(); \
+  } while (0)
 
 constexpr int TB_THREADS = 320;
 constexpr int TB_KB = TB_C / 64;                 // K blocks of a 320-wide operand
 constexpr int TB_ABLK = TB_M * 128;              // one [128 rows x 64 cols] 16-bit K-major block: 16 KB
-constexpr int TB_SLOT = 20480;                   // ring slot: [160 rows x 64] = 20 KB (W1 boxes use 16 KB, attention units 8 KB)
-constexpr int TB_NSLOT = 5;
+constexpr int TB_RING = 102400;                  // operand ring: five 20 KB slots ([160 rows x 64]; W1 boxes use 16 KB, attention units
+                                                 // 8 KB), or ten 10 KB slots in the CTA-pair build (every unit is half as large per CTA)
+constexpr int TB_MAXSLOT = 10;
 constexpr int TB_NCHUNK = TB_HID / TB_CHUNK;     // 20 feed-forward chunks
 constexpr int OFF_A = 0;
 constexpr int OFF_G = OFF_A + TB_KB * TB_ABLK;           // 81920: two [128 x 64] buffers (P of the attentions / GEGLU chunks)
 constexpr int OFF_RING = OFF_G + 2 * TB_ABLK;            // 114688
-constexpr int OFF_BFF = OFF_RING + TB_NSLOT * TB_SLOT;   // 217088
+constexpr int OFF_BFF = OFF_RING + TB_RING;              // 217088
 constexpr int OFF_CSM = OFF_BFF + 2 * TB_HID * 4;        // 227328
 constexpr int OFF_STAT = OFF_CSM + 2 * 64 * 4;           // 227840
 constexpr int OFF_BARS = OFF_STAT + 2 * TB_M * 8;        // 229888
-constexpr int TB_SMEM = OFF_BARS + 256;                  // 230144
+constexpr int TB_SMEM = OFF_BARS + 320;                  // 230208
 static_assert(TB_SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t COL_X = 0, COL_G = 320, COL_S = 448;
 
-enum Bar : int { B_RING_FULL = 0, B_RING_EMPTY = 5, B_A_FULL = 10, B_A_FREE = 11, B_ACC = 12, B_S = 13, B_A_READY = 14, B_P_READY = 15,
-                 B_GACC_FULL = 16, B_GACC_FREE = 17, B_GBUF_FULL = 18, B_GBUF_EMPTY = 20, B_X_FREE = 22, B_COUNT = 23 };
+enum Bar : int { B_RING_FULL = 0, B_RING_EMPTY = 10, B_A_FULL = 20, B_A_FREE = 21, B_ACC = 22, B_S = 23, B_A_READY = 24, B_P_READY = 25,
+                 B_GACC_FULL = 26, B_GACC_FREE = 27, B_GBUF_FULL = 28, B_GBUF_EMPTY = 30, B_X_FREE = 32, B_COUNT = 33 };
 
 WD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -69,12 +85,22 @@ WD_DEVINL float ex2_fast(float x) {
 // phases after which a debug launch stops (TBlockArgs::stage)
 WD_DEVINL bool stop_after(int stage, int phase) { return stage != 0 && stage == phase; }
 
-__global__ void __launch_bounds__(TB_THREADS, 1)
-tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapWpi,
-                   const __grid_constant__ CUtensorMap mapF0, const __grid_constant__ CUtensorMap mapF1,
-                   const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
-                   const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
-                   const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
+WD_DEVINL void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <bool PAIR>
+WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, const CUtensorMap& mapF0, const CUtensorMap& mapF1,
+                           const CUtensorMap& mapF2, const CUtensorMap& mapF3, const CUtensorMap& mapW1, const CUtensorMap& mapW2,
+                           const CUtensorMap& mapWpo, const CUtensorMap& mapOut, const TBlockArgs& args) {
+  constexpr int TB_NSLOT = PAIR ? 10 : 5;
+  constexpr int TB_SLOT = TB_RING / TB_NSLOT;
+  constexpr int TILE_M = PAIR ? 2 * TB_M : TB_M;   // tokens per tile (both CTAs of a pair)
+  constexpr uint32_t N_EPI = PAIR ? 16 : 8;        // epilogue-warp arrivals on an epilogue -> MMA barrier
   extern __shared__ __align__(1024) uint8_t tb_smem[];
   uint8_t* const smem = tb_smem;
   if (smem_u32(smem) & 1023) __trap();
@@ -88,8 +114,13 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = args.M / TB_M;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
+  const int m_tiles = args.M / TILE_M;
   const int stage = args.stage;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nworkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // a barrier the peer CTA signals too lives in the leader: its shared::cluster address (the local one in the single-CTA build)
+  auto leader_bar = [&](int b) -> uint32_t { return PAIR ? mapa_shared(smem_u32(&bars[b]), 0) : smem_u32(&bars[b]); };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapG);
@@ -110,23 +141,27 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
     mbar_init(&bars[B_A_FREE], 1);
     mbar_init(&bars[B_ACC], 1);
     mbar_init(&bars[B_S], 1);
-    mbar_init(&bars[B_A_READY], 8);
-    mbar_init(&bars[B_P_READY], 8);
+    mbar_init(&bars[B_A_READY], N_EPI);
+    mbar_init(&bars[B_P_READY], N_EPI);
     mbar_init(&bars[B_GACC_FULL], 1);
-    mbar_init(&bars[B_GACC_FREE], 8);
+    mbar_init(&bars[B_GACC_FREE], N_EPI);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[B_GBUF_FULL + i], 8);
+      mbar_init(&bars[B_GBUF_FULL + i], N_EPI);
       mbar_init(&bars[B_GBUF_EMPTY + i], 1);
     }
-    mbar_init(&bars[B_X_FREE], 8);
+    mbar_init(&bars[B_X_FREE], N_EPI);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   // static data: the folded GEGLU bias (weights only) -> shared memory
   for (int i = threadIdx.x; i < 2 * TB_HID / 4; i += TB_THREADS)
     reinterpret_cast<float4*>(sBff)[i] = __ldg(reinterpret_cast<const float4*>(args.b_ff) + i);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
@@ -137,60 +172,96 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
     if (elect_one()) {
       int slot = 0;
       uint32_t phase = 0;
+      // `bytes` = what BOTH CTAs of a pair load into this slot (the leader's full barrier counts them all)
       auto acquire = [&](uint32_t bytes) -> uint8_t* {
         mbar_wait(&bars[B_RING_EMPTY + slot], phase ^ 1);
-        mbar_arrive_expect_tx(&bars[B_RING_FULL + slot], bytes);
+        if (rank == 0) mbar_arrive_expect_tx(&bars[B_RING_FULL + slot], bytes);
         return sRing + slot * TB_SLOT;
       };
       auto advance = [&]() {
         if (++slot == TB_NSLOT) { slot = 0; phase ^= 1; }
       };
-      auto weight_320_half = [&](const CUtensorMap* mp, int nh) {  // one N half of a [320 x 320] weight: 5 K blocks of [160 x 64]
+      auto load2 = [&](void* dst, const CUtensorMap* mp, int bar, int c0, int c1) {
+        if (PAIR) tma_load_2d_pair(dst, mp, leader_bar(bar), c0, c1);
+        else tma_load_2d(dst, mp, &bars[bar], c0, c1);
+      };
+      auto load3 = [&](void* dst, const CUtensorMap* mp, int bar, int c0, int c1, int c2) {
+        if (PAIR) tma_load_3d_pair(dst, mp, leader_bar(bar), c0, c1, c2);
+        else tma_load_3d(dst, mp, &bars[bar], c0, c1, c2);
+      };
+      // one N half of a [320 x 320] weight: 5 K blocks of [160 x 64] (pair: this CTA's 80 of the 160 rows)
+      auto weight_320_half = [&](const CUtensorMap* mp, int nh) {
         for (int kb = 0; kb < TB_KB; ++kb) {
           uint8_t* dst = acquire(160 * 128);
-          tma_load_2d(dst, mp, &bars[B_RING_FULL + slot], kb * 64, nh * 160);
+          load2(dst, mp, B_RING_FULL + slot, kb * 64, nh * 160 + (PAIR ? static_cast<int>(rank) * 80 : 0));
           advance();
         }
       };
-      auto fold_units = [&](const CUtensorMap* mp, int sample) {  // five units of four [16 keys x 64] boxes (one per head)
+      // score operand of one attention: five K blocks of four [16 keys x 64] boxes, one per head (pair: this CTA's two heads)
+      auto fold_m_units = [&](const CUtensorMap* mp, int sample) {
         for (int b = 0; b < TB_KB; ++b) {
           uint8_t* dst = acquire(TB_HEADS * TB_KEYS * 128);
-          for (int h = 0; h < TB_HEADS; ++h) tma_load_3d(dst + h * (TB_KEYS * 128), mp, &bars[B_RING_FULL + slot], h * TB_C + b * 64, 0, sample);
+          if (PAIR) {
+            for (int hl = 0; hl < 2; ++hl)
+              load3(dst + hl * (TB_KEYS * 128), mp, B_RING_FULL + slot, (static_cast<int>(rank) * 2 + hl) * TB_C + b * 64, 0, sample);
+          } else {
+            for (int h = 0; h < TB_HEADS; ++h) load3(dst + h * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample);
+          }
           advance();
         }
       };
-      auto w1_units = [&](int c) {
+      // output operand of one attention (MN-major: rows = (head, key), 64 output columns per row).  Single CTA: five 64-column
+      // units.  Pair: three N = 128 MMAs; this CTA supplies column block 2 nb + rank (the peer has none for the last one: its
+      // half of that MMA lands in TMEM columns [320, 384), which belong to the idle GEGLU accumulator)
+      auto fold_n_units = [&](const CUtensorMap* mp, int sample) {
+        if (PAIR) {
+          for (int nb = 0; nb < 3; ++nb) {
+            const int blk = 2 * nb + static_cast<int>(rank);
+            uint8_t* dst = acquire((nb < 2 ? 2 : 1) * TB_HEADS * TB_KEYS * 128);
+            if (blk < TB_KB)
+              for (int h = 0; h < TB_HEADS; ++h) load3(dst + h * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + blk * 64, 0, sample);
+            advance();
+          }
+        } else {
+          for (int b = 0; b < TB_KB; ++b) {
+            uint8_t* dst = acquire(TB_HEADS * TB_KEYS * 128);
+            for (int h = 0; h < TB_HEADS; ++h) load3(dst + h * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample);
+            advance();
+          }
+        }
+      };
+      auto w1_units = [&](int c) {  // pair: rank 0 holds the chunk's 64 value rows, rank 1 its 64 gate rows
         for (int kb = 0; kb < TB_KB; ++kb) {
           uint8_t* dst = acquire(2 * TB_CHUNK * 128);
-          tma_load_2d(dst, &mapW1, &bars[B_RING_FULL + slot], kb * 64, c * 2 * TB_CHUNK);
+          load2(dst, &mapW1, B_RING_FULL + slot, kb * 64, c * 2 * TB_CHUNK + (PAIR ? static_cast<int>(rank) * TB_CHUNK : 0));
           advance();
         }
       };
       auto w2_units = [&](int c) {
         for (int nh = 0; nh < 2; ++nh) {
           uint8_t* dst = acquire(160 * 128);
-          tma_load_2d(dst, &mapW2, &bars[B_RING_FULL + slot], c * TB_CHUNK, nh * 160);
+          load2(dst, &mapW2, B_RING_FULL + slot, c * TB_CHUNK, nh * 160 + (PAIR ? static_cast<int>(rank) * 80 : 0));
           advance();
         }
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-        const int m0 = tile * TB_M;
-        const int sample = m0 / args.HW;
+      for (int tile = worker; tile < m_tiles; tile += nworkers, ++it) {
+        const int m0 = tile * TILE_M + static_cast<int>(rank) * TB_M;  // this CTA's 128 rows
+        const int sample = (tile * TILE_M) / args.HW;
         // the first five weight units fill the ring while the previous tile finishes (exactly the ring's capacity: issuing more
         // before the g operand could block on a slot that only this tile's MMAs -- which wait for g -- can free)
         weight_320_half(&mapWpi, 0);
         // the A buffer is free once the previous tile's output store has read it
         mbar_wait(&bars[B_A_FREE], (it & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars[B_A_FULL], TB_KB * TB_ABLK);
-        for (int kb = 0; kb < TB_KB; ++kb) tma_load_2d(sA + kb * TB_ABLK, &mapG, &bars[B_A_FULL], kb * 64, m0);
+        if (rank == 0) mbar_arrive_expect_tx(&bars[B_A_FULL], (PAIR ? 2 : 1) * TB_KB * TB_ABLK);
+        for (int kb = 0; kb < TB_KB; ++kb) load2(sA + kb * TB_ABLK, &mapG, B_A_FULL, kb * 64, m0);
         weight_320_half(&mapWpi, 1);
         if (stop_after(stage, 1)) continue;
-        fold_units(&mapF0, sample);
-        fold_units(&mapF1, sample);
+        fold_m_units(&mapF0, sample);
+        fold_n_units(&mapF1, sample);
         if (stop_after(stage, 2)) continue;
-        fold_units(&mapF2, sample);
-        fold_units(&mapF3, sample);
+        fold_m_units(&mapF2, sample);
+        fold_n_units(&mapF3, sample);
         if (stop_after(stage, 3)) continue;
         for (int c = 0; c < TB_NCHUNK; ++c) {
           w1_units(c);
@@ -204,12 +275,24 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      constexpr uint32_t ID_BF16_160 = make_idesc_bf16_f32(TB_M, 160);
-      constexpr uint32_t ID_F16_160 = make_idesc_f16_f32(TB_M, 160);
-      constexpr uint32_t ID_F16_128 = make_idesc_f16_f32(TB_M, 128);
-      constexpr uint32_t ID_F16_64 = make_idesc_f16_f32(TB_M, 64);
-      constexpr uint32_t ID_F16_64_MN = ID_F16_64 | (1u << 16);  // B operand MN-major
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t ID_BF16_160 = make_idesc_bf16_f32(TILE_M, 160);
+      constexpr uint32_t ID_F16_160 = make_idesc_f16_f32(TILE_M, 160);
+      constexpr uint32_t ID_F16_128 = make_idesc_f16_f32(TILE_M, 128);
+      constexpr uint32_t ID_F16_64 = make_idesc_f16_f32(TILE_M, 64);
+      constexpr uint32_t ID_F16_64_MN = ID_F16_64 | (1u << 16);    // B operand MN-major
+      constexpr uint32_t ID_F16_128_MN = ID_F16_128 | (1u << 16);
+      auto mma = [&](uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+        if (PAIR) umma_f16_ss_pair(d, a_desc, b_desc, idesc, acc);
+        else umma_f16_ss(d, a_desc, b_desc, idesc, acc);
+      };
+      auto commit = [&](int b) {  // pair: arrives on the barrier at this offset in BOTH CTAs
+        if (PAIR) umma_commit_pair(&bars[b]);
+        else umma_commit(&bars[b]);
+      };
+      auto wait_epi = [&](int b, uint32_t parity) {  // a barrier the epilogue warps (of both CTAs) arrive on
+        mbar_wait(&bars[b], parity);  // CTA-scope acquire also for the peer's arrivals (see mbar_arrive_remote)
+      };
       int slot = 0;
       uint32_t phase = 0;
       uint32_t n_a_ready = 0, n_p_ready = 0, n_gchunk = 0;  // completed-phase counters of the barriers this thread waits on
@@ -220,7 +303,7 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
         return smem_u32(sRing + slot * TB_SLOT);
       };
       auto ring_release = [&]() {
-        umma_commit(&bars[B_RING_EMPTY + slot]);
+        commit(B_RING_EMPTY + slot);
         if (++slot == TB_NSLOT) { slot = 0; phase ^= 1; }
       };
       // X[:, nh*160 ..] (+)= A[128 x 320] W^T for a [320 x 320] weight streamed as 2 x 5 units
@@ -231,69 +314,77 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + kb * TB_ABLK));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_ss(tmem_base + COL_X + nh * 160, a_desc + 2 * k, b_desc + 2 * k, idesc, (!fresh || (kb | k) != 0) ? 1u : 0u);
+              mma(tmem_base + COL_X + nh * 160, a_desc + 2 * k, b_desc + 2 * k, idesc, (!fresh || (kb | k) != 0) ? 1u : 0u);
             ring_release();
           }
       };
       auto wait_a_ready = [&]() {
-        mbar_wait(&bars[B_A_READY], n_a_ready & 1);
+        wait_epi(B_A_READY, n_a_ready & 1);
         ++n_a_ready;
         tc_fence_after();
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < m_tiles; tile += nworkers, ++it) {
         // ---- proj_in: X = g Wpi^T ----
+        TB_STAMP(0, it, 0);
         mbar_wait(&bars[B_A_FULL], it & 1);
-        mbar_wait(&bars[B_X_FREE], (it & 1) ^ 1);  // the previous tile's epilogue has read its last accumulator
+        wait_epi(B_X_FREE, (it & 1) ^ 1);  // the previous tile's epilogue has read its last accumulator
         tc_fence_after();
+        TB_STAMP(0, it, 1);
         gemm_320(ID_BF16_160, true);
-        umma_commit(&bars[B_ACC]);
+        commit(B_ACC);
+        TB_STAMP(0, it, 2);
         if (stop_after(stage, 1)) continue;
         // ---- two cross-attentions: S = xhat M^T ; X += P N^T ----
         for (int a = 0; a < 2; ++a) {
           wait_a_ready();
+          TB_STAMP(0, it, 3 + 4 * a);
           for (int kb = 0; kb < TB_KB; ++kb) {
             const uint64_t b_desc = make_smem_desc_sw128(ring_wait());
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + kb * TB_ABLK));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + COL_S, a_desc + 2 * k, b_desc + 2 * k, ID_F16_64, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) mma(tmem_base + COL_S, a_desc + 2 * k, b_desc + 2 * k, ID_F16_64, (kb | k) != 0);
             ring_release();
           }
-          umma_commit(&bars[B_S]);
-          mbar_wait(&bars[B_P_READY], n_p_ready & 1);
+          commit(B_S);
+          TB_STAMP(0, it, 4 + 4 * a);
+          wait_epi(B_P_READY, n_p_ready & 1);
           ++n_p_ready;
           tc_fence_after();
+          TB_STAMP(0, it, 5 + 4 * a);
           const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sG));
-          for (int nb = 0; nb < TB_KB; ++nb) {
+          for (int nb = 0; nb < (PAIR ? 3 : TB_KB); ++nb) {
             const uint64_t b_desc = desc_mn_sw128(ring_wait());
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // K step k = the 16 key slots of head k: rows [16 k, 16 k + 16) of the MN-major unit
-              umma_f16_ss(tmem_base + COL_X + nb * 64, p_desc + 2 * k, b_desc + 128 * k, ID_F16_64_MN, 1u);
+              mma(tmem_base + COL_X + nb * (PAIR ? 128 : 64), p_desc + 2 * k, b_desc + 128 * k, PAIR ? ID_F16_128_MN : ID_F16_64_MN, 1u);
             ring_release();
           }
-          umma_commit(&bars[B_ACC]);
+          commit(B_ACC);
+          TB_STAMP(0, it, 6 + 4 * a);
           if (stop_after(stage, 2 + a)) break;
         }
         if (stop_after(stage, 2) || stop_after(stage, 3)) continue;
         // ---- feed-forward: per 64-column hidden chunk  Gacc = xhat W1_c^T ; X += GEGLU(Gacc) W2_c^T ----
         wait_a_ready();
+        TB_STAMP(0, it, 11);
         auto mma2 = [&](int c) {
           const int b = c & 1;
-          mbar_wait(&bars[B_GBUF_FULL + b], n_gbuf[b] & 1);
+          wait_epi(B_GBUF_FULL + b, n_gbuf[b] & 1);
           ++n_gbuf[b];
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sG + b * TB_ABLK));
           for (int nh = 0; nh < 2; ++nh) {
             const uint64_t b_desc = make_smem_desc_sw128(ring_wait());
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + COL_X + nh * 160, a_desc + 2 * k, b_desc + 2 * k, ID_BF16_160, 1u);
+            for (int k = 0; k < 4; ++k) mma(tmem_base + COL_X + nh * 160, a_desc + 2 * k, b_desc + 2 * k, ID_BF16_160, 1u);
             ring_release();
           }
-          umma_commit(&bars[B_GBUF_EMPTY + b]);
+          commit(B_GBUF_EMPTY + b);
         };
         for (int c = 0; c < TB_NCHUNK; ++c) {
           if (n_gchunk > 0) {  // the epilogue has drained the previous chunk's accumulator
-            mbar_wait(&bars[B_GACC_FREE], (n_gchunk - 1) & 1);
+            wait_epi(B_GACC_FREE, (n_gchunk - 1) & 1);
             tc_fence_after();
           }
           ++n_gchunk;
@@ -301,19 +392,23 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
             const uint64_t b_desc = make_smem_desc_sw128(ring_wait());
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + kb * TB_ABLK));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + COL_G, a_desc + 2 * k, b_desc + 2 * k, ID_F16_128, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) mma(tmem_base + COL_G, a_desc + 2 * k, b_desc + 2 * k, ID_F16_128, (kb | k) != 0);
             ring_release();
           }
-          umma_commit(&bars[B_GACC_FULL]);
+          commit(B_GACC_FULL);
           if (c > 0) mma2(c - 1);
+          if (c < 8) TB_STAMP(0, it, 16 + c);  // issue progress of the first chunks
         }
         mma2(TB_NCHUNK - 1);
-        umma_commit(&bars[B_ACC]);
+        commit(B_ACC);
+        TB_STAMP(0, it, 12);
         if (stop_after(stage, 4)) continue;
         // ---- proj_out: X = x3 Wpo^T (fresh accumulator; the epilogue adds bias and x_in) ----
         wait_a_ready();
+        TB_STAMP(0, it, 13);
         gemm_320(ID_F16_160, true);
-        umma_commit(&bars[B_ACC]);
+        commit(B_ACC);
+        TB_STAMP(0, it, 14);
       }
     }
   } else {
@@ -331,9 +426,12 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
       ++n_acc;
       tc_fence_after();
     };
-    auto arrive_warp = [&](int bar) {
+    auto arrive_warp = [&](int bar) {  // epilogue -> MMA barrier (in the leader CTA)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[bar]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(leader_bar(bar));
+        else mbar_arrive(&bars[bar]);
+      }
     };
     // X + cb -> 16-bit operand copy in the A buffer.  NORM: (x - mean) * rstd as fp16 (LayerNorm without its affine part, which
     // is folded into the weights that consume the copy); else the raw value as fp16.
@@ -432,9 +530,9 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
     };
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      const int m0 = tile * TB_M;
-      const int sample = m0 / args.HW;
+    for (int tile = worker; tile < m_tiles; tile += nworkers, ++it) {
+      const int m0 = tile * TILE_M + static_cast<int>(rank) * TB_M;
+      const int sample = (tile * TILE_M) / args.HW;
       // per-sample score constants of both attentions -> shared memory, slot (h, j) = h * 16 + j
       if (et < 128) {
         const int a = et >> 6, n = et & 63, h = n >> 4, j = n & 15;
@@ -444,8 +542,12 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
       named_barrier_sync(6, 256);
 
       // ---- after proj_in ----
+      const bool tr = warp == 2 && lane == 0;
+      if (tr) TB_STAMP(1, it, 0);
       wait_acc();
+      if (tr) TB_STAMP(1, it, 1);
       x_to_a(args.cb, true);
+      if (tr) TB_STAMP(1, it, 2);
       if (stop_after(stage, 1)) { store_a_tile(m0); continue; }
       arrive_warp(B_A_READY);
       // ---- attention 1 / 2 ----
@@ -453,8 +555,11 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
       for (int a = 0; a < 2; ++a) {
         softmax_to_p(sC + a * 64);
         arrive_warp(B_P_READY);
+        if (tr) TB_STAMP(1, it, 3 + 3 * a);
         wait_acc();
+        if (tr) TB_STAMP(1, it, 4 + 3 * a);
         x_to_a(args.cb + (1 + a) * TB_C, true);
+        if (tr) TB_STAMP(1, it, 5 + 3 * a);
         if (stop_after(stage, 2 + a)) { store_a_tile(m0); stopped = true; break; }
         arrive_warp(B_A_READY);
       }
@@ -466,6 +571,7 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
         mbar_wait(&bars[B_GACC_FULL], n_gacc & 1);
         ++n_gacc;
         tc_fence_after();
+        if (tr && c < 8) TB_STAMP(1, it, 16 + 2 * c);
         uint32_t vv[32], vg[32];
         tmem_ld_32x32b_x32(t_row + COL_G + half * 32, vv);
         tmem_ld_32x32b_x32(t_row + COL_G + TB_CHUNK + half * 32, vg);
@@ -491,17 +597,22 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
           *reinterpret_cast<uint4*>(grow + (((half * 4 + k) ^ (row & 7)) << 4)) = make_uint4(pk[k * 4], pk[k * 4 + 1], pk[k * 4 + 2], pk[k * 4 + 3]);
         fence_proxy_async();
         arrive_warp(B_GBUF_FULL + b);
+        if (tr && c < 8) TB_STAMP(1, it, 17 + 2 * c);
       }
+      if (tr) TB_STAMP(1, it, 9);
       // the last two chunks' MMAs are covered by the accumulator barrier below; account for their buffer releases
       n_gbuf_empty[0] += 1;
       n_gbuf_empty[1] += 1;
       // ---- x3 (raw) -> operand of proj_out ----
       wait_acc();
+      if (tr) TB_STAMP(1, it, 10);
       x_to_a(args.cb + 3 * TB_C, false);
+      if (tr) TB_STAMP(1, it, 11);
       if (stop_after(stage, 4)) { store_a_tile(m0); continue; }
       arrive_warp(B_A_READY);
       // ---- proj_out accumulator + bias + x_in -> fp16 tile in the A buffer (its MMAs have retired), GroupNorm partials ----
       wait_acc();
+      if (tr) TB_STAMP(1, it, 12);
       {
         const int c0 = half * 160;
         const __half* xr = args.x_in + static_cast<size_t>(m0 + row) * args.x_in_ld + c0;
@@ -559,13 +670,36 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
           }
         }
       }
+      if (tr) TB_STAMP(1, it, 13);
       store_a_tile(m0);
+      if (tr) TB_STAMP(1, it, 14);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while its peer may still read its smem / signal its barriers
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapWpi,
+                   const __grid_constant__ CUtensorMap mapF0, const __grid_constant__ CUtensorMap mapF1,
+                   const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
+                   const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                   const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
+  tblock_body<false>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TB_THREADS, 1)
+tblock_unet_pair_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapWpi,
+                        const __grid_constant__ CUtensorMap mapF0, const __grid_constant__ CUtensorMap mapF1,
+                        const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
+                        const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                        const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
+  tblock_body<true>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -654,15 +788,56 @@ bool tblock_enabled() {
   return v != 0;
 }
 
+}  // namespace wd
+// debug aid (not part of the product ABI): the phase stamps recorded under WD_TBLOCK_TRACE=1
+extern "C" int wdx_tblock_trace_read(unsigned long long* host, int clear) {
+  if (cudaMemcpyFromSymbol(host, wd::g_tb_trace, sizeof(unsigned long long) * 2 * 8 * 64) != cudaSuccess) return -1;
+  if (clear) {
+    static unsigned long long z[2 * 8 * 64];
+    if (cudaMemcpyToSymbol(wd::g_tb_trace, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+namespace wd {
+
+static bool tblock_trace_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TBLOCK_TRACE");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
+bool tblock_use_pair(int HW) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TBLOCK_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0 && HW % (2 * TB_M) == 0;
+}
+
 cudaError_t tblock_launch(const TBlockLaunch& L, int num_sms, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(tblock_unet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tblock_unet_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  const TBlockArgs& a = L.args;
+  TBlockArgs a = L.args;
+  a.trace = tblock_trace_enabled() ? 1 : 0;
   if (a.M <= 0 || a.M % TB_M || a.HW % TB_M || a.L < 1 || a.L > TB_KEYS || a.x_in_ld % 8) return cudaErrorInvalidValue;
+  if (a.pair) {  // the tensor maps of the weights were encoded with the half-unit boxes (tblock_use_pair)
+    if (a.HW % (2 * TB_M)) return cudaErrorInvalidValue;
+    const int tiles = a.M / (2 * TB_M);
+    const int max_pairs = num_sms / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    return launch_pdl(tblock_unet_pair_kernel, dim3(2 * pairs), dim3(TB_THREADS), TB_SMEM, stream, L.mapG, L.mapWpi, L.mapF[0],
+                      L.mapF[1], L.mapF[2], L.mapF[3], L.mapW1, L.mapW2, L.mapWpo, L.mapOut, a);
+  }
   const int tiles = a.M / TB_M;
   const int grid = tiles < num_sms ? tiles : num_sms;
   return launch_pdl(tblock_unet_kernel, dim3(grid), dim3(TB_THREADS), TB_SMEM, stream, L.mapG, L.mapWpi, L.mapF[0], L.mapF[1],

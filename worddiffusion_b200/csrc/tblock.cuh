@@ -45,12 +45,15 @@ struct TBlockArgs {
   int x_in_ld;
   float* gn_partial;   // GroupNorm partials of `out`: [sample][32 groups][HW / 32][2], or null
   float ln_eps;
+  int pair;            // 1: CTA-pair kernel (256-token tiles, HW % 256 == 0; weight maps encoded with half-unit boxes)
+  int trace;           // set by tblock_launch from env WD_TBLOCK_TRACE: CTA 0 records clock64 phase stamps (tools/tblock_trace.py)
   int stage;           // 0: full block.  Debug (operator test): 1..4 -> `out` receives the normalised operand copy after
                        // proj_in / attn1 / attn2 (LayerNorm without gamma / beta) or the raw residual stream after ff (4)
 };
 
 struct TBlockLaunch {
   CUtensorMap mapG;     // g     bf16 [M, 320]            box {64, 128}
+  // weight boxes below are for the single-CTA kernel; the pair kernel (args.pair) takes half of each: {64, 80} / W1 {64, 64}
   CUtensorMap mapWpi;   // proj_in  bf16 [320, 320]       box {64, 160}
   CUtensorMap mapF[4];  // per-sample fold operands (fp16): attn1 M, attn1 N, attn2 M, attn2 N; 3-D (1280, L, batch), box {64, 16, 1}
   CUtensorMap mapW1;    // ff.net.0.proj folded, fp16 [2560, 320], box {64, 128}
@@ -61,6 +64,7 @@ struct TBlockLaunch {
 };
 
 bool tblock_enabled();  // env WD_TBLOCK (default on)
+bool tblock_use_pair(int HW);  // env WD_TBLOCK_PAIR (default on) and HW % 256 == 0
 cudaError_t tblock_launch(const TBlockLaunch& L, int num_sms, cudaStream_t stream);
 
 // Weight-load time: W_fold rows of one attention (bf16 [2560, 320]) and the score-constant vectors u (fp32 [4][320]).
