@@ -51,10 +51,10 @@ def _plain_ln(x):
     return F.layer_norm(x, (CH,), None, None, 1e-5)
 
 
-def _reference(W, g, x_in, ctx, B, HW, L):
-    """-> dict stage -> tensor [B*HW, 320] (fp32)."""
+def _reference(W, g, x_in, ctx, B, HW, L, mid=False):
+    """-> dict stage -> tensor [B*HW, 320] (fp32).  mid: x_in is the residual stream itself (no proj_in / proj_out)."""
     out = {}
-    x = g @ W["pi_w"].T + W["pi_b"]
+    x = x_in if mid else g @ W["pi_w"].T + W["pi_b"]
     out[1] = _plain_ln(x)
     c = ctx.view(B, L, CH)
     for a in (1, 2):
@@ -71,6 +71,7 @@ def _reference(W, g, x_in, ctx, B, HW, L):
     val, gate = pr.chunk(2, dim=-1)
     x = x + (val * F.gelu(gate)) @ W["ff2_w"].T + W["ff2_b"]
     out[4] = x
+    out[5] = x
     out[0] = x @ W["po_w"].T + W["po_b"] + x_in
     return out
 
@@ -84,7 +85,7 @@ def _run(W, g16, x16, ctx16, B, HW, L, stage, want_stats=False):
     return out, stats
 
 
-@pytest.mark.parametrize("B,HW,L", [(2, 256, 10), (5, 128, 16), (3, 256, 1), (160, 256, 10)])
+@pytest.mark.parametrize("B,HW,L", [(2, 256, 10), (5, 128, 16), (3, 256, 1), (160, 256, 10), (6, 64, 10), (5, 64, 16), (1, 64, 3), (301, 64, 10)])
 def test_fused_block_every_stage(B, HW, L):
     W = _weights(3 + B)
     gen = torch.Generator().manual_seed(100 + B)
@@ -119,3 +120,20 @@ def test_fused_block_rows_do_not_mix():
     b, _ = _run(W, g16[perm].reshape(-1, CH).contiguous(), x16[perm].reshape(-1, CH).contiguous(),
                 ctx16[perm].reshape(-1, CH).contiguous(), B, HW, L, 0)
     assert torch.equal(a.view(B, HW, CH)[perm], b.view(B, HW, CH))
+
+
+@pytest.mark.parametrize("B,HW,L", [(7, 64, 10), (256, 64, 10), (4, 256, 10), (3, 128, 7)])
+def test_fused_block_middle_form(B, HW, L):
+    """SpatialTransformers whose channel count differs from 320 (the 4 x 16 level, 640 channels) keep proj_in / proj_out as GEMMs:
+    the kernel takes the fp16 residual stream and returns it after both attentions and the feed-forward (stage 5)."""
+    W = _weights(40 + B)
+    gen = torch.Generator().manual_seed(200 + B)
+    g16 = torch.zeros(B * HW, CH).to(DEV).to(torch.bfloat16)
+    x16 = torch.randn(B * HW, CH, generator=gen).to(DEV).to(torch.float16)
+    ctx16 = torch.randn(B * L, CH, generator=gen).to(DEV).to(torch.bfloat16)
+    ref = _reference(W, g16.float(), x16.float(), ctx16.float(), B, HW, L, mid=True)
+    out, _ = _run(W, g16, x16, ctx16, B, HW, L, 5)
+    assert torch.isfinite(out.float()).all()
+    e = relerr(out.float(), ref[5])
+    print(f"middle form B={B} HW={HW} L={L}: {e:.2e}")
+    assert e < TOL

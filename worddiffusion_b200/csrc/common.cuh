@@ -169,6 +169,19 @@ WD_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// same with an L2 evict_last cache hint when `keep` (experiment WD_GEMM_DBG & 64: keep a GEMM's output in L2 for its consumer)
+WD_DEVINL void tma_store_2d_keep(const CUtensorMap* m, const void* smem_src, int c0, int c1, bool keep) {
+  if (keep) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+  } else {
+    tma_store_2d(m, smem_src, c0, c1);
+  }
+}
 // 1-D bulk copies (no tensor map): global -> shared with mbarrier completion, shared -> global as a bulk group.
 // Addresses and sizes are multiples of 16 bytes.
 WD_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

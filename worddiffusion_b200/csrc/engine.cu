@@ -116,6 +116,7 @@ struct TBlockL {
   int fold_idx = -1;        // position of this block's first attention in the pools
   GemmW ff128;              // ff.net.0.proj with LayerNorm 3 folded in, value / gate rows interleaved per 64-column chunk
   float* cb = nullptr;      // [4][320] cumulative residual-stream biases
+  bool mid = false;         // SpatialTransformer channels != 320: proj_in / proj_out stay GEMMs, the kernel runs its "middle" form
 };
 struct STL {
   int C = 0, heads = 0, dh = 0;
@@ -249,6 +250,7 @@ struct wd_engine {
   int fold_next = 0;
   bf16* fold_pool = nullptr;   // [fold_count][2560][320] bf16: ONE GEMM per trajectory produces every per-sample attention operand
   float* u_pool = nullptr;     // [fold_count][4][320]
+  bf16* tb_identity = nullptr; // 320 x 320 fp16 identity: "proj_in" of the fused kernel's middle form (x I = the residual stream)
   // activations
   char* abase = nullptr;
   size_t acap = 0;
@@ -412,7 +414,9 @@ struct Builder {
       t.a2_out = linear(tp + "attn2.to_out.0", inner, inner, true);
       linear_ln(t.ff_proj, tp + "ff.net.0.proj", inner * 8, inner, true, t.ln3, 0, 0, gemm_geglu_block(inner * 8));
       t.ff_out = linear(tp + "ff.net.2", inner, inner * 4, true);
-      if (e->cfg.variant == WD_VARIANT_UNET && inner == TB_C && heads == TB_HEADS && dh == TB_DH && ctx_dim == TB_C && C == TB_C) {
+      if (e->cfg.variant == WD_VARIANT_UNET && inner == TB_C && heads == TB_HEADS && dh == TB_DH && ctx_dim == TB_C) {
+        t.mid = C != TB_C;
+        if (t.mid && !e->tb_identity) e->tb_identity = A.alloc<bf16>(static_cast<size_t>(TB_C) * TB_C);
         // operands of the fused transformer-block kernel (tblock.cuh)
         for (int a = 0; a < 2; ++a) {
           const std::string ap = tp + (a ? "attn2" : "attn1");
@@ -488,6 +492,7 @@ struct Builder {
     e->fold_next = 0;
     e->fold_pool = nullptr;
     e->u_pool = nullptr;
+    e->tb_identity = nullptr;
     e->raw_extra.clear();
     e->st.clear();
     e->samp.clear();
@@ -827,9 +832,19 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
       const float* add[4] = {st.proj_in.bias, t.a1_out.bias, t.a2_out.bias, t.ff_out.bias};
       for (int i = 0; i < 4; ++i) {
         if (i > 0) CUDA_TRY(repack_vec_launch(t.cb + (i - 1) * TB_C, t.cb + i * TB_C, TB_C, 0, 0, 0, s));
-        CUDA_TRY(repack_vec_launch(add[i], t.cb + i * TB_C, TB_C, 0, 0, i > 0 ? 1 : 0, s));
+        if (i == 0 && t.mid) {  // the proj_in GEMM in front of the kernel has already added its bias
+          CUDA_TRY(cudaMemsetAsync(t.cb, 0, TB_C * sizeof(float), s));
+        } else {
+          CUDA_TRY(repack_vec_launch(add[i], t.cb + i * TB_C, TB_C, 0, 0, i > 0 ? 1 : 0, s));
+        }
       }
     }
+  if (e->tb_identity) {
+    std::vector<uint16_t> eye(static_cast<size_t>(TB_C) * TB_C, 0);
+    for (int i = 0; i < TB_C; ++i) eye[static_cast<size_t>(i) * TB_C + i] = 0x3C00;  // fp16 1.0
+    CUDA_TRY(cudaMemcpyAsync(e->tb_identity, eye.data(), eye.size() * 2, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
   for (auto& r : e->res) {
     CUDA_TRY(repack_vec_launch(r.b_main, r.conv2.bias, r.Cout, 0, 0, 0, s));
     if (r.skip_conv) CUDA_TRY(repack_vec_launch(r.b_skip, r.conv2.bias, r.Cout, 0, 0, 1, s));
@@ -1160,9 +1175,11 @@ struct PlanBuilder {
   }
 
   // ---- the whole transformer block as ONE kernel (tblock.cu): unet.UNetModel, 128-token tiles inside one sample ----
+  // mid form (t.mid): `g` is the fp16 residual stream after the proj_in GEMM, `out` the raw fp16 stream after the feed-forward
   bool st_block_fused(std::vector<Op>& ops, const STL& s, const TBlockL& t, const Act& x_in, const Act& g, Act& out) {
     const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = TB_C;
     const int Ltot = plan->Ltot;
+    const bool mid = t.mid;
     out = new_act(H, W, C, true);
     Op op;
     memset(&op, 0, sizeof(op));
@@ -1180,20 +1197,22 @@ struct PlanBuilder {
     a.x_in = reinterpret_cast<const __half*>(x_in.p);
     a.x_in_ld = x_in.C;
     a.ln_eps = 1e-5f;  // nn.LayerNorm default (unet.py:314-316)
-    a.stage = 0;
+    a.stage = mid ? 4 : 0;
+    a.mid = mid ? 1 : 0;
     a.pair = tblock_use_pair(HW) ? 1 : 0;
     const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
-    if (epilogue_stats_ok(HW, C)) {
+    if (!mid && epilogue_stats_ok(HW, C)) {
       a.gn_partial = out.stats;
       out.pslots = HW / 32;
     }
     // algorithmic work = the reference's ops (unet.py:337-345, 381-412): proj_in, 2 x (to_q, QK^T, PV, to_out), GEGLU ff, proj_out
+    // (the middle form leaves proj_in / proj_out to their own GEMM ops)
     const double lin = 2.0 * M * C * C;
-    op.flops = lin + 2.0 * (2.0 * lin + 4.0 * M * C * Ltot) + 2.0 * M * C * (8.0 * C) + 2.0 * M * (4.0 * C) * C + lin;
+    op.flops = (mid ? 0.0 : 2.0 * lin) + 2.0 * (2.0 * lin + 4.0 * M * C * Ltot) + 2.0 * M * C * (8.0 * C) + 2.0 * M * (4.0 * C) * C;
     op.bytes = 2.0 * M * C * 3 + 2.0 * (3.0 * C * C + 12.0 * C * C) + 2.0 * 4 * (static_cast<double>(M) / HW) * Ltot * TB_HEADS * C;
     if (!dry) {
       bool ok = tmap_encode_2d_bf16(&op.tb.mapG, g.p, C, M, g.C, 64, TB_M) &&
-                tmap_encode_2d_bf16(&op.tb.mapWpi, s.proj_in.w, C, C, C, 64, wbox) &&
+                tmap_encode_2d_bf16(&op.tb.mapWpi, mid ? e->tb_identity : s.proj_in.w, C, C, C, 64, wbox) &&
                 tmap_encode_2d_bf16(&op.tb.mapW1, t.ff128.w, C, 8 * C, C, 64, w1box) &&
                 tmap_encode_2d_bf16(&op.tb.mapW2, t.ff_out.w, 4 * C, C, 4 * C, 64, wbox) &&
                 tmap_encode_2d_bf16(&op.tb.mapWpo, s.proj_out.w, C, C, C, 64, wbox) &&
@@ -1206,7 +1225,7 @@ struct PlanBuilder {
       if (!ok) { err = "cuTensorMapEncodeTiled failed (fused transformer block)"; return false; }
     }
     ops.push_back(op);
-    if (!out.pslots && !ensure_stats(ops, out)) return false;
+    if (!mid && !out.pslots && !ensure_stats(ops, out)) return false;
     return true;
   }
 
@@ -1216,8 +1235,32 @@ struct PlanBuilder {
     const int Ltot = plan->Ltot;
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
-    if (fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && HW % TB_M == 0 && x_in.f16 && x_in.C == TB_C && s.C == TB_C)
+    const bool tb_ok = fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && x_in.f16 && s.heads * s.dh == TB_C;
+    if (tb_ok && !s.blocks[0].mid && HW % TB_M == 0 && x_in.C == TB_C && s.C == TB_C)
       return st_block_fused(ops, s, s.blocks[0], x_in, g, out);
+    if (tb_ok && s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2)) {
+      // channels != 320 (the 4 x 16 level: 640): proj_in and proj_out as GEMMs around the kernel's middle form
+      Act x = new_act(H, W, TB_C, true), x3;
+      {
+        Epi ep;
+        ep.out = x.p;
+        ep.out_ld = TB_C;
+        ep.out_f16 = 1;
+        if (!gemm_op(ops, M, false, 0, 0, {ASrc{g.p, g.C, g.C, 1, 1, H, W}}, s.proj_in, ep)) return false;
+      }
+      if (!st_block_fused(ops, s, s.blocks[0], x_in, x, x3)) return false;
+      out = new_act(H, W, s.C, true);
+      Epi ep;
+      ep.out = out.p;
+      ep.out_ld = s.C;
+      ep.out_f16 = 1;
+      ep.residual = x_in.p;
+      ep.res_ld = x_in.C;
+      ep.res_f16 = x_in.f16 ? 1 : 0;
+      ep.rows_per_sample = HW;
+      ep.stats_for = &out;
+      return gemm_op(ops, M, false, 0, 0, {ASrc{x3.p, TB_C, TB_C, 1, 1, H, W, true}}, s.proj_out, ep);
+    }
     if (C % 80) { err = "spatial transformer: inner channels must be a multiple of 80 (LayerNorm folding)"; return false; }
     // LayerNorm is folded into the GEMMs around it: the producer of each token tensor writes per-row {sum, sum of squares}
     // (4 column blocks of 80), the consumer GEMM reads the raw fp16 tensor with gamma-scaled weights and normalises in its epilogue
@@ -2224,13 +2267,17 @@ extern "C" int wd_op_attention(const void* q, int ldq, const void* k, const void
 //  9 attn1.to_q.w  10 attn1.to_k.w  11 attn1.to_v.w  12 attn1.to_out.0.w  13 attn1.to_out.0.b
 // 14 attn2.to_q.w  15 attn2.to_k.w  16 attn2.to_v.w  17 attn2.to_out.0.w  18 attn2.to_out.0.b
 // 19 ff.net.0.proj.w [2560,320]  20 ff.net.0.proj.b [2560]  21 ff.net.2.w [320,1280]  22 ff.net.2.b  23 proj_out.w  24 proj_out.b
-// stage: TBlockArgs::stage.  out: fp16 [M,320]; gn_partial: fp32 [B][32][HW/32][2] or NULL.  Synchronises the stream.
+// stage: TBlockArgs::stage, or 5 = the middle form (x_in is the residual stream itself: no proj_in / proj_out, out = the raw
+// stream after the feed-forward).  HW: a multiple of 128, or 64 (two samples per tile; B may be odd).
+// out: fp16 [M,320]; gn_partial: fp32 [B][32][HW/32][2] or NULL.  Synchronises the stream.
 extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int B, int HW, int L, int stage, void* out_f16,
                                  float* gn_partial, void* stream) {
   if (!tensors || n_tensors != 25 || !out_f16) return fail(WD_ERR_INVALID, "op_tblock_unet: expects 25 tensors");
   for (int i = 0; i < 25; ++i)
     if (!tensors[i]) return fail(WD_ERR_INVALID, "op_tblock_unet: tensor %d is null", i);
-  if (B < 1 || HW % TB_M || L < 1 || L > TB_KEYS || stage < 0 || stage > 4) return fail(WD_ERR_INVALID, "op_tblock_unet: bad shape");
+  if (B < 1 || (HW % TB_M && HW != TB_M / 2) || L < 1 || L > TB_KEYS || stage < 0 || stage > 5)
+    return fail(WD_ERR_INVALID, "op_tblock_unet: bad shape");
+  const bool mid = stage == 5;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto F = [&](int i) { return static_cast<const float*>(tensors[i]); };
   const int C = TB_C, M = B * HW;
@@ -2252,6 +2299,7 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     float* cb = A.alloc<float>(4 * C);
     bf16* fold_out = A.alloc<bf16>(static_cast<size_t>(B) * L * 2 * TB_FOLD_N);
     float* cvec = A.alloc<float>(static_cast<size_t>(B) * L * 2 * TB_HEADS);
+    bf16* eye_d = A.alloc<bf16>(static_cast<size_t>(C) * C);
 #define TB_TRY(x) if ((x) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "op_tblock_unet: %s", cudaGetErrorString(cudaGetLastError())); break; }
     TB_TRY(repack_linear_launch(F(3), w_pi, C, C, C, 0, 0, 0, 0, s));
     TB_TRY(repack_linear_launch(F(23), w_po, C, C, C, 0, 0, 0, 1, s));
@@ -2264,9 +2312,19 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     const float* add[4] = {F(4), F(13), F(18), F(22)};
     for (int i = 0; i < 4; ++i) {
       if (i > 0) TB_TRY(repack_vec_launch(cb + (i - 1) * C, cb + i * C, C, 0, 0, 0, s));
-      TB_TRY(repack_vec_launch(add[i], cb + i * C, C, 0, 0, i > 0 ? 1 : 0, s));
+      if (i == 0 && mid) {
+        TB_TRY(cudaMemsetAsync(cb, 0, C * sizeof(float), s));
+      } else {
+        TB_TRY(repack_vec_launch(add[i], cb + i * C, C, 0, 0, i > 0 ? 1 : 0, s));
+      }
     }
     if (rc != WD_OK) break;
+    if (mid) {
+      std::vector<uint16_t> eye(static_cast<size_t>(C) * C, 0);
+      for (int i = 0; i < C; ++i) eye[static_cast<size_t>(i) * C + i] = 0x3C00;
+      TB_TRY(cudaMemcpyAsync(eye_d, eye.data(), eye.size() * 2, cudaMemcpyHostToDevice, s));
+      TB_TRY(cudaStreamSynchronize(s));
+    }
     rc = op_gemm_impl(tensors[2], w_fold, nullptr, nullptr, fold_out, B * L, 2 * TB_FOLD_N, C, 0, 0, 0, 0, 1, s);
     if (rc != WD_OK) break;
     TB_TRY(tblock_cvec_launch(static_cast<const bf16*>(tensors[2]), u, cvec, B * L, 2 * TB_HEADS, s));
@@ -2275,11 +2333,13 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     TBlockArgs& a = T.args;
     a.M = M; a.HW = HW; a.L = L; a.cb = cb; a.b_ff = b_ff1; a.cvec1 = cvec; a.cvec2 = cvec + TB_HEADS; a.cvec_ld = 2 * TB_HEADS;
     a.b_po = F(24); a.x_in = static_cast<const __half*>(tensors[1]); a.x_in_ld = C; a.gn_partial = gn_partial; a.ln_eps = 1e-5f;
-    a.stage = stage;
+    a.stage = mid ? 4 : stage;
+    a.mid = mid ? 1 : 0;
     a.pair = tblock_use_pair(HW) ? 1 : 0;
     const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
     const int fold_ld = 2 * TB_FOLD_N;
-    bool ok = tmap_encode_2d_bf16(&T.mapG, tensors[0], C, M, C, 64, TB_M) && tmap_encode_2d_bf16(&T.mapWpi, w_pi, C, C, C, 64, wbox) &&
+    bool ok = tmap_encode_2d_bf16(&T.mapG, mid ? tensors[1] : tensors[0], C, M, C, 64, TB_M) &&
+              tmap_encode_2d_bf16(&T.mapWpi, mid ? eye_d : w_pi, C, C, C, 64, wbox) &&
               tmap_encode_2d_bf16(&T.mapW1, w_ff1, C, 8 * C, C, 64, w1box) &&
               tmap_encode_2d_bf16(&T.mapW2, w_ff2, 4 * C, C, 4 * C, 64, wbox) && tmap_encode_2d_bf16(&T.mapWpo, w_po, C, C, C, 64, wbox) &&
               tmap_encode_2d_bf16(&T.mapOut, out_f16, C, M, C, 64, TB_M);

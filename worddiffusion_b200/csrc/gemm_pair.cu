@@ -343,10 +343,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (leader_warp && elect_one()) {
             if (!args.geglu) {
               const int oc0 = n0 + half * 160 + rnd * 80;
-              tma_store_2d(&mapOut, stg_half, oc0, m0);
-              tma_store_2d(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0);
+              tma_store_2d_keep(&mapOut, stg_half, oc0, m0, (args.dbg & 64) != 0);
+              tma_store_2d_keep(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0, (args.dbg & 64) != 0);
             } else {
-              tma_store_2d(&mapOut, stg_half, n_tile * 160 + half * 80 + rnd * 40, m0);
+              tma_store_2d_keep(&mapOut, stg_half, n_tile * 160 + half * 80 + rnd * 40, m0, (args.dbg & 64) != 0);
             }
             bulk_commit_group();
             if (has_res) {

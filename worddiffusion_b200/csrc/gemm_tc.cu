@@ -339,8 +339,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         fence_proxy_async();
         named_barrier_sync(bar_id, 128);
         if (leader_warp && elect_one()) {
-          tma_store_2d(&mapOut, stg_g, n_tile * HC, m0);
-          tma_store_2d(&mapOut, stg_g + C::SUB_BYTES, n_tile * HC + GEMM_SUB_N, m0);
+          tma_store_2d_keep(&mapOut, stg_g, n_tile * HC, m0, (args.dbg & 64) != 0);
+          tma_store_2d_keep(&mapOut, stg_g + C::SUB_BYTES, n_tile * HC + GEMM_SUB_N, m0, (args.dbg & 64) != 0);
           bulk_commit_group();
         }
       }
@@ -643,9 +643,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (!args.geglu) {
 #pragma unroll
               for (int s = 0; s < NSUB; ++s)
-                tma_store_2d(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0);
+                tma_store_2d_keep(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0, (args.dbg & 64) != 0);
             } else {
-              tma_store_2d(&mapOut, src, n_tile * HC + half * 40, m0);
+              tma_store_2d_keep(&mapOut, src, n_tile * HC + half * 40, m0, (args.dbg & 64) != 0);
             }
             bulk_commit_group();
             const int next = tile + gridDim.x;

@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(512, 2) groupnorm_apply_bulk_kernel(const Grou
   const int ng = Cs / cpg;
   const uint32_t row_bytes = static_cast<uint32_t>(Cs) * 2;
   const uint32_t item_bytes = GNB_P * row_bytes;
-  const int first = blockIdx.x * per_cta;
+  // WD_GN_REVERSE experiment (a.reverse): CTA 0 takes the LAST items -- the rows the producing GEMM wrote most recently and the
+  // likeliest to still sit in L2
+  const int cta = a.reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int first = cta * per_cta;
   const int last = min(first + per_cta, n_items);
 
   if (threadIdx.x == 0) {
@@ -383,6 +386,8 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
     if (attr_err != cudaSuccess) return attr_err;
     GroupNormArgs a2 = a;
     a2.nchunk = a.HW / GNB_P;
+    static const int rev = [] { const char* e = getenv("WD_GN_REVERSE"); return e ? atoi(e) : 0; }();
+    a2.reverse = rev;
     const int n_items = B * nslab * a2.nchunk;
     const int per = (n_items + 2 * sms - 1) / (2 * sms);  // contiguous items per CTA: consecutive chunks share their statistics
     const int grid = (n_items + per - 1) / per;

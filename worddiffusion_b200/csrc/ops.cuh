@@ -36,6 +36,7 @@ struct GroupNormArgs {
   int silu;
   int nchunk;  // pixel chunks per sample of the apply grid
   int x_f16[2];  // per source: 1 = fp16 input (residual-stream tensors), 0 = bf16.  The output is always bf16.
+  int reverse;   // bulk kernel: walk the items from the end of the tensor (set by groupnorm_launch)
 };
 // normalise (+SiLU) from the partial statistics
 int groupnorm_apply_chunks(int HW);  // pixel chunks per sample of the apply grid (GroupNormArgs::nchunk)

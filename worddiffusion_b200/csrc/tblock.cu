@@ -45,9 +45,9 @@ constexpr int OFF_G = OFF_A + TB_KB * TB_ABLK;           // 81920: two [128 x 64
 constexpr int OFF_RING = OFF_G + 2 * TB_ABLK;            // 114688
 constexpr int OFF_BFF = OFF_RING + TB_RING;              // 217088
 constexpr int OFF_CSM = OFF_BFF + 2 * TB_HID * 4;        // 227328
-constexpr int OFF_STAT = OFF_CSM + 2 * 64 * 4;           // 227840
-constexpr int OFF_BARS = OFF_STAT + 2 * TB_M * 8;        // 229888
-constexpr int TB_SMEM = OFF_BARS + 320;                  // 230208
+constexpr int OFF_STAT = OFF_CSM + 4 * 64 * 4;           // 228352 (score constants: 2 attentions x up to 2 samples x 64)
+constexpr int OFF_BARS = OFF_STAT + 2 * TB_M * 8;        // 230400
+constexpr int TB_SMEM = OFF_BARS + 320;                  // 230720
 static_assert(TB_SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t COL_X = 0, COL_G = 320, COL_S = 448;
 
@@ -93,7 +93,11 @@ WD_DEVINL void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t b
       : "memory");
 }
 
-template <bool PAIR>
+// SPT = samples per 128-token tile: 1 (a sample holds a multiple of 128 tokens) or 2 (64 tokens per sample, the 4 x 16 level).
+// With two samples the score GEMM runs against both samples' keys (N = 128, into the idle GEGLU accumulator columns), each row
+// soft-maxes its own sample's 64 score columns and writes zeros for the other sample's keys, and the output GEMM reduces over
+// both samples' (head, key) rows (K = 128).
+template <bool PAIR, int SPT>
 WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, const CUtensorMap& mapF0, const CUtensorMap& mapF1,
                            const CUtensorMap& mapF2, const CUtensorMap& mapF3, const CUtensorMap& mapW1, const CUtensorMap& mapW2,
                            const CUtensorMap& mapWpo, const CUtensorMap& mapOut, const TBlockArgs& args) {
@@ -115,7 +119,10 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
-  const int m_tiles = args.M / TILE_M;
+  static_assert(!(PAIR && SPT != 1), "the pair build takes whole samples per CTA");
+  const int m_tiles = (args.M + TILE_M - 1) / TILE_M;  // a ragged last tile (M % 128 == 64) is zero-filled / clipped by TMA
+  const int n_samples = args.M / args.HW;
+  constexpr uint32_t COL_SC = SPT == 2 ? COL_G : COL_S;  // score accumulator: N = 64 SPT columns
   const int stage = args.stage;
   const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int nworkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -200,12 +207,14 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       // score operand of one attention: five K blocks of four [16 keys x 64] boxes, one per head (pair: this CTA's two heads)
       auto fold_m_units = [&](const CUtensorMap* mp, int sample) {
         for (int b = 0; b < TB_KB; ++b) {
-          uint8_t* dst = acquire(TB_HEADS * TB_KEYS * 128);
+          uint8_t* dst = acquire(SPT * TB_HEADS * TB_KEYS * 128);
           if (PAIR) {
             for (int hl = 0; hl < 2; ++hl)
               load3(dst + hl * (TB_KEYS * 128), mp, B_RING_FULL + slot, (static_cast<int>(rank) * 2 + hl) * TB_C + b * 64, 0, sample);
           } else {
-            for (int h = 0; h < TB_HEADS; ++h) load3(dst + h * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample);
+            for (int sl = 0; sl < SPT; ++sl)  // a sample index past the batch (ragged last tile) is zero-filled
+              for (int h = 0; h < TB_HEADS; ++h)
+                load3(dst + (sl * TB_HEADS + h) * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample + sl);
           }
           advance();
         }
@@ -224,8 +233,10 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
           }
         } else {
           for (int b = 0; b < TB_KB; ++b) {
-            uint8_t* dst = acquire(TB_HEADS * TB_KEYS * 128);
-            for (int h = 0; h < TB_HEADS; ++h) load3(dst + h * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample);
+            uint8_t* dst = acquire(SPT * TB_HEADS * TB_KEYS * 128);
+            for (int sl = 0; sl < SPT; ++sl)
+              for (int h = 0; h < TB_HEADS; ++h)
+                load3(dst + (sl * TB_HEADS + h) * (TB_KEYS * 128), mp, B_RING_FULL + slot, h * TB_C + b * 64, 0, sample + sl);
             advance();
           }
         }
@@ -331,7 +342,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         wait_epi(B_X_FREE, (it & 1) ^ 1);  // the previous tile's epilogue has read its last accumulator
         tc_fence_after();
         TB_STAMP(0, it, 1);
-        gemm_320(ID_BF16_160, true);
+        gemm_320(args.mid ? ID_F16_160 : ID_BF16_160, true);  // mid: x (fp16) times the identity = the residual stream itself
         commit(B_ACC);
         TB_STAMP(0, it, 2);
         if (stop_after(stage, 1)) continue;
@@ -343,7 +354,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
             const uint64_t b_desc = make_smem_desc_sw128(ring_wait());
             const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + kb * TB_ABLK));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma(tmem_base + COL_S, a_desc + 2 * k, b_desc + 2 * k, ID_F16_64, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) mma(tmem_base + COL_SC, a_desc + 2 * k, b_desc + 2 * k, SPT == 2 ? ID_F16_128 : ID_F16_64, (kb | k) != 0);
             ring_release();
           }
           commit(B_S);
@@ -356,8 +367,9 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
           for (int nb = 0; nb < (PAIR ? 3 : TB_KB); ++nb) {
             const uint64_t b_desc = desc_mn_sw128(ring_wait());
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // K step k = the 16 key slots of head k: rows [16 k, 16 k + 16) of the MN-major unit
-              mma(tmem_base + COL_X + nb * (PAIR ? 128 : 64), p_desc + 2 * k, b_desc + 128 * k, PAIR ? ID_F16_128_MN : ID_F16_64_MN, 1u);
+            for (int k = 0; k < 4 * SPT; ++k)  // K step k = the 16 key slots of (sample k / 4, head k % 4): rows [16 k, +16) of the MN-major unit
+              mma(tmem_base + COL_X + nb * (PAIR ? 128 : 64), p_desc + (k >> 2) * (TB_ABLK >> 4) + 2 * (k & 3), b_desc + 128 * k,
+                  PAIR ? ID_F16_128_MN : ID_F16_64_MN, 1u);
             ring_release();
           }
           commit(B_ACC);
@@ -487,8 +499,9 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       mbar_wait(&bars[B_S], n_s & 1);
       ++n_s;
       tc_fence_after();
+      const int sel = SPT == 2 ? (q >> 1) : 0;  // which of the tile's samples this row belongs to (64 rows each)
       uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + COL_S + half * 32, v);
+      tmem_ld_32x32b_x32(t_row + COL_SC + sel * 64 + half * 32, v);
       tmem_ld_wait();
       tc_fence_before();
       uint32_t pk[16];
@@ -498,7 +511,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          sc[j] = (j < args.L) ? __uint_as_float(v[hh * 16 + j]) + cs[half * 32 + hh * 16 + j] : -INFINITY;
+          sc[j] = (j < args.L) ? __uint_as_float(v[hh * 16 + j]) + cs[sel * 64 + half * 32 + hh * 16 + j] : -INFINITY;
           mx = fmaxf(mx, sc[j]);
         }
         float l = 0.f;
@@ -511,10 +524,15 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
 #pragma unroll
         for (int j = 0; j < 16; j += 2) pk[hh * 8 + j / 2] = pack_f16x2(sc[j] * inv, sc[j + 1] * inv);
       }
-      uint8_t* const prow = sG + row * 128;
+      uint8_t* const prow = sG + sel * TB_ABLK + row * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      if (SPT == 2) {  // this row takes nothing from the other sample's keys
+        uint8_t* const zrow = sG + (sel ^ 1) * TB_ABLK + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(zrow + (((half * 4 + c) ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      }
       fence_proxy_async();
     };
     // the A buffer holds a finished [128 x 320] fp16 tile: store it to `out`, then free the buffer and the accumulator
@@ -534,10 +552,10 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       const int m0 = tile * TILE_M + static_cast<int>(rank) * TB_M;
       const int sample = (tile * TILE_M) / args.HW;
       // per-sample score constants of both attentions -> shared memory, slot (h, j) = h * 16 + j
-      if (et < 128) {
-        const int a = et >> 6, n = et & 63, h = n >> 4, j = n & 15;
+      if (et < 128 * SPT) {  // layout [attention][sample of the tile][head][key]
+        const int a = et / (64 * SPT), sl = (et / 64) % SPT, n = et & 63, h = n >> 4, j = n & 15;
         const float* cv = a ? args.cvec2 : args.cvec1;
-        sC[et] = (j < args.L) ? __ldg(cv + (static_cast<size_t>(sample) * args.L + j) * args.cvec_ld + h) : 0.f;
+        sC[et] = (j < args.L && sample + sl < n_samples) ? __ldg(cv + (static_cast<size_t>(sample + sl) * args.L + j) * args.cvec_ld + h) : 0.f;
       }
       named_barrier_sync(6, 256);
 
@@ -553,7 +571,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       // ---- attention 1 / 2 ----
       bool stopped = false;
       for (int a = 0; a < 2; ++a) {
-        softmax_to_p(sC + a * 64);
+        softmax_to_p(sC + a * 64 * SPT);
         arrive_warp(B_P_READY);
         if (tr) TB_STAMP(1, it, 3 + 3 * a);
         wait_acc();
@@ -615,7 +633,8 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       if (tr) TB_STAMP(1, it, 12);
       {
         const int c0 = half * 160;
-        const __half* xr = args.x_in + static_cast<size_t>(m0 + row) * args.x_in_ld + c0;
+        const bool valid = m0 + row < args.M;
+        const __half* xr = args.x_in + static_cast<size_t>(valid ? m0 + row : 0) * args.x_in_ld + c0;
         float gs[32];  // 16 groups of 10 columns: [2 g] = sum, [2 g + 1] = sum of squares
 #pragma unroll
         for (int i = 0; i < 32; ++i) gs[i] = 0.f;
@@ -656,6 +675,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         if (args.gn_partial) {
           // the 32 rows of a warp belong to one sample and one 32-row slot: reduce over the rows, 8 groups per pass
           const int mw = m0 + q * 32;
+          const int smp_w = mw / args.HW;  // the sample of this warp's 32 rows
           const int slot = (mw % args.HW) >> 5, nslot = args.HW >> 5;
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -663,9 +683,9 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
 #pragma unroll
             for (int i = 0; i < 16; ++i) part[i] = gs[p * 16 + i];
             const float tot = warp_transpose_reduce16(part, lane);
-            if (lane < 16) {
+            if (lane < 16 && mw < args.M) {
               const int g = half * 16 + p * 8 + (lane >> 1);
-              args.gn_partial[((static_cast<size_t>(sample) * 32 + g) * nslot + slot) * 2 + (lane & 1)] = tot;
+              args.gn_partial[((static_cast<size_t>(smp_w) * 32 + g) * nslot + slot) * 2 + (lane & 1)] = tot;
             }
           }
         }
@@ -691,7 +711,15 @@ tblock_unet_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_consta
                    const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
                    const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
                    const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
-  tblock_body<false>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
+  tblock_body<false, 1>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
+}
+__global__ void __launch_bounds__(TB_THREADS, 1)
+tblock_unet_spt2_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapWpi,
+                        const __grid_constant__ CUtensorMap mapF0, const __grid_constant__ CUtensorMap mapF1,
+                        const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
+                        const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                        const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
+  tblock_body<false, 2>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
 }
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TB_THREADS, 1)
 tblock_unet_pair_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapWpi,
@@ -699,7 +727,7 @@ tblock_unet_pair_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_c
                         const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapF3,
                         const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
                         const __grid_constant__ CUtensorMap mapWpo, const __grid_constant__ CUtensorMap mapOut, const TBlockArgs args) {
-  tblock_body<true>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
+  tblock_body<true, 1>(mapG, mapWpi, mapF0, mapF1, mapF2, mapF3, mapW1, mapW2, mapWpo, mapOut, args);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -825,11 +853,22 @@ cudaError_t tblock_launch(const TBlockLaunch& L, int num_sms, cudaStream_t strea
     attr_err = cudaFuncSetAttribute(tblock_unet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(tblock_unet_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tblock_unet_spt2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
   });
   if (attr_err != cudaSuccess) return attr_err;
   TBlockArgs a = L.args;
   a.trace = tblock_trace_enabled() ? 1 : 0;
-  if (a.M <= 0 || a.M % TB_M || a.HW % TB_M || a.L < 1 || a.L > TB_KEYS || a.x_in_ld % 8) return cudaErrorInvalidValue;
+  const bool spt2 = a.HW == TB_M / 2;  // two samples per tile (4 x 16 latents); a ragged last tile is allowed there
+  if (a.M <= 0 || a.M % a.HW || (!spt2 && a.HW % TB_M) || a.L < 1 || a.L > TB_KEYS || a.x_in_ld % 8 || (spt2 && a.pair))
+    return cudaErrorInvalidValue;
+  if (a.mid && a.stage != 4) return cudaErrorInvalidValue;  // the mid form ends with the raw residual stream (no proj_out)
+  if (spt2) {
+    const int tiles = (a.M + TB_M - 1) / TB_M;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    return launch_pdl(tblock_unet_spt2_kernel, dim3(grid), dim3(TB_THREADS), TB_SMEM, stream, L.mapG, L.mapWpi, L.mapF[0], L.mapF[1],
+                      L.mapF[2], L.mapF[3], L.mapW1, L.mapW2, L.mapWpo, L.mapOut, a);
+  }
   if (a.pair) {  // the tensor maps of the weights were encoded with the half-unit boxes (tblock_use_pair)
     if (a.HW % (2 * TB_M)) return cudaErrorInvalidValue;
     const int tiles = a.M / (2 * TB_M);

@@ -33,7 +33,7 @@ constexpr int TB_FOLD_N = 2 * TB_HEADS * TB_C;  // rows of W_fold per attention:
 
 struct TBlockArgs {
   int M;    // rows = batch * HW, a multiple of 128
-  int HW;   // tokens per sample, a multiple of 128 (a tile lies inside one sample)
+  int HW;   // tokens per sample: a multiple of 128 (a tile lies inside one sample), or 64 (two samples per tile)
   int L;    // context keys, 1 .. 16
   const float* cb;     // [4][320] cumulative biases of the residual stream after proj_in / attn1 / attn2 / ff
   const float* b_ff;   // [2560] GEGLU bias with LayerNorm-3 folded in, chunk-interleaved (64 values ++ 64 gates per chunk)
@@ -46,6 +46,9 @@ struct TBlockArgs {
   float* gn_partial;   // GroupNorm partials of `out`: [sample][32 groups][HW / 32][2], or null
   float ln_eps;
   int pair;            // 1: CTA-pair kernel (256-token tiles, HW % 256 == 0; weight maps encoded with half-unit boxes)
+  int mid;             // 1: "middle" form for SpatialTransformers whose in/out channels differ from 320 (proj_in / proj_out stay
+                       // separate GEMMs): mapG = the fp16 residual stream x [M, 320], mapWpi = a 320 x 320 fp16 identity, cb[0] = 0,
+                       // stage = 4 (the tile leaves as the raw fp16 stream after the feed-forward)
   int trace;           // set by tblock_launch from env WD_TBLOCK_TRACE: CTA 0 records clock64 phase stamps (tools/tblock_trace.py)
   int stage;           // 0: full block.  Debug (operator test): 1..4 -> `out` receives the normalised operand copy after
                        // proj_in / attn1 / attn2 (LayerNorm without gamma / beta) or the raw residual stream after ff (4)
