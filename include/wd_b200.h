@@ -251,6 +251,16 @@ int wd_f32_unet_eval_maps(wd_f32* e, int batch, const float* x, const int64_t* t
                           float* eps_out, void* stream);
 int wd_f32_read_attention_map(wd_f32* e, int which, int scale, float* dst, int* H, int* W, int* L, void* stream);
 int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream);
+/* ==== VAE decode: reference train.py:239-247, regenerateFromtrain2.py:624-636 --
+ *     latents = 1 / 0.18215 * x ; image = vae.decode(latents).sample ; image = (image / 2 + 0.5).clamp(0, 1)
+ * with vae = diffusers' AutoencoderKL (train.py:415).  The handle is a wd_f32 that holds the VAE's state_dict (load every
+ * `post_quant_conv.*` / `decoder.*` entry with wd_f32_load_param, free with wd_f32_destroy); the layer sequence is recovered from
+ * the keys.  wd_vae_decode: latents fp32 NCHW [n, 4, h, w] (multiplied by `scale`, the reference's 1 / 0.18215) ->
+ * images fp32 NCHW [n, 3, 8h, 8w]; postprocess != 0 applies the reference's (image / 2 + 0.5).clamp(0, 1).  The batch is walked in
+ * chunks of `chunk` latents (<= 0: 32) so the activation arena stays bounded. */
+int wd_vae_create(wd_f32** out);
+int wd_vae_decode(wd_f32* e, int n, const float* latents, int h, int w, float scale, int postprocess, float* images, int chunk,
+                  void* stream);
 int wd_f32_last_launch_count(const wd_f32* e);
 size_t wd_f32_workspace_bytes(const wd_f32* e);
 /* single operators of the fp32 path (parity tests): 3x3 conv pad 1 (stride 1|2, or nearest-2x upsampling first), fp32 NHWC,

@@ -1236,7 +1236,7 @@ struct PlanBuilder {
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
     const bool tb_ok = fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && x_in.f16 && s.heads * s.dh == TB_C;
-    if (tb_ok && !s.blocks[0].mid && HW % TB_M == 0 && x_in.C == TB_C && s.C == TB_C)
+    if (tb_ok && !s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2) && x_in.C == TB_C && s.C == TB_C)
       return st_block_fused(ops, s, s.blocks[0], x_in, g, out);
     if (tb_ok && s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2)) {
       // channels != 320 (the 4 x 16 level: 640): proj_in and proj_out as GEMMs around the kernel's middle form

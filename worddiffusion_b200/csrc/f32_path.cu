@@ -840,8 +840,10 @@ void attention(wd_f32* e, const float* q, size_t q_bs, int ldq, const float* k, 
     f32_attention_kernel<5><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
   else if (d <= 320)
     f32_attention_kernel<10><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
+  else if (d <= 512)  // the VAE decoder's single 512-wide head
+    f32_attention_kernel<16><<<grid, 256, 0, e->s>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, out, o_bs, ldo, B, Sq, Skv, heads, d, scale);
   else
-    fail(WD_ERR_UNSUPPORTED, "fp32 path: attention head width > 320");
+    fail(WD_ERR_UNSUPPORTED, "fp32 path: attention head width > 512");
   after_launch(e, "attention");
 }
 
@@ -1072,6 +1074,108 @@ int check_bad_flag(wd_f32* e, const char* what) {
   return WD_OK;
 }
 
+
+// =====================================================================================================
+// VAE decode (reference train.py:239-247, regenerateFromtrain2.py:624-636):
+//     latents = 1 / 0.18215 * x ; image = vae.decode(latents).sample ; image = (image / 2 + 0.5).clamp(0, 1)
+// `vae` is diffusers' AutoencoderKL of Stable Diffusion v1 (train.py:415, AutoencoderKL.from_pretrained(..., subfolder="vae")).
+// diffusers is not part of the reference tree (requirements only); its published decoder is restated here, layer sequence
+// recovered from the loaded state_dict keys:
+//     post_quant_conv (1x1) -> decoder.conv_in (3x3) -> mid_block: ResnetBlock2D, Attention (1 head over all pixels), ResnetBlock2D
+//     -> up_blocks.i: resnets.j (ResnetBlock2D: GroupNorm32(eps 1e-6)+SiLU, conv3x3, GroupNorm32+SiLU, conv3x3, + shortcut /
+//        1x1 conv_shortcut), upsamplers.0 (nearest x2 + conv3x3) -> conv_norm_out (GroupNorm32 + SiLU) -> conv_out (3x3)
+// fp32 storage and arithmetic on the kernels of this file.
+// =====================================================================================================
+__global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ out, int n, int C, size_t plane, float scale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n) * plane) return;
+  const size_t img = i / plane, p = i - img * plane;
+  const float* zi = z + img * C * plane + p;
+  float* oi = out + img * C * plane + p;
+  for (int o = 0; o < C; ++o) {
+    float acc = b ? b[o] : 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(w ? w[o * C + c] : (o == c ? 1.f : 0.f), zi[c * plane] * scale, acc);
+    oi[o * plane] = acc;
+  }
+}
+__global__ void vae_postprocess_kernel(float* __restrict__ img, size_t n) {  // (image / 2 + 0.5).clamp(0, 1), train.py:243
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) img[i] = fminf(fmaxf(img[i] / 2.f + 0.5f, 0.f), 1.f);
+}
+
+Act vae_resnet(wd_f32* e, const std::string& pfx, const Act& x, int B) {
+  Act n1 = groupnorm(e, pfx + "norm1", x, nullptr, B, 1e-6f, 1);
+  Act c1 = conv3x3(e, pfx + "conv1", n1, nullptr, B, nullptr, 0, nullptr, 1, 0);
+  Act n2 = groupnorm(e, pfx + "norm2", c1, nullptr, B, 1e-6f, 1);
+  const float* res = x.p;
+  if (has(e, pfx + "conv_shortcut.weight")) res = linear(e, pfx + "conv_shortcut", x, B, true).p;
+  else if (has(e, pfx + "nin_shortcut.weight")) res = linear(e, pfx + "nin_shortcut", x, B, true).p;
+  return conv3x3(e, pfx + "conv2", n2, nullptr, B, nullptr, 0, res, 1, 0);
+}
+
+Act vae_attention(wd_f32* e, const std::string& pfx, const Act& x, int B) {
+  // diffusers >= 0.15 names the projections to_q / to_k / to_v / to_out.0, older checkpoints query / key / value / proj_attn
+  const bool new_names = has(e, pfx + "to_q.weight");
+  const std::string nq = new_names ? "to_q" : "query", nk = new_names ? "to_k" : "key", nv = new_names ? "to_v" : "value",
+                    no = new_names ? "to_out.0" : "proj_attn";
+  Act n = groupnorm(e, pfx + "group_norm", x, nullptr, B, 1e-6f, 0);
+  Act q = linear(e, pfx + nq, n, B, true);
+  Act k = linear(e, pfx + nk, n, B, true);
+  Act v = linear(e, pfx + nv, n, B, true);
+  const int S = x.H * x.W, C = q.C;
+  Act o = q;
+  o.p = alloc(e, static_cast<size_t>(B) * S * C);
+  attention(e, q.p, static_cast<size_t>(S) * C, C, k.p, v.p, static_cast<size_t>(S) * C, C, o.p, static_cast<size_t>(S) * C, C, B, S, S, 1,
+            C, 1.0f / sqrtf(static_cast<float>(C)));
+  return linear(e, pfx + no, o, B, true, x.p);
+}
+
+void vae_decode_impl(wd_f32* e, int B, const float* latents, int h, int w, float scale, int postprocess, float* images) {
+  const Param& cin = P(e, "decoder.conv_in.weight");
+  const int zc = static_cast<int>(cin.shape[1]);
+  if (zc != 4) fail(WD_ERR_UNSUPPORTED, "vae decode: latent_channels must be 4");
+  const size_t plane = static_cast<size_t>(h) * w;
+  float* z = alloc(e, static_cast<size_t>(B) * zc * plane);
+  if (!e->dry) {
+    const bool pq = has(e, "post_quant_conv.weight");
+    const size_t tot = static_cast<size_t>(B) * plane;
+    vae_post_quant_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, e->s>>>(
+        latents, pq ? P(e, "post_quant_conv.weight").p : nullptr, pq ? P(e, "post_quant_conv.bias").p : nullptr, z, B, zc, plane, scale);
+    after_launch(e, "vae post_quant_conv");
+  }
+  Act zin;
+  zin.p = z;
+  zin.H = h;
+  zin.W = w;
+  zin.C = zc;
+  ConvSpec cs;
+  cs.taps = 9;
+  cs.a_nchw = 1;
+  Act x = gemm(e, zin, nullptr, B, cin.p, static_cast<int>(cin.shape[0]), P(e, "decoder.conv_in.bias").p, nullptr, 0, nullptr, cs);
+  x = vae_resnet(e, "decoder.mid_block.resnets.0.", x, B);
+  if (has(e, "decoder.mid_block.attentions.0.group_norm.weight")) x = vae_attention(e, "decoder.mid_block.attentions.0.", x, B);
+  x = vae_resnet(e, "decoder.mid_block.resnets.1.", x, B);
+  for (int i = 0; has(e, "decoder.up_blocks." + std::to_string(i) + ".resnets.0.norm1.weight"); ++i) {
+    const std::string bp = "decoder.up_blocks." + std::to_string(i) + ".";
+    for (int j = 0; has(e, bp + "resnets." + std::to_string(j) + ".norm1.weight"); ++j)
+      x = vae_resnet(e, bp + "resnets." + std::to_string(j) + ".", x, B);
+    if (has(e, bp + "upsamplers.0.conv.weight")) x = conv3x3(e, bp + "upsamplers.0.conv", x, nullptr, B, nullptr, 0, nullptr, 1, 1);
+  }
+  Act n = groupnorm(e, "decoder.conv_norm_out", x, nullptr, B, 1e-6f, 1);
+  const Param& cout = P(e, "decoder.conv_out.weight");
+  if (!cout.packed3x3 || cout.shape[1] != n.C) fail(WD_ERR_INVALID, "vae decode: decoder.conv_out does not match the last block");
+  ConvSpec co;
+  co.taps = 9;
+  co.out_nchw = 1;
+  Act img = gemm(e, n, nullptr, B, cout.p, static_cast<int>(cout.shape[0]), P(e, "decoder.conv_out.bias").p, nullptr, 0, nullptr, co, images);
+  if (postprocess && !e->dry) {
+    const size_t tot = static_cast<size_t>(B) * img.C * img.H * img.W;
+    vae_postprocess_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, e->s>>>(images, tot);
+    after_launch(e, "vae postprocess");
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -1276,6 +1380,57 @@ int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream) {
   if (bytes != have) return wd_set_error(WD_ERR_INVALID, "wd_f32_read_context: size mismatch");
   if (cudaMemcpyAsync(dst, e->ctx, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
     return wd_set_error(WD_ERR_CUDA, "wd_f32_read_context: copy failed");
+  return WD_OK;
+}
+
+
+/* ---- VAE decode (AutoencoderKL decoder) ---- */
+int wd_vae_create(wd_f32** out) {
+  if (!out) return wd_set_error(WD_ERR_INVALID, "wd_vae_create: null argument");
+  int dev = 0;
+  cudaDeviceProp prop{};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_vae_create: no CUDA device");
+  if (prop.major != 10) return wd_set_error(WD_ERR_UNSUPPORTED, "wd_vae_create: libwd_b200 is built for sm_100a only");
+  wd_f32* e = new wd_f32();
+  *out = e;
+  return WD_OK;
+}
+
+int wd_vae_decode(wd_f32* e, int n, const float* latents, int h, int w, float scale, int postprocess, float* images, int chunk,
+                  void* stream) {
+  if (!e || !latents || !images || n < 0 || h <= 0 || w <= 0) return wd_set_error(WD_ERR_INVALID, "wd_vae_decode: invalid argument");
+  if (chunk <= 0) chunk = 32;
+  e->s = static_cast<cudaStream_t>(stream);
+  try {
+    int ups = 0, out_c = 3;
+    for (int i = 0; has(e, "decoder.up_blocks." + std::to_string(i) + ".resnets.0.norm1.weight"); ++i)
+      if (has(e, "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv.weight")) ++ups;
+    out_c = static_cast<int>(P(e, "decoder.conv_out.weight").shape[0]);
+    const size_t in_stride = static_cast<size_t>(4) * h * w;
+    const size_t out_stride = static_cast<size_t>(out_c) * (static_cast<size_t>(h) << ups) * (static_cast<size_t>(w) << ups);
+    e->launches = 0;
+    for (int b0 = 0; b0 < n; b0 += chunk) {
+      const int B = n - b0 < chunk ? n - b0 : chunk;
+      e->dry = true;
+      e->arena_off = 0;
+      vae_decode_impl(e, B, latents + b0 * in_stride, h, w, scale, postprocess, images + b0 * out_stride);
+      const int rc = ensure_arena(e, e->arena_off);
+      if (rc != WD_OK) {
+        e->dry = false;
+        return rc;
+      }
+      e->dry = false;
+      e->arena_off = 0;
+      vae_decode_impl(e, B, latents + b0 * in_stride, h, w, scale, postprocess, images + b0 * out_stride);
+    }
+  } catch (const Fail& f) {
+    e->dry = false;
+    return finish(e, f);
+  } catch (const std::exception& ex) {
+    e->dry = false;
+    return wd_set_error(WD_ERR_STATE, ex.what());
+  }
   return WD_OK;
 }
 
