@@ -251,6 +251,23 @@ int wd_f32_unet_eval_maps(wd_f32* e, int batch, const float* x, const int64_t* t
                           float* eps_out, void* stream);
 int wd_f32_read_attention_map(wd_f32* e, int which, int scale, float* dst, int* H, int* W, int* L, void* stream);
 int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream);
+/* ==== variants of unet.UNetModel ====
+ * wd_set_context / wd_f32_set_context: the context as a dense fp32 tensor [batch, L, context_dim] instead of tokens -- the
+ *   reference's args.wrdChrWrStyl == 1 path, context = wrd_proj(wrdChrWrStyl) (unet.py:1590-1591,1617-1618); replaces
+ *   wd_encode_context / wd_f32_encode_context for that trajectory.  wd_f32_op_linear: the projection itself in fp32.
+ * wd_engine_set_label_mix / wd_f32_set_label_mix: label_emb.weight[row] = (1 - mix) w[s1] + mix w[s2], the style interpolation of
+ *   args.interpolation (unet.py:1558-1572); `row` is a scratch class (the module creates its engines with one class more).
+ * wd_f32_ctc_head: tdec = auxhead(eps) of args.ocrTraining == 1 (CTCtopC, unet.py:1054-1092,1829) in eval mode,
+ *   eps fp32 NCHW [batch, C, H, W] -> out fp32 [256, batch, nclasses]. */
+int wd_set_context(wd_engine* e, int batch, const float* ctx_f32, int L, void* stream);
+/* out = torch.lerp(start, end, weight), fp32 (train.py:226-228: the guidance mix of two evaluations) */
+int wd_lerp(const float* start, const float* end, float weight, float* out, size_t n, void* stream);
+int wd_engine_set_label_mix(wd_engine* e, int row, int s1, int s2, float mix, void* stream);
+int wd_f32_set_context(wd_f32* e, int batch, const float* ctx, int L, void* stream);
+int wd_f32_set_label_mix(wd_f32* e, int row, int s1, int s2, float mix, void* stream);
+int wd_f32_ctc_head(wd_f32* e, int batch, const float* eps, int C, int H, int W, float* out, void* stream);
+int wd_f32_op_linear(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, void* stream);
+
 /* ==== VAE decode: reference train.py:239-247, regenerateFromtrain2.py:624-636 --
  *     latents = 1 / 0.18215 * x ; image = vae.decode(latents).sample ; image = (image / 2 + 0.5).clamp(0, 1)
  * with vae = diffusers' AutoencoderKL (train.py:415).  The handle is a wd_f32 that holds the VAE's state_dict (load every

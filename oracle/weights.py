@@ -54,3 +54,32 @@ def make_inputs(B, seed=1234, L=10, phosc_len=769, vocab=53, num_classes=339, la
     phoc = (torch.rand((B, phosc_len - 165), generator=g) < 0.05).long()
     phosc = torch.cat([phos, phoc], dim=1)
     return dict(x=x, t=t, context=ctx, y=y, phosc=phosc)
+
+
+def variant_state_dict(spec, rename=None, seed=1234):
+    """Fixture weights of a flag variant of unet.UNetModel (oracle/make_golden_variants.py): the keys shared with the plain model
+    carry the seed-1234 unet fixture (optionally renamed, e.g. to the attentionMaps = 1 layout), the new ones (auxhead.*,
+    conv_layer*.*) come from the same generator with seed 4321; BatchNorm running_var is made positive, num_batches_tracked = 3."""
+    base = make_state_dict(load_spec("unet"), seed)
+    if rename:
+        base = {rename(k): v for k, v in base.items()}
+    spec = [(k, tuple(s)) for k, s in spec]
+    extra = make_state_dict([(k, s) for k, s in spec if k not in base], seed=4321)
+    for k, v in extra.items():
+        if k.endswith("running_var"):
+            extra[k] = v.abs() + 0.5
+        elif k.endswith("num_batches_tracked"):
+            extra[k] = torch.tensor(3, dtype=torch.int64)
+    sd = dict(base)
+    sd.update(extra)
+    assert sorted(sd) == sorted(k for k, _ in spec)
+    return sd
+
+
+def rename_to_attnmaps(key):
+    """middle_block.{0,1,2}.* (attentionMaps = 0) -> middle_block1.{0.0,0.1,1.0}.* (attentionMaps = 1, unet.py:1336-1364)."""
+    for old, new in (("middle_block.0.", "middle_block1.0.0."), ("middle_block.1.", "middle_block1.0.1."),
+                     ("middle_block.2.", "middle_block1.1.0.")):
+        if key.startswith(old):
+            return new + key[len(old):]
+    return key

@@ -36,9 +36,23 @@ def test_fresh_model_has_reference_zero_init():
     assert float(sd["input_blocks.1.0.in_layers.2.weight"].abs().max()) > 0
 
 
+def test_flag_variant_layouts_match_reference():
+    """args.ocrTraining / args.charImages change the reference's key set (unet.py:1468,1217-1223): same keys, order and shapes as
+    the reference modules built with those flags (tests/golden/state_dict_spec_unet_variants.json, oracle/make_golden_variants.py)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_spec_unet_variants.json")) as f:
+        specs = json.load(f)
+    for name, flags in (("ocr", dict(attentionMaps=1, ocrTraining=1)), ("charimg", dict(charImages=1))):
+        m = UNetModel(args=default_args("cpu", **flags), **KW)
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == specs[name], name
+    for flags in (dict(charLevelEmb=1), dict(wrdChrWrStyl=1), dict(interpolation=True)):
+        m = UNetModel(args=default_args("cpu", **flags), **KW)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == W.load_spec("unet")
+
+
 def test_unsupported_configurations_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        UNetModel(args=default_args("cpu", ocrTraining=1), **KW)
     with pytest.raises(NotImplementedError):
         UNetModel(args=default_args("cpu"), **dict(KW, use_scale_shift_norm=True))
     with pytest.raises(NotImplementedError):

@@ -90,6 +90,13 @@ SIGNATURES = {
     "wd_f32_unet_eval_maps": (_I, [_P, _I, _P, _P, _I64, _P, _P, _P]),
     "wd_f32_read_attention_map": (_I, [_P, _I, _I, _P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _P]),
     "wd_f32_read_context": (_I, [_P, _P, C.c_size_t, _P]),
+    "wd_set_context": (_I, [_P, _I, _P, _I, _P]),
+    "wd_lerp": (_I, [_P, _P, _F, _P, C.c_size_t, _P]),
+    "wd_engine_set_label_mix": (_I, [_P, _I, _I, _I, _F, _P]),
+    "wd_f32_set_context": (_I, [_P, _I, _P, _I, _P]),
+    "wd_f32_set_label_mix": (_I, [_P, _I, _I, _I, _F, _P]),
+    "wd_f32_ctc_head": (_I, [_P, _I, _P, _I, _I, _I, _P, _P]),
+    "wd_f32_op_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "wd_vae_create": (_I, [C.POINTER(_P)]),
     "wd_vae_decode": (_I, [_P, _I, _P, _I, _I, _F, _I, _P, _I, _P]),
     "wd_f32_last_launch_count": (_I, [_P]),

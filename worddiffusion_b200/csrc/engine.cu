@@ -186,6 +186,7 @@ struct Plan {
   std::vector<Op> step_ops;
   size_t bytes = 0;
   bool context_valid = false;
+  bf16* ctx_buf = nullptr;  // encoded context [B, Ltot, context_dim] (wd_set_context writes it directly)
   // CUDA graphs of the step launch sequence, each valid for one set of caller pointers: g_step for wd_sampler_step (the
   // per-step scalars live in wd_engine::sp_dev), g_eval for wd_unet_eval with per-row timesteps (the forward() path).
   // `seen` counts consecutive calls with the same pointers: the first runs eagerly, the second captures, later ones replay.
@@ -652,6 +653,10 @@ bool is_dead_param(const std::string& n, int variant) {
   if (n.find(".to_kv.") != std::string::npos) return true;
   if (n.rfind("res.", 0) == 0) return true;
   if (n.rfind("wrd_proj.", 0) == 0) return true;
+  // args.ocrTraining == 1 / args.charImages == 1 (unet.py:1468,1217-1223): the OCR head reads the UNet's output (wd_f32_ctc_head),
+  // the character-image convolutions feed a value the reference forward discards (unet.py:1625-1627)
+  if (n.rfind("auxhead.", 0) == 0 || n.rfind("conv_layer1.", 0) == 0 || n.rfind("conv_layer2.", 0) == 0 || n.rfind("conv_layer3.", 0) == 0)
+    return true;
   if (variant == WD_VARIANT_UNET && n.find(".norm1.") != std::string::npos) return true;
   if (variant == WD_VARIANT_PHOSC) {
     // the self-attention's to_k/to_v are used; nothing else is dead
@@ -1395,6 +1400,7 @@ struct PlanBuilder {
 
     // ================= context (time-invariant) =================
     bf16* ctx = A.alloc<bf16>(static_cast<size_t>(B) * Ltot * D);
+    plan->ctx_buf = ctx;
     {
       const int nseg = c.phosc_len > 0 ? 2 : 1;
       for (int seg = 0; seg < nseg; ++seg) {
@@ -1879,6 +1885,48 @@ extern "C" int wd_encode_context(wd_engine* e, int batch, const int64_t* ctx_tok
   rc = run_ops(e, p->ctx_ops, r, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   p->context_valid = true;
+  return WD_OK;
+}
+
+// The context given directly as a dense fp32 tensor [batch, L, context_dim] instead of character tokens: the reference's
+// args.wrdChrWrStyl == 1 path replaces word_emb(context) by wrd_proj(wrdChrWrStyl) (unet.py:1590-1591,1617-1618).  Runs the
+// time-invariant part that follows the context encoder (K/V projections, fused-block operands).
+extern "C" int wd_set_context(wd_engine* e, int batch, const float* ctx_f32, int L, void* stream) {
+  if (!e || !ctx_f32) return fail(WD_ERR_INVALID, "null argument");
+  if (e->cfg.phosc_len > 0) return fail(WD_ERR_UNSUPPORTED, "wd_set_context: the PHOSC variants build their context from tokens");
+  Plan* p = nullptr;
+  int rc = ensure_plan(e, batch, L, &p);
+  if (rc) return rc;
+  e->cur = p;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(repack_linear_launch(ctx_f32, p->ctx_buf, batch * p->Ltot, e->cfg.context_dim, e->cfg.context_dim, 0, 0, 0, 0, s));
+  std::vector<Op> rest;
+  for (const Op& op : p->ctx_ops)
+    if (op.kind != OP_EMBED && op.kind != OP_WORDATTN) rest.push_back(op);
+  RunCtx r;
+  rc = run_ops(e, rest, r, s);
+  if (rc) return rc;
+  p->context_valid = true;
+  return WD_OK;
+}
+
+// label_emb.weight[row] = (1 - mix) * label_emb.weight[s1] + mix * label_emb.weight[s2]: the style interpolation of
+// args.interpolation (unet.py:1558-1572) with the reference's rounding (two products, one sum).  `row` is a scratch row of the
+// table (the drop-in module creates the engine with one more class than the model has).
+extern "C" int wd_engine_set_label_mix(wd_engine* e, int row, int s1, int s2, float mix, void* stream) {
+  if (!e || !e->label_emb) return fail(WD_ERR_STATE, "wd_engine_set_label_mix: the model has no label embedding");
+  const int n = e->cfg.num_classes;
+  if (row < 0 || row >= n || s1 < 0 || s1 >= n || s2 < 0 || s2 >= n) return fail(WD_ERR_INVALID, "wd_engine_set_label_mix: class out of range");
+  CUDA_TRY(label_mix_launch(e->label_emb, e->time_dim, row, s1, s2, mix, static_cast<cudaStream_t>(stream)));
+  if (e->cur) {  // captured graphs read the table by pointer: nothing to refresh
+  }
+  return WD_OK;
+}
+
+// out = torch.lerp(start, end, weight) on fp32 device tensors (train.py:228: predicted_noise = lerp(uncond, cond, cfg_scale))
+extern "C" int wd_lerp(const float* start, const float* end, float weight, float* out, size_t n, void* stream) {
+  if (!start || !end || !out) return fail(WD_ERR_INVALID, "wd_lerp: null argument");
+  if (n) CUDA_TRY(lerp_launch(start, end, weight, out, n, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }
 

@@ -1075,6 +1075,66 @@ int check_bad_flag(wd_f32* e, const char* what) {
 }
 
 
+
+// =====================================================================================================
+// OCR head of args.ocrTraining == 1 (CTCtopC, unet.py:1054-1092) in eval mode: four (1 x 5) convolutions with BatchNorm (running
+// statistics) + ReLU, a (1 x 5) convolution to the classes, Linear(32, 128) and Linear(128, 256) along the width, and
+// `y.permute(2, 3, 0, 1)[0]`: only image row 0 leaves the head, and no layer mixes rows, so only row 0 is computed.
+// Activations [B, W, C] (token-major); weights as stored ([Cout, Cin, 1, 5]).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) ctc_conv1x5_kernel(const float* __restrict__ x, int x_nchw_H, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                          const float* __restrict__ bn_b, const float* __restrict__ bn_rm,
+                                                          const float* __restrict__ bn_rv, float* __restrict__ out, int B, int W,
+                                                          int Cin, int Cout) {
+  // one thread per (b, w, co); x_nchw_H > 0: x is the NCHW tensor [B, Cin, H, W], row 0 is read
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * W * Cout) return;
+  const int co = static_cast<int>(idx % Cout);
+  const int wq = static_cast<int>((idx / Cout) % W);
+  const int b = static_cast<int>(idx / (static_cast<size_t>(Cout) * W));
+  float acc = bias[co];
+  for (int tap = 0; tap < 5; ++tap) {
+    const int wi = wq + tap - 2;
+    if (wi < 0 || wi >= W) continue;
+    const float* wr = w + static_cast<size_t>(co) * Cin * 5 + tap;
+    if (x_nchw_H > 0) {
+      for (int ci = 0; ci < Cin; ++ci)
+        acc = fmaf(x[((static_cast<size_t>(b) * Cin + ci) * x_nchw_H) * W + wi], wr[ci * 5], acc);
+    } else {
+      const float* xr = x + (static_cast<size_t>(b) * W + wi) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xr[ci], wr[ci * 5], acc);
+    }
+  }
+  if (bn_w) {  // BatchNorm2d in eval mode (eps 1e-5) + ReLU
+    acc = (acc - bn_rm[co]) / sqrtf(bn_rv[co] + 1e-5f) * bn_w[co] + bn_b[co];
+    acc = fmaxf(acc, 0.f);
+  }
+  out[idx] = acc;
+}
+// t [B, W = 32, C] -> lin1 over the width -> lin2 -> out [256, B, C]; one CTA per (b, c)
+__global__ void __launch_bounds__(256) ctc_lin_kernel(const float* __restrict__ t, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
+                                                      int B, int W, int C, int N1, int N2) {
+  extern __shared__ float sm[];
+  float* row = sm;        // [W]
+  float* y1 = sm + W;     // [N1]
+  const int b = blockIdx.x / C, c = blockIdx.x % C;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) row[i] = t[(static_cast<size_t>(b) * W + i) * C + c];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N1; j += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < W; ++i) acc = fmaf(row[i], w1[j * W + i], acc);
+    y1[j] = acc + b1[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < N1; ++i) acc = fmaf(y1[i], w2[j * N1 + i], acc);
+    out[(static_cast<size_t>(j) * B + b) * C + c] = acc + b2[j];
+  }
+}
+
 // =====================================================================================================
 // VAE decode (reference train.py:239-247, regenerateFromtrain2.py:624-636):
 //     latents = 1 / 0.18215 * x ; image = vae.decode(latents).sample ; image = (image / 2 + 0.5).clamp(0, 1)
@@ -1383,6 +1443,114 @@ int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream) {
   return WD_OK;
 }
 
+
+/* ---- variants of unet.UNetModel: dense context, style interpolation, OCR head ---- */
+int wd_f32_set_context(wd_f32* e, int batch, const float* ctx, int L, void* stream) {
+  if (!e || !ctx || batch <= 0 || L <= 0) return wd_set_error(WD_ERR_INVALID, "wd_f32_set_context: invalid argument");
+  const size_t need = static_cast<size_t>(batch) * L * e->cfg.context_dim;
+  if (need > e->ctx_cap) {
+    cudaDeviceSynchronize();
+    cudaFree(e->ctx);
+    e->ctx = nullptr;
+    e->ctx_cap = 0;
+    if (cudaMalloc(&e->ctx, need * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_set_context: cudaMalloc failed");
+    e->ctx_cap = need;
+  }
+  if (cudaMemcpyAsync(e->ctx, ctx, need * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return wd_set_error(WD_ERR_CUDA, "wd_f32_set_context: copy failed");
+  e->ctx_B = batch;
+  e->ctx_L = L;
+  return WD_OK;
+}
+
+__global__ void f32_label_mix_kernel(float* __restrict__ w, int D, int row, int s1, int s2, float mix) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  w[static_cast<size_t>(row) * D + c] =
+      __fadd_rn(__fmul_rn(1.0f - mix, w[static_cast<size_t>(s1) * D + c]), __fmul_rn(mix, w[static_cast<size_t>(s2) * D + c]));
+}
+int wd_f32_set_label_mix(wd_f32* e, int row, int s1, int s2, float mix, void* stream) {
+  if (!e || !e->params.count("label_emb.weight")) return wd_set_error(WD_ERR_STATE, "wd_f32_set_label_mix: no label embedding loaded");
+  const Param& p = e->params["label_emb.weight"];
+  const int n = static_cast<int>(p.shape[0]), D = static_cast<int>(p.shape[1]);
+  if (row < 0 || row >= n || s1 < 0 || s1 >= n || s2 < 0 || s2 >= n) return wd_set_error(WD_ERR_INVALID, "wd_f32_set_label_mix: class out of range");
+  f32_label_mix_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.p, D, row, s1, s2, mix);
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+/* tdec = auxhead(eps) of args.ocrTraining == 1 (CTCtopC, unet.py:1054-1092,1829) in eval mode: eps fp32 NCHW [B, C, H, W = 32]
+ * -> out fp32 [256, B, nclasses].  The auxhead.* entries must have been loaded with wd_f32_load_param. */
+int wd_f32_ctc_head(wd_f32* e, int batch, const float* eps, int C, int H, int W, float* out, void* stream) {
+  if (!e || !eps || !out || batch <= 0) return wd_set_error(WD_ERR_INVALID, "wd_f32_ctc_head: invalid argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float *a = nullptr, *b = nullptr;
+  int rc = WD_OK;
+  try {
+    const Param& wi = P(e, "auxhead.temporal_i.0.weight");
+    const int hid = static_cast<int>(wi.shape[0]);
+    if (wi.shape.size() != 4 || wi.shape[1] != C || wi.shape[2] != 1 || wi.shape[3] != 5) fail(WD_ERR_INVALID, "ctc head: temporal_i shape");
+    const Param& l1 = P(e, "auxhead.lin1.weight");
+    const Param& l2 = P(e, "auxhead.lin2.weight");
+    if (l1.shape[1] != W || l2.shape[1] != l1.shape[0]) fail(WD_ERR_INVALID, "ctc head: lin1 expects the latent width (32)");
+    const Param& wo = P(e, "auxhead.temporal_o.weight");
+    const int ncls = static_cast<int>(wo.shape[0]);
+    const size_t n_act = static_cast<size_t>(batch) * W * (hid > ncls ? hid : ncls);
+    if (cudaMalloc(&a, n_act * sizeof(float)) != cudaSuccess || cudaMalloc(&b, n_act * sizeof(float)) != cudaSuccess)
+      fail(WD_ERR_CUDA, "ctc head: cudaMalloc failed");
+    auto conv = [&](const float* x, int nchw_h, const std::string& cw, const std::string& bn, float* o, int cin, int cout) {
+      const size_t tot = static_cast<size_t>(batch) * W * cout;
+      const bool has_bn = !bn.empty();
+      ctc_conv1x5_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(
+          x, nchw_h, P(e, cw + ".weight").p, P(e, cw + ".bias").p, has_bn ? P(e, bn + ".weight").p : nullptr,
+          has_bn ? P(e, bn + ".bias").p : nullptr, has_bn ? P(e, bn + ".running_mean").p : nullptr,
+          has_bn ? P(e, bn + ".running_var").p : nullptr, o, batch, W, cin, cout);
+      if (cudaGetLastError() != cudaSuccess) fail(WD_ERR_CUDA, "ctc head: conv launch failed");
+    };
+    conv(eps, H, "auxhead.temporal_i.0", "auxhead.temporal_i.1", a, C, hid);
+    float *cur = a, *nxt = b;
+    for (int i = 0; has(e, "auxhead.temporal_m." + std::to_string(i) + ".0.weight"); ++i) {
+      const std::string pfx = "auxhead.temporal_m." + std::to_string(i);
+      conv(cur, 0, pfx + ".0", pfx + ".1", nxt, hid, hid);
+      std::swap(cur, nxt);
+    }
+    conv(cur, 0, "auxhead.temporal_o", "", nxt, hid, ncls);
+    const int N1 = static_cast<int>(l1.shape[0]), N2 = static_cast<int>(l2.shape[0]);
+    ctc_lin_kernel<<<batch * ncls, 256, (W + N1) * sizeof(float), s>>>(nxt, l1.p, P(e, "auxhead.lin1.bias").p, l2.p,
+                                                                      P(e, "auxhead.lin2.bias").p, out, batch, W, ncls, N1, N2);
+    if (cudaGetLastError() != cudaSuccess) fail(WD_ERR_CUDA, "ctc head: linear launch failed");
+  } catch (const Fail& f) {
+    rc = wd_set_error(f.code, f.msg.c_str());
+  } catch (const std::exception& ex) {
+    rc = wd_set_error(WD_ERR_STATE, ex.what());
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(a);
+  cudaFree(b);
+  return rc;
+}
+
+/* out[M, N] = x[M, K] w[N, K]^T + bias, fp32 FFMA (wrd_proj of args.wrdChrWrStyl == 1, unet.py:1590-1591) */
+int wd_f32_op_linear(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, void* stream) {
+  if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || (K & 3)) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_linear: invalid argument");
+  GemmF32 g{};
+  g.a1 = x;
+  g.C1 = K;
+  g.taps = 1;
+  g.Hin = g.Win = g.Hout = g.Wout = 1;
+  g.stride = 1;
+  g.w = w;
+  g.bias = bias;
+  g.out = out;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  launch_gemm(g, static_cast<cudaStream_t>(stream));
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
 
 /* ---- VAE decode (AutoencoderKL decoder) ---- */
 int wd_vae_create(wd_f32** out) {

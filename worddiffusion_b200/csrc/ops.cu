@@ -402,6 +402,32 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
   return launch_pdl(groupnorm_apply_kernel, dim3(B, nslab, a.nchunk), dim3(nv * R), 0, s, a);
 }
 
+// torch.lerp(start, end, weight) with torch's formula (weight < 0.5 ? start + weight (end - start) : end - (end - start)(1 - weight)):
+// the classifier-free-guidance mix of train.py:226-228
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float w, float* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = __fsub_rn(b[i], a[i]);
+  out[i] = (fabsf(w) < 0.5f) ? __fadd_rn(a[i], __fmul_rn(w, d)) : __fsub_rn(b[i], __fmul_rn(d, 1.0f - w));
+}
+cudaError_t lerp_launch(const float* a, const float* b, float w, float* out, size_t n, cudaStream_t s) {
+  lerp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(a, b, w, out, n);
+  return cudaGetLastError();
+}
+
+// label_emb.weight[row] = (1 - mix) * w[s1] + mix * w[s2] with the reference's roundings (unet.py:1568)
+__global__ void label_mix_kernel(float* __restrict__ w, int D, int row, int s1, int s2, float mix) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const float a = __fmul_rn(1.0f - mix, w[static_cast<size_t>(s1) * D + c]);
+  const float b = __fmul_rn(mix, w[static_cast<size_t>(s2) * D + c]);
+  w[static_cast<size_t>(row) * D + c] = __fadd_rn(a, b);
+}
+cudaError_t label_mix_launch(float* table, int D, int row, int s1, int s2, float mix, cudaStream_t s) {
+  label_mix_kernel<<<(D + 255) / 256, 256, 0, s>>>(table, D, row, s1, s2, mix);
+  return cudaGetLastError();
+}
+
 // =====================================================================================================
 // LayerNorm: one warp per token, fp32 two-pass in registers, bf16 in/out.
 // =====================================================================================================

@@ -42,6 +42,9 @@ struct GroupNormArgs {
 int groupnorm_apply_chunks(int HW);  // pixel chunks per sample of the apply grid (GroupNormArgs::nchunk)
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
 
+cudaError_t lerp_launch(const float* a, const float* b, float w, float* out, size_t n, cudaStream_t s);
+cudaError_t label_mix_launch(float* table, int D, int row, int s1, int s2, float mix, cudaStream_t s);
+
 // ---------------- LayerNorm over the channel dim, bf16 -> bf16 (unet.py:314-316) ----------------
 cudaError_t layernorm_launch(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta, int M,
                              int C, float eps, int x_f16, cudaStream_t s);

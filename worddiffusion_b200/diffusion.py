@@ -182,16 +182,40 @@ class Diffusion:
     def sampling(self, model, vae, n, x_text, labels, args=None, mix_rate=None, cfg_scale=3, phosc=None, seed=0):
         """Same call shape as train.Diffusion.sampling (train.py:200-251).  The VAE decode at the end is outside the hot
         path: with ``vae=None`` the scaled latents ``x / 0.18215`` are returned instead of images."""
-        if mix_rate is not None:
-            raise NotImplementedError("style interpolation (mix_rate) is not implemented")
         toks = torch.tensor([label_padding(x_text)] * n, dtype=torch.int64, device=self.device)
-        x = self.sample_latents(model, toks, labels, phosc=phosc, seed=seed)
-        latents = 1 / 0.18215 * x
+        if mix_rate is not None:
+            x = self._sample_latents_mixed(model, toks, labels, mix_rate, cfg_scale, seed)
+        else:
+            x = self.sample_latents(model, toks, labels, phosc=phosc, seed=seed)
         if vae is None:
-            return latents
-        image = vae.decode(latents).sample
-        image = (image / 2 + 0.5).clamp(0, 1)
-        return image
+            return 1 / 0.18215 * x
+        from .vae import AutoencoderKL
+        if isinstance(vae, AutoencoderKL):
+            # train.py:239-243 in one call: 1 / 0.18215 scaling, decode, (image / 2 + 0.5).clamp(0, 1)
+            return vae.decode(x, scale=1 / 0.18215, postprocess=True).sample
+        image = vae.decode(1 / 0.18215 * x).sample  # a foreign (e.g. diffusers) autoencoder: the reference's own sequence
+        return (image / 2 + 0.5).clamp(0, 1)
+
+    def _sample_latents_mixed(self, model, toks, labels, mix_rate, cfg_scale, seed):
+        """Style interpolation (args.interpolation, train.py:221-236 with mix_rate): the reference evaluates the model TWICE per
+        step, each call drawing its own random writer pair (unet.py:1561-1570), and lerps the two predictions with cfg_scale."""
+        from ._lib import check, lib
+        from .engine import _ptr, _stream_ptr
+        n = toks.shape[0]
+        h, w = self.img_size[0] // 8, self.img_size[1] // 8
+        x = philox_normal_latents(n, (4, h, w), seed, 0, self.device)
+        eng = model.engine(self.device, latent_hw=(h, w))
+        y = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        for i in reversed(range(1, self.noise_steps)):
+            t = torch.full((n,), i, device=self.device, dtype=torch.int64)
+            eps = model(x, None, timesteps=t, context=toks, y=y, mix_rate=mix_rate)
+            if cfg_scale > 0:
+                unc = model(x, None, timesteps=t, context=toks, y=y, mix_rate=mix_rate)
+                with torch.cuda.device(self.device):
+                    check(lib().wd_lerp(_ptr(unc), _ptr(eps), float(cfg_scale), _ptr(eps), eps.numel(), _stream_ptr()), "wd_lerp")
+            eng.sampler_update(x, eps, STEP_DDPM, self._ddpm_coef[i], philox_seed=(seed if i > 1 else None), sample_offset=0,
+                               step_index=i)
+        return x
 
     # ------------------------------------------------------------------ multi-GPU: shard the batch, gather the latents
     @torch.no_grad()

@@ -129,6 +129,22 @@ class HotPathEngine:
         self._ctx_key = key
         self._ctx_dirty = False
 
+    def set_context(self, ctx_dense):
+        """Dense fp32 context [B, L, context_dim] in place of tokens (args.wrdChrWrStyl == 1, unet.py:1617-1618)."""
+        ctx = ctx_dense.to(device=self.device, dtype=torch.float32).contiguous()
+        B, L, D = ctx.shape
+        if D != self.cfg.context_dim:
+            raise _lib.WdError(f"dense context must be [B, L, {self.cfg.context_dim}], got {tuple(ctx.shape)}")
+        with torch.cuda.device(self.device):
+            check(lib().wd_set_context(self._h, B, _ptr(ctx), L, _stream_ptr()), "wd_set_context")
+        self._ctx_hold = (ctx, None)
+        self._ctx_key = None
+
+    def set_label_mix(self, row, s1, s2, mix):
+        with torch.cuda.device(self.device):
+            check(lib().wd_engine_set_label_mix(self._h, int(row), int(s1), int(s2), float(mix), _stream_ptr()),
+                  "wd_engine_set_label_mix")
+
     def unet_eval(self, x, timesteps, y, out=None):
         B = x.shape[0]
         if out is None:
@@ -260,6 +276,30 @@ class F32Engine:
         with torch.cuda.device(self.device):
             check(lib().wd_f32_encode_context(self._h, B, _ptr(ctx), L, _ptr(ph), _stream_ptr()), "wd_f32_encode_context")
         self._ctx_key = key
+
+    def set_context(self, ctx_dense):
+        ctx = ctx_dense.to(device=self.device, dtype=torch.float32).contiguous()
+        B, L, D = ctx.shape
+        if D != self.cfg.context_dim:
+            raise _lib.WdError(f"dense context must be [B, L, {self.cfg.context_dim}], got {tuple(ctx.shape)}")
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_set_context(self._h, B, _ptr(ctx), L, _stream_ptr()), "wd_f32_set_context")
+        self._ctx_key = None
+
+    def set_label_mix(self, row, s1, s2, mix):
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_set_label_mix(self._h, int(row), int(s1), int(s2), float(mix), _stream_ptr()),
+                  "wd_f32_set_label_mix")
+
+    def ctc_head(self, eps):
+        """tdec = auxhead(eps) (CTCtopC, unet.py:1054-1092) in eval mode -> fp32 [256, B, nclasses]."""
+        B, Cc, H, W = eps.shape
+        ncls = self.cfg.vocab_size - 2
+        out = torch.empty((256, B, ncls), device=self.device, dtype=torch.float32)
+        e = eps.to(torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib().wd_f32_ctc_head(self._h, B, _ptr(e), Cc, H, W, _ptr(out), _stream_ptr()), "wd_f32_ctc_head")
+        return out
 
     def unet_eval(self, x, timesteps, y, out=None):
         B = x.shape[0]

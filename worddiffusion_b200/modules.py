@@ -162,6 +162,23 @@ class CharacterEncoder(_Holder):
         self.positional_encoding = character_positional_encoding(max_seq_len, hidden_size)
 
 
+class CTCtopC(_Holder):
+    """OCR head of args.ocrTraining == 1 (unet.py:1054-1092): parameter / buffer tree only (the arithmetic is wd_f32_ctc_head)."""
+
+    def __init__(self, input_size, head_cfg, nclasses):
+        super().__init__()
+        hidden_size, num_layers = head_cfg
+
+        def stage(cin):
+            return nn.Sequential(nn.Conv2d(cin, hidden_size, kernel_size=(1, 5), stride=(1, 1), padding=(0, 2)),
+                                 nn.BatchNorm2d(hidden_size), nn.ReLU(), nn.Dropout(.25))
+        self.temporal_i = stage(input_size)
+        self.temporal_m = nn.ModuleList([stage(hidden_size) for _ in range(num_layers)])
+        self.temporal_o = nn.Conv2d(hidden_size, nclasses, kernel_size=(1, 5), stride=1, padding=(0, 2))
+        self.lin1 = nn.Linear(32, 128)
+        self.lin2 = nn.Linear(128, 256)
+
+
 class TimestepEmbedSequential(nn.Sequential):
     def forward(self, *a, **k):  # pragma: no cover - guard
         raise RuntimeError("parameter holder of the B200 engine; call the enclosing UNetModel")

@@ -68,8 +68,8 @@ class UNetBase(nn.Module):
         self.vocab_size = vocab_size
         self.max_seq_len = max_seq_len
         self.interpolation = args.interpolation
-        if self.interpolation:
-            raise NotImplementedError("worddiffusion_b200 does not implement args.interpolation (random style mixing)")
+        if self.interpolation and self.VARIANT != _lib.VARIANT_UNET:
+            raise NotImplementedError("worddiffusion_b200 implements args.interpolation (random style mixing) for unet.UNetModel only")
         self._engine = None
         self._engine_sig = None
         self._train_engine = None
@@ -115,7 +115,15 @@ class UNetBase(nn.Module):
                 if k.startswith(old):
                     k = new + k[len(old):]
                     break
+            if k == "label_emb.weight" and self._engine_classes() != self.num_classes:
+                v = torch.cat([v, v.new_zeros((1, v.shape[1]))], dim=0)  # scratch row of the style interpolation
             yield k, v
+
+    def _engine_classes(self):
+        """args.interpolation: the engines get one scratch class after the model's own (wd_engine_set_label_mix writes it)."""
+        if self.num_classes is not None and getattr(self, "interpolation", False):
+            return self.num_classes + 1
+        return self.num_classes
 
     def engine(self, device=None, latent_hw=None):
         """The B200 engine bound to this module's parameters (created / re-synchronised lazily)."""
@@ -135,7 +143,7 @@ class UNetBase(nn.Module):
                 attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
                 num_heads=self.num_heads, num_head_channels=self.num_head_channels,
                 transformer_depth=self.transformer_depth, context_dim=self.context_dim, vocab_size=self.vocab_size,
-                num_classes=self.num_classes, max_seq_len=self.max_seq_len, latent_hw=latent_hw,
+                num_classes=self._engine_classes(), max_seq_len=self.max_seq_len, latent_hw=latent_hw,
                 add_label_emb=self._add_label_emb(), phosc_len=self._phosc_len(), device=device)
             self._engine_sig = None
         sig = self._weights_signature()
@@ -152,7 +160,7 @@ class UNetBase(nn.Module):
                 attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
                 num_heads=self.num_heads, num_head_channels=self.num_head_channels,
                 transformer_depth=self.transformer_depth, context_dim=self.context_dim, vocab_size=self.vocab_size,
-                num_classes=self.num_classes, max_seq_len=self.max_seq_len, latent_hw=latent_hw,
+                num_classes=self._engine_classes(), max_seq_len=self.max_seq_len, latent_hw=latent_hw,
                 add_label_emb=self._add_label_emb(), phosc_len=self._phosc_len())
             self._engine_f32 = F32Engine(cfg, latent_hw, device)
             self._engine_f32_sig = None
@@ -211,7 +219,7 @@ class UNetBase(nn.Module):
             self._train_engine = TrainEngine(self, device, latent_hw)
         return self._train_engine
 
-    def _run(self, x, timesteps, context, y, phosc):
+    def _run(self, x, timesteps, context, y, phosc, dense_context=None, label_mix=None):
         if context is None:
             raise NotImplementedError("worddiffusion_b200 needs the character context (context=None is not implemented)")
         if x.device.type != "cuda":
@@ -224,6 +232,11 @@ class UNetBase(nn.Module):
         xin = x.to(torch.float32).contiguous()
         if y is not None:
             y = y.to(device=x.device, dtype=torch.int64).contiguous()
-        eng.encode_context(context, phosc)
+        if label_mix is not None:
+            eng.set_label_mix(self.num_classes, *label_mix)
+        if dense_context is not None:
+            eng.set_context(dense_context)
+        else:
+            eng.encode_context(context, phosc)
         out = eng.unet_eval(xin, timesteps, y)
         return out.type(x.dtype)
