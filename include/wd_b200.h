@@ -260,6 +260,16 @@ int wd_f32_read_context(wd_f32* e, float* dst, size_t bytes, void* stream);
  * wd_f32_ctc_head: tdec = auxhead(eps) of args.ocrTraining == 1 (CTCtopC, unet.py:1054-1092,1829) in eval mode,
  *   eps fp32 NCHW [batch, C, H, W] -> out fp32 [256, batch, nclasses]. */
 int wd_set_context(wd_engine* e, int batch, const float* ctx_f32, int L, void* stream);
+/* Front and back end of the noise-prediction step (train.py:190-194 Diffusion.noise_images, :287 nn.MSELoss):
+ * wd_noise_images: x_t = sqrt(alpha_hat[t]) x + sqrt(1 - alpha_hat[t]) eps in one pass over fp32 [batch, elems_per_latent]; eps comes
+ *   from eps_in, or (eps_in == NULL) from the sampler's Philox4x32-10 stream keyed by (seed, sample_offset + latent, stream_id);
+ *   alpha_hat: device fp32 [T]; t: device int64 [batch].  Both x_t and eps are written.
+ * wd_mse_loss_grad: loss = mean((pred - target)^2) (device scalar), d_pred = 2 (pred - target) / n; deterministic reduction.
+ *   workspace: wd_mse_workspace_bytes(n) bytes of device memory, zeroed once. */
+int wd_noise_images(const float* x, const int64_t* t, const float* alpha_hat, int T, const float* eps_in, uint64_t seed,
+                    uint64_t sample_offset, uint32_t stream_id, float* x_t, float* eps_out, int batch, int elems_per_latent, void* stream);
+size_t wd_mse_workspace_bytes(size_t n);
+int wd_mse_loss_grad(const float* pred, const float* target, float* d_pred, float* loss, void* workspace, size_t n, void* stream);
 /* out = torch.lerp(start, end, weight), fp32 (train.py:226-228: the guidance mix of two evaluations) */
 int wd_lerp(const float* start, const float* end, float weight, float* out, size_t n, void* stream);
 int wd_engine_set_label_mix(wd_engine* e, int row, int s1, int s2, float mix, void* stream);

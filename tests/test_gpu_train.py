@@ -261,3 +261,44 @@ def test_data_parallel_training_two_gpus():
                         "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "ddp_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert "DDP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_noise_images_kernel_matches_the_reference_formula():
+    """Diffusion.noise_images (train.py:190-194) as one kernel: exact given eps; Philox noise has unit moments and does not depend
+    on how the batch is sharded."""
+    from worddiffusion_b200.diffusion import Diffusion
+    diff = Diffusion(noise_steps=1000, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(64, 4, 8, 32, generator=g).to(DEV)
+    t = torch.randint(1, 1000, (64,), generator=g)
+    eps = torch.randn(64, 4, 8, 32, generator=g).to(DEV)
+    x_t, e = diff.noise_images(x, t, eps=eps)
+    ah = diff.alpha_hat.to(DEV)[t.to(DEV)][:, None, None, None]
+    want = torch.sqrt(ah) * x + torch.sqrt(1 - ah) * eps
+    assert torch.equal(e, eps) and float((x_t - want).abs().max()) < 1e-6
+    x_a, e_a = diff.noise_images(x, t, seed=9)
+    x_b, e_b = diff.noise_images(x[40:], t[40:], seed=9, sample_offset=40)
+    assert torch.equal(e_a[40:], e_b) and torch.equal(x_a[40:], x_b)
+    assert abs(float(e_a.mean())) < 2e-2 and abs(float(e_a.std()) - 1.0) < 2e-2
+    _, e1 = diff.noise_images(x, t)
+    _, e2 = diff.noise_images(x, t)
+    assert not torch.equal(e1, e2)          # successive training steps draw fresh noise
+    with pytest.raises(IndexError):
+        diff.noise_images(x, torch.full((64,), 1000))
+
+
+def test_mse_loss_and_gradient_kernel():
+    from worddiffusion_b200._lib import check, lib
+    from gpu_util import P, S
+    for n in (5, 4 * 8 * 32 * 3, 224 * 1024 + 17):
+        g = torch.Generator().manual_seed(n)
+        a = torch.randn(n, generator=g).to(DEV)
+        b = torch.randn(n, generator=g).to(DEV)
+        ws = torch.zeros(int(lib().wd_mse_workspace_bytes(n)), device=DEV, dtype=torch.uint8)
+        d = torch.empty_like(a)
+        loss = torch.empty((), device=DEV)
+        for _ in range(2):  # the ticket counter re-arms itself
+            check(lib().wd_mse_loss_grad(P(a), P(b), P(d), P(loss), P(ws), n, S()), "wd_mse_loss_grad")
+        ref = torch.nn.functional.mse_loss(a.double(), b.double())
+        assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, float(ref))
+        assert float((d - (a - b) * (2.0 / n)).abs().max()) < 1e-7

@@ -92,6 +92,9 @@ SIGNATURES = {
     "wd_f32_read_context": (_I, [_P, _P, C.c_size_t, _P]),
     "wd_set_context": (_I, [_P, _I, _P, _I, _P]),
     "wd_lerp": (_I, [_P, _P, _F, _P, C.c_size_t, _P]),
+    "wd_noise_images": (_I, [_P, _P, _P, _I, _P, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P, _I, _I, _P]),
+    "wd_mse_workspace_bytes": (C.c_size_t, [C.c_size_t]),
+    "wd_mse_loss_grad": (_I, [_P, _P, _P, _P, _P, C.c_size_t, _P]),
     "wd_engine_set_label_mix": (_I, [_P, _I, _I, _I, _F, _P]),
     "wd_f32_set_context": (_I, [_P, _I, _P, _I, _P]),
     "wd_f32_set_label_mix": (_I, [_P, _I, _I, _I, _F, _P]),

@@ -1923,6 +1923,26 @@ extern "C" int wd_engine_set_label_mix(wd_engine* e, int row, int s1, int s2, fl
   return WD_OK;
 }
 
+// Training-step front and back ends (train.py:190-194,287): wd_noise_images writes x_t and eps in one pass (eps from
+// `eps_in`, or Philox keyed by (seed, sample_offset, stream_id) when eps_in is NULL); wd_mse_loss_grad writes the MSE loss (device
+// scalar) and d loss / d pred.  `workspace`: wd_mse_workspace_bytes(n) bytes, zeroed once by the caller.
+extern "C" int wd_noise_images(const float* x, const int64_t* t, const float* alpha_hat, int T, const float* eps_in, uint64_t seed,
+                               uint64_t sample_offset, uint32_t stream_id, float* x_t, float* eps_out, int batch, int elems_per_latent,
+                               void* stream) {
+  if (!x || !t || !alpha_hat || !x_t || !eps_out || batch < 0 || elems_per_latent < 1) return fail(WD_ERR_INVALID, "wd_noise_images: invalid argument");
+  CUDA_TRY(noise_images_launch(x, reinterpret_cast<const long long*>(t), alpha_hat, T, eps_in, seed,
+                               sample_offset * static_cast<uint64_t>(elems_per_latent), stream_id, x_t, eps_out,
+                               static_cast<size_t>(batch) * elems_per_latent, elems_per_latent, nullptr, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+extern "C" size_t wd_mse_workspace_bytes(size_t n) { return mse_grad_workspace_bytes(n); }
+extern "C" int wd_mse_loss_grad(const float* pred, const float* target, float* d_pred, float* loss, void* workspace, size_t n,
+                                void* stream) {
+  if (!pred || !target || !d_pred || !loss || !workspace || !n) return fail(WD_ERR_INVALID, "wd_mse_loss_grad: invalid argument");
+  CUDA_TRY(mse_grad_launch(pred, target, d_pred, loss, workspace, n, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
 // out = torch.lerp(start, end, weight) on fp32 device tensors (train.py:228: predicted_noise = lerp(uncond, cond, cfg_scale))
 extern "C" int wd_lerp(const float* start, const float* end, float weight, float* out, size_t n, void* stream) {
   if (!start || !end || !out) return fail(WD_ERR_INVALID, "wd_lerp: null argument");

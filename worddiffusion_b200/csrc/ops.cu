@@ -402,6 +402,86 @@ cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStrea
   return launch_pdl(groupnorm_apply_kernel, dim3(B, nslab, a.nchunk), dim3(nv * R), 0, s, a);
 }
 
+// Forward noising of the training step (train.py:190-194): x_t = sqrt(ah[t]) x + sqrt(1 - ah[t]) eps, eps ~ N(0, I)
+// from the caller (eps_in) or from the sampler's Philox4x32-10 stream keyed by (seed, global element, stream id) -- one pass that
+// writes both x_t and eps.  alpha_hat: the schedule's cumulative products [T] on the device; t: int64 [n].
+__global__ void noise_images_kernel(const float* __restrict__ x, const long long* __restrict__ t, const float* __restrict__ alpha_hat,
+                                    int T, const float* __restrict__ eps_in, unsigned long long seed, unsigned long long elem_offset,
+                                    uint32_t stream_id, float* __restrict__ x_t, float* __restrict__ eps_out, size_t n, int per,
+                                    int* __restrict__ bad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long ti = t[i / per];
+  if (ti < 0 || ti >= T) {  // the reference's alpha_hat[t] raises IndexError
+    if (bad) atomicExch(bad, 1);
+    return;
+  }
+  const float ah = alpha_hat[ti];
+  const float e = eps_in ? eps_in[i] : philox_normal(seed, elem_offset + i, stream_id);
+  eps_out[i] = e;
+  x_t[i] = __fadd_rn(__fmul_rn(sqrtf(ah), x[i]), __fmul_rn(sqrtf(1.0f - ah), e));
+}
+cudaError_t noise_images_launch(const float* x, const long long* t, const float* alpha_hat, int T, const float* eps_in,
+                                unsigned long long seed, unsigned long long elem_offset, uint32_t stream_id, float* x_t, float* eps_out,
+                                size_t n, int per, int* bad, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  noise_images_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, t, alpha_hat, T, eps_in, seed, elem_offset, stream_id, x_t,
+                                                                             eps_out, n, per, bad);
+  return cudaGetLastError();
+}
+
+// nn.MSELoss (train.py:287) and its gradient in one pass: d[i] = 2 (pred[i] - target[i]) / n, loss = mean((pred - target)^2).
+// Deterministic: per-CTA partial sums in fixed order, folded by the last CTA to finish (ticket counter, no float atomics).
+constexpr int MSE_THREADS = 256, MSE_PER_THREAD = 8;
+__global__ void __launch_bounds__(MSE_THREADS) mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                               float* __restrict__ d, float* __restrict__ partial,
+                                                               unsigned int* __restrict__ ticket, float* __restrict__ loss, size_t n) {
+  __shared__ float red[MSE_THREADS / 32];
+  __shared__ bool last;
+  const float inv = 2.0f / static_cast<float>(n);
+  float acc = 0.f;
+  const size_t base = static_cast<size_t>(blockIdx.x) * MSE_THREADS * MSE_PER_THREAD;
+#pragma unroll
+  for (int k = 0; k < MSE_PER_THREAD; ++k) {
+    const size_t i = base + static_cast<size_t>(k) * MSE_THREADS + threadIdx.x;
+    if (i < n) {
+      const float df = pred[i] - target[i];
+      d[i] = df * inv;
+      acc = fmaf(df, df, acc);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < MSE_THREADS / 32; ++w) tsum += red[w];
+    partial[blockIdx.x] = tsum;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) tot += static_cast<double>(partial[b]);
+    *loss = static_cast<float>(tot / static_cast<double>(n));
+    *ticket = 0u;  // ready for the next call
+  }
+}
+size_t mse_grad_workspace_bytes(size_t n) {
+  const size_t blocks = (n + MSE_THREADS * MSE_PER_THREAD - 1) / (MSE_THREADS * MSE_PER_THREAD);
+  return 16 + blocks * sizeof(float);
+}
+cudaError_t mse_grad_launch(const float* pred, const float* target, float* d, float* loss, void* workspace, size_t n, cudaStream_t s) {
+  if (!n) return cudaErrorInvalidValue;
+  const unsigned blocks = static_cast<unsigned>((n + MSE_THREADS * MSE_PER_THREAD - 1) / (MSE_THREADS * MSE_PER_THREAD));
+  unsigned int* ticket = static_cast<unsigned int*>(workspace);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
+  mse_grad_kernel<<<blocks, MSE_THREADS, 0, s>>>(pred, target, d, partial, ticket, loss, n);
+  return cudaGetLastError();
+}
+
 // torch.lerp(start, end, weight) with torch's formula (weight < 0.5 ? start + weight (end - start) : end - (end - start)(1 - weight)):
 // the classifier-free-guidance mix of train.py:226-228
 __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float w, float* __restrict__ out, size_t n) {

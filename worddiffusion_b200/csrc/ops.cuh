@@ -42,6 +42,11 @@ struct GroupNormArgs {
 int groupnorm_apply_chunks(int HW);  // pixel chunks per sample of the apply grid (GroupNormArgs::nchunk)
 cudaError_t groupnorm_launch(const GroupNormArgs& a, int B, int nslab, cudaStream_t s);
 
+cudaError_t noise_images_launch(const float* x, const long long* t, const float* alpha_hat, int T, const float* eps_in,
+                                unsigned long long seed, unsigned long long elem_offset, uint32_t stream_id, float* x_t, float* eps_out,
+                                size_t n, int per, int* bad, cudaStream_t s);
+size_t mse_grad_workspace_bytes(size_t n);
+cudaError_t mse_grad_launch(const float* pred, const float* target, float* d, float* loss, void* workspace, size_t n, cudaStream_t s);
 cudaError_t lerp_launch(const float* a, const float* b, float w, float* out, size_t n, cudaStream_t s);
 cudaError_t label_mix_launch(float* table, int D, int row, int s1, int s2, float mix, cudaStream_t s);
 

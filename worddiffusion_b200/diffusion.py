@@ -14,7 +14,7 @@ What changes against the reference loop, and why:
 import numpy as np
 import torch
 
-from ._lib import STEP_DDIM, STEP_DDPM
+from ._lib import STEP_DDIM, STEP_DDPM, WdError
 
 MAX_CHARS = 10
 C_CLASSES = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
@@ -51,12 +51,40 @@ class Diffusion:
     def prepare_noise_schedule(self):
         return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
 
-    def noise_images(self, x, t):
-        """train.py:190-194."""
-        sqrt_alpha_hat = torch.sqrt(self.alpha_hat[t])[:, None, None, None]
-        sqrt_one_minus_alpha_hat = torch.sqrt(1 - self.alpha_hat[t])[:, None, None, None]
-        eps = torch.randn_like(x)
-        return sqrt_alpha_hat * x + sqrt_one_minus_alpha_hat * eps, eps
+    def noise_images(self, x, t, eps=None, seed=None, sample_offset=0):
+        """train.py:190-194: ``(x_t, eps)`` with x_t = sqrt(alpha_hat[t]) x + sqrt(1 - alpha_hat[t]) eps, one kernel
+        (``wd_noise_images``).  ``eps``: the noise to use (parity runs); otherwise N(0, I) from the library's Philox stream --
+        ``seed`` (default: a per-object call counter) and ``sample_offset`` (global index of the first latent) key it, so a
+        sharded batch draws the same noise as the full one."""
+        from ._lib import check, lib
+        from .engine import _ptr, _stream_ptr
+        if x.device.type != "cuda":
+            raise WdError("worddiffusion_b200 has no CPU path: inputs must live on a CUDA (B200) device")
+        xx = x.detach().to(torch.float32).contiguous()
+        if t.device.type == "cpu" and t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.noise_steps):
+            raise IndexError(f"index out of range: timesteps must lie in [0, {self.noise_steps})")  # alpha_hat[t]
+        tt = t.to(device=x.device, dtype=torch.int64).contiguous()
+        ah = self._alpha_hat_dev(x.device)
+        x_t, e_out = torch.empty_like(xx), torch.empty_like(xx)
+        e_in = None if eps is None else eps.to(device=x.device, dtype=torch.float32).contiguous()
+        if seed is None:
+            self._noise_calls = getattr(self, "_noise_calls", 0) + 1
+            seed, stream = 0x6E6F6973, self._noise_calls
+        else:
+            stream = 0
+        n = xx.shape[0]
+        with torch.cuda.device(x.device):
+            check(lib().wd_noise_images(_ptr(xx), _ptr(tt), _ptr(ah), self.noise_steps, _ptr(e_in), int(seed), int(sample_offset),
+                                        int(stream) & 0xFFFFFFFF, _ptr(x_t), _ptr(e_out), n, xx[0].numel() if n else 1,
+                                        _stream_ptr()), "wd_noise_images")
+        return x_t, e_out
+
+    def _alpha_hat_dev(self, device):
+        cur = getattr(self, "_ah_dev", None)
+        if cur is None or cur.device != device:
+            cur = self.alpha_hat.to(device=device, dtype=torch.float32).contiguous()
+            self._ah_dev = cur
+        return cur
 
     def sample_timesteps(self, n):
         """train.py:196-197."""

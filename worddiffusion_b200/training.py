@@ -270,9 +270,17 @@ class FusedTrainStep:
     def step(self, x_t, timesteps, context, y, noise):
         eng = self.eng
         eps = eng.forward(x_t, timesteps, y, context)
-        diff = eps - noise
-        loss = (diff * diff).mean()                   # nn.MSELoss (train.py:287)
-        d_eps = diff * (2.0 / diff.numel())
+        # nn.MSELoss (train.py:287) and its gradient in one kernel: loss = mean((eps - noise)^2), d_eps = 2 (eps - noise) / n
+        noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        n_el = eps.numel()
+        if getattr(self, "_mse_ws_n", None) != n_el:
+            self._mse_ws = torch.zeros(int(lib().wd_mse_workspace_bytes(n_el)), device=self.device, dtype=torch.uint8)
+            self._mse_ws_n = n_el
+        d_eps = torch.empty_like(eps)
+        loss = torch.empty((), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().wd_mse_loss_grad(_ptr(eps), _ptr(noise), _ptr(d_eps), _ptr(loss), _ptr(self._mse_ws), n_el, _stream_ptr()),
+                  "wd_mse_loss_grad")
         eng.backward(d_eps)
         ws = allreduce_sum_(eng.flat_grad, self.pg)
         self.t += 1
