@@ -294,9 +294,13 @@ size_t wd_f32_workspace_bytes(const wd_f32* e);
  * weights in the state_dict layout [Cout,Cin,3,3]; softmax(q k^T scale) v with q [B,Sq,heads*d], k,v [B,Skv,heads*d] */
 int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W, int Cin,
                       int Cout, int stride, int up, void* stream);
-/* out[M,N] = A[M,K] W[N,K]^T + bias through the opt-in split-TF32 tcgen05 kernel (csrc/f32_gemm_tc.cu: three kind::tf32 MMAs per
- * K step on pre-split operands; WD_F32_TC=1 routes the fp32 mode's contractions through it).  M % 128 == 0, N % 160 == 0, K % 32 == 0 */
+/* out[M,N] = A[M,K] W[N,K]^T + bias through the split-TF32 tcgen05 kernel (csrc/f32_gemm_tc.cu: three kind::tf32 MMAs per K step on
+ * pre-split operands, chunks of K = 320 summed in fp32 registers; the fp32 mode's Linear / 1x1 / 3x3 contractions run on it unless
+ * WD_F32_TC=0).  M % 128 == 0, N % 160 == 0, K % 32 == 0 */
 int wd_f32_op_gemm_tc(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, void* stream);
+/* 3x3 pad-1 stride-1 convolution over cat([x1, x2], channel) (x2 NULL: one source) as an implicit GEMM on the split-TF32 kernel */
+int wd_f32_op_conv3x3_tc(const float* x1, const float* x2, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W,
+                         int C1, int C2, int Cout, void* stream);
 int wd_f32_op_attention(const float* q, const float* k, const float* v, float* out, int B, int Sq, int Skv, int heads, int d,
                         float scale, void* stream);
 

@@ -6,7 +6,7 @@
 # Usage (from the repo root): gpurun --timeout 300 -- 'bash tools/gpu_check_f32_tc.sh'
 set -u
 mkdir -p gpurun_out
-echo "== 1. operator test"; WD_F32_TC_TEST=1 timeout 120 python -m pytest tests/test_gpu_zfp32.py -q -s -k f32_tc_gemm 2>&1 | tail -8
+echo "== 1. operator tests"; timeout 120 python -m pytest tests/test_gpu_zfp32.py -q -s -k f32_tc 2>&1 | tail -8
 echo "== 2. fp32 parity suite through the tensor-core GEMM"; WD_F32_TC=1 timeout 200 python -m pytest tests/test_gpu_zfp32.py -q -s 2>&1 | grep -E "err|passed|failed|Error" | tail -30
 for tc in 0 1; do
   echo "== 3. fp32 leg, WD_F32_TC=$tc"

@@ -106,6 +106,7 @@ SIGNATURES = {
     "wd_f32_workspace_bytes": (C.c_size_t, [_P]),
     "wd_f32_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "wd_f32_op_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "wd_f32_op_conv3x3_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wd_f32_op_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
 }
 

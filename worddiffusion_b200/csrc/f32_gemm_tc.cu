@@ -38,7 +38,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;  // 20 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_W_BYTES;  // 72 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256;  // + barriers / TMEM slot
-constexpr uint32_t TC_TMEM_COLS = 256;  // power of two >= 160
+constexpr uint32_t TC_TMEM_COLS = 512;  // two 160-column chunk accumulators at columns 0 and 256
 // The tensor core's fp32 accumulation truncates: the error of one TMEM accumulation grows with K (measured 1.6e-6 at K = 320,
 // 1.3e-5 at K = 2880).  Longer contractions are therefore cut into chunks of TC_SPLIT_KB K blocks (K = 320) whose partial tiles a
 // second kernel adds in fp32 (two-level accumulation).
@@ -61,6 +61,11 @@ WD_DEVINL void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, u
 
 struct TcArgs {
   int M, N, K;
+  // implicit 3x3 pad-1 stride-1 convolution: A rows are 4-D TMA boxes (c, w, h, n) of the split NHWC source(s), shifted per filter
+  // tap (out-of-bounds zero fill = the padding); k = tap (C1 + C2) + c over the channel concatenation of up to two sources
+  int conv;
+  int HW, W;     // output (= input) pixels per image, row length
+  int cb1, cb2;  // 32-channel K blocks of source 1 / source 2
   const float* bias;
   const float* rowbias;
   int rb_ld;
@@ -68,38 +73,47 @@ struct TcArgs {
   const float* residual;
   float* out;
   int act_silu;
-  // split-K (two-level accumulation): blockIdx.z accumulates K blocks [z kb_per_split, (z + 1) kb_per_split) in TMEM and writes the
-  // raw tile to partial + z M N; f32tc_reduce_kernel adds the partials in fp32, in order, and applies the epilogue
-  int kb_per_split;  // 0: no split
-  float* partial;
+  // two-level accumulation: the tensor core's fp32 accumulation truncates (error grows with K), so K is walked in chunks of
+  // kb_per_chunk K blocks; each chunk accumulates in one of two TMEM buffers and the epilogue warps add the finished chunk to fp32
+  // REGISTER accumulators (exact fp32 adds, in order: deterministic) while the next chunk's MMAs run in the other buffer
+  int kb_per_chunk;
 };
 
 __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                                                            const __grid_constant__ CUtensorMap mapA2h, const __grid_constant__ CUtensorMap mapA2l,
                                                             const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                                                             const TcArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* acc_bar = empty_bar + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + TC_STAGES;   // [2]: chunk accumulator complete (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;           // [2]: chunk accumulator drained (4 epilogue warps -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
-  const bool split = args.kb_per_split > 0;
-  const int kb0 = split ? static_cast<int>(blockIdx.z) * args.kb_per_split : 0;
-  const int nkb = split ? min(args.kb_per_split, args.K / TC_BK - kb0) : args.K / TC_BK;
+  const int nkb = args.K / TC_BK;
+  const int kpc = args.kb_per_chunk;
+  const int nchunks = (nkb + kpc - 1) / kpc;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapAh);
     tma_prefetch_desc(&mapAl);
     tma_prefetch_desc(&mapWh);
     tma_prefetch_desc(&mapWl);
+    if (args.cb2) {
+      tma_prefetch_desc(&mapA2h);
+      tma_prefetch_desc(&mapA2l);
+    }
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_slot);
@@ -112,13 +126,28 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int cbt = args.cb1 + args.cb2;
+      int img = 0, oh0 = 0;
+      if (args.conv) {
+        img = m0 / args.HW;
+        oh0 = (m0 % args.HW) / args.W;
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
         uint8_t* s = smem + stage * TC_STAGE_BYTES;
-        const int kc = (kb0 + kb) * TC_BK;
-        tma_load_2d(s, &mapAh, &full_bar[stage], kc, m0);
-        tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kc, m0);
+        const int kc = kb * TC_BK;
+        if (args.conv) {
+          const int tap = kb / cbt, cb = kb - tap * cbt;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const bool second = cb >= args.cb1;
+          const int c0 = (second ? cb - args.cb1 : cb) * TC_BK;
+          tma_load_4d(s, second ? &mapA2h : &mapAh, &full_bar[stage], c0, dx, oh0 + dy, img);
+          tma_load_4d(s + TC_A_BYTES, second ? &mapA2l : &mapAl, &full_bar[stage], c0, dx, oh0 + dy, img);
+        } else {
+          tma_load_2d(s, &mapAh, &full_bar[stage], kc, m0);
+          tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kc, m0);
+        }
         tma_load_2d(s + 2 * TC_A_BYTES, &mapWh, &full_bar[stage], kc, n0);
         tma_load_2d(s + 2 * TC_A_BYTES + TC_W_BYTES, &mapWl, &full_bar[stage], kc, n0);
         if (++stage == TC_STAGES) {
@@ -132,49 +161,72 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
       constexpr uint32_t idesc = make_idesc_tf32_f32(TC_BM, TC_BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t s = smem_u32(smem + stage * TC_STAGE_BYTES);
-        const uint64_t ah = make_smem_desc_sw128(s), al = make_smem_desc_sw128(s + TC_A_BYTES);
-        const uint64_t wh = make_smem_desc_sw128(s + 2 * TC_A_BYTES), wl = make_smem_desc_sw128(s + 2 * TC_A_BYTES + TC_W_BYTES);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch >= 2) {  // the epilogue warps have added chunk ch - 2 (same buffer) to their registers
+          mbar_wait(&acc_empty[buf], ((ch >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d = tmem_base + buf * 256;
+        const int kend = min(nkb, (ch + 1) * kpc);
+        for (int kb = ch * kpc; kb < kend; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t s = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint64_t ah = make_smem_desc_sw128(s), al = make_smem_desc_sw128(s + TC_A_BYTES);
+          const uint64_t wh = make_smem_desc_sw128(s + 2 * TC_A_BYTES), wl = make_smem_desc_sw128(s + 2 * TC_A_BYTES + TC_W_BYTES);
+          const bool first = kb == ch * kpc;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          // advance 8 tf32 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field; small terms first
-          umma_tf32_ss(tmem_base, al + 2 * k, wh + 2 * k, idesc, (kb | k) != 0);
-          umma_tf32_ss(tmem_base, ah + 2 * k, wl + 2 * k, idesc, 1u);
-          umma_tf32_ss(tmem_base, ah + 2 * k, wh + 2 * k, idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            // advance 8 tf32 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field; small terms first
+            umma_tf32_ss(d, al + 2 * k, wh + 2 * k, idesc, (!first || k != 0) ? 1u : 0u);
+            umma_tf32_ss(d, ah + 2 * k, wl + 2 * k, idesc, 1u);
+            umma_tf32_ss(d, ah + 2 * k, wh + 2 * k, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
-        if (++stage == TC_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&acc_full[buf]);  // chunk accumulator complete
       }
-      umma_commit(acc_bar);  // accumulator complete
     }
   } else {
     // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32); thread = one output row
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int sample = args.rowbias ? m / args.rows_per_sample : 0;
-    float* orow = (split ? args.partial + static_cast<size_t>(blockIdx.z) * args.M * args.N : args.out) + static_cast<size_t>(m) * args.N + n0;
-    const float* rrow = (args.residual && !split) ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
-    const float* rbrow = (args.rowbias && !split) ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
-    const float* bias = split ? nullptr : args.bias;
-    const int act_silu = split ? 0 : args.act_silu;
+    float acc[TC_BN];  // second accumulation level, fp32 registers (every index below is a compile-time constant)
 #pragma unroll 1
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(&acc_full[buf], (ch >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < TC_BN / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + buf * 256 + c * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c * 16 + j] = ch == 0 ? __uint_as_float(v[j]) : acc[c * 16 + j] + __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    const int sample = args.rowbias ? m / args.rows_per_sample : 0;
+    float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
+    const float* rrow = args.residual ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
+    const float* rbrow = args.rowbias ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
+    const float* bias = args.bias;
+    const int act_silu = args.act_silu;
+#pragma unroll
     for (int c = 0; c < TC_BN / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_row + c * 16, v);
-      tmem_ld_wait();
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(v[j]);
+        float x = acc[c * 16 + j];
         const int n = c * 16 + j;
         if (bias) x += bias[n0 + n];
         if (rbrow) x += rbrow[n];
@@ -191,32 +243,6 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
-}
-
-// second accumulation level of the split-K form: out = act(sum_z partial[z] + bias + rowbias + residual), z in order (deterministic)
-__global__ void f32tc_reduce_kernel(const TcArgs args, int splits) {
-  const size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t MN = static_cast<size_t>(args.M) * args.N;
-  if (i4 * 4 >= MN) return;
-  const size_t m = (i4 * 4) / args.N;
-  const int n = static_cast<int>(i4 * 4 - m * args.N);
-  float4 acc = reinterpret_cast<const float4*>(args.partial)[i4];
-  for (int z = 1; z < splits; ++z) {
-    const float4 p = reinterpret_cast<const float4*>(args.partial + static_cast<size_t>(z) * MN)[i4];
-    acc.x += p.x;
-    acc.y += p.y;
-    acc.z += p.z;
-    acc.w += p.w;
-  }
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (args.bias) v[j] += args.bias[n + j];
-    if (args.rowbias) v[j] += args.rowbias[(m / args.rows_per_sample) * args.rb_ld + n + j];
-    if (args.residual) v[j] += args.residual[m * args.N + n + j];
-    if (args.act_silu) v[j] = v[j] / (1.0f + expf(-v[j]));
-  }
-  reinterpret_cast<float4*>(args.out)[i4] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // a -> (tf32_rn(a), a - tf32_rn(a))
@@ -300,13 +326,37 @@ bool tmap_f32(CUtensorMap* m, const float* base, uint64_t K, uint64_t rows, uint
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 NHWC [N, H, W, C]: boxes of 32 channels x bw x bh x bn pixels, SWIZZLE_128B, out-of-bounds elements read as zero
+bool tmap_f32_4d(CUtensorMap* m, const float* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t bw, uint32_t bh, uint32_t bn) {
+  PFN_encodeTiled fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 4, C * 4 * W, C * 4 * W * H};
+  cuuint32_t box[4] = {TC_BK, bw, bh, bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mA2h, const CUtensorMap& mA2l, const CUtensorMap& mWh,
+                      const CUtensorMap& mWl, const TcArgs& a, cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  f32tc_gemm_kernel<<<dim3(a.M / TC_BM, a.N / TC_BN, 1), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
-bool f32tc_enabled() {
+bool f32tc_enabled() {  // default ON since round 2 (measured: profiles/R2o_*); WD_F32_TC=0 keeps every contraction on the FFMA kernel
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WD_F32_TC");
-    v = e ? (atoi(e) != 0) : 0;
+    v = e ? (atoi(e) != 0) : 1;
   }
   return v != 0;
 }
@@ -330,22 +380,16 @@ cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2,
   return cudaGetLastError();
 }
 
-int f32tc_splits(int K) { return K > TC_SPLIT_MIN_K ? (K / TC_BK + TC_SPLIT_KB - 1) / TC_SPLIT_KB : 1; }
+int f32tc_splits(int) { return 1; }  // the second accumulation level lives in the kernel's registers: no partial workspace
 
 cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
                        const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
-                       float* partial_ws, cudaStream_t s) {
+                       float* /*partial_ws*/, cudaStream_t s) {
   if (!f32tc_shape_ok(M, N, K)) return cudaErrorInvalidValue;
   CUtensorMap mAh, mAl, mWh, mWl;
   if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, TC_BN) ||
       !tmap_f32(&mWl, w_lo, K, N, TC_BN))
     return cudaErrorInvalidValue;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
   TcArgs a{};
   a.M = M;
   a.N = N;
@@ -357,17 +401,56 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
   a.residual = residual;
   a.out = out;
   a.act_silu = act_silu;
-  const int splits = partial_ws ? f32tc_splits(K) : 1;
-  if (splits > 1) {
-    a.kb_per_split = TC_SPLIT_KB;
-    a.partial = partial_ws;
+  a.kb_per_chunk = TC_SPLIT_KB;
+  return launch_tc(mAh, mAl, mAh, mAl, mWh, mWl, a, s);
+}
+
+bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N) {
+  const int HW = H * W, M = B * HW;
+  if (M <= 0 || M % TC_BM || N % TC_BN || C1 % TC_BK || C2 % TC_BK || C1 <= 0) return false;
+  if (HW >= TC_BM) return HW % TC_BM == 0 && TC_BM % W == 0 && W <= 256;
+  return TC_BM % HW == 0 && W <= 256 && H <= 256;
+}
+
+cudaError_t f32tc_conv3x3(const float* a1_hi, const float* a1_lo, int C1, const float* a2_hi, const float* a2_lo, int C2, int B, int H, int W,
+                          const float* w_hi, const float* w_lo, int N, const float* bias, const float* rowbias, int rb_ld,
+                          const float* residual, float* out, int act_silu, cudaStream_t s) {
+  if (!f32tc_conv_ok(B, H, W, C1, C2, N)) return cudaErrorInvalidValue;
+  const int HW = H * W, K = 9 * (C1 + C2);
+  uint32_t bw = W, bh, bn;
+  if (HW >= TC_BM) {
+    bh = TC_BM / W;
+    bn = 1;
+  } else {
+    bh = H;
+    bn = TC_BM / HW;
   }
-  f32tc_gemm_kernel<<<dim3(M / TC_BM, N / TC_BN, splits), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mWh, mWl, a);
-  cudaError_t ce = cudaGetLastError();
-  if (ce != cudaSuccess || splits == 1) return ce;
-  const size_t n4 = static_cast<size_t>(M) * N / 4;
-  f32tc_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(a, splits);
-  return cudaGetLastError();
+  CUtensorMap mAh, mAl, mA2h, mA2l, mWh, mWl;
+  if (!tmap_f32_4d(&mAh, a1_hi, C1, W, H, B, bw, bh, bn) || !tmap_f32_4d(&mAl, a1_lo, C1, W, H, B, bw, bh, bn) ||
+      !tmap_f32(&mWh, w_hi, K, N, TC_BN) || !tmap_f32(&mWl, w_lo, K, N, TC_BN))
+    return cudaErrorInvalidValue;
+  mA2h = mAh;
+  mA2l = mAl;
+  if (C2 > 0 && (!tmap_f32_4d(&mA2h, a2_hi, C2, W, H, B, bw, bh, bn) || !tmap_f32_4d(&mA2l, a2_lo, C2, W, H, B, bw, bh, bn)))
+    return cudaErrorInvalidValue;
+  TcArgs a{};
+  a.M = B * HW;
+  a.N = N;
+  a.K = K;
+  a.conv = 1;
+  a.HW = HW;
+  a.W = W;
+  a.cb1 = C1 / TC_BK;
+  a.cb2 = C2 / TC_BK;
+  a.bias = bias;
+  a.rowbias = rowbias;
+  a.rb_ld = rb_ld;
+  a.rows_per_sample = HW;
+  a.residual = residual;
+  a.out = out;
+  a.act_silu = act_silu;
+  a.kb_per_chunk = TC_SPLIT_KB;
+  return launch_tc(mAh, mAl, mA2h, mA2l, mWh, mWl, a, s);
 }
 
 }  // namespace wd

@@ -750,6 +750,29 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
   g.out = o.p;
   // opt-in tensor-core route (split TF32, f32_gemm_tc.cu): operands are split into (hi, lo) pairs first -- a plain split for a
   // Linear / 1x1 conv input, the split patch matrix for a 3x3 conv
+  // implicit 3x3 stride-1 convolution on the tensor cores: only the NHWC sources are split (no patch matrix)
+  if (w_hi && w_lo && wd::f32tc_enabled() && cs.taps == 9 && cs.stride == 1 && !cs.up && !cs.a_nchw && !cs.out_nchw &&
+      wd::f32tc_conv_ok(B, a1.H, a1.W, g.C1, g.C2, N)) {
+    const size_t n1 = static_cast<size_t>(g.M) * g.C1, n2 = static_cast<size_t>(g.M) * g.C2;
+    float* h1 = alloc(e, n1);
+    float* l1 = alloc(e, n1);
+    float* h2 = n2 ? alloc(e, n2) : nullptr;
+    float* l2 = n2 ? alloc(e, n2) : nullptr;
+    if (!e->dry) {
+      cudaError_t ce = wd::f32tc_split(a1.p, h1, l1, n1, e->s);
+      ++e->launches;
+      if (ce == cudaSuccess && n2) {
+        ce = wd::f32tc_split(a2->p, h2, l2, n2, e->s);
+        ++e->launches;
+      }
+      if (ce == cudaSuccess) {
+        ce = wd::f32tc_conv3x3(h1, l1, g.C1, h2, l2, g.C2, B, a1.H, a1.W, w_hi, w_lo, N, bias, rowbias, rb_ld, residual, o.p, cs.silu, e->s);
+        ++e->launches;
+      }
+      if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: tensor-core conv: ") + cudaGetErrorString(ce));
+    }
+    return o;
+  }
   if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K) && (cs.taps == 9 || !a2)) {
     const size_t nA = static_cast<size_t>(g.M) * g.K;
     float* a_hi = alloc(e, nA);
@@ -1634,6 +1657,31 @@ int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bia
   const cudaError_t ce = cudaGetLastError();
   cudaStreamSynchronize(s);
   cudaFree(wp);
+  if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  return WD_OK;
+}
+
+/* 3x3 pad-1 stride-1 convolution over cat([x1, x2], channel) on the split-TF32 tensor-core kernel (implicit GEMM: 4-D TMA boxes of the
+ * split NHWC sources, f32_gemm_tc.cu); x2 may be NULL (C2 = 0).  fp32 NHWC in / out, weights [Cout, C1 + C2, 3, 3]. */
+int wd_f32_op_conv3x3_tc(const float* x1, const float* x2, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W,
+                         int C1, int C2, int Cout, void* stream) {
+  if (!x1 || !w_oihw || !out_nhwc || (C2 > 0 && !x2) || !wd::f32tc_conv_ok(B, H, W, C1, C2, Cout))
+    return wd_set_error(WD_ERR_INVALID, "wd_f32_op_conv3x3_tc: unsupported shape (B H W % 128, channels % 32, Cout % 160)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Cin = C1 + C2;
+  const size_t nw = static_cast<size_t>(Cout) * Cin * 9, n1 = static_cast<size_t>(B) * H * W * C1, n2 = static_cast<size_t>(B) * H * W * C2;
+  float* buf = nullptr;
+  if (cudaMalloc(&buf, (3 * nw + 2 * (n1 + n2)) * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_op_conv3x3_tc: cudaMalloc failed");
+  float *wp = buf, *wh = wp + nw, *wl = wh + nw, *h1 = wl + nw, *l1 = h1 + n1, *h2 = l1 + n1, *l2 = h2 + n2;
+  f32_pack_conv_kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(w_oihw, wp, Cout, Cin);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = wd::f32tc_split(wp, wh, wl, nw, s);
+  if (ce == cudaSuccess) ce = wd::f32tc_split(x1, h1, l1, n1, s);
+  if (ce == cudaSuccess && n2) ce = wd::f32tc_split(x2, h2, l2, n2, s);
+  if (ce == cudaSuccess)
+    ce = wd::f32tc_conv3x3(h1, l1, C1, n2 ? h2 : nullptr, n2 ? l2 : nullptr, C2, B, H, W, wh, wl, Cout, bias, nullptr, 0, nullptr, out_nhwc, 0, s);
+  cudaStreamSynchronize(s);
+  cudaFree(buf);
   if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
   return WD_OK;
 }

@@ -4,7 +4,7 @@
 #include <stddef.h>
 
 namespace wd {
-bool f32tc_enabled();                        // env WD_F32_TC=1 (default off: the kernel has not been measured yet)
+bool f32tc_enabled();                        // env WD_F32_TC (default on; 0 keeps every contraction on the FFMA kernel)
 bool f32tc_shape_ok(int M, int N, int K);    // M % 128 == 0, N % 160 == 0, K % 32 == 0
 // a[n] -> hi[n] = tf32_rn(a), lo[n] = a - hi   (n % 4 == 0)
 cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStream_t s);
@@ -18,4 +18,10 @@ int f32tc_splits(int K);
 cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
                        const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
                        float* partial_ws, cudaStream_t s);
+// implicit 3x3 pad-1 stride-1 convolution over the channel concatenation of up to two split NHWC sources [B, H, W, C1 | C2]
+// (C % 32 == 0; 128 % W == 0 and HW % 128 == 0, or 128 % HW == 0); weights [N, 9 (C1 + C2)] split, k = tap (C1 + C2) + c
+bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N);
+cudaError_t f32tc_conv3x3(const float* a1_hi, const float* a1_lo, int C1, const float* a2_hi, const float* a2_lo, int C2, int B, int H, int W,
+                          const float* w_hi, const float* w_lo, int N, const float* bias, const float* rowbias, int rb_ld,
+                          const float* residual, float* out, int act_silu, cudaStream_t s);
 }  // namespace wd
