@@ -363,7 +363,8 @@ def train_leg(args, world, rank, dev):
 
 def fp32_leg(args, model, diff, inp, dev, variant):
     """BASELINE.json configs[1] asks for the batch-256 sampling step in fp32 as well: the same module with
-    ``precision = "fp32"`` (csrc/f32_path.cu: fp32 storage, FFMA arithmetic, 1e-4 of the reference).  Rank 0 only, a few steps."""
+    ``precision = "fp32"`` (csrc/f32_path.cu: fp32 storage; Linear / 1x1 / 3x3 contractions on the split-TF32 tcgen05 kernel of
+    csrc/f32_gemm_tc.cu, the rest fp32 SIMT; 1e-4 of the reference).  Rank 0 only, a few steps."""
     import torch
     B = args.batch
     ctx, y = inp["context"].to(dev), inp["y"].to(dev)
@@ -400,13 +401,43 @@ def fp32_leg(args, model, diff, inp, dev, variant):
         model.precision = "bf16"
     tf = B * GFLOP_PER_LATENT[variant] * 1e9 / (ms * 1e-3) / 1e12
     peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    # ceiling of the split-TF32 route: kind::tf32 runs at half the bf16 rate and every fp32 product costs three MMAs
+    tc_ceiling = load_peaks()["tf_burst"] / 2.0 / 3.0
     err = float((e16.double() - e32.double()).abs().max() / e32.double().abs().max())
     return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": args.fp32_steps, "dtype": "f32",
             "step_tflops": round(tf, 2), "frac_of_fp32_ffma_peak": round(tf / peak, 4),
-            "fp32_ffma_peak_tflops": round(peak, 1), "gpu_launches_per_step": launches + 1,
+            "fp32_ffma_peak_tflops": round(peak, 1), "split_tf32_ceiling_tflops": round(tc_ceiling, 1),
+            "frac_of_split_tf32_ceiling": round(tf / tc_ceiling, 4),
+            "tensor_core_route": os.environ.get("WD_F32_TC", "1") != "0", "gpu_launches_per_step": launches + 1,
             "workspace_gb": round(ws / 1e9, 2), "bf16_engine_vs_fp32_mode_max_rel": err,
-            "workload": f"{variant} DDPM sampling step in fp32 mode (fp32 storage + FFMA kernels, separate sampler-update kernel), "
-                        f"batch {B}; parity 1e-4 vs the reference (tests/test_gpu_zfp32.py)"}
+            "workload": f"{variant} DDPM sampling step in fp32 mode (fp32 storage; contractions as three kind::tf32 tcgen05 MMAs per K step "
+                        f"on split operands with fp32 second-level accumulation, norms / attention fp32 SIMT; separate sampler-update "
+                        f"kernel), batch {B}; parity 1e-4 vs the reference (tests/test_gpu_zfp32.py)"}
+
+
+def vae_leg(dev, W, batch=64):
+    """the VAE decode at the end of a sampling run (train.py:239-247) through worddiffusion_b200.vae.AutoencoderKL
+    (wd_vae_decode, Stable Diffusion v1 decoder shape, random-init weights): latents [batch, 4, 8, 32] -> images [batch, 3, 64, 256]."""
+    import torch
+    from worddiffusion_b200.vae import AutoencoderKL
+    vae = AutoencoderKL()
+    spec = [(k, tuple(v.shape)) for k, v in vae.state_dict().items()]
+    vae.load_state_dict(W.make_state_dict(spec, seed=77))
+    vae.to(dev)
+    z = torch.randn(batch, 4, 8, 32, device=dev)
+    vae.decode(z[:8], scale=1 / 0.18215, postprocess=True)  # builds the engine, sizes the arena
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    img = vae.decode(z, scale=1 / 0.18215, postprocess=True).sample
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"metric": "vae_decode_images_per_sec", "value": batch / (ms * 1e-3), "unit": "images/s", "batch": batch, "ms": round(ms, 2),
+            "image_shape": list(img.shape[1:]), "dtype": "f32", "finite": bool(torch.isfinite(img).all()),
+            "workload": "AutoencoderKL decode (SD v1 decoder: 49.5 M parameters, 1.24 TFLOP per 64x64 latent -> 78 GFLOP per 8x32 latent) on the "
+                        "fp32 path (split-TF32 tcgen05 contractions where the shapes allow, fp32 SIMT otherwise); parity 1e-5 vs "
+                        "oracle/vae_oracle.py (tests/test_gpu_vae.py; parity unpinned: diffusers absent)"}
 
 
 def run_ours(args):
@@ -614,6 +645,14 @@ def run_ours(args):
                 "avg_launch_ms": round(cls_t[g] / cls_n[g], 5), "share_of_step": kernels[g]["share"], "traffic": None,
                 "timing": "CUDA events around every launch of the same K steps, run as a second pass right after the timed region "
                           "(events between launches switch off programmatic dependent launch: that pass took %.3f ms/step)" % prof_ms}
+    if "tblock" in cls_t and cls_t["tblock"] > 0:
+        # second-largest class: the fused transformer block (csrc/tblock.cu).  `tflops` counts the reference's operations
+        # (to_q / QK^T / PV / to_out per attention); the kernel executes the algebraically folded form (8x fewer attention FLOPs)
+        tb = cls_f["tblock"] / (cls_t["tblock"] * 1e-3) / 1e12
+        roofline["fused_block"] = {"kernel": "tblock_unet_kernel (tcgen05 / TMEM / TMA, cta_group::2)", "bound": "tensor",
+                                   "achieved_reference_ops": round(tb, 2), "frac": round(tb / peaks["tf_burst"], 4),
+                                   "launches_per_step": cls_n["tblock"], "share_of_step": kernels["tblock"]["share"],
+                                   "evidence": "profiles/R2d_ncu_tblock.txt, profiles/R2g_tblock_trace_pair*.txt"}
     tr = load_traffic()
     if tr and variant == "unet" and B == tr.get("batch"):
         roofline["traffic"] = tr["gemm_tc_kernel"]["dram_bytes_per_launch"]
@@ -639,6 +678,11 @@ def run_ours(args):
         out["train_step"] = train
     if fp32 is not None:
         out["fp32_mode"] = fp32
+    if world == 1 and args.vae_batch > 0:
+        try:
+            out["vae_decode"] = vae_leg(dev, W, args.vae_batch)
+        except Exception as ex:   # a side leg must not cost the headline line
+            out["vae_decode"] = {"error": f"{type(ex).__name__}: {ex}"}
     out.update(extra)
     if world == 1 and args.eager_steps > 0:
         try:
@@ -667,6 +711,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the training leg (0: skip it)")
     ap.add_argument("--fp32-steps", type=int, default=3, help="timed steps of the fp32-mode leg on rank 0 (0: skip it)")
     ap.add_argument("--train-batch", type=int, default=224, help="GLOBAL batch of the training leg (BASELINE config 4)")
+    ap.add_argument("--vae-batch", type=int, default=64, help="latents of the VAE-decode leg on rank 0 (0: skip it)")
     ap.add_argument("--eager-steps", type=int, default=5, help="timed steps of the torch-eager-on-GPU comparator (0: skip it)")
     ap.add_argument("--ddim-batches", default="1,16,256,1024,4096", help="global batches of the DDIM-50 sweep leg (config 5)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip strong-scaling / config-3 / config-5 legs")
