@@ -36,15 +36,18 @@ namespace {
 constexpr int TB_THREADS = 320;
 constexpr int TB_KB = TB_C / 64;                 // K blocks of a 320-wide operand
 constexpr int TB_ABLK = TB_M * 128;              // one [128 rows x 64 cols] 16-bit K-major block: 16 KB
-constexpr int TB_RING = 102400;                  // operand ring: five 20 KB slots ([160 rows x 64]; W1 boxes use 16 KB, attention units
-                                                 // 8 KB), or ten 10 KB slots in the CTA-pair build (every unit is half as large per CTA)
+constexpr int TB_RING = 92160;                   // operand ring: four 20 KB slots ([160 rows x 64]; W1 boxes use 16 KB, attention units
+                                                 // 8-16 KB), or nine 10 KB slots in the CTA-pair build (every unit is half as large per
+                                                 // CTA).  (One slot fewer than the first build: the 10 KB went to the bias vectors below --
+                                                 // the phase trace showed the hand-overs waiting on L2 latency of per-group bias loads.)
 constexpr int TB_MAXSLOT = 10;
 constexpr int TB_NCHUNK = TB_HID / TB_CHUNK;     // 20 feed-forward chunks
 constexpr int OFF_A = 0;
 constexpr int OFF_G = OFF_A + TB_KB * TB_ABLK;           // 81920: two [128 x 64] buffers (P of the attentions / GEGLU chunks)
 constexpr int OFF_RING = OFF_G + 2 * TB_ABLK;            // 114688
-constexpr int OFF_BFF = OFF_RING + TB_RING;              // 217088
-constexpr int OFF_CSM = OFF_BFF + 2 * TB_HID * 4;        // 227328
+constexpr int OFF_BFF = OFF_RING + TB_RING;              // 206848
+constexpr int OFF_CB = OFF_BFF + 2 * TB_HID * 4;         // 217088: cumulative stream biases [4][320] ++ proj_out bias [320]
+constexpr int OFF_CSM = OFF_CB + 5 * TB_C * 4;           // 223488
 constexpr int OFF_STAT = OFF_CSM + 4 * 64 * 4;           // 228352 (score constants: 2 attentions x up to 2 samples x 64)
 constexpr int OFF_BARS = OFF_STAT + 2 * TB_M * 8;        // 230400
 constexpr int TB_SMEM = OFF_BARS + 320;                  // 230720
@@ -93,6 +96,77 @@ WD_DEVINL void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t b
       : "memory");
 }
 
+// X + cb -> 16-bit operand copy in the A buffer.  NORM: (x - mean) * rstd as fp16 (LayerNorm without its affine part, which is folded
+// into the weights that consume the copy); else the raw value as fp16.  One out-of-line copy for the four call sites: fully inlined
+// the kernel was 148 KB of SASS, far beyond the instruction cache.  TMEM loads run one 32-column group ahead of the arithmetic; the
+// biases come from shared memory (the first build read them from global memory per group: five exposed L2 round trips per pass).
+template <int G>
+WD_DEVINL void x_stats_group(const uint32_t (&v)[32], const float* cbg, float& s, float& sq) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(cbg + i);
+    const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
+    const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
+    s += (x0 + x1) + (x2 + x3);
+    sq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq))));
+  }
+}
+WD_DEVINL void x_copy_group(const uint32_t (&v)[32], const float* cbg, uint8_t* sA, int row, int col0, float mu, float rstd) {
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(cbg + c8 * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(cbg + c8 * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (__uint_as_float(v[c8 * 8 + j]) + bb[j] - mu) * rstd;
+    *reinterpret_cast<uint4*>(sA + a_chunk_off(row, col0 + c8 * 8)) =
+        make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+  }
+}
+__device__ __noinline__ void x_to_a_fn(uint32_t t_row, const float* cb, bool norm, uint8_t* sA, float2* sStat, int row, int half, int q,
+                                       float ln_eps) {
+  float mu = 0.f, rstd = 1.f;
+  const int c0 = half * 160;
+  const uint32_t t0 = t_row + COL_X + c0;
+  uint32_t v0[32], v1[32];
+  if (norm) {
+    float s = 0.f, sq = 0.f;
+    tmem_ld_32x32b_x32(t0, v0);
+#pragma unroll 1
+    for (int gp = 0; gp < 2; ++gp) {  // groups (0, 1), (2, 3)
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(t0 + (2 * gp + 1) * 32, v1);
+      x_stats_group<0>(v0, cb + c0 + (2 * gp) * 32, s, sq);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(t0 + (2 * gp + 2) * 32, v0);
+      x_stats_group<0>(v1, cb + c0 + (2 * gp + 1) * 32, s, sq);
+    }
+    tmem_ld_wait();
+    x_stats_group<0>(v0, cb + c0 + 4 * 32, s, sq);
+    sStat[half * TB_M + row] = make_float2(s, sq);
+    named_barrier_sync(1 + q, 64);  // the two warps that share this lane quarter
+    const float2 o = sStat[(half ^ 1) * TB_M + row];
+    mu = (s + o.x) * (1.0f / TB_C);
+    const float var = fmaxf((sq + o.y) * (1.0f / TB_C) - mu * mu, 0.f);
+    rstd = rsqrtf(var + ln_eps);
+  }
+  tmem_ld_32x32b_x32(t0, v0);
+#pragma unroll 1
+  for (int gp = 0; gp < 2; ++gp) {
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(t0 + (2 * gp + 1) * 32, v1);
+    x_copy_group(v0, cb + c0 + (2 * gp) * 32, sA, row, c0 + (2 * gp) * 32, mu, rstd);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(t0 + (2 * gp + 2) * 32, v0);
+    x_copy_group(v1, cb + c0 + (2 * gp + 1) * 32, sA, row, c0 + (2 * gp + 1) * 32, mu, rstd);
+  }
+  tmem_ld_wait();
+  x_copy_group(v0, cb + c0 + 4 * 32, sA, row, c0 + 4 * 32, mu, rstd);
+  fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor core / TMA (async proxy)
+  tc_fence_before();
+}
+
 // SPT = samples per 128-token tile: 1 (a sample holds a multiple of 128 tokens) or 2 (64 tokens per sample, the 4 x 16 level).
 // With two samples the score GEMM runs against both samples' keys (N = 128, into the idle GEGLU accumulator columns), each row
 // soft-maxes its own sample's 64 score columns and writes zeros for the other sample's keys, and the output GEMM reduces over
@@ -101,8 +175,9 @@ template <bool PAIR, int SPT>
 WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, const CUtensorMap& mapF0, const CUtensorMap& mapF1,
                            const CUtensorMap& mapF2, const CUtensorMap& mapF3, const CUtensorMap& mapW1, const CUtensorMap& mapW2,
                            const CUtensorMap& mapWpo, const CUtensorMap& mapOut, const TBlockArgs& args) {
-  constexpr int TB_NSLOT = PAIR ? 10 : 5;
-  constexpr int TB_SLOT = TB_RING / TB_NSLOT;
+  constexpr int TB_NSLOT = PAIR ? 9 : 4;
+  constexpr int TB_SLOT = PAIR ? 10240 : 20480;
+  static_assert(TB_NSLOT * TB_SLOT <= TB_RING, "ring");
   constexpr int TILE_M = PAIR ? 2 * TB_M : TB_M;   // tokens per tile (both CTAs of a pair)
   constexpr uint32_t N_EPI = PAIR ? 16 : 8;        // epilogue-warp arrivals on an epilogue -> MMA barrier
   extern __shared__ __align__(1024) uint8_t tb_smem[];
@@ -113,6 +188,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
   uint8_t* const sRing = smem + OFF_RING;
   float* const sBff = reinterpret_cast<float*>(smem + OFF_BFF);
   float* const sC = reinterpret_cast<float*>(smem + OFF_CSM);
+  float* const sCb = reinterpret_cast<float*>(smem + OFF_CB);  // [4][320] cb ++ [320] b_po
   float2* const sStat = reinterpret_cast<float2*>(smem + OFF_STAT);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
@@ -166,6 +242,10 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
   // static data: the folded GEGLU bias (weights only) -> shared memory
   for (int i = threadIdx.x; i < 2 * TB_HID / 4; i += TB_THREADS)
     reinterpret_cast<float4*>(sBff)[i] = __ldg(reinterpret_cast<const float4*>(args.b_ff) + i);
+  for (int i = threadIdx.x; i < 4 * TB_C / 4; i += TB_THREADS)
+    reinterpret_cast<float4*>(sCb)[i] = __ldg(reinterpret_cast<const float4*>(args.cb) + i);
+  for (int i = threadIdx.x; i < TB_C / 4; i += TB_THREADS)
+    reinterpret_cast<float4*>(sCb + 4 * TB_C)[i] = __ldg(reinterpret_cast<const float4*>(args.b_po) + i);
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them
@@ -197,13 +277,14 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         else tma_load_3d(dst, mp, &bars[bar], c0, c1, c2);
       };
       // one N half of a [320 x 320] weight: 5 K blocks of [160 x 64] (pair: this CTA's 80 of the 160 rows)
-      auto weight_320_half = [&](const CUtensorMap* mp, int nh) {
-        for (int kb = 0; kb < TB_KB; ++kb) {
+      auto weight_320_units = [&](const CUtensorMap* mp, int nh, int kb0, int kb1) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           uint8_t* dst = acquire(160 * 128);
           load2(dst, mp, B_RING_FULL + slot, kb * 64, nh * 160 + (PAIR ? static_cast<int>(rank) * 80 : 0));
           advance();
         }
       };
+      auto weight_320_half = [&](const CUtensorMap* mp, int nh) { weight_320_units(mp, nh, 0, TB_KB); };
       // score operand of one attention: five K blocks of four [16 keys x 64] boxes, one per head (pair: this CTA's two heads)
       auto fold_m_units = [&](const CUtensorMap* mp, int sample) {
         for (int b = 0; b < TB_KB; ++b) {
@@ -259,13 +340,15 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       for (int tile = worker; tile < m_tiles; tile += nworkers, ++it) {
         const int m0 = tile * TILE_M + static_cast<int>(rank) * TB_M;  // this CTA's 128 rows
         const int sample = (tile * TILE_M) / args.HW;
-        // the first five weight units fill the ring while the previous tile finishes (exactly the ring's capacity: issuing more
-        // before the g operand could block on a slot that only this tile's MMAs -- which wait for g -- can free)
-        weight_320_half(&mapWpi, 0);
+        // the first weight units fill the ring while the previous tile finishes -- no more than the ring holds: issuing more
+        // before the g operand could block on a slot that only this tile's MMAs (which wait for g) can free
+        constexpr int PRE = TB_NSLOT < TB_KB ? TB_NSLOT : TB_KB;
+        weight_320_units(&mapWpi, 0, 0, PRE);
         // the A buffer is free once the previous tile's output store has read it
         mbar_wait(&bars[B_A_FREE], (it & 1) ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(&bars[B_A_FULL], (PAIR ? 2 : 1) * TB_KB * TB_ABLK);
         for (int kb = 0; kb < TB_KB; ++kb) load2(sA + kb * TB_ABLK, &mapG, B_A_FULL, kb * 64, m0);
+        weight_320_units(&mapWpi, 0, PRE, TB_KB);
         weight_320_half(&mapWpi, 1);
         if (stop_after(stage, 1)) continue;
         fold_m_units(&mapF0, sample);
@@ -447,53 +530,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
     };
     // X + cb -> 16-bit operand copy in the A buffer.  NORM: (x - mean) * rstd as fp16 (LayerNorm without its affine part, which
     // is folded into the weights that consume the copy); else the raw value as fp16.
-    auto x_to_a = [&](const float* cb, bool norm) {
-      float mu = 0.f, rstd = 1.f;
-      const int c0 = half * 160;
-      if (norm) {
-        float s = 0.f, sq = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < 5; ++g) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + COL_X + c0 + g * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + c0 + g * 32 + i));
-            const float x0 = __uint_as_float(v[i]) + b4.x, x1 = __uint_as_float(v[i + 1]) + b4.y;
-            const float x2 = __uint_as_float(v[i + 2]) + b4.z, x3 = __uint_as_float(v[i + 3]) + b4.w;
-            s += (x0 + x1) + (x2 + x3);
-            sq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq))));
-          }
-        }
-        sStat[half * TB_M + row] = make_float2(s, sq);
-        named_barrier_sync(1 + q, 64);  // the two warps that share this lane quarter
-        const float2 o = sStat[(half ^ 1) * TB_M + row];
-        mu = (s + o.x) * (1.0f / TB_C);
-        const float var = fmaxf((sq + o.y) * (1.0f / TB_C) - mu * mu, 0.f);
-        rstd = rsqrtf(var + args.ln_eps);
-      }
-#pragma unroll 1
-      for (int g = 0; g < 5; ++g) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + COL_X + c0 + g * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int col = c0 + g * 32 + c8 * 8;
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(cb + col));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(cb + col + 4));
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = (__uint_as_float(v[c8 * 8 + j]) + bb[j] - mu) * rstd;
-          *reinterpret_cast<uint4*>(sA + a_chunk_off(row, col)) =
-              make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-        }
-      }
-      fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor core / TMA (async proxy)
-      tc_fence_before();
-    };
+    auto x_to_a = [&](const float* cb, bool norm) { x_to_a_fn(t_row, cb, norm, sA, sStat, row, half, q, args.ln_eps); };
     // scores (+ per-sample constants) -> softmax over the L keys of each head -> fp16 probabilities, K-major P tile
     auto softmax_to_p = [&](const float* cs) {
       mbar_wait(&bars[B_S], n_s & 1);
@@ -564,7 +601,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       if (tr) TB_STAMP(1, it, 0);
       wait_acc();
       if (tr) TB_STAMP(1, it, 1);
-      x_to_a(args.cb, true);
+      x_to_a(sCb, true);
       if (tr) TB_STAMP(1, it, 2);
       if (stop_after(stage, 1)) { store_a_tile(m0); continue; }
       arrive_warp(B_A_READY);
@@ -576,7 +613,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         if (tr) TB_STAMP(1, it, 3 + 3 * a);
         wait_acc();
         if (tr) TB_STAMP(1, it, 4 + 3 * a);
-        x_to_a(args.cb + (1 + a) * TB_C, true);
+        x_to_a(sCb + (1 + a) * TB_C, true);
         if (tr) TB_STAMP(1, it, 5 + 3 * a);
         if (stop_after(stage, 2 + a)) { store_a_tile(m0); stopped = true; break; }
         arrive_warp(B_A_READY);
@@ -624,7 +661,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       // ---- x3 (raw) -> operand of proj_out ----
       wait_acc();
       if (tr) TB_STAMP(1, it, 10);
-      x_to_a(args.cb + 3 * TB_C, false);
+      x_to_a(sCb + 3 * TB_C, false);
       if (tr) TB_STAMP(1, it, 11);
       if (stop_after(stage, 4)) { store_a_tile(m0); continue; }
       arrive_warp(B_A_READY);
@@ -638,27 +675,34 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         float gs[32];  // 16 groups of 10 columns: [2 g] = sum, [2 g + 1] = sum of squares
 #pragma unroll
         for (int i = 0; i < 32; ++i) gs[i] = 0.f;
+        // the TMEM group and the x_in row piece of group g + 1 are in flight while group g is combined
+        const float* bpo = sCb + 4 * TB_C + c0;
+        uint32_t v[2][32];
+        uint4 r4[2][4];
+        tmem_ld_32x32b_x32(t_row + COL_X + c0, v[0]);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) r4[0][c8] = __ldg(reinterpret_cast<const uint4*>(xr + c8 * 8));
 #pragma unroll
         for (int g = 0; g < 5; ++g) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + COL_X + c0 + g * 32, v);
-          uint4 r4[4];
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) r4[c8] = __ldg(reinterpret_cast<const uint4*>(xr + g * 32 + c8 * 8));
           tmem_ld_wait();
+          if (g + 1 < 5) {
+            tmem_ld_32x32b_x32(t_row + COL_X + c0 + (g + 1) * 32, v[(g + 1) & 1]);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) r4[(g + 1) & 1][c8] = __ldg(reinterpret_cast<const uint4*>(xr + (g + 1) * 32 + c8 * 8));
+          }
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             const int cl = g * 32 + c8 * 8;  // column inside this thread's 160
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.b_po + c0 + cl));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.b_po + c0 + cl + 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(bpo + cl);
+            const float4 b1 = *reinterpret_cast<const float4*>(bpo + cl + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const uint32_t ru[4] = {r4[c8].x, r4[c8].y, r4[c8].z, r4[c8].w};
+            const uint32_t ru[4] = {r4[g & 1][c8].x, r4[g & 1][c8].y, r4[g & 1][c8].z, r4[g & 1][c8].w};
             float f[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 t = unpack_f16x2(ru[j]);
-              f[2 * j] = __uint_as_float(v[c8 * 8 + 2 * j]) + bb[2 * j] + t.x;
-              f[2 * j + 1] = __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bb[2 * j + 1] + t.y;
+              f[2 * j] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j]) + bb[2 * j] + t.x;
+              f[2 * j + 1] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j + 1]) + bb[2 * j + 1] + t.y;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
