@@ -56,7 +56,7 @@ def test_unet_forward_vs_reference_golden(unet, golden_dir):
     with torch.no_grad():
         eps = m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
     assert eps.shape == (2, 4, 8, 32) and eps.dtype == torch.float32
-    assert m._engine.last_launch_count > 50
+    assert m._engine.last_launch_count > 30
     err = relerr(eps, torch.from_numpy(g["eps"]))
     print("unet eps max-rel err vs reference:", err)
     assert err < TOL_BF16

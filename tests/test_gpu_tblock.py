@@ -76,8 +76,8 @@ def _reference(W, g, x_in, ctx, B, HW, L, mid=False):
     return out
 
 
-def _run(W, g16, x16, ctx16, B, HW, L, stage, want_stats=False):
-    tensors = [g16, x16, ctx16] + [W[k] for k in ORDER]
+def _run(W, g16, x16, ctx16, B, HW, L, stage, want_stats=False, gn=None):
+    tensors = [g16, x16, ctx16] + [W[k] for k in ORDER] + (list(gn) if gn is not None else [])
     arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
     out = torch.full((B * HW, CH), float("nan"), device=DEV, dtype=torch.float16)
     stats = torch.zeros((B, 32, HW // 32, 2), device=DEV, dtype=torch.float32) if want_stats else None
@@ -137,3 +137,28 @@ def test_fused_block_middle_form(B, HW, L):
     e = relerr(out.float(), ref[5])
     print(f"middle form B={B} HW={HW} L={L}: {e:.2e}")
     assert e < TOL
+
+
+@pytest.mark.parametrize("B,HW,L", [(2, 256, 10), (5, 128, 16), (7, 64, 10), (96, 256, 10)])
+def test_fused_block_with_its_input_groupnorm(B, HW, L):
+    """SpatialTransformer.norm (GroupNorm32, eps 1e-6, no SiLU: unet.py:388,161-162) inside the kernel: the tile of x_in is normalised in
+    shared memory from the producer's partial statistics before proj_in; everything downstream as in the 25-tensor form."""
+    W = _weights(60 + B)
+    gen = torch.Generator().manual_seed(300 + B)
+    x16 = (torch.randn(B * HW, CH, generator=gen) * 1.5 + 0.3).to(DEV).to(torch.float16)
+    ctx16 = torch.randn(B * L, CH, generator=gen).to(DEV).to(torch.bfloat16)
+    gamma = (1.0 + 0.1 * torch.randn(CH, generator=gen)).to(DEV)
+    beta = (0.05 * torch.randn(CH, generator=gen)).to(DEV)
+    xf = x16.float().view(B, HW, CH)
+    g = F.group_norm(xf.transpose(1, 2), 32, gamma, beta, eps=1e-6).transpose(1, 2).reshape(B * HW, CH)
+    g16 = g.to(torch.bfloat16)  # the kernel rounds the normalised operand to bf16 like groupnorm_apply_bulk_kernel does
+    ref = _reference(W, g16.float(), x16.float(), ctx16.float(), B, HW, L)
+    dummy = torch.zeros_like(g16)
+    out, stats = _run(W, dummy, x16, ctx16, B, HW, L, 0, want_stats=True, gn=(gamma, beta))
+    e = relerr(out.float(), ref[0])
+    s1, _ = _run(W, dummy, x16, ctx16, B, HW, L, 1, gn=(gamma, beta))
+    e1 = relerr(s1.float(), ref[1])
+    print(f"fused block with input GroupNorm B={B} HW={HW}: out {e:.2e}, after proj_in {e1:.2e}")
+    assert e < TOL and e1 < TOL
+    a, _ = _run(W, g16, x16, ctx16, B, HW, L, 0)   # the 25-tensor form on the pre-normalised operand
+    assert relerr(out.float(), a.float()) < 2.0 ** -9

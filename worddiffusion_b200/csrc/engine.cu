@@ -1181,7 +1181,8 @@ struct PlanBuilder {
 
   // ---- the whole transformer block as ONE kernel (tblock.cu): unet.UNetModel, 128-token tiles inside one sample ----
   // mid form (t.mid): `g` is the fp16 residual stream after the proj_in GEMM, `out` the raw fp16 stream after the feed-forward
-  bool st_block_fused(std::vector<Op>& ops, const STL& s, const TBlockL& t, const Act& x_in, const Act& g, Act& out) {
+  bool st_block_fused(std::vector<Op>& ops, const STL& s, const TBlockL& t, const Act& x_in, const Act& g, Act& out,
+                      const NormW* gn_in = nullptr) {
     const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = TB_C;
     const int Ltot = plan->Ltot;
     const bool mid = t.mid;
@@ -1205,6 +1206,14 @@ struct PlanBuilder {
     a.stage = mid ? 4 : 0;
     a.mid = mid ? 1 : 0;
     a.pair = tblock_use_pair(HW) ? 1 : 0;
+    if (gn_in) {
+      if (!x_in.pslots || mid) { err = "fused transformer block: the input carries no GroupNorm statistics"; return false; }
+      a.gn_in_partial = x_in.stats;
+      a.gn_in_slots = x_in.pslots;
+      a.gn_gamma = gn_in->g;
+      a.gn_beta = gn_in->b;
+      a.gn_eps = 1e-6f;  // SpatialTransformer.norm: Normalize(in_channels), unet.py:161-162
+    }
     const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
     if (!mid && epilogue_stats_ok(HW, C)) {
       a.gn_partial = out.stats;
@@ -1238,9 +1247,15 @@ struct PlanBuilder {
   bool st_block(std::vector<Op>& ops, const STL& s, const Act& x_in, const std::vector<bf16*>& kv, Act& out) {
     const int H = x_in.H, W = x_in.W, HW = H * W, M = B * HW, C = s.heads * s.dh;
     const int Ltot = plan->Ltot;
+    const bool tb_ok = fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && x_in.f16 && s.heads * s.dh == TB_C;
+    if (tb_ok && !s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2) && x_in.C == TB_C && s.C == TB_C && tblock_gn_fused()) {
+      // the SpatialTransformer's GroupNorm runs inside the fused kernel (x_in's partial statistics come from its producer)
+      Act xs = x_in;
+      if (!ensure_stats(ops, xs)) return false;
+      return st_block_fused(ops, s, s.blocks[0], xs, xs, out, &s.gn);
+    }
     Act g;
     if (!gn_op(ops, {x_in}, s.gn, 1e-6f, 0, g)) return false;
-    const bool tb_ok = fold_out && s.blocks.size() == 1 && s.blocks[0].w_fold && x_in.f16 && s.heads * s.dh == TB_C;
     if (tb_ok && !s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2) && x_in.C == TB_C && s.C == TB_C)
       return st_block_fused(ops, s, s.blocks[0], x_in, g, out);
     if (tb_ok && s.blocks[0].mid && (HW % TB_M == 0 || HW == TB_M / 2)) {
@@ -2340,8 +2355,11 @@ extern "C" int wd_op_attention(const void* q, int ldq, const void* k, const void
 // out: fp16 [M,320]; gn_partial: fp32 [B][32][HW/32][2] or NULL.  Synchronises the stream.
 extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int B, int HW, int L, int stage, void* out_f16,
                                  float* gn_partial, void* stream) {
-  if (!tensors || n_tensors != 25 || !out_f16) return fail(WD_ERR_INVALID, "op_tblock_unet: expects 25 tensors");
-  for (int i = 0; i < 25; ++i)
+  // 27 tensors: [25] / [26] = norm.weight / norm.bias of the SpatialTransformer's GroupNorm -- the kernel normalises x_in itself
+  // (tensors[0] is ignored) from partial statistics computed here by groupnorm_stats_kernel
+  if (!tensors || (n_tensors != 25 && n_tensors != 27) || !out_f16) return fail(WD_ERR_INVALID, "op_tblock_unet: expects 25 or 27 tensors");
+  const bool gn_in = n_tensors == 27;
+  for (int i = 0; i < n_tensors; ++i)
     if (!tensors[i]) return fail(WD_ERR_INVALID, "op_tblock_unet: tensor %d is null", i);
   if (B < 1 || (HW % TB_M && HW != TB_M / 2) || L < 1 || L > TB_KEYS || stage < 0 || stage > 5)
     return fail(WD_ERR_INVALID, "op_tblock_unet: bad shape");
@@ -2368,6 +2386,8 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     bf16* fold_out = A.alloc<bf16>(static_cast<size_t>(B) * L * 2 * TB_FOLD_N);
     float* cvec = A.alloc<float>(static_cast<size_t>(B) * L * 2 * TB_HEADS);
     bf16* eye_d = A.alloc<bf16>(static_cast<size_t>(C) * C);
+    const int gn_slots = groupnorm_stats_slots(HW);
+    float* gn_part = A.alloc<float>(static_cast<size_t>(B) * 32 * gn_slots * 2);
 #define TB_TRY(x) if ((x) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "op_tblock_unet: %s", cudaGetErrorString(cudaGetLastError())); break; }
     TB_TRY(repack_linear_launch(F(3), w_pi, C, C, C, 0, 0, 0, 0, s));
     TB_TRY(repack_linear_launch(F(23), w_po, C, C, C, 0, 0, 0, 1, s));
@@ -2404,9 +2424,19 @@ extern "C" int wd_op_tblock_unet(const void* const* tensors, int n_tensors, int 
     a.stage = mid ? 4 : stage;
     a.mid = mid ? 1 : 0;
     a.pair = tblock_use_pair(HW) ? 1 : 0;
+    if (gn_in) {
+      if (mid) { rc = fail(WD_ERR_INVALID, "op_tblock_unet: the middle form has no input GroupNorm"); break; }
+      GroupNormStatsArgs st{static_cast<const bf16*>(tensors[1]), C, gn_part, HW, C, C / 32, gn_slots, 1};
+      TB_TRY(groupnorm_stats_launch(st, B, s));
+      a.gn_in_partial = gn_part;
+      a.gn_in_slots = gn_slots;
+      a.gn_gamma = F(25);
+      a.gn_beta = F(26);
+      a.gn_eps = 1e-6f;
+    }
     const int wbox = a.pair ? 80 : 160, w1box = a.pair ? TB_CHUNK : 2 * TB_CHUNK;
     const int fold_ld = 2 * TB_FOLD_N;
-    bool ok = tmap_encode_2d_bf16(&T.mapG, mid ? tensors[1] : tensors[0], C, M, C, 64, TB_M) &&
+    bool ok = tmap_encode_2d_bf16(&T.mapG, (mid || gn_in) ? tensors[1] : tensors[0], C, M, C, 64, TB_M) &&
               tmap_encode_2d_bf16(&T.mapWpi, mid ? eye_d : w_pi, C, C, C, 64, wbox) &&
               tmap_encode_2d_bf16(&T.mapW1, w_ff1, C, 8 * C, C, 64, w1box) &&
               tmap_encode_2d_bf16(&T.mapW2, w_ff2, 4 * C, C, 4 * C, 64, wbox) && tmap_encode_2d_bf16(&T.mapWpo, w_po, C, C, C, 64, wbox) &&

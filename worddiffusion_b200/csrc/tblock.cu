@@ -167,6 +167,134 @@ __device__ __noinline__ void x_to_a_fn(uint32_t t_row, const float* cb, bool nor
   tc_fence_before();
 }
 
+// GroupNorm of the input tile in place (fp16 x_in -> bf16 g): per-sample scale / shift from the producer's partial statistics.
+// Out of line (once per tile; the kernel's hot loops are sensitive to its code size).
+template <int SPT>
+__device__ __noinline__ void gn_in_fn(const TBlockArgs& args, uint8_t* sA, uint8_t* sG, uint64_t* a_full, uint32_t parity, int sample,
+                                      int n_samples, int et, int row, int half, int q) {
+    // ---- GroupNorm of the input tile in place (fp16 x_in -> bf16 g): per-sample scale / shift from the producer's partials ----
+        float* const sGn = reinterpret_cast<float*>(sG);  // [SPT samples][mean/rstd 64 | scale 320 | shift 320] (sG is idle here)
+        constexpr int GN_STRIDE = 64 + 2 * TB_C;
+        if (et < 32 * SPT) {
+          const int sl = et >> 5, g = et & 31;
+          float S = 0.f, Q = 0.f;
+          if (sample + sl < n_samples) {
+            const float2* part = reinterpret_cast<const float2*>(args.gn_in_partial) + (static_cast<size_t>(sample + sl) * 32 + g) * args.gn_in_slots;
+            for (int k = 0; k < args.gn_in_slots; ++k) {  // fixed order: bit-reproducible, the same fold as groupnorm_apply_bulk_kernel
+              const float2 t = __ldg(part + k);
+              S += t.x;
+              Q += t.y;
+            }
+          }
+          const float inv_n = 1.0f / static_cast<float>((TB_C / 32) * args.HW);
+          const float mean = S * inv_n;
+          const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+          sGn[sl * GN_STRIDE + g] = mean;
+          sGn[sl * GN_STRIDE + 32 + g] = rsqrtf(var + args.gn_eps);
+        }
+        named_barrier_sync(6, 256);
+        for (int i = et; i < TB_C * SPT; i += 256) {
+          const int sl = i / TB_C, c = i - sl * TB_C, g = c / (TB_C / 32);
+          const float sc = sGn[sl * GN_STRIDE + 32 + g] * __ldg(args.gn_gamma + c);
+          sGn[sl * GN_STRIDE + 64 + c] = sc;
+          sGn[sl * GN_STRIDE + 64 + TB_C + c] = __ldg(args.gn_beta + c) - sGn[sl * GN_STRIDE + g] * sc;
+        }
+        named_barrier_sync(6, 256);
+        mbar_wait(a_full, parity);  // this CTA's rows have landed
+        {
+          const int sl = SPT == 2 ? (q >> 1) : 0;
+          const float* scp = sGn + sl * GN_STRIDE + 64 + half * 160;
+          const float* shp = scp + TB_C;
+#pragma unroll 4
+          for (int c8 = 0; c8 < 20; ++c8) {
+            uint4* const p = reinterpret_cast<uint4*>(sA + a_chunk_off(row, half * 160 + c8 * 8));
+            const uint4 xv = *p;
+            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float4 s0 = *reinterpret_cast<const float4*>(scp + c8 * 8), s1 = *reinterpret_cast<const float4*>(scp + c8 * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(shp + c8 * 8), h1 = *reinterpret_cast<const float4*>(shp + c8 * 8 + 4);
+            const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_f16x2(xu[j]);
+              o[j] = pack_bf16x2(fmaf(f.x, scv[2 * j], shv[2 * j]), fmaf(f.y, scv[2 * j + 1], shv[2 * j + 1]));
+            }
+            *p = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+}
+
+// proj_out accumulator + bias + x_in -> fp16 tile in the A buffer (its MMAs have retired), GroupNorm partials of the output.
+// (An out-of-line copy of this one measured 2.8 k cycles slower per tile: profiles/R2y_trace.txt.)
+WD_DEVINL void out_tile_fn(const TBlockArgs& args, uint32_t t_row, uint8_t* sA, const float* sCb, int m0, int row, int half, int q,
+                                         int lane) {
+    const int c0 = half * 160;
+    const bool valid = m0 + row < args.M;
+    const __half* xr = args.x_in + static_cast<size_t>(valid ? m0 + row : 0) * args.x_in_ld + c0;
+    float gs[32];  // 16 groups of 10 columns: [2 g] = sum, [2 g + 1] = sum of squares
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gs[i] = 0.f;
+    // the TMEM group and the x_in row piece of group g + 1 are in flight while group g is combined
+    const float* bpo = sCb + 4 * TB_C + c0;
+    uint32_t v[2][32];
+    uint4 r4[2][4];
+    tmem_ld_32x32b_x32(t_row + COL_X + c0, v[0]);
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) r4[0][c8] = __ldg(reinterpret_cast<const uint4*>(xr + c8 * 8));
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      tmem_ld_wait();
+      if (g + 1 < 5) {
+        tmem_ld_32x32b_x32(t_row + COL_X + c0 + (g + 1) * 32, v[(g + 1) & 1]);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) r4[(g + 1) & 1][c8] = __ldg(reinterpret_cast<const uint4*>(xr + (g + 1) * 32 + c8 * 8));
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const int cl = g * 32 + c8 * 8;  // column inside this thread's 160
+        const float4 b0 = *reinterpret_cast<const float4*>(bpo + cl);
+        const float4 b1 = *reinterpret_cast<const float4*>(bpo + cl + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t ru[4] = {r4[g & 1][c8].x, r4[g & 1][c8].y, r4[g & 1][c8].z, r4[g & 1][c8].w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_f16x2(ru[j]);
+          f[2 * j] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j]) + bb[2 * j] + t.x;
+          f[2 * j + 1] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j + 1]) + bb[2 * j + 1] + t.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int grp = (cl + j) / 10;  // compile-time after unrolling
+          gs[2 * grp] += f[j];
+          gs[2 * grp + 1] = fmaf(f[j], f[j], gs[2 * grp + 1]);
+        }
+        *reinterpret_cast<uint4*>(sA + a_chunk_off(row, c0 + cl)) =
+            make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    if (args.gn_partial) {
+      // the 32 rows of a warp belong to one sample and one 32-row slot: reduce over the rows, 8 groups per pass
+      const int mw = m0 + q * 32;
+      const int smp_w = mw / args.HW;  // the sample of this warp's 32 rows
+      const int slot = (mw % args.HW) >> 5, nslot = args.HW >> 5;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float part[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[i] = gs[p * 16 + i];
+        const float tot = warp_transpose_reduce16(part, lane);
+        if (lane < 16 && mw < args.M) {
+          const int g = half * 16 + p * 8 + (lane >> 1);
+          args.gn_partial[((static_cast<size_t>(smp_w) * 32 + g) * nslot + slot) * 2 + (lane & 1)] = tot;
+        }
+      }
+    }
+}
+
 // SPT = samples per 128-token tile: 1 (a sample holds a multiple of 128 tokens) or 2 (64 tokens per sample, the 4 x 16 level).
 // With two samples the score GEMM runs against both samples' keys (N = 128, into the idle GEGLU accumulator columns), each row
 // soft-maxes its own sample's 64 score columns and writes zeros for the other sample's keys, and the output GEMM reduces over
@@ -200,6 +328,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
   const int n_samples = args.M / args.HW;
   constexpr uint32_t COL_SC = SPT == 2 ? COL_G : COL_S;  // score accumulator: N = 64 SPT columns
   const int stage = args.stage;
+  const bool gn_in = args.gn_in_partial != nullptr;
   const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int nworkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   // a barrier the peer CTA signals too lives in the leader: its shared::cluster address (the local one in the single-CTA build)
@@ -346,8 +475,16 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
         weight_320_units(&mapWpi, 0, 0, PRE);
         // the A buffer is free once the previous tile's output store has read it
         mbar_wait(&bars[B_A_FREE], (it & 1) ^ 1);
-        if (rank == 0) mbar_arrive_expect_tx(&bars[B_A_FULL], (PAIR ? 2 : 1) * TB_KB * TB_ABLK);
-        for (int kb = 0; kb < TB_KB; ++kb) load2(sA + kb * TB_ABLK, &mapG, B_A_FULL, kb * 64, m0);
+        if (gn_in) {  // the epilogue warps of THIS CTA normalise the tile first: its own barrier, its own 80 KB
+          mbar_arrive_expect_tx(&bars[B_A_FULL], TB_KB * TB_ABLK);
+          for (int kb = 0; kb < TB_KB; ++kb) {
+            if (PAIR) tma_load_2d_pair(sA + kb * TB_ABLK, &mapG, mapa_shared(smem_u32(&bars[B_A_FULL]), rank), kb * 64, m0);
+            else tma_load_2d(sA + kb * TB_ABLK, &mapG, &bars[B_A_FULL], kb * 64, m0);
+          }
+        } else {
+          if (rank == 0) mbar_arrive_expect_tx(&bars[B_A_FULL], (PAIR ? 2 : 1) * TB_KB * TB_ABLK);
+          for (int kb = 0; kb < TB_KB; ++kb) load2(sA + kb * TB_ABLK, &mapG, B_A_FULL, kb * 64, m0);
+        }
         weight_320_units(&mapWpi, 0, PRE, TB_KB);
         weight_320_half(&mapWpi, 1);
         if (stop_after(stage, 1)) continue;
@@ -421,7 +558,8 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       for (int tile = worker; tile < m_tiles; tile += nworkers, ++it) {
         // ---- proj_in: X = g Wpi^T ----
         TB_STAMP(0, it, 0);
-        mbar_wait(&bars[B_A_FULL], it & 1);
+        if (gn_in) wait_a_ready();  // the tile has landed AND the epilogue warps (of both CTAs) have normalised it in place
+        else mbar_wait(&bars[B_A_FULL], it & 1);
         wait_epi(B_X_FREE, (it & 1) ^ 1);  // the previous tile's epilogue has read its last accumulator
         tc_fence_after();
         TB_STAMP(0, it, 1);
@@ -471,6 +609,8 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sG + b * TB_ABLK));
           for (int nh = 0; nh < 2; ++nh) {
             const uint64_t b_desc = make_smem_desc_sw128(ring_wait());
+            // (handing the chunk over as a TMEM-resident A operand -- tcgen05.st by the epilogue, tcgen05.mma [d], [a_tmem], b_desc --
+            //  was correct on its first run and measured SLOWER: 0.896 vs 0.846 ms for the four launches, profiles/R2v_*)
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma(tmem_base + COL_X + nh * 160, a_desc + 2 * k, b_desc + 2 * k, ID_BF16_160, 1u);
             ring_release();
@@ -596,6 +736,13 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       }
       named_barrier_sync(6, 256);
 
+      if (gn_in) {
+        gn_in_fn<SPT>(args, sA, sG, &bars[B_A_FULL], it & 1, sample, n_samples, et, row, half, q);
+        fence_proxy_async();
+        named_barrier_sync(6, 256);  // sGn (in the P / GEGLU buffer) has been read by everybody
+        arrive_warp(B_A_READY);
+      }
+
       // ---- after proj_in ----
       const bool tr = warp == 2 && lane == 0;
       if (tr) TB_STAMP(1, it, 0);
@@ -668,72 +815,7 @@ WD_DEVINL void tblock_body(const CUtensorMap& mapG, const CUtensorMap& mapWpi, c
       // ---- proj_out accumulator + bias + x_in -> fp16 tile in the A buffer (its MMAs have retired), GroupNorm partials ----
       wait_acc();
       if (tr) TB_STAMP(1, it, 12);
-      {
-        const int c0 = half * 160;
-        const bool valid = m0 + row < args.M;
-        const __half* xr = args.x_in + static_cast<size_t>(valid ? m0 + row : 0) * args.x_in_ld + c0;
-        float gs[32];  // 16 groups of 10 columns: [2 g] = sum, [2 g + 1] = sum of squares
-#pragma unroll
-        for (int i = 0; i < 32; ++i) gs[i] = 0.f;
-        // the TMEM group and the x_in row piece of group g + 1 are in flight while group g is combined
-        const float* bpo = sCb + 4 * TB_C + c0;
-        uint32_t v[2][32];
-        uint4 r4[2][4];
-        tmem_ld_32x32b_x32(t_row + COL_X + c0, v[0]);
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) r4[0][c8] = __ldg(reinterpret_cast<const uint4*>(xr + c8 * 8));
-#pragma unroll
-        for (int g = 0; g < 5; ++g) {
-          tmem_ld_wait();
-          if (g + 1 < 5) {
-            tmem_ld_32x32b_x32(t_row + COL_X + c0 + (g + 1) * 32, v[(g + 1) & 1]);
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) r4[(g + 1) & 1][c8] = __ldg(reinterpret_cast<const uint4*>(xr + (g + 1) * 32 + c8 * 8));
-          }
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const int cl = g * 32 + c8 * 8;  // column inside this thread's 160
-            const float4 b0 = *reinterpret_cast<const float4*>(bpo + cl);
-            const float4 b1 = *reinterpret_cast<const float4*>(bpo + cl + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const uint32_t ru[4] = {r4[g & 1][c8].x, r4[g & 1][c8].y, r4[g & 1][c8].z, r4[g & 1][c8].w};
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 t = unpack_f16x2(ru[j]);
-              f[2 * j] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j]) + bb[2 * j] + t.x;
-              f[2 * j + 1] = __uint_as_float(v[g & 1][c8 * 8 + 2 * j + 1]) + bb[2 * j + 1] + t.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int grp = (cl + j) / 10;  // compile-time after unrolling
-              gs[2 * grp] += f[j];
-              gs[2 * grp + 1] = fmaf(f[j], f[j], gs[2 * grp + 1]);
-            }
-            *reinterpret_cast<uint4*>(sA + a_chunk_off(row, c0 + cl)) =
-                make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        if (args.gn_partial) {
-          // the 32 rows of a warp belong to one sample and one 32-row slot: reduce over the rows, 8 groups per pass
-          const int mw = m0 + q * 32;
-          const int smp_w = mw / args.HW;  // the sample of this warp's 32 rows
-          const int slot = (mw % args.HW) >> 5, nslot = args.HW >> 5;
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            float part[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) part[i] = gs[p * 16 + i];
-            const float tot = warp_transpose_reduce16(part, lane);
-            if (lane < 16 && mw < args.M) {
-              const int g = half * 16 + p * 8 + (lane >> 1);
-              args.gn_partial[((static_cast<size_t>(smp_w) * 32 + g) * nslot + slot) * 2 + (lane & 1)] = tot;
-            }
-          }
-        }
-      }
+      out_tile_fn(args, t_row, sA, sCb, m0, row, half, q, lane);
       if (tr) TB_STAMP(1, it, 13);
       store_a_tile(m0);
       if (tr) TB_STAMP(1, it, 14);
@@ -877,6 +959,15 @@ static bool tblock_trace_enabled() {
   if (v < 0) {
     const char* e = getenv("WD_TBLOCK_TRACE");
     v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
+bool tblock_gn_fused() {  // env WD_TBLOCK_GN (default on): the block's input GroupNorm runs inside the kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_TBLOCK_GN");
+    v = e ? (atoi(e) != 0) : 1;
   }
   return v != 0;
 }

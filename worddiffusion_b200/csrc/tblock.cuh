@@ -44,6 +44,13 @@ struct TBlockArgs {
   const __half* x_in;  // [M, x_in_ld] fp16: the SpatialTransformer input (residual of proj_out)
   int x_in_ld;
   float* gn_partial;   // GroupNorm partials of `out`: [sample][32 groups][HW / 32][2], or null
+  // GroupNorm of the block's input inside the kernel (SpatialTransformer.norm, unet.py:388: GroupNorm32 without SiLU, eps 1e-6): when
+  // gn_in_partial != null, mapG maps x_in itself (fp16) and the epilogue warps normalise the tile in shared memory before proj_in
+  const float* gn_in_partial;  // partial statistics of x_in: [sample][32 groups][gn_in_slots][2]
+  int gn_in_slots;
+  const float* gn_gamma;       // [320]
+  const float* gn_beta;
+  float gn_eps;
   float ln_eps;
   int pair;            // 1: CTA-pair kernel (256-token tiles, HW % 256 == 0; weight maps encoded with half-unit boxes)
   int mid;             // 1: "middle" form for SpatialTransformers whose in/out channels differ from 320 (proj_in / proj_out stay
@@ -67,6 +74,7 @@ struct TBlockLaunch {
 };
 
 bool tblock_enabled();  // env WD_TBLOCK (default on)
+bool tblock_gn_fused();        // env WD_TBLOCK_GN (default on): SpatialTransformer.norm inside the kernel
 bool tblock_use_pair(int HW);  // env WD_TBLOCK_PAIR (default on) and HW % 256 == 0
 cudaError_t tblock_launch(const TBlockLaunch& L, int num_sms, cudaStream_t stream);
 
