@@ -92,7 +92,12 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  // persistent: CTA b walks tiles b, b + gridDim.x, ... (n-tile fastest, so concurrent CTAs share the A rows in L2); the chunk
+  // accumulators alternate between the two TMEM buffers ACROSS tiles, so the epilogue of one tile (registers -> global) runs under
+  // the MMAs of the next.  (The first build launched one CTA per tile: ~16 us of prologue / pipeline fill / epilogue per tile
+  // against 9 us of MMA time at K = 320, profiles/R2q_fp32_launches.txt.)
+  const int n_tiles = args.N / TC_BN;
+  const int total_tiles = n_tiles * (args.M / TC_BM);
   const int nkb = args.K / TC_BK;
   const int kpc = args.kb_per_chunk;
   const int nchunks = (nkb + kpc - 1) / kpc;
@@ -127,6 +132,8 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int cbt = args.cb1 + args.cb2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
       int img = 0, oh0 = 0;
       if (args.conv) {
         img = m0 / args.HW;
@@ -155,16 +162,19 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
           phase ^= 1;
         }
       }
+      }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32_f32(TC_BM, TC_BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        if (ch >= 2) {  // the epilogue warps have added chunk ch - 2 (same buffer) to their registers
-          mbar_wait(&acc_empty[buf], ((ch >> 1) - 1) & 1);
+      uint32_t gch = 0;  // chunks issued so far by this CTA (over all its tiles)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+      for (int ch = 0; ch < nchunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        if (gch >= 2) {  // the epilogue warps have added the chunk that used this buffer last to their registers
+          mbar_wait(&acc_empty[buf], ((gch >> 1) - 1) & 1);
           tc_fence_after();
         }
         const uint32_t d = tmem_base + buf * 256;
@@ -195,48 +205,57 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   } else {
     // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32); thread = one output row
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float acc[TC_BN];  // second accumulation level, fp32 registers (every index below is a compile-time constant)
+    uint32_t gch = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
+      const int m = m0 + q * 32 + lane;
+      float acc[TC_BN];  // second accumulation level, fp32 registers (every index below is a compile-time constant)
 #pragma unroll 1
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int buf = ch & 1;
-      mbar_wait(&acc_full[buf], (ch >> 1) & 1);
-      tc_fence_after();
+      for (int ch = 0; ch < nchunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        mbar_wait(&acc_full[buf], (gch >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < TC_BN / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row + buf * 256 + c * 16, v);
-        tmem_ld_wait();
+        for (int c = 0; c < TC_BN / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + buf * 256 + c * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c * 16 + j] = ch == 0 ? __uint_as_float(v[j]) : acc[c * 16 + j] + __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) acc[c * 16 + j] = ch == 0 ? __uint_as_float(v[j]) : acc[c * 16 + j] + __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-    }
-    const int sample = args.rowbias ? m / args.rows_per_sample : 0;
-    float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
-    const float* rrow = args.residual ? args.residual + static_cast<size_t>(m) * args.N + n0 : nullptr;
-    const float* rbrow = args.rowbias ? args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0 : nullptr;
-    const float* bias = args.bias;
-    const int act_silu = args.act_silu;
-#pragma unroll
-    for (int c = 0; c < TC_BN / 16; ++c) {
-      float o[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = acc[c * 16 + j];
-        const int n = c * 16 + j;
-        if (bias) x += bias[n0 + n];
-        if (rbrow) x += rbrow[n];
-        if (rrow) x += rrow[n];
-        if (act_silu) x = x / (1.0f + expf(-x));
-        o[j] = x;
-      }
+      const int sample = args.rowbias ? m / args.rows_per_sample : 0;
+      float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
+      const float4* rrow = args.residual ? reinterpret_cast<const float4*>(args.residual + static_cast<size_t>(m) * args.N + n0) : nullptr;
+      const float4* rbrow = args.rowbias ? reinterpret_cast<const float4*>(args.rowbias + static_cast<size_t>(sample) * args.rb_ld + n0) : nullptr;
+      const float4* bias = args.bias ? reinterpret_cast<const float4*>(args.bias + n0) : nullptr;
+      const int act_silu = args.act_silu;
       if (m < args.M) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + c * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        for (int c4 = 0; c4 < TC_BN / 4; ++c4) {  // 16-byte loads of bias / row bias / residual (N, n0, rb_ld are multiples of 4)
+          float4 o = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+          if (bias) {
+            const float4 b = __ldg(bias + c4);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (rbrow) {
+            const float4 b = __ldg(rbrow + c4);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (rrow) {
+            const float4 b = __ldg(rrow + c4);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (act_silu) {
+            o.x = o.x / (1.0f + expf(-o.x)); o.y = o.y / (1.0f + expf(-o.y));
+            o.z = o.z / (1.0f + expf(-o.z)); o.w = o.w / (1.0f + expf(-o.w));
+          }
+          *reinterpret_cast<float4*>(orow + c4 * 4) = o;
+        }
       }
     }
   }
@@ -346,7 +365,13 @@ cudaError_t launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
     attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  f32tc_gemm_kernel<<<dim3(a.M / TC_BM, a.N / TC_BN, 1), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
+  static int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int tiles = (a.M / TC_BM) * (a.N / TC_BN);
+  f32tc_gemm_kernel<<<dim3(tiles < sms ? tiles : sms), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
   return cudaGetLastError();
 }
 
