@@ -296,7 +296,7 @@ int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bia
                       int Cout, int stride, int up, void* stream);
 /* out[M,N] = A[M,K] W[N,K]^T + bias through the split-TF32 tcgen05 kernel (csrc/f32_gemm_tc.cu: three kind::tf32 MMAs per K step on
  * pre-split operands, chunks of K = 320 summed in fp32 registers; the fp32 mode's Linear / 1x1 / 3x3 contractions run on it unless
- * WD_F32_TC=0).  M % 128 == 0, N % 160 == 0, K % 32 == 0 */
+ * WD_F32_TC=0).  M % 128 == 0, N % 160 == 0 or N % 128 == 0, K % 32 == 0 */
 int wd_f32_op_gemm_tc(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, void* stream);
 /* 3x3 pad-1 stride-1 convolution over cat([x1, x2], channel) (x2 NULL: one source) as an implicit GEMM on the split-TF32 kernel */
 int wd_f32_op_conv3x3_tc(const float* x1, const float* x2, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W,

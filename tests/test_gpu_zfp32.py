@@ -226,7 +226,8 @@ def test_attention_maps_variant_vs_reference_golden(golden_dir):
         m(inp["x"], None, timesteps=inp["t"], context=inp["context"], y=inp["y"])
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (256, 320, 320), (128, 160, 544), (512, 320, 2880), (256, 640, 5760)])
+@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (256, 320, 320), (128, 160, 544), (512, 320, 2880), (256, 640, 5760),
+                                   (256, 512, 512), (384, 128, 4608), (20096, 256, 2304)])
 def test_f32_tc_gemm_operator(M, N, K):
     """C = A W^T + bias through three kind::tf32 MMAs per K step on pre-split operands, K walked in chunks of 320 whose TMEM
     accumulators are summed in fp32 registers: fp32-class accuracy (vs fp64 torch) whatever K.  (With ONE TMEM accumulation the
@@ -245,7 +246,8 @@ def test_f32_tc_gemm_operator(M, N, K):
 
 
 @pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(2, 8, 32, 320, 0, 320), (4, 4, 16, 320, 320, 320), (1, 8, 32, 64, 32, 160),
-                                              (2, 8, 16, 640, 0, 640), (8, 4, 4, 32, 0, 160)])
+                                              (2, 8, 16, 640, 0, 640), (8, 4, 4, 32, 0, 160), (1, 16, 64, 512, 0, 512),
+                                              (2, 64, 256, 128, 0, 128)])
 def test_f32_tc_conv3x3_operator(B, H, W, C1, C2, Cout):
     """3x3 pad-1 convolution as an implicit GEMM on the split-TF32 kernel: shifted 4-D TMA boxes of the split NHWC sources (zero fill =
     padding), channel concatenation of two sources (decoder skip, unet.py:1750), tiles inside one image and tiles over several."""

@@ -33,6 +33,9 @@ namespace wd {
 namespace {
 
 constexpr int TC_BM = 128, TC_BN = 160, TC_BK = 32;  // 32 fp32 = 128 B = one SWIZZLE_128B row
+// The kernel is also built with 128-column tiles for widths that are multiples of 128 but not of 160 (the VAE decoder's 512 / 256 /
+// 128 channels); tile width for a given N:
+constexpr int tc_bn_for(int N) { return N % TC_BN == 0 ? TC_BN : (N % 128 == 0 ? 128 : 0); }
 constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;  // 20 KB
@@ -79,13 +82,16 @@ struct TcArgs {
   int kb_per_chunk;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                                                             const __grid_constant__ CUtensorMap mapA2h, const __grid_constant__ CUtensorMap mapA2l,
                                                             const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                                                             const TcArgs args) {
+  constexpr int W_B = BN * TC_BK * 4;                // one weight box
+  constexpr int STAGE_B = 2 * TC_A_BYTES + 2 * W_B;  // A_hi, A_lo, W_hi, W_lo
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment (no static shared memory in this kernel)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_B);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* acc_full = empty_bar + TC_STAGES;   // [2]: chunk accumulator complete (MMA -> epilogue)
   uint64_t* acc_empty = acc_full + 2;           // [2]: chunk accumulator drained (4 epilogue warps -> MMA)
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   // accumulators alternate between the two TMEM buffers ACROSS tiles, so the epilogue of one tile (registers -> global) runs under
   // the MMAs of the next.  (The first build launched one CTA per tile: ~16 us of prologue / pipeline fill / epilogue per tile
   // against 9 us of MMA time at K = 320, profiles/R2q_fp32_launches.txt.)
-  const int n_tiles = args.N / TC_BN;
+  const int n_tiles = args.N / BN;
   const int total_tiles = n_tiles * (args.M / TC_BM);
   const int nkb = args.K / TC_BK;
   const int kpc = args.kb_per_chunk;
@@ -133,30 +139,31 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
       uint32_t phase = 0;
       const int cbt = args.cb1 + args.cb2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
-      int img = 0, oh0 = 0;
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
+      int img = 0, oh0 = 0, ow0 = 0;
       if (args.conv) {
         img = m0 / args.HW;
         oh0 = (m0 % args.HW) / args.W;
+        ow0 = m0 % args.W;  // non-zero only for rows longer than a tile (W a multiple of 128)
       }
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-        uint8_t* s = smem + stage * TC_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_B);
+        uint8_t* s = smem + stage * STAGE_B;
         const int kc = kb * TC_BK;
         if (args.conv) {
           const int tap = kb / cbt, cb = kb - tap * cbt;
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           const bool second = cb >= args.cb1;
           const int c0 = (second ? cb - args.cb1 : cb) * TC_BK;
-          tma_load_4d(s, second ? &mapA2h : &mapAh, &full_bar[stage], c0, dx, oh0 + dy, img);
-          tma_load_4d(s + TC_A_BYTES, second ? &mapA2l : &mapAl, &full_bar[stage], c0, dx, oh0 + dy, img);
+          tma_load_4d(s, second ? &mapA2h : &mapAh, &full_bar[stage], c0, ow0 + dx, oh0 + dy, img);
+          tma_load_4d(s + TC_A_BYTES, second ? &mapA2l : &mapAl, &full_bar[stage], c0, ow0 + dx, oh0 + dy, img);
         } else {
           tma_load_2d(s, &mapAh, &full_bar[stage], kc, m0);
           tma_load_2d(s + TC_A_BYTES, &mapAl, &full_bar[stage], kc, m0);
         }
         tma_load_2d(s + 2 * TC_A_BYTES, &mapWh, &full_bar[stage], kc, n0);
-        tma_load_2d(s + 2 * TC_A_BYTES + TC_W_BYTES, &mapWl, &full_bar[stage], kc, n0);
+        tma_load_2d(s + 2 * TC_A_BYTES + W_B, &mapWl, &full_bar[stage], kc, n0);
         if (++stage == TC_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32_f32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = make_idesc_tf32_f32(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t gch = 0;  // chunks issued so far by this CTA (over all its tiles)
@@ -182,9 +189,9 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
         for (int kb = ch * kpc; kb < kend; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t s = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint32_t s = smem_u32(smem + stage * STAGE_B);
           const uint64_t ah = make_smem_desc_sw128(s), al = make_smem_desc_sw128(s + TC_A_BYTES);
-          const uint64_t wh = make_smem_desc_sw128(s + 2 * TC_A_BYTES), wl = make_smem_desc_sw128(s + 2 * TC_A_BYTES + TC_W_BYTES);
+          const uint64_t wh = make_smem_desc_sw128(s + 2 * TC_A_BYTES), wl = make_smem_desc_sw128(s + 2 * TC_A_BYTES + W_B);
           const bool first = kb == ch * kpc;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
@@ -208,16 +215,16 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t gch = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
       const int m = m0 + q * 32 + lane;
-      float acc[TC_BN];  // second accumulation level, fp32 registers (every index below is a compile-time constant)
+      float acc[BN];  // second accumulation level, fp32 registers (every index below is a compile-time constant)
 #pragma unroll 1
       for (int ch = 0; ch < nchunks; ++ch, ++gch) {
         const int buf = gch & 1;
         mbar_wait(&acc_full[buf], (gch >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < TC_BN / 16; ++c) {
+        for (int c = 0; c < BN / 16; ++c) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(t_row + buf * 256 + c * 16, v);
           tmem_ld_wait();
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
       const int act_silu = args.act_silu;
       if (m < args.M) {
 #pragma unroll
-        for (int c4 = 0; c4 < TC_BN / 4; ++c4) {  // 16-byte loads of bias / row bias / residual (N, n0, rb_ld are multiples of 4)
+        for (int c4 = 0; c4 < BN / 4; ++c4) {  // 16-byte loads of bias / row bias / residual (N, n0, rb_ld are multiples of 4)
           float4 o = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
           if (bias) {
             const float4 b = __ldg(bias + c4);
@@ -362,7 +369,9 @@ cudaError_t launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(f32tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
   static int sms = [] {
@@ -370,8 +379,11 @@ cudaError_t launch_tc(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUte
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n > 0 ? n : 148;
   }();
-  const int tiles = (a.M / TC_BM) * (a.N / TC_BN);
-  f32tc_gemm_kernel<<<dim3(tiles < sms ? tiles : sms), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
+  const int bn = tc_bn_for(a.N);
+  if (!bn) return cudaErrorInvalidValue;
+  const int tiles = (a.M / TC_BM) * (a.N / bn);
+  if (bn == TC_BN) f32tc_gemm_kernel<160><<<dim3(tiles < sms ? tiles : sms), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
+  else f32tc_gemm_kernel<128><<<dim3(tiles < sms ? tiles : sms), 192, TC_SMEM_BYTES, s>>>(mAh, mAl, mA2h, mA2l, mWh, mWl, a);
   return cudaGetLastError();
 }
 
@@ -386,7 +398,7 @@ bool f32tc_enabled() {  // default ON since round 2 (measured: profiles/R2o_*); 
   return v != 0;
 }
 
-bool f32tc_shape_ok(int M, int N, int K) { return M > 0 && M % TC_BM == 0 && N % TC_BN == 0 && K % TC_BK == 0 && K >= TC_BK; }
+bool f32tc_shape_ok(int M, int N, int K) { return M > 0 && M % TC_BM == 0 && tc_bn_for(N) != 0 && K % TC_BK == 0 && K >= TC_BK; }
 
 cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStream_t s) {
   if (n & 3) return cudaErrorInvalidValue;
@@ -412,8 +424,8 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
                        float* /*partial_ws*/, cudaStream_t s) {
   if (!f32tc_shape_ok(M, N, K)) return cudaErrorInvalidValue;
   CUtensorMap mAh, mAl, mWh, mWl;
-  if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, TC_BN) ||
-      !tmap_f32(&mWl, w_lo, K, N, TC_BN))
+  if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, tc_bn_for(N)) ||
+      !tmap_f32(&mWl, w_lo, K, N, tc_bn_for(N)))
     return cudaErrorInvalidValue;
   TcArgs a{};
   a.M = M;
@@ -432,9 +444,10 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
 
 bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N) {
   const int HW = H * W, M = B * HW;
-  if (M <= 0 || M % TC_BM || N % TC_BN || C1 % TC_BK || C2 % TC_BK || C1 <= 0) return false;
-  if (HW >= TC_BM) return HW % TC_BM == 0 && TC_BM % W == 0 && W <= 256;
-  return TC_BM % HW == 0 && W <= 256 && H <= 256;
+  if (M <= 0 || M % TC_BM || tc_bn_for(N) == 0 || C1 % TC_BK || C2 % TC_BK || C1 <= 0) return false;
+  if (W > TC_BM) return W % TC_BM == 0;  // a tile is a 128-pixel piece of one image row
+  if (HW >= TC_BM) return HW % TC_BM == 0 && TC_BM % W == 0;
+  return TC_BM % HW == 0 && H <= 256;
 }
 
 cudaError_t f32tc_conv3x3(const float* a1_hi, const float* a1_lo, int C1, const float* a2_hi, const float* a2_lo, int C2, int B, int H, int W,
@@ -443,7 +456,11 @@ cudaError_t f32tc_conv3x3(const float* a1_hi, const float* a1_lo, int C1, const 
   if (!f32tc_conv_ok(B, H, W, C1, C2, N)) return cudaErrorInvalidValue;
   const int HW = H * W, K = 9 * (C1 + C2);
   uint32_t bw = W, bh, bn;
-  if (HW >= TC_BM) {
+  if (W > TC_BM) {
+    bw = TC_BM;
+    bh = 1;
+    bn = 1;
+  } else if (HW >= TC_BM) {
     bh = TC_BM / W;
     bn = 1;
   } else {
@@ -452,7 +469,7 @@ cudaError_t f32tc_conv3x3(const float* a1_hi, const float* a1_lo, int C1, const 
   }
   CUtensorMap mAh, mAl, mA2h, mA2l, mWh, mWl;
   if (!tmap_f32_4d(&mAh, a1_hi, C1, W, H, B, bw, bh, bn) || !tmap_f32_4d(&mAl, a1_lo, C1, W, H, B, bw, bh, bn) ||
-      !tmap_f32(&mWh, w_hi, K, N, TC_BN) || !tmap_f32(&mWl, w_lo, K, N, TC_BN))
+      !tmap_f32(&mWh, w_hi, K, N, tc_bn_for(N)) || !tmap_f32(&mWl, w_lo, K, N, tc_bn_for(N)))
     return cudaErrorInvalidValue;
   mA2h = mAh;
   mA2l = mAl;

@@ -1666,7 +1666,7 @@ int wd_f32_op_conv3x3(const float* x_nhwc, const float* w_oihw, const float* bia
 int wd_f32_op_conv3x3_tc(const float* x1, const float* x2, const float* w_oihw, const float* bias, float* out_nhwc, int B, int H, int W,
                          int C1, int C2, int Cout, void* stream) {
   if (!x1 || !w_oihw || !out_nhwc || (C2 > 0 && !x2) || !wd::f32tc_conv_ok(B, H, W, C1, C2, Cout))
-    return wd_set_error(WD_ERR_INVALID, "wd_f32_op_conv3x3_tc: unsupported shape (B H W % 128, channels % 32, Cout % 160)");
+    return wd_set_error(WD_ERR_INVALID, "wd_f32_op_conv3x3_tc: unsupported shape (B H W % 128, channels % 32, Cout % 160 or % 128)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Cin = C1 + C2;
   const size_t nw = static_cast<size_t>(Cout) * Cin * 9, n1 = static_cast<size_t>(B) * H * W * C1, n2 = static_cast<size_t>(B) * H * W * C2;
@@ -1688,7 +1688,7 @@ int wd_f32_op_conv3x3_tc(const float* x1, const float* x2, const float* w_oihw, 
 
 /* out[M,N] = A[M,K] W[N,K]^T + bias on the split-TF32 tensor-core kernel (f32_gemm_tc.cu); splits both operands itself */
 int wd_f32_op_gemm_tc(const float* a, const float* w, const float* bias, float* out, int M, int N, int K, void* stream) {
-  if (!a || !w || !out || !wd::f32tc_shape_ok(M, N, K)) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_gemm_tc: need M % 128 == 0, N % 160 == 0, K % 32 == 0");
+  if (!a || !w || !out || !wd::f32tc_shape_ok(M, N, K)) return wd_set_error(WD_ERR_INVALID, "wd_f32_op_gemm_tc: need M % 128 == 0, N % 160 == 0 or N % 128 == 0, K % 32 == 0");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* buf = nullptr;
   const size_t nA = static_cast<size_t>(M) * K, nW = static_cast<size_t>(N) * K;
