@@ -1284,6 +1284,69 @@ cudaError_t repack_conv3x3_T_launch(const float* w, bf16_t* dst, int Cout, int C
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) repack_multi_kernel(const PackDesc* __restrict__ jobs, int njobs, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int lo = 0, hi = njobs - 1;  // last job whose start <= idx
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].start <= idx) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackDesc j = jobs[lo];
+  const long long i = idx - j.start;
+  bf16_t* d = static_cast<bf16_t*>(j.dst);
+  auto to16 = [](float v, int as_f16) -> bf16_t {
+    if (!as_f16) return __float2bfloat16(v);
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const bf16_t*>(&h);
+  };
+  switch (j.kind) {
+    case 0: {
+      const int k = static_cast<int>(i % j.K), n = static_cast<int>(i / j.K);
+      d[static_cast<size_t>(n + j.off1) * j.ld + j.off0 + k] = __float2bfloat16(j.src[i]);
+      break;
+    }
+    case 1: {
+      const int n = static_cast<int>(i % j.N), k = static_cast<int>(i / j.N);
+      d[static_cast<size_t>(j.off1 + k) * j.ld + j.off0 + n] = __float2bfloat16(j.src[static_cast<size_t>(n) * j.K + k]);
+      break;
+    }
+    case 2: {
+      const int tap = static_cast<int>(i % 9), c = static_cast<int>((i / 9) % j.K), n = static_cast<int>(i / (9LL * j.K));
+      const float w = j.src[i];
+      if (j.off1 == 2) {
+        const float h = __bfloat162float(__float2bfloat16(w));
+        d[static_cast<size_t>(n) * j.ld + j.off0 + tap * j.K + c] = __float2bfloat16(h);
+        d[static_cast<size_t>(n + 4) * j.ld + j.off0 + tap * j.K + c] = __float2bfloat16(w - h);
+      } else {
+        d[static_cast<size_t>(n) * j.ld + j.off0 + tap * j.K + c] = to16(w, j.off1);
+      }
+      break;
+    }
+    case 3: {
+      const int n = static_cast<int>(i % j.N), tap = static_cast<int>((i / j.N) % 9), c = static_cast<int>(i / (9LL * j.N));
+      d[static_cast<size_t>(c) * 9 * j.ld + (8 - tap) * j.ld + n] = __float2bfloat16(j.src[(static_cast<size_t>(n) * j.K + c) * 9 + tap]);
+      break;
+    }
+    default: {  // conv_in
+      const int k = static_cast<int>(i % 128), n = static_cast<int>(i / 128);
+      float v = 0.f;
+      if (k < 108) {
+        const float wv = j.src[n * 36 + k % 36];
+        const float h = __bfloat162float(__float2bfloat16(wv));
+        v = k < 72 ? h : wv - h;
+      }
+      d[i] = __float2bfloat16(v);
+    }
+  }
+}
+cudaError_t repack_multi_launch(const PackDesc* jobs_dev, int njobs, long long total, cudaStream_t s) {
+  if (njobs <= 0 || total <= 0) return cudaSuccess;
+  repack_multi_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(jobs_dev, njobs, total);
+  return cudaGetLastError();
+}
+
 // =====================================================================================================
 // AdamW + EMA
 // =====================================================================================================

@@ -94,6 +94,18 @@ cudaError_t word_attn_bwd_launch(const float* q, const float* k, const float* v,
 // nn.Linear / 1x1 conv weight fp32 [N, K] -> bf16 dst[k_row_off + k][n_off + n]   (row stride ldn)
 cudaError_t repack_linear_T_launch(const float* w, bf16_t* dst, int N, int K, int ldn, int n_off, int k_row_off, cudaStream_t s);
 // conv3x3 weight fp32 [Cout, Cin, 3, 3] -> bf16 dst[c][(8 - tap) * cout_pad + n]   (row stride 9 * cout_pad)
+// Every weight pack of the trainer in ONE launch (wd_trainer_sync_weights ran ~200 small launches per step: 1.0 ms of the 16 ms
+// step at batch 224, a sixth of the 28-latent step): `jobs` is a device table sorted by `start` (first element index of the job).
+// kind: 0 linear [N,K] -> dst[(n + off1) ld + off0 + k] | 1 linear transposed -> dst[(off1 + k) ld + off0 + n] |
+//       2 conv3x3 [Cout=N, Cin=K, 3, 3] -> dst[n ld + off0 + tap K + c] (off1: 0 bf16, 1 fp16 bits, 2 bf16 hi / lo rows n, n + 4) |
+//       3 conv3x3 transposed, flipped taps -> dst[c 9 ld + (8 - tap) ld + n] | 4 conv_in [Cout=N, 4, 3, 3] -> bf16 [N, 128] hi|hi|lo|0
+struct PackDesc {
+  const float* src;
+  void* dst;
+  long long start;
+  int kind, N, K, ld, off0, off1;
+};
+cudaError_t repack_multi_launch(const PackDesc* jobs_dev, int njobs, long long total, cudaStream_t s);
 cudaError_t repack_conv3x3_T_launch(const float* w, bf16_t* dst, int Cout, int Cin, int cout_pad, cudaStream_t s);
 
 // ---------------- AdamW + EMA (train.py:405 `optim.AdamW(lr=1e-4)`, train.py:140-170 `EMA(0.995)`) ----------------

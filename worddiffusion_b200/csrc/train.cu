@@ -170,6 +170,8 @@ struct wd_trainer {
   std::unordered_map<std::string, TParam> params;
   std::unordered_map<std::string, int64_t> expected;  // live parameters: key -> element count
   std::vector<PackJob> jobs;
+  void* pack_tab_dev = nullptr;       // device copy of the matrix-pack job table (repack_multi_launch)
+  std::vector<char> pack_tab_host;    // what was uploaded last
   char* wbase = nullptr;
   size_t wbytes = 0;
   // inventory
@@ -1585,6 +1587,7 @@ extern "C" void wd_trainer_destroy(wd_trainer* e) {
   cudaDeviceSynchronize();
   if (e->wbase) cudaFree(e->wbase);
   if (e->abase) cudaFree(e->abase);
+  if (e->pack_tab_dev) cudaFree(e->pack_tab_dev);
   delete e;
 }
 
@@ -1619,7 +1622,52 @@ extern "C" int wd_trainer_set_pos_encoding(wd_trainer* e, const float* pe, void*
 extern "C" int wd_trainer_sync_weights(wd_trainer* e, void* stream) {
   if (!e) return tfail(WD_ERR_INVALID, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // every matrix pack in one launch (device job table, re-uploaded only when a binding changed); the bias vectors keep their own
+  // small launches because some of them accumulate into a slot another job wrote first
+  static const bool multi = [] { const char* v = getenv("WD_TRAIN_MULTI_PACK"); return v ? atoi(v) != 0 : true; }();
+  if (multi) {
+    std::vector<PackDesc> tab;
+    long long total = 0;
+    for (const PackJob& j : e->jobs) {
+      if (j.kind == PK_VEC) continue;
+      auto it = e->params.find(j.src);
+      if (it == e->params.end() || !it->second.w) return tfail(WD_ERR_STATE, "parameter '%s' is not bound", j.src.c_str());
+      PackDesc d{};
+      d.src = it->second.w;
+      d.dst = j.dst;
+      d.start = total;
+      d.N = j.N;
+      d.K = j.K;
+      d.ld = j.ld;
+      d.off0 = j.off0;
+      d.off1 = j.off1;
+      long long n = 0;
+      switch (j.kind) {
+        case PK_LIN: d.kind = 0; n = static_cast<long long>(j.N) * j.K; break;
+        case PK_LIN_T: d.kind = 1; n = static_cast<long long>(j.N) * j.K; break;
+        case PK_CONV3: d.kind = 2; n = 9LL * j.N * j.K; break;
+        case PK_CONV3_T: d.kind = 3; n = 9LL * j.N * j.K; break;
+        case PK_CONV_IN: d.kind = 4; n = 128LL * j.N; break;
+        default: break;
+      }
+      total += n;
+      tab.push_back(d);
+    }
+    const size_t bytes = tab.size() * sizeof(PackDesc);
+    if (bytes != e->pack_tab_host.size() || memcmp(tab.data(), e->pack_tab_host.data(), bytes) != 0) {
+      if (e->pack_tab_dev) {
+        cudaStreamSynchronize(s);  // a previous launch may still read the old table
+        cudaFree(e->pack_tab_dev);
+        e->pack_tab_dev = nullptr;
+      }
+      T_CUDA_TRY(cudaMalloc(&e->pack_tab_dev, bytes ? bytes : 16));
+      T_CUDA_TRY(cudaMemcpy(e->pack_tab_dev, tab.data(), bytes, cudaMemcpyHostToDevice));
+      e->pack_tab_host.assign(reinterpret_cast<const char*>(tab.data()), reinterpret_cast<const char*>(tab.data()) + bytes);
+    }
+    T_CUDA_TRY(repack_multi_launch(static_cast<const PackDesc*>(e->pack_tab_dev), static_cast<int>(tab.size()), total, s));
+  }
   for (const PackJob& j : e->jobs) {
+    if (multi && j.kind != PK_VEC) continue;
     auto it = e->params.find(j.src);
     if (it == e->params.end() || !it->second.w) return tfail(WD_ERR_STATE, "parameter '%s' is not bound", j.src.c_str());
     const float* src = it->second.w;
