@@ -106,6 +106,8 @@ struct PackDesc {
   int kind, N, K, ld, off0, off1;
 };
 cudaError_t repack_multi_launch(const PackDesc* jobs_dev, int njobs, long long total, cudaStream_t s);
+// the transposed jobs (kind 1, 3) as 32 x 32 shared-memory tiles; `start` = first tile index of the job
+cudaError_t repack_multi_T_launch(const PackDesc* jobs_dev, int njobs, long long total_tiles, cudaStream_t s);
 cudaError_t repack_conv3x3_T_launch(const float* w, bf16_t* dst, int Cout, int Cin, int cout_pad, cudaStream_t s);
 
 // ---------------- AdamW + EMA (train.py:405 `optim.AdamW(lr=1e-4)`, train.py:140-170 `EMA(0.995)`) ----------------

@@ -1626,8 +1626,9 @@ extern "C" int wd_trainer_sync_weights(wd_trainer* e, void* stream) {
   // small launches because some of them accumulate into a slot another job wrote first
   static const bool multi = [] { const char* v = getenv("WD_TRAIN_MULTI_PACK"); return v ? atoi(v) != 0 : true; }();
   if (multi) {
-    std::vector<PackDesc> tab;
-    long long total = 0;
+    // table = [element-per-thread jobs (kinds 0, 2, 4)] ++ [tiled transposes (kinds 1, 3)]
+    std::vector<PackDesc> tab, tabT;
+    long long total = 0, total_tiles = 0;
     for (const PackJob& j : e->jobs) {
       if (j.kind == PK_VEC) continue;
       auto it = e->params.find(j.src);
@@ -1635,24 +1636,32 @@ extern "C" int wd_trainer_sync_weights(wd_trainer* e, void* stream) {
       PackDesc d{};
       d.src = it->second.w;
       d.dst = j.dst;
-      d.start = total;
       d.N = j.N;
       d.K = j.K;
       d.ld = j.ld;
       d.off0 = j.off0;
       d.off1 = j.off1;
+      if (j.kind == PK_LIN_T || j.kind == PK_CONV3_T) {
+        d.kind = j.kind == PK_LIN_T ? 1 : 3;
+        const long long C = j.kind == PK_LIN_T ? j.K : 9LL * j.K;
+        d.start = total_tiles;
+        total_tiles += ((j.N + 31) / 32) * ((C + 31) / 32);
+        tabT.push_back(d);
+        continue;
+      }
       long long n = 0;
       switch (j.kind) {
         case PK_LIN: d.kind = 0; n = static_cast<long long>(j.N) * j.K; break;
-        case PK_LIN_T: d.kind = 1; n = static_cast<long long>(j.N) * j.K; break;
         case PK_CONV3: d.kind = 2; n = 9LL * j.N * j.K; break;
-        case PK_CONV3_T: d.kind = 3; n = 9LL * j.N * j.K; break;
         case PK_CONV_IN: d.kind = 4; n = 128LL * j.N; break;
         default: break;
       }
+      d.start = total;
       total += n;
       tab.push_back(d);
     }
+    const int n_plain = static_cast<int>(tab.size()), n_T = static_cast<int>(tabT.size());
+    tab.insert(tab.end(), tabT.begin(), tabT.end());
     const size_t bytes = tab.size() * sizeof(PackDesc);
     if (bytes != e->pack_tab_host.size() || memcmp(tab.data(), e->pack_tab_host.data(), bytes) != 0) {
       if (e->pack_tab_dev) {
@@ -1664,7 +1673,9 @@ extern "C" int wd_trainer_sync_weights(wd_trainer* e, void* stream) {
       T_CUDA_TRY(cudaMemcpy(e->pack_tab_dev, tab.data(), bytes, cudaMemcpyHostToDevice));
       e->pack_tab_host.assign(reinterpret_cast<const char*>(tab.data()), reinterpret_cast<const char*>(tab.data()) + bytes);
     }
-    T_CUDA_TRY(repack_multi_launch(static_cast<const PackDesc*>(e->pack_tab_dev), static_cast<int>(tab.size()), total, s));
+    const PackDesc* dev = static_cast<const PackDesc*>(e->pack_tab_dev);
+    T_CUDA_TRY(repack_multi_launch(dev, n_plain, total, s));
+    T_CUDA_TRY(repack_multi_T_launch(dev + n_plain, n_T, total_tiles, s));
   }
   for (const PackJob& j : e->jobs) {
     if (multi && j.kind != PK_VEC) continue;
