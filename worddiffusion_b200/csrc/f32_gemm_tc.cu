@@ -291,6 +291,24 @@ __global__ void f32tc_split_kernel(const float* __restrict__ a, float* __restric
   reinterpret_cast<float4*>(lo)[i] = l;
 }
 
+// channel concatenation of two row-major sources [M, C1], [M, C2] -> split [M, C1 + C2] (a 1x1 convolution over torch.cat([h, skip]))
+__global__ void f32tc_split_concat_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2, float* __restrict__ hi,
+                                          float* __restrict__ lo, size_t total4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int K4 = (C1 + C2) / 4;
+  const size_t m = i / K4;
+  const int c = static_cast<int>(i - m * K4) * 4;
+  const float4 v = c < C1 ? *reinterpret_cast<const float4*>(a1 + m * C1 + c) : *reinterpret_cast<const float4*>(a2 + m * C2 + (c - C1));
+  float4 h, l;
+  h.x = tf32_rn(v.x); l.x = v.x - h.x;
+  h.y = tf32_rn(v.y); l.y = v.y - h.y;
+  h.z = tf32_rn(v.z); l.z = v.z - h.z;
+  h.w = tf32_rn(v.w); l.w = v.w - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
 // 3x3 pad-1 patch matrix of an NHWC fp32 tensor (channel concat of up to two sources), split: hi, lo [M, 9 (C1 + C2)], k = tap (C1 + C2) + c
 __global__ void f32tc_im2col_split_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2, int Hin, int Win,
                                           int Hout, int Wout, int stride, int up, float* __restrict__ hi, float* __restrict__ lo,
@@ -404,6 +422,13 @@ cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStre
   if (n & 3) return cudaErrorInvalidValue;
   const size_t n4 = n / 4;
   f32tc_split_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(a, hi, lo, n4);
+  return cudaGetLastError();
+}
+
+cudaError_t f32tc_split_concat(const float* a1, const float* a2, int C1, int C2, size_t M, float* hi, float* lo, cudaStream_t s) {
+  if (((C1 | C2) & 3) != 0) return cudaErrorInvalidValue;
+  const size_t total4 = M * static_cast<size_t>(C1 + C2) / 4;
+  f32tc_split_concat_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, s>>>(a1, a2, C1, C2, hi, lo, total4);
   return cudaGetLastError();
 }
 

@@ -773,7 +773,7 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
     }
     return o;
   }
-  if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K) && (cs.taps == 9 || !a2)) {
+  if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K)) {
     const size_t nA = static_cast<size_t>(g.M) * g.K;
     float* a_hi = alloc(e, nA);
     float* a_lo = alloc(e, nA);
@@ -781,7 +781,8 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
     float* ws = splits > 1 ? alloc(e, static_cast<size_t>(splits) * g.M * N) : nullptr;
     if (!e->dry) {
       cudaError_t ce = cs.taps == 9 ? wd::f32tc_im2col_split(a1.p, a2 ? a2->p : nullptr, g.C1, g.C2, B, a1.H, a1.W, cs.stride, cs.up, a_hi, a_lo, e->s)
-                                    : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
+                       : a2       ? wd::f32tc_split_concat(a1.p, a2->p, g.C1, g.C2, static_cast<size_t>(g.M), a_hi, a_lo, e->s)
+                                  : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
       ++e->launches;
       if (ce == cudaSuccess) {
         ce = wd::f32tc_gemm(a_hi, a_lo, w_hi, w_lo, g.M, N, g.K, bias, rowbias, rb_ld, g.Hout * g.Wout, residual, o.p, cs.silu, ws, e->s);

@@ -8,6 +8,8 @@ bool f32tc_enabled();                        // env WD_F32_TC (default on; 0 kee
 bool f32tc_shape_ok(int M, int N, int K);    // M % 128 == 0, N % 160 == 0, K % 32 == 0
 // a[n] -> hi[n] = tf32_rn(a), lo[n] = a - hi   (n % 4 == 0)
 cudaError_t f32tc_split(const float* a, float* hi, float* lo, size_t n, cudaStream_t s);
+// [M, C1] ++ [M, C2] along the channels, split (C1, C2 % 4 == 0)
+cudaError_t f32tc_split_concat(const float* a1, const float* a2, int C1, int C2, size_t M, float* hi, float* lo, cudaStream_t s);
 // 3x3 pad-1 patch matrix [B Hout Wout, 9 (C1 + C2)] of NHWC source(s), already split (stride 1|2, or nearest-2x first)
 cudaError_t f32tc_im2col_split(const float* a1, const float* a2, int C1, int C2, int B, int Hin, int Win, int stride, int up, float* hi,
                                float* lo, cudaStream_t s);
