@@ -147,6 +147,13 @@ int wd_op_gemm_f16(const void* a_bf16, const void* w_bf16, const float* bias, co
 /* 3x3 conv, pad 1, stride 1|2, NHWC bf16, weights pre-packed [Cout, 9*Cin] by wd_op_pack_conv3x3 */
 int wd_op_conv3x3(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* rowbias, int rb_ld,
                   const void* residual_bf16, void* out_bf16, int B, int H, int W, int Cin, int Cout, int stride, void* stream);
+/* conv3x3 (stride 1) + bias + per-sample row bias -> GroupNorm32 -> SiLU, the front half of ResBlock._forward (unet.py:657-667
+ * then :592-594), with the normalisation applied by the conv kernel's own epilogue (the raw conv output never reaches HBM).
+ * Cout == 320, H*W divides 256 and is a multiple of 32, K = 9*Cin/64 blocks long enough for the CTA-pair kernel (else
+ * WD_ERR_UNSUPPORTED).  stats_ws: fp32 [B][32][H*W/32][2] scratch.  out: bf16 NHWC. */
+int wd_op_conv3x3_gn_silu(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* rowbias, int rb_ld,
+                          const float* gamma, const float* beta, float eps, void* out_bf16, float* stats_ws, int B, int H, int W,
+                          int Cin, int Cout, void* stream);
 int wd_op_pack_conv3x3(const float* w_oihw, void* dst_bf16, int Cout, int Cin, void* stream);
 /* fp32 [N,K] -> bf16 [N,K] (geglu_perm != 0 applies the GEGLU tile permutation used by wd_op_gemm) */
 int wd_op_pack_linear(const float* w, void* dst_bf16, int N, int K, int geglu_perm, void* stream);

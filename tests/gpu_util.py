@@ -65,3 +65,15 @@ def conv3x3(x_nhwc, w_packed, bias, rowbias=None, residual=None, stride=1):
     check(lib().wd_op_conv3x3(P(x_nhwc), P(w_packed), P(bias), P(rowbias), rb_ld, P(residual), P(out), B, H, W, Cin, Cout,
                               stride, S()), "wd_op_conv3x3")
     return out
+
+
+def conv3x3_gn_silu(x_nhwc, w_packed, bias, rowbias, gamma, beta, eps=1e-5):
+    """conv3x3 + bias + row bias -> GroupNorm32 -> SiLU with the normalisation in the conv kernel's epilogue."""
+    B, H, W, Cin = x_nhwc.shape
+    Cout = w_packed.shape[0]
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ws = torch.zeros(B * 32 * max(H * W // 32, 1) * 2, device=DEV, dtype=torch.float32)
+    rb_ld = rowbias.shape[1] if rowbias is not None else 0
+    check(lib().wd_op_conv3x3_gn_silu(P(x_nhwc), P(w_packed), P(bias), P(rowbias), rb_ld, P(gamma), P(beta), float(eps), P(out),
+                                      P(ws), B, H, W, Cin, Cout, S()), "wd_op_conv3x3_gn_silu")
+    return out

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import DEV, P, S, bf, conv3x3, f32, gemm, pack_conv, pack_linear, relerr, sync  # noqa: E402
+from gpu_util import DEV, P, S, bf, conv3x3, conv3x3_gn_silu, f32, gemm, pack_conv, pack_linear, relerr, sync  # noqa: E402
 from worddiffusion_b200._lib import check, lib  # noqa: E402
 
 BF16_STORE = 2 ** -8   # bf16 has 8 significant bits: storing fp32 -> bf16 costs <= 2^-9 relative, 2^-8 with slack
@@ -99,6 +99,32 @@ def test_conv3x3(B, H, W, Cin, stride):
     ref = (ref + rowbias[:, :, None, None]).permute(0, 2, 3, 1)
     assert not torch.isnan(o.float()).any()
     assert relerr(o.float(), ref) < BF16_STORE
+
+
+@pytest.mark.parametrize("B,H,W,Cin", [(2, 8, 32, 320), (3, 4, 16, 320), (4, 4, 16, 640), (5, 4, 16, 320), (1, 8, 32, 640),
+                                       (148, 8, 32, 640), (2, 4, 8, 320)])
+def test_conv3x3_groupnorm_silu_in_the_producer(B, H, W, Cin):
+    """ResBlock front half (unet.py:657-667 then :592-594): conv3x3 + bias + emb row bias -> GroupNorm32 -> SiLU with the
+    normalisation applied by the conv kernel's epilogue (CTA-pair kernel: the 256-row tile holds whole samples).  Covers one
+    sample per pair tile (8x32), four / eight samples per tile, ragged last tiles (B = 3, 5) and more tiles than CTA pairs."""
+    Cout = 320
+    x = bf(torch.randn(B, H, W, Cin, generator=g(40)))
+    w = torch.randn(Cout, Cin, 3, 3, generator=g(41)) / math.sqrt(9 * Cin)
+    bias = f32(torch.randn(Cout, generator=g(42)) * 0.1)
+    rowbias = f32(torch.randn(B, Cout, generator=g(43)))
+    gamma = f32(1.0 + 0.2 * torch.randn(Cout, generator=g(44)))
+    beta = f32(0.2 * torch.randn(Cout, generator=g(45)))
+    o = conv3x3_gn_silu(x, pack_conv(w), bias, rowbias, gamma, beta, 1e-5)
+    sync()
+    h = F.conv2d(x.float().permute(0, 3, 1, 2), bf(w).float(), bias, padding=1) + rowbias[:, :, None, None]
+    ref = F.silu(F.group_norm(h, 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert not torch.isnan(o.float()).any()
+    assert relerr(o.float(), ref) < BF16_STORE
+    # and it is the same function as the two-kernel form (conv3x3 then the GroupNorm kernel) up to the storage rounding
+    h16 = conv3x3(x, pack_conv(w), bias, rowbias=rowbias).reshape(B, H * W, Cout).contiguous()
+    two = torch.empty_like(h16)
+    check(lib().wd_op_groupnorm(P(h16), P(two), P(gamma), P(beta), B, H * W, Cout, 32, 1e-5, 1, S()), "groupnorm")
+    assert relerr(o.float().reshape(B, H * W, Cout), two.float()) < 3 * BF16_STORE
 
 
 def test_conv3x3_residual():

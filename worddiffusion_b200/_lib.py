@@ -50,6 +50,7 @@ SIGNATURES = {
     "wd_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wd_op_gemm_f16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "wd_op_conv3x3": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "wd_op_conv3x3_gn_silu": (_I, [_P, _P, _P, _P, _I, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
     "wd_op_pack_conv3x3": (_I, [_P, _P, _I, _I, _P]),
     "wd_op_pack_linear": (_I, [_P, _P, _I, _I, _I, _P]),
     "wd_op_pack_vec_geglu": (_I, [_P, _P, _I, _P]),

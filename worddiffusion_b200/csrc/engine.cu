@@ -888,12 +888,26 @@ struct Epi {
   const float* ln_stats = nullptr;  // A is an un-normalised tensor with these row statistics (weights carry gamma, see GemmW::ln_s)
   int ln_dim = 0;
   Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
+  const NormW* gn_apply = nullptr;  // producer-side GroupNorm + SiLU (GemmArgs::gn_apply): `out` receives the normalised tensor
+  float gn_eps = 1e-5f;
   int epi = EPI_STD;
   // context attention fused into the to_q projection (GemmArgs::att_*): K / V rows [B, att_L, att_ld], `out` receives softmax(qK^T)V
   const bf16* att_kv = nullptr;
   int att_ld = 0, att_voff = 0, att_L = 0;
   float att_scale = 0.f;
 };
+
+// env WD_GN_PRODUCER: GroupNorm of a ResBlock's h applied by conv1's epilogue.  0: never; 1: only when the conv has more
+// 256-row tiles than the GPU has CTA pairs, so that all but the last tile's epilogue runs under the next tile's MMAs;
+// 2: always (conv1 then runs on the pair kernel whatever its size).  Default 1.
+static int gn_producer_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_GN_PRODUCER");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 
 struct PlanBuilder {
   wd_engine* e;
@@ -976,6 +990,13 @@ struct PlanBuilder {
       a.gn_partial = ep.stats_for->stats;
       a.gn_cpg = 10;
       ep.stats_for->pslots = ep.rows_per_sample / 32;
+    }
+    if (ep.gn_apply) {
+      if (!a.gn_partial || ep.gn_apply->C != w.N) { err = "gemm: producer-side GroupNorm needs epilogue statistics"; return false; }
+      a.gn_apply = 1;
+      a.gn_gamma = ep.gn_apply->g;
+      a.gn_beta = ep.gn_apply->b;
+      a.gn_eps = ep.gn_eps;
     }
     int ktot = 0;
     if (srcs.empty() || srcs.size() > GEMM_MAX_SRC) { err = "gemm: bad source count"; return false; }
@@ -1121,8 +1142,33 @@ struct PlanBuilder {
     const int H = in[0].H, W = in[0].W, HW = H * W;
     Act a1;
     if (!gn_op(ops, in, r.gn1, 1e-5f, 1, a1)) return false;
-    Act h2 = new_act(H, W, r.Cout, true);  // only read by GroupNorm: fp16
-    {
+    Act a2;
+    // conv1 -> GroupNorm -> SiLU (unet.py:657-667 then :592-594): when conv1 runs on the pair kernel and its 256-row tiles hold
+    // whole samples, the epilogue normalises the tile itself and h never reaches HBM (one launch and one HBM round trip fewer)
+    // (R4d: 2.405 -> 2.353 ms per batch-256 step when only the multi-tile launches are fused; single-wave launches expose the
+    //  longer epilogue -- its straight-line code runs once, from a cold instruction cache -- and gain nothing)
+    bool fuse_gn2 = gn_producer_mode() > 0 && gemm_pair_enabled() && epilogue_stats_ok(HW, r.Cout) && 256 % HW == 0 &&
+                    r.Cout == GEMM_PAIR_BLOCK_N && r.gn2.C == r.Cout && a1.C % GEMM_BLOCK_K == 0 && 9 * a1.C / GEMM_BLOCK_K >= 40;
+    if (fuse_gn2 && gn_producer_mode() == 1) {
+      int sms = 148, dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      fuse_gn2 = (static_cast<long long>(B) * HW + 255) / 256 > sms / 2;
+    }
+    if (fuse_gn2) {
+      a2 = new_act(H, W, r.Cout);
+      Act hs{nullptr, r.Cout, H, W, A.alloc<float>(static_cast<size_t>(B) * 32 * 8 * 2), 0, true};  // statistics of h only
+      Epi ep;
+      ep.rowbias = emb_out + r.emb_off;
+      ep.rb_ld = emb_ld;
+      ep.rows_per_sample = HW;
+      ep.out = a2.p;
+      ep.out_ld = r.Cout;
+      ep.stats_for = &hs;
+      ep.gn_apply = &r.gn2;
+      ep.gn_eps = 1e-5f;
+      if (!gemm_op(ops, B * HW, true, H, W, {ASrc{a1.p, a1.C, a1.C, 9, 1, H, W}}, r.conv1, ep)) return false;
+    } else {
+      Act h2 = new_act(H, W, r.Cout, true);  // only read by GroupNorm: fp16
       Epi ep;
       ep.rowbias = emb_out + r.emb_off;
       ep.rb_ld = emb_ld;
@@ -1132,9 +1178,8 @@ struct PlanBuilder {
       ep.out_f16 = 1;
       ep.stats_for = &h2;
       if (!gemm_op(ops, B * HW, true, H, W, {ASrc{a1.p, a1.C, a1.C, 9, 1, H, W}}, r.conv1, ep)) return false;
+      if (!gn_op(ops, {h2}, r.gn2, 1e-5f, 1, a2)) return false;
     }
-    Act a2;
-    if (!gn_op(ops, {h2}, r.gn2, 1e-5f, 1, a2)) return false;
     out = new_act(H, W, r.Cout, true);  // residual stream: fp16
     {
       Epi ep;
@@ -2309,6 +2354,62 @@ extern "C" int wd_op_conv3x3(const void* x, const void* w_packed, const float* b
   L.mapOut = L.mapRes = L.mapB;
   if (!tmap_encode_out_bf16(&L.mapOut, out, Cout, a.M, Cout)) return fail(WD_ERR_CUDA, "tensor map out");
   if (residual && !tmap_encode_out_bf16(&L.mapRes, residual, Cout, a.M, Cout)) return fail(WD_ERR_CUDA, "tensor map residual");
+  CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
+  return WD_OK;
+}
+
+// conv3x3 (stride 1) + bias + per-sample row bias -> GroupNorm(32 groups) -> SiLU with the normalisation applied by the conv's own
+// epilogue (GemmArgs::gn_apply, pair kernel): the front half of ResBlock._forward (unet.py:657-667 then :592-594)
+extern "C" int wd_op_conv3x3_gn_silu(const void* x, const void* w_packed, const float* bias, const float* rowbias, int rb_ld,
+                                     const float* gamma, const float* beta, float eps, void* out, float* stats_ws, int B, int H, int W,
+                                     int Cin, int Cout, void* stream) {
+  if (!x || !w_packed || !gamma || !beta || !out || !stats_ws) return fail(WD_ERR_INVALID, "conv3x3_gn_silu: null argument");
+  if (Cin % GEMM_BLOCK_K || Cout != GEMM_PAIR_BLOCK_N) return fail(WD_ERR_UNSUPPORTED, "conv3x3_gn_silu: channel counts");
+  const int HW = H * W;
+  if (HW % 32 || 256 % HW) return fail(WD_ERR_UNSUPPORTED, "conv3x3_gn_silu: H*W must divide 256 and be a multiple of 32");
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  GemmArgs& a = L.args;
+  a.M = B * HW;
+  a.N = Cout;
+  a.num_src = 1;
+  a.taps[0] = 9;
+  a.chunks[0] = Cin / GEMM_BLOCK_K;
+  a.stride[0] = 1;
+  a.conv = 1;
+  a.Wout = W;
+  a.HWout = HW;
+  a.bias = bias;
+  a.rowbias = rowbias;
+  a.rb_ld = rb_ld;
+  a.rows_per_sample = HW;
+  a.out = out;
+  a.out_ld = Cout;
+  a.gn_partial = stats_ws;  // [B][32][HW / 32][2] fp32
+  a.gn_cpg = 10;
+  a.gn_apply = 1;
+  a.gn_gamma = gamma;
+  a.gn_beta = beta;
+  a.gn_eps = eps;
+  if (!gemm_uses_pair(a)) return fail(WD_ERR_UNSUPPORTED, "conv3x3_gn_silu: this shape does not run on the pair kernel");
+  uint32_t bw, bh, bnn;
+  if (HW >= GEMM_BLOCK_M) {
+    if (HW % GEMM_BLOCK_M || GEMM_BLOCK_M % W) return fail(WD_ERR_UNSUPPORTED, "conv3x3_gn_silu: spatial size");
+    bw = W;
+    bh = GEMM_BLOCK_M / W;
+    bnn = 1;
+  } else {
+    if (GEMM_BLOCK_M % HW) return fail(WD_ERR_UNSUPPORTED, "conv3x3_gn_silu: spatial size");
+    bw = W;
+    bh = H;
+    bnn = GEMM_BLOCK_M / HW;
+  }
+  if (!tmap_encode_4d_bf16(&L.mapA[0], x, Cin, W, H, B, Cin, GEMM_BLOCK_K, bw, bh, bnn, 1)) return fail(WD_ERR_CUDA, "tensor map A");
+  L.mapA[1] = L.mapA[2] = L.mapA[0];
+  if (!tmap_encode_2d_bf16(&L.mapB, w_packed, 9 * Cin, Cout, 9 * Cin, GEMM_BLOCK_K, gemm_b_box_rows(a)))
+    return fail(WD_ERR_CUDA, "tensor map B");
+  L.mapOut = L.mapRes = L.mapB;
+  if (!tmap_encode_out_bf16(&L.mapOut, out, Cout, a.M, Cout)) return fail(WD_ERR_CUDA, "tensor map out");
   CUDA_TRY(gemm_tc_launch(L, static_cast<cudaStream_t>(stream)));
   return WD_OK;
 }

@@ -66,6 +66,51 @@ WD_DEVINL void epi_round80(const uint32_t* v, const float* wvr, uint8_t* srow, i
   }
 }
 
+// ---- GroupNorm applied by the producer (GemmArgs::gn_apply, gemm_pair.cu) ----
+// Round that stays in registers: f = acc + additive terms, GroupNorm partial sums as in epi_round80<.., GN = true, ..>, the 80 values
+// packed as fp16 pairs into h[40].
+WD_DEVINL void epi_round80_hold(const uint32_t* v, const float* wvr, uint32_t* h, bool valid, float* gs) {
+#pragma unroll
+  for (int c = 0; c < 10; ++c) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(wvr + c * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(wvr + c * 8 + 4);
+    f[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
+    f[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
+    f[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
+    f[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c * 8 + j) / 10;
+      const float x = valid ? f[j] : 0.f;
+      gs[2 * g] += x;
+      gs[2 * g + 1] = fmaf(x, x, gs[2 * g + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[c * 4 + j] = pack_f16x2(f[2 * j], f[2 * j + 1]);
+  }
+}
+// 8 columns of y = silu(h * sc + sh), bf16, from 8 fp16 values; sc8 / sh8: shared memory, the pre-halved scale / shift of the 8
+// columns (sc = rstd_g gamma / 2, sh = (beta - mean_g rstd_g gamma) / 2).  SiLU as y/2 + y/2 tanh(y/2) with one packed
+// tanh.approx.f16x2 per two elements: the arithmetic of ops.cu gn_vec8<true, true>, bit for bit.
+WD_DEVINL uint4 gn_apply_vec8(const uint4 hv, const float* sc8, const float* sh8) {
+  const uint32_t u[4] = {hv.x, hv.y, hv.z, hv.w};
+  const float4 s0 = *reinterpret_cast<const float4*>(sc8), s1 = *reinterpret_cast<const float4*>(sc8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(sh8), b1 = *reinterpret_cast<const float4*>(sh8 + 4);
+  const float2 sc2[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+  const float2 sh2[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 y = __ffma2_rn(unpack_f16x2(u[j]), sc2[j], sh2[j]);  // y / 2
+    uint32_t h16 = pack_f16x2(y.x, y.y), t16;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t16) : "r"(h16));
+    y = __ffma2_rn(y, unpack_f16x2(t16), y);
+    o[j] = pack_bf16x2(y.x, y.y);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // LayerNorm-consuming flavour: y = rstd * acc + (b'[c] - rstd*mu * s[c]); wvr = b', wsr = s (shared memory); bf16 out
 WD_DEVINL void epi_round80_lnc(const uint32_t* v, const float* wvr, const float* wsr, float rstd, float rstd_mu, uint8_t* srow,
                                int sub_stride) {

@@ -57,7 +57,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + PAIR_STAGES;                       // local (multicast commit)
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;                            // leader's: 16 epilogue-warp arrivals
   uint64_t* res_full_bar = tmem_empty_bar + 1;                             // [2 halves], local
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 2);
+  uint64_t* gn_bar = res_full_bar + 2;                                     // [2 rounds], local: 16 epilogue-warp arrivals (GemmArgs::gn_apply)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gn_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +90,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     mbar_init(tmem_empty_bar, 2 * GEMM_EPI_WARPS);  // one arrival per epilogue warp of BOTH CTAs
     mbar_init(&res_full_bar[0], 1);
     mbar_init(&res_full_bar[1], 1);
+    mbar_init(&gn_bar[0], 2 * GEMM_EPI_WARPS);
+    mbar_init(&gn_bar[1], 2 * GEMM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair<PAIR_TMEM_COLS>(tmem_slot);
@@ -268,6 +271,142 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       uint8_t* const srow = stg_half + row * (GEMM_SUB_N * 2);
 
+      if (args.gn_apply) {
+        // ===== GroupNorm + SiLU of the tile applied here (GemmArgs::gn_apply): out = silu(GN(acc + bias + row-bias)), bf16 =====
+        // Each round's partial sums are published as soon as the round is drained (global memory, release / acquire at cluster
+        // scope on gn_bar[rnd]); the exchange of round 0 travels under the TMEM drain of round 1 and that of round 1 under the
+        // normalisation / store of round 0.
+        const int rps = args.rows_per_sample;  // 256 % rps == 0, rps % 32 == 0: the pair tile holds whole samples
+        const int mw = m0 + q * 32;            // the 32 rows of a warp lie in one sample
+        const bool wvalid = mw < args.M;
+        const int smp = wvalid ? mw / rps : 0;
+        const int slot = (mw % rps) >> 5, nslot = rps >> 5;
+        const int G = args.N / 10;
+        float2* const part = reinterpret_cast<float2*>(args.gn_partial) + (static_cast<size_t>(smp) * G + half * 16) * nslot;
+        float mean = 0.f, rstd = 0.f;  // lane L < 8: group (16 half + 8 rnd + L) of the warp's sample, re-formed per round
+        auto publish = [&](int rnd_, float tot) {
+          if (wvalid && lane < 16) reinterpret_cast<float*>(part + static_cast<size_t>(8 * rnd_ + (lane >> 1)) * nslot + slot)[lane & 1] = tot;
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(mapa_shared(smem_u32(&gn_bar[rnd_]), 0));
+            mbar_arrive_cluster(mapa_shared(smem_u32(&gn_bar[rnd_]), 1));
+          }
+        };
+        // every epilogue warp of the pair has published its partials of round rnd_: statistics + the round's 80 scale factors
+        auto form_stats = [&](int rnd_) {
+          mbar_wait_cluster(&gn_bar[rnd_], it & 1);
+          if (wvalid && lane < 8) {
+            const float2* pg = part + static_cast<size_t>(8 * rnd_ + lane) * nslot;
+            float S = 0.f, Q = 0.f;
+            for (int i = 0; i < nslot; ++i) {  // fixed order: bit-reproducible, the order of groupnorm_apply_bulk_kernel
+              const float2 t = __ldcg(pg + i);
+              S += t.x;
+              Q += t.y;
+            }
+            const float inv_n = 1.0f / static_cast<float>(10 * rps);
+            mean = S * inv_n;
+            rstd = rsqrtf(fmaxf(fmaf(-mean, mean, Q * inv_n), 0.f) + args.gn_eps);
+          }
+        };
+        float gam[3], bet[3];  // gamma / beta of columns lane, lane + 32, lane + 64 of the current round (prefetched)
+        auto load_gb = [&](int rnd_) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c = lane + 32 * i;
+            gam[i] = c < 80 ? __ldg(args.gn_gamma + n0 + half * 160 + rnd_ * 80 + c) : 0.f;
+            bet[i] = c < 80 ? __ldg(args.gn_beta + n0 + half * 160 + rnd_ * 80 + c) : 0.f;
+          }
+        };
+        // scale / shift of the round's 80 columns -> wv[0..79] = sc / 2, wv[80..159] = sh / 2: the warp's 160-float vector is free
+        // once round 1's additive terms have been consumed.  sc = rstd gamma, sh = fma(-mean, sc, beta): the operations of
+        // groupnorm_apply_bulk_kernel, so both forms of the ResBlock give the same bits
+        auto build_table = [&]() {
+          __syncwarp();  // every lane is done with the previous contents
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c = lane + 32 * i;
+            const float r = __shfl_sync(0xffffffffu, rstd, (c < 80 ? c : 0) / 10);
+            const float mu = __shfl_sync(0xffffffffu, mean, (c < 80 ? c : 0) / 10);
+            if (c < 80) {
+              const float sc = r * gam[i];
+              const float sh = fmaf(-mu, sc, bet[i]);
+              wv[c] = 0.5f * sc;
+              wv[80 + c] = 0.5f * sh;
+            }
+          }
+          __syncwarp();
+        };
+        uint32_t hreg[40];  // round 1 waits here (fp16 pairs); round 0 waits in the staging tile
+        {
+          uint32_t v[80];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) tmem_ld_32x32b_x16p(t_row + half * 160 + c * 16, v + c * 16);
+          tmem_ld_wait();
+          if (leader_warp) {
+            if (elect_one()) bulk_wait_group_read<0>();  // the previous tile's last store has read the staging tile
+          }
+          named_barrier_sync(bar_id, 128);
+          float gs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+          epi_round80<false, true, true>(v, wv, srow, PAIR_SUB_BYTES, valid, gs);
+          publish(0, warp_transpose_reduce16(gs, lane));
+        }
+        {
+          uint32_t v[80];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) tmem_ld_32x32b_x16p(t_row + half * 160 + 80 + c * 16, v + c * 16);
+          load_gb(0);
+          tmem_ld_wait();
+          tc_fence_before();  // accumulator fully read by this warp: hand TMEM back to the leader's MMA warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(te_addr);
+          float gs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+          epi_round80_hold(v, wv + 80, hreg, valid, gs);
+          publish(1, warp_transpose_reduce16(gs, lane));
+        }
+        // ---- round 0: normalise the staged fp16 rows in place, store ----
+        form_stats(0);
+        build_table();
+        load_gb(1);
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+          uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * PAIR_SUB_BYTES + (c % 5) * 16);
+          *sp = gn_apply_vec8(*sp, wv + c * 8, wv + 80 + c * 8);
+        }
+        fence_proxy_async();
+        named_barrier_sync(bar_id, 128);
+        if (leader_warp && elect_one()) {
+          const int oc0 = n0 + half * 160;
+          tma_store_2d(&mapOut, stg_half, oc0, m0);
+          tma_store_2d(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0);
+          bulk_commit_group();
+        }
+        // ---- round 1: from the registers ----
+        form_stats(1);
+        build_table();
+        if (leader_warp) {
+          if (elect_one()) bulk_wait_group_read<0>();  // round 0's store has read the staging tile
+        }
+        named_barrier_sync(bar_id, 128);
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+          uint4* sp = reinterpret_cast<uint4*>(srow + (c / 5) * PAIR_SUB_BYTES + (c % 5) * 16);
+          *sp = gn_apply_vec8(make_uint4(hreg[c * 4], hreg[c * 4 + 1], hreg[c * 4 + 2], hreg[c * 4 + 3]), wv + c * 8, wv + 80 + c * 8);
+        }
+        fence_proxy_async();
+        named_barrier_sync(bar_id, 128);
+        if (leader_warp && elect_one()) {
+          const int oc0 = n0 + half * 160 + 80;
+          tma_store_2d(&mapOut, stg_half, oc0, m0);
+          tma_store_2d(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0);
+          bulk_commit_group();
+        }
+        continue;
+      }
+
 #pragma unroll 1
       for (int rnd = 0; rnd < 2; ++rnd) {
         // ---- drain 32 rows x 80 accumulator columns (GEGLU: 40 value + 40 gate columns) ----
@@ -377,6 +516,9 @@ bool gemm_pair_supported(const GemmArgs& a) {
   if (a.ln_out || a.ln_stats) return false;  // LayerNorm folding lives in the single-CTA kernel (K = 320 GEMMs)
   if (a.geglu) return false;  // the kernel implements it (value | gate per 320-column tile) but the weights are packed for 160-column tiles
   if (a.out_f32 && a.residual) return false;
+  if (a.gn_apply && (a.N != PAIR_BN || !a.gn_partial || a.gn_cpg != 10 || !a.gn_gamma || !a.gn_beta || a.residual || a.out_f32 ||
+                     a.act != ACT_NONE || a.rows_per_sample % 32 || 256 % a.rows_per_sample))
+    return false;
   return true;
 }
 

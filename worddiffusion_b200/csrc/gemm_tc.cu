@@ -909,6 +909,7 @@ static int gemm_pair_min_kblocks(int M) {
 }
 bool gemm_uses_pair(const GemmArgs& a) {
   if (!gemm_pair_enabled() || !gemm_pair_supported(a)) return false;
+  if (a.gn_apply) return true;  // the producer-side GroupNorm exists in the pair kernel only (the caller checked the shape)
   int total_k = 0;
   for (int s = 0; s < a.num_src; ++s) total_k += a.taps[s] * a.chunks[s];
   return total_k >= gemm_pair_min_kblocks(a.M);
@@ -928,6 +929,7 @@ cudaError_t gemm_tc_launch(const GemmLaunch& L0, cudaStream_t stream) {
     return launch_impl<GEMM_BLOCK_N_OUT, EPI_SAMPLER, 8, 0>(L, stream);
   }
   if (a.gn_partial && (a.gn_cpg != 10 || a.rows_per_sample % 32 || a.geglu || a.N % 10)) return cudaErrorInvalidValue;
+  if (a.gn_apply && !gemm_uses_pair(a)) return cudaErrorInvalidValue;  // the producer-side GroupNorm lives in the pair kernel only
   if (a.geglu && (a.residual || a.out_f32 || a.out_f16)) return cudaErrorInvalidValue;
   if (a.ln_out && (a.gn_partial || !a.out_f16 || a.out_f32 || a.geglu || a.act != ACT_NONE || a.N % 80)) return cudaErrorInvalidValue;
   if (a.ln_stats && (a.residual || a.gn_partial || a.out_f32 || a.out_f16 || a.rowbias || a.act != ACT_NONE || !a.ln_s ||

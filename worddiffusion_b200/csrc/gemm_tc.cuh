@@ -113,6 +113,15 @@ struct GemmArgs {
   // GroupNorm partial statistics of the written tensor: gn_partial[sample][N/gn_cpg groups][rows_per_sample/32][2]
   float* gn_partial;  // null: off.  Needs gn_cpg == 10, rows_per_sample % 32 == 0
   int gn_cpg;
+  // GroupNorm + SiLU of the written tensor applied by the PRODUCER (pair kernel only; unet.py:592-596 after :657-666):
+  // `out` receives silu(GroupNorm(acc + bias + row-bias)) as bf16 and the raw tensor never reaches HBM.  A 256-row pair tile
+  // holds whole samples (256 % rows_per_sample == 0), so the per-(sample, group) statistics are complete once the 16 epilogue
+  // warps of the pair have published their partials (gn_partial, exchanged through L2 behind a cluster-scope mbarrier).
+  // The values wait as fp16 (what the separate GroupNorm kernel used to read): round 0 in the staging tile, round 1 in registers.
+  int gn_apply;
+  const float* gn_gamma;  // [N]
+  const float* gn_beta;   // [N]
+  float gn_eps;
   // ---- sampler epilogue (EPI_SAMPLER; N tile = 16, columns 0..3 = predicted-noise channels) ----
   float* eps_out;      // fp32 NCHW [B,4,H,W] or null
   float* x;            // fp32 NCHW latent, updated in place when mode != STEP_EPS_ONLY

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(640, 2) groupnorm_apply_kernel(const GroupNorm
     }
     const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
     const float mean = S * inv_n;
-    const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+    const float var = fmaxf(fmaf(-mean, mean, Q * inv_n), 0.f);
     s_mean[threadIdx.x] = mean;
     s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
   }
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(512, 2) groupnorm_apply_bulk_kernel(const Grou
         }
         const float inv_n = 1.0f / static_cast<float>(cpg * a.HW);
         const float mean = S * inv_n;
-        const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+        const float var = fmaxf(fmaf(-mean, mean, Q * inv_n), 0.f);
         s_mean[threadIdx.x] = mean;
         s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
       }
@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(512, 2) groupnorm_apply_bulk_kernel(const Grou
       for (int j = 0; j < 4; ++j) {
         const int g0i = (col * 8 + 2 * j) / cpg, g1i = (col * 8 + 2 * j + 1) / cpg;
         sc2[j] = make_float2(s_rstd[g0i] * gm[2 * j], s_rstd[g1i] * gm[2 * j + 1]);
-        sh2[j] = make_float2(be[2 * j] - s_mean[g0i] * sc2[j].x, be[2 * j + 1] - s_mean[g1i] * sc2[j].y);
+        // (explicit fma: gemm_pair.cu's producer-side GroupNorm forms the same scale / shift and must give the same bits)
+        sh2[j] = make_float2(fmaf(-s_mean[g0i], sc2[j].x, be[2 * j]), fmaf(-s_mean[g1i], sc2[j].y, be[2 * j + 1]));
       }
       if constexpr (SILU) {  // gn_vec8 wants h = y / 2
 #pragma unroll
