@@ -202,6 +202,16 @@ int wd_trainer_forward(wd_trainer* t, int batch, const float* x, const int64_t* 
  * 2 (eps - noise) / numel).  y / ctx_tokens: the same index tensors as in the forward call (embedding gradients). */
 int wd_trainer_backward(wd_trainer* t, const float* d_eps, const int64_t* y, const int64_t* ctx_tokens, void* stream);
 int wd_trainer_launch_counts(const wd_trainer* t, int* fwd, int* bwd);
+/* Staged backward = the same launch list cut at layer boundaries, for a bucketed gradient all-reduce that overlaps the backward
+ * pass (what DistributedDataParallel does for the reference's `--ddp` training, train.py:253-316).
+ * wd_trainer_num_grad_stages: number of stages (one per layer, in execution order: output conv first, embeddings last).
+ * wd_trainer_grad_stage: the stage after which the gradient of state_dict key `name` is final (it may be reduced then).
+ * wd_trainer_backward_stages: runs stages [stage_begin, stage_end) of the last forward on `stream`; a whole backward pass is the
+ * calls (0,a), (a,b), ..., (z,n) in order; d_eps is read by the call that starts at stage 0.  Each range replays as its own
+ * CUDA graph from its third call on. */
+int wd_trainer_num_grad_stages(wd_trainer* t, int* n);
+int wd_trainer_grad_stage(wd_trainer* t, const char* name, int* stage);
+int wd_trainer_backward_stages(wd_trainer* t, const float* d_eps, int stage_begin, int stage_end, void* stream);
 /* test hook: copies a named intermediate of the last forward ("temb", "h1p", "h1", "embp", "emb_act" bf16 [B,*];
  * "emb_out" fp32 [B, 8*320]; "ctx", "kv_all" bf16) into dst (device); `bytes` must match. */
 int wd_trainer_read_tensor(const wd_trainer* t, const char* name, void* dst, size_t bytes, void* stream);

@@ -180,6 +180,47 @@ def test_fused_train_step_reduces_loss_and_tracks_ema():
     assert float(torch.nn.functional.mse_loss(noise, e)) < losses[0]
 
 
+def test_staged_backward_equals_the_whole_backward():
+    """wd_trainer_backward_stages (the backward pass cut at layer boundaries for a bucketed, overlapped gradient
+    all-reduce): every parameter's gradient is final after the stage wd_trainer_grad_stage names, the flat buffer is laid out in
+    that order, and running the stages bucket by bucket gives the gradients of the single-call backward (the fp32 atomics of
+    the weight-gradient epilogues make the two agree to rounding, not bit for bit).  Four rounds: eager, capture, replay."""
+    from worddiffusion_b200.training import plan_grad_buckets
+    m, _ = _model()
+    eng = m.train_engine(DEV)
+    eng.bind()
+    eng.sync_weights()
+    B = 4
+    inp = {k: v.to(DEV) for k, v in W.make_inputs(B, seed=SEED + 5).items()}
+    d_eps = torch.randn((B, 4, 8, 32), generator=torch.Generator().manual_seed(6)).to(DEV) / 1024
+    st = [eng.stage_of[n] for n, _ in eng.live]
+    assert eng.n_stages > 10 and st == sorted(st) and min(st) == 0 and max(st) == eng.n_stages - 1
+    assert eng.stage_of["out.2.weight"] == 0 and eng.stage_of["time_embed.0.weight"] >= eng.stage_of["input_blocks.1.0.in_layers.2.weight"]
+    offs = [eng.offsets[n] for n, _ in eng.live]
+    assert offs == sorted(offs)
+    buckets = eng.grad_buckets(4)
+    assert len(buckets) == 4 and buckets[-1][0] == eng.n_stages and buckets[-1][2] == eng.flat_grad.numel()
+    assert buckets == plan_grad_buckets(st, [(p.numel() + 63) // 64 * 64 for _, p in eng.live], eng.n_stages, 4)
+    eng.forward(inp["x"], inp["t"], inp["y"], inp["context"])
+    eng.backward(d_eps)
+    whole = eng.flat_grad.clone()
+    for rnd in range(4):
+        eng.forward(inp["x"], inp["t"], inp["y"], inp["context"])
+        s0 = 0
+        for s1, lo, hi in buckets:
+            eng.backward_stages(d_eps, s0, s1)
+            # what an all-reduce launched here would read: already final
+            part = eng.flat_grad[lo:hi].clone()
+            assert relerr(part, whole[lo:hi]) < 1e-5, (rnd, s1)
+            s0 = s1
+        assert relerr(eng.flat_grad, whole) < 1e-5
+    # stages out of order are refused
+    from worddiffusion_b200._lib import WdError
+    eng.forward(inp["x"], inp["t"], inp["y"], inp["context"])
+    with pytest.raises(WdError, match="in order"):
+        eng.backward_stages(d_eps, 1, 2)
+
+
 def test_trainer_validates_every_extent():
     """the C side copies batch * C * H * W floats from the pointers it is handed; a wrong latent size / ragged
     conditioning must raise before any kernel runs, not read out of bounds."""

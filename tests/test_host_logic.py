@@ -349,3 +349,53 @@ def test_all_gather_with_an_empty_shard_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, 1, True), (1, 0, True)]
+
+
+def test_gradient_bucket_plan():
+    """plan_grad_buckets (training.py): contiguous, covering, cut only at stage boundaries, last bucket ends the pass."""
+    from worddiffusion_b200.training import plan_grad_buckets
+    stages = [0, 0, 1, 2, 2, 3, 5, 5]
+    sizes = [64, 64, 192, 64, 64, 256, 64, 64]
+    for nb in (1, 2, 3, 4, 8, 50):
+        b = plan_grad_buckets(stages, sizes, 7, nb)
+        assert 1 <= len(b) <= nb and b[0][1] == 0 and b[-1][2] == sum(sizes) and b[-1][0] == 7
+        assert all(x[2] == y[1] for x, y in zip(b, b[1:])) and all(x[0] < y[0] for x, y in zip(b, b[1:]))
+        pos = 0
+        for st, sz in zip(stages, sizes):  # a slice lies in a bucket whose stage_end is past the slice's final stage
+            k = next(i for i, x in enumerate(b) if x[1] <= pos < x[2])
+            assert b[k][0] > st and pos + sz <= b[k][2]
+            pos += sz
+    with pytest.raises(ValueError):
+        plan_grad_buckets([1, 0], [64, 64], 2, 2)
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from worddiffusion_b200.training import plan_grad_buckets
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1024, generator=g)
+    whole = flat.clone()
+    dist.all_reduce(whole)
+    works = [dist.all_reduce(flat[lo:hi], async_op=True) for _, lo, hi in plan_grad_buckets([0, 1, 2, 3], [256] * 4, 4, 3)]
+    for w in works:
+        w.wait()
+    q.put((rank, bool(torch.equal(flat, whole))))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_whole_allreduce_gloo():
+    """world_size 2 on CPU (gloo): all-reducing the buckets of the flat gradient one by one, asynchronously, is the
+    all-reduce of the whole buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert res == {0: True, 1: True}

@@ -68,6 +68,9 @@ SIGNATURES = {
     "wd_trainer_forward": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wd_trainer_backward": (_I, [_P, _P, _P, _P, _P]),
     "wd_trainer_launch_counts": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "wd_trainer_num_grad_stages": (_I, [_P, C.POINTER(_I)]),
+    "wd_trainer_grad_stage": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
+    "wd_trainer_backward_stages": (_I, [_P, _P, _I, _I, _P]),
     "wd_trainer_read_tensor": (_I, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "wd_trainer_workspace_bytes": (C.c_size_t, [_P]),
     "wd_trainer_weight_bytes": (C.c_size_t, [_P]),

@@ -156,9 +156,18 @@ struct TPlan {
   float* in_deps = nullptr;
   cudaGraphExec_t g_fwd = nullptr, g_bwd = nullptr;
   int fwd_calls = 0, bwd_calls = 0;
+  // Backward stages (one per layer of the tape, in execution order): stage s covers bwd[stage_end[s-1], stage_end[s]).
+  // grad_stage[name] = the last stage that writes the gradient of that parameter (it is final once the stage has run), so
+  // the caller can all-reduce a bucket of gradients while the later stages still run (wd_trainer_backward_stages).
+  std::vector<int> stage_end;
+  std::map<std::string, int> grad_stage;
+  struct Seg { cudaGraphExec_t exec = nullptr; int calls = 0; };
+  std::map<std::pair<int, int>, Seg> segs;  // launch list [stage_begin, stage_end) as its own CUDA graph
   ~TPlan() {
     if (g_fwd) cudaGraphExecDestroy(g_fwd);
     if (g_bwd) cudaGraphExecDestroy(g_bwd);
+    for (auto& kv : segs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   }
 };
 
@@ -202,6 +211,9 @@ struct wd_trainer {
   TPlan* cur = nullptr;
   bool fwd_done = false;
   bool packs_valid = false;
+  std::map<std::string, int> grad_stage;  // from a dry plan build (the order does not depend on batch / context length)
+  int n_stages = 0;
+  int bwd_next_stage = 0;  // staged backward: the stage the next wd_trainer_backward_stages call must start at
 };
 
 namespace {
@@ -503,7 +515,11 @@ struct TPlanBuilder {
   std::vector<std::function<bool()>> tape;  // backward emitters, run in reverse order
 
   const float* W(const std::string& n) { return dry ? nullptr : e->params[n].w; }
-  float* G(const std::string& n) { return dry ? nullptr : e->params[n].g; }
+  std::vector<std::string> g_touched;  // gradients named by the backward emitter that is running
+  float* G(const std::string& n) {
+    g_touched.push_back(n);
+    return dry ? nullptr : e->params[n].g;
+  }
 
   TT* new_t(int H, int Wd, int C, bool with_grad = true) {
     plan->tensors.emplace_back();
@@ -1402,8 +1418,14 @@ struct TPlanBuilder {
       });
     }
     // ================= backward plan: the tape in reverse =================
-    for (auto it = tape.rbegin(); it != tape.rend(); ++it)
+    g_touched.clear();
+    for (auto it = tape.rbegin(); it != tape.rend(); ++it) {
       if (!(*it)()) return false;
+      const int stage = static_cast<int>(plan->stage_end.size());
+      for (const std::string& n : g_touched) plan->grad_stage[n] = stage;
+      g_touched.clear();
+      plan->stage_end.push_back(static_cast<int>(plan->bwd.size()));
+    }
     plan->bytes = A.used;
     return true;
   }
@@ -1450,6 +1472,14 @@ int ensure_tplan(wd_trainer* e, int B, int L, TPlan** out) {
   TPlanBuilder pb{e, p.get(), A, false, B};
   if (!pb.build()) return tfail(WD_ERR_UNSUPPORTED, "train plan: %s", pb.err.c_str());
   for (auto& z : pb.T_ZERO_ONCE) T_CUDA_TRY(cudaMemset(z.first, 0, z.second));
+  if (e->n_stages > 0) {  // the caller may already have laid its gradient buckets out by stage
+    if (static_cast<int>(p->stage_end.size()) != e->n_stages) return tfail(WD_ERR_STATE, "backward stage count changed between plans");
+    for (auto& kv : p->grad_stage) {
+      auto it2 = e->grad_stage.find(kv.first);
+      const int promised = it2 == e->grad_stage.end() ? e->n_stages - 1 : it2->second;
+      if (kv.second > promised) return tfail(WD_ERR_STATE, "gradient of '%s' finishes in a later stage than announced", kv.first.c_str());
+    }
+  }
   *out = p.get();
   // plans of different batch sizes alias the same arena: only one is valid at a time
   e->plans.clear();
@@ -1513,6 +1543,19 @@ bool train_graph_enabled() {  // env WD_TRAIN_GRAPH (default on): replay the lau
   return v != 0 && !train_prof_enabled();
 }
 // first call of a plan: eager (kernel attributes get set, errors surface per launch); second call: captured; then replayed
+// dry plan build -> which backward stage finishes each parameter's gradient (structure only: no device memory is touched)
+int compute_grad_stages(wd_trainer* e) {
+  if (e->n_stages > 0) return WD_OK;
+  TPlan tmp;
+  tmp.B = 2;
+  tmp.L = std::max(1, std::min(e->cfg.max_seq_len, 16));
+  TPlanBuilder pb{e, &tmp, TArena(), true, tmp.B};
+  if (!pb.build()) return tfail(WD_ERR_UNSUPPORTED, "train plan: %s", pb.err.c_str());
+  e->grad_stage = tmp.grad_stage;
+  e->n_stages = static_cast<int>(tmp.stage_end.size());
+  return WD_OK;
+}
+
 int run_list(const std::vector<TOp>& ops, const TRun& r, cudaStream_t s, const char* phase, cudaGraphExec_t* exec, int* calls,
              const std::vector<std::pair<void*, size_t>>* zero_first) {
   ++*calls;
@@ -1732,6 +1775,7 @@ extern "C" int wd_trainer_forward(wd_trainer* e, int batch, const float* x, cons
   if (rc) return rc;
   T_CUDA_TRY(cudaMemcpyAsync(eps_out, p->out_eps, static_cast<size_t>(batch) * e->cfg.out_channels * HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   e->fwd_done = true;
+  e->bwd_next_stage = 0;
   return WD_OK;
 }
 
@@ -1751,6 +1795,57 @@ extern "C" int wd_trainer_backward(wd_trainer* e, const float* d_eps, const int6
   const int rc = run_list(p->bwd, r, s, "backward", &p->g_bwd, &p->bwd_calls, &p->zero_on_bwd);
   e->fwd_done = false;
   return rc;
+}
+
+// ---- staged backward: the same launch list cut at layer boundaries, so that the caller can start the all-reduce of the
+// gradients a stage has finished while the later stages still run (bucketed, overlapped gradient exchange) ----
+extern "C" int wd_trainer_num_grad_stages(wd_trainer* e, int* n) {
+  if (!e || !n) return tfail(WD_ERR_INVALID, "null argument");
+  const int rc = compute_grad_stages(e);
+  if (rc) return rc;
+  *n = e->n_stages;
+  return WD_OK;
+}
+// *stage = the backward stage after which the gradient of parameter `name` is final (0-based, execution order)
+extern "C" int wd_trainer_grad_stage(wd_trainer* e, const char* name, int* stage) {
+  if (!e || !name || !stage) return tfail(WD_ERR_INVALID, "null argument");
+  const int rc = compute_grad_stages(e);
+  if (rc) return rc;
+  if (!e->expected.count(name)) return tfail(WD_ERR_INVALID, "'%s' is not a parameter that receives a gradient", name);
+  auto it = e->grad_stage.find(name);
+  *stage = it == e->grad_stage.end() ? e->n_stages - 1 : it->second;  // not named by the dry build: final at the end
+  return WD_OK;
+}
+// runs the backward stages [stage_begin, stage_end) of the last forward; a whole backward pass is the calls
+// (0, a), (a, b), ..., (z, n) in order.  d_eps is read by the call that starts at stage 0.
+extern "C" int wd_trainer_backward_stages(wd_trainer* e, const float* d_eps, int stage_begin, int stage_end, void* stream) {
+  if (!e) return tfail(WD_ERR_INVALID, "null argument");
+  if (!e->cur || !e->fwd_done) return tfail(WD_ERR_STATE, "wd_trainer_forward must run before wd_trainer_backward_stages");
+  TPlan* p = e->cur;
+  const int n = static_cast<int>(p->stage_end.size());
+  if (stage_begin < 0 || stage_end <= stage_begin || stage_end > n) return tfail(WD_ERR_INVALID, "bad stage range [%d, %d) of %d", stage_begin, stage_end, n);
+  if (stage_begin != e->bwd_next_stage) return tfail(WD_ERR_STATE, "backward stages must run in order: expected stage %d, got %d", e->bwd_next_stage, stage_begin);
+  if (stage_begin == 0 && !d_eps) return tfail(WD_ERR_INVALID, "d_eps is required by the first stage");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (stage_begin == 0) {
+    const size_t HW = static_cast<size_t>(e->cfg.latent_h) * e->cfg.latent_w;
+    T_CUDA_TRY(cudaMemcpyAsync(p->in_deps, d_eps, static_cast<size_t>(p->B) * e->cfg.out_channels * HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  TRun r;
+  r.d_eps = p->in_deps;
+  r.y = p->in_y;
+  r.ctx = p->in_ctx;
+  const int lo = stage_begin == 0 ? 0 : p->stage_end[stage_begin - 1], hi = p->stage_end[stage_end - 1];
+  std::vector<TOp> ops(p->bwd.begin() + lo, p->bwd.begin() + hi);
+  TPlan::Seg& seg = p->segs[std::make_pair(stage_begin, stage_end)];
+  const int rc = run_list(ops, r, s, "backward stages", &seg.exec, &seg.calls, stage_begin == 0 ? &p->zero_on_bwd : nullptr);
+  if (rc) {
+    e->bwd_next_stage = 0;
+    return rc;
+  }
+  e->bwd_next_stage = stage_end == n ? 0 : stage_end;
+  if (stage_end == n) e->fwd_done = false;
+  return WD_OK;
 }
 
 extern "C" int wd_trainer_launch_counts(const wd_trainer* e, int* fwd, int* bwd) {

@@ -102,6 +102,22 @@ class TrainEngine:
                 offsets[n] = total
                 total += (p.numel() + 63) // 64 * 64  # 256-byte aligned slices
                 live.append((n, p))
+        # lay the slices out in the order the backward pass finishes them (wd_trainer_grad_stage): a bucket of the gradient
+        # all-reduce is then one contiguous range that can leave while the later stages still run (plan_grad_buckets)
+        nst = C.c_int(0)
+        check(l.wd_trainer_num_grad_stages(self._h, C.byref(nst)), "wd_trainer_num_grad_stages")
+        self.n_stages = nst.value
+        stage_of = {}
+        for n, _ in live:
+            st = C.c_int(0)
+            check(l.wd_trainer_grad_stage(self._h, n.encode(), C.byref(st)), f"grad_stage({n})")
+            stage_of[n] = st.value
+        live.sort(key=lambda np_: stage_of[np_[0]])  # stable: state_dict order inside a stage
+        offsets, total = {}, 0
+        for n, p in live:
+            offsets[n] = total
+            total += (p.numel() + 63) // 64 * 64  # 256-byte aligned slices
+        self.stage_of = stage_of
         if flat_grad is None:
             flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
         elif flat_grad.numel() != total:
@@ -160,6 +176,30 @@ class TrainEngine:
         self._hold_shape = tuple(x.shape)
         return out
 
+    def grad_buckets(self, n_buckets):
+        """[(stage_end, lo, hi)]: once the backward stages [.., stage_end) have run, flat_grad[lo:hi] is final."""
+        stages = [self.stage_of[n] for n, _ in self.live]
+        sizes = [(p.numel() + 63) // 64 * 64 for _, p in self.live]
+        return plan_grad_buckets(stages, sizes, self.n_stages, n_buckets)
+
+    def backward_stages(self, d_eps, stage_begin, stage_end, zero=True):
+        """Stages [stage_begin, stage_end) of the backward pass of the last forward (wd_trainer_backward_stages); the call
+        that starts at stage 0 zeroes the flat gradient buffer (``zero``) and reads ``d_eps``."""
+        if self._hold is None:
+            raise _lib.WdError("backward called without a forward")
+        d = None
+        if stage_begin == 0:
+            if tuple(d_eps.shape) != self._hold_shape:
+                raise _lib.WdError(f"d_eps must have the shape of the forward's x {self._hold_shape}, got {tuple(d_eps.shape)}")
+            d = d_eps.to(device=self.device, dtype=torch.float32).contiguous()
+            if zero:
+                self.flat_grad.zero_()
+        with torch.cuda.device(self.device):
+            check(lib().wd_trainer_backward_stages(self._h, _ptr(d), int(stage_begin), int(stage_end), _stream_ptr()),
+                  "wd_trainer_backward_stages")
+        if stage_end == self.n_stages:
+            self._hold = None
+
     def backward(self, d_eps, zero=True):
         """Accumulates the parameter gradients of the last forward into the flat gradient buffer."""
         if self._hold is None:
@@ -211,6 +251,29 @@ def unet_train_forward(module, x, timesteps, context, y):
     return _UNetTrainFn.apply(module, x, timesteps, context, y, *params)
 
 
+def plan_grad_buckets(stages, sizes, n_stages, n_buckets):
+    """Cuts the flat gradient buffer into at most ``n_buckets`` contiguous ranges of roughly equal size at backward-stage
+    boundaries.  ``stages[i]`` / ``sizes[i]``: final stage and (padded) element count of slice i, in buffer order, stages
+    non-decreasing.  Returns ``[(stage_end, lo, hi)]`` with stage_end strictly increasing and the last one == n_stages:
+    after stages [.., stage_end) the elements [lo, hi) are final (torch DDP's gradient buckets, built from the engine's own
+    backward order instead of autograd hooks)."""
+    if any(b < a for a, b in zip(stages, stages[1:])):
+        raise ValueError("slices must be ordered by the stage that finishes them")
+    total = sum(sizes)
+    n_buckets = max(1, int(n_buckets))
+    buckets, lo, pos, k = [], 0, 0, 1
+    for i, (st, sz) in enumerate(zip(stages, sizes)):
+        pos += sz
+        last_of_stage = i + 1 == len(stages) or stages[i + 1] != st
+        if last_of_stage and k < n_buckets and pos >= total * k / n_buckets and i + 1 < len(stages):
+            buckets.append((st + 1, lo, pos))
+            lo = pos
+            while pos >= total * k / n_buckets:
+                k += 1
+    buckets.append((n_stages, lo, total))
+    return buckets
+
+
 def allreduce_sum_(flat, group=None):
     """Data-parallel gradient exchange (train.py --ddp): in-place SUM all-reduce of the flat gradient buffer.
     Returns the world size (the optimizer kernel divides by it: DDP's gradient averaging)."""
@@ -237,7 +300,7 @@ class FusedTrainStep:
     gradient is sum-all-reduced over NCCL and averaged (DDP semantics) before the update."""
 
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, ema_beta=0.995,
-                 step_start_ema=2000, process_group=None, use_ema=True, latent_hw=(8, 32)):
+                 step_start_ema=2000, process_group=None, use_ema=True, latent_hw=(8, 32), grad_buckets=4):
         p0 = next(module.parameters())
         self.module = module
         self.device = p0.device
@@ -259,6 +322,9 @@ class FusedTrainStep:
         self.ema_beta, self.step_start_ema = ema_beta, step_start_ema
         self.t = 0
         self.pg = process_group
+        # gradient exchange: `grad_buckets` contiguous ranges of the flat buffer, each all-reduced (async, NCCL's own stream)
+        # as soon as the backward stage that finishes it has been launched, under the remaining stages
+        self.buckets = eng.grad_buckets(grad_buckets)
         eng.sync_weights(force=True)
 
     def world_size(self):
@@ -281,8 +347,21 @@ class FusedTrainStep:
         with torch.cuda.device(self.device):
             check(lib().wd_mse_loss_grad(_ptr(eps), _ptr(noise), _ptr(d_eps), _ptr(loss), _ptr(self._mse_ws), n_el, _stream_ptr()),
                   "wd_mse_loss_grad")
-        eng.backward(d_eps)
-        ws = allreduce_sum_(eng.flat_grad, self.pg)
+        ws = self.world_size()
+        if ws > 1 and len(self.buckets) > 1:
+            import torch.distributed as dist
+            works, s0 = [], 0
+            for s1, lo, hi in self.buckets:
+                eng.backward_stages(d_eps, s0, s1)
+                # the collective is ordered after the launches above (NCCL's stream waits for the current stream here) and
+                # runs beside the stages launched next; the optimizer kernel waits for all of them
+                works.append(dist.all_reduce(eng.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                s0 = s1
+            for w in works:
+                w.wait()
+        else:
+            eng.backward(d_eps)
+            ws = allreduce_sum_(eng.flat_grad, self.pg)
         self.t += 1
         # EMA.step_ema (train.py:161-167): copy during the warm-up, moving average afterwards
         ema_mode = 0 if self.ema is None else (1 if self.t <= self.step_start_ema else 2)
