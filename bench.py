@@ -357,6 +357,9 @@ def train_leg(args, world, rank, dev):
             "global_batch": gb, "batch_per_gpu": hi - lo, "scaling": "strong", "steps": args.train_steps,
             "model_tflops": round(3 * (9.153 + 0.039) * 1e9 * gb / (ms * 1e-3) / 1e12, 1),
             "gpu_launches_per_step": f + b + 1, "loss_first": first, "loss_last": float(loss),
+            "grad_allreduce": (f"{len(step.buckets)} buckets by backward stage, each launched (async, NCCL) behind the stage that "
+                               "finishes it" if world > 1 and len(step.buckets) > 1 else "one all-reduce after the backward pass"
+                               if world > 1 else "none (1 GPU)"),
             "workload": "unet.UNetModel noise-prediction training step: forward + backward + gradient all-reduce + AdamW + EMA "
                         "(bf16 tensor-core operands, fp32 master weights / accumulation)"}
 

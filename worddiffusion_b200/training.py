@@ -300,7 +300,7 @@ class FusedTrainStep:
     gradient is sum-all-reduced over NCCL and averaged (DDP semantics) before the update."""
 
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, ema_beta=0.995,
-                 step_start_ema=2000, process_group=None, use_ema=True, latent_hw=(8, 32), grad_buckets=4):
+                 step_start_ema=2000, process_group=None, use_ema=True, latent_hw=(8, 32), grad_buckets=None):
         p0 = next(module.parameters())
         self.module = module
         self.device = p0.device
@@ -324,6 +324,9 @@ class FusedTrainStep:
         self.pg = process_group
         # gradient exchange: `grad_buckets` contiguous ranges of the flat buffer, each all-reduced (async, NCCL's own stream)
         # as soon as the backward stage that finishes it has been launched, under the remaining stages
+        if grad_buckets is None:
+            import os
+            grad_buckets = int(os.environ.get("WD_GRAD_BUCKETS", "4"))  # 1: one all-reduce after the whole backward pass
         self.buckets = eng.grad_buckets(grad_buckets)
         eng.sync_weights(force=True)
 
