@@ -6,26 +6,30 @@
 // One CTA = (MT x 128 query rows, head, sample).  MT = 1 (default): 4 ring slots, 112 KB of shared memory, two CTAs per SM, 192
 // threads.  MT = 2 (env WD_ATTN_TC_MT2=1; both query tiles of a 256-token sample share every K / V tile, 8 slots, 224 KB, one CTA
 // per SM, 320 threads) halves the L2 -> SM operand traffic but measured slower: a lone CTA cannot hide its softmax <-> MMA chain.
-//   warp 0     TMA producer: Q once, then the K tiles (pass 1) and K, V tiles (pass 2) of 64 keys as UNITS through a ring of 16 KB
-//              slots (a K slot is released when its QK^T retires, a V slot after its PV).  Every operand tile is a pair of
+//   warp 0     TMA producer: Q once, then K(0), V(0), K(1), V(1), ... tiles of 64 keys as UNITS through a ring of 16 KB slots
+//              (a K slot is released when its QK^T retires, a V slot after its PV).  Every operand tile is a pair of
 //              SWIZZLE_128B boxes of 64 channels starting at the head's first channel: the second box over-fetches 48 channels of
 //              the next head (zero-filled past the tensor's last column), only its first 16 are used.
 //   warp 1     TMEM allocation + single-thread MMA issue.
 //                S = Q K^T : 128 x 64 x 16, five K steps (four in box 0, one in box 1), both operands K-major.
 //                O += P V  : 128 x 80 x 16, four K steps of 16 keys; P is K-major (written by the softmax warps), V is consumed
 //                            as an MN-major operand straight from its [key][channel] boxes (descriptor LBO = box pitch).
-//   warps 2..  softmax (four warps per M tile), one query row per thread (= TMEM lane).  TWO PASSES over the keys instead of an
-//              online softmax: pass 1 only reduces the row maximum of the scores, pass 2 recomputes S, forms P = exp2(scale log2e (S - max)) as bf16 in
-//              a swizzled shared-memory tile and accumulates the row sum.  O is therefore never rescaled in TMEM (an online
-//              softmax needs a tcgen05.ld / st round trip of the 128 x 80 accumulator whenever a maximum moves); the price is a
-//              second QK^T (and a second read of K), which the tensor pipe has room for.
-//              S is double-buffered in TMEM, so QK^T of tile j+1 overlaps the exponentials of tile j.
+//   warps 2..  softmax (four warps per M tile), one query row per thread (= TMEM lane).  ONE pass over the keys with a LAZY
+//              running maximum: P = exp2(scale log2e (S - m)) where m only moves when a tile's maximum exceeds it by more than
+//              2^8 in the exponent (P stays <= 256, exact in bf16 range; O / l does not depend on m).  When it moves, the warp
+//              rescales its own 32 rows of O in TMEM (tcgen05.ld / st) between the retirement of PV(j-1) and its P(j) arrival
+//              -- with bounded scores that is the first tile or two.  Round 1 ran TWO passes (row maxima first, then a second
+//              QK^T and a second read of K): 1.5x the MMAs, 1.5x the K / V operand bytes (the binding resource: L2 -> SM
+//              ingest), and ~1.7x the softmax-warp instructions of this form.
+//              S is double-buffered in TMEM and handed back as soon as the scores are in registers, so QK^T of tile j+1 / j+2
+//              overlaps the exponentials of tile j.
 // Keys beyond Skv are zero-filled by TMA (3-D maps: channel, row, sample) and masked to -inf; query rows beyond Sq are
 // computed on zero-filled operands and not stored.
 #include "ops.cuh"
 
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 namespace wd {
 
@@ -71,6 +75,12 @@ WD_DEVINL uint64_t at_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
+WD_DEVINL float at_max3(float a, float b, float c) {  // FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 WD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
@@ -79,9 +89,9 @@ WD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       : "memory");
 }
 
-// Operand tiles travel through a ring of 16 KB slots as UNITS: pass 1: K(0), K(1), ...; pass 2: K(0), V(0), K(1), V(1), ...
+// Operand tiles travel through a ring of 16 KB slots as UNITS: K(0), V(0), K(1), V(1), ...
 // Unit w lives in slot w % SLOTS (parity (w / SLOTS) & 1).  A K slot is released as soon as its QK^T has retired, a V slot after
-// its PV -- so in pass 1 SLOTS K tiles are in flight, in pass 2 SLOTS / 2 tiles.
+// its PV -- SLOTS / 2 key tiles are in flight.
 template <int MT>
 __global__ void __launch_bounds__(ATCfg<MT>::THREADS, MT == 1 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -145,12 +155,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         tma_load_3d(sQ + mt * AT_QT_BYTES, &mapQ, q_full, c_head, q0 + mt * AT_BM, b);
         tma_load_3d(sQ + mt * AT_QT_BYTES + AT_BM * 128, &mapQ, q_full, c_head + 64, q0 + mt * AT_BM, b);
       }
-      const int units = 3 * ntiles;
+      const int units = 2 * ntiles;  // K(0), V(0), K(1), V(1), ...
       for (int w = 0; w < units; ++w) {
         const int sl = w % NS;
-        // unit -> (operand, key tile): pass 1 holds K(w); pass 2 alternates K(j), V(j)
-        const bool is_v = w >= ntiles && ((w - ntiles) & 1);
-        const int j = w < ntiles ? w : (w - ntiles) >> 1;
+        const bool is_v = (w & 1) != 0;
+        const int j = w >> 1;
         mbar_wait(&u_empty[sl], ((w / NS) & 1) ^ 1);
         uint8_t* dst = sRing + sl * AT_SLOT_BYTES;
         mbar_arrive_expect_tx(&u_full[sl], AT_SLOT_BYTES);
@@ -166,11 +175,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(AT_BM, AT_DH) | (1u << 16);  // B (= V) is MN-major
       mbar_wait(q_full, 0);
       tc_fence_after();
-      // QK^T of score-buffer use `u` (tile counter over both passes) from the K tile in ring unit `w`
-      auto issue_qk = [&](int u, int w) {
-        const int buf = u & 1, sl = w % NS;
+      // S(j) = Q K(j)^T into score buffer j & 1 from ring unit 2 j
+      auto issue_qk = [&](int j) {
+        const int buf = j & 1, w = 2 * j, sl = w % NS;
         mbar_wait(&u_full[sl], (w / NS) & 1);
-        mbar_wait(&s_empty[buf], ((u >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sRing + sl * AT_SLOT_BYTES);
         const uint64_t k_desc0 = make_smem_desc_sw128(k_addr);
@@ -187,16 +196,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         umma_commit(&s_full[buf]);
         umma_commit(&u_empty[sl]);  // the K tile is free once these MMAs retire
       };
-      int u = 0;
-      // ---- pass 1: scores only (row maxima) ----
-      for (int j = 0; j < ntiles; ++j, ++u) issue_qk(u, j);
-      // ---- pass 2: S(j+1) is issued ahead of P(j) V(j) ----
-      issue_qk(u, ntiles);
-      for (int j = 0; j < ntiles; ++j, ++u) {
-        if (j + 1 < ntiles) issue_qk(u + 1, ntiles + 2 * (j + 1));
-        const int wv = ntiles + 2 * j + 1, sl = wv % NS;
+      // S(j+1) is issued ahead of P(j) V(j)
+      issue_qk(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_qk(j + 1);
+        const int wv = 2 * j + 1, sl = wv % NS;
         mbar_wait(&u_full[sl], (wv / NS) & 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, j & 1);  // P(j) is written -- and the softmax warps are done rescaling O
         tc_fence_after();
         const uint64_t v_desc = at_desc_mn_sw128(smem_u32(sRing + sl * AT_SLOT_BYTES));
 #pragma unroll
@@ -217,57 +223,97 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const int qd = warp & 3;         // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(qd * 32) << 16;
-    int u = 0;
-    // ---- pass 1: row maximum of the raw scores ----
-    float mx = -INFINITY;
-    for (int j = 0; j < ntiles; ++j, ++u) {
-      const int buf = u & 1;
-      mbar_wait(&s_full[buf], (u >> 1) & 1);
+    // ---- one pass over the keys: P = exp2(sl2 (S - m)) with a LAZY running maximum m.  m only moves when a tile's maximum
+    // exceeds it by more than 2^8 in the exponent; then this warp rescales its 32 rows of O in TMEM (and l) before P(j) is
+    // published -- PV(j-1) has retired by then (p_empty) and PV(j) is not issued before every warp's P(j) arrival.  With
+    // bounded score ranges that happens on the first tiles only, and O / l is exact whatever m was used. ----
+    float m_used = -INFINITY, l = 0.f;
+    uint8_t* const prow = sP + mt * AT_PT_BYTES + row * 128;
+    const uint32_t o_addr = tmem_base + t_lane + C::O_COL + mt * AT_DH;
+    const bool ragged = (a.Skv % AT_BK) != 0;
+    for (int j = 0; j < ntiles; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK + half * 32, v);
+      uint32_t v[64];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(v);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(v + 32);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK, v0);
+        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK + 32, v1);
         tmem_ld_wait();
-        const int key0 = j * AT_BK + half * 32;
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (key0 + c < a.Skv) mx = fmaxf(mx, __uint_as_float(v[c]));
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[buf]);
-    }
-    const float mxs = mx * a.sl2;
-    // ---- pass 2: P = exp2(sl2 S - max) -> bf16 swizzled tile, row sums ----
-    float l = 0.f;
-    uint8_t* const prow = sP + mt * AT_PT_BYTES + row * 128;
-    for (int j = 0; j < ntiles; ++j, ++u) {
-      const int buf = u & 1;
-      mbar_wait(&s_full[buf], (u >> 1) & 1);
-      tc_fence_after();
-      uint32_t pk[32];  // 64 probabilities as bf16 pairs
+      if (lane == 0) mbar_arrive(&s_empty[buf]);  // the scores are in registers: S(j+2) may overwrite the buffer
+      const bool mask = ragged && j == ntiles - 1;
+      const int nvalid = a.Skv - j * AT_BK;  // valid keys of this tile (only read when mask)
+      float tm = -INFINITY;
+      if (!mask) {
+        // four independent chains of 3-input maxima (a single fmaxf chain is 64 dependent instructions deep)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + t_lane + (2 * mt + buf) * AT_BK + half * 32, v);
-        tmem_ld_wait();
-        const int key0 = j * AT_BK + half * 32;
+        for (int c = 0; c < 64; c += 8) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float p0, p1;  // MUFU.EX2 directly: the arguments are <= 0, no range fix-up is needed
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[c]), a.sl2, -mxs)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[c + 1]), a.sl2, -mxs)));
-          if (key0 + c >= a.Skv) p0 = 0.f;
-          if (key0 + c + 1 >= a.Skv) p1 = 0.f;
-          l += p0 + p1;
-          pk[half * 16 + c / 2] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 4; ++i) m4[i] = at_max3(m4[i], __uint_as_float(v[c + 2 * i]), __uint_as_float(v[c + 2 * i + 1]));
+        }
+        tm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c < nvalid) tm = fmaxf(tm, __uint_as_float(v[c]));
+      }
+      bool waited = false;
+      if (j == 0) {
+        m_used = tm;
+      } else {
+        const bool need = (tm - m_used) * a.sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(p_empty, (j - 1) & 1);  // PV(j-1) has retired: O holds tiles 0 .. j-1
+          waited = true;
+          tc_fence_after();
+          float f = 1.0f;
+          if (need) {
+            f = exp2f((m_used - tm) * a.sl2);
+            m_used = tm;
+          }
+#pragma unroll
+          for (int cb = 0; cb < AT_DH / 16; ++cb) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(o_addr + cb * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32b_x16(o_addr + cb * 16, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          l *= f;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[buf]);  // the score buffer may be overwritten by S(j+2)
-      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);  // P(j-1) V(j-1) has read the tile
+      const float mxs = m_used * a.sl2;
+      uint32_t pk[32];  // 64 probabilities as bf16 pairs
+      const float2 sl2_2 = make_float2(a.sl2, a.sl2), nm2 = make_float2(-mxs, -mxs);
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // packed fp32 arithmetic: half the issue slots
+      auto exps = [&](auto masked) {  // two straight-line variants: only the last tile of a ragged key sequence masks
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), sl2_2, nm2);
+          float2 pp;  // MUFU.EX2 directly: the arguments are <= 8, no range fix-up is needed
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pp.x) : "f"(x.x));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pp.y) : "f"(x.y));
+          if constexpr (decltype(masked)::value) {
+            if (c >= nvalid) pp.x = 0.f;
+            if (c + 1 >= nvalid) pp.y = 0.f;
+          }
+          ls[(c >> 1) & 1] = __fadd2_rn(ls[(c >> 1) & 1], pp);
+          pk[c / 2] = pack_bf16x2(pp.x, pp.y);
+        }
+      };
+      if (mask) exps(std::true_type{});
+      else exps(std::false_type{});
+      l += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+      if (j > 0 && !waited) mbar_wait(p_empty, (j - 1) & 1);  // P(j-1) V(j-1) has read the tile
       // K-major SWIZZLE_128B: 16-byte chunk c16 of row r lives at chunk (c16 ^ (r & 7))
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16)
