@@ -306,6 +306,108 @@ __global__ void __launch_bounds__(256) f32_groupnorm_kernel(const float* __restr
   }
 }
 
+// ---- coalesced two-kernel GroupNorm (the kernel above reads 40-80 byte channel runs three times: 1 TB/s) ----
+// Statistics: a CTA takes `rpc` pixel rows of one sample and reads them as whole rows (float4 per thread, fixed channels per
+// thread), sums x - shift and (x - shift)^2 per channel (shift = the sample's first value of the channel's group: the one-pass
+// variance then has nothing to cancel), folds them per group in a fixed order and writes one partial per (sample, group, chunk).
+// Apply: every CTA re-forms mean / rstd from the sample's partials (fixed order), then streams its rows once.
+constexpr int GN32_T = 256;
+__device__ __forceinline__ float gn32_shift(const float* a1, const float* a2, int C1, int C2, size_t pix0, int ch) {
+  return ch < C1 ? __ldg(a1 + pix0 * C1 + ch) : __ldg(a2 + pix0 * C2 + (ch - C1));
+}
+__global__ void __launch_bounds__(GN32_T) f32_gn_stats_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2,
+                                                              int HW, int groups, int rpc, int nch, float2* __restrict__ partial) {
+  __shared__ float ss[1024], sq[1024];
+  const int C = C1 + C2, cg = C / groups;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int r0 = chunk * rpc, r1 = min(r0 + rpc, HW);
+  const size_t pix0 = static_cast<size_t>(b) * HW;
+  for (int src = 0; src < 2; ++src) {
+    const int Cs = src ? C2 : C1, coff = src ? C1 : 0;
+    if (Cs == 0) continue;
+    const float* ap = src ? a2 : a1;
+    const int nv = Cs >> 2, R = GN32_T / nv;
+    const int v = threadIdx.x % nv, rl = threadIdx.x / nv;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
+    if (rl < R) {
+      float sh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sh[j] = gn32_shift(a1, a2, C1, C2, pix0, ((coff + 4 * v + j) / cg) * cg);
+      for (int p = r0 + rl; p < r1; p += R) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(ap + (pix0 + p) * Cs) + v);
+        const float d0 = x.x - sh[0], d1 = x.y - sh[1], d2 = x.z - sh[2], d3 = x.w - sh[3];
+        s4.x += d0; s4.y += d1; s4.z += d2; s4.w += d3;
+        q4.x = fmaf(d0, d0, q4.x); q4.y = fmaf(d1, d1, q4.y); q4.z = fmaf(d2, d2, q4.z); q4.w = fmaf(d3, d3, q4.w);
+      }
+      float* ps = ss + rl * Cs + 4 * v;
+      float* pq = sq + rl * Cs + 4 * v;
+      ps[0] = s4.x; ps[1] = s4.y; ps[2] = s4.z; ps[3] = s4.w;
+      pq[0] = q4.x; pq[1] = q4.y; pq[2] = q4.z; pq[3] = q4.w;
+    }
+    __syncthreads();
+    const int gl = threadIdx.x;
+    if (gl < Cs / cg) {
+      float S = 0.f, Q = 0.f;
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < cg; ++c) {
+          S += ss[r * Cs + gl * cg + c];
+          Q += sq[r * Cs + gl * cg + c];
+        }
+      partial[(static_cast<size_t>(b) * groups + coff / cg + gl) * nch + chunk] = make_float2(S, Q);
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(GN32_T) f32_gn_apply_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float* __restrict__ out, int HW, int groups, int rpc, int nch,
+                                                              const float2* __restrict__ partial, float eps, int silu) {
+  __shared__ float s_mean[128], s_rstd[128];
+  const int C = C1 + C2, cg = C / groups;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int r0 = chunk * rpc, r1 = min(r0 + rpc, HW);
+  const size_t pix0 = static_cast<size_t>(b) * HW;
+  if (static_cast<int>(threadIdx.x) < groups) {
+    const int g = threadIdx.x;
+    const float2* pg = partial + (static_cast<size_t>(b) * groups + g) * nch;
+    float S = 0.f, Q = 0.f;
+    for (int i = 0; i < nch; ++i) {
+      const float2 t = __ldg(pg + i);
+      S += t.x;
+      Q += t.y;
+    }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * static_cast<float>(cg));
+    const float ms = S * inv_n;  // mean - shift
+    const float var = fmaxf(fmaf(-ms, ms, Q * inv_n), 0.f);
+    s_mean[g] = gn32_shift(a1, a2, C1, C2, pix0, g * cg) + ms;
+    s_rstd[g] = 1.0f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int src = 0; src < 2; ++src) {
+    const int Cs = src ? C2 : C1, coff = src ? C1 : 0;
+    if (Cs == 0) continue;
+    const float* ap = src ? a2 : a1;
+    const int nv = Cs >> 2, R = GN32_T / nv;
+    const int v = threadIdx.x % nv, rl = threadIdx.x / nv;
+    if (rl >= R) continue;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = coff + 4 * v + j, g = c / cg;
+      sc[j] = s_rstd[g] * __ldg(gamma + c);
+      sh[j] = fmaf(-s_mean[g], sc[j], __ldg(beta + c));
+    }
+    for (int p = r0 + rl; p < r1; p += R) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(ap + (pix0 + p) * Cs) + v);
+      float4 y = make_float4(fmaf(x.x, sc[0], sh[0]), fmaf(x.y, sc[1], sh[1]), fmaf(x.z, sc[2], sh[2]), fmaf(x.w, sc[3], sh[3]));
+      if (silu) {
+        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+      }
+      reinterpret_cast<float4*>(out + (pix0 + p) * C + coff)[v] = y;
+    }
+  }
+}
+
 // nn.LayerNorm(C), eps 1e-5 (unet.py:314-316): one warp per token
 __global__ void __launch_bounds__(256) f32_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ out, int M,
@@ -824,6 +926,15 @@ Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int 
   return gemm(e, a, a2, B, w.p, static_cast<int>(w.shape[0]), P(e, pfx + ".bias").p, rowbias, rb_ld, residual, cs, nullptr, w.hi, w.lo);
 }
 
+static bool gn_fast_enabled() {  // env WD_F32_GN_FAST (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* x = getenv("WD_F32_GN_FAST");
+    v = x ? (atoi(x) != 0) : 1;
+  }
+  return v != 0;
+}
+
 Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, float eps, int silu) {
   Act o;
   o.H = a.H;
@@ -831,10 +942,23 @@ Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, in
   o.C = a.C + (a2 ? a2->C : 0);
   if (o.C % 32) fail(WD_ERR_UNSUPPORTED, "fp32 path: GroupNorm32 needs channels % 32 == 0");
   o.p = alloc(e, static_cast<size_t>(B) * a.H * a.W * o.C);
+  // coalesced statistics + apply kernels when every source holds whole groups and whole float4 vectors of at most 1024 channels
+  const int HW = a.H * a.W, C1 = a.C, C2 = a2 ? a2->C : 0, cg = o.C / 32;
+  const bool fast = gn_fast_enabled() && (C1 % 4) == 0 && (C2 % 4) == 0 && C1 % cg == 0 && C1 <= 1024 && C2 <= 1024;
+  const int rpc = HW <= 512 ? 32 : (HW + 15) / 16, nch = (HW + rpc - 1) / rpc;
+  float2* partial = fast ? reinterpret_cast<float2*>(alloc(e, static_cast<size_t>(B) * 32 * nch * 2)) : nullptr;
   if (!e->dry) {
-    f32_groupnorm_kernel<<<dim3(32, B), 256, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, a.C, a2 ? a2->C : 0, P(e, pfx + ".weight").p,
-                                                       P(e, pfx + ".bias").p, o.p, a.H * a.W, 32, eps, silu);
-    after_launch(e, "groupnorm");
+    const float* gm = P(e, pfx + ".weight").p;
+    const float* bt = P(e, pfx + ".bias").p;
+    if (fast) {
+      f32_gn_stats_kernel<<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, HW, 32, rpc, nch, partial);
+      after_launch(e, "groupnorm statistics");
+      f32_gn_apply_kernel<<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.p, HW, 32, rpc, nch, partial, eps, silu);
+      after_launch(e, "groupnorm apply");
+    } else {
+      f32_groupnorm_kernel<<<dim3(32, B), 256, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.p, HW, 32, eps, silu);
+      after_launch(e, "groupnorm");
+    }
   }
   return o;
 }
