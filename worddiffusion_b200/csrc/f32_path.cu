@@ -358,10 +358,17 @@ __global__ void __launch_bounds__(GN32_T) f32_gn_stats_kernel(const float* __res
     __syncthreads();
   }
 }
+// SPLIT: write the result as its TF32 split (hi = tf32_rn(y), lo = y - hi: the arithmetic of f32tc_split_kernel) into out / out_lo
+__device__ __forceinline__ float gn32_tf32_rn(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r & 0xFFFFE000u);
+}
+template <bool SPLIT>
 __global__ void __launch_bounds__(GN32_T) f32_gn_apply_kernel(const float* __restrict__ a1, const float* __restrict__ a2, int C1, int C2,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              float* __restrict__ out, int HW, int groups, int rpc, int nch,
-                                                              const float2* __restrict__ partial, float eps, int silu) {
+                                                              float* __restrict__ out, float* __restrict__ out_lo, int HW, int groups,
+                                                              int rpc, int nch, const float2* __restrict__ partial, float eps, int silu) {
   __shared__ float s_mean[128], s_rstd[128];
   const int C = C1 + C2, cg = C / groups;
   const int chunk = blockIdx.x, b = blockIdx.y;
@@ -403,7 +410,13 @@ __global__ void __launch_bounds__(GN32_T) f32_gn_apply_kernel(const float* __res
       if (silu) {
         y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
       }
-      reinterpret_cast<float4*>(out + (pix0 + p) * C + coff)[v] = y;
+      if constexpr (SPLIT) {
+        const float4 h = make_float4(gn32_tf32_rn(y.x), gn32_tf32_rn(y.y), gn32_tf32_rn(y.z), gn32_tf32_rn(y.w));
+        reinterpret_cast<float4*>(out + (pix0 + p) * C + coff)[v] = h;
+        reinterpret_cast<float4*>(out_lo + (pix0 + p) * C + coff)[v] = make_float4(y.x - h.x, y.y - h.y, y.z - h.z, y.w - h.w);
+      } else {
+        reinterpret_cast<float4*>(out + (pix0 + p) * C + coff)[v] = y;
+      }
     }
   }
 }
@@ -751,6 +764,10 @@ struct Param {
 struct Act {  // token-major activation
   float* p = nullptr;
   int H = 0, W = 0, C = 0;
+  // TF32 split of the tensor written by its producer (GroupNorm apply feeding a tensor-core convolution): when set, p is null
+  // and the consumer skips its own split pass
+  float* hi = nullptr;
+  float* lo = nullptr;
 };
 
 }  // namespace
@@ -856,13 +873,17 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
   if (w_hi && w_lo && wd::f32tc_enabled() && cs.taps == 9 && cs.stride == 1 && !cs.up && !cs.a_nchw && !cs.out_nchw &&
       wd::f32tc_conv_ok(B, a1.H, a1.W, g.C1, g.C2, N)) {
     const size_t n1 = static_cast<size_t>(g.M) * g.C1, n2 = static_cast<size_t>(g.M) * g.C2;
-    float* h1 = alloc(e, n1);
-    float* l1 = alloc(e, n1);
+    const bool presplit = a1.hi && a1.lo;  // written by the producer (GroupNorm apply)
+    float* h1 = presplit ? a1.hi : alloc(e, n1);
+    float* l1 = presplit ? a1.lo : alloc(e, n1);
     float* h2 = n2 ? alloc(e, n2) : nullptr;
     float* l2 = n2 ? alloc(e, n2) : nullptr;
     if (!e->dry) {
-      cudaError_t ce = wd::f32tc_split(a1.p, h1, l1, n1, e->s);
-      ++e->launches;
+      cudaError_t ce = cudaSuccess;
+      if (!presplit) {
+        ce = wd::f32tc_split(a1.p, h1, l1, n1, e->s);
+        ++e->launches;
+      }
       if (ce == cudaSuccess && n2) {
         ce = wd::f32tc_split(a2->p, h2, l2, n2, e->s);
         ++e->launches;
@@ -875,6 +896,7 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
     }
     return o;
   }
+  if (!a1.p) fail(WD_ERR_STATE, "fp32 path: a split-only activation reached a contraction that is not the implicit tensor-core conv");
   if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K)) {
     const size_t nA = static_cast<size_t>(g.M) * g.K;
     float* a_hi = alloc(e, nA);
@@ -935,25 +957,35 @@ static bool gn_fast_enabled() {  // env WD_F32_GN_FAST (default on)
   return v != 0;
 }
 
-Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, float eps, int silu) {
+Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, float eps, int silu, bool split_out = false) {
   Act o;
   o.H = a.H;
   o.W = a.W;
   o.C = a.C + (a2 ? a2->C : 0);
   if (o.C % 32) fail(WD_ERR_UNSUPPORTED, "fp32 path: GroupNorm32 needs channels % 32 == 0");
-  o.p = alloc(e, static_cast<size_t>(B) * a.H * a.W * o.C);
   // coalesced statistics + apply kernels when every source holds whole groups and whole float4 vectors of at most 1024 channels
   const int HW = a.H * a.W, C1 = a.C, C2 = a2 ? a2->C : 0, cg = o.C / 32;
   const bool fast = gn_fast_enabled() && (C1 % 4) == 0 && (C2 % 4) == 0 && C1 % cg == 0 && C1 <= 1024 && C2 <= 1024;
   const int rpc = HW <= 512 ? 32 : (HW + 15) / 16, nch = (HW + rpc - 1) / rpc;
   float2* partial = fast ? reinterpret_cast<float2*>(alloc(e, static_cast<size_t>(B) * 32 * nch * 2)) : nullptr;
+  const size_t n_out = static_cast<size_t>(B) * HW * o.C;
+  const bool split = fast && split_out;  // the consumer is a tensor-core convolution: hand it the TF32 split, nothing else reads it
+  if (split) {
+    o.hi = alloc(e, n_out);
+    o.lo = alloc(e, n_out);
+  } else {
+    o.p = alloc(e, n_out);
+  }
   if (!e->dry) {
     const float* gm = P(e, pfx + ".weight").p;
     const float* bt = P(e, pfx + ".bias").p;
     if (fast) {
       f32_gn_stats_kernel<<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, HW, 32, rpc, nch, partial);
       after_launch(e, "groupnorm statistics");
-      f32_gn_apply_kernel<<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.p, HW, 32, rpc, nch, partial, eps, silu);
+      if (split)
+        f32_gn_apply_kernel<true><<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.hi, o.lo, HW, 32, rpc, nch, partial, eps, silu);
+      else
+        f32_gn_apply_kernel<false><<<dim3(nch, B), GN32_T, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.p, nullptr, HW, 32, rpc, nch, partial, eps, silu);
       after_launch(e, "groupnorm apply");
     } else {
       f32_groupnorm_kernel<<<dim3(32, B), 256, 0, e->s>>>(a.p, a2 ? a2->p : nullptr, C1, C2, gm, bt, o.p, HW, 32, eps, silu);
@@ -1064,12 +1096,19 @@ Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, 
   return linear(e, pfx + "proj_out", t, B, true, x.p);
 }
 
+// will conv3x3(pfx) over a single [B, H, W, C] source run as the implicit tensor-core convolution (the route of gemm() that
+// consumes a pre-split source)?  Same predicate as gemm().
+bool conv_takes_split(wd_f32* e, const std::string& pfx, int H, int W, int C, int B) {
+  const Param& w = P(e, pfx + ".weight");
+  return w.packed3x3 && w.hi && w.lo && wd::f32tc_enabled() && wd::f32tc_conv_ok(B, H, W, C, 0, static_cast<int>(w.shape[0]));
+}
+
 // ResBlock._forward (unet.py:646-671), input = channel concat of a (and a2)
 Act res_block(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, const Act& semb) {
-  Act g1 = groupnorm(e, pfx + "in_layers.0", a, a2, B, 1e-5f, 1);
+  Act g1 = groupnorm(e, pfx + "in_layers.0", a, a2, B, 1e-5f, 1, conv_takes_split(e, pfx + "in_layers.2", a.H, a.W, a.C + (a2 ? a2->C : 0), B));
   Act eo = linear(e, pfx + "emb_layers.1", semb, B, true);
   Act h1 = conv3x3(e, pfx + "in_layers.2", g1, nullptr, B, eo.p, eo.C, nullptr, 1, 0);
-  Act g2 = groupnorm(e, pfx + "out_layers.0", h1, nullptr, B, 1e-5f, 1);
+  Act g2 = groupnorm(e, pfx + "out_layers.0", h1, nullptr, B, 1e-5f, 1, conv_takes_split(e, pfx + "out_layers.3", h1.H, h1.W, h1.C, B));
   const float* skip;
   if (has(e, pfx + "skip_connection.weight")) {
     skip = linear(e, pfx + "skip_connection", a, B, true, nullptr, 0, a2).p;
