@@ -189,6 +189,21 @@ def test_phosc_batch_invariance_at_benchmark_batches(phosc, B):
     assert torch.equal(e_big[idx], e_small)
 
 
+@pytest.mark.parametrize("B,latent", [(3, (4, 8, 16)), (1, (4, 8, 32)), (5, (4, 8, 32))])
+def test_forward_vs_oracle_other_latent_sizes(B, latent, unet):
+    """train.Diffusion's default img_size (64, 128) gives 8 x 16 latents (train.py:175): the engine plans per latent size; the
+    one-kernel output head (GroupNorm + conv_out + sampler update over a shared-memory image of the sample) and the producer-
+    side GroupNorm of the ResBlocks run at 128-pixel samples, ragged batches and a single latent."""
+    m, sd = unet
+    inp = W.make_inputs(B, seed=641, latent=latent)
+    ci = _cuda(inp)
+    with torch.no_grad():
+        eps = m(ci["x"], None, timesteps=ci["t"], context=ci["context"], y=ci["y"])
+    ref = UO.unet_forward(sd, inp["x"], inp["t"], inp["context"], inp["y"], variant="unet")
+    assert eps.shape == ref.shape
+    assert relerr(eps, ref) < TOL_BF16
+
+
 @pytest.mark.parametrize("variant,B", [("unetPhosc", 64), ("unet", 64)])
 def test_forward_vs_oracle_at_batch_64(variant, B, unet, phosc):
     """eps vs the CPU oracle at a batch where every kernel runs multi-wave grids (the golden fixtures are B = 2)."""

@@ -150,7 +150,7 @@ struct Slot {
 // launch plan
 // ----------------------------------------------------------------------------------------------
 enum OpKind { OP_TEMB, OP_GEMM, OP_GN, OP_LN, OP_ATTN_SMALL, OP_ATTN_FLASH, OP_CONV_IN, OP_GNSTATS, OP_UPSAMPLE,
-              OP_EMBED, OP_LINF32, OP_WORDATTN, OP_EMBTBL, OP_TBLOCK, OP_TB_CVEC };
+              OP_EMBED, OP_LINF32, OP_WORDATTN, OP_EMBTBL, OP_TBLOCK, OP_TB_CVEC, OP_OUTHEAD };
 // step ops that exist in two flavours: the time-embedding MLP per step (per-row timesteps: wd_unet_eval) or the lookup in
 // the per-trajectory table (one timestep for the whole batch: wd_sampler_step)
 enum OpCond { COND_ALWAYS = 0, COND_NO_TABLE = 1, COND_TABLE = 2 };
@@ -178,6 +178,7 @@ struct Op {
   struct { const float* q; const float* k; const float* v; bf16* ctx; int B, L, D, Ltot, row_off; } wa;
   TBlockLaunch tb;
   struct { const bf16* ctx; const float* u; float* out; int rows, heads; } cv;
+  OutHeadArgs oh;  // per-call fields (x, eps_out, noise, sampler scalars) are patched in like P_SAMPLER
 };
 
 struct Plan {
@@ -896,6 +897,15 @@ struct Epi {
   int att_ld = 0, att_voff = 0, att_L = 0;
   float att_scale = 0.f;
 };
+
+static bool out_head_enabled() {  // env WD_OUT_HEAD (default on): out GroupNorm + conv_out + sampler update as one kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_OUT_HEAD");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 
 // env WD_GN_PRODUCER: GroupNorm of a ResBlock's h applied by conv1's epilogue.  0: never; 1: only when the conv has more
 // 256-row tiles than the GPU has CTA pairs, so that all but the last tile's epilogue runs under the next tile's MMAs;
@@ -1699,7 +1709,30 @@ struct PlanBuilder {
       if (skip.H != h.H || skip.W != h.W) { err = "skip connection spatial mismatch"; return false; }
       if (!run_block(blk, {h, skip})) return false;
     }
-    // out: GN + SiLU, then conv_out fused with the sampler update
+    // out: GN + SiLU + conv_out + sampler update as ONE kernel with the sample's image in shared memory (ops.cuh: OutHeadArgs)
+    if (out_head_enabled() && h.f16 && h.pslots > 0 && h.C % 32 == 0 && c.out_channels == 4 && out_head_supported(h.H, h.W, h.C)) {
+      Op op;
+      memset(&op, 0, sizeof(op));
+      op.kind = OP_OUTHEAD;
+      op.oh.h = reinterpret_cast<const __half*>(h.p);
+      op.oh.partial = h.stats;
+      op.oh.pslots = h.pslots;
+      op.oh.gamma = e->out_gn.g;
+      op.oh.beta = e->out_gn.b;
+      op.oh.gn_eps = 1e-5f;
+      op.oh.w = e->conv_out.w;
+      op.oh.bias = e->conv_out.bias;
+      op.oh.B = B;
+      op.oh.H = h.H;
+      op.oh.W = h.W;
+      op.oh.C = h.C;
+      op.bytes = static_cast<double>(B) * h.H * h.W * (2.0 * h.C + 4.0 * c.out_channels * 4);  // h read; x in/out, noise, eps
+      op.flops = 2.0 * B * h.H * h.W * h.C * 9 * c.out_channels;
+      sops.push_back(op);
+      plan->bytes = A.used;
+      return true;
+    }
+    // fallback: GN + SiLU kernel, then conv_out on the tensor cores fused with the sampler update
     Act a;
     if (!gn_op(sops, {h}, e->out_gn, 1e-5f, 1, a)) return false;
     {
@@ -1897,6 +1930,21 @@ int run_ops(wd_engine* e, const std::vector<Op>& ops, const RunCtx& rc, cudaStre
       case OP_TB_CVEC:
         err = tblock_cvec_launch(op.cv.ctx, op.cv.u, op.cv.out, op.cv.rows, op.cv.heads, s);
         break;
+      case OP_OUTHEAD: {
+        OutHeadArgs oa = op.oh;
+        oa.eps_out = rc.eps_out;
+        oa.x = rc.x_rw;
+        oa.noise = rc.noise;
+        oa.use_philox = rc.use_philox;
+        oa.seed = rc.seed;
+        oa.sample_offset = rc.sample_offset;
+        oa.step_index = rc.step_index;
+        oa.coef = rc.coef;
+        oa.mode = rc.mode;
+        oa.sp = rc.sp;
+        err = out_head_launch(oa, s);
+        break;
+      }
       case OP_LINF32:
         err = linear_f32_launch(op.lin.x, op.lin.W, op.lin.b, op.lin.out, op.lin.M, op.lin.N, op.lin.K, s);
         break;
@@ -2148,7 +2196,7 @@ extern "C" int wd_engine_profile_read(wd_engine* e, int cap, int* kinds, double*
     // the table lookup reports as the timestep-embedding class; ops of the flavour the profiled steps skipped carry no work
     const bool skipped = (ops[i].cond == COND_TABLE && !e->prof_used_table) || (ops[i].cond == COND_NO_TABLE && e->prof_used_table);
     // indices into engine.py's OP_KINDS: 0 .. 8 = OP_TEMB .. OP_UPSAMPLE, 9 = the fused transformer block
-    kinds[i] = ops[i].kind == OP_EMBTBL ? static_cast<int>(OP_TEMB) : (ops[i].kind == OP_TBLOCK ? 9 : static_cast<int>(ops[i].kind));
+    kinds[i] = ops[i].kind == OP_EMBTBL ? static_cast<int>(OP_TEMB) : (ops[i].kind == OP_TBLOCK ? 9 : (ops[i].kind == OP_OUTHEAD ? 10 : static_cast<int>(ops[i].kind)));
     flops[i] = skipped ? 0.0 : ops[i].flops;
     bytes[i] = skipped ? 0.0 : ops[i].bytes;
     ms_sum[i] = 0.f;

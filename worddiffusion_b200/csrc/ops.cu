@@ -921,6 +921,231 @@ cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B,
 }
 
 // =====================================================================================================
+// output head: GroupNorm32 + SiLU + conv3x3 (C -> 4) + sampler update, one CTA per sample (ops.cuh: OutHeadArgs)
+// =====================================================================================================
+constexpr int OH_THREADS = 256;
+constexpr int OH_WROWS = 8;  // weight rows used: 4 hi + 4 lo
+WD_DEVINL void oh_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+static size_t out_head_smem_bytes(int H, int W, int C) {
+  const size_t pitch = static_cast<size_t>(C) * 2 + 16;           // bytes per pixel row (+16: ldmatrix rows land in distinct banks)
+  const size_t wpitch = (static_cast<size_t>(9) * C + 8) * 2;     // bytes per weight row (+16)
+  return (static_cast<size_t>(H) * W + 1) * pitch + OH_WROWS * wpitch + static_cast<size_t>(C) * 8 + 256 + 64;  // tables, statistics, 2 mbarriers
+}
+bool out_head_supported(int H, int W, int C) {
+  return H >= 1 && W >= 1 && (H * W) % 16 == 0 && C % 32 == 0 && C % 16 == 0 && (C / 32) % 2 == 0 && C <= 1024 &&
+         out_head_smem_bytes(H, W, C) <= 227 * 1024;
+}
+
+__global__ void __launch_bounds__(OH_THREADS, 1) out_head_kernel(const OutHeadArgs a) {
+  extern __shared__ __align__(128) uint8_t oh_smem[];
+  const int HW = a.H * a.W, C = a.C, cpg = C / 32;
+  const int pitch = C * 2 + 16, wpitch = (9 * C + 8) * 2;
+  uint8_t* s_act = oh_smem;                                  // [HW + 1][pitch]: row HW is the zero (padding) row
+  uint8_t* s_w = s_act + static_cast<size_t>(HW + 1) * pitch;  // [8][wpitch]
+  float* s_sc = reinterpret_cast<float*>(s_w + OH_WROWS * wpitch);  // [C] scale / 2, then [C] shift / 2
+  float* s_sh = s_sc + C;
+  float* s_mean = s_sh + C;  // [32], [32]: the 256 spare bytes of out_head_smem_bytes (no static shared memory: the dynamic
+  float* s_rstd = s_mean + 32;  // allocation may then use the whole 227 KB)
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nv = C >> 3;  // 16-byte vectors per pixel row
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rstd + 32);  // [3]: weights landed, first / second half of the image landed
+  // ---- everything arrives by bulk copies (one per weight row / pixel row, straight into the padded rows): 210 KB in flight
+  // per SM instead of a few dependent 16-byte loads per thread ----
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2, wrow_bytes = static_cast<uint32_t>(9 * C) * 2;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < pitch / 16; i += OH_THREADS) *reinterpret_cast<uint4*>(s_act + static_cast<size_t>(HW) * pitch + i * 16) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (warp == 0) {  // the weights do not depend on the previous kernel
+    if (lane == 0) mbar_arrive_expect_tx(&bars[0], OH_WROWS * wrow_bytes);
+    __syncwarp();
+    if (lane < OH_WROWS) bulk_load_1d(s_w + lane * wpitch, a.w + static_cast<size_t>(lane) * 9 * C, wrow_bytes, &bars[0]);
+  }
+  pdl_trigger();
+  pdl_wait();  // h and its statistics come from the previous kernel
+  if (warp == 0) {
+    const int half_rows = HW / 2;  // HW % 16 == 0
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[1], static_cast<uint32_t>(half_rows) * row_bytes);
+      mbar_arrive_expect_tx(&bars[2], static_cast<uint32_t>(HW - half_rows) * row_bytes);
+    }
+    __syncwarp();
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.h + static_cast<size_t>(b) * HW * C);
+    for (int p = lane; p < HW; p += 32)
+      bulk_load_1d(s_act + static_cast<size_t>(p) * pitch, src + static_cast<size_t>(p) * row_bytes, row_bytes, &bars[p < half_rows ? 1 : 2]);
+  }
+  // ---- statistics of this sample (the arithmetic of groupnorm_apply_bulk_kernel) -> scale / shift tables ----
+  if (tid >= 32 && tid < 64) {
+    const int g = tid - 32;
+    const float2* part = reinterpret_cast<const float2*>(a.partial) + (static_cast<size_t>(b) * 32 + g) * a.pslots;
+    float S = 0.f, Q = 0.f;
+    for (int i = 0; i < a.pslots; ++i) {
+      const float2 t = __ldg(part + i);
+      S += t.x;
+      Q += t.y;
+    }
+    const float inv_n = 1.0f / static_cast<float>(cpg * HW);
+    const float mean = S * inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, Q * inv_n), 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + a.gn_eps);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += OH_THREADS) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(a.gamma + c);
+    const float sh = fmaf(-s_mean[g], sc, __ldg(a.beta + c));
+    s_sc[c] = 0.5f * sc;
+    s_sh[c] = 0.5f * sh;
+  }
+  __syncthreads();
+  // ---- h -> silu(GroupNorm(h)) as bf16, in place in the shared-memory image: a thread keeps ONE 8-channel column (its scale /
+  // shift pairs stay in registers) and walks the rows; the first half is normalised while the second is still landing ----
+  {
+    const int rows_par = OH_THREADS / nv;  // rows in flight (threads beyond rows_par * nv idle: 16 of 256 at C = 320)
+    const int col = tid % nv, r0 = tid / nv;
+    if (r0 < rows_par) {
+      const float4 c0 = *reinterpret_cast<const float4*>(s_sc + col * 8), c1 = *reinterpret_cast<const float4*>(s_sc + col * 8 + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(s_sh + col * 8), h1 = *reinterpret_cast<const float4*>(s_sh + col * 8 + 4);
+      const float2 sc2[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+      const float2 sh2[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
+      const int half_rows = HW / 2;
+      mbar_wait(&bars[1], 0);
+      int p = r0;
+      for (; p < half_rows; p += rows_par) {
+        uint4* sp = reinterpret_cast<uint4*>(s_act + static_cast<size_t>(p) * pitch + col * 16);
+        *sp = gn_vec8<true, true>(*sp, sc2, sh2);
+      }
+      mbar_wait(&bars[2], 0);
+      for (; p < HW; p += rows_par) {
+        uint4* sp = reinterpret_cast<uint4*>(s_act + static_cast<size_t>(p) * pitch + col * 16);
+        *sp = gn_vec8<true, true>(*sp, sc2, sh2);
+      }
+    }
+  }
+  mbar_wait(&bars[0], 0);
+  __syncthreads();
+
+  // ---- 3 x 3 convolution on mma.sync: M = pixels (16 per tile), N = 8 weight rows, K = 9 C ----
+  const float4 coef = a.sp ? a.sp->coef : a.coef;
+  const int mode = a.sp ? a.sp->mode : a.mode;
+  const int use_philox = a.sp ? a.sp->use_philox : a.use_philox;
+  const unsigned long long seed = a.sp ? a.sp->seed : a.seed;
+  const unsigned long long sample_offset = a.sp ? a.sp->sample_offset : a.sample_offset;
+  const int step_index = a.sp ? a.sp->step_index : a.step_index;
+  const int g = lane >> 2, tq = lane & 3;
+  const int ntile = HW / 16;
+  const uint32_t act_base = smem_u32(s_act);
+  const int ksteps = C / 16;
+  for (int t0 = warp * 2; t0 < ntile; t0 += 2 * (OH_THREADS / 32)) {
+    const bool two = t0 + 1 < ntile;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc0b[4] = {0.f, 0.f, 0.f, 0.f}, acc1b[4] = {0.f, 0.f, 0.f, 0.f};  // odd k steps: four independent HMMA chains per warp
+    // this lane's ldmatrix row: pixel (tile * 16 + r), 8-column half kh
+    const int r = (lane & 7) + ((lane >> 3) & 1) * 8, kh = lane >> 4;
+    const int p0 = t0 * 16 + r, p1 = (two ? t0 + 1 : t0) * 16 + r;
+    const int y0 = p0 / a.W, x0 = p0 - y0 * a.W, y1 = p1 / a.W, x1 = p1 - y1 * a.W;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const int sy0 = y0 + dy, sx0 = x0 + dx, sy1 = y1 + dy, sx1 = x1 + dx;
+      const int q0 = (sy0 >= 0 && sy0 < a.H && sx0 >= 0 && sx0 < a.W) ? sy0 * a.W + sx0 : HW;  // HW = the zero row
+      const int q1 = (sy1 >= 0 && sy1 < a.H && sx1 >= 0 && sx1 < a.W) ? sy1 * a.W + sx1 : HW;
+      const uint32_t ra0 = act_base + static_cast<uint32_t>(q0) * pitch + kh * 16;
+      const uint32_t ra1 = act_base + static_cast<uint32_t>(q1) * pitch + kh * 16;
+      const uint8_t* wrow = s_w + g * wpitch + (static_cast<size_t>(tap) * C + 2 * tq) * 2;
+#pragma unroll 4
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + ks * 32);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + ks * 32 + 16);
+        uint32_t f0[4], f1[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(f0[0]), "=r"(f0[1]), "=r"(f0[2]), "=r"(f0[3])
+                     : "r"(ra0 + ks * 32));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(f1[0]), "=r"(f1[1]), "=r"(f1[2]), "=r"(f1[3])
+                     : "r"(ra1 + ks * 32));
+        if (ks & 1) {
+          oh_mma_16816(acc0b, f0, b0, b1);
+          oh_mma_16816(acc1b, f1, b0, b1);
+        } else {
+          oh_mma_16816(acc0, f0, b0, b1);
+          oh_mma_16816(acc1, f1, b0, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc0[i] += acc0b[i];
+      acc1[i] += acc1b[i];
+    }
+    // ---- epilogue: eps = (hi + lo) + bias, sampler update (the arithmetic of gemm_tc.cu's EPI_SAMPLER, bit for bit) ----
+    // columns 2 tq, 2 tq + 1 of rows g, g + 8; the lo part of output channel o sits in column 4 + o = lane + 2's column o
+    float lo0[4], lo1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      lo0[i] = __shfl_down_sync(0xffffffffu, acc0[i], 2);
+      lo1[i] = __shfl_down_sync(0xffffffffu, acc1[i], 2);
+    }
+    if (tq < 2) {
+      const int nel = two ? 8 : 4;
+      size_t idx[8];
+      float eps[8], xv[8], z[8];
+      // all loads first (x / noise may not be reordered across the eps_out stores by the compiler: every load would wait ~1 us)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int tt = e >> 2, i = e & 3;
+        const int o = 2 * tq + (i & 1);
+        const int pix = (t0 + tt) * 16 + g + (i >> 1) * 8;
+        idx[e] = (static_cast<size_t>(b) * 4 + o) * HW + pix;
+        eps[e] = ((tt ? acc1[i] : acc0[i]) + (tt ? lo1[i] : lo0[i])) + __ldg(a.bias + o);
+        xv[e] = 0.f;
+        z[e] = 0.f;
+        if (e < nel && mode != STEP_EPS_ONLY) {
+          xv[e] = a.x[idx[e]];
+          if (mode == STEP_DDPM && a.noise) z[e] = __ldg(a.noise + idx[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (e >= nel) break;
+        if (a.eps_out) a.eps_out[idx[e]] = eps[e];
+        if (mode == STEP_DDPM) {
+          float zz = z[e];
+          if (!a.noise && use_philox) zz = philox_normal(seed, sample_offset * (4ull * HW) + idx[e], static_cast<uint32_t>(step_index));
+          const float inner = __fsub_rn(xv[e], __fmul_rn(coef.y, eps[e]));
+          a.x[idx[e]] = __fadd_rn(__fmul_rn(coef.x, inner), __fmul_rn(coef.z, zz));
+        } else if (mode == STEP_DDIM) {
+          const float x0v = __fmul_rn(__fsub_rn(xv[e], __fmul_rn(coef.y, eps[e])), coef.x);
+          a.x[idx[e]] = __fadd_rn(__fmul_rn(coef.z, x0v), __fmul_rn(coef.w, eps[e]));
+        }
+      }
+    }
+  }
+}
+
+cudaError_t out_head_launch(const OutHeadArgs& a, cudaStream_t s) {
+  if (!out_head_supported(a.H, a.W, a.C) || a.B < 1 || a.pslots < 1 || !a.h || !a.partial || !a.w || !a.bias) return cudaErrorInvalidValue;
+  const size_t smem = out_head_smem_bytes(a.H, a.W, a.C);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(out_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (attr_err != cudaSuccess) return attr_err;
+  return launch_pdl(out_head_kernel, dim3(a.B), dim3(OH_THREADS), smem, s, a);
+}
+
+// =====================================================================================================
 // weight repacking
 // =====================================================================================================
 WD_DEVINL int geglu_perm(int n, int N, int bn) {

@@ -107,6 +107,37 @@ cudaError_t timestep_embed_launch(const long long* t_dev, long long t_scalar, __
 // columns j = c*9+ky*3+kx: x_hi, 36 + j: x_lo (x - x_hi), 72 + j: x_hi again (pairs with w_lo), 108..127: zero
 cudaError_t conv_in_im2col_launch(const float* x, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
 
+// ---------------- output head in one kernel: GroupNorm32 + SiLU + conv3x3 C -> 4 + sampler update ----------------
+// (unet.py:1454-1458,1815 then train.py:229-236).  One CTA per sample: the raw fp16 tensor is read ONCE, normalised into a
+// shared-memory image (bf16, one padded row per pixel + a zero row that plays the conv's padding), the 3 x 3 x C x 8 contraction
+// (4 output channels as bf16 hi + lo weight rows) runs on mma.sync from that image, and the epilogue applies the DDPM / DDIM
+// update exactly like the tcgen05 output conv's sampler epilogue.  Replaces a GroupNorm launch (write + re-read of the
+// normalised tensor) and an N = 16 tcgen05 launch that fetched every activation nine times through L2.
+struct OutHeadArgs {
+  const __half* h;        // [B, HW, C] fp16 (residual stream)
+  const float* partial;   // GroupNorm partial statistics of h: [B][32][pslots][2]
+  int pslots;
+  const float* gamma;
+  const float* beta;
+  float gn_eps;
+  const __nv_bfloat16* w;  // [>= 8][9 C]: rows 0..3 = hi part of out.2.weight (k = tap C + c), rows 4..7 = lo part
+  const float* bias;       // [4]
+  int B, H, W, C;
+  // sampler (same meaning as GemmArgs)
+  float* eps_out;
+  float* x;
+  const float* noise;
+  int use_philox;
+  unsigned long long seed;
+  unsigned long long sample_offset;
+  int step_index;
+  float4 coef;
+  int mode;
+  const StepParams* sp;
+};
+bool out_head_supported(int H, int W, int C);  // shared-memory image fits, whole 16-pixel tiles, whole groups of C / 32 channels
+cudaError_t out_head_launch(const OutHeadArgs& a, cudaStream_t s);
+
 // ---------------- nearest 2x upsample NHWC bf16 (unet.py:497) ----------------
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
 

@@ -183,7 +183,7 @@ class HotPathEngine:
         return x
 
     OP_KINDS = ("timestep_embed", "gemm_tc", "groupnorm", "layernorm", "attn_small", "attn_flash", "conv_in",
-                "groupnorm_stats", "upsample", "tblock")
+                "groupnorm_stats", "upsample", "tblock", "out_head")
 
     def set_profiling(self, on):
         check(lib().wd_engine_set_profiling(self._h, 1 if on else 0), "wd_engine_set_profiling")
