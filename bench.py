@@ -428,7 +428,10 @@ def vae_leg(dev, W, batch=64):
     vae.load_state_dict(W.make_state_dict(spec, seed=77))
     vae.to(dev)
     z = torch.randn(batch, 4, 8, 32, device=dev)
-    vae.decode(z[:8], scale=1 / 0.18215, postprocess=True)  # builds the engine, sizes the arena
+    # builds the engine and sizes the arena for this batch (a smaller warm-up batch left the arena growth -- a multi-GB
+    # cudaFree + cudaMalloc whose cost depends on what the earlier legs left allocated: 87 ms one run, 480 ms another -- inside
+    # the timed call)
+    vae.decode(z, scale=1 / 0.18215, postprocess=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
