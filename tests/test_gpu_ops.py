@@ -84,7 +84,7 @@ def test_gemm_geglu():
 
 
 @pytest.mark.parametrize("B,H,W,Cin,stride", [(2, 8, 32, 320, 1), (3, 4, 16, 320, 1), (4, 4, 16, 640, 1), (2, 8, 32, 320, 2),
-                                              (1, 8, 32, 64, 1), (5, 4, 16, 320, 1)])
+                                              (1, 8, 32, 64, 1), (5, 4, 16, 320, 1), (90, 8, 32, 320, 1), (90, 8, 32, 640, 1)])
 def test_conv3x3(B, H, W, Cin, stride):
     """Implicit-GEMM 3x3 conv (pad 1): TMA zero-fill is the padding; stride 2 is the Downsample op (unet.py:540-551)."""
     Cout = 320
@@ -102,7 +102,7 @@ def test_conv3x3(B, H, W, Cin, stride):
 
 
 @pytest.mark.parametrize("B,H,W,Cin", [(2, 8, 32, 320), (3, 4, 16, 320), (4, 4, 16, 640), (5, 4, 16, 320), (1, 8, 32, 640),
-                                       (148, 8, 32, 640), (2, 4, 8, 320)])
+                                       (148, 8, 32, 640), (2, 4, 8, 320), (90, 8, 32, 640), (95, 8, 32, 320)])
 def test_conv3x3_groupnorm_silu_in_the_producer(B, H, W, Cin):
     """ResBlock front half (unet.py:657-667 then :592-594): conv3x3 + bias + emb row bias -> GroupNorm32 -> SiLU with the
     normalisation applied by the conv kernel's epilogue (CTA-pair kernel: the 256-row tile holds whole samples).  Covers one
@@ -127,8 +127,10 @@ def test_conv3x3_groupnorm_silu_in_the_producer(B, H, W, Cin):
     assert relerr(o.float().reshape(B, H * W, Cout), two.float()) < 3 * BF16_STORE
 
 
-def test_conv3x3_residual():
-    B, H, W, C = 2, 8, 32, 320
+@pytest.mark.parametrize("B", [2, 90])
+def test_conv3x3_residual(B):
+    """B = 90: 90 pair tiles on 74 CTA pairs -> the 16 tiles of the last round are cut into 160-column halves (tail split)."""
+    H, W, C = 8, 32, 320
     x = bf(torch.randn(B, H, W, C, generator=g(14)))
     w = torch.randn(C, C, 3, 3, generator=g(15)) / math.sqrt(9 * C)
     bias = f32(torch.zeros(C))

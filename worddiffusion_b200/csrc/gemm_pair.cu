@@ -42,6 +42,34 @@ static_assert(PAIR_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 }  // namespace
 
+// Tile schedule of one CTA pair.  Full rounds hand out whole 256 x 320 tiles (tile = pair + it * pairs).  A last, partial round
+// (rem < pairs tiles) would leave most pairs idle for a whole tile time -- 256 tiles on 74 pairs = 3.46 waves, 13.5 % of the launch --
+// so when 2 * rem <= pairs each tail tile is cut into its two 160-column halves and handed to two neighbouring pairs: the same A rows
+// (shared through L2), half of the weights, half of the MMAs; load-bound at ~0.6 of a whole tile's time, no cross-CTA exchange.
+// nmask: bit h set = this pair computes columns [160 h, 160 h + 160) of the tile.
+struct PairSched {
+  int P, R, rem;
+  bool split;
+};
+WD_DEVINL bool pair_sched(const PairSched& s, int pair, int it, int* tile, int* nmask) {
+  if (it < s.R) {
+    *tile = pair + it * s.P;
+    *nmask = 3;
+    return true;
+  }
+  if (it > s.R) return false;
+  if (s.split) {
+    if (pair >= 2 * s.rem) return false;
+    *tile = s.R * s.P + (pair >> 1);
+    *nmask = 1 << (pair & 1);
+    return true;
+  }
+  if (pair >= s.rem) return false;
+  *tile = s.R * s.P + pair;
+  *nmask = 3;
+  return true;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -69,6 +97,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int total_tiles = n_tiles * m_tiles;
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
+  PairSched sched;
+  sched.P = npairs;
+  sched.R = total_tiles / npairs;
+  sched.rem = total_tiles % npairs;
+  sched.split = args.tail_split && n_tiles == 1 && sched.rem > 0 && 2 * sched.rem <= npairs;
 
   int total_k = 0;
 #pragma unroll
@@ -110,7 +143,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
+      int tile, nmask;
+      for (int pit = 0; pair_sched(sched, pair, pit, &tile, &nmask); ++pit) {
         const int m0 = (tile / n_tiles) * (2 * GEMM_BLOCK_M) + static_cast<int>(rank) * GEMM_BLOCK_M;  // this CTA's rows
         const int n0 = (tile % n_tiles) * PAIR_BN;
         int img = 0, oh0 = 0;
@@ -130,8 +164,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's full barrier
+              const int nb_boxes = nmask == 3 ? 2 : 1;  // weight boxes per CTA: one per 160-column half this pair computes
               if (is_leader)
-                mbar_arrive_expect_tx(&full_bar[stage], 2 * (((args.dbg & 8) ? 0 : PAIR_A_BYTES) + ((args.dbg & 4) ? 0 : 2 * PAIR_BH_BYTES)));
+                mbar_arrive_expect_tx(&full_bar[stage], 2 * (((args.dbg & 8) ? 0 : PAIR_A_BYTES) + ((args.dbg & 4) ? 0 : nb_boxes * PAIR_BH_BYTES)));
               uint8_t* sA = smem + stage * PAIR_STAGE_BYTES;
               uint8_t* sB = sA + PAIR_A_BYTES;
               if (!(args.dbg & 8)) {
@@ -142,8 +177,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               }
               // weight rows of MMA j (columns n0 + 160 j ..): this CTA supplies rows [80 rank, +80) of them
               if (!(args.dbg & 4)) {
-                tma_load_2d_pair(sB, &mapB, fb, kb * GEMM_BLOCK_K, n0 + static_cast<int>(rank) * 80);
-                tma_load_2d_pair(sB + PAIR_BH_BYTES, &mapB, fb, kb * GEMM_BLOCK_K, n0 + 160 + static_cast<int>(rank) * 80);
+                if (nmask & 1) tma_load_2d_pair(sB, &mapB, fb, kb * GEMM_BLOCK_K, n0 + static_cast<int>(rank) * 80);
+                if (nmask & 2) tma_load_2d_pair(sB + PAIR_BH_BYTES, &mapB, fb, kb * GEMM_BLOCK_K, n0 + 160 + static_cast<int>(rank) * 80);
               }
               ++kb;
               if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
@@ -169,7 +204,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      int tile, nmask;
+      for (; pair_sched(sched, pair, it, &tile, &nmask); ++it) {
         // both CTAs' epilogues have drained the accumulator.  CTA-scope acquire / release on both sides (mbar_arrive_remote): the
         // cluster-scope forms put a MEMBAR.ALL.GPU in front of every epilogue warp's arrival (-2 % on the GEMM class, R2f)
         mbar_wait(tmem_empty_bar, (it & 1) ^ 1);
@@ -186,8 +222,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (!(args.dbg & 16)) {
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-              umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc0 + 2 * k, idesc, (kb | k) != 0);
-              umma_f16_ss_pair(tmem_base + 160, a_desc + 2 * k, b_desc1 + 2 * k, idesc, (kb | k) != 0);
+              if (nmask & 1) umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc0 + 2 * k, idesc, (kb | k) != 0);
+              if (nmask & 2) umma_f16_ss_pair(tmem_base + 160, a_desc + 2 * k, b_desc1 + 2 * k, idesc, (kb | k) != 0);
             }
           }
           umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs when these MMAs retire
@@ -224,12 +260,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       tma_load_2d(stg_half, &mapRes, &res_full_bar[half], c0_, m0_);
       tma_load_2d(stg_half + PAIR_SUB_BYTES, &mapRes, &res_full_bar[half], c0_ + GEMM_SUB_N, m0_);
     };
-    if (has_res && leader_warp && pair < total_tiles) {
-      if (elect_one()) issue_res_load(pair, 0);
+    {
+      int t0_, nm0_;
+      if (has_res && leader_warp && pair_sched(sched, pair, 0, &t0_, &nm0_) && ((nm0_ >> half) & 1)) {
+        if (elect_one()) issue_res_load(t0_, 0);
+      }
     }
 
     int it = 0;
-    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+    int tile, nmask;
+    for (; pair_sched(sched, pair, it, &tile, &nmask); ++it) {
       const int n_tile = tile % n_tiles;
       const int m0 = (tile / n_tiles) * (2 * GEMM_BLOCK_M) + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = n_tile * PAIR_BN;
@@ -264,6 +304,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       mbar_wait(tmem_full_bar, it & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      if (!((nmask >> half) & 1)) {
+        // tail half-tile owned by the other column half: this warp only keeps the pair's barrier protocols whole
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_remote(te_addr);
+          if (args.gn_apply) {
+#pragma unroll
+            for (int r_ = 0; r_ < 2; ++r_) {
+              mbar_arrive_cluster(mapa_shared(smem_u32(&gn_bar[r_]), 0));
+              mbar_arrive_cluster(mapa_shared(smem_u32(&gn_bar[r_]), 1));
+            }
+          }
+        }
+        continue;
+      }
       if (args.dbg & 2) {  // experiment: no epilogue at all
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(te_addr);
@@ -489,8 +544,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
             bulk_commit_group();
             if (has_res) {
-              const int nt = rnd == 0 ? tile : tile + npairs;
-              if (nt < total_tiles) {
+              int nt = tile, nm_ = nmask;
+              const bool more = rnd == 0 ? true : (pair_sched(sched, pair, it + 1, &nt, &nm_) && ((nm_ >> half) & 1));
+              if (more) {
                 bulk_wait_group_read<0>();  // the store above has read the staging buffer
                 issue_res_load(nt, rnd ^ 1);
               }
@@ -534,8 +590,14 @@ cudaError_t gemm_pair_launch(const GemmLaunch& L, int num_sms, cudaStream_t stre
   const int tiles = (a.N / PAIR_BN) * ((a.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
   const int max_pairs = num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  static const int tail_split = [] {  // env WD_PAIR_TAIL_SPLIT (default on)
+    const char* e = getenv("WD_PAIR_TAIL_SPLIT");
+    return e ? (atoi(e) != 0) : 1;
+  }();
+  GemmArgs a2 = a;
+  a2.tail_split = tail_split && !a.geglu && !a.out_f32 && a.act == ACT_NONE;
   return launch_pdl(gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, L.mapA[0], L.mapA[1], L.mapA[2],
-                    L.mapB, L.mapOut, L.mapRes, a);
+                    L.mapB, L.mapOut, L.mapRes, a2);
 }
 
 }  // namespace wd

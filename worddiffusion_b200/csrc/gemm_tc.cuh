@@ -119,6 +119,7 @@ struct GemmArgs {
   // warps of the pair have published their partials (gn_partial, exchanged through L2 behind a cluster-scope mbarrier).
   // The values wait as fp16 (what the separate GroupNorm kernel used to read): round 0 in the staging tile, round 1 in registers.
   int gn_apply;
+  int tail_split;  // pair kernel: cut the tiles of a last, at most half-full round into 160-column halves (set by gemm_pair_launch)
   const float* gn_gamma;  // [N]
   const float* gn_beta;   // [N]
   float gn_eps;
