@@ -62,6 +62,13 @@ WD_DEVINL void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, u
       : "memory");
 }
 
+// a -> tf32_rn(a) (low 13 mantissa bits zero); a - tf32_rn(a) is exact in fp32
+WD_DEVINL float tf32_rn(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r & 0xFFFFE000u);
+}
+
 struct TcArgs {
   int M, N, K;
   // implicit 3x3 pad-1 stride-1 convolution: A rows are 4-D TMA boxes (c, w, h, n) of the split NHWC source(s), shifted per filter
@@ -80,6 +87,11 @@ struct TcArgs {
   // kb_per_chunk K blocks; each chunk accumulates in one of two TMEM buffers and the epilogue warps add the finished chunk to fp32
   // REGISTER accumulators (exact fp32 adds, in order: deterministic) while the next chunk's MMAs run in the other buffer
   int kb_per_chunk;
+  // GEGLU epilogue (unet.py:122-130): the weight rows were permuted so that a 160-column tile holds 80 value columns and their 80
+  // gates (f32tc_geglu_permute); out[m, n0 / 2 + j] = (acc[j] + b[j]) * gelu_erf(acc[80 + j] + b[80 + j]), row stride N / 2.
+  // out_lo != null: the result leaves as its TF32 split (out = hi, out_lo = lo) for the Linear that consumes it.
+  int geglu;
+  float* out_lo;
 };
 
 template <int BN>
@@ -235,6 +247,32 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
+      if constexpr (BN == TC_BN) {
+        if (args.geglu) {
+          if (m < args.M) {
+            const size_t o0 = static_cast<size_t>(m) * (args.N / 2) + n0 / 2;
+            const float4* bv = reinterpret_cast<const float4*>(args.bias + n0);
+            const float4* bg = reinterpret_cast<const float4*>(args.bias + n0 + 80);
+#pragma unroll
+            for (int c4 = 0; c4 < 20; ++c4) {
+              const float4 b1 = __ldg(bv + c4), b2 = __ldg(bg + c4);
+              const float val[4] = {acc[c4 * 4] + b1.x, acc[c4 * 4 + 1] + b1.y, acc[c4 * 4 + 2] + b1.z, acc[c4 * 4 + 3] + b1.w};
+              const float gt[4] = {acc[80 + c4 * 4] + b2.x, acc[80 + c4 * 4 + 1] + b2.y, acc[80 + c4 * 4 + 2] + b2.z, acc[80 + c4 * 4 + 3] + b2.w};
+              float o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = val[j] * (0.5f * gt[j] * (1.0f + erff(gt[j] * 0.70710678118654752440f)));
+              if (args.out_lo) {
+                const float4 h = make_float4(tf32_rn(o[0]), tf32_rn(o[1]), tf32_rn(o[2]), tf32_rn(o[3]));
+                *reinterpret_cast<float4*>(args.out + o0 + c4 * 4) = h;
+                *reinterpret_cast<float4*>(args.out_lo + o0 + c4 * 4) = make_float4(o[0] - h.x, o[1] - h.y, o[2] - h.z, o[3] - h.w);
+              } else {
+                *reinterpret_cast<float4*>(args.out + o0 + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+          continue;
+        }
+      }
       const int sample = args.rowbias ? m / args.rows_per_sample : 0;
       float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
       const float4* rrow = args.residual ? reinterpret_cast<const float4*>(args.residual + static_cast<size_t>(m) * args.N + n0) : nullptr;
@@ -271,12 +309,6 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
 }
 
-// a -> (tf32_rn(a), a - tf32_rn(a))
-WD_DEVINL float tf32_rn(float a) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-  return __uint_as_float(r & 0xFFFFE000u);
-}
 
 __global__ void f32tc_split_kernel(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -465,6 +497,45 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
   a.act_silu = act_silu;
   a.kb_per_chunk = TC_SPLIT_KB;
   return launch_tc(mAh, mAl, mAh, mAl, mWh, mWl, a, s);
+}
+
+// GEGLU projection with the gating in the epilogue: w_hi / w_lo and bias are in the f32tc_geglu_permute row order; out (and out_lo)
+// are [M, N / 2].
+cudaError_t f32tc_gemm_geglu(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
+                             const float* bias_perm, float* out, float* out_lo, cudaStream_t s) {
+  if (!f32tc_shape_ok(M, N, K) || N % (2 * TC_BN) || !bias_perm) return cudaErrorInvalidValue;
+  CUtensorMap mAh, mAl, mWh, mWl;
+  if (!tmap_f32(&mAh, a_hi, K, M, TC_BM) || !tmap_f32(&mAl, a_lo, K, M, TC_BM) || !tmap_f32(&mWh, w_hi, K, N, TC_BN) ||
+      !tmap_f32(&mWl, w_lo, K, N, TC_BN))
+    return cudaErrorInvalidValue;
+  TcArgs a{};
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.bias = bias_perm;
+  a.rows_per_sample = 1;
+  a.out = out;
+  a.out_lo = out_lo;
+  a.geglu = 1;
+  a.kb_per_chunk = TC_SPLIT_KB;
+  return launch_tc(mAh, mAl, mAh, mAl, mWh, mWl, a, s);
+}
+
+// rows of nn.Linear(K, N) of GEGLU.proj ([values (N / 2) ; gates (N / 2)], unet.py:125-128) -> 160-row tiles of 80 values + their 80 gates
+__global__ void f32tc_geglu_permute_kernel(const float* __restrict__ w, float* __restrict__ dst, int N, size_t K) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(N) * K) return;
+  const int n = static_cast<int>(idx / K);
+  const size_t k = idx - static_cast<size_t>(n) * K;
+  const int half = N / 2, gate = n >= half ? 1 : 0, j = gate ? n - half : n;
+  const int row = (j / 80) * 160 + gate * 80 + (j % 80);
+  dst[static_cast<size_t>(row) * K + k] = w[idx];
+}
+cudaError_t f32tc_geglu_permute(const float* w, float* dst, int N, int K, cudaStream_t s) {
+  if (N % (2 * TC_BN)) return cudaErrorInvalidValue;
+  const size_t n = static_cast<size_t>(N) * K;
+  f32tc_geglu_permute_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(w, dst, N, static_cast<size_t>(K));
+  return cudaGetLastError();
 }
 
 bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N) {

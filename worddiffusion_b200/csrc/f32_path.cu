@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -759,6 +760,11 @@ struct Param {
   bool packed3x3 = false;
   float* hi = nullptr;  // TF32 split of p for the tensor-core GEMM (WD_F32_TC=1 only)
   float* lo = nullptr;
+  // GEGLU.proj only (keys "...ff.net.0.proj.weight" / ".bias"): the rows in the 80-values-then-80-gates tile order of
+  // f32tc_gemm_geglu (perm; for the weight also its TF32 split ghi / glo)
+  float* perm = nullptr;
+  float* ghi = nullptr;
+  float* glo = nullptr;
 };
 
 struct Act {  // token-major activation
@@ -896,18 +902,23 @@ Act gemm(wd_f32* e, const Act& a1, const Act* a2, int B, const float* w, int N, 
     }
     return o;
   }
-  if (!a1.p) fail(WD_ERR_STATE, "fp32 path: a split-only activation reached a contraction that is not the implicit tensor-core conv");
+  const bool presplit_lin = a1.hi && a1.lo && cs.taps == 1 && !a2;  // written by the producer (GEGLU epilogue)
+  if (!a1.p && !(presplit_lin && w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K)))
+    fail(WD_ERR_STATE, "fp32 path: a split-only activation reached a contraction that cannot consume it");
   if (w_hi && w_lo && wd::f32tc_enabled() && !cs.a_nchw && !cs.out_nchw && wd::f32tc_shape_ok(g.M, N, g.K)) {
     const size_t nA = static_cast<size_t>(g.M) * g.K;
-    float* a_hi = alloc(e, nA);
-    float* a_lo = alloc(e, nA);
+    float* a_hi = presplit_lin ? a1.hi : alloc(e, nA);
+    float* a_lo = presplit_lin ? a1.lo : alloc(e, nA);
     const int splits = wd::f32tc_splits(g.K);
     float* ws = splits > 1 ? alloc(e, static_cast<size_t>(splits) * g.M * N) : nullptr;
     if (!e->dry) {
-      cudaError_t ce = cs.taps == 9 ? wd::f32tc_im2col_split(a1.p, a2 ? a2->p : nullptr, g.C1, g.C2, B, a1.H, a1.W, cs.stride, cs.up, a_hi, a_lo, e->s)
-                       : a2       ? wd::f32tc_split_concat(a1.p, a2->p, g.C1, g.C2, static_cast<size_t>(g.M), a_hi, a_lo, e->s)
-                                  : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
-      ++e->launches;
+      cudaError_t ce = cudaSuccess;
+      if (!presplit_lin) {
+        ce = cs.taps == 9 ? wd::f32tc_im2col_split(a1.p, a2 ? a2->p : nullptr, g.C1, g.C2, B, a1.H, a1.W, cs.stride, cs.up, a_hi, a_lo, e->s)
+             : a2       ? wd::f32tc_split_concat(a1.p, a2->p, g.C1, g.C2, static_cast<size_t>(g.M), a_hi, a_lo, e->s)
+                        : wd::f32tc_split(a1.p, a_hi, a_lo, nA, e->s);
+        ++e->launches;
+      }
       if (ce == cudaSuccess) {
         ce = wd::f32tc_gemm(a_hi, a_lo, w_hi, w_lo, g.M, N, g.K, bias, rowbias, rb_ld, g.Hout * g.Wout, residual, o.p, cs.silu, ws, e->s);
         ++e->launches;
@@ -948,6 +959,14 @@ Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int 
   return gemm(e, a, a2, B, w.p, static_cast<int>(w.shape[0]), P(e, pfx + ".bias").p, rowbias, rb_ld, residual, cs, nullptr, w.hi, w.lo);
 }
 
+static bool geglu_fused_enabled() {  // env WD_F32_GEGLU_FUSED (default on)
+  static int v = -1;
+  if (v < 0) {
+    const char* x = getenv("WD_F32_GEGLU_FUSED");
+    v = x ? (atoi(x) != 0) : 1;
+  }
+  return v != 0;
+}
 static bool gn_fast_enabled() {  // env WD_F32_GN_FAST (default on)
   static int v = -1;
   if (v < 0) {
@@ -1081,15 +1100,41 @@ Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, 
       t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p);
     }
     Act l3 = layernorm(e, bp + "norm3", t, B);
-    Act pr = linear(e, bp + "ff.net.0.proj", l3, B, true);
-    const int Hd = pr.C / 2;
     const size_t M = static_cast<size_t>(B) * t.H * t.W;
+    const Param& wp = P(e, bp + "ff.net.0.proj.weight");
+    const Param& bp_ = P(e, bp + "ff.net.0.proj.bias");
+    const Param& w2 = P(e, bp + "ff.net.2.weight");
+    const int Np = static_cast<int>(wp.shape[0]), Kp = static_cast<int>(wp.shape[1]), Hd = Np / 2;
     Act gg = t;
     gg.C = Hd;
-    gg.p = alloc(e, M * Hd);
-    if (!e->dry) {
-      f32_geglu_kernel<<<static_cast<unsigned>((M * Hd + 255) / 256), 256, 0, e->s>>>(pr.p, gg.p, M, Hd);
-      after_launch(e, "geglu");
+    // GEGLU (unet.py:122-130) in the projection's own epilogue, the product written as the TF32 split the next Linear consumes:
+    // the [M, 2 Hd] projection, the gating pass over it and the split pass never touch HBM
+    const bool fused = geglu_fused_enabled() && wp.ghi && wp.glo && bp_.perm && w2.hi && w2.lo && wd::f32tc_enabled() && Kp == l3.C &&
+                       wd::f32tc_shape_ok(static_cast<int>(M), Np, Kp) && Np % 320 == 0 &&
+                       wd::f32tc_shape_ok(static_cast<int>(M), static_cast<int>(w2.shape[0]), Hd) && l3.p;
+    if (fused) {
+      const size_t nA = M * Kp;
+      float* a_hi = alloc(e, nA);
+      float* a_lo = alloc(e, nA);
+      gg.p = nullptr;
+      gg.hi = alloc(e, M * Hd);
+      gg.lo = alloc(e, M * Hd);
+      if (!e->dry) {
+        cudaError_t ce = wd::f32tc_split(l3.p, a_hi, a_lo, nA, e->s);
+        ++e->launches;
+        if (ce == cudaSuccess) {
+          ce = wd::f32tc_gemm_geglu(a_hi, a_lo, wp.ghi, wp.glo, static_cast<int>(M), Np, Kp, bp_.perm, gg.hi, gg.lo, e->s);
+          ++e->launches;
+        }
+        if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: fused GEGLU projection: ") + cudaGetErrorString(ce));
+      }
+    } else {
+      Act pr = linear(e, bp + "ff.net.0.proj", l3, B, true);
+      gg.p = alloc(e, M * Hd);
+      if (!e->dry) {
+        f32_geglu_kernel<<<static_cast<unsigned>((M * Hd + 255) / 256), 256, 0, e->s>>>(pr.p, gg.p, M, Hd);
+        after_launch(e, "geglu");
+      }
     }
     t = linear(e, bp + "ff.net.2", gg, B, true, t.p);
   }
@@ -1452,6 +1497,9 @@ void wd_f32_destroy(wd_f32* e) {
     cudaFree(kv.second.p);
     cudaFree(kv.second.hi);
     cudaFree(kv.second.lo);
+    cudaFree(kv.second.perm);
+    cudaFree(kv.second.ghi);
+    cudaFree(kv.second.glo);
   }
   cudaFree(e->pe);
   cudaFree(e->ctx);
@@ -1498,6 +1546,29 @@ int wd_f32_load_param(wd_f32* e, const char* name, const float* src, const int64
       return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc of the TF32 split failed");
     ce = wd::f32tc_split(p.p, p.hi, p.lo, n, s);
     if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  // GEGLU.proj (unet.py:125): a second copy in the tile order of the fused GEGLU epilogue
+  {
+    const std::string nm(name);
+    auto ends_with = [&](const char* suf) {
+      const size_t l = strlen(suf);
+      return nm.size() >= l && nm.compare(nm.size() - l, l, suf) == 0;
+    };
+    const bool gw = ends_with("ff.net.0.proj.weight") && ndim == 2, gb = ends_with("ff.net.0.proj.bias") && ndim == 1;
+    if (wd::f32tc_enabled() && (gw || gb) && shape[0] % 320 == 0 && (n & 3) == 0) {
+      cudaFree(p.perm);
+      cudaFree(p.ghi);
+      cudaFree(p.glo);
+      p.perm = p.ghi = p.glo = nullptr;
+      if (cudaMalloc(&p.perm, n * sizeof(float)) != cudaSuccess) return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc failed");
+      ce = wd::f32tc_geglu_permute(p.p, p.perm, static_cast<int>(shape[0]), gw ? static_cast<int>(shape[1]) : 1, s);
+      if (ce == cudaSuccess && gw) {
+        if (cudaMalloc(&p.ghi, n * sizeof(float)) != cudaSuccess || cudaMalloc(&p.glo, n * sizeof(float)) != cudaSuccess)
+          return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc failed");
+        ce = wd::f32tc_split(p.perm, p.ghi, p.glo, n, s);
+      }
+      if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+    }
   }
   return WD_OK;
 }

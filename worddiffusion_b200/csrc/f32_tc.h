@@ -20,6 +20,12 @@ int f32tc_splits(int K);
 cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K, const float* bias,
                        const float* rowbias, int rb_ld, int rows_per_sample, const float* residual, float* out, int act_silu,
                        float* partial_ws, cudaStream_t s);
+// GEGLU.proj with the gating in the GEMM's epilogue (unet.py:122-130): out[M, N / 2] = (A Wv^T + bv) * gelu_erf(A Wg^T + bg).
+// w_hi / w_lo / bias_perm are in f32tc_geglu_permute order (160-row tiles of 80 values + their 80 gates; N % 320 == 0; a bias is a
+// [N, 1] matrix for the permutation).  out_lo != null: the result is written as its TF32 split (out = hi, out_lo = lo).
+cudaError_t f32tc_geglu_permute(const float* w, float* dst, int N, int K, cudaStream_t s);
+cudaError_t f32tc_gemm_geglu(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
+                             const float* bias_perm, float* out, float* out_lo, cudaStream_t s);
 // implicit 3x3 pad-1 stride-1 convolution over the channel concatenation of up to two split NHWC sources [B, H, W, C1 | C2]
 // (C % 32 == 0; 128 % W == 0 and HW % 128 == 0, or 128 % HW == 0); weights [N, 9 (C1 + C2)] split, k = tap (C1 + C2) + c
 bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N);
