@@ -423,9 +423,11 @@ __global__ void __launch_bounds__(GN32_T) f32_gn_apply_kernel(const float* __res
 }
 
 // nn.LayerNorm(C), eps 1e-5 (unet.py:314-316): one warp per token
+// SPLIT: the result leaves as its TF32 split (out = hi, out_lo = lo) for the tensor-core Linear(s) that consume it
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) f32_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float* __restrict__ out, int M,
-                                                            int C, float eps) {
+                                                            const float* __restrict__ beta, float* __restrict__ out,
+                                                            float* __restrict__ out_lo, int M, int C, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* xr = x + static_cast<size_t>(row) * C;
@@ -441,7 +443,16 @@ __global__ void __launch_bounds__(256) f32_layernorm_kernel(const float* __restr
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
   float* orow = out + static_cast<size_t>(row) * C;
-  for (int c = lane; c < C; c += 32) orow[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+  for (int c = lane; c < C; c += 32) {
+    const float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if constexpr (SPLIT) {
+      const float h = gn32_tf32_rn(y);
+      orow[c] = h;
+      out_lo[static_cast<size_t>(row) * C + c] = y - h;
+    } else {
+      orow[c] = y;
+    }
+  }
 }
 
 // =====================================================================================================
@@ -1014,12 +1025,30 @@ Act groupnorm(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, in
   return o;
 }
 
-Act layernorm(wd_f32* e, const std::string& pfx, const Act& a, int B) {
+// will linear(wpfx) over an [M, K] activation take the tensor-core route (the one that consumes a pre-split activation)?
+bool lin_takes_split(wd_f32* e, const std::string& wpfx, int M, int K) {
+  const Param& w = P(e, wpfx + ".weight");
+  int Kw = 1;  // nn.Linear [N, K] or a 1x1 convolution [N, K, 1, 1] (as linear() reads it)
+  for (size_t i = 1; i < w.shape.size(); ++i) Kw *= static_cast<int>(w.shape[i]);
+  return w.hi && w.lo && !w.packed3x3 && Kw == K && wd::f32tc_enabled() && wd::f32tc_shape_ok(M, static_cast<int>(w.shape[0]), K);
+}
+
+Act layernorm(wd_f32* e, const std::string& pfx, const Act& a, int B, bool split_out = false) {
   Act o = a;
   const int M = B * a.H * a.W;
-  o.p = alloc(e, static_cast<size_t>(M) * a.C);
+  const size_t n = static_cast<size_t>(M) * a.C;
+  if (split_out) {  // every consumer is a tensor-core Linear: hand them the TF32 split, nothing else reads it
+    o.p = nullptr;
+    o.hi = alloc(e, n);
+    o.lo = alloc(e, n);
+  } else {
+    o.p = alloc(e, n);
+  }
   if (!e->dry) {
-    f32_layernorm_kernel<<<(M + 7) / 8, 256, 0, e->s>>>(a.p, P(e, pfx + ".weight").p, P(e, pfx + ".bias").p, o.p, M, a.C, 1e-5f);
+    if (split_out)
+      f32_layernorm_kernel<true><<<(M + 7) / 8, 256, 0, e->s>>>(a.p, P(e, pfx + ".weight").p, P(e, pfx + ".bias").p, o.hi, o.lo, M, a.C, 1e-5f);
+    else
+      f32_layernorm_kernel<false><<<(M + 7) / 8, 256, 0, e->s>>>(a.p, P(e, pfx + ".weight").p, P(e, pfx + ".bias").p, o.p, nullptr, M, a.C, 1e-5f);
     after_launch(e, "layernorm");
   }
   return o;
@@ -1074,14 +1103,15 @@ Act cross_attention(wd_f32* e, const std::string& pfx, const Act& xq, int B, con
 
 // SpatialTransformer.forward (unet.py:381-412 / unetPhosc.py:282-300) with BasicTransformerBlock (unet.py:337-345 / unetPhosc.py:241-246)
 Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, const Act& ctx) {
-  Act n = groupnorm(e, pfx + "norm", x, nullptr, B, 1e-6f, 0);
+  Act n = groupnorm(e, pfx + "norm", x, nullptr, B, 1e-6f, 0, lin_takes_split(e, pfx + "proj_in", B * x.H * x.W, x.C));
   Act t = linear(e, pfx + "proj_in", n, B, true);
   for (int dpt = 0; dpt < e->cfg.transformer_depth; ++dpt) {
     const std::string bp = pfx + "transformer_blocks." + std::to_string(dpt) + ".";
     if (e->cfg.variant == WD_VARIANT_UNET) {
-      Act l1 = layernorm(e, bp + "norm2", t, B);
+      const int Mt = B * t.H * t.W;
+      Act l1 = layernorm(e, bp + "norm2", t, B, lin_takes_split(e, bp + "attn1.to_q", Mt, t.C));
       t = cross_attention(e, bp + "attn1.", l1, B, &ctx, t.p);
-      Act l2 = layernorm(e, bp + "norm2", t, B);
+      Act l2 = layernorm(e, bp + "norm2", t, B, lin_takes_split(e, bp + "attn2.to_q", Mt, t.C));
       float* probs = nullptr;
       if (e->want_maps && dpt == e->cfg.transformer_depth - 1) {  // SpatialTransformer returns the LAST block's attn (unet.py:396-397)
         const int L = ctx.H * ctx.W;
@@ -1094,12 +1124,15 @@ Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, 
       }
       t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p, probs);
     } else {
-      Act l1 = layernorm(e, bp + "norm1", t, B);
+      const int Mt = B * t.H * t.W;
+      Act l1 = layernorm(e, bp + "norm1", t, B,
+                         lin_takes_split(e, bp + "attn1.to_q", Mt, t.C) && lin_takes_split(e, bp + "attn1.to_k", Mt, t.C) &&
+                             lin_takes_split(e, bp + "attn1.to_v", Mt, t.C));
       t = cross_attention(e, bp + "attn1.", l1, B, nullptr, t.p);
-      Act l2 = layernorm(e, bp + "norm2", t, B);
+      Act l2 = layernorm(e, bp + "norm2", t, B, lin_takes_split(e, bp + "attn2.to_q", Mt, t.C));
       t = cross_attention(e, bp + "attn2.", l2, B, &ctx, t.p);
     }
-    Act l3 = layernorm(e, bp + "norm3", t, B);
+    Act l3 = layernorm(e, bp + "norm3", t, B, lin_takes_split(e, bp + "ff.net.0.proj", B * t.H * t.W, t.C));
     const size_t M = static_cast<size_t>(B) * t.H * t.W;
     const Param& wp = P(e, bp + "ff.net.0.proj.weight");
     const Param& bp_ = P(e, bp + "ff.net.0.proj.bias");
@@ -1111,17 +1144,21 @@ Act spatial_transformer(wd_f32* e, const std::string& pfx, const Act& x, int B, 
     // the [M, 2 Hd] projection, the gating pass over it and the split pass never touch HBM
     const bool fused = geglu_fused_enabled() && wp.ghi && wp.glo && bp_.perm && w2.hi && w2.lo && wd::f32tc_enabled() && Kp == l3.C &&
                        wd::f32tc_shape_ok(static_cast<int>(M), Np, Kp) && Np % 320 == 0 &&
-                       wd::f32tc_shape_ok(static_cast<int>(M), static_cast<int>(w2.shape[0]), Hd) && l3.p;
+                       wd::f32tc_shape_ok(static_cast<int>(M), static_cast<int>(w2.shape[0]), Hd);
     if (fused) {
       const size_t nA = M * Kp;
-      float* a_hi = alloc(e, nA);
-      float* a_lo = alloc(e, nA);
+      const bool l3_split = l3.hi && l3.lo;
+      float* a_hi = l3_split ? l3.hi : alloc(e, nA);
+      float* a_lo = l3_split ? l3.lo : alloc(e, nA);
       gg.p = nullptr;
       gg.hi = alloc(e, M * Hd);
       gg.lo = alloc(e, M * Hd);
       if (!e->dry) {
-        cudaError_t ce = wd::f32tc_split(l3.p, a_hi, a_lo, nA, e->s);
-        ++e->launches;
+        cudaError_t ce = cudaSuccess;
+        if (!l3_split) {
+          ce = wd::f32tc_split(l3.p, a_hi, a_lo, nA, e->s);
+          ++e->launches;
+        }
         if (ce == cudaSuccess) {
           ce = wd::f32tc_gemm_geglu(a_hi, a_lo, wp.ghi, wp.glo, static_cast<int>(M), Np, Kp, bp_.perm, gg.hi, gg.lo, e->s);
           ++e->launches;
