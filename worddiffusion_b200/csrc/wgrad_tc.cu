@@ -1,6 +1,7 @@
 // tcgen05 weight-gradient kernel, see wgrad_tc.cuh for the contract.
 #include "wgrad_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace wd {
@@ -196,9 +197,16 @@ cudaError_t launch_bn(const WgradLaunch& L, cudaStream_t stream) {
 }  // namespace
 
 int wgrad_pick_splits(int M, int items_base) {
-  // aim at ~2 work items per SM, but keep at least 8 token blocks (512 tokens) per item
+  // One full wave: the largest token split whose work items still fit the 148 SMs at once (each item ends with 128 x 320 scattered
+  // fp32 atomics, a fixed cost per item, and a second, partial wave doubles the launch's MMA time), but at least 8 token blocks
+  // (512 tokens) per item.  Measured (tools/ab_r4w.sh): the former "2 items per SM" (297 items for a 320 -> 320 conv) against 135
+  // items: training step 15.4 -> 14.4 ms at batch 224, 6.19 -> 5.89 ms at batch 28.  WD_WGRAD_TARGET_ITEMS overrides the item budget.
   const int kb_total = (M + WG_BLOCK_TOK - 1) / WG_BLOCK_TOK;
-  int s = (2 * 148 + items_base - 1) / items_base;
+  static const int target = [] {
+    const char* e = getenv("WD_WGRAD_TARGET_ITEMS");
+    return e && atoi(e) > 0 ? atoi(e) : 0;
+  }();
+  int s = target > 0 ? (target + items_base - 1) / items_base : 148 / (items_base > 0 ? items_base : 1);
   const int max_s = kb_total / 8 > 0 ? kb_total / 8 : 1;
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
