@@ -905,6 +905,9 @@ static int gemm_pair_min_kblocks(int M) {
     v = e ? atoi(e) : -1;
   }
   if (v >= 0) return v;
+  // fewer than 48 pair tiles (0.65 of a wave of 74 pairs): the single-CTA kernel's 128 x 160 tiles fill 4x as many SMs and walk a K
+  // block in half the time -- unet step at batch 32 / 8 / 1: 0.989 -> 0.840, 0.947 -> 0.796, 0.872 -> 0.709 ms (tools/ab_r4B.sh)
+  if (M < 48 * 256) return 1 << 30;
   return M <= 32768 ? 40 : 50;
 }
 bool gemm_uses_pair(const GemmArgs& a) {
