@@ -36,7 +36,7 @@ MODEL_KW = dict(image_size=(64, 256), in_channels=4, model_channels=320, out_cha
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/traffic.json, written by tools/summarize_ncu.py numbers of profiles/r01q_ncu_gemm_step_window.txt)."""
+    capture (profiles/traffic.json, from the tools/summarize_ncu.py numbers of profiles/R4q_ncu_gemm.txt)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
@@ -658,7 +658,7 @@ def run_ours(args):
         roofline["fused_block"] = {"kernel": "tblock_unet_kernel (tcgen05 / TMEM / TMA, cta_group::2)", "bound": "tensor",
                                    "achieved_reference_ops": round(tb, 2), "frac": round(tb / peaks["tf_burst"], 4),
                                    "launches_per_step": cls_n["tblock"], "share_of_step": kernels["tblock"]["share"],
-                                   "evidence": "profiles/R2d_ncu_tblock.txt, profiles/R2g_tblock_trace_pair*.txt"}
+                                   "evidence": "profiles/R4q_ncu_tblock.txt, profiles/R2y_tblock_trace_pair1.txt"}
     tr = load_traffic()
     if tr and variant == "unet" and B == tr.get("batch"):
         roofline["traffic"] = tr["gemm_tc_kernel"]["dram_bytes_per_launch"]
