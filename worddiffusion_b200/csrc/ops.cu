@@ -934,7 +934,8 @@ WD_DEVINL void oh_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, 
 static size_t out_head_smem_bytes(int H, int W, int C) {
   const size_t pitch = static_cast<size_t>(C) * 2 + 16;           // bytes per pixel row (+16: ldmatrix rows land in distinct banks)
   const size_t wpitch = (static_cast<size_t>(9) * C + 8) * 2;     // bytes per weight row (+16)
-  return (static_cast<size_t>(H) * W + 1) * pitch + OH_WROWS * wpitch + static_cast<size_t>(C) * 8 + 256 + 64;  // tables, statistics, 2 mbarriers
+  return (static_cast<size_t>(H) * W + 1) * pitch + OH_WROWS * wpitch + static_cast<size_t>(C) * 8 + 256 + 64 +  // tables, statistics, mbarriers
+         static_cast<size_t>(H) * W * 32;  // [HW][8] fp32 output tile of the shifted accumulation
 }
 bool out_head_supported(int H, int W, int C) {
   return H >= 1 && W >= 1 && (H * W) % 16 == 0 && C % 32 == 0 && C % 16 == 0 && (C / 32) % 2 == 0 && C <= 1024 &&
@@ -1037,7 +1038,12 @@ __global__ void __launch_bounds__(OH_THREADS, 1) out_head_kernel(const OutHeadAr
   mbar_wait(&bars[0], 0);
   __syncthreads();
 
-  // ---- 3 x 3 convolution on mma.sync: M = pixels (16 per tile), N = 8 weight rows, K = 9 C ----
+  // ---- 3 x 3 convolution on mma.sync, SOURCE-tile form: a warp loads the A fragments of a 16-pixel source tile ONCE per K step
+  // (no shift, no padding row) and multiplies them by all nine taps' weight fragments (nine accumulators of 16 x 8 per tile);
+  // tap (dy, dx)'s accumulator of source pixel (y, x) then belongs to output pixel (y - dy, x - dx).  The first version walked
+  // output tiles and re-read the image through ldmatrix once per tap: 1.5 MB of shared-memory reads per CTA, the kernel's bound
+  // (profiles/R4p_out_head.txt); this form reads it once.  The shifted accumulators are added into a [HW][8] fp32 tile tap by
+  // tap (within a tap every output pixel receives from exactly one thread: plain adds, fixed order, deterministic). ----
   const float4 coef = a.sp ? a.sp->coef : a.coef;
   const int mode = a.sp ? a.sp->mode : a.mode;
   const int use_philox = a.sp ? a.sp->use_philox : a.use_philox;
@@ -1048,27 +1054,26 @@ __global__ void __launch_bounds__(OH_THREADS, 1) out_head_kernel(const OutHeadAr
   const int ntile = HW / 16;
   const uint32_t act_base = smem_u32(s_act);
   const int ksteps = C / 16;
-  for (int t0 = warp * 2; t0 < ntile; t0 += 2 * (OH_THREADS / 32)) {
-    const bool two = t0 + 1 < ntile;
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-    float acc0b[4] = {0.f, 0.f, 0.f, 0.f}, acc1b[4] = {0.f, 0.f, 0.f, 0.f};  // odd k steps: four independent HMMA chains per warp
-    // this lane's ldmatrix row: pixel (tile * 16 + r), 8-column half kh
-    const int r = (lane & 7) + ((lane >> 3) & 1) * 8, kh = lane >> 4;
-    const int p0 = t0 * 16 + r, p1 = (two ? t0 + 1 : t0) * 16 + r;
-    const int y0 = p0 / a.W, x0 = p0 - y0 * a.W, y1 = p1 / a.W, x1 = p1 - y1 * a.W;
+  float* s_out = reinterpret_cast<float*>(bars + 4);  // [HW][8] fp32
+  for (int i = tid; i < HW * 8; i += OH_THREADS) s_out[i] = 0.f;
+  constexpr int OH_WARPS = OH_THREADS / 32;
+  const int rounds = (ntile + 2 * OH_WARPS - 1) / (2 * OH_WARPS);
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int t0 = (rd * OH_WARPS + warp) * 2;
+    const bool have0 = t0 < ntile, have1 = t0 + 1 < ntile;
+    float acc0[9][4], acc1[9][4];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc0[tp][i] = acc1[tp][i] = 0.f;
+    if (have0) {
+      // this lane's ldmatrix row: source pixel (tile * 16 + r), 8-column half kh
+      const int r = (lane & 7) + ((lane >> 3) & 1) * 8, kh = lane >> 4;
+      const uint32_t ra0 = act_base + static_cast<uint32_t>(t0 * 16 + r) * pitch + kh * 16;
+      const uint32_t ra1 = act_base + static_cast<uint32_t>((have1 ? t0 + 1 : t0) * 16 + r) * pitch + kh * 16;
+      const uint8_t* wrow = s_w + g * wpitch + (2 * tq) * 2;
 #pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      const int sy0 = y0 + dy, sx0 = x0 + dx, sy1 = y1 + dy, sx1 = x1 + dx;
-      const int q0 = (sy0 >= 0 && sy0 < a.H && sx0 >= 0 && sx0 < a.W) ? sy0 * a.W + sx0 : HW;  // HW = the zero row
-      const int q1 = (sy1 >= 0 && sy1 < a.H && sx1 >= 0 && sx1 < a.W) ? sy1 * a.W + sx1 : HW;
-      const uint32_t ra0 = act_base + static_cast<uint32_t>(q0) * pitch + kh * 16;
-      const uint32_t ra1 = act_base + static_cast<uint32_t>(q1) * pitch + kh * 16;
-      const uint8_t* wrow = s_w + g * wpitch + (static_cast<size_t>(tap) * C + 2 * tq) * 2;
-#pragma unroll 4
       for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + ks * 32);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + ks * 32 + 16);
         uint32_t f0[4], f1[4];
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                      : "=r"(f0[0]), "=r"(f0[1]), "=r"(f0[2]), "=r"(f0[3])
@@ -1076,60 +1081,71 @@ __global__ void __launch_bounds__(OH_THREADS, 1) out_head_kernel(const OutHeadAr
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                      : "=r"(f1[0]), "=r"(f1[1]), "=r"(f1[2]), "=r"(f1[3])
                      : "r"(ra1 + ks * 32));
-        if (ks & 1) {
-          oh_mma_16816(acc0b, f0, b0, b1);
-          oh_mma_16816(acc1b, f1, b0, b1);
-        } else {
-          oh_mma_16816(acc0, f0, b0, b1);
-          oh_mma_16816(acc1, f1, b0, b1);
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          const uint8_t* wp = wrow + (static_cast<size_t>(tp) * C + ks * 16) * 2;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wp + 16);
+          oh_mma_16816(acc0[tp], f0, b0, b1);
+          oh_mma_16816(acc1[tp], f1, b0, b1);
         }
       }
     }
+    // shifted accumulation, tap by tap (every thread takes part in the barriers)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc0[i] += acc0b[i];
-      acc1[i] += acc1b[i];
-    }
-    // ---- epilogue: eps = (hi + lo) + bias, sampler update (the arithmetic of gemm_tc.cu's EPI_SAMPLER, bit for bit) ----
-    // columns 2 tq, 2 tq + 1 of rows g, g + 8; the lo part of output channel o sits in column 4 + o = lane + 2's column o
-    float lo0[4], lo1[4];
+    for (int tp = 0; tp < 9; ++tp) {
+      const int dy = tp / 3 - 1, dx = tp % 3 - 1;
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      lo0[i] = __shfl_down_sync(0xffffffffu, acc0[i], 2);
-      lo1[i] = __shfl_down_sync(0xffffffffu, acc1[i], 2);
-    }
-    if (tq < 2) {
-      const int nel = two ? 8 : 4;
-      size_t idx[8];
-      float eps[8], xv[8], z[8];
-      // all loads first (x / noise may not be reordered across the eps_out stores by the compiler: every load would wait ~1 us)
+      for (int tt = 0; tt < 2; ++tt) {
+        if (!(tt ? have1 : have0)) continue;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int tt = e >> 2, i = e & 3;
-        const int o = 2 * tq + (i & 1);
-        const int pix = (t0 + tt) * 16 + g + (i >> 1) * 8;
-        idx[e] = (static_cast<size_t>(b) * 4 + o) * HW + pix;
-        eps[e] = ((tt ? acc1[i] : acc0[i]) + (tt ? lo1[i] : lo0[i])) + __ldg(a.bias + o);
-        xv[e] = 0.f;
-        z[e] = 0.f;
-        if (e < nel && mode != STEP_EPS_ONLY) {
-          xv[e] = a.x[idx[e]];
-          if (mode == STEP_DDPM && a.noise) z[e] = __ldg(a.noise + idx[e]);
+        for (int hr = 0; hr < 2; ++hr) {
+          const int p = (t0 + tt) * 16 + g + hr * 8;  // source pixel
+          const int y = p / a.W, x = p - y * a.W;
+          const int oy = y - dy, ox = x - dx;
+          if (oy >= 0 && oy < a.H && ox >= 0 && ox < a.W) {
+            float2* dst = reinterpret_cast<float2*>(s_out + static_cast<size_t>(oy * a.W + ox) * 8 + 2 * tq);
+            float2 v = *dst;
+            v.x += tt ? acc1[tp][2 * hr] : acc0[tp][2 * hr];
+            v.y += tt ? acc1[tp][2 * hr + 1] : acc0[tp][2 * hr + 1];
+            *dst = v;
+          }
         }
       }
+    }
+  }
+  __syncthreads();
+  // ---- epilogue: eps = (hi + lo) + bias, sampler update (the arithmetic of gemm_tc.cu's EPI_SAMPLER); one pixel per thread and
+  // pass, so every global access of a warp is 32 consecutive floats ----
+  for (int pix = tid; pix < HW; pix += OH_THREADS) {
+    const float4 hi = *reinterpret_cast<const float4*>(s_out + static_cast<size_t>(pix) * 8);
+    const float4 lo = *reinterpret_cast<const float4*>(s_out + static_cast<size_t>(pix) * 8 + 4);
+    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+    size_t idx[4];
+    float eps[4], xv[4], z[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (e >= nel) break;
-        if (a.eps_out) a.eps_out[idx[e]] = eps[e];
-        if (mode == STEP_DDPM) {
-          float zz = z[e];
-          if (!a.noise && use_philox) zz = philox_normal(seed, sample_offset * (4ull * HW) + idx[e], static_cast<uint32_t>(step_index));
-          const float inner = __fsub_rn(xv[e], __fmul_rn(coef.y, eps[e]));
-          a.x[idx[e]] = __fadd_rn(__fmul_rn(coef.x, inner), __fmul_rn(coef.z, zz));
-        } else if (mode == STEP_DDIM) {
-          const float x0v = __fmul_rn(__fsub_rn(xv[e], __fmul_rn(coef.y, eps[e])), coef.x);
-          a.x[idx[e]] = __fadd_rn(__fmul_rn(coef.z, x0v), __fmul_rn(coef.w, eps[e]));
-        }
+    for (int o = 0; o < 4; ++o) {
+      idx[o] = (static_cast<size_t>(b) * 4 + o) * HW + pix;
+      eps[o] = (hv[o] + lv[o]) + __ldg(a.bias + o);
+      xv[o] = 0.f;
+      z[o] = 0.f;
+      if (mode != STEP_EPS_ONLY) {
+        xv[o] = a.x[idx[o]];
+        if (mode == STEP_DDPM && a.noise) z[o] = __ldg(a.noise + idx[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (a.eps_out) a.eps_out[idx[o]] = eps[o];
+      if (mode == STEP_DDPM) {
+        float zz = z[o];
+        if (!a.noise && use_philox) zz = philox_normal(seed, sample_offset * (4ull * HW) + idx[o], static_cast<uint32_t>(step_index));
+        const float inner = __fsub_rn(xv[o], __fmul_rn(coef.y, eps[o]));
+        a.x[idx[o]] = __fadd_rn(__fmul_rn(coef.x, inner), __fmul_rn(coef.z, zz));
+      } else if (mode == STEP_DDIM) {
+        const float x0v = __fmul_rn(__fsub_rn(xv[o], __fmul_rn(coef.y, eps[o])), coef.x);
+        a.x[idx[o]] = __fadd_rn(__fmul_rn(coef.z, x0v), __fmul_rn(coef.w, eps[o]));
       }
     }
   }
