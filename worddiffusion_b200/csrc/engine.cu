@@ -1710,7 +1710,9 @@ struct PlanBuilder {
       if (!run_block(blk, {h, skip})) return false;
     }
     // out: GN + SiLU + conv_out + sampler update as ONE kernel with the sample's image in shared memory (ops.cuh: OutHeadArgs)
-    if (out_head_enabled() && h.f16 && h.pslots > 0 && h.C % 32 == 0 && c.out_channels == 4 && out_head_supported(h.H, h.W, h.C)) {
+    // (one CTA per sample: below ~64 latents the grid leaves the GPU empty and the kernel's serial phases show -- batch 1: 0.778 vs
+    //  0.720 ms per step with the two-launch form; batch 32 and 256: equal -- so small batches keep the two launches)
+    if (out_head_enabled() && B >= 64 && h.f16 && h.pslots > 0 && h.C % 32 == 0 && c.out_channels == 4 && out_head_supported(h.H, h.W, h.C)) {
       Op op;
       memset(&op, 0, sizeof(op));
       op.kind = OP_OUTHEAD;
