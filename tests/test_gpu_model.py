@@ -189,11 +189,11 @@ def test_phosc_batch_invariance_at_benchmark_batches(phosc, B):
     assert torch.equal(e_big[idx], e_small)
 
 
-@pytest.mark.parametrize("B,latent", [(3, (4, 8, 16)), (1, (4, 8, 32)), (5, (4, 8, 32))])
+@pytest.mark.parametrize("B,latent", [(3, (4, 8, 16)), (1, (4, 8, 32)), (5, (4, 8, 32)), (64, (4, 8, 16))])
 def test_forward_vs_oracle_other_latent_sizes(B, latent, unet):
     """train.Diffusion's default img_size (64, 128) gives 8 x 16 latents (train.py:175): the engine plans per latent size; the
     one-kernel output head (GroupNorm + conv_out + sampler update over a shared-memory image of the sample) and the producer-
-    side GroupNorm of the ResBlocks run at 128-pixel samples, ragged batches and a single latent."""
+    side GroupNorm of the ResBlocks run at 128-pixel samples (the output head from 64 latents up), ragged batches and a single latent."""
     m, sd = unet
     inp = W.make_inputs(B, seed=641, latent=latent)
     ci = _cuda(inp)
