@@ -612,17 +612,40 @@ cudaError_t groupnorm_bwd_launch(const GroupNormBwdArgs& a, int B, int nslab, cu
 // =====================================================================================================
 // LayerNorm backward: one warp per token (looping), per-lane register accumulators for dgamma / dbeta
 // =====================================================================================================
+constexpr int LNB_STAGES = 4;
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16_t* __restrict__ x, const bf16_t* __restrict__ dy,
                                                             const float* __restrict__ gamma, const bf16_t* __restrict__ add,
                                                             bf16_t* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int M, int C, float eps) {
-  extern __shared__ float lnb_smem[];  // [2][C]
+  // [2][C] fp32 column sums, then per warp LNB_STAGES x (x row, dy row) bf16 staging buffers filled by cp.async.bulk (one token per
+  // stage, three tokens in flight per warp: with plain loads a warp had ONE token = 1.3 KB in flight and the 12 launches of a
+  // batch-224 backward pass ran at 1.45 TB/s), then the stages' mbarriers
+  extern __shared__ __align__(128) float lnb_smem[];
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int nwarps = blockDim.x >> 5;
+  const int warps_total = gridDim.x * nwarps;
   const int nv = C >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(lnb_smem + 2 * C);
+  uint8_t* wbuf = stage_base + static_cast<size_t>(warp_in_block) * LNB_STAGES * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + static_cast<size_t>(nwarps) * LNB_STAGES * 2 * row_bytes);
+  uint64_t* wbar = bars + warp_in_block * LNB_STAGES;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) lnb_smem[i] = 0.f;
+  if (threadIdx.x < nwarps * LNB_STAGES) mbar_init(&bars[threadIdx.x], 1);
+  fence_barrier_init();
   __syncthreads();
+  const int tok0 = blockIdx.x * nwarps + warp_in_block;
+  const int ntok = tok0 < M ? (M - tok0 + warps_total - 1) / warps_total : 0;  // tokens of this warp: tok0 + k * warps_total
+  auto issue = [&](int k) {  // lane 0 only
+    const int st = k % LNB_STAGES;
+    const size_t tokk = static_cast<size_t>(tok0) + static_cast<size_t>(k) * warps_total;
+    mbar_arrive_expect_tx(&wbar[st], 2 * row_bytes);
+    bulk_load_1d(wbuf + static_cast<size_t>(st) * 2 * row_bytes, x + tokk * C, row_bytes, &wbar[st]);
+    bulk_load_1d(wbuf + static_cast<size_t>(st) * 2 * row_bytes + row_bytes, dy + tokk * C, row_bytes, &wbar[st]);
+  };
+  if (lane == 0)
+    for (int k = 0; k < LNB_STAGES - 1 && k < ntok; ++k) issue(k);
   float gm[MAXV][8], ag[MAXV][8], ab[MAXV][8];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -631,17 +654,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16_t* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
   }
-  for (int tok = blockIdx.x * (blockDim.x >> 5) + warp_in_block; tok < M; tok += warps_total) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(tok) * C);
-    const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(tok) * C);
+  for (int k = 0; k < ntok; ++k) {
+    const int tok = tok0 + k * warps_total;
+    const int st = k % LNB_STAGES;
+    if (lane == 0 && k + LNB_STAGES - 1 < ntok) issue(k + LNB_STAGES - 1);  // its stage was drained in iteration k - 1
+    mbar_wait(&wbar[st], (k / LNB_STAGES) & 1);
+    const uint4* xr = reinterpret_cast<const uint4*>(wbuf + static_cast<size_t>(st) * 2 * row_bytes);
+    const uint4* dr = reinterpret_cast<const uint4*>(wbuf + static_cast<size_t>(st) * 2 * row_bytes + row_bytes);
     float f[MAXV][8], d[MAXV][8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nv) {
-        unpack8(__ldg(xr + vi), f[i]);
-        unpack8(__ldg(dr + vi), d[i]);
+        unpack8(xr[vi], f[i]);
+        unpack8(dr[vi], d[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum += f[i][j];
       }
@@ -703,6 +730,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16_t* __rest
         orow[vi] = pack8(o8);
       }
     }
+    __syncwarp();  // every lane has read the stage (f / d are in registers) before lane 0 refills it
   }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -728,7 +756,15 @@ cudaError_t layernorm_bwd_launch(const bf16_t* x, const bf16_t* dy, const float*
   int blocks = (M + 31) / 32;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  if (C % 8) return cudaErrorInvalidValue;  // bulk copies of whole rows: 16-byte multiples
+  const size_t smem = static_cast<size_t>(2) * C * sizeof(float) + static_cast<size_t>(8) * LNB_STAGES * 2 * C * 2 + 8 * LNB_STAGES * 8;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
   if (C <= 8 * 32 * 2)
     layernorm_bwd_kernel<2><<<blocks, 256, smem, s>>>(x, dy, gamma, add, dx, dgamma, dbeta, M, C, eps);
   else
