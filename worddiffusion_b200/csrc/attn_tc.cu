@@ -60,7 +60,7 @@ struct ATCfg {
 struct AttnTcArgs {
   __nv_bfloat16* out;
   int out_ld;
-  int Sq, Skv, heads;
+  int Sq, Skv, heads, batch;
   float sl2;  // scale * log2(e)
 };
 
@@ -113,12 +113,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   uint64_t* p_empty = p_full + 1;
   uint64_t* q_full = p_empty + 1;
   uint64_t* o_full = q_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* q_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (AT_BM * MT), h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (a.Skv + AT_BK - 1) / AT_BK;
-  const int c_head = h * AT_DH;
+  // PERSISTENT: the CTA walks work items (query tile, head, sample) = blockIdx.x, + gridDim.x, ... (query tile fastest: concurrent
+  // CTAs share a (head, sample)'s K / V through L2).  Every barrier parity runs on counters that continue across items, so the
+  // producer loads the next item's Q (as soon as the last QK^T of the current one has retired: q_empty) and K / V tiles, and the
+  // MMA thread issues its first QK^T, while the softmax warps are still in the current item's last tiles and output epilogue --
+  // a non-persistent CTA spent ~4 us on start-up and tear-down, half the time of a 256-key self-attention item.
+  const int q_tiles = (a.Sq + AT_BM * MT - 1) / (AT_BM * MT);
+  const int total_items = q_tiles * a.heads * a.batch;
+  auto item_coords = [&](int item, int* q0_, int* c_head_, int* b_) {
+    const int qt = item % q_tiles, hb = item / q_tiles;
+    *q0_ = qt * (AT_BM * MT);
+    *c_head_ = (hb % a.heads) * AT_DH;
+    *b_ = hb / a.heads;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapQ);
@@ -136,6 +148,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     mbar_init(p_empty, 1);
     mbar_init(q_full, 1);
     mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -149,23 +162,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, MT * AT_QT_BYTES);
+      int wg = 0;  // ring unit counter over all items
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        int q0, c_head, b;
+        item_coords(item, &q0, &c_head, &b);
+        mbar_wait(q_empty, (it & 1) ^ 1);  // the previous item's last QK^T has read sQ (passes at once for the first item)
+        mbar_arrive_expect_tx(q_full, MT * AT_QT_BYTES);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        tma_load_3d(sQ + mt * AT_QT_BYTES, &mapQ, q_full, c_head, q0 + mt * AT_BM, b);
-        tma_load_3d(sQ + mt * AT_QT_BYTES + AT_BM * 128, &mapQ, q_full, c_head + 64, q0 + mt * AT_BM, b);
-      }
-      const int units = 2 * ntiles;  // K(0), V(0), K(1), V(1), ...
-      for (int w = 0; w < units; ++w) {
-        const int sl = w % NS;
-        const bool is_v = (w & 1) != 0;
-        const int j = w >> 1;
-        mbar_wait(&u_empty[sl], ((w / NS) & 1) ^ 1);
-        uint8_t* dst = sRing + sl * AT_SLOT_BYTES;
-        mbar_arrive_expect_tx(&u_full[sl], AT_SLOT_BYTES);
-        const CUtensorMap* mp = is_v ? &mapV : &mapK;
-        tma_load_3d(dst, mp, &u_full[sl], c_head, j * AT_BK, b);
-        tma_load_3d(dst + AT_KV_BOX, mp, &u_full[sl], c_head + 64, j * AT_BK, b);
+        for (int mt = 0; mt < MT; ++mt) {
+          tma_load_3d(sQ + mt * AT_QT_BYTES, &mapQ, q_full, c_head, q0 + mt * AT_BM, b);
+          tma_load_3d(sQ + mt * AT_QT_BYTES + AT_BM * 128, &mapQ, q_full, c_head + 64, q0 + mt * AT_BM, b);
+        }
+        const int units = 2 * ntiles;  // K(0), V(0), K(1), V(1), ...
+        for (int w = 0; w < units; ++w, ++wg) {
+          const int sl = wg % NS;
+          const bool is_v = (w & 1) != 0;
+          const int j = w >> 1;
+          mbar_wait(&u_empty[sl], ((wg / NS) & 1) ^ 1);
+          uint8_t* dst = sRing + sl * AT_SLOT_BYTES;
+          mbar_arrive_expect_tx(&u_full[sl], AT_SLOT_BYTES);
+          const CUtensorMap* mp = is_v ? &mapV : &mapK;
+          tma_load_3d(dst, mp, &u_full[sl], c_head, j * AT_BK, b);
+          tma_load_3d(dst + AT_KV_BOX, mp, &u_full[sl], c_head + 64, j * AT_BK, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -173,49 +193,56 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16_f32(AT_BM, AT_BK);
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(AT_BM, AT_DH) | (1u << 16);  // B (= V) is MN-major
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      // S(j) = Q K(j)^T into score buffer j & 1 from ring unit 2 j
-      auto issue_qk = [&](int j) {
-        const int buf = j & 1, w = 2 * j, sl = w % NS;
-        mbar_wait(&u_full[sl], (w / NS) & 1);
-        mbar_wait(&s_empty[buf], ((j >> 1) & 1) ^ 1);
+      int jg0 = 0;  // key-tile counter over all items (score buffer, P tile and ring parities)
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it, jg0 += ntiles) {
+        mbar_wait(q_full, it & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sRing + sl * AT_SLOT_BYTES);
-        const uint64_t k_desc0 = make_smem_desc_sw128(k_addr);
-        const uint64_t k_desc1 = make_smem_desc_sw128(k_addr + AT_KV_BOX);
+        // S(j) = Q K(j)^T into score buffer (jg0 + j) & 1 from ring unit 2 (jg0 + j)
+        auto issue_qk = [&](int j) {
+          const int jg = jg0 + j;
+          const int buf = jg & 1, w = 2 * jg, sl = w % NS;
+          mbar_wait(&u_full[sl], (w / NS) & 1);
+          mbar_wait(&s_empty[buf], ((jg >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sRing + sl * AT_SLOT_BYTES);
+          const uint64_t k_desc0 = make_smem_desc_sw128(k_addr);
+          const uint64_t k_desc1 = make_smem_desc_sw128(k_addr + AT_KV_BOX);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES));
-          const uint64_t q_desc1 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES + AT_BM * 128));
-          const uint32_t d_tmem = tmem_base + (2 * mt + buf) * AT_BK;
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES));
+            const uint64_t q_desc1 = make_smem_desc_sw128(smem_u32(sQ + mt * AT_QT_BYTES + AT_BM * 128));
+            const uint32_t d_tmem = tmem_base + (2 * mt + buf) * AT_BK;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, q_desc0 + 2 * k, k_desc0 + 2 * k, idesc_qk, k != 0);
-          umma_f16_ss(d_tmem, q_desc1, k_desc1, idesc_qk, 1u);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, q_desc0 + 2 * k, k_desc0 + 2 * k, idesc_qk, k != 0);
+            umma_f16_ss(d_tmem, q_desc1, k_desc1, idesc_qk, 1u);
+          }
+          umma_commit(&s_full[buf]);
+          umma_commit(&u_empty[sl]);  // the K tile is free once these MMAs retire
+          if (j == ntiles - 1) umma_commit(q_empty);  // ... and so is sQ after the item's last QK^T
+        };
+        // S(j+1) is issued ahead of P(j) V(j)
+        issue_qk(0);
+        for (int j = 0; j < ntiles; ++j) {
+          if (j + 1 < ntiles) issue_qk(j + 1);
+          const int jg = jg0 + j;
+          const int wv = 2 * jg + 1, sl = wv % NS;
+          mbar_wait(&u_full[sl], (wv / NS) & 1);
+          mbar_wait(p_full, jg & 1);  // P(j) is written -- and the softmax warps are done rescaling O / reading the previous item's O
+          tc_fence_after();
+          const uint64_t v_desc = at_desc_mn_sw128(smem_u32(sRing + sl * AT_SLOT_BYTES));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP + mt * AT_PT_BYTES));
+#pragma unroll
+            for (int k = 0; k < AT_BK / 16; ++k)
+              umma_f16_ss(tmem_base + C::O_COL + mt * AT_DH, p_desc + 2 * k, v_desc + 128 * k, idesc_pv, (j | k) != 0);
+          }
+          umma_commit(&u_empty[sl]);
+          umma_commit(p_empty);
         }
-        umma_commit(&s_full[buf]);
-        umma_commit(&u_empty[sl]);  // the K tile is free once these MMAs retire
-      };
-      // S(j+1) is issued ahead of P(j) V(j)
-      issue_qk(0);
-      for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_qk(j + 1);
-        const int wv = 2 * j + 1, sl = wv % NS;
-        mbar_wait(&u_full[sl], (wv / NS) & 1);
-        mbar_wait(p_full, j & 1);  // P(j) is written -- and the softmax warps are done rescaling O
-        tc_fence_after();
-        const uint64_t v_desc = at_desc_mn_sw128(smem_u32(sRing + sl * AT_SLOT_BYTES));
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP + mt * AT_PT_BYTES));
-#pragma unroll
-          for (int k = 0; k < AT_BK / 16; ++k)
-            umma_f16_ss(tmem_base + C::O_COL + mt * AT_DH, p_desc + 2 * k, v_desc + 128 * k, idesc_pv, (j | k) != 0);
-        }
-        umma_commit(&u_empty[sl]);
-        umma_commit(p_empty);
+        umma_commit(o_full);
       }
-      umma_commit(o_full);
     }
   } else {
     // =========================== softmax warps (one query row per thread) ===========================
@@ -227,13 +254,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     // exceeds it by more than 2^8 in the exponent; then this warp rescales its 32 rows of O in TMEM (and l) before P(j) is
     // published -- PV(j-1) has retired by then (p_empty) and PV(j) is not issued before every warp's P(j) arrival.  With
     // bounded score ranges that happens on the first tiles only, and O / l is exact whatever m was used. ----
-    float m_used = -INFINITY, l = 0.f;
     uint8_t* const prow = sP + mt * AT_PT_BYTES + row * 128;
     const uint32_t o_addr = tmem_base + t_lane + C::O_COL + mt * AT_DH;
     const bool ragged = (a.Skv % AT_BK) != 0;
+    int jg0 = 0, it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it, jg0 += ntiles) {
+    int q0, c_head, b;
+    item_coords(item, &q0, &c_head, &b);
+    float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < ntiles; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      const int jg = jg0 + j;
+      const int buf = jg & 1;
+      mbar_wait(&s_full[buf], (jg >> 1) & 1);
       tc_fence_after();
       uint32_t v[64];
       {
@@ -269,7 +301,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       } else {
         const bool need = (tm - m_used) * a.sl2 > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(p_empty, (j - 1) & 1);  // PV(j-1) has retired: O holds tiles 0 .. j-1
+          mbar_wait(p_empty, (jg - 1) & 1);  // PV(j-1) has retired: O holds tiles 0 .. j-1
           waited = true;
           tc_fence_after();
           float f = 1.0f;
@@ -313,7 +345,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       if (mask) exps(std::true_type{});
       else exps(std::false_type{});
       l += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
-      if (j > 0 && !waited) mbar_wait(p_empty, (j - 1) & 1);  // P(j-1) V(j-1) has read the tile
+      if (jg > 0 && !waited) mbar_wait(p_empty, (jg - 1) & 1);  // P(j-1) V(j-1) (of the previous item when j == 0) has read the tile
       // K-major SWIZZLE_128B: 16-byte chunk c16 of row r lives at chunk (c16 ^ (r & 7))
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16)
@@ -323,7 +355,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- O / l -> bf16 -> global ----
-    mbar_wait(o_full, 0);
+    mbar_wait(o_full, it & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     const int q = q0 + mt * AT_BM + row;
@@ -347,6 +379,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         reinterpret_cast<uint4*>(orow + cb * 16)[1] = o1;
       }
     }
+    // PV(next item, tile 0) overwrites O: it is issued only after this warp's P arrival for that tile, i.e. after the loads above
+    tc_fence_before();
+    }  // items
   }
 
   tc_fence_before();
@@ -395,12 +430,20 @@ bool attn_tc_try_launch(const AttnFlashArgs& a, int B, cudaStream_t s, cudaError
     *err = cudaErrorInvalidValue;
     return true;
   }
-  AttnTcArgs ta{a.out, a.out_ld, a.Sq, a.Skv, a.heads, a.scale * 1.4426950408889634f};
-  if (two)
-    *err = launch_pdl(attn_tc_kernel<2>, dim3(a.Sq / (2 * AT_BM), a.heads, B), dim3(ATCfg<2>::THREADS), ATCfg<2>::SMEM_BYTES, s, mq, mk, mv, ta);
-  else
-    *err = launch_pdl(attn_tc_kernel<1>, dim3((a.Sq + AT_BM - 1) / AT_BM, a.heads, B), dim3(ATCfg<1>::THREADS), ATCfg<1>::SMEM_BYTES, s, mq, mk,
+  AttnTcArgs ta{a.out, a.out_ld, a.Sq, a.Skv, a.heads, B, a.scale * 1.4426950408889634f};
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  if (two) {
+    const int items = (a.Sq / (2 * AT_BM)) * a.heads * B;
+    *err = launch_pdl(attn_tc_kernel<2>, dim3(items < sms ? items : sms), dim3(ATCfg<2>::THREADS), ATCfg<2>::SMEM_BYTES, s, mq, mk, mv, ta);
+  } else {
+    const int items = ((a.Sq + AT_BM - 1) / AT_BM) * a.heads * B;
+    *err = launch_pdl(attn_tc_kernel<1>, dim3(items < 2 * sms ? items : 2 * sms), dim3(ATCfg<1>::THREADS), ATCfg<1>::SMEM_BYTES, s, mq, mk,
                       mv, ta);
+  }
   return true;
 }
 

@@ -898,11 +898,15 @@ struct Epi {
   float att_scale = 0.f;
 };
 
-static bool out_head_enabled() {  // env WD_OUT_HEAD (default on): out GroupNorm + conv_out + sampler update as one kernel
+// env WD_OUT_HEAD=1: out GroupNorm + conv_out + sampler update as ONE kernel (ops.cu out_head_kernel).  Default OFF: measured
+// neutral at batch 32 / 256 (the two launches it replaces overlap their neighbours through PDL; its own body is bound by the
+// legacy HMMA rate) and slower at batch 1 (one CTA per sample: 0.778 vs 0.720 ms per step); and the choice must not depend on
+// the batch size, because the two forms sum in different orders and batch invariance is bit-exact (tests/test_gpu_model.py).
+static bool out_head_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WD_OUT_HEAD");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? (atoi(e) != 0) : 0;
   }
   return v != 0;
 }
@@ -1710,9 +1714,7 @@ struct PlanBuilder {
       if (!run_block(blk, {h, skip})) return false;
     }
     // out: GN + SiLU + conv_out + sampler update as ONE kernel with the sample's image in shared memory (ops.cuh: OutHeadArgs)
-    // (one CTA per sample: below ~64 latents the grid leaves the GPU empty and the kernel's serial phases show -- batch 1: 0.778 vs
-    //  0.720 ms per step with the two-launch form; batch 32 and 256: equal -- so small batches keep the two launches)
-    if (out_head_enabled() && B >= 64 && h.f16 && h.pslots > 0 && h.C % 32 == 0 && c.out_channels == 4 && out_head_supported(h.H, h.W, h.C)) {
+    if (out_head_enabled() && h.f16 && h.pslots > 0 && h.C % 32 == 0 && c.out_channels == 4 && out_head_supported(h.H, h.W, h.C)) {
       Op op;
       memset(&op, 0, sizeof(op));
       op.kind = OP_OUTHEAD;
