@@ -127,6 +127,10 @@ struct STL {
 struct SampL {
   int C = 0;
   GemmW conv;
+  // Upsample only: sub-pixel weights [4 phases][C][4 taps][C] (GemmArgs::up_phase) folded from the fp32 copy at finalize
+  bf16* w_phase = nullptr;
+  float* raw_w = nullptr;
+  int as_f16 = 0;
 };
 enum LayerKind { L_CONVIN, L_RES, L_ST, L_DOWN, L_UP };
 struct Layer {
@@ -459,11 +463,16 @@ struct Builder {
     return static_cast<int>(e->st.size()) - 1;
   }
 
-  int add_samp(const std::string& pfx, int C) {
+  int add_samp(const std::string& pfx, int C, bool upsample = false) {
     SampL s;
     s.C = C;
     s.conv = conv3(pfx, C, C, 0, 1);  // Down/Upsample convs read residual-stream (fp16) tensors
     slot(pfx + ".bias", S_VEC, s.conv.bias, C);
+    if (upsample) {
+      s.w_phase = A.alloc<bf16>(static_cast<size_t>(4) * C * 4 * C);
+      s.raw_w = raw_copy(pfx + ".weight", static_cast<int64_t>(C) * C * 9);
+      s.as_f16 = 1;
+    }
     e->samp.push_back(s);
     return static_cast<int>(e->samp.size()) - 1;
   }
@@ -593,7 +602,7 @@ struct Builder {
           b.push_back(Layer{L_ST, add_st(pfx + std::to_string(li++) + ".", ch, heads, dh)});
         }
         if (level && i == c.num_res_blocks) {
-          b.push_back(Layer{L_UP, add_samp(pfx + std::to_string(li++) + ".conv", ch)});
+          b.push_back(Layer{L_UP, add_samp(pfx + std::to_string(li++) + ".conv", ch, true)});
           ds /= 2;
         }
         e->output_blocks.push_back(b);
@@ -825,6 +834,8 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
       if (rc != WD_OK) return rc;
     }
   }
+  for (auto& sp : e->samp)
+    if (sp.w_phase && sp.raw_w) CUDA_TRY(upconv_phase_fold_launch(sp.raw_w, sp.w_phase, sp.C, sp.C, sp.as_f16, s));
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
   for (auto& st : e->st)
@@ -889,6 +900,7 @@ struct Epi {
   const float* ln_stats = nullptr;  // A is an un-normalised tensor with these row statistics (weights carry gamma, see GemmW::ln_s)
   int ln_dim = 0;
   Act* stats_for = nullptr;  // output tensor whose GroupNorm partials the epilogue should write (if it can)
+  int up_phase = 0;  // sub-pixel phase of "upsample, then conv3x3" (GemmArgs::up_phase): `out` = the [B, 2H, 2W, C] tensor
   const NormW* gn_apply = nullptr;  // producer-side GroupNorm + SiLU (GemmArgs::gn_apply): `out` receives the normalised tensor
   float gn_eps = 1e-5f;
   int epi = EPI_STD;
@@ -897,6 +909,15 @@ struct Epi {
   int att_ld = 0, att_voff = 0, att_L = 0;
   float att_scale = 0.f;
 };
+
+static bool up_phase_enabled() {  // env WD_UP_PHASE (default on): Upsample + conv3x3 as four sub-pixel 2 x 2 convolutions
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WD_UP_PHASE");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 
 // env WD_OUT_HEAD=1: out GroupNorm + conv_out + sampler update as ONE kernel (ops.cu out_head_kernel).  Default OFF: measured
 // neutral at batch 32 / 256 (the two launches it replaces overlap their neighbours through PDL; its own body is bound by the
@@ -1004,6 +1025,16 @@ struct PlanBuilder {
       a.gn_partial = ep.stats_for->stats;
       a.gn_cpg = 10;
       ep.stats_for->pslots = ep.rows_per_sample / 32;
+      if (ep.up_phase) {  // the phase grid's rows are a quarter of the output sample: 4 phases x (H W / 32) slots
+        a.gn_nslot = 4 * (ep.rows_per_sample / 32);
+        a.gn_slot_base = (ep.up_phase - 1) * (ep.rows_per_sample / 32);
+        ep.stats_for->pslots = a.gn_nslot;
+      }
+    }
+    a.up_phase = ep.up_phase;
+    if (ep.up_phase && (!conv || srcs.size() != 1 || srcs[0].taps != 4 || GEMM_BLOCK_M % (Hout * Wout) || !a.gn_partial)) {
+      err = "gemm: the sub-pixel upsample conv needs one 4-tap source, whole images per tile and epilogue statistics";
+      return false;
     }
     if (ep.gn_apply) {
       if (!a.gn_partial || ep.gn_apply->C != w.N) { err = "gemm: producer-side GroupNorm needs epilogue statistics"; return false; }
@@ -1063,8 +1094,16 @@ struct PlanBuilder {
       }
       op.gemm.mapOut = op.gemm.mapB;
       op.gemm.mapRes = op.gemm.mapB;
-      if (ep.epi != EPI_SAMPLER && !ep.out_f32 &&
-          !tmap_encode_out_bf16(&op.gemm.mapOut, ep.out, ep.geglu ? w.N / 2 : w.N, M, ep.out_ld)) {
+      if (ep.up_phase) {
+        // phase (a, b) starts at pixel (a, b) of every [2H, 2W] image and steps two pixels / two rows
+        const int pa = (ep.up_phase - 1) >> 1, pb = (ep.up_phase - 1) & 1;
+        const bf16* base = static_cast<const bf16*>(ep.out) + (static_cast<size_t>(pa) * 2 * Wout + pb) * w.N;
+        if (ep.out_ld != w.N || !tmap_encode_out_phase_bf16(&op.gemm.mapOut, base, w.N, Wout, Hout, B)) {
+          err = "cuTensorMapEncodeTiled failed (out phase)";
+          return false;
+        }
+      } else if (ep.epi != EPI_SAMPLER && !ep.out_f32 &&
+                 !tmap_encode_out_bf16(&op.gemm.mapOut, ep.out, ep.geglu ? w.N / 2 : w.N, M, ep.out_ld)) {
         err = "cuTensorMapEncodeTiled failed (out)";
         return false;
       }
@@ -1676,6 +1715,29 @@ struct PlanBuilder {
           case L_UP: {
             const Act& x = in[0];
             if (!x.f16) { err = "upsample expects an fp16 residual-stream input"; return false; }
+            const SampL& sp = e->samp[l.idx];
+            if (up_phase_enabled() && sp.w_phase && GEMM_BLOCK_M % (x.H * x.W) == 0 && epilogue_stats_ok(x.H * x.W, x.C) &&
+                (4 * x.H * x.W) / 32 <= 8) {
+              // sub-pixel form (GemmArgs::up_phase): four 2 x 2 convolutions of the H x W input, one per output phase, 9/4 fewer
+              // MACs than the 3 x 3 conv on the upsampled tensor, which is never materialised
+              out = new_act(x.H * 2, x.W * 2, x.C, true);
+              for (int ph = 0; ph < 4; ++ph) {
+                GemmW wp = sp.conv;
+                wp.w = sp.w_phase + static_cast<size_t>(ph) * x.C * 4 * x.C;
+                wp.K = 4 * x.C;
+                Epi ep;
+                ep.out = out.p;
+                ep.out_ld = x.C;
+                ep.out_f16 = 1;
+                ep.rows_per_sample = x.H * x.W;
+                ep.stats_for = &out;
+                ep.up_phase = ph + 1;
+                if (!gemm_op(sops, B * x.H * x.W, true, x.H, x.W, {ASrc{x.p, x.C, x.C, 4, 1, x.H, x.W, true}}, wp, ep)) return false;
+                // algorithmic work = the reference's 3 x 3 conv on the upsampled tensor (a quarter of it per phase); 4/9 of it is executed
+                if (!dry) sops.back().flops = 2.0 * B * x.H * x.W * x.C * 9.0 * x.C;
+              }
+              break;
+            }
             Act up = new_act(x.H * 2, x.W * 2, x.C, true);  // 16-bit copy, format-agnostic
             Op op;
             memset(&op, 0, sizeof(op));

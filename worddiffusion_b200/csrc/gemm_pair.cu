@@ -159,8 +159,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int chunks = args.chunks[s];
           const int st = args.stride[s];
           for (int tap = 0; tap < taps; ++tap) {
-            const int dy = (taps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (taps == 9) ? tap % 3 - 1 : 0;
+            const int up_a = (args.up_phase - 1) >> 1, up_b = (args.up_phase - 1) & 1;
+            const int dy = (taps == 9) ? tap / 3 - 1 : (taps == 4 ? (tap >> 1) - 1 + up_a : 0);
+            const int dx = (taps == 9) ? tap % 3 - 1 : (taps == 4 ? (tap & 1) - 1 + up_b : 0);
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's full barrier
@@ -520,8 +521,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               const int mw = m0 + q * 32;
               if (mw < args.M && lane < 16) {
                 const int smp = mw / args.rows_per_sample;
-                const int slot = (mw % args.rows_per_sample) >> 5;
-                const int nslot = args.rows_per_sample >> 5;
+                const int slot = args.gn_slot_base + ((mw % args.rows_per_sample) >> 5);
+                const int nslot = args.gn_nslot ? args.gn_nslot : args.rows_per_sample >> 5;
                 const int G = args.N / 10;
                 const int g = (nb / 10) + (lane >> 1);
                 args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
@@ -537,8 +538,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (leader_warp && elect_one()) {
             if (!args.geglu) {
               const int oc0 = n0 + half * 160 + rnd * 80;
-              tma_store_2d_keep(&mapOut, stg_half, oc0, m0, (args.dbg & 64) != 0);
-              tma_store_2d_keep(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0, (args.dbg & 64) != 0);
+              if (args.up_phase) {  // sub-pixel phase: (c, x, y, n) of the phase grid; this CTA's 128 rows hold whole images
+                tma_store_4d(&mapOut, stg_half, oc0, 0, 0, m0 / args.HWout);
+                tma_store_4d(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, 0, 0, m0 / args.HWout);
+              } else {
+                tma_store_2d_keep(&mapOut, stg_half, oc0, m0, (args.dbg & 64) != 0);
+                tma_store_2d_keep(&mapOut, stg_half + PAIR_SUB_BYTES, oc0 + GEMM_SUB_N, m0, (args.dbg & 64) != 0);
+              }
             } else {
               tma_store_2d_keep(&mapOut, stg_half, n_tile * 160 + half * 80 + rnd * 40, m0, (args.dbg & 64) != 0);
             }
@@ -572,6 +578,9 @@ bool gemm_pair_supported(const GemmArgs& a) {
   if (a.ln_out || a.ln_stats) return false;  // LayerNorm folding lives in the single-CTA kernel (K = 320 GEMMs)
   if (a.geglu) return false;  // the kernel implements it (value | gate per 320-column tile) but the weights are packed for 160-column tiles
   if (a.out_f32 && a.residual) return false;
+  if (a.up_phase && (a.gn_apply || a.residual || a.out_f32 || a.geglu || a.num_src != 1 || a.taps[0] != 4 || !a.conv || a.HWout <= 0 ||
+                     GEMM_BLOCK_M % a.HWout))
+    return false;
   if (a.gn_apply && (a.N != PAIR_BN || !a.gn_partial || a.gn_cpg != 10 || !a.gn_gamma || !a.gn_beta || a.residual || a.out_f32 ||
                      a.act != ACT_NONE || a.rows_per_sample % 32 || 256 % a.rows_per_sample))
     return false;

@@ -149,8 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const int chunks = args.chunks[s];
           const int st = args.stride[s];
           for (int tap = 0; tap < taps; ++tap) {
-            const int dy = (taps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (taps == 9) ? tap % 3 - 1 : 0;
+            const int up_a = (args.up_phase - 1) >> 1, up_b = (args.up_phase - 1) & 1;
+            const int dy = (taps == 9) ? tap / 3 - 1 : (taps == 4 ? (tap >> 1) - 1 + up_a : 0);
+            const int dx = (taps == 9) ? tap % 3 - 1 : (taps == 4 ? (tap & 1) - 1 + up_b : 0);
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full_bar[stage],
@@ -622,8 +623,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const int mw = m0 + q * 32;
               if (mw < args.M && lane < 16) {
                 const int smp = mw / args.rows_per_sample;
-                const int slot = (mw % args.rows_per_sample) >> 5;
-                const int nslot = args.rows_per_sample >> 5;
+                const int slot = args.gn_slot_base + ((mw % args.rows_per_sample) >> 5);
+                const int nslot = args.gn_nslot ? args.gn_nslot : args.rows_per_sample >> 5;
                 const int G = args.N / 10;
                 const int g = n_tile * (BN / 10) + half * (HC / 10) + (lane >> 1);
                 args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
@@ -642,8 +643,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint8_t* src = stg_half + sb * C::HALF_STG_BYTES;
             if (!args.geglu) {
 #pragma unroll
-              for (int s = 0; s < NSUB; ++s)
-                tma_store_2d_keep(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0, (args.dbg & 64) != 0);
+              for (int s = 0; s < NSUB; ++s) {
+                if (args.up_phase)  // sub-pixel phase: (c, x, y, n) of the phase grid; the tile holds whole images
+                  tma_store_4d(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, 0, 0, m0 / args.HWout);
+                else
+                  tma_store_2d_keep(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0, (args.dbg & 64) != 0);
+              }
             } else {
               tma_store_2d_keep(&mapOut, src, n_tile * HC + half * 40, m0, (args.dbg & 64) != 0);
             }
@@ -718,6 +723,21 @@ bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(4d) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
+bool tmap_encode_out_phase_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn || W * H == 0 || GEMM_BLOCK_M % (W * H)) return false;
+  cuuint64_t dims[4] = {C, W, H, N};
+  // the phase grid steps two pixels / two rows of the [N, 2H, 2W, C] tensor
+  cuuint64_t strides[3] = {2 * C * 2, 2 * (2 * W) * C * 2, (2 * H) * (2 * W) * C * 2};
+  cuuint32_t box[4] = {GEMM_SUB_N, static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(H), static_cast<cuuint32_t>(GEMM_BLOCK_M / (W * H))};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(out phase) failed: %d\n", (int)r);
   return r == CUDA_SUCCESS;
 }
 

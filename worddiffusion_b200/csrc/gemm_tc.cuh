@@ -119,6 +119,14 @@ struct GemmArgs {
   // warps of the pair have published their partials (gn_partial, exchanged through L2 behind a cluster-scope mbarrier).
   // The values wait as fp16 (what the separate GroupNorm kernel used to read): round 0 in the staging tile, round 1 in registers.
   int gn_apply;
+  // Sub-pixel form of "nearest 2x upsample, then conv3x3" (unet.py:497-499): output phase (a, b) = (up_phase - 1) >> 1, & 1 of the
+  // 2H x 2W image is a 2 x 2 convolution of the H x W input with the taps that hit the same input pixel summed into one weight
+  // (9/4 fewer MACs, no upsampled tensor).  taps[0] == 4: tap t reads input offset (dy, dx) = ((t >> 1) - 1 + a, (t & 1) - 1 + b);
+  // the tile is stored through a 4-D output map (c, x, y, n) whose strides step two pixels; the GroupNorm partials of the
+  // 2H x 2W output go to slot gn_slot_base + (row-in-phase >> 5) of gn_nslot.  0: off.  Needs 128 % (H W) == 0.
+  int up_phase;
+  int gn_slot_base;
+  int gn_nslot;
   int tail_split;  // pair kernel: cut the tiles of a last, at most half-full round into 160-column halves (set by gemm_pair_launch)
   const float* gn_gamma;  // [N]
   const float* gn_beta;   // [N]
@@ -157,6 +165,9 @@ bool tmap_encode_4d_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t 
 // 3-D (inner, rows, batch) map with a {box_inner, box_rows, 1} SWIZZLE_128B box (attention operands, per-sample fold operands)
 bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride_elems,
                          uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows);
+// output map of one sub-pixel phase (GemmArgs::up_phase): dims (C, W, H, N) of the PHASE grid over a [N, 2H, 2W, C] tensor whose
+// base already points at the phase's first pixel; box {GEMM_SUB_N, W, H, 128 / (W H)}, no swizzle
+bool tmap_encode_out_phase_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N);
 // output / residual tensor map of the staging sub-tiles
 bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems);
 cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);

@@ -1162,6 +1162,40 @@ cudaError_t out_head_launch(const OutHeadArgs& a, cudaStream_t s) {
 }
 
 // =====================================================================================================
+// sub-pixel weights of upsample + conv3x3 (ops.cuh)
+// =====================================================================================================
+__global__ void upconv_phase_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int as_f16) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(4) * Cout * 4 * Cin;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cin);
+  size_t r = idx / Cin;
+  const int t = static_cast<int>(r % 4);
+  r /= 4;
+  const int n = static_cast<int>(r % Cout);
+  const int ph = static_cast<int>(r / Cout);
+  const int a = ph >> 1, b = ph & 1, ty = t >> 1, tx = t & 1;
+  // 3x3 taps that read input row (ty - 1 + a): a = 0: ty = 0 <- {0}, ty = 1 <- {1, 2};  a = 1: ty = 0 <- {0, 1}, ty = 1 <- {2}
+  const int ky0 = a == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = a == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+  const int kx0 = b == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = b == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+  const float* wn = w + (static_cast<size_t>(n) * Cin + c) * 9;
+  float acc = 0.f;
+  for (int ky = ky0; ky <= ky1; ++ky)
+    for (int kx = kx0; kx <= kx1; ++kx) acc += wn[ky * 3 + kx];
+  if (as_f16) {
+    const __half h = __float2half_rn(acc);
+    dst[idx] = *reinterpret_cast<const __nv_bfloat16*>(&h);
+  } else {
+    dst[idx] = __float2bfloat16(acc);
+  }
+}
+cudaError_t upconv_phase_fold_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int as_f16, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(4) * Cout * 4 * Cin;
+  upconv_phase_fold_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w, dst, Cout, Cin, as_f16);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
 // weight repacking
 // =====================================================================================================
 WD_DEVINL int geglu_perm(int n, int N, int bn) {

@@ -141,6 +141,12 @@ cudaError_t out_head_launch(const OutHeadArgs& a, cudaStream_t s);
 // ---------------- nearest 2x upsample NHWC bf16 (unet.py:497) ----------------
 cudaError_t upsample2x_launch(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
 
+// ---------------- sub-pixel weights of "nearest 2x upsample, then conv3x3" (GemmArgs::up_phase) ----------------
+// w [Cout, Cin, 3, 3] fp32 -> dst [4 phases][Cout][4 taps][Cin] (bf16, or fp16 bit patterns when as_f16): phase (a, b), tap
+// (ty, tx) holds the sum of the 3x3 taps (ky, kx) that read input pixel (ty - 1 + a, tx - 1 + b): rows a = 0: {0}, {1, 2};
+// a = 1: {0, 1}, {2} (same for the columns), summed in fp32 and rounded once.
+cudaError_t upconv_phase_fold_launch(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int as_f16, cudaStream_t s);
+
 // ---------------- weight repacking (fp32 state_dict tensors -> packed bf16 / fp32 layouts) ----------------
 // conv3x3 weight [Cout, Cin, 3, 3] -> dst[n, k_off + tap*Cin + c]   (row stride ldk); as_f16: store fp16 bit patterns
 // (weight columns that multiply an fp16 A source, see GemmArgs::a_f16)
