@@ -175,6 +175,12 @@ WD_DEVINL void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+WD_DEVINL void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 // same with an L2 evict_last cache hint when `keep` (experiment WD_GEMM_DBG & 64: keep a GEMM's output in L2 for its consumer)
 WD_DEVINL void tma_store_2d_keep(const CUtensorMap* m, const void* smem_src, int c0, int c1, bool keep) {
   if (keep) {

@@ -130,6 +130,7 @@ struct SampL {
   // Upsample only: sub-pixel weights [4 phases][C][4 taps][C] (GemmArgs::up_phase) folded from the fp32 copy at finalize
   bf16* w_phase = nullptr;
   float* raw_w = nullptr;
+  float* bias4 = nullptr;  // the bias once per phase ([4 C]: all phases in one launch, GemmArgs::up_phase == 5)
   int as_f16 = 0;
 };
 enum LayerKind { L_CONVIN, L_RES, L_ST, L_DOWN, L_UP };
@@ -471,6 +472,7 @@ struct Builder {
     if (upsample) {
       s.w_phase = A.alloc<bf16>(static_cast<size_t>(4) * C * 4 * C);
       s.raw_w = raw_copy(pfx + ".weight", static_cast<int64_t>(C) * C * 9);
+      s.bias4 = A.alloc<float>(static_cast<size_t>(4) * C);
       s.as_f16 = 1;
     }
     e->samp.push_back(s);
@@ -835,7 +837,11 @@ extern "C" int wd_engine_finalize_params(wd_engine* e, void* stream) {
     }
   }
   for (auto& sp : e->samp)
-    if (sp.w_phase && sp.raw_w) CUDA_TRY(upconv_phase_fold_launch(sp.raw_w, sp.w_phase, sp.C, sp.C, sp.as_f16, s));
+    if (sp.w_phase && sp.raw_w) {
+      CUDA_TRY(upconv_phase_fold_launch(sp.raw_w, sp.w_phase, sp.C, sp.C, sp.as_f16, s));
+      for (int ph = 0; ph < 4; ++ph)
+        CUDA_TRY(cudaMemcpyAsync(sp.bias4 + ph * sp.C, sp.conv.bias, static_cast<size_t>(sp.C) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
   for (auto& f : e->ln_folds)
     CUDA_TRY(fold_ln_linear_launch(f.raw_w, f.gamma, f.beta, f.raw_b, f.dst, f.s_out, f.b_out, f.N, f.K, f.ldk, f.n_off, f.geglu_bn, s));
   for (auto& st : e->st)
@@ -910,14 +916,17 @@ struct Epi {
   float att_scale = 0.f;
 };
 
-static bool up_phase_enabled() {  // env WD_UP_PHASE (default on): Upsample + conv3x3 as four sub-pixel 2 x 2 convolutions
+// env WD_UP_PHASE: Upsample + conv3x3 as four sub-pixel 2 x 2 convolutions.  0: off (upsample kernel + 3 x 3 conv); 1: one launch
+// per phase; 2 (default): all four phases in one launch
+static int up_phase_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WD_UP_PHASE");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? atoi(e) : 2;
   }
-  return v != 0;
+  return v;
 }
+static bool up_phase_enabled() { return up_phase_mode() != 0; }
 
 // env WD_OUT_HEAD=1: out GroupNorm + conv_out + sampler update as ONE kernel (ops.cu out_head_kernel).  Default OFF: measured
 // neutral at batch 32 / 256 (the two launches it replaces overlap their neighbours through PDL; its own body is bound by the
@@ -1021,13 +1030,14 @@ struct PlanBuilder {
     a.att_voff = ep.att_voff;
     a.att_L = ep.att_L;
     a.att_scale = ep.att_scale;
-    if (ep.stats_for && epilogue_stats_ok(ep.rows_per_sample, w.N) && ep.stats_for->C == w.N) {
+    const int n_stats = ep.up_phase == 5 ? w.N / 4 : w.N;  // (all four phases as N tiles: the output tensor has N / 4 channels)
+    if (ep.stats_for && epilogue_stats_ok(ep.rows_per_sample, n_stats) && ep.stats_for->C == n_stats) {
       a.gn_partial = ep.stats_for->stats;
       a.gn_cpg = 10;
       ep.stats_for->pslots = ep.rows_per_sample / 32;
       if (ep.up_phase) {  // the phase grid's rows are a quarter of the output sample: 4 phases x (H W / 32) slots
         a.gn_nslot = 4 * (ep.rows_per_sample / 32);
-        a.gn_slot_base = (ep.up_phase - 1) * (ep.rows_per_sample / 32);
+        a.gn_slot_base = ep.up_phase == 5 ? 0 : (ep.up_phase - 1) * (ep.rows_per_sample / 32);
         ep.stats_for->pslots = a.gn_nslot;
       }
     }
@@ -1094,7 +1104,12 @@ struct PlanBuilder {
       }
       op.gemm.mapOut = op.gemm.mapB;
       op.gemm.mapRes = op.gemm.mapB;
-      if (ep.up_phase) {
+      if (ep.up_phase == 5) {
+        if (ep.out_ld != w.N / 4 || !tmap_encode_out_phase5_bf16(&op.gemm.mapOut, ep.out, w.N / 4, Wout, Hout, B)) {
+          err = "cuTensorMapEncodeTiled failed (out phase5)";
+          return false;
+        }
+      } else if (ep.up_phase) {
         // phase (a, b) starts at pixel (a, b) of every [2H, 2W] image and steps two pixels / two rows
         const int pa = (ep.up_phase - 1) >> 1, pb = (ep.up_phase - 1) & 1;
         const bf16* base = static_cast<const bf16*>(ep.out) + (static_cast<size_t>(pa) * 2 * Wout + pb) * w.N;
@@ -1721,6 +1736,25 @@ struct PlanBuilder {
               // sub-pixel form (GemmArgs::up_phase): four 2 x 2 convolutions of the H x W input, one per output phase, 9/4 fewer
               // MACs than the 3 x 3 conv on the upsampled tensor, which is never materialised
               out = new_act(x.H * 2, x.W * 2, x.C, true);
+              if (up_phase_mode() >= 2 && GEMM_BLOCK_M % x.W == 0 && x.C == 320) {
+                // all four phases in ONE launch: the phases are N tiles of a [4 C, 4 C] weight (1 024 tiles at batch 256 instead of
+                // four launches of 256 tiles each)
+                GemmW wp = sp.conv;
+                wp.w = sp.w_phase;
+                wp.N = 4 * x.C;
+                wp.K = 4 * x.C;
+                wp.bias = sp.bias4;
+                Epi ep;
+                ep.out = out.p;
+                ep.out_ld = x.C;
+                ep.out_f16 = 1;
+                ep.rows_per_sample = x.H * x.W;
+                ep.stats_for = &out;
+                ep.up_phase = 5;
+                if (!gemm_op(sops, B * x.H * x.W, true, x.H, x.W, {ASrc{x.p, x.C, x.C, 4, 1, x.H, x.W, true}}, wp, ep)) return false;
+                sops.back().flops = 2.0 * B * 4 * x.H * x.W * x.C * 9.0 * x.C;  // the reference's conv on the upsampled tensor
+                break;
+              }
               for (int ph = 0; ph < 4; ++ph) {
                 GemmW wp = sp.conv;
                 wp.w = sp.w_phase + static_cast<size_t>(ph) * x.C * 4 * x.C;

@@ -578,6 +578,7 @@ bool gemm_pair_supported(const GemmArgs& a) {
   if (a.ln_out || a.ln_stats) return false;  // LayerNorm folding lives in the single-CTA kernel (K = 320 GEMMs)
   if (a.geglu) return false;  // the kernel implements it (value | gate per 320-column tile) but the weights are packed for 160-column tiles
   if (a.out_f32 && a.residual) return false;
+  if (a.up_phase == 5) return false;  // all phases in one launch: single-CTA kernel only
   if (a.up_phase && (a.gn_apply || a.residual || a.out_f32 || a.geglu || a.num_src != 1 || a.taps[0] != 4 || !a.conv || a.HWout <= 0 ||
                      GEMM_BLOCK_M % a.HWout))
     return false;

@@ -149,7 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const int chunks = args.chunks[s];
           const int st = args.stride[s];
           for (int tap = 0; tap < taps; ++tap) {
-            const int up_a = (args.up_phase - 1) >> 1, up_b = (args.up_phase - 1) & 1;
+            const int up_ph = args.up_phase == 5 ? n0 / 320 : args.up_phase - 1;
+            const int up_a = up_ph >> 1, up_b = up_ph & 1;
             const int dy = (taps == 9) ? tap / 3 - 1 : (taps == 4 ? (tap >> 1) - 1 + up_a : 0);
             const int dx = (taps == 9) ? tap % 3 - 1 : (taps == 4 ? (tap & 1) - 1 + up_b : 0);
             for (int ch = 0; ch < chunks; ++ch) {
@@ -623,10 +624,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const int mw = m0 + q * 32;
               if (mw < args.M && lane < 16) {
                 const int smp = mw / args.rows_per_sample;
-                const int slot = args.gn_slot_base + ((mw % args.rows_per_sample) >> 5);
+                const bool up5 = args.up_phase == 5;  // phases as N tiles: phase = n0 / 320, 32 groups per phase
+                const int slot = (up5 ? (n0 / 320) * (args.rows_per_sample >> 5) : args.gn_slot_base) + ((mw % args.rows_per_sample) >> 5);
                 const int nslot = args.gn_nslot ? args.gn_nslot : args.rows_per_sample >> 5;
-                const int G = args.N / 10;
-                const int g = n_tile * (BN / 10) + half * (HC / 10) + (lane >> 1);
+                const int G = up5 ? 32 : args.N / 10;
+                const int g = (up5 ? (n0 % 320) / 10 : n_tile * (BN / 10)) + half * (HC / 10) + (lane >> 1);
                 args.gn_partial[((static_cast<size_t>(smp) * G + g) * nslot + slot) * 2 + (lane & 1)] = tot;
               }
             }
@@ -644,7 +646,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (!args.geglu) {
 #pragma unroll
               for (int s = 0; s < NSUB; ++s) {
-                if (args.up_phase)  // sub-pixel phase: (c, x, y, n) of the phase grid; the tile holds whole images
+                if (args.up_phase == 5)  // (c, b, x, a, image-row) with the phase (a, b) = n0 / 320
+                  tma_store_5d(&mapOut, src + s * C::SUB_BYTES, n0 % 320 + half * HC + s * GEMM_SUB_N, (n0 / 320) & 1, 0, (n0 / 320) >> 1,
+                               (m0 / args.HWout) * (args.HWout / args.Wout));
+                else if (args.up_phase)  // sub-pixel phase: (c, x, y, n) of the phase grid; the tile holds whole images
                   tma_store_4d(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, 0, 0, m0 / args.HWout);
                 else
                   tma_store_2d_keep(&mapOut, src + s * C::SUB_BYTES, n0 + half * HC + s * GEMM_SUB_N, m0, (args.dbg & 64) != 0);
@@ -738,6 +743,21 @@ bool tmap_encode_out_phase_bf16(CUtensorMap* m, const void* base, uint64_t C, ui
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(out phase) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
+bool tmap_encode_out_phase5_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn || W == 0 || H == 0 || GEMM_BLOCK_M % W || GEMM_BLOCK_M % (W * H)) return false;
+  // pixel (n, 2 y + a, 2 x + b): address / (2 C bytes) = b/2 ... written as ascending strides: b: C, x: 2 C, a: 2 W C, (n H + y): 4 W C
+  cuuint64_t dims[5] = {C, 2, W, 2, N * H};
+  cuuint64_t strides[4] = {C * 2, 2 * C * 2, 2 * W * C * 2, 4 * W * C * 2};
+  cuuint32_t box[5] = {GEMM_SUB_N, 1, static_cast<cuuint32_t>(W), 1, static_cast<cuuint32_t>(GEMM_BLOCK_M / W)};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[wd_b200] cuTensorMapEncodeTiled(out phase5) failed: %d\n", (int)r);
   return r == CUDA_SUCCESS;
 }
 

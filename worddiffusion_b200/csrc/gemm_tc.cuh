@@ -124,7 +124,8 @@ struct GemmArgs {
   // (9/4 fewer MACs, no upsampled tensor).  taps[0] == 4: tap t reads input offset (dy, dx) = ((t >> 1) - 1 + a, (t & 1) - 1 + b);
   // the tile is stored through a 4-D output map (c, x, y, n) whose strides step two pixels; the GroupNorm partials of the
   // 2H x 2W output go to slot gn_slot_base + (row-in-phase >> 5) of gn_nslot.  0: off.  Needs 128 % (H W) == 0.
-  int up_phase;
+  int up_phase;  // 1..4: one phase per launch; 5: all four phases in ONE launch as N tiles (N = 4 x 320: phase = n0 / 320; single-CTA
+                 // kernel only; bias replicated per phase; 5-D output map (c, b, x, a, image-row))
   int gn_slot_base;
   int gn_nslot;
   int tail_split;  // pair kernel: cut the tiles of a last, at most half-full round into 160-column halves (set by gemm_pair_launch)
@@ -168,6 +169,8 @@ bool tmap_encode_3d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint6
 // output map of one sub-pixel phase (GemmArgs::up_phase): dims (C, W, H, N) of the PHASE grid over a [N, 2H, 2W, C] tensor whose
 // base already points at the phase's first pixel; box {GEMM_SUB_N, W, H, 128 / (W H)}, no swizzle
 bool tmap_encode_out_phase_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N);
+// all four phases behind one map: dims (C, b, W, a, N H) over the [N, 2H, 2W, C] tensor (strides ascending), box {GEMM_SUB_N, 1, W, 1, 128 / W}
+bool tmap_encode_out_phase5_bf16(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N);
 // output / residual tensor map of the staging sub-tiles
 bool tmap_encode_out_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems);
 cudaError_t gemm_tc_launch(const GemmLaunch& L, cudaStream_t stream);
