@@ -92,6 +92,12 @@ struct TcArgs {
   // out_lo != null: the result leaves as its TF32 split (out = hi, out_lo = lo) for the Linear that consumes it.
   int geglu;
   float* out_lo;
+  // Sub-pixel form of "nearest 2x upsample, then conv3x3" (unet.py:497-499): the four output phases (a, b) are N tiles of a
+  // [4 up_cout, 4 C] weight (phase = n0 / up_cout); tap t of phase (a, b) reads input offset ((t >> 1) - 1 + a, (t & 1) - 1 + b);
+  // row m = (image, y, x) of the H x W input grid is written to pixel (image, 2 y + a, 2 x + b) of the [B, 2H, 2W, up_cout] output.
+  int up;
+  int up_cout;
+  int H;
 };
 
 template <int BN>
@@ -165,7 +171,12 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
         const int kc = kb * TC_BK;
         if (args.conv) {
           const int tap = kb / cbt, cb = kb - tap * cbt;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          if (args.up) {
+            const int ph = n0 / args.up_cout;
+            dy = (tap >> 1) - 1 + (ph >> 1);
+            dx = (tap & 1) - 1 + (ph & 1);
+          }
           const bool second = cb >= args.cb1;
           const int c0 = (second ? cb - args.cb1 : cb) * TC_BK;
           tma_load_4d(s, second ? &mapA2h : &mapAh, &full_bar[stage], c0, ow0 + dx, oh0 + dy, img);
@@ -272,6 +283,25 @@ __global__ void __launch_bounds__(192, 1) f32tc_gemm_kernel(const __grid_constan
           }
           continue;
         }
+      }
+      if (args.up) {
+        if (m < args.M) {
+          const int ph = n0 / args.up_cout, nc = n0 - ph * args.up_cout;
+          const int img = m / args.HW, rem = m - img * args.HW, y = rem / args.W, x = rem - y * args.W;
+          const size_t opix = (static_cast<size_t>(img) * 2 * args.H + 2 * y + (ph >> 1)) * (2 * args.W) + 2 * x + (ph & 1);
+          float* orow_u = args.out + opix * args.up_cout + nc;
+          const float4* bias_u = args.bias ? reinterpret_cast<const float4*>(args.bias + nc) : nullptr;
+#pragma unroll
+          for (int c4 = 0; c4 < BN / 4; ++c4) {
+            float4 o = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+            if (bias_u) {
+              const float4 b = __ldg(bias_u + c4);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(orow_u + c4 * 4) = o;
+          }
+        }
+        continue;
       }
       const int sample = args.rowbias ? m / args.rows_per_sample : 0;
       float* orow = args.out + static_cast<size_t>(m) * args.N + n0;
@@ -495,6 +525,73 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
   a.residual = residual;
   a.out = out;
   a.act_silu = act_silu;
+  a.kb_per_chunk = TC_SPLIT_KB;
+  return launch_tc(mAh, mAl, mAh, mAl, mWh, mWl, a, s);
+}
+
+// fp32 sub-pixel weights: packed [Cout][9 taps][C] -> [4 phases][Cout][4 taps][C] (taps that read the same input pixel summed)
+__global__ void f32tc_upconv_fold_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int C) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(4) * Cout * 4 * C;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  size_t r = idx / C;
+  const int t = static_cast<int>(r % 4);
+  r /= 4;
+  const int n = static_cast<int>(r % Cout);
+  const int ph = static_cast<int>(r / Cout);
+  const int a = ph >> 1, b = ph & 1, ty = t >> 1, tx = t & 1;
+  const int ky0 = a == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = a == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+  const int kx0 = b == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = b == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+  float acc = 0.f;
+  for (int ky = ky0; ky <= ky1; ++ky)
+    for (int kx = kx0; kx <= kx1; ++kx) acc += w[(static_cast<size_t>(n) * 9 + ky * 3 + kx) * C + c];
+  dst[idx] = acc;
+}
+cudaError_t f32tc_upconv_fold(const float* w_packed, float* dst, int Cout, int C, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(4) * Cout * 4 * C;
+  f32tc_upconv_fold_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w_packed, dst, Cout, C);
+  return cudaGetLastError();
+}
+bool f32tc_upconv_ok(int B, int H, int W, int C, int Cout) {
+  const int bn = tc_bn_for(4 * Cout);
+  return bn != 0 && Cout % bn == 0 && f32tc_conv_ok(B, H, W, C, 0, 4 * Cout);
+}
+cudaError_t f32tc_upconv(const float* a_hi, const float* a_lo, int C, int B, int H, int W, const float* w_hi, const float* w_lo, int Cout,
+                         const float* bias, float* out, cudaStream_t s) {
+  if (!f32tc_upconv_ok(B, H, W, C, Cout)) return cudaErrorInvalidValue;
+  const int HW = H * W, K = 4 * C, N = 4 * Cout;
+  uint32_t bw = W, bh, bn;
+  if (W > TC_BM) {
+    bw = TC_BM;
+    bh = 1;
+    bn = 1;
+  } else if (HW >= TC_BM) {
+    bh = TC_BM / W;
+    bn = 1;
+  } else {
+    bh = H;
+    bn = TC_BM / HW;
+  }
+  CUtensorMap mAh, mAl, mWh, mWl;
+  if (!tmap_f32_4d(&mAh, a_hi, C, W, H, B, bw, bh, bn) || !tmap_f32_4d(&mAl, a_lo, C, W, H, B, bw, bh, bn) ||
+      !tmap_f32(&mWh, w_hi, K, N, tc_bn_for(N)) || !tmap_f32(&mWl, w_lo, K, N, tc_bn_for(N)))
+    return cudaErrorInvalidValue;
+  TcArgs a{};
+  a.M = B * HW;
+  a.N = N;
+  a.K = K;
+  a.conv = 1;
+  a.HW = HW;
+  a.W = W;
+  a.H = H;
+  a.cb1 = C / TC_BK;
+  a.cb2 = 0;
+  a.bias = bias;
+  a.rows_per_sample = HW;
+  a.out = out;
+  a.up = 1;
+  a.up_cout = Cout;
   a.kb_per_chunk = TC_SPLIT_KB;
   return launch_tc(mAh, mAl, mAh, mAl, mWh, mWl, a, s);
 }

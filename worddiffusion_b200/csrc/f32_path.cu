@@ -776,6 +776,11 @@ struct Param {
   float* perm = nullptr;
   float* ghi = nullptr;
   float* glo = nullptr;
+  // Upsample convs only (keys "output_blocks.*.conv.weight", "...upsamplers.0.conv.weight"): the sub-pixel fold [4 Cout][4 Cin]
+  // of f32tc_upconv (uf) and its TF32 split (uhi / ulo)
+  float* uf = nullptr;
+  float* uhi = nullptr;
+  float* ulo = nullptr;
 };
 
 struct Act {  // token-major activation
@@ -958,11 +963,43 @@ Act linear(wd_f32* e, const std::string& pfx, const Act& a, int B, bool bias, co
   return gemm(e, a, a2, B, w.p, N, bias ? P(e, pfx + ".bias").p : nullptr, nullptr, 0, residual, cs, nullptr, w.hi, w.lo);
 }
 
+static bool upconv_enabled() {  // env WD_F32_UPCONV (default on): Upsample + conv3x3 in sub-pixel form
+  static int v = -1;
+  if (v < 0) {
+    const char* x = getenv("WD_F32_UPCONV");
+    v = x ? (atoi(x) != 0) : 1;
+  }
+  return v != 0;
+}
+
 Act conv3x3(wd_f32* e, const std::string& pfx, const Act& a, const Act* a2, int B, const float* rowbias, int rb_ld,
             const float* residual, int stride, int up) {
   const Param& w = P(e, pfx + ".weight");
   if (!w.packed3x3) fail(WD_ERR_INVALID, "fp32 path: " + pfx + " is not a 3x3 convolution");
   if (w.shape[1] != a.C + (a2 ? a2->C : 0)) fail(WD_ERR_INVALID, "fp32 path: " + pfx + ": input channels do not match the weight");
+  // nearest 2x upsample + conv in sub-pixel form on the tensor cores (f32tc_upconv): no upsampled tensor, no patch matrix
+  if (up && stride == 1 && !a2 && !rowbias && !residual && w.uhi && w.ulo && a.p && upconv_enabled() && wd::f32tc_enabled() &&
+      wd::f32tc_upconv_ok(B, a.H, a.W, a.C, static_cast<int>(w.shape[0]))) {
+    const int Cout = static_cast<int>(w.shape[0]);
+    const size_t nA = static_cast<size_t>(B) * a.H * a.W * a.C;
+    float* a_hi = alloc(e, nA);
+    float* a_lo = alloc(e, nA);
+    Act o;
+    o.H = 2 * a.H;
+    o.W = 2 * a.W;
+    o.C = Cout;
+    o.p = alloc(e, static_cast<size_t>(B) * o.H * o.W * Cout);
+    if (!e->dry) {
+      cudaError_t ce = wd::f32tc_split(a.p, a_hi, a_lo, nA, e->s);
+      ++e->launches;
+      if (ce == cudaSuccess) {
+        ce = wd::f32tc_upconv(a_hi, a_lo, a.C, B, a.H, a.W, w.uhi, w.ulo, Cout, P(e, pfx + ".bias").p, o.p, e->s);
+        ++e->launches;
+      }
+      if (ce != cudaSuccess) fail(WD_ERR_CUDA, std::string("fp32 path: sub-pixel upsample conv: ") + cudaGetErrorString(ce));
+    }
+    return o;
+  }
   ConvSpec cs;
   cs.taps = 9;
   cs.stride = stride;
@@ -1537,6 +1574,9 @@ void wd_f32_destroy(wd_f32* e) {
     cudaFree(kv.second.perm);
     cudaFree(kv.second.ghi);
     cudaFree(kv.second.glo);
+    cudaFree(kv.second.uf);
+    cudaFree(kv.second.uhi);
+    cudaFree(kv.second.ulo);
   }
   cudaFree(e->pe);
   cudaFree(e->ctx);
@@ -1591,6 +1631,22 @@ int wd_f32_load_param(wd_f32* e, const char* name, const float* src, const int64
       const size_t l = strlen(suf);
       return nm.size() >= l && nm.compare(nm.size() - l, l, suf) == 0;
     };
+    // Upsample convs (unet.py:472-500; diffusers Upsample2D): sub-pixel weights for f32tc_upconv
+    if (wd::f32tc_enabled() && p.packed3x3 && ends_with(".conv.weight") &&
+        (nm.find("output_blocks.") != std::string::npos || nm.find("upsamplers.") != std::string::npos)) {
+      const int Co = static_cast<int>(shape[0]), Ci = static_cast<int>(shape[1]);
+      const size_t nf = static_cast<size_t>(16) * Co * Ci;
+      cudaFree(p.uf);
+      cudaFree(p.uhi);
+      cudaFree(p.ulo);
+      p.uf = p.uhi = p.ulo = nullptr;
+      if (cudaMalloc(&p.uf, nf * sizeof(float)) != cudaSuccess || cudaMalloc(&p.uhi, nf * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&p.ulo, nf * sizeof(float)) != cudaSuccess)
+        return wd_set_error(WD_ERR_CUDA, "wd_f32_load_param: cudaMalloc failed");
+      ce = wd::f32tc_upconv_fold(p.p, p.uf, Co, Ci, s);
+      if (ce == cudaSuccess) ce = wd::f32tc_split(p.uf, p.uhi, p.ulo, nf, s);
+      if (ce != cudaSuccess) return wd_set_error(WD_ERR_CUDA, cudaGetErrorString(ce));
+    }
     const bool gw = ends_with("ff.net.0.proj.weight") && ndim == 2, gb = ends_with("ff.net.0.proj.bias") && ndim == 1;
     if (wd::f32tc_enabled() && (gw || gb) && shape[0] % 320 == 0 && (n & 3) == 0) {
       cudaFree(p.perm);

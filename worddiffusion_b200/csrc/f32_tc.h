@@ -26,6 +26,13 @@ cudaError_t f32tc_gemm(const float* a_hi, const float* a_lo, const float* w_hi, 
 cudaError_t f32tc_geglu_permute(const float* w, float* dst, int N, int K, cudaStream_t s);
 cudaError_t f32tc_gemm_geglu(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
                              const float* bias_perm, float* out, float* out_lo, cudaStream_t s);
+// "nearest 2x upsample, then conv3x3" (unet.py:497-499) in sub-pixel form: four 2 x 2 convolutions of the H x W input, one per output
+// phase, as ONE implicit GEMM (9/4 fewer MACs, no upsampled tensor, no patch matrix).  w_hi / w_lo: the TF32 split of
+// f32tc_upconv_fold(packed [Cout][9][C]) = [4 Cout][4 C]; out: [B, 2H, 2W, Cout].
+cudaError_t f32tc_upconv_fold(const float* w_packed, float* dst, int Cout, int C, cudaStream_t s);
+bool f32tc_upconv_ok(int B, int H, int W, int C, int Cout);
+cudaError_t f32tc_upconv(const float* a_hi, const float* a_lo, int C, int B, int H, int W, const float* w_hi, const float* w_lo, int Cout,
+                         const float* bias, float* out, cudaStream_t s);
 // implicit 3x3 pad-1 stride-1 convolution over the channel concatenation of up to two split NHWC sources [B, H, W, C1 | C2]
 // (C % 32 == 0; 128 % W == 0 and HW % 128 == 0, or 128 % HW == 0); weights [N, 9 (C1 + C2)] split, k = tap (C1 + C2) + c
 bool f32tc_conv_ok(int B, int H, int W, int C1, int C2, int N);
