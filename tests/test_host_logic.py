@@ -399,3 +399,29 @@ def test_bucketed_allreduce_equals_whole_allreduce_gloo():
     for p in ps:
         p.join(60)
     assert res == {0: True, 1: True}
+
+
+def test_subpixel_form_of_upsample_conv():
+    """The identity behind GemmArgs::up_phase / f32tc_upconv (csrc/ops.cu upconv_phase_fold_kernel): conv3x3(nearest-2x(x)) ==
+    four 2x2 convolutions of x, one per output phase (a, b), whose weights are the sums of the 3x3 taps that read the same
+    input pixel (rows a = 0: {0}, {1, 2}; a = 1: {0, 1}, {2}; same for the columns).  fp64, reference ops only."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    B, C, Co, H, W = 2, 8, 6, 4, 16
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Co, C, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(Co, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)   # unet.py:497-499
+    taps = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for a in (0, 1):
+        for bb in (0, 1):
+            acc = torch.zeros(B, Co, H, W, dtype=torch.float64)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    wf = sum(w[:, :, ky, kx] for ky in taps[a][ty] for kx in taps[bb][tx])
+                    dy, dx = ty - 1 + a, tx - 1 + bb
+                    acc += torch.einsum("oc,bchw->bohw", wf, xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W])
+            out[:, :, a::2, bb::2] = acc + b[None, :, None, None]
+    assert float((out - ref).abs().max()) < 1e-12
